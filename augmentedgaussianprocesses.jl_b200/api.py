@@ -1,0 +1,802 @@
+"""Host-side mirror of the reference API for the AnalyticVI / AnalyticSVI path.
+
+Same names, argument meaning and error behaviour as theogf/AugmentedGaussianProcesses.jl
+(`SVGP`, `MOSVGP`, `AnalyticVI`, `AnalyticSVI`, `RobbinsMonro`, `train!` -> `train`, `predict_f`,
+`predict_y`, `proba_y`, `ELBO`), with every numerical operation delegated to the CUDA engine behind the
+C ABI of include/agp_b200.h.  No arithmetic of the hot path happens in Python and there is no CPU
+fallback.  Reference citations are paths under /root/reference/src.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+
+JITTER = {np.float64: 1e-4, np.float32: 1e-3, np.float16: 1e-2}  # functions/utils.jl:8-10
+
+
+# --------------------------------------------------------------------------------------------------
+# KernelFunctions.jl surface used by the reference call sites
+# --------------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class ScaleTransform:
+    s: float = 1.0
+
+
+@dataclass(frozen=True)
+class Kernel:
+    """variance * base(s*x, s*z);  `2.0 * SqExponentialKernel() @ ScaleTransform(10.0)` mirrors
+    `2.0 * SqExponentialKernel() ∘ ScaleTransform(10.0)` (test/likelihood/logistic.jl:3)."""
+
+    kind: int = L.KERNEL_SQEXP
+    scale: float = 1.0
+    variance: float = 1.0
+
+    def __rmul__(self, v):
+        return Kernel(self.kind, self.scale, self.variance * float(v))
+
+    __mul__ = __rmul__
+
+    def __matmul__(self, t: ScaleTransform):
+        return Kernel(self.kind, self.scale * float(t.s), self.variance)
+
+
+def SqExponentialKernel():
+    return Kernel(L.KERNEL_SQEXP)
+
+
+def Matern32Kernel():
+    return Kernel(L.KERNEL_MATERN32)
+
+
+def Matern52Kernel():
+    return Kernel(L.KERNEL_MATERN52)
+
+
+def transform(k: Kernel, t: ScaleTransform):
+    return k @ t
+
+
+def with_lengthscale(k: Kernel, lengthscale: float):
+    return k @ ScaleTransform(1.0 / float(lengthscale))
+
+
+# --------------------------------------------------------------------------------------------------
+# Likelihoods (AnalyticVI-capable ones of likelihood/*.jl)
+# --------------------------------------------------------------------------------------------------
+class AbstractLikelihood:
+    kind: int
+    p0 = 0.0
+    p1 = 0.0
+    n_latent = 1
+
+
+class GaussianLikelihood(AbstractLikelihood):
+    """likelihood/gaussian.jl:10-24"""
+
+    kind = L.LIK_GAUSSIAN
+
+    def __init__(self, sigma2: float = 1e-3, opt_noise=False):
+        if opt_noise:
+            raise NotImplementedError("opt_noise (noise optimisation) is outside the accelerated path")
+        self.sigma2 = float(sigma2)
+        self.p0 = self.sigma2
+
+    def __repr__(self):
+        return f"Gaussian likelihood (σ² = {self.sigma2})"
+
+
+class LogisticLikelihood(AbstractLikelihood):
+    """likelihood/logistic.jl:19 (BernoulliLikelihood(LogisticLink()))"""
+
+    kind = L.LIK_LOGISTIC
+
+    def __repr__(self):
+        return "Bernoulli Likelihood with Logistic Link"
+
+
+class StudentTLikelihood(AbstractLikelihood):
+    """likelihood/studentt.jl:23-35"""
+
+    kind = L.LIK_STUDENTT
+
+    def __init__(self, nu: float, sigma: float = 1.0):
+        if not nu > 0.5:
+            raise ValueError("ν should be greater than 0.5")
+        self.nu, self.sigma = float(nu), float(sigma)
+        self.p0, self.p1 = self.nu, self.sigma
+
+    def __repr__(self):
+        return f"Student-t likelihood (ν={self.nu}, σ={self.sigma})"
+
+
+class LogisticSoftMaxLikelihood(AbstractLikelihood):
+    """likelihood/logisticsoftmax.jl:23 + likelihood/multiclass.jl:1-24"""
+
+    kind = L.LIK_LOGISTICSOFTMAX
+
+    def __init__(self, x):
+        if isinstance(x, (int, np.integer)):
+            self.n_class = int(x)
+            self.class_mapping = None
+            self.ind_mapping = None
+        else:
+            self.class_mapping = list(x)
+            self.n_class = len(self.class_mapping)
+            self.ind_mapping = {v: i for i, v in enumerate(self.class_mapping)}
+
+    @property
+    def n_latent(self):
+        return self.n_class
+
+    def __repr__(self):
+        return f"Multiclass Likelihood ({self.n_class} classes, Logistic-SoftMax Link )"
+
+
+def create_mapping(l: LogisticSoftMaxLikelihood, y):
+    """likelihood/multiclass.jl:62-78"""
+    K = l.n_latent
+    if l.class_mapping is None:
+        seen = []
+        for v in y:
+            if v not in seen:
+                seen.append(v)
+        l.class_mapping = seen
+        ints = all(isinstance(v, (int, np.integer)) for v in seen)
+        if len(seen) <= K and ints and set(seen) <= set(range(1, K + 1)):
+            l.class_mapping = list(range(1, K + 1))
+        elif len(seen) > K:
+            raise ValueError(
+                f"The number of unique labels in the data : {seen} is not of the same size then the predefined class number ; {K}"
+            )
+    l.ind_mapping = {v: i for i, v in enumerate(l.class_mapping)}
+    return l.ind_mapping
+
+
+def _class_indices(l: LogisticSoftMaxLikelihood, y) -> np.ndarray:
+    """treat_labels! + create_one_hot (multiclass.jl:40-44, 81-94) as 0-based int32 class indices."""
+    y = y.tolist() if isinstance(y, np.ndarray) else list(y)
+    if l.ind_mapping is None:
+        create_mapping(l, y)
+    try:
+        return np.fromiter((l.ind_mapping[v] for v in y), dtype=np.int32, count=len(y))
+    except KeyError:
+        raise ValueError("Some labels of y are not part of the expect labels") from None
+
+
+def treat_labels(y, lik) -> np.ndarray:
+    """likelihood/classification.jl:29-45, regression.jl:10-15, multiclass.jl:40-44"""
+    if lik.kind == L.LIK_LOGISTIC:
+        y = np.asarray(y)
+        if not (np.issubdtype(y.dtype, np.number) or y.dtype == bool):
+            raise TypeError("For classification target(s) should be real valued (Bool, Integer or Float)")
+        labels = sorted(int(v) for v in np.unique(y))
+        if labels == [0, 1]:
+            return np.sign(y.astype(np.float64) - 0.5)
+        if labels == [-1, 1]:
+            return np.ascontiguousarray(y, dtype=np.float64)
+        raise ValueError("Labels of y should be binary {-1,1} or {0,1}")
+    if lik.kind == L.LIK_LOGISTICSOFTMAX:
+        return _class_indices(lik, y)
+    y = np.asarray(y)
+    if not np.issubdtype(y.dtype, np.number):
+        raise TypeError("For regression target(s) should be real valued")
+    return np.ascontiguousarray(y, dtype=np.float64)
+
+
+# --------------------------------------------------------------------------------------------------
+# Inference objects (inference/analyticVI.jl:1-52, inference/optimisers.jl:1-19)
+# --------------------------------------------------------------------------------------------------
+class RobbinsMonro:
+    def __init__(self, kappa: float = 0.51, tau: float = 1.0):
+        if not (0.5 < kappa <= 1):
+            raise ValueError("κ should be in the interval (0.5,1]")
+        if not tau > 0:
+            raise ValueError("τ should be positive")
+        self.kappa, self.tau = float(kappa), float(tau)
+
+
+class AnalyticVI:
+    """inference/analyticVI.jl:1-14.  `AnalyticVI()` = full batch, `AnalyticSVI(B)` = stochastic."""
+
+    def __init__(self, eps: float = 1e-5, *, _optimiser=None, _batchsize: int = 0, _stoch: bool = False):
+        self.eps = eps
+        self.n_iter = 0
+        self.stoch = _stoch
+        self.batchsize = int(_batchsize)
+        self.rho = 1.0
+        self.HyperParametersUpdated = True
+        self.optimiser = _optimiser
+
+    def __repr__(self):
+        return "Analytic" + (" Stochastic" if self.stoch else "") + " Variational Inference"
+
+
+def AnalyticSVI(nMinibatch: int, eps: float = 1e-5, optimiser: Optional[RobbinsMonro] = None):
+    """inference/analyticVI.jl:48-52"""
+    optimiser = optimiser if optimiser is not None else RobbinsMonro()
+    if not isinstance(optimiser, RobbinsMonro):
+        raise NotImplementedError("only the RobbinsMonro variational optimiser is accelerated")
+    return AnalyticVI(eps, _optimiser=optimiser, _batchsize=int(nMinibatch), _stoch=True)
+
+
+def is_stochastic(i: AnalyticVI) -> bool:
+    return i.stoch
+
+
+# --------------------------------------------------------------------------------------------------
+# engine handle
+# --------------------------------------------------------------------------------------------------
+class _Engine:
+    """Owns one agp_ctx + agp_model.  Created lazily (the batch capacity is only known at train time)."""
+
+    def __init__(self, desc_kwargs: dict, device: int, stream):
+        lib = L.load()
+        self.lib = lib
+        self.ctx = C.c_void_p()
+        rc = lib.agp_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(self.ctx))
+        if rc != L.AGP_OK:
+            raise L.AGPError(rc, "agp_ctx_create failed: no usable CUDA device (there is no CPU fallback)")
+        self._keep = []
+        d = L.ModelDesc()
+        for k, v in desc_kwargs.items():
+            if isinstance(v, np.ndarray):
+                self._keep.append(v)
+                if v.dtype == np.int32:
+                    v = v.ctypes.data_as(L.c_int32_p)
+                else:
+                    v = v.ctypes.data_as(L.c_double_p)
+            setattr(d, k, v)
+        self.desc = d
+        self.model = C.c_void_p()
+        rc = lib.agp_model_create(self.ctx, C.byref(d), C.byref(self.model))
+        try:
+            L.check(self.ctx, rc)
+        except Exception:
+            lib.agp_ctx_destroy(self.ctx)
+            self.ctx = None
+            raise
+        self.capacity = int(d.batch_capacity)
+
+    def ck(self, rc):
+        L.check(self.ctx, rc)
+
+    def close(self):
+        if getattr(self, "model", None):
+            self.lib.agp_model_destroy(self.model)
+            self.model = None
+        if getattr(self, "ctx", None):
+            self.lib.agp_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _x_args(X):
+    """(array kept alive, void*, dtype code, layout code, n, D) for a host matrix, without copying when possible."""
+    X = np.asarray(X)
+    if X.ndim == 1:
+        X = X[:, None]
+    if X.dtype not in (np.float64, np.float32):
+        X = X.astype(np.float64)
+    if X.flags.c_contiguous:
+        layout = L.LAYOUT_ROWMAJOR
+    elif X.flags.f_contiguous:
+        layout = L.LAYOUT_COLMAJOR
+    else:
+        X = np.ascontiguousarray(X)
+        layout = L.LAYOUT_ROWMAJOR
+    dt = L.DTYPE_F64 if X.dtype == np.float64 else L.DTYPE_F32
+    return X, X.ctypes.data_as(C.c_void_p), dt, layout, X.shape[0], X.shape[1]
+
+
+# --------------------------------------------------------------------------------------------------
+# Models
+# --------------------------------------------------------------------------------------------------
+class AbstractGPModel:
+    model_kind = L.MODEL_SVGP
+
+    def _common_init(self, inference, verbose, atfrequency, optimiser, Zoptimiser, T, precision, device, stream, shard):
+        if not isinstance(inference, AnalyticVI):
+            raise TypeError(
+                "The inference object should be of type `VariationalInference` : either `AnalyticVI` or `NumericalVI`"
+                " (only AnalyticVI / AnalyticSVI are accelerated)"
+            )
+        if optimiser not in (None, False) or Zoptimiser not in (None, False):
+            raise NotImplementedError(
+                "kernel / inducing-point hyper-parameter optimisation (Zygote path, hyperparameter/autotuning.jl) "
+                "is outside the accelerated path: pass optimiser=False, Zoptimiser=False"
+            )
+        if T not in JITTER:
+            raise TypeError("T must be np.float64 / np.float32 / np.float16")
+        if precision not in L.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(L.PRECISIONS)}")
+        self.inference = inference
+        self.verbose = verbose
+        self.atfrequency = atfrequency
+        self.trained = False
+        self.T = T
+        self.jitter = JITTER[T]
+        self.precision = precision
+        self.device = device
+        self.stream = stream
+        self.rank, self.world = shard if shard is not None else (0, 1)
+        self._eng: Optional[_Engine] = None
+        self._data_key = None
+        self._n = 0
+
+    # ---- lazily (re)create the engine with enough batch capacity, carrying the posterior over
+    def _engine(self, capacity: int) -> _Engine:
+        if self._eng is not None and capacity <= self._eng.capacity:
+            return self._eng
+        old = self._eng
+        saved = None
+        if old is not None:
+            saved = [self._get_posterior_raw(q) for q in range(self.n_latent_local)]
+            cnt = self.counters()
+            old.close()
+        cap = int(capacity)
+        if self.precision == "tf32x3":
+            cap = (cap + 127) // 128 * 128
+        self._eng = _Engine(self._desc(cap), self.device, self.stream)
+        self._data_key = None
+        if saved is not None:
+            for q, (mu, S, e1, e2) in enumerate(saved):
+                self._eng.ck(self._eng.lib.agp_set_posterior(self._eng.model, q, L.dptr(e1), L.dptr(e2)))
+            self._eng.ck(self._eng.lib.agp_set_counters(self._eng.model, cnt[0], cnt[1]))
+        return self._eng
+
+    def _latent_range(self):
+        Q = self.n_latent
+        if Q % self.world:
+            raise ValueError("the number of latent GPs must be divisible by the number of ranks")
+        per = Q // self.world
+        return self.rank * per, per
+
+    @property
+    def n_latent_local(self):
+        return self._latent_range()[1]
+
+    def _get_posterior_raw(self, q):
+        e = self._eng
+        m = self.m
+        mu, e1 = np.empty(m), np.empty(m)
+        S, e2 = np.empty((m, m)), np.empty((m, m))
+        e.ck(e.lib.agp_get_posterior(e.model, q, L.dptr(mu), L.dptr(S), L.dptr(e1), L.dptr(e2)))
+        return mu, S, e1, e2
+
+    # ---- accessors mirroring mean(gp), cov(gp), nat1(gp), nat2(gp) (gpblocks/latentgp.jl:163-168)
+    def posterior(self, q: int = 0):
+        """(mu, Sigma, eta1, eta2) of the q-th OWNED latent."""
+        if self._eng is None:
+            m = self.m
+            return np.zeros(m), np.eye(m), np.zeros(m), -0.5 * np.eye(m)  # posterior.jl:29-37
+        return self._get_posterior_raw(q)
+
+    def counters(self):
+        e = self._eng
+        t, c = C.c_int64(), C.c_int64()
+        e.ck(e.lib.agp_get_counters(e.model, C.byref(t), C.byref(c)))
+        return t.value, c.value
+
+    def launch_count(self) -> int:
+        return int(self._eng.lib.agp_launch_count(self._eng.model)) if self._eng else 0
+
+
+class SVGP(AbstractGPModel):
+    """models/SVGP.jl:22-80.  `SVGP(kernel, likelihood, inference, Z; optimiser=false, Zoptimiser=false)`.
+
+    precision: "f64" (fp64 SIMT, exact mode), "f32" (fp32 SIMT) or "tf32x3" (tcgen05 tensor cores).
+    shard=(rank, world): own n_latent/world latents (LogisticSoftMax classes) on this process.
+    """
+
+    model_kind = L.MODEL_SVGP
+
+    def __init__(self, kernel: Kernel, likelihood: AbstractLikelihood, inference: AnalyticVI, Z, *, verbose: int = 0,
+                 optimiser=False, atfrequency: int = 1, mean=None, Zoptimiser=False, T=np.float64, precision: str = "f32",
+                 device: int = 0, stream=None, shard=None):
+        if not isinstance(likelihood, AbstractLikelihood):
+            raise TypeError(f"The {likelihood} is not compatible or implemented with the {inference}")
+        self._common_init(inference, verbose, atfrequency, optimiser, Zoptimiser, T, precision, device, stream, shard)
+        self.likelihood = likelihood
+        self.likelihoods = [likelihood]
+        self.kernel = kernel
+        Z = np.ascontiguousarray(np.asarray(Z, dtype=np.float64))
+        if Z.ndim == 1:
+            Z = Z[:, None]
+        self.Z = Z
+        self.m, self.D = Z.shape
+        self.n_latent = likelihood.n_latent
+        self.kernels = [kernel] * self.n_latent
+        self.Zs = [Z] * self.n_latent
+        if mean is None:
+            self.mu0 = None
+        elif np.isscalar(mean):
+            self.mu0 = np.full(self.m, float(mean))  # ConstantMean (mean/constantmean.jl)
+        else:
+            raise NotImplementedError("only ZeroMean / ConstantMean priors cross the boundary (mu0 evaluated at Z)")
+        self.A = None
+
+    def _desc(self, capacity: int) -> dict:
+        return _make_desc(self, capacity)
+
+    def __repr__(self):
+        return f"Sparse Variational Gaussian Process with a {self.likelihood} infered by {self.inference} "
+
+
+class MOSVGP(AbstractGPModel):
+    """models/MOSVGP.jl:22-115 with single-latent task likelihoods; A is T x Q (rows normalised like
+    MOSVGP.jl:100-103).  `Aoptimiser` must be False (update_A! is not accelerated yet)."""
+
+    model_kind = L.MODEL_MOSVGP
+
+    def __init__(self, kernel, likelihoods: Sequence[AbstractLikelihood], inference: AnalyticVI, Zs: Sequence, *, A=None,
+                 verbose: int = 0, atfrequency: int = 1, mean=None, optimiser=False, Aoptimiser=False, Zoptimiser=False,
+                 T=np.float64, precision: str = "f32", device: int = 0, stream=None, shard=None, rng=None):
+        self._common_init(inference, verbose, atfrequency, optimiser, Zoptimiser, T, precision, device, stream, shard)
+        if Aoptimiser not in (None, False):
+            raise NotImplementedError("update_A! (single_and_multi_output_utils.jl:87-118) is not accelerated: pass Aoptimiser=False")
+        if mean is not None:
+            raise NotImplementedError("MOSVGP with a non-zero prior mean is not supported")
+        self.likelihoods = list(likelihoods)
+        for l in self.likelihoods:
+            if not isinstance(l, AbstractLikelihood) or l.n_latent != 1:
+                raise TypeError(f"One (or more) of the likelihoods {likelihoods} are not compatible or implemented with the {inference}")
+        self.likelihood = self.likelihoods
+        kernels = [kernel] if isinstance(kernel, Kernel) else list(kernel)
+        self.Zs = [np.ascontiguousarray(np.asarray(z, dtype=np.float64)) for z in Zs]
+        self.n_latent = len(self.Zs)
+        self.n_task = len(self.likelihoods)
+        if not isinstance(kernel, Kernel) and len(kernels) != self.n_task:
+            raise ValueError("Number of kernels should be equal to the number of tasks")
+        self.kernels = [kernels[i % len(kernels)] for i in range(self.n_latent)]
+        self.m, self.D = self.Zs[0].shape
+        if any(z.shape != (self.m, self.D) for z in self.Zs):
+            raise ValueError("all latent GPs must share the same number of inducing points and input dimension")
+        if A is None:
+            rng = rng or np.random.default_rng()
+            A = rng.standard_normal((self.n_task, self.n_latent))
+            A /= np.linalg.norm(A, axis=1, keepdims=True)
+        self.A = np.ascontiguousarray(np.asarray(A, dtype=np.float64))
+        if self.A.shape != (self.n_task, self.n_latent):
+            raise ValueError("A must be (n_task, n_latent)")
+        self.mu0 = None
+
+    def _desc(self, capacity: int) -> dict:
+        return _make_desc(self, capacity)
+
+    def __repr__(self):
+        return f"Multioutput Sparse Variational Gaussian Process with the likelihoods {self.likelihoods} infered by {self.inference} "
+
+
+def VGP(*a, **k):
+    """models/VGP.jl -- the full (non-sparse) variational GP is O(n^3) and outside the accelerated hot path."""
+    raise NotImplementedError("VGP (full variational GP) is out of scope of the B200 engine; use SVGP")
+
+
+def _make_desc(model, capacity: int) -> dict:
+    q0, ql = model._latent_range()
+    inf = model.inference
+    opt = inf.optimiser if inf.stoch else None
+    liks = model.likelihoods
+    Z = np.ascontiguousarray(np.stack(model.Zs[q0 : q0 + ql]))
+    d = dict(
+        model_kind=model.model_kind,
+        n_latent_global=model.n_latent,
+        latent_begin=q0,
+        n_latent_local=ql,
+        m=model.m,
+        D=model.D,
+        batch_capacity=int(capacity),
+        precision=L.PRECISIONS[model.precision],
+        stochastic=1 if inf.stoch else 0,
+        rm_kappa=opt.kappa if opt else 0.51,
+        rm_tau=opt.tau if opt else 1.0,
+        jitter=model.jitter,
+        n_task=len(liks),
+        lik_kind=np.array([l.kind for l in liks], dtype=np.int32),
+        lik_p0=np.array([l.p0 for l in liks], dtype=np.float64),
+        lik_p1=np.array([l.p1 for l in liks], dtype=np.float64),
+        kernel_kind=np.array([k.kind for k in model.kernels[q0 : q0 + ql]], dtype=np.int32),
+        kernel_scale=np.array([k.scale for k in model.kernels[q0 : q0 + ql]], dtype=np.float64),
+        kernel_variance=np.array([k.variance for k in model.kernels[q0 : q0 + ql]], dtype=np.float64),
+        Z=Z,
+    )
+    if model.A is not None:
+        d["A"] = model.A
+    if model.mu0 is not None:
+        d["mu0"] = np.ascontiguousarray(np.tile(model.mu0, (ql, 1)))
+    return d
+
+
+# --------------------------------------------------------------------------------------------------
+# state (training/states.jl): the device holds it; this object exposes it
+# --------------------------------------------------------------------------------------------------
+class State:
+    """Handle on the device-resident training state of the last step (local_vars, opt_state,
+    kernel_matrices of the reference's `state` NamedTuple)."""
+
+    def __init__(self, model):
+        self.model = model
+        self.B = 0
+
+    def local(self, name: str, row: int = 0) -> np.ndarray:
+        e = self.model._eng
+        out = np.empty(self.B)
+        e.ck(e.lib.agp_get_local(e.model, name.encode(), row, L.dptr(out), self.B))
+        return out
+
+    def kernel_matrices(self, q: int = 0):
+        e = self.model._eng
+        m = self.model.m
+        Knm, kappa = np.empty((self.B, m)), np.empty((self.B, m))
+        e.ck(e.lib.agp_get_kernel_matrices(e.model, q, L.dptr(Knm), L.dptr(kappa), self.B))
+        return dict(Knm=Knm, kappa=kappa, Ktilde=self.local("Ktilde", q))
+
+    @property
+    def opt_state(self):
+        t, _ = self.model.counters()
+        return dict(state_eta1=t, state_eta2=t)
+
+
+# --------------------------------------------------------------------------------------------------
+# train!  (training/training.jl:13-111)
+# --------------------------------------------------------------------------------------------------
+def _wrap_y(model, y):
+    if isinstance(model, MOSVGP):
+        if len(y) != model.n_task:
+            raise ValueError("one target vector per task is required")
+        return [treat_labels(yt, l) for yt, l in zip(y, model.likelihoods)]
+    return [treat_labels(y, model.likelihood)]
+
+
+def _upload(model, eng, X, ys, key):
+    if model._data_key == key:
+        return
+    Xk, xp, dt, layout, n, D = _x_args(X)
+    if D != model.D:
+        raise ValueError("input dimension of X does not match the inducing points")
+    for yt in ys:
+        if len(yt) != n:
+            raise ValueError(f"There is not the same number of samples in X ({n}) and y ({len(yt)})")
+    is_class = ys[0].dtype == np.int32
+    arr = (C.c_void_p * len(ys))(*[yt.ctypes.data_as(C.c_void_p) for yt in ys])
+    eng.ck(eng.lib.agp_data_upload(eng.model, xp, dt, layout, n, arr, L.Y_CLASS if is_class else L.Y_REAL))
+    model._data_key = key
+    model._n = n
+
+
+def train(model: AbstractGPModel, X, y, iterations: int = 100, *, callback=None, convergence=None, state: Optional[State] = None,
+          obsdim: int = 1, minibatches: Optional[Sequence[np.ndarray]] = None, rng=None, check_every: int = 1):
+    """`train!(model, X, y, iterations; callback, state)`.
+
+    minibatches: optional list of 0-based index arrays, one per iteration (the reference draws them with
+    StatsBase.sample on Julia's global RNG, training.jl:51-53, which cannot be reproduced; parity runs
+    inject the lists).  check_every: read the device status back every k iterations (1 = after every
+    step, like the reference's immediate error).
+    """
+    if iterations <= 0:
+        raise ValueError("Number of iterations should be positive")
+    X = np.asarray(X)
+    if X.ndim == 2 and obsdim == 2:
+        X = X.T
+    ys = _wrap_y(model, y)
+    n = X.shape[0]
+    inf = model.inference
+    if inf.stoch:
+        if not (0 < inf.batchsize <= n):
+            raise ValueError(
+                f"The size of mini-batch {inf.batchsize} is incorrect (negative or bigger than number of samples), "
+                "please set `batchsize` correctly in the inference object"
+            )
+        inf.rho = n / inf.batchsize
+    else:
+        inf.batchsize = n
+    B = inf.batchsize
+    eng = model._engine(B)
+    _upload(model, eng, X, ys, (id(X), tuple(id(v) for v in ys), X.shape))
+    lib = eng.lib
+    if state is None:
+        inf.HyperParametersUpdated = True
+        eng.ck(lib.agp_state_reset(eng.model))
+        state = State(model)
+    if inf.HyperParametersUpdated:
+        eng.ck(lib.agp_refresh_K(eng.model))  # compute_K, once per train! call (training.jl:41-43, Q3)
+        inf.HyperParametersUpdated = False
+    state.B = B
+    rng = rng or np.random.default_rng()
+    full = np.arange(n, dtype=np.int64) if not inf.stoch else None
+    for it in range(iterations):
+        if inf.stoch:
+            idx = minibatches[it] if minibatches is not None else rng.choice(n, B, replace=False)
+            idx = np.ascontiguousarray(idx, dtype=np.int64)
+            if idx.shape != (B,):
+                raise ValueError("minibatch index list has the wrong length")
+        else:
+            idx = full
+        ip = idx.ctypes.data_as(L.c_int64_p)
+        if model.world > 1:
+            _sharded_step(model, eng, ip, B, inf.rho)
+            if (it + 1) % check_every == 0 or it == iterations - 1:
+                eng.ck(lib.agp_sync(eng.model))
+        elif (it + 1) % check_every == 0 or it == iterations - 1:
+            eng.ck(lib.agp_step(eng.model, ip, B, 0, inf.rho))
+        else:
+            eng.ck(lib.agp_step_async(eng.model, ip, B, 0, inf.rho))
+        model.trained = True
+        if callback is not None:
+            callback(model, state, inf.n_iter)
+        inf.n_iter += 1
+    return model, state
+
+
+train_ = train  # `train!`
+
+
+def _moment_views(model, eng):
+    """torch views (zero-copy) on the [Q][ldB] device moment arrays, for the NCCL all-gather."""
+    import torch
+
+    if getattr(model, "_mviews", None) is not None and model._mviews[0] is eng:
+        return model._mviews[1]
+    views = []
+    for which in (0, 1):
+        ld = C.c_int64()
+        p = eng.lib.agp_moments_devptr(eng.model, which, C.byref(ld))
+
+        class _Arr:
+            __cuda_array_interface__ = dict(shape=(model.n_latent * ld.value,), typestr="<f8", data=(int(p), False), version=2)
+
+        views.append(torch.as_tensor(_Arr(), device=f"cuda:{model.device}"))
+    model._mviews = (eng, (views, ld.value))
+    return model._mviews[1]
+
+
+def _allgather_moments(model, eng):
+    import torch.distributed as dist
+
+    (mean_v, var_v), ld = _moment_views(model, eng)
+    q0, ql = model._latent_range()
+    for v in (mean_v, var_v):
+        dist.all_gather_into_tensor(v, v[q0 * ld : (q0 + ql) * ld])
+
+
+def _sharded_step(model, eng, ip, B, rho):
+    """one-latent(-group)-per-rank step: moments -> NCCL all-gather of (mean_f, var_f) rows -> update."""
+    eng.ck(eng.lib.agp_step_moments_async(eng.model, ip, B, 0))
+    _allgather_moments(model, eng)
+    eng.ck(eng.lib.agp_step_update_async(eng.model, rho))
+
+
+# --------------------------------------------------------------------------------------------------
+# ELBO / objective (inference/analyticVI.jl:255-297)
+# --------------------------------------------------------------------------------------------------
+def ELBO(model: AbstractGPModel, state: Optional[State] = None, y=None) -> float:
+    """ELBO(model, state, y) on the last minibatch (y is implied by the state: the labels of that batch)."""
+    eng = model._eng
+    if eng is None:
+        raise RuntimeError("the model has not been trained yet")
+    out = np.zeros(3)
+    rho = model.inference.rho
+    if model.world > 1:
+        import torch
+        import torch.distributed as dist
+
+        eng.ck(eng.lib.agp_elbo_moments_async(eng.model))
+        _allgather_moments(model, eng)
+        eng.ck(eng.lib.agp_elbo(eng.model, rho, L.dptr(out)))
+        kl = torch.tensor([out[1]], dtype=torch.float64, device=f"cuda:{model.device}")
+        dist.all_reduce(kl)  # the single scalar all-reduce of the north star
+        out[1] = float(kl.item())
+    else:
+        eng.ck(eng.lib.agp_elbo(eng.model, rho, L.dptr(out)))
+    return float(out[0] - out[1] - out[2])
+
+
+objective = ELBO
+
+
+# --------------------------------------------------------------------------------------------------
+# predictions (training/predictions.jl)
+# --------------------------------------------------------------------------------------------------
+_GH = None
+
+
+def _pred_nodes():
+    """predictions.jl:4 : 100-point Gauss-Hermite nodes * sqrt2, weights / sqrt(pi)"""
+    global _GH
+    if _GH is None:
+        x, w = np.polynomial.hermite.hermgauss(100)
+        _GH = (np.ascontiguousarray(x * math.sqrt(2.0)), np.ascontiguousarray(w / math.sqrt(math.pi)))
+    return _GH
+
+
+def _predict_f(model, X_test, cov: bool):
+    """(Q_local, N*) latent moments of the owned latents, then multi-output mixing on the host."""
+    if model.world > 1:
+        raise NotImplementedError("prediction on a latent-sharded model: gather the posterior on one rank first")
+    eng = model._engine(max(model.inference.batchsize, 1) if model._eng is None else 1)
+    Xk, xp, dt, layout, nt, D = _x_args(X_test)
+    if D != model.D:
+        raise ValueError("input dimension of X_test does not match the inducing points")
+    ql = model.n_latent_local
+    mu = np.empty((ql, nt))
+    var = np.empty((ql, nt)) if cov else None
+    eng.ck(eng.lib.agp_predict_f(eng.model, xp, dt, layout, nt, 1 if cov else 0, L.dptr(mu), L.dptr(var) if cov else None))
+    if isinstance(model, MOSVGP):  # predictions.jl:63-84
+        mu_t = model.A @ mu
+        return (mu_t, (model.A**2) @ var) if cov else (mu_t, None)
+    return mu, var
+
+
+def predict_f(model, X_test, state=None, *, cov: bool = False, diag: bool = True, obsdim: int = 1):
+    """predictions.jl:136-163"""
+    if not diag:
+        raise NotImplementedError("full predictive covariance (diag=false) is not accelerated")
+    X_test = np.asarray(X_test)
+    if X_test.ndim == 2 and obsdim == 2:
+        X_test = X_test.T
+    mu, var = _predict_f(model, X_test, cov)
+    if mu.shape[0] == 1:
+        return (mu[0], var[0]) if cov else mu[0]
+    return (tuple(mu), tuple(var)) if cov else tuple(mu)
+
+
+def _predict_y_lik(lik, mu):
+    if lik.kind == L.LIK_LOGISTIC:  # classification.jl:47
+        return mu[0] > 0
+    if lik.kind == L.LIK_LOGISTICSOFTMAX:  # predictions.jl:196-198
+        am = np.argmax(mu, axis=0)
+        return np.array([lik.class_mapping[i] for i in am])
+    return mu[0]  # regression.jl:17
+
+
+def predict_y(model, X_test, state=None, *, obsdim: int = 1):
+    """predictions.jl:178-198"""
+    X_test = np.asarray(X_test)
+    if X_test.ndim == 2 and obsdim == 2:
+        X_test = X_test.T
+    mu, _ = _predict_f(model, X_test, False)
+    if isinstance(model, MOSVGP):
+        return [_predict_y_lik(l, mu[t : t + 1]) for t, l in enumerate(model.likelihoods)]
+    return _predict_y_lik(model.likelihood, mu)
+
+
+def _compute_proba(model, lik, mu, var):
+    if lik.kind == L.LIK_LOGISTIC:  # classification.jl:14-26, Gauss-Hermite on the device
+        eng = model._eng
+        nodes, weights = _pred_nodes()
+        m_ = np.ascontiguousarray(mu[0])
+        v_ = np.ascontiguousarray(var[0])
+        p, pv = np.empty_like(m_), np.empty_like(m_)
+        eng.ck(eng.lib.agp_proba_logistic(eng.model, L.dptr(m_), L.dptr(v_), len(m_), L.dptr(nodes), L.dptr(weights),
+                                          len(nodes), L.dptr(p), L.dptr(pv)))
+        return p, pv
+    if lik.kind == L.LIK_GAUSSIAN:  # gaussian.jl:41-45
+        return mu[0], var[0] + lik.sigma2
+    if lik.kind == L.LIK_STUDENTT:  # studentt.jl:57-61
+        return mu[0], np.maximum(var[0], 0.0) + lik.nu * lik.sigma**2 / (2.0 * (lik.nu / 2.0 - 1.0))
+    if lik.kind == L.LIK_LOGISTICSOFTMAX:  # multiclass.jl:96-117, logisticsoftmax.jl:28-30
+        s = 1.0 / (1.0 + np.exp(-mu))
+        return s / np.sum(s, axis=0, keepdims=True)
+    raise ValueError("unknown likelihood")
+
+
+def proba_y(model, X_test, state=None, *, obsdim: int = 1):
+    """predictions.jl:231-246"""
+    X_test = np.asarray(X_test)
+    if X_test.ndim == 2 and obsdim == 2:
+        X_test = X_test.T
+    mu, var = _predict_f(model, X_test, True)
+    if isinstance(model, MOSVGP):
+        return [_compute_proba(model, l, mu[t : t + 1], var[t : t + 1]) for t, l in enumerate(model.likelihoods)]
+    return _compute_proba(model, model.likelihood, mu, var)

@@ -1,0 +1,529 @@
+// Elementwise / reduction / small-matrix kernels of the CAVI step (everything that is not a big GEMM).
+// Reference formulas are cited per kernel (paths relative to /root/reference/src).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "agp_gemm_simt.cuh"
+
+namespace agp {
+
+// sticky device status bits (read back by agp_sync)
+enum : int { ST_KTILDE = 1, ST_NOT_POSDEF = 2 };
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// data preparation
+// ------------------------------------------------------------------------------------------------
+// convert a chunk of host-layout X (staged on device) to row-major T with leading dimension ldx
+// and compute the squared row norms used by the GEMM-form distance.
+template <typename TS, typename T>
+__global__ void convert_rows_kernel(const TS* __restrict__ src, int layout, int64_t src_ld /*n for colmajor, D for rowmajor*/,
+                                    int64_t rows, int D, T* __restrict__ dst, int64_t ldx, T* __restrict__ xx) {
+  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  double s = 0.0;
+  for (int d = 0; d < D; ++d) {
+    double v = layout == 0 ? (double)src[r + src_ld * d] : (double)src[r * src_ld + d];
+    dst[r * ldx + d] = (T)v;
+    T q = (T)v;
+    s += (double)q * (double)q;
+  }
+  if (xx) xx[r] = (T)s;
+}
+
+template <typename TS>
+__global__ void convert_vec_kernel(const TS* __restrict__ src, double* __restrict__ dst, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (double)src[i];
+}
+
+__global__ void idx_rebase_kernel(const int64_t* __restrict__ src, int64_t* __restrict__ dst, int64_t n, int base) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i] - base;
+}
+
+// copy the index list of the current cursor position into the fixed per-step buffer (so that every
+// later kernel of the step - and a captured CUDA graph - reads one fixed address)
+__global__ void idx_select_kernel(const int64_t* __restrict__ pool, int64_t n_lists, int B,
+                                  const int64_t* __restrict__ counters /*[0]=t,[1]=cursor*/, int64_t* __restrict__ dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  int64_t cur = counters[1] % n_lists;
+  dst[i] = pool[cur * B + i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-row statistics  (gpblocks/latentgp.jl:212-213 K̃; :179 mean_f; :189 var_f; functions/utils.jl:55-57)
+//   Ktilde = kdiag + jitter - rowsum(kappa .* Knm);  mean_f = kappa * mu;  var_f = rowsum((kappa Sigma) .* kappa) + Ktilde
+// one warp per minibatch row; sums accumulate in fp64 whatever T is.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void rowstats_kernel(const T* __restrict__ Knm, const T* __restrict__ kappa, const T* __restrict__ KS,
+                                const double* __restrict__ mu, int B, int m, int64_t ld, double kdiag_jit,
+                                double* __restrict__ Ktilde, double* __restrict__ mean_f, double* __restrict__ var_f,
+                                int* __restrict__ status, int compute_ktilde) {
+  using V = typename VecOf<T>::type;
+  constexpr int W = VecOf<T>::W;
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= B) return;
+  const T* kn = Knm + (int64_t)warp * ld;
+  const T* kp = kappa + (int64_t)warp * ld;
+  const T* ks = KS + (int64_t)warp * ld;
+  double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int m4 = (m + 3) & ~3;  // padding columns are zero
+  for (int j = lane * W; j < m4; j += 32 * W) {
+    V a = *reinterpret_cast<const V*>(kp + j);
+    V c = *reinterpret_cast<const V*>(ks + j);
+    V b;
+    if (compute_ktilde) b = *reinterpret_cast<const V*>(kn + j); else b = a;
+    double av[W], bv[W], cv[W];
+    av[0] = a.x; av[1] = a.y; bv[0] = b.x; bv[1] = b.y; cv[0] = c.x; cv[1] = c.y;
+    if constexpr (W == 4) { av[2] = a.z; av[3] = a.w; bv[2] = b.z; bv[3] = b.w; cv[2] = c.z; cv[3] = c.w; }
+#pragma unroll
+    for (int q = 0; q < W; ++q) {
+      double muj = (j + q < m) ? mu[j + q] : 0.0;
+      s1 += av[q] * bv[q];
+      s2 += av[q] * muj;
+      s3 += av[q] * cv[q];
+    }
+  }
+  s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
+  if (lane == 0) {
+    double kt;
+    if (compute_ktilde) {
+      kt = kdiag_jit - s1;
+      Ktilde[warp] = kt;
+      if (!(kt > 0.0)) atomicOr(status, ST_KTILDE);  // latentgp.jl:213
+    } else {
+      kt = Ktilde[warp];
+    }
+    mean_f[warp] = s2;
+    var_f[warp] = s3 + kt;
+  }
+}
+
+// out[j] += sum_b kappa[b][j] * g[b]   (transpose(kappa) * grad_mu of analyticVI.jl:168; rho applied later)
+template <typename T>
+__global__ void gemv_t_kernel(const T* __restrict__ kappa, int64_t ld, const double* __restrict__ g, int B, int m,
+                              double* __restrict__ out) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  int b0 = blockIdx.y * 64, b1 = min(B, b0 + 64);
+  if (j >= m) return;
+  double s = 0.0;
+  for (int b = b0; b < b1; ++b) s += (double)kappa[(int64_t)b * ld + j] * g[b];
+  atomicAdd(out + j, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// special functions
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double digamma_pos(double x) {  // x > 0
+  double r = 0.0;
+  while (x < 10.0) { r -= 1.0 / x; x += 1.0; }
+  double f = 1.0 / (x * x);
+  double t = f * (-1.0 / 12.0 + f * (1.0 / 120.0 + f * (-1.0 / 252.0 + f * (1.0 / 240.0 + f * (-1.0 / 132.0 + f * (691.0 / 32760.0 + f * (-1.0 / 12.0)))))));
+  return r + log(x) - 0.5 / x + t;
+}
+__device__ __forceinline__ double logistic_d(double x) { return 1.0 / (1.0 + exp(-x)); }
+// functions/utils.jl:84-86
+__device__ __forceinline__ double safe_expcosh_d(double mu, double c) {
+  double v = exp(mu) / cosh(c);
+  return isfinite(v) ? v : 2.0 * logistic_d(2.0 * fmax(mu, c));
+}
+// functions/utils.jl:89-91
+__device__ __forceinline__ double logcosh_d(double c) { return log(exp(-2.0 * c) + 1.0) + c - 0.6931471805599453; }
+__device__ __forceinline__ double xlogx_d(double x) { return x > 0.0 ? x * log(x) : 0.0; }
+
+// ------------------------------------------------------------------------------------------------
+// likelihood local updates + expectation gradients (one thread per minibatch sample, fp64)
+// ------------------------------------------------------------------------------------------------
+struct LikParams {
+  int model_kind, n_task, Q, B;
+  int64_t ldB;
+  int latent_begin, n_latent_local;
+  const int* lik_kind; const double* p0; const double* p1;  // [T] device
+  const double* A;                                           // [T*Q] device (MOSVGP)
+  const double* mean_f; const double* var_f;                 // [Q][ldB] latent moments (all latents)
+  // labels: resident data + gather list, or (idx == nullptr) already in yb / ycls
+  const double* y_all; int64_t n; const int* ycls_all; const int64_t* idx;
+  double* yb; int* ycls;                                     // [T][ldB], [ldB]  minibatch labels (kept for the ELBO)
+  double* c; double* theta; double* gamma; double* alpha;    // local variables [R][ldB] (R = T or K), alpha [ldB]
+  double* tmu; double* tvar;                                 // [T][ldB] task moments (MOSVGP scratch / ELBO)
+  double* gm; double* gs;                                    // [T][ldB] per-task gradients (MOSVGP scratch)
+  double* gmu; double* gS;                                   // [n_latent_local][ldB] outputs
+  int update;                                                // 1: local_updates!, 0: only (re)compute task moments
+};
+
+// one single-latent likelihood: c, theta and the two expectation gradients
+__device__ __forceinline__ void lik_single(int kind, double p0, double p1, double y, double mu, double var, double& c,
+                                           double& th, double& gm, double& gs) {
+  if (kind == 1) {  // likelihood/logistic.jl:39-51, 64-69
+    c = sqrt(mu * mu + var);
+    th = tanh(0.5 * c) / (2.0 * c);
+    gm = 0.5 * y;
+  } else if (kind == 2) {  // likelihood/studentt.jl:68-82, 96-99
+    double d = mu - y;
+    c = 0.5 * (d * d + var + p1 * p1 * p0);
+    th = 0.5 * (p0 + 1.0) / c;
+    gm = th * y;
+  } else {  // likelihood/gaussian.jl:56-80
+    c = 0.0;
+    th = 1.0 / p0;
+    gm = y / p0;
+  }
+  gs = 0.5 * th;
+}
+
+__global__ void lik_update_kernel(const LikParams p) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= p.B) return;
+  const int64_t ld = p.ldB;
+  const int64_t src = p.idx ? p.idx[b] : (int64_t)b;
+  if (p.model_kind == 0 && p.lik_kind[0] == 3) {
+    // ---- LogisticSoftMax (likelihood/logisticsoftmax.jl:55-79, 98-103) ----
+    const int K = p.Q;
+    int cls = p.idx ? p.ycls_all[src] : p.ycls[b];
+    if (p.idx) p.ycls[b] = cls;
+    if (!p.update) return;
+    double alpha = p.alpha[b];
+    const double beta = (double)K;  // beta stays = K forever (Q6)
+    for (int k = 0; k < K; ++k) {
+      double mu = p.mean_f[k * ld + b], var = p.var_f[k * ld + b];
+      p.c[k * ld + b] = sqrt(mu * mu + var);
+    }
+    for (int pass = 0; pass < 2; ++pass) {
+      double e = exp(digamma_pos(alpha));
+      double s = 0.0;
+      for (int k = 0; k < K; ++k) {
+        double mu = p.mean_f[k * ld + b], c = p.c[k * ld + b];
+        double g = e * safe_expcosh_d(-0.5 * mu, 0.5 * c) / (2.0 * beta);
+        p.gamma[k * ld + b] = g;
+        s += g;
+      }
+      alpha = 1.0 + s;
+    }
+    p.alpha[b] = alpha;
+    for (int k = 0; k < K; ++k) {
+      double c = p.c[k * ld + b], g = p.gamma[k * ld + b];
+      double yk = (k == cls) ? 1.0 : 0.0;
+      double th = (yk + g) * tanh(0.5 * c) / (2.0 * c);
+      p.theta[k * ld + b] = th;
+      int ql = k - p.latent_begin;
+      if (ql >= 0 && ql < p.n_latent_local) {
+        p.gmu[ql * ld + b] = 0.5 * (yk - g);
+        p.gS[ql * ld + b] = 0.5 * th;
+      }
+    }
+    return;
+  }
+  if (p.model_kind == 0) {
+    // ---- single-latent SVGP ----
+    double y = p.idx ? p.y_all[src] : p.yb[b];
+    if (p.idx) p.yb[b] = y;
+    if (!p.update) return;
+    double c, th, gm, gs;
+    lik_single(p.lik_kind[0], p.p0[0], p.p1[0], y, p.mean_f[b], p.var_f[b], c, th, gm, gs);
+    p.c[b] = c; p.theta[b] = th;
+    p.gmu[b] = gm; p.gS[b] = gs;
+    return;
+  }
+  // ---- MOSVGP (models/single_and_multi_output_utils.jl:24-84) ----
+  const int T = p.n_task, Q = p.Q;
+  for (int t = 0; t < T; ++t) {
+    double y = p.idx ? p.y_all[(int64_t)t * p.n + src] : p.yb[t * ld + b];
+    if (p.idx) p.yb[t * ld + b] = y;
+    double mt = 0.0, vt = 0.0;
+    for (int q = 0; q < Q; ++q) {
+      double a = p.A[t * Q + q];
+      mt += a * p.mean_f[q * ld + b];
+      vt += a * a * p.var_f[q * ld + b];
+    }
+    p.tmu[t * ld + b] = mt; p.tvar[t * ld + b] = vt;
+    if (p.update) {
+      double c, th, gm, gs;
+      lik_single(p.lik_kind[t], p.p0[t], p.p1[t], y, mt, vt, c, th, gm, gs);
+      p.c[t * ld + b] = c; p.theta[t * ld + b] = th;
+      p.gm[t * ld + b] = gm; p.gs[t * ld + b] = gs;
+    }
+  }
+  if (!p.update) return;
+  for (int ql = 0; ql < p.n_latent_local; ++ql) {
+    int q = p.latent_begin + ql;
+    double muq = p.mean_f[q * ld + b];
+    double a1 = 0.0, a2 = 0.0;
+    for (int t = 0; t < T; ++t) {
+      double a = p.A[t * Q + q];
+      double others = p.tmu[t * ld + b] - a * muq;
+      a1 += a * (p.gm[t * ld + b] - 2.0 * p.gs[t * ld + b] * others);
+      a2 += a * a * p.gs[t * ld + b];
+    }
+    p.gmu[ql * ld + b] = a1;
+    p.gS[ql * ld + b] = a2;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ELBO likelihood terms (inference/analyticVI.jl:255-297): out[0] += expec_loglikelihood (un-scaled),
+// out[2] += AugmentedKL (un-scaled).  Block-reduced, one atomicAdd pair per block.
+// ------------------------------------------------------------------------------------------------
+__global__ void elbo_lik_kernel(const LikParams p, double* __restrict__ out) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  double e = 0.0, kl = 0.0;
+  const int64_t ld = p.ldB;
+  if (b < p.B) {
+    if (p.model_kind == 0 && p.lik_kind[0] == 3) {
+      // logisticsoftmax.jl:106-140 ; KLdivergences.jl:83-98 (Q2, Q10)
+      const int K = p.Q;
+      int cls = p.ycls[b];
+      double alpha = p.alpha[b], beta = (double)K;
+      double psi = digamma_pos(alpha), lb = log(beta);
+      e += -(double)K * 0.6931471805599453;
+      for (int k = 0; k < K; ++k) {
+        double mu = p.mean_f[k * ld + b], var = p.var_f[k * ld + b];
+        double g = p.gamma[k * ld + b], th = p.theta[k * ld + b], c = p.c[k * ld + b];
+        double yk = (k == cls) ? 1.0 : 0.0;
+        e += -(g + yk) * 0.6931471805599453 + 0.5 * (mu * (yk - g) - th * mu * mu - th * var);
+        kl += (yk + g) * logcosh_d(0.5 * c) - 0.5 * c * c * th;          // PolyaGammaKL
+        kl += alpha / beta - g + xlogx_d(g) - g * (psi - lb);           // PoissonKL
+      }
+      kl += -alpha - lgamma(alpha) - (1.0 - alpha) * psi;               // GammaEntropy (per-sample part)
+      if (b == 0) kl += lb;                                             // Q2: log(beta[1]) once
+    } else {
+      int T = p.model_kind == 0 ? 1 : p.n_task;
+      for (int t = 0; t < T; ++t) {
+        double mu, var;
+        if (p.model_kind == 0) { mu = p.mean_f[b]; var = p.var_f[b]; }
+        else { mu = p.tmu[t * ld + b]; var = p.tvar[t * ld + b]; }
+        double y = p.yb[t * ld + b], th = p.theta[t * ld + b], c = p.c[t * ld + b];
+        int kind = p.lik_kind[t];
+        double p0 = p.p0[t], p1 = p.p1[t];
+        if (kind == 1) {  // logistic.jl:73-92 (Q1: theta*mu, not theta*mu^2)
+          e += -0.5 * 0.6931471805599453 + 0.5 * (mu * y - th * var - th * mu);
+          kl += logcosh_d(0.5 * c) - 0.5 * c * c * th;
+        } else if (kind == 2) {  // studentt.jl:103-127 ; KLdivergences.jl:62-67
+          double al = 0.5 * (p0 + 1.0), ap = 0.5 * p0, bp = ap * p1 * p1;
+          e += -0.5 * log(6.283185307179586 * p1 * p1) - (log(c) - digamma_pos(al)) -
+               0.5 * (th * var + th * mu * mu - 2.0 * th * mu * y + th * y * y);
+          kl += (al - ap) * digamma_pos(al) - log(tgamma(al)) + log(tgamma(ap)) + ap * (log(c) - log(bp)) + al * (bp - c) / c;
+        } else {  // gaussian.jl:82-95
+          double d = y - mu;
+          e += -0.5 * (log(6.283185307179586) + log(p0) + (d * d + var) / p0);
+        }
+      }
+    }
+  }
+  __shared__ double se[8], sk[8];
+  e = warp_sum(e); kl = warp_sum(kl);
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { se[w] = e; sk[w] = kl; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, c2 = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += se[i]; c2 += sk[i]; }
+    atomicAdd(out + 0, a);
+    atomicAdd(out + 2, c2);
+  }
+}
+
+// GaussianKL pieces (functions/KLdivergences.jl:11-18): out[0] += sum_ij Kinv_ij Sigma_ij  (tr(K\Sigma)),
+// out[1] += (mu-mu0)^T Kinv (mu-mu0)  (invquad)
+__global__ void gauss_kl_kernel(const double* __restrict__ Kinv, const double* __restrict__ Sigma, int64_t ld, int m,
+                                const double* __restrict__ mu, const double* __restrict__ mu0, double* __restrict__ out) {
+  int row = blockIdx.x;
+  double tr = 0.0, q = 0.0;
+  double di = mu[row] - (mu0 ? mu0[row] : 0.0);
+  for (int j = threadIdx.x; j < m; j += blockDim.x) {
+    double kv = Kinv[(int64_t)row * ld + j];
+    tr += kv * Sigma[(int64_t)row * ld + j];
+    q += kv * di * (mu[j] - (mu0 ? mu0[j] : 0.0));
+  }
+  __shared__ double s1[8], s2[8];
+  tr = warp_sum(tr); q = warp_sum(q);
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { s1[w] = tr; s2[w] = q; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, c = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += s1[i]; c += s2[i]; }
+    atomicAdd(out + 0, a);
+    atomicAdd(out + 1, c);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// m x m tail (always fp64)
+// ------------------------------------------------------------------------------------------------
+struct TailParams {
+  int m, mp;            // logical / padded (power-of-two multiple of 64) size
+  int64_t ld;           // = mp : leading dimension of every fp64 m x m matrix
+  int n_split; int64_t gpart_stride; int64_t gpart_ld;  // G partials [n_split][m][gpart_ld]
+  const double* v1;     // kappa^T grad_mu (un-scaled by rho)
+  const double* Kinv; const double* Kinv_mu0;
+  double* eta1; double* eta2; double* P;
+  const int64_t* counters;  // [0] = Robbins-Monro t (starts at 1)
+  int stochastic; double rm_kappa, rm_tau, rho;
+  double* logdet; int* status;
+};
+
+// natural gradient + global update of the natural parameters (inference/analyticVI.jl:160-180, 229-246;
+// inference/optimisers.jl:14-19) and P = -2 eta2 (the matrix whose inverse is Sigma, inference.jl:26).
+// G is symmetrised from its upper triangle like Julia's Symmetric() (analyticVI.jl:238, Q5).
+template <typename TG>
+__global__ void combine_kernel(const TailParams p, const TG* __restrict__ Gpart) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  int i = blockIdx.y;
+  if (j >= p.mp) return;
+  double lr = 1.0;
+  if (p.stochastic) lr = pow(p.rm_tau + (double)p.counters[0], -p.rm_kappa);
+  if (i >= p.m || j >= p.m) {
+    p.P[(int64_t)i * p.ld + j] = (i == j) ? 1.0 : 0.0;
+    return;
+  }
+  int a = min(i, j), b = max(i, j);
+  double g = 0.0;
+  for (int s = 0; s < p.n_split; ++s) g += (double)Gpart[s * p.gpart_stride + (int64_t)a * p.gpart_ld + b];
+  int64_t o = (int64_t)i * p.ld + j;
+  double e2 = p.eta2[o];
+  double d2 = -(g + 0.5 * p.Kinv[o]) - e2;
+  e2 += lr * d2;
+  p.eta2[o] = e2;
+  p.P[o] = -2.0 * e2;
+  if (i == 0) {
+    double e1 = p.eta1[j];
+    double d1 = p.rho * p.v1[j] + p.Kinv_mu0[j] - e1;
+    p.eta1[j] = e1 + lr * d1;
+    if (j == 0) *p.logdet = 0.0;
+  }
+}
+
+// Unblocked Cholesky of one 64 x 64 diagonal block held in shared memory, fused with the inverse of
+// its factor (the rank-1 update that eliminates column j is applied to [A | W], W starting as I, so
+// W ends as L^-1).  In: lower triangle of Ablk.  Out: L in the lower triangle of Ablk, L^-1 (lower,
+// explicit zeros above the diagonal) in Xblk, logdet += 2 sum log L_jj.
+constexpr int POTF2_NB = 64;
+__global__ void __launch_bounds__(256) potf2_inv_kernel(double* __restrict__ Ablk, int64_t lda, double* __restrict__ Xblk,
+                                                        int64_t ldx, double* __restrict__ logdet, int* __restrict__ status) {
+  constexpr int NB = POTF2_NB, LDS = NB + 1;
+  extern __shared__ double sm[];
+  double* a = sm;              // [NB][LDS]
+  double* w = sm + NB * LDS;   // [NB][LDS]
+  const int tid = threadIdx.x;
+  for (int e = tid; e < NB * NB; e += 256) {
+    int i = e / NB, j = e % NB;
+    a[i * LDS + j] = (j <= i) ? Ablk[(int64_t)i * lda + j] : 0.0;
+    w[i * LDS + j] = (i == j) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  double ld_acc = 0.0;
+  bool bad = false;
+  for (int j = 0; j < NB; ++j) {
+    double d = a[j * LDS + j];
+    if (!(d > 0.0)) { bad = true; d = 1.0; }
+    double r = rsqrt(d);
+    ld_acc += log(d);
+    __syncthreads();
+    // scale column j of A (rows >= j) and row j of W (cols <= j)
+    if (tid < NB) {
+      if (tid >= j) a[tid * LDS + j] *= r;
+    } else if (tid < 2 * NB) {
+      int c = tid - NB;
+      if (c <= j) w[j * LDS + c] *= r;
+    }
+    __syncthreads();
+    // eliminate: rows i > j.  cols c > j (c <= i): A update;  cols c <= j: W update.
+    int nrow = NB - 1 - j;
+    for (int e = tid; e < nrow * NB; e += 256) {
+      int i = j + 1 + e / NB, c = e % NB;
+      double lij = a[i * LDS + j];
+      if (c > j) { if (c <= i) a[i * LDS + c] -= lij * a[c * LDS + j]; }
+      else w[i * LDS + c] -= lij * w[j * LDS + c];
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < NB * NB; e += 256) {
+    int i = e / NB, j = e % NB;
+    if (j <= i) Ablk[(int64_t)i * lda + j] = a[i * LDS + j];
+    Xblk[(int64_t)i * ldx + j] = (j <= i) ? w[i * LDS + j] : 0.0;
+  }
+  if (tid == 0) {
+    atomicAdd(logdet, ld_acc);
+    if (bad) atomicOr(status, ST_NOT_POSDEF);
+  }
+}
+
+// Sigma lower triangle (from the lower-only X^T X product) -> full symmetric fp64 master + T shadow
+template <typename T>
+__global__ void symmetrize_shadow_kernel(double* __restrict__ S, int64_t ld, int m, T* __restrict__ shadow, int64_t lds) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  int i = blockIdx.y;
+  if (j >= m || i >= m) return;
+  double v = (j <= i) ? S[(int64_t)i * ld + j] : S[(int64_t)j * ld + i];
+  if (j > i) S[(int64_t)i * ld + j] = v;
+  if (shadow) shadow[(int64_t)i * lds + j] = (T)v;
+}
+
+// fp64 matrix (ld) -> T shadow copy (lds)
+template <typename T>
+__global__ void shadow_kernel(const double* __restrict__ S, int64_t ld, int m, T* __restrict__ shadow, int64_t lds) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  int i = blockIdx.y;
+  if (j >= m || i >= m) return;
+  shadow[(int64_t)i * lds + j] = (T)S[(int64_t)i * ld + j];
+}
+
+// y = S x  (mu = Sigma * eta1, inference/inference.jl:27); one warp per row
+__global__ void symv_kernel(const double* __restrict__ S, int64_t ld, int m, const double* __restrict__ x,
+                            double* __restrict__ y) {
+  int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= m) return;
+  double s = 0.0;
+  for (int j = lane; j < m; j += 32) s += S[(int64_t)row * ld + j] * x[j];
+  s = warp_sum(s);
+  if (lane == 0) y[row] = s;
+}
+
+__global__ void bump_counters_kernel(int64_t* counters, int bump_t, int bump_cursor) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) { counters[0] += bump_t; counters[1] += bump_cursor; }
+}
+
+// K_mm finishing touch in fp64 (gpblocks/latentgp.jl:206): exact diagonal variance + jitter, identity padding
+__global__ void kmm_fix_kernel(double* __restrict__ K, int64_t ld, int m, int mp, double diag) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  int i = blockIdx.y;
+  if (j >= mp) return;
+  if (i >= m || j >= m) K[(int64_t)i * ld + j] = (i == j) ? 1.0 : 0.0;
+  else if (i == j) K[(int64_t)i * ld + j] = diag;
+}
+
+__global__ void set_identity_kernel(double* __restrict__ S, int64_t ld, int mp, double diag) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  int i = blockIdx.y;
+  if (j >= mp) return;
+  S[(int64_t)i * ld + j] = (i == j) ? diag : 0.0;
+}
+
+// Bernoulli predictive by Gauss-Hermite quadrature (likelihood/classification.jl:14-26)
+__global__ void proba_logistic_kernel(const double* __restrict__ mu, const double* __restrict__ var, int64_t n,
+                                      const double* __restrict__ nodes, const double* __restrict__ weights, int nn,
+                                      double* __restrict__ p, double* __restrict__ pv) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double sd = sqrt(fmax(var[i], 0.0)), m = mu[i];
+  double s1 = 0.0, s2 = 0.0;
+  for (int k = 0; k < nn; ++k) {
+    double l = logistic_d(nodes[k] * sd + m);
+    s1 += weights[k] * l;
+    s2 += weights[k] * l * l;
+  }
+  p[i] = s1;
+  pv[i] = fmax(s2 - s1 * s1, 0.0);
+}
+
+}  // namespace agp

@@ -1,0 +1,203 @@
+/*
+ * agp_b200.h -- C ABI of the B200-native sparse-variational-GP CAVI engine.
+ *
+ * The reference (theogf/AugmentedGaussianProcesses.jl, pure Julia) has NO FFI boundary for this
+ * path; the seam is Julia multiple dispatch.  Each entry point below names the reference method
+ * (file:line under /root/reference/src) whose work it replaces.  A Julia shim overrides those
+ * methods and `ccall`s this library (julia/AGPB200.jl).
+ *
+ * Conventions
+ *   - plain C: pointers + sizes only, no torch / C++ types.
+ *   - caller owns every host buffer; the library owns device memory behind opaque handles.
+ *   - every function returns an int status (AGP_OK == 0) unless documented otherwise; the text of
+ *     the last error is available from agp_last_error().
+ *   - one calling thread per agp_ctx (the reference is single-threaded).
+ *   - all host floating-point buffers are double unless a dtype argument says otherwise
+ *     (the reference path is Float64-only: models/SVGP.jl:43, training/states.jl:15).
+ *   - there is NO CPU fallback: without a CUDA device every call fails with AGP_ERR_CUDA.
+ */
+#ifndef AGP_B200_H
+#define AGP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AGP_ABI_VERSION 1
+
+/* ---- status codes (reference error sites) ------------------------------------------------ */
+#define AGP_OK 0
+#define AGP_ERR_BAD_ARG 1       /* training/training.jl:27-29, models/SVGP.jl:45-49 (argument checks) */
+#define AGP_ERR_CUDA 2          /* CUDA runtime failure (no reference counterpart)                    */
+#define AGP_ERR_KTILDE_NONPOS 3 /* gpblocks/latentgp.jl:213  error("K̃ has negative values")          */
+#define AGP_ERR_NOT_POSDEF 4    /* PosDefException from cholesky(): latentgp.jl:206, inference.jl:26  */
+#define AGP_ERR_STATE 5         /* call order violated (e.g. step before data upload)                 */
+
+/* ---- enums -------------------------------------------------------------------------------- */
+/* KernelFunctions.jl kernels used by the reference call sites (gpblocks/latentgp.jl:206,210,212) */
+#define AGP_KERNEL_SQEXP 0    /* SqExponentialKernel: exp(-d^2/2)               */
+#define AGP_KERNEL_MATERN32 1 /* Matern32Kernel: (1+sqrt3 d) exp(-sqrt3 d)      */
+#define AGP_KERNEL_MATERN52 2 /* Matern52Kernel                                 */
+
+/* likelihood/*.jl (AnalyticVI methods only) */
+#define AGP_LIK_GAUSSIAN 0        /* likelihood/gaussian.jl:56-95        p0 = sigma^2            */
+#define AGP_LIK_LOGISTIC 1        /* likelihood/logistic.jl:39-92                                  */
+#define AGP_LIK_STUDENTT 2        /* likelihood/studentt.jl:68-127       p0 = nu, p1 = sigma      */
+#define AGP_LIK_LOGISTICSOFTMAX 3 /* likelihood/logisticsoftmax.jl:43-140  (n_latent = #classes)  */
+
+#define AGP_MODEL_SVGP 0   /* models/SVGP.jl:22-80: one likelihood, n_latent(likelihood) latents */
+#define AGP_MODEL_MOSVGP 1 /* models/MOSVGP.jl:22-115: T single-latent tasks mixed from Q latents */
+
+/* arithmetic of the B x m contractions; the m x m tail (eta update, Cholesky, inverse) is always f64 */
+#define AGP_PREC_F64 0    /* everything in fp64 SIMT: bit-for-bit algorithm of the oracle        */
+#define AGP_PREC_F32 1    /* fp32 SIMT contractions                                              */
+#define AGP_PREC_TF32X3 2 /* tcgen05 tensor-core contractions, 3xTF32 error-compensated split    */
+
+#define AGP_DTYPE_F64 0
+#define AGP_DTYPE_F32 1
+#define AGP_LAYOUT_COLMAJOR 0 /* Julia Matrix n x D (obsdim = 1): X[i + n*d]  (data/datacontainer.jl:64-66) */
+#define AGP_LAYOUT_ROWMAJOR 1 /* C / NumPy n x D: X[i*D + d]                                               */
+
+#define AGP_Y_REAL 0  /* double[n] per task: +-1 labels (classification.jl:29-39) or reals   */
+#define AGP_Y_CLASS 1 /* int32[n] 0-based class index (one-hot of multiclass.jl:81-94)       */
+
+typedef struct agp_ctx agp_ctx;
+typedef struct agp_model agp_model;
+
+/* Everything the constructors SVGP(...) / MOSVGP(...) + AnalyticVI()/AnalyticSVI(B) fix
+ * (models/SVGP.jl:33-80, models/MOSVGP.jl:40-115, inference/analyticVI.jl:44-52). */
+typedef struct agp_model_desc {
+  int32_t model_kind;       /* AGP_MODEL_*                                                        */
+  int32_t n_latent_global;  /* Q: latent GPs of the whole model (all ranks)                       */
+  int32_t latent_begin;     /* first latent owned by this process (0 when not sharded)            */
+  int32_t n_latent_local;   /* latents owned by this process                                      */
+  int32_t m;                /* inducing points per latent                                         */
+  int32_t D;                /* input dimension                                                    */
+  int32_t batch_capacity;   /* largest B any step / ELBO call will use                            */
+  int32_t precision;        /* AGP_PREC_*                                                         */
+  int32_t stochastic;       /* 1: AnalyticSVI (optimisers.jl RobbinsMonro), 0: AnalyticVI (lr=1)  */
+  double rm_kappa, rm_tau;  /* RobbinsMonro(kappa=0.51, tau=1)  inference/optimisers.jl:6-19      */
+  double jitter;            /* functions/utils.jl:8 (1e-4 for Float64)                            */
+  int32_t n_task;           /* T: 1 for SVGP, #likelihoods for MOSVGP                             */
+  const int32_t* lik_kind;  /* [T] AGP_LIK_*                                                      */
+  const double* lik_p0;     /* [T]                                                                */
+  const double* lik_p1;     /* [T]                                                                */
+  const double* A;          /* [T*Q] row-major mixing weights (MOSVGP.jl:103), NULL for SVGP      */
+  const int32_t* kernel_kind;    /* [n_latent_local]                                              */
+  const double* kernel_scale;    /* [n_latent_local] ScaleTransform(s) (= 1/lengthscale)          */
+  const double* kernel_variance; /* [n_latent_local] sigma^2 * k                                  */
+  const double* Z;               /* [n_latent_local][m][D] row-major inducing points              */
+  const double* mu0;             /* [n_latent_local][m] prior mean at Z, or NULL (ZeroMean)       */
+} agp_model_desc;
+
+/* ---- context ------------------------------------------------------------------------------ */
+int agp_abi_version(void);
+/* cuda_stream: a cudaStream_t to launch on (e.g. the host framework's current stream), or NULL to
+ * let the library create its own. */
+int agp_ctx_create(int device, void* cuda_stream, agp_ctx** out);
+void agp_ctx_destroy(agp_ctx* ctx);
+const char* agp_last_error(const agp_ctx* ctx);
+
+/* ---- model (SVGP.jl:33-80 / MOSVGP.jl:40-115; posterior init gpblocks/posterior.jl:29-37) -- */
+int agp_model_create(agp_ctx* ctx, const agp_model_desc* desc, agp_model** out);
+void agp_model_destroy(agp_model* model);
+
+/* wrap_X / wrap_data (data/datacontainer.jl:64-74, data/utils.jl:20-28): upload once, keep resident.
+ * y: array of T pointers (one per task). */
+int agp_data_upload(agp_model* model, const void* X, int x_dtype, int x_layout, int64_t n,
+                    const void* const* y, int y_kind);
+
+/* Resident minibatch index lists (training/training.jl:51-53 draws them with StatsBase.sample; the
+ * RNG stream cannot be reproduced outside Julia, so the lists cross the ABI).  idx: [n_lists][B].
+ * Steps called with idx == NULL consume the lists in order (wrapping around). */
+int agp_minibatches_upload(agp_model* model, const int64_t* idx, int64_t n_lists, int32_t B,
+                           int32_t idx_base /* 0 or 1 */);
+
+/* init_state (training/states.jl:1-9, 61-71): what a train! call without `state` does -- Robbins-Monro
+ * counters back to 1, local variables back to init_local_vars (LogisticSoftMax alpha = K).  The
+ * posterior (mu, Sigma, eta1, eta2) is NOT touched (it lives in the model, not in the state). */
+int agp_state_reset(agp_model* model);
+
+/* compute_K (gpblocks/latentgp.jl:205-207) for every local latent: K_mm + jitter I, its Cholesky,
+ * K^-1, logdet K, K^-1 mu0.  Called once per train! (training/training.jl:41-43, quirk Q3). */
+int agp_refresh_K(agp_model* model);
+/* setkernel! (hyper-parameter change from the host side); follow with agp_refresh_K. */
+int agp_set_kernel(agp_model* model, int32_t latent_local, int32_t kind, double scale, double variance);
+
+/* ---- the hot path: update_parameters!(model::SVGP, state, x, y)  (training/training.jl:140-157)
+ *   = compute_kernel_matrices (training.jl:187-208) -> compute_kappa (latentgp.jl:209-215)
+ *   + variational_updates (inference/analyticVI.jl:62-111): mean_f/var_f (latentgp.jl:171-189),
+ *     local_updates! + grad_E_mu/grad_E_Sigma (likelihood/<lik>.jl), natural_gradient!
+ *     (analyticVI.jl:143-180), global_update! (analyticVI.jl:229-246, inference/inference.jl:25-28).
+ * idx: host list of B row indices into the uploaded data (idx_base 0 or 1), or NULL to take the next
+ * resident list.  rho = n / B (training.jl:30). */
+int agp_step(agp_model* model, const int64_t* idx, int32_t B, int32_t idx_base, double rho);
+/* same, without the trailing synchronisation / error read-back (errors surface at agp_sync). */
+int agp_step_async(agp_model* model, const int64_t* idx, int32_t B, int32_t idx_base, double rho);
+/* same step for a minibatch handed over as HOST arrays (the x, y views update_parameters! receives):
+ * xb: B x D, yb: array of T pointers of length-B vectors.  Copies host->device inside the call. */
+int agp_step_batch(agp_model* model, const void* xb, int x_dtype, int x_layout, const void* const* yb,
+                   int y_kind, int32_t B, double rho);
+/* wait for the stream and return the sticky device status (AGP_ERR_KTILDE_NONPOS / NOT_POSDEF). */
+int agp_sync(agp_model* model);
+
+/* ---- latent-sharded variant (one process per GPU) ---------------------------------
+ * phase 1: kernel matrices + per-latent predictive moments of the owned latents (latentgp.jl:171-215)
+ * written into rows [latent_begin, latent_begin+n_latent_local) of two [Q][ldB] double device arrays.
+ * The host all-gathers those rows (NCCL) in place, then phase 2 runs local updates for all latents
+ * (single_and_multi_output_utils.jl:24-84, logisticsoftmax.jl:55-79) and the natural-gradient /
+ * global update of the owned latents. */
+int agp_step_moments_async(agp_model* model, const int64_t* idx, int32_t B, int32_t idx_base);
+int agp_step_update_async(agp_model* model, double rho);
+/* device pointers + leading dimension of the moment arrays (which: 0 = mean_f, 1 = var_f). */
+void* agp_moments_devptr(agp_model* model, int32_t which, int64_t* ld_out);
+
+/* ---- ELBO(model, state, y) (inference/analyticVI.jl:255-297) on the last minibatch -----------
+ * out[0] = rho * expec_loglikelihood, out[1] = GaussianKL summed over OWNED latents
+ * (functions/KLdivergences.jl:2-18), out[2] = rho * AugmentedKL;  ELBO = out[0] - out[1] - out[2]
+ * (a sharded host all-reduces out[1]). */
+int agp_elbo(agp_model* model, double rho, double* out3);
+/* sharded ELBO: recompute the owned latents' moments under the updated posterior (the host then
+ * all-gathers them before calling agp_elbo; a non-sharded agp_elbo does this internally). */
+int agp_elbo_moments_async(agp_model* model);
+
+/* ---- posterior access / checkpoint (gpblocks/posterior.jl:21-27; train!(...; state) re-entry) - */
+int agp_get_posterior(agp_model* model, int32_t latent_local, double* mu, double* Sigma, double* eta1,
+                      double* eta2); /* any pointer may be NULL; matrices are m x m row-major */
+int agp_set_posterior(agp_model* model, int32_t latent_local, const double* eta1, const double* eta2);
+/* Robbins-Monro step counters (states.jl:67-68) and index-list cursor */
+int agp_get_counters(agp_model* model, int64_t* rm_t, int64_t* cursor);
+int agp_set_counters(agp_model* model, int64_t rm_t, int64_t cursor);
+/* local variables of the last step: name in {"c","theta","gamma","alpha","mean_f","var_f",
+ * "Ktilde","grad_mu","grad_Sigma"}; row = task / class / latent index; out: double[B]. */
+int agp_get_local(agp_model* model, const char* name, int32_t row, double* out, int32_t B);
+/* kernel matrices of the last step for one owned latent (state.kernel_matrices): B x m row-major */
+int agp_get_kernel_matrices(agp_model* model, int32_t latent_local, double* Knm, double* kappa, int32_t B);
+/* K^-1 and logdet K from the last agp_refresh_K */
+int agp_get_Kinv(agp_model* model, int32_t latent_local, double* Kinv, double* logdetK);
+
+/* ---- _predict_f (training/predictions.jl:25-50, diag = true) for the owned latents ------------
+ * mu, var: [n_latent_local][nt] (var may be NULL when want_var == 0). */
+int agp_predict_f(agp_model* model, const void* Xt, int x_dtype, int x_layout, int64_t nt, int want_var,
+                  double* mu, double* var);
+/* compute_proba(::BernoulliLikelihood) (likelihood/classification.jl:14-26): Gauss-Hermite
+ * expectation of the logistic link; nodes/weights as in predictions.jl:4 (already scaled). */
+int agp_proba_logistic(agp_model* model, const double* mu, const double* var, int64_t n, const double* nodes,
+                       const double* weights, int32_t n_nodes, double* p, double* p_var);
+
+/* ---- measurement hooks ------------------------------------------------------------------------ */
+/* per-phase CUDA-event timers around the kernels of a step (off by default; adds event records). */
+int agp_profile_enable(agp_model* model, int on);
+/* number of phases; names[i] points to a static string, ms[i] / launches[i] accumulate since enable */
+int agp_profile_read(agp_model* model, int32_t max_phases, const char** names, double* ms, int64_t* launches);
+/* kernels launched by this model since creation (the `gpu_launches` claim of bench.py). */
+int64_t agp_launch_count(agp_model* model);
+/* capture the step into a CUDA graph and replay it on later agp_step*(idx == NULL) calls. */
+int agp_use_graph(agp_model* model, int on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGP_B200_H */

@@ -1,0 +1,771 @@
+"""CPU oracle: fp64 NumPy/SciPy restatement of the reference AnalyticVI/AnalyticSVI path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in the product package may import this file; only
+`tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference`
+legs use it, and only as the checker / the reported CPU baseline.
+
+PARITY UNPINNED: the reference (theogf/AugmentedGaussianProcesses.jl v0.11.6) is pure
+Julia; Julia is not installed here, its arithmetic lives in un-vendored packages
+(KernelFunctions.jl 0.8-0.10, Optimisers.jl 0.1/0.3, StatsBase 0.32/0.33 -- compat
+ranges only, no Manifest pin) and its own tests hold no golden mu/Sigma/ELBO vectors.
+This file is therefore a *restatement by code reading*; each function cites the
+reference file:line it follows (paths relative to /root/reference/src).  The only
+known-answer tests the reference ships for this path (test/functions/utils.jl,
+test/likelihood/multiclass.jl, test/inference/analyticVI.jl) are re-run against this
+file in tests/test_oracle.py.
+
+Reference quirks reproduced on purpose: Q1 logistic ELBO uses
+dot(theta, mu); Q2 GammaEntropy uses log(beta[0]) only; Q3 K_mm factorised once per
+train call; Q6 LogisticSoftMax local variables persist across minibatches; Q9
+Robbins-Monro counter starts at 1; Q10 length(y) of a one-hot y is B*K.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+import scipy.linalg as sla
+import scipy.special as ssp
+
+LOGTWO = math.log(2.0)
+TWOPI = 2.0 * math.pi
+JITTER_F64 = 1e-4  # functions/utils.jl:8
+JITTER_F32 = 1e-3  # functions/utils.jl:9
+JITTER_F16 = 1e-2  # functions/utils.jl:10
+
+
+# --------------------------------------------------------------------------------------
+# functions/utils.jl
+# --------------------------------------------------------------------------------------
+def sqrt_expec_square(mu, s2):
+    """functions/utils.jl:22-24"""
+    return np.sqrt(np.abs(mu) ** 2 + s2)
+
+
+def invquad(L, x):
+    """functions/utils.jl:47  (L = lower Cholesky factor)"""
+    return float(np.sum(sla.solve_triangular(L, x, lower=True) ** 2))
+
+
+def trace_ABt(A, B):
+    """functions/utils.jl:50-52"""
+    return float(np.sum(A * B))
+
+
+def diag_ABt(A, B):
+    """functions/utils.jl:55-57"""
+    return np.sum(A * B, axis=1)
+
+
+def kdiagthetak(kappa, theta):
+    """functions/utils.jl:65-67"""
+    return (theta[:, None] * kappa).T @ kappa
+
+
+def rho_kdiagthetak(rho, kappa, theta):
+    """functions/utils.jl:70-72"""
+    return ((rho * theta)[:, None] * kappa).T @ kappa
+
+
+def logistic(x):
+    return ssp.expit(x)
+
+
+def safe_expcosh(mu, c):
+    """functions/utils.jl:84-86"""
+    mu = np.asarray(mu, dtype=np.float64)
+    c = np.asarray(c, dtype=np.float64)
+    with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
+        v = np.exp(mu) / np.cosh(c)
+    alt = 2.0 * logistic(2.0 * np.maximum(mu, c))
+    return np.where(np.isfinite(v), v, alt)
+
+
+def logcosh(c):
+    """functions/utils.jl:89-91"""
+    c = np.asarray(c, dtype=np.float64)
+    return np.log(np.exp(-2.0 * c) + 1.0) + c - LOGTWO
+
+
+def xlogx(x):
+    x = np.asarray(x, dtype=np.float64)
+    return ssp.xlogy(x, x)
+
+
+# --------------------------------------------------------------------------------------
+# KernelFunctions.jl (external; restated from its published definitions)
+# --------------------------------------------------------------------------------------
+@dataclass
+class Kernel:
+    """variance * base(scale * x, scale * z).   `with_lengthscale(k, l)` == scale 1/l."""
+
+    kind: str = "sqexp"  # "sqexp" | "matern32" | "matern52"
+    scale: float = 1.0  # ScaleTransform(s)
+    variance: float = 1.0  # sigma^2 * k
+
+    def _base(self, d2):
+        if self.kind == "sqexp":
+            return np.exp(-0.5 * d2)
+        d = np.sqrt(np.maximum(d2, 0.0))
+        if self.kind == "matern32":
+            return (1.0 + math.sqrt(3.0) * d) * np.exp(-math.sqrt(3.0) * d)
+        if self.kind == "matern52":
+            return (1.0 + math.sqrt(5.0) * d + 5.0 * d2 / 3.0) * np.exp(-math.sqrt(5.0) * d)
+        raise ValueError(self.kind)
+
+
+def kernelmatrix(k: Kernel, X, Z=None):
+    X = np.asarray(X, dtype=np.float64) * k.scale
+    Zs = X if Z is None else np.asarray(Z, dtype=np.float64) * k.scale
+    xx = np.sum(X * X, axis=1)[:, None]
+    zz = np.sum(Zs * Zs, axis=1)[None, :]
+    d2 = np.maximum(xx + zz - 2.0 * (X @ Zs.T), 0.0)
+    if Z is None:
+        np.fill_diagonal(d2, 0.0)
+    return k.variance * k._base(d2)
+
+
+def kernelmatrix_exact(k: Kernel, X, Z):
+    """Pairwise-difference form (no cancellation); used by tests to bound the GEMM form."""
+    X = np.asarray(X, dtype=np.float64) * k.scale
+    Z = np.asarray(Z, dtype=np.float64) * k.scale
+    d2 = np.sum((X[:, None, :] - Z[None, :, :]) ** 2, axis=2)
+    return k.variance * k._base(d2)
+
+
+def kernelmatrix_diag(k: Kernel, X):
+    return np.full(len(X), k.variance, dtype=np.float64)
+
+
+# --------------------------------------------------------------------------------------
+# Likelihood descriptors (likelihood/*.jl)
+# --------------------------------------------------------------------------------------
+@dataclass
+class GaussianLikelihood:
+    """likelihood/gaussian.jl:10-24 (default sigma2 = 1e-3, opt_noise off)."""
+
+    sigma2: float = 1e-3
+    n_latent: int = 1
+    name: str = "gaussian"
+
+
+@dataclass
+class LogisticLikelihood:
+    """likelihood/logistic.jl:19"""
+
+    n_latent: int = 1
+    name: str = "logistic"
+
+
+@dataclass
+class StudentTLikelihood:
+    """likelihood/studentt.jl:23-31"""
+
+    nu: float = 3.0
+    sigma: float = 1.0
+    n_latent: int = 1
+    name: str = "studentt"
+
+    @property
+    def alpha(self):
+        return (self.nu + 1.0) / 2.0
+
+
+@dataclass
+class LogisticSoftMaxLikelihood:
+    """likelihood/logisticsoftmax.jl:23 + multiclass.jl:1-24"""
+
+    n_class: int = 2
+    class_mapping: Optional[list] = None
+    name: str = "logisticsoftmax"
+
+    @property
+    def n_latent(self):
+        return self.n_class
+
+    def __post_init__(self):
+        if not isinstance(self.n_class, (int, np.integer)):
+            labels = list(self.n_class)
+            self.class_mapping = labels
+            self.n_class = len(labels)
+        self.ind_mapping = (
+            {v: i for i, v in enumerate(self.class_mapping)} if self.class_mapping is not None else None
+        )
+
+
+def create_mapping(l: LogisticSoftMaxLikelihood, y):
+    """likelihood/multiclass.jl:62-78 (0-based indices here, 1-based in Julia)."""
+    K = l.n_latent
+    if l.class_mapping is None:
+        seen = []
+        for v in y:
+            if v not in seen:
+                seen.append(v)
+        l.class_mapping = seen
+        ints = all(isinstance(v, (int, np.integer)) for v in seen)
+        if len(seen) <= K and ints and set(seen) <= set(range(1, K + 1)):
+            l.class_mapping = list(range(1, K + 1))
+        elif len(seen) > K:
+            raise ValueError(
+                "The number of unique labels in the data is not of the same size then the predefined class number"
+            )
+    l.ind_mapping = {v: i for i, v in enumerate(l.class_mapping)}
+    return l.ind_mapping
+
+
+def create_one_hot(l: LogisticSoftMaxLikelihood, y):
+    """likelihood/multiclass.jl:81-94"""
+    if not set(y) <= set(l.class_mapping):
+        raise ValueError("Some labels of y are not part of the expect labels")
+    Y = np.zeros((len(y), l.n_class), dtype=bool)
+    for i, v in enumerate(y):
+        Y[i, l.class_mapping.index(v)] = True
+    return Y
+
+
+def treat_labels(y, lik):
+    """classification.jl:29-39, multiclass.jl:40-44, regression.jl:10-15"""
+    if lik.name == "logistic":
+        y = np.asarray(y)
+        labels = sorted(int(v) for v in np.unique(y))
+        if labels == [0, 1]:
+            return np.sign(y.astype(np.float64) - 0.5)
+        if labels == [-1, 1]:
+            return y.astype(np.float64)
+        raise ValueError("Labels of y should be binary {-1,1} or {0,1}")
+    if lik.name == "logisticsoftmax":
+        y = list(y.tolist()) if isinstance(y, np.ndarray) else list(y)
+        if lik.ind_mapping is None:
+            create_mapping(lik, y)
+        return create_one_hot(lik, y)
+    return np.asarray(y, dtype=np.float64)
+
+
+# ---- init_local_vars -------------------------------------------------------------------
+def init_local_vars(lik, B):
+    """classification.jl:10-12, studentt.jl:64-66, gaussian.jl:47-54, logisticsoftmax.jl:43-53.
+    Random initial c / theta / gamma are overwritten before first use (Q7) -> zeros here."""
+    if lik.name in ("logistic", "studentt"):
+        return dict(c=np.zeros(B), theta=np.zeros(B))
+    if lik.name == "gaussian":
+        return dict(theta=np.full(B, 1.0 / lik.sigma2))
+    if lik.name == "logisticsoftmax":
+        K = lik.n_class
+        return dict(
+            c=np.ones((K, B)),
+            alpha=K * np.ones(B),
+            beta=K * np.ones(B),
+            theta=np.zeros((K, B)),
+            gamma=np.zeros((K, B)),
+        )
+    raise ValueError(lik.name)
+
+
+# ---- local_updates! --------------------------------------------------------------------
+def local_updates(lv, lik, y, mu, var):
+    """mu, var: (K, B) arrays of per-latent predictive moments on the minibatch."""
+    if lik.name == "logistic":  # logistic.jl:39-51
+        lv["c"] = sqrt_expec_square(mu[0], var[0])
+        lv["theta"] = np.tanh(lv["c"] / 2.0) / (2.0 * lv["c"])
+    elif lik.name == "studentt":  # studentt.jl:68-82
+        lv["c"] = (np.abs(mu[0] - y) ** 2 + var[0] + lik.sigma**2 * lik.nu) / 2.0
+        lv["theta"] = lik.alpha / lv["c"]
+    elif lik.name == "gaussian":  # gaussian.jl:56-72 (opt_noise = nothing)
+        lv["theta"] = np.full(mu.shape[1], 1.0 / lik.sigma2)
+    elif lik.name == "logisticsoftmax":  # logisticsoftmax.jl:55-79
+        lv["c"] = sqrt_expec_square(mu, var)
+        for _ in range(2):
+            psi = ssp.digamma(lv["alpha"])
+            lv["gamma"] = np.exp(psi)[None, :] * safe_expcosh(-mu / 2.0, lv["c"] / 2.0) / (2.0 * lv["beta"][None, :])
+            lv["alpha"] = 1.0 + np.sum(lv["gamma"], axis=0)
+        lv["theta"] = (y.T + lv["gamma"]) * np.tanh(lv["c"] / 2.0) / (2.0 * lv["c"])
+    else:
+        raise ValueError(lik.name)
+    return lv
+
+
+def grad_E_mu(lik, y, lv):
+    """(K, B).  logistic.jl:64-66, studentt.jl:96, gaussian.jl:74-76, logisticsoftmax.jl:98-100"""
+    if lik.name == "logistic":
+        return (y / 2.0)[None, :]
+    if lik.name == "studentt":
+        return (lv["theta"] * y)[None, :]
+    if lik.name == "gaussian":
+        return (y / lik.sigma2)[None, :]
+    if lik.name == "logisticsoftmax":
+        return (y.T - lv["gamma"]) / 2.0
+    raise ValueError(lik.name)
+
+
+def grad_E_Sigma(lik, y, lv):
+    """(K, B).  logistic.jl:67-69, studentt.jl:97-99, gaussian.jl:78-80, logisticsoftmax.jl:101-103"""
+    th = lv["theta"]
+    return (th / 2.0)[None, :] if th.ndim == 1 else th / 2.0
+
+
+# ---- ELBO pieces -----------------------------------------------------------------------
+def PolyaGammaKL(b, c, theta):
+    """functions/KLdivergences.jl:96-98"""
+    return float(np.dot(b, logcosh(c / 2.0)) - np.dot(np.abs(c) ** 2, theta) / 2.0)
+
+
+def GammaKL(alpha, beta, alpha_p, beta_p):
+    """functions/KLdivergences.jl:62-67 (alpha scalar, beta vector)"""
+    return float(
+        np.sum(
+            (alpha - alpha_p) * ssp.digamma(alpha)
+            - math.log(math.gamma(alpha))
+            + math.log(math.gamma(alpha_p))
+            + alpha_p * (np.log(beta) - math.log(beta_p))
+            + alpha * (beta_p - beta) / beta
+        )
+    )
+
+
+def PoissonKL(lam, lam0, psi):
+    """functions/KLdivergences.jl:83-89"""
+    return float(np.sum(lam0) - np.sum(lam) + np.sum(xlogx(lam)) - np.dot(lam, psi))
+
+
+def expec_loglikelihood(lik, y, mu, var, lv):
+    if lik.name == "logistic":  # logistic.jl:73-84  (Q1)
+        th = lv["theta"]
+        tot = -len(y) * LOGTWO / 2.0
+        tot += (np.dot(mu[0], y) - np.dot(th, var[0]) - np.dot(th, mu[0])) / 2.0
+        return float(tot)
+    if lik.name == "studentt":  # studentt.jl:103-119
+        th = lv["theta"]
+        tot = -len(y) * math.log(TWOPI * lik.sigma**2) / 2.0
+        tot += -np.sum(np.log(lv["c"]) - ssp.digamma(lik.alpha))
+        tot += -(
+            np.dot(th, var[0]) + np.dot(th, mu[0] ** 2) - 2.0 * np.dot(th, mu[0] * y) + np.dot(th, y**2)
+        ) / 2.0
+        return float(tot)
+    if lik.name == "gaussian":  # gaussian.jl:82-93
+        return float(
+            -(len(y) * (math.log(TWOPI) + math.log(lik.sigma2)) + (np.sum((y - mu[0]) ** 2) + np.sum(var[0])) / lik.sigma2)
+            / 2.0
+        )
+    if lik.name == "logisticsoftmax":  # logisticsoftmax.jl:106-115  (Q10: length(y) = B*K)
+        Y = y.T.astype(np.float64)
+        g, th = lv["gamma"], lv["theta"]
+        tot = -y.size * LOGTWO
+        tot += -np.sum(g + Y) * LOGTWO
+        tot += np.sum(mu * (Y - g) - th * mu**2 - th * var) / 2.0
+        return float(tot)
+    raise ValueError(lik.name)
+
+
+def AugmentedKL(lik, lv, y):
+    if lik.name == "logistic":  # logistic.jl:86-92
+        return PolyaGammaKL(np.ones_like(lv["c"]), lv["c"], lv["theta"])
+    if lik.name == "studentt":  # studentt.jl:121-127
+        a_p = lik.nu / 2.0
+        return GammaKL(lik.alpha, lv["c"], a_p, a_p * lik.sigma**2)
+    if lik.name == "gaussian":  # gaussian.jl:95
+        return 0.0
+    if lik.name == "logisticsoftmax":  # logisticsoftmax.jl:117-140
+        Y = y.T.astype(np.float64)
+        K = lik.n_class
+        pg = sum(PolyaGammaKL(Y[k] + lv["gamma"][k], lv["c"][k], lv["theta"][k]) for k in range(K))
+        psi = ssp.digamma(lv["alpha"])
+        po = sum(PoissonKL(lv["gamma"][k], lv["alpha"] / lv["beta"], psi - np.log(lv["beta"])) for k in range(K))
+        ge = (
+            -np.sum(lv["alpha"])
+            + math.log(lv["beta"][0])  # Q2
+            - np.sum(ssp.gammaln(lv["alpha"]))
+            - np.dot(1.0 - lv["alpha"], psi)
+        )
+        return float(pg + po + ge)
+    raise ValueError(lik.name)
+
+
+def GaussianKL(mu, mu0, Sigma, L):
+    """functions/KLdivergences.jl:11-18 (L = chol(K) lower)"""
+    logdetK = 2.0 * np.sum(np.log(np.diag(L)))
+    _, logdetS = np.linalg.slogdet(Sigma)
+    KinvS = sla.cho_solve((L, True), Sigma)
+    return float((logdetK - logdetS + np.trace(KinvS) + invquad(L, mu - mu0) - len(mu)) / 2.0)
+
+
+# --------------------------------------------------------------------------------------
+# Optimisers (inference/optimisers.jl, analyticVI.jl:44-52)
+# --------------------------------------------------------------------------------------
+@dataclass
+class RobbinsMonro:
+    """inference/optimisers.jl:1-19 : lr = (tau + n)^-kappa, n starts at 1 (Q9)."""
+
+    kappa: float = 0.51
+    tau: float = 1.0
+
+    def __post_init__(self):
+        if not (0.5 < self.kappa <= 1):
+            raise ValueError("kappa should be in the interval (0.5,1]")
+        if not self.tau > 0:
+            raise ValueError("tau should be positive")
+
+    def init(self):
+        return 1
+
+    def apply(self, st, delta):
+        return st + 1, delta * 1.0 / (self.tau + st) ** self.kappa
+
+
+@dataclass
+class AnalyticVI:
+    """inference/analyticVI.jl:1-52"""
+
+    eps: float = 1e-5
+    stoch: bool = False
+    batchsize: int = 0
+    optimiser: object = None  # RobbinsMonro for SVI; Descent(1.0) (lr = 1) otherwise
+    rho: float = 1.0
+    n_iter: int = 0
+    HyperParametersUpdated: bool = True
+
+
+def AnalyticSVI(nMinibatch, eps=1e-5, optimiser=None):
+    return AnalyticVI(eps=eps, stoch=True, batchsize=int(nMinibatch), optimiser=optimiser or RobbinsMonro())
+
+
+# --------------------------------------------------------------------------------------
+# gpblocks: SparseVarLatent (latentgp.jl:44-70, posterior.jl:21-37)
+# --------------------------------------------------------------------------------------
+class SparseVarLatent:
+    def __init__(self, Z, kernel: Kernel, mu0=None):
+        self.Z = np.array(Z, dtype=np.float64)
+        self.kernel = kernel
+        m = self.Z.shape[0]
+        self.dim = m
+        self.mu0 = np.zeros(m) if mu0 is None else np.asarray(mu0, dtype=np.float64)
+        self.mu = np.zeros(m)
+        self.Sigma = np.eye(m)
+        self.eta1 = np.zeros(m)
+        self.eta2 = -0.5 * np.eye(m)
+
+
+def compute_K(gp: SparseVarLatent, jitt):
+    """gpblocks/latentgp.jl:205-207 -> lower Cholesky factor"""
+    K = kernelmatrix(gp.kernel, gp.Z) + jitt * np.eye(gp.dim)
+    return np.linalg.cholesky(K)
+
+
+def compute_kappa(gp: SparseVarLatent, X, L, jitt):
+    """gpblocks/latentgp.jl:209-215"""
+    Knm = kernelmatrix(gp.kernel, X, gp.Z)
+    kappa = sla.cho_solve((L, True), Knm.T).T  # Knm / K
+    Ktilde = kernelmatrix_diag(gp.kernel, X) + jitt - diag_ABt(kappa, Knm)
+    if not np.all(Ktilde > 0):
+        raise FloatingPointError("K̃ has negative values")
+    return dict(Knm=Knm, kappa=kappa, Ktilde=Ktilde)
+
+
+def mean_f(gp, km):
+    """latentgp.jl:174-179"""
+    return km["kappa"] @ gp.mu
+
+
+def var_f(gp, km):
+    """latentgp.jl:184-189"""
+    return diag_ABt(km["kappa"] @ gp.Sigma, km["kappa"]) + km["Ktilde"]
+
+
+def global_update(gp):
+    """inference/inference.jl:25-28"""
+    gp.Sigma = -np.linalg.inv(gp.eta2) / 2.0
+    gp.Sigma = (gp.Sigma + gp.Sigma.T) / 2.0  # Σ is a `Symmetric` in the reference
+    gp.mu = gp.Sigma @ gp.eta1
+
+
+def _symmetric_upper(A):
+    """Julia `Symmetric(A)` reads the upper triangle (analyticVI.jl:238, Q5)."""
+    U = np.triu(A)
+    return U + np.triu(A, 1).T
+
+
+# --------------------------------------------------------------------------------------
+# Models
+# --------------------------------------------------------------------------------------
+class SVGP:
+    """models/SVGP.jl:22-80 with `optimiser=false, Zoptimiser=false` semantics."""
+
+    def __init__(self, kernel: Kernel, likelihood, inference: AnalyticVI, Z, mean=None, jitter=JITTER_F64):
+        self.likelihood = likelihood
+        self.inference = inference
+        self.jitter = jitter
+        self.f = [SparseVarLatent(Z, kernel, mean) for _ in range(likelihood.n_latent)]
+        self.trained = False
+
+    # -- states.jl:1-9,61-71
+    def init_state(self):
+        B = self.inference.batchsize
+        opt_state = [dict(t1=1, t2=1) for _ in self.f]
+        return dict(local_vars=init_local_vars(self.likelihood, B), opt_state=opt_state, kernel_matrices=None)
+
+    # -- training.jl:187-208
+    def compute_kernel_matrices(self, state, x, update=False):
+        inf = self.inference
+        if inf.HyperParametersUpdated or update:
+            kms = [dict(L=compute_K(gp, self.jitter)) for gp in self.f]
+        else:
+            kms = state["kernel_matrices"]
+        if inf.HyperParametersUpdated or inf.stoch or update:
+            kms = [{**km, **compute_kappa(gp, x, km["L"], self.jitter)} for gp, km in zip(self.f, kms)]
+        inf.HyperParametersUpdated = False
+        state["kernel_matrices"] = kms
+        return state
+
+    def moments(self, state):
+        kms = state["kernel_matrices"]
+        mu = np.stack([mean_f(gp, km) for gp, km in zip(self.f, kms)])
+        var = np.stack([var_f(gp, km) for gp, km in zip(self.f, kms)])
+        return mu, var
+
+    # -- analyticVI.jl:62-85
+    def variational_updates(self, state, y):
+        inf = self.inference
+        mu, var = self.moments(state)
+        lv = local_updates(state["local_vars"], self.likelihood, y, mu, var)
+        gmu = grad_E_mu(self.likelihood, y, lv)
+        gS = grad_E_Sigma(self.likelihood, y, lv)
+        self._natgrad_and_update(state, gmu, gS)
+        return state
+
+    def _natgrad_and_update(self, state, gmu, gS):
+        inf = self.inference
+        for k, (gp, km, os_) in enumerate(zip(self.f, state["kernel_matrices"], state["opt_state"])):
+            kappa, L = km["kappa"], km["L"]
+            # analyticVI.jl:160-180
+            d1 = kappa.T @ (inf.rho * gmu[k]) + sla.cho_solve((L, True), gp.mu0) - gp.eta1
+            Kinv = sla.cho_solve((L, True), np.eye(gp.dim))
+            d2 = -(rho_kdiagthetak(inf.rho, kappa, gS[k]) + Kinv / 2.0) - gp.eta2
+            # analyticVI.jl:229-246
+            if inf.stoch:
+                os_["t1"], D1 = inf.optimiser.apply(os_["t1"], d1)
+                os_["t2"], D2 = inf.optimiser.apply(os_["t2"], d2)
+                gp.eta1 = gp.eta1 + D1
+                gp.eta2 = _symmetric_upper(D2) + gp.eta2
+            else:
+                gp.eta1 = gp.eta1 + d1
+                gp.eta2 = _symmetric_upper(d2 + gp.eta2)
+            global_update(gp)
+
+    # -- training.jl:140-144
+    def update_parameters(self, state, x, y):
+        state = self.compute_kernel_matrices(state, x)
+        return self.variational_updates(state, y)
+
+    # -- analyticVI.jl:255-274
+    def ELBO(self, state, y):
+        inf = self.inference
+        mu, var = self.moments(state)
+        tot = inf.rho * expec_loglikelihood(self.likelihood, y, mu, var, state["local_vars"])
+        tot -= sum(GaussianKL(gp.mu, gp.mu0, gp.Sigma, km["L"]) for gp, km in zip(self.f, state["kernel_matrices"]))
+        tot -= inf.rho * AugmentedKL(self.likelihood, state["local_vars"], y)
+        return float(tot)
+
+    # -- functions/ELBO.jl:32-47
+    def ELBO_external(self, X, y):
+        y = treat_labels(y, self.likelihood)
+        state = dict(kernel_matrices=None)
+        state = self.compute_kernel_matrices(state, np.asarray(X, dtype=np.float64), update=True)
+        lv = init_local_vars(self.likelihood, len(X))
+        mu, var = self.moments(state)
+        state["local_vars"] = local_updates(lv, self.likelihood, y, mu, var)
+        return self.ELBO(state, y)
+
+
+def train(model, X, y, iterations=100, state=None, minibatches: Optional[Sequence[np.ndarray]] = None,
+          callback=None, rng=None):
+    """training/training.jl:13-111.  `minibatches[i]` = 0-based row indices of iteration i
+    (StatsBase.sample's RNG stream cannot be reproduced outside Julia: indices are injected)."""
+    if iterations <= 0:
+        raise ValueError("Number of iterations should be positive")
+    X = np.asarray(X, dtype=np.float64)
+    inf = model.inference
+    ydata = _wrap_y(model, y)
+    n = X.shape[0]
+    if inf.stoch:
+        if not (0 < inf.batchsize <= n):
+            raise ValueError("The size of mini-batch is incorrect")
+        inf.rho = n / inf.batchsize
+    else:
+        inf.batchsize = n
+    if state is None:
+        inf.HyperParametersUpdated = True
+        state = model.init_state()
+    rng = rng or np.random.default_rng(0)
+    for it in range(iterations):
+        if inf.stoch:
+            idx = minibatches[it] if minibatches is not None else rng.choice(n, inf.batchsize, replace=False)
+            x = X[idx]
+            yb = _view_y(ydata, idx)
+        else:
+            x, yb = X, ydata
+        state = model.update_parameters(state, x, yb)
+        state["y_batch"] = yb
+        model.trained = True
+        if callback is not None:
+            callback(model, state, inf.n_iter)
+        inf.n_iter += 1
+    return model, state
+
+
+def _wrap_y(model, y):
+    if isinstance(model, MOSVGP):
+        return [treat_labels(yt, l) for yt, l in zip(y, model.likelihoods)]
+    return treat_labels(y, model.likelihood)
+
+
+def _view_y(y, idx):
+    if isinstance(y, list):
+        return [yt[idx] for yt in y]
+    return y[idx]
+
+
+# --------------------------------------------------------------------------------------
+# MOSVGP (models/MOSVGP.jl, single_and_multi_output_utils.jl:24-84), A fixed (Aoptimiser=false)
+# --------------------------------------------------------------------------------------
+class MOSVGP:
+    """Each task has a single-latent likelihood (nf_per_task = 1).  A: (T, Q)."""
+
+    def __init__(self, kernels, likelihoods, inference: AnalyticVI, Zs, A, jitter=JITTER_F64):
+        self.likelihoods = list(likelihoods)
+        self.inference = inference
+        self.jitter = jitter
+        kernels = [kernels] if isinstance(kernels, Kernel) else list(kernels)
+        self.f = [SparseVarLatent(Z, kernels[i % len(kernels)]) for i, Z in enumerate(Zs)]
+        self.A = np.asarray(A, dtype=np.float64)
+        assert self.A.shape == (len(self.likelihoods), len(self.f))
+        self.trained = False
+
+    def init_state(self):
+        B = self.inference.batchsize
+        return dict(
+            local_vars=[init_local_vars(l, B) for l in self.likelihoods],
+            opt_state=[dict(t1=1, t2=1) for _ in self.f],
+            kernel_matrices=None,
+        )
+
+    compute_kernel_matrices = SVGP.compute_kernel_matrices
+    _natgrad_and_update = SVGP._natgrad_and_update
+
+    def latent_moments(self, state):
+        kms = state["kernel_matrices"]
+        mu_q = np.stack([mean_f(gp, km) for gp, km in zip(self.f, kms)])
+        var_q = np.stack([var_f(gp, km) for gp, km in zip(self.f, kms)])
+        return mu_q, var_q
+
+    def task_moments(self, state):
+        """single_and_multi_output_utils.jl:24-45"""
+        mu_q, var_q = self.latent_moments(state)
+        return self.A @ mu_q, (self.A**2) @ var_q, mu_q
+
+    def variational_updates(self, state, ys):
+        """analyticVI.jl:87-111 + single_and_multi_output_utils.jl:48-84"""
+        mu_t, var_t, mu_q = self.task_moments(state)
+        T, Q = self.A.shape
+        gm, gs = [], []
+        for t, l in enumerate(self.likelihoods):
+            lv = local_updates(state["local_vars"][t], l, ys[t], mu_t[t : t + 1], var_t[t : t + 1])
+            gm.append(grad_E_mu(l, ys[t], lv)[0])
+            gs.append(grad_E_Sigma(l, ys[t], lv)[0])
+        gmu = np.zeros_like(mu_q)
+        gS = np.zeros_like(mu_q)
+        for t in range(T):
+            for q in range(Q):
+                others = mu_t[t] - self.A[t, q] * mu_q[q]
+                gmu[q] += self.A[t, q] * (gm[t] - 2.0 * gs[t] * others)
+                gS[q] += self.A[t, q] ** 2 * gs[t]
+        self._natgrad_and_update(state, gmu, gS)
+        return state
+
+    def update_parameters(self, state, x, ys):
+        state = self.compute_kernel_matrices(state, x)
+        return self.variational_updates(state, ys)
+
+    def ELBO(self, state, ys):
+        """analyticVI.jl:277-297"""
+        inf = self.inference
+        mu_t, var_t, _ = self.task_moments(state)
+        tot = 0.0
+        for t, l in enumerate(self.likelihoods):
+            tot += inf.rho * expec_loglikelihood(l, ys[t], mu_t[t : t + 1], var_t[t : t + 1], state["local_vars"][t])
+            tot -= inf.rho * AugmentedKL(l, state["local_vars"][t], ys[t])
+        tot -= sum(GaussianKL(gp.mu, gp.mu0, gp.Sigma, km["L"]) for gp, km in zip(self.f, state["kernel_matrices"]))
+        return float(tot)
+
+
+# --------------------------------------------------------------------------------------
+# Predictions (training/predictions.jl)
+# --------------------------------------------------------------------------------------
+_GH_X, _GH_W = np.polynomial.hermite.hermgauss(100)
+PRED_NODES = _GH_X * math.sqrt(2.0)  # predictions.jl:4
+PRED_WEIGHTS = _GH_W / math.sqrt(math.pi)
+
+
+def predict_f(model, X_test, cov=True):
+    """predictions.jl:25-50 (diag=true).  Returns (K, N*) arrays of latent moments."""
+    X_test = np.asarray(X_test, dtype=np.float64)
+    mus, vars_ = [], []
+    for gp in model.f:
+        L = compute_K(gp, model.jitter)
+        ks = kernelmatrix(gp.kernel, X_test, gp.Z)
+        mus.append(ks @ sla.cho_solve((L, True), gp.mu))
+        if cov:
+            m = gp.dim
+            SK = sla.cho_solve((L, True), gp.Sigma.T).T  # Σ / K
+            A = sla.cho_solve((L, True), np.eye(m) - SK)
+            vars_.append(kernelmatrix_diag(gp.kernel, X_test) + model.jitter - diag_ABt(ks @ A, ks))
+    mu = np.stack(mus)
+    if isinstance(model, MOSVGP):
+        mu_t = model.A @ mu
+        if not cov:
+            return mu_t
+        return mu_t, (model.A**2) @ np.stack(vars_)
+    return (mu, np.stack(vars_)) if cov else mu
+
+
+def predict_y(model, X_test):
+    """predictions.jl:178-198; classification.jl:47; regression.jl:17"""
+    mu = predict_f(model, X_test, cov=False)
+    if isinstance(model, MOSVGP):
+        return [_predict_y_lik(l, mu[t : t + 1]) for t, l in enumerate(model.likelihoods)]
+    return _predict_y_lik(model.likelihood, mu)
+
+
+def _predict_y_lik(lik, mu):
+    if lik.name == "logistic":
+        return mu[0] > 0
+    if lik.name == "logisticsoftmax":
+        am = np.argmax(mu, axis=0)
+        return np.array([lik.class_mapping[i] for i in am])
+    return mu[0]
+
+
+def compute_proba(lik, mu, var):
+    if lik.name == "logistic":  # classification.jl:14-26
+        sd = np.sqrt(np.maximum(var[0], 0.0))
+        x = PRED_NODES[None, :] * sd[:, None] + mu[0][:, None]
+        p = logistic(x)
+        pred = p @ PRED_WEIGHTS
+        v = np.maximum((p**2) @ PRED_WEIGHTS - pred**2, 0.0)
+        return pred, v
+    if lik.name == "gaussian":  # gaussian.jl:41-45
+        return mu[0], var[0] + lik.sigma2
+    if lik.name == "studentt":  # studentt.jl:57-61
+        return mu[0], np.maximum(var[0], 0.0) + lik.nu * lik.sigma**2 / (2.0 * (lik.nu / 2.0 - 1.0))
+    if lik.name == "logisticsoftmax":  # multiclass.jl:96-117 (variance unused) ; logisticsoftmax.jl:28-30
+        s = logistic(mu)
+        return s / np.sum(s, axis=0, keepdims=True)
+    raise ValueError(lik.name)
+
+
+def proba_y(model, X_test):
+    """predictions.jl:231-246"""
+    mu, var = predict_f(model, X_test, cov=True)
+    if isinstance(model, MOSVGP):
+        return [compute_proba(l, mu[t : t + 1], var[t : t + 1]) for t, l in enumerate(model.likelihoods)]
+    return compute_proba(model.likelihood, mu, var)

@@ -1,0 +1,28 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def agp():
+    # building is part of "does it build"; the .so normally already exists in-tree
+    sys.path.insert(0, os.path.join(ROOT, "augmentedgaussianprocesses.jl_b200"))
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("agp_build", os.path.join(ROOT, "augmentedgaussianprocesses.jl_b200", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.build()
+    import agp_b200
+
+    return agp_b200

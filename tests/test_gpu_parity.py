@@ -1,0 +1,134 @@
+"""GPU parity tests: the CUDA engine (through the C ABI) against the fp64 oracle on identical seeded inputs.
+
+Tolerances (stated per precision mode):
+  f64    : 1e-8  relative (same algorithm in fp64; differences are summation order only)
+  f32    : 2e-4  relative on mu / Sigma / ELBO (fp32 contractions, fp64 m x m tail)
+  tf32x3 : 2e-4  relative (3xTF32 error-compensated tensor-core contractions, fp64 tail)
+"""
+import numpy as np
+import pytest
+
+import agp_oracle as O
+from problems import engine_kernel, engine_lik, make_data, oracle_kernel, oracle_lik, rel_fro
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"f64": 1e-8, "f32": 2e-4, "tf32x3": 2e-4}
+
+
+def run_pair(agp, lik, precision, n=600, D=3, m=24, B=128, iters=8, kind="sqexp", scale=None, variance=1.0, stoch=True,
+             n_class=3, seed=0):
+    scale = scale if scale is not None else 1.0 / np.sqrt(D)
+    X, y, Z, mbs, F, rng = make_data(lik, n, D, m, B, iters, seed=seed, n_class=n_class)
+    inf_o = O.AnalyticSVI(B) if stoch else O.AnalyticVI()
+    mo = O.SVGP(oracle_kernel(O, kind, scale, variance), oracle_lik(O, lik, n_class), inf_o, Z)
+    mo, so = O.train(mo, X, y, iters, minibatches=mbs)
+    inf_e = agp.AnalyticSVI(B) if stoch else agp.AnalyticVI()
+    me = agp.SVGP(engine_kernel(agp, kind, scale, variance), engine_lik(agp, lik, n_class), inf_e, Z, precision=precision)
+    me, se = agp.train(me, X, y, iters, minibatches=mbs)
+    return (mo, so), (me, se), (X, y, F)
+
+
+def check_pair(agp, oracle, engine, tol):
+    (mo, so), (me, se) = oracle, engine
+    for q, gp in enumerate(mo.f):
+        mu, S, e1, e2 = me.posterior(q)
+        assert rel_fro(mu, gp.mu) < tol, ("mu", q, rel_fro(mu, gp.mu))
+        assert rel_fro(S, gp.Sigma) < tol, ("Sigma", q, rel_fro(S, gp.Sigma))
+        assert rel_fro(e1, gp.eta1) < tol, ("eta1", q)
+        assert rel_fro(e2, gp.eta2) < tol, ("eta2", q)
+    elbo_o = mo.ELBO(so, so["y_batch"])
+    elbo_e = agp.ELBO(me, se)
+    assert abs(elbo_e - elbo_o) <= tol * max(1.0, abs(elbo_o)) * 5, (elbo_e, elbo_o)
+
+
+@pytest.mark.parametrize("lik", ["gaussian", "logistic", "studentt", "logisticsoftmax"])
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_svi_parity(agp, lik, precision):
+    oracle, engine, _ = run_pair(agp, lik, precision)
+    check_pair(agp, oracle, engine, TOL[precision])
+
+
+@pytest.mark.parametrize("kind", ["matern32", "matern52"])
+def test_matern_kernels(agp, kind):
+    oracle, engine, _ = run_pair(agp, "studentt", "f64", kind=kind, variance=2.0)
+    check_pair(agp, oracle, engine, TOL["f64"])
+
+
+@pytest.mark.parametrize("lik", ["gaussian", "logistic"])
+def test_full_batch_avi(agp, lik):
+    oracle, engine, _ = run_pair(agp, lik, "f64", n=200, B=200, iters=4, stoch=False)
+    check_pair(agp, oracle, engine, TOL["f64"])
+
+
+def test_local_vars_and_kernel_matrices(agp):
+    (mo, so), (me, se), _ = run_pair(agp, "logistic", "f64", iters=3)
+    km = se.kernel_matrices(0)
+    ko = so["kernel_matrices"][0]
+    assert rel_fro(km["Knm"], ko["Knm"]) < 1e-10
+    assert rel_fro(km["kappa"], ko["kappa"]) < 1e-8
+    assert rel_fro(km["Ktilde"], ko["Ktilde"]) < 1e-7
+    assert rel_fro(se.local("c"), so["local_vars"]["c"]) < 1e-8
+    assert rel_fro(se.local("theta"), so["local_vars"]["theta"]) < 1e-8
+    assert se.opt_state["state_eta1"] == so["opt_state"][0]["t1"]
+
+
+def test_predictions(agp):
+    (mo, so), (me, se), (X, y, F) = run_pair(agp, "logistic", "f64", iters=10)
+    Xt = X[:300]
+    mu_o, var_o = O.predict_f(mo, Xt, cov=True)
+    mu_e, var_e = agp.predict_f(me, Xt, cov=True)
+    assert rel_fro(mu_e, mu_o[0]) < 1e-8 and rel_fro(var_e, var_o[0]) < 1e-7
+    assert np.array_equal(agp.predict_y(me, Xt), O.predict_y(mo, Xt))
+    p_o, v_o = O.proba_y(mo, Xt)
+    p_e, v_e = agp.proba_y(me, Xt)
+    assert rel_fro(p_e, p_o) < 1e-8 and np.all(v_e >= 0) and np.allclose(v_e, v_o, atol=1e-10)
+    # testconv threshold of the reference (test/testingtools.jl:223-253): classification error < 0.5
+    assert np.mean(agp.predict_y(me, X) != (y > 0)) < 0.5
+
+
+def test_multiclass_predict(agp):
+    (mo, so), (me, se), (X, y, F) = run_pair(agp, "logisticsoftmax", "f64", iters=10, n_class=4)
+    assert np.array_equal(agp.predict_y(me, X[:200]), O.predict_y(mo, X[:200]))
+    assert np.mean(agp.predict_y(me, X) != y) < 0.9
+    assert rel_fro(agp.proba_y(me, X[:50]), O.proba_y(mo, X[:50])) < 1e-8
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_mosvgp_parity(agp, precision):
+    n, D, m, B, iters, Q = 500, 3, 20, 100, 6, 3
+    X, _, Z, mbs, F, rng = make_data("mo", n, D, m, B, iters, seed=3, n_task=Q)
+    ys = [np.sign(F[:, 0] + 1e-3), F[:, 1] + 0.1 * rng.standard_normal(n), F[:, 2] + 0.1 * rng.standard_t(3.0, n)]
+    A = rng.standard_normal((Q, Q))
+    A /= np.linalg.norm(A, axis=1, keepdims=True)
+    Zs = [X[rng.permutation(n)[:m]].copy() for _ in range(Q)]
+    sc = 1.0 / np.sqrt(D)
+    mo = O.MOSVGP(O.Kernel("sqexp", scale=sc), [O.LogisticLikelihood(), O.GaussianLikelihood(1e-2), O.StudentTLikelihood(3.0)],
+                  O.AnalyticSVI(B), Zs, A)
+    mo, so = O.train(mo, X, ys, iters, minibatches=mbs)
+    me = agp.MOSVGP(agp.SqExponentialKernel() @ agp.ScaleTransform(sc),
+                    [agp.LogisticLikelihood(), agp.GaussianLikelihood(1e-2), agp.StudentTLikelihood(3.0)], agp.AnalyticSVI(B), Zs,
+                    A=A, precision=precision)
+    me, se = agp.train(me, X, ys, iters, minibatches=mbs)
+    check_pair(agp, (mo, so), (me, se), TOL[precision])
+    mu_o = O.predict_f(mo, X[:100], cov=False)
+    mu_e = agp.predict_f(me, X[:100])
+    assert rel_fro(np.stack(mu_e), mu_o) < TOL[precision] * 10
+
+
+def test_ktilde_error_and_checkpoint(agp):
+    # an indefinite K_mm (negative "jitter") must make the Cholesky fail loudly (PosDefException in the reference)
+    X, y, Z, mbs, F, rng = make_data("gaussian", 200, 2, 8, 50, 2)
+    me = agp.SVGP(agp.SqExponentialKernel(), agp.GaussianLikelihood(1e-2), agp.AnalyticSVI(50), Z, precision="f64")
+    me.jitter = -0.9
+    with pytest.raises(agp.PosDefException):
+        agp.train(me, X, y, 1, minibatches=mbs)
+    # re-entry with state (train!(...; state)) continues the Robbins-Monro schedule
+    mo = O.SVGP(O.Kernel("sqexp"), O.GaussianLikelihood(1e-2), O.AnalyticSVI(50), Z)
+    mo, so = O.train(mo, X, y, 2, minibatches=mbs)
+    mo, so = O.train(mo, X, y, 2, minibatches=mbs, state=so)
+    m2 = agp.SVGP(agp.SqExponentialKernel(), agp.GaussianLikelihood(1e-2), agp.AnalyticSVI(50), Z, precision="f64")
+    m2, s2 = agp.train(m2, X, y, 2, minibatches=mbs)
+    m2, s2 = agp.train(m2, X, y, 2, minibatches=mbs, state=s2)
+    assert rel_fro(m2.posterior(0)[0], mo.f[0].mu) < 1e-8
+    assert s2.opt_state["state_eta1"] == 5
