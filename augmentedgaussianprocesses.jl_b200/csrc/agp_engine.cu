@@ -48,7 +48,7 @@ enum Phase {
   PH_IDX = 0, PH_KMAT, PH_KAPPA, PH_KSIGMA, PH_ROWSTATS, PH_LIK, PH_GRADMU, PH_GRAM, PH_COMBINE, PH_CHOL, PH_TRTRI,
   PH_SIGMA, PH_FINAL, PH_SPLIT, PH_COUNT
 };
-static const char* kPhaseNames[PH_COUNT] = {"idx_select",  "kmat_knm",   "gemm_kappa", "gemm_kappa_sigma", "rowstats",
+static const char* kPhaseNames[PH_COUNT] = {"idx_select",  "kmat_knm",   "gemm_v",     "gemm_v_sigma", "rowstats",
                                             "lik_update",  "gemv_grad1", "gemm_gram",  "combine_eta",      "chol_blocked",
                                             "trtri",       "gemm_sigma", "finalize",   "tf32_split"};
 
@@ -101,25 +101,32 @@ struct Engine : EngineBase {
   bool is_lsm = false;
   int R = 1;  // rows of the local-variable arrays
 
+  // One latent GP.  The device works in the WHITENED basis u = L v (K = L L^T):
+  //   V = Knm L^-T,  mu = L mu_v,  Sigma = L Sigma_v L^T,  eta1_v = L^T eta1,  eta2_v = L^T eta2 L.
+  // It is the same iteration as the reference's (every map is linear), but the prior precision becomes I
+  // and P_v = -2 eta2_v >= lr*I, so fp32 / TF32 contractions lose sqrt(cond K) digits instead of cond K.
+  // The canonical (mu, Sigma, eta1, eta2) are produced on request (get_posterior) in fp64.
   struct Latent {
     int kind; double scale, variance;
     std::vector<double> hZ, hmu0;
     bool has_mu0 = false;
-    T* Z = nullptr; T* zz = nullptr;            // [m][Dp], [m]
+    T* Z = nullptr; T* zz = nullptr;              // [m][Dp], [m]
     double* Zd = nullptr; double* zzd = nullptr;  // fp64 copies for K_mm
-    double *Kinv = nullptr, *Kinv_mu0 = nullptr, *mu0 = nullptr;
-    T* Kinv_T = nullptr;
+    double *Lc = nullptr, *Linv = nullptr, *Kinv = nullptr;  // chol(K) lower, its inverse, K^-1   [mp][mp]
+    double *mu0 = nullptr, *mu0v = nullptr;                  // prior mean at Z, L^-1 mu0
+    T* Linv_T = nullptr;
     double logdetK = 0.0;
-    double *eta1 = nullptr, *eta2 = nullptr, *mu = nullptr, *Sigma = nullptr;
-    T* Sigma_T = nullptr;
-    T *Knm = nullptr, *kappa = nullptr, *KS = nullptr;
+    double *eta1c = nullptr, *eta2c = nullptr;               // canonical natural parameters (valid when !white_valid or after sync)
+    double *eta1v = nullptr, *eta2v = nullptr, *muv = nullptr, *SigmaV = nullptr;  // whitened state
+    bool white_valid = false;                                // whitened state is the live one
+    T* SigmaV_T = nullptr;
+    T *Knm = nullptr, *V = nullptr, *VS = nullptr;           // [Bcap][ldm]
     double* Ktilde = nullptr;
     T* Gpart = nullptr;
     double* v1 = nullptr;
     double *P = nullptr, *X = nullptr, *W = nullptr;  // tail workspaces [mp][mp]
-    double* logdetP = nullptr;                        // device scalar (+1 scratch for K)
-    // tcgen05 path: hi/lo TF32 splits
-    UmmaLatent um;
+    double* logdetP = nullptr;                        // device scalars: [0] logdet P_v, [1] scratch for K
+    UmmaLatent um;                                    // tcgen05 path: hi/lo TF32 splits
   };
   std::vector<Latent> lat;
 
@@ -128,7 +135,8 @@ struct Engine : EngineBase {
   T* X = nullptr; T* xx = nullptr;
   double* y_all = nullptr; int* ycls_all = nullptr;
   T* Xb = nullptr; T* xxb = nullptr;  // host-batch path
-  T *pKnm = nullptr, *pKS = nullptr, *pA = nullptr;  // prediction scratch (keeps the step state intact)
+  T *pKS = nullptr, *pXb = nullptr, *pxxb = nullptr;  // scratch: kappa getter, prediction input rows
+  bool kernel_matrices_stale = false;  // predict_f reused Knm / V / VS: recompute them before the next ELBO
   void* stage = nullptr; size_t stage_bytes = 0;
   int64_t* idx_pool = nullptr; int64_t n_lists = 0; int pool_B = 0;
   int64_t* idx_cur = nullptr;
@@ -246,22 +254,21 @@ struct Engine : EngineBase {
       if (d->mu0) { L.hmu0.assign(d->mu0 + (size_t)q * m, d->mu0 + (size_t)(q + 1) * m); L.has_mu0 = true; }
       CKS(dalloc(&L.Z, (size_t)m * Dp)); CKS(dalloc(&L.zz, m));
       CKS(dalloc(&L.Zd, (size_t)m * Dp)); CKS(dalloc(&L.zzd, m));
-      CKS(dalloc(&L.Kinv, (size_t)mp * mp)); CKS(dalloc(&L.Kinv_mu0, mp)); CKS(dalloc(&L.mu0, mp));
-      CKS(dalloc(&L.Kinv_T, (size_t)m * ldm));
-      CKS(dalloc(&L.eta1, mp)); CKS(dalloc(&L.eta2, (size_t)mp * mp)); CKS(dalloc(&L.mu, mp)); CKS(dalloc(&L.Sigma, (size_t)mp * mp));
-      CKS(dalloc(&L.Sigma_T, (size_t)m * ldm));
-      CKS(dalloc(&L.Knm, (size_t)Bcap * ldm)); CKS(dalloc(&L.kappa, (size_t)Bcap * ldm)); CKS(dalloc(&L.KS, (size_t)Bcap * ldm));
+      CKS(dalloc(&L.Lc, (size_t)mp * mp)); CKS(dalloc(&L.Linv, (size_t)mp * mp)); CKS(dalloc(&L.Kinv, (size_t)mp * mp));
+      CKS(dalloc(&L.mu0, mp)); CKS(dalloc(&L.mu0v, mp));
+      CKS(dalloc(&L.Linv_T, (size_t)m * ldm));
+      CKS(dalloc(&L.eta1c, mp)); CKS(dalloc(&L.eta2c, (size_t)mp * mp));
+      CKS(dalloc(&L.eta1v, mp)); CKS(dalloc(&L.eta2v, (size_t)mp * mp)); CKS(dalloc(&L.muv, mp)); CKS(dalloc(&L.SigmaV, (size_t)mp * mp));
+      CKS(dalloc(&L.SigmaV_T, (size_t)m * ldm));
+      CKS(dalloc(&L.Knm, (size_t)Bcap * ldm)); CKS(dalloc(&L.V, (size_t)Bcap * ldm)); CKS(dalloc(&L.VS, (size_t)Bcap * ldm));
       CKS(dalloc(&L.Ktilde, ldB));
       CKS(dalloc(&L.Gpart, (size_t)n_split * m * ldm));
       CKS(dalloc(&L.v1, mp));
       CKS(dalloc(&L.P, (size_t)mp * mp)); CKS(dalloc(&L.X, (size_t)mp * mp)); CKS(dalloc(&L.W, (size_t)mp * mp));
       CKS(dalloc(&L.logdetP, 2));
-      // posterior init (gpblocks/posterior.jl:29-37): mu = 0, Sigma = I, eta1 = 0, eta2 = -I/2
-      dim3 g((mp + 127) / 128, mp);
-      set_identity_kernel<<<g, 128, 0, st()>>>(L.Sigma, mp, mp, 1.0);
-      set_identity_kernel<<<g, 128, 0, st()>>>(L.eta2, mp, mp, -0.5);
-      shadow_kernel<T><<<dim3((m + 127) / 128, m), 128, 0, st()>>>(L.Sigma, mp, m, L.Sigma_T, ldm);
-      launches += 3;
+      // posterior init (gpblocks/posterior.jl:29-37): mu = 0, Sigma = I, eta1 = 0, eta2 = -I/2 (canonical; whitened at refresh_K)
+      set_identity_kernel<<<dim3((mp + 127) / 128, mp), 128, 0, st()>>>(L.eta2c, mp, mp, -0.5);
+      ++launches;
       // inducing points
       std::vector<double> zp((size_t)m * Dp, 0.0), zn(m, 0.0);
       std::vector<T> zt((size_t)m * Dp, T(0)), znt(m, T(0));
@@ -323,12 +330,12 @@ struct Engine : EngineBase {
     for (auto e : ev_pool) cudaEventDestroy(e);
     if (gexec) cudaGraphExecDestroy(gexec);
     for (auto& L : lat) {
-      void* ps[] = {L.Z, L.zz, L.Zd, L.zzd, L.Kinv, L.Kinv_mu0, L.mu0, L.Kinv_T, L.eta1, L.eta2, L.mu, L.Sigma, L.Sigma_T,
-                    L.Knm, L.kappa, L.KS, L.Ktilde, L.Gpart, L.v1, L.P, L.X, L.W, L.logdetP};
+      void* ps[] = {L.Z, L.zz, L.Zd, L.zzd, L.Lc, L.Linv, L.Kinv, L.mu0, L.mu0v, L.Linv_T, L.eta1c, L.eta2c, L.eta1v, L.eta2v,
+                    L.muv, L.SigmaV, L.SigmaV_T, L.Knm, L.V, L.VS, L.Ktilde, L.Gpart, L.v1, L.P, L.X, L.W, L.logdetP};
       for (void* p : ps) cudaFree(p);
       umma_latent_free(L.um);
     }
-    void* ps[] = {pKnm, pKS, pA, X, xx, y_all, ycls_all, Xb, xxb, stage, idx_pool, idx_cur, counters, status, d_lik_kind, d_p0, d_p1, d_A,
+    void* ps[] = {pKS, pXb, pxxb, X, xx, y_all, ycls_all, Xb, xxb, stage, idx_pool, idx_cur, counters, status, d_lik_kind, d_p0, d_p1, d_A,
                   mean_f, var_f, gmu, gS, lc, ltheta, lgamma_, lalpha, tmu, tvar, gm, gs, yb, ycls, d_out};
     for (void* p : ps) cudaFree(p);
   }
@@ -468,26 +475,66 @@ struct Engine : EngineBase {
     ph_end();
   }
 
+  // ---- small fp64 m x m helpers (off the hot path) ------------------------------------------------------
+  void dgemm(bool at, bool bt, const double* A, const double* B, double* Cc, double alpha, double beta) {
+    GemmParams<double> g{};
+    g.A = A; g.lda = mp; g.B = B; g.ldb = mp; g.C = Cc; g.ldc = mp; g.M = mp; g.N = mp; g.K = mp; g.alpha = alpha; g.beta = beta;
+    if (!at && !bt) gemm_simt_launch<double, false, false, EPI_PLAIN>(g, 1, st());
+    else if (!at && bt) gemm_simt_launch<double, false, true, EPI_PLAIN>(g, 1, st());
+    else gemm_simt_launch<double, true, true, EPI_PLAIN>(g, 1, st());
+    ++launches;
+  }
+  dim3 grid_mp() const { return dim3((mp + 127) / 128, mp); }
+
+  // whitened -> canonical natural parameters: eta1 = L^-T eta1_v, eta2 = L^-T eta2_v L^-1   (X = L^-1)
+  void canonicalize(Latent& L) {
+    matvec_t_kernel<<<(mp + 127) / 128, 128, 0, st()>>>(L.Linv, mp, mp, L.eta1v, L.eta1c);
+    ++launches;
+    dgemm(false, true, L.eta2v, L.Linv, L.W, 1.0, 0.0);   // W = eta2_v * X
+    dgemm(true, true, L.Linv, L.W, L.eta2c, 1.0, 0.0);    // eta2 = X^T * W
+  }
+  // canonical -> whitened: eta1_v = L^T eta1, P_v = L^T (-2 eta2) L, then Sigma_v = P_v^-1, mu_v = Sigma_v eta1_v
+  int whiten(Latent& L) {
+    matvec_t_kernel<<<(mp + 127) / 128, 128, 0, st()>>>(L.Lc, mp, mp, L.eta1c, L.eta1v);
+    ++launches;
+    dgemm(false, true, L.eta2c, L.Lc, L.W, 1.0, 0.0);     // W = eta2 * L
+    dgemm(true, true, L.Lc, L.W, L.eta2v, 1.0, 0.0);      // eta2_v = L^T * W
+    scale_pad_kernel<<<grid_mp(), 128, 0, st()>>>(L.eta2v, L.P, mp, m, mp, -2.0);
+    ++launches;
+    CK(cudaMemsetAsync(L.logdetP, 0, sizeof(double), st()));
+    CKS(eta_to_moments(L));
+    L.white_valid = true;
+    return AGP_OK;
+  }
+
   int refresh_K() override {
     for (auto& L : lat) {
+      if (L.white_valid) { canonicalize(L); L.white_valid = false; }  // K changes: carry the posterior over in canonical form
       // K_mm in fp64 (GEMM form of the squared distance is exact enough in fp64), then the exact diagonal
       GemmParams<double> g{};
       g.A = L.Zd; g.lda = Dp; g.B = L.Zd; g.ldb = Dp; g.C = L.P; g.ldc = mp; g.M = m; g.N = m; g.K = D;
       g.alpha = 1.0; g.xx = L.zzd; g.zz = L.zzd; g.scale2 = L.scale * L.scale; g.variance = L.variance; g.kernel_kind = L.kind;
       gemm_simt_launch<double, false, false, EPI_KERNELFN>(g, 1, st());
-      kmm_fix_kernel<<<dim3((mp + 127) / 128, mp), 128, 0, st()>>>(L.P, mp, m, mp, L.variance + jitter);
+      kmm_fix_kernel<<<grid_mp(), 128, 0, st()>>>(L.P, mp, m, mp, L.variance + jitter);
       launches += 2;
       CK(cudaMemsetAsync(L.logdetP + 1, 0, sizeof(double), st()));
       spd_inverse(L.P, L.X, L.W, L.Kinv, L.logdetP + 1);
-      symmetrize_shadow_kernel<T><<<dim3((m + 127) / 128, m), 128, 0, st()>>>(L.Kinv, mp, m, L.Kinv_T, ldm);
-      symv_kernel<<<(m * 32 + 255) / 256, 256, 0, st()>>>(L.Kinv, mp, m, L.mu0, L.Kinv_mu0);
-      launches += 2;
+      copy_lower_kernel<<<grid_mp(), 128, 0, st()>>>(L.P, L.Lc, mp, mp);
+      copy_lower_kernel<<<grid_mp(), 128, 0, st()>>>(L.X, L.Linv, mp, mp);
+      symmetrize_shadow_kernel<T><<<dim3((m + 127) / 128, m), 128, 0, st()>>>(L.Kinv, mp, m, (T*)nullptr, ldm);
+      shadow_kernel<T><<<dim3((m + 127) / 128, m), 128, 0, st()>>>(L.Linv, mp, m, L.Linv_T, ldm);
+      symv_kernel<<<(m * 32 + 255) / 256, 256, 0, st()>>>(L.Linv, mp, m, L.mu0, L.mu0v);  // L^-1 mu0
+      launches += 5;
       CK(cudaMemcpyAsync(&L.logdetK, L.logdetP + 1, sizeof(double), cudaMemcpyDeviceToHost, st()));
-      if (prec == AGP_PREC_TF32X3) { CKS(umma_split_matrix(ctx_err(), L.um, UM_KINV, (const float*)(const void*)L.Kinv_T, m, st())); ++launches; }
+      if (prec == AGP_PREC_TF32X3) { CKS(umma_split_matrix(ctx_err(), L.um, UM_LINV, (const float*)(const void*)L.Linv_T, m, st())); ++launches; }
+      int s0 = sync_status();   // a failed Cholesky of K must not be hidden by the next factorisation
+      if (s0 != AGP_OK) { have_K = false; return s0; }
+      CKS(whiten(L));
     }
     CK(cudaGetLastError());
     int s = sync_status();
-    if (s == AGP_OK) have_K = true;
+    have_K = (s == AGP_OK);
+    drop_graph();
     return s;
   }
 
@@ -526,11 +573,11 @@ struct Engine : EngineBase {
     return AGP_OK;
   }
 
-  // kernel matrices + predictive moments of the owned latents for the current minibatch
-  int moments_impl(bool from_batch, int B, bool fresh_kernel_matrices) {
-    const T* Xsrc = from_batch ? Xb : X;
-    const T* xsrc = from_batch ? xxb : xx;
-    const int64_t* gather = from_batch ? nullptr : idx_cur;
+  // kernel matrices + predictive moments of the owned latents for B rows of Xsrc (gathered through `gather` when given).
+  // Also the whole of _predict_f (training/predictions.jl:25-50): mu* = k* (K \ mu) = V* mu_v and
+  // sigma2* = kdiag + jitter - diag(k* A k*^T) = Ktilde* + rowsum((V* Sigma_v) .* V*).
+  int moments_rows(const T* Xsrc, const T* xsrc, const int64_t* gather, int B, bool fresh_kernel_matrices, double* mean_out,
+                   double* var_out, int64_t out_ld, bool need_var) {
     for (int q = 0; q < Ql; ++q) {
       Latent& L = lat[q];
       if (fresh_kernel_matrices) {
@@ -544,36 +591,43 @@ struct Engine : EngineBase {
         ph_end();
         if (prec == AGP_PREC_TF32X3) {
           ph_begin(PH_SPLIT); CKS(umma_split_matrix(ctx_err(), L.um, UM_KNM, (const float*)(const void*)L.Knm, B, st())); ++launches; ph_end();
-          ph_begin(PH_KAPPA); CKS(umma_gemm_nt(ctx_err(), L.um, UM_KNM, UM_KINV, (float*)(void*)L.kappa, B, m, st())); ++launches; ph_end();
-          ph_begin(PH_SPLIT); CKS(umma_split_matrix(ctx_err(), L.um, UM_KAPPA, (const float*)(const void*)L.kappa, B, st())); ++launches; ph_end();
+          ph_begin(PH_KAPPA); CKS(umma_gemm_nt(ctx_err(), L.um, UM_KNM, UM_LINV, (float*)(void*)L.V, B, m, st())); ++launches; ph_end();
+          ph_begin(PH_SPLIT); CKS(umma_split_matrix(ctx_err(), L.um, UM_V, (const float*)(const void*)L.V, B, st())); ++launches; ph_end();
         } else {
           ph_begin(PH_KAPPA);
-          GemmParams<T> k{};  // kappa = Knm / K (latentgp.jl:211) as Knm * K^-1 with the cached inverse
-          k.A = L.Knm; k.lda = ldm; k.B = L.Kinv_T; k.ldb = ldm; k.C = L.kappa; k.ldc = ldm; k.M = B; k.N = m; k.K = m; k.alpha = 1.0;
+          GemmParams<T> k{};  // V = Knm L^-T  (the whitened kappa of latentgp.jl:211); L^-1 is lower triangular
+          k.A = L.Knm; k.lda = ldm; k.B = L.Linv_T; k.ldb = ldm; k.C = L.V; k.ldc = ldm; k.M = B; k.N = m; k.K = m; k.alpha = 1.0;
+          k.k_to_diag = 1;
           gemm_simt_launch<T, false, false, EPI_PLAIN>(k, 1, st());
           ++launches;
           ph_end();
         }
       }
-      ph_begin(PH_KSIGMA);
-      if (prec == AGP_PREC_TF32X3) {
-        CKS(umma_gemm_nt(ctx_err(), L.um, UM_KAPPA, UM_SIGMA, (float*)(void*)L.KS, B, m, st()));
-      } else {
-        GemmParams<T> s{};  // kappa * Sigma (latentgp.jl:189)
-        s.A = L.kappa; s.lda = ldm; s.B = L.Sigma_T; s.ldb = ldm; s.C = L.KS; s.ldc = ldm; s.M = B; s.N = m; s.K = m; s.alpha = 1.0;
-        gemm_simt_launch<T, false, false, EPI_PLAIN>(s, 1, st());
+      if (need_var) {
+        ph_begin(PH_KSIGMA);
+        if (prec == AGP_PREC_TF32X3) {
+          CKS(umma_gemm_nt(ctx_err(), L.um, UM_V, UM_SIGMA, (float*)(void*)L.VS, B, m, st()));
+        } else {
+          GemmParams<T> s{};  // V Sigma_v  (kappa * Sigma of latentgp.jl:189)
+          s.A = L.V; s.lda = ldm; s.B = L.SigmaV_T; s.ldb = ldm; s.C = L.VS; s.ldc = ldm; s.M = B; s.N = m; s.K = m; s.alpha = 1.0;
+          gemm_simt_launch<T, false, false, EPI_PLAIN>(s, 1, st());
+        }
+        ++launches;
+        ph_end();
       }
-      ++launches;
-      ph_end();
       ph_begin(PH_ROWSTATS);
-      rowstats_kernel<T><<<(B * 32 + 255) / 256, 256, 0, st()>>>(L.Knm, L.kappa, L.KS, L.mu, B, m, ldm, L.variance + jitter, L.Ktilde,
-                                                                 mean_f + (size_t)(qbeg + q) * ldB, var_f + (size_t)(qbeg + q) * ldB,
+      rowstats_kernel<T><<<(B * 32 + 255) / 256, 256, 0, st()>>>(L.V, need_var ? L.VS : L.V, L.muv, B, m, ldm, L.variance + jitter,
+                                                                 L.Ktilde, mean_out + (size_t)q * out_ld, var_out + (size_t)q * out_ld,
                                                                  status, fresh_kernel_matrices ? 1 : 0);
       ++launches;
       ph_end();
     }
     CK(cudaGetLastError());
     return AGP_OK;
+  }
+  int moments_impl(bool from_batch, int B, bool fresh) {
+    return moments_rows(from_batch ? Xb : X, from_batch ? xxb : xx, from_batch ? nullptr : idx_cur, B, fresh,
+                        mean_f + (size_t)qbeg * ldB, var_f + (size_t)qbeg * ldB, ldB, true);
   }
 
   LikParams lik_params(int B, bool from_batch, int update) {
@@ -592,7 +646,7 @@ struct Engine : EngineBase {
     if (B < 1 || B > Bcap) BAD("The size of mini-batch is incorrect (negative or bigger than the batch capacity)");
     if (prec == AGP_PREC_TF32X3 && (B % 128)) BAD("TF32X3 precision needs B % 128 == 0");
     if (!from_batch) CKS(prep_idx(idx, B, base));
-    curB = B; cur_from_batch = from_batch;
+    curB = B; cur_from_batch = from_batch; kernel_matrices_stale = false;
     CKS(moments_impl(from_batch, B, true));
     return AGP_OK;
   }
@@ -608,17 +662,17 @@ struct Engine : EngineBase {
       Latent& L = lat[q];
       ph_begin(PH_GRADMU);
       CK(cudaMemsetAsync(L.v1, 0, m * sizeof(double), st()));
-      gemv_t_kernel<T><<<dim3((m + 127) / 128, (B + 63) / 64), 128, 0, st()>>>(L.kappa, ldm, gmu + (size_t)q * ldB, B, m, L.v1);
+      gemv_t_kernel<T><<<dim3((m + 127) / 128, (B + 63) / 64), 128, 0, st()>>>(L.V, ldm, gmu + (size_t)q * ldB, B, m, L.v1);
       ++launches;
       ph_end();
       ph_begin(PH_GRAM);
       int ns = n_split;
       if (prec == AGP_PREC_TF32X3) {
-        CKS(umma_gram(ctx_err(), L.um, (const float*)(const void*)L.kappa, gS + (size_t)q * ldB, rho, (float*)(void*)L.Gpart, B, m, &ns, st()));
+        CKS(umma_gram(ctx_err(), L.um, (const float*)(const void*)L.V, gS + (size_t)q * ldB, rho, (float*)(void*)L.Gpart, B, m, &ns, st()));
         launches += 2;
       } else {
-        GemmParams<T> g{};  // rho * kappa^T diag(grad_Sigma) kappa  (functions/utils.jl:70-72), split over the minibatch
-        g.A = L.kappa; g.lda = ldm; g.B = L.kappa; g.ldb = ldm; g.C = L.Gpart; g.ldc = ldm; g.M = m; g.N = m; g.K = B;
+        GemmParams<T> g{};  // rho * V^T diag(grad_Sigma) V  (functions/utils.jl:70-72, whitened), split over the minibatch
+        g.A = L.V; g.lda = ldm; g.B = L.V; g.ldb = ldm; g.C = L.Gpart; g.ldc = ldm; g.M = m; g.N = m; g.K = B;
         g.k_scale = gS + (size_t)q * ldB; g.k_scale_mul = rho; g.k_chunk = k_chunk; g.zs_c = (int64_t)m * ldm; g.alpha = 1.0;
         ns = (B + k_chunk - 1) / k_chunk;
         gemm_simt_launch<T, true, true, EPI_PLAIN>(g, ns, st());
@@ -628,10 +682,10 @@ struct Engine : EngineBase {
       ph_begin(PH_COMBINE);
       TailParams tp{};
       tp.m = m; tp.mp = mp; tp.ld = mp; tp.n_split = ns; tp.gpart_stride = (int64_t)m * ldm; tp.gpart_ld = ldm;
-      tp.v1 = L.v1; tp.Kinv = L.Kinv; tp.Kinv_mu0 = L.Kinv_mu0; tp.eta1 = L.eta1; tp.eta2 = L.eta2; tp.P = L.P;
+      tp.v1 = L.v1; tp.mu0v = L.mu0v; tp.eta1 = L.eta1v; tp.eta2 = L.eta2v; tp.P = L.P;
       tp.counters = counters; tp.stochastic = stochastic; tp.rm_kappa = rm_kappa; tp.rm_tau = rm_tau; tp.rho = rho;
       tp.logdet = L.logdetP; tp.status = status;
-      combine_kernel<T><<<dim3((mp + 127) / 128, mp), 128, 0, st()>>>(tp, L.Gpart);
+      combine_kernel<T><<<grid_mp(), 128, 0, st()>>>(tp, L.Gpart);
       ++launches;
       ph_end();
       CKS(eta_to_moments(L));
@@ -645,14 +699,14 @@ struct Engine : EngineBase {
     return AGP_OK;
   }
 
-  // global_update!(gp) (inference/inference.jl:25-28): Sigma = -inv(eta2)/2 = inv(P), mu = Sigma eta1
+  // global_update!(gp) (inference/inference.jl:25-28) in the whitened basis: Sigma_v = inv(P_v), mu_v = Sigma_v eta1_v
   int eta_to_moments(Latent& L) {
-    spd_inverse(L.P, L.X, L.W, L.Sigma, L.logdetP);
+    spd_inverse(L.P, L.X, L.W, L.SigmaV, L.logdetP);
     ph_begin(PH_FINAL);
-    symmetrize_shadow_kernel<T><<<dim3((m + 127) / 128, m), 128, 0, st()>>>(L.Sigma, mp, m, L.Sigma_T, ldm);
-    symv_kernel<<<(m * 32 + 255) / 256, 256, 0, st()>>>(L.Sigma, mp, m, L.eta1, L.mu);
+    symmetrize_shadow_kernel<T><<<dim3((m + 127) / 128, m), 128, 0, st()>>>(L.SigmaV, mp, m, L.SigmaV_T, ldm);
+    symv_kernel<<<(m * 32 + 255) / 256, 256, 0, st()>>>(L.SigmaV, mp, m, L.eta1v, L.muv);
     launches += 2;
-    if (prec == AGP_PREC_TF32X3) { CKS(umma_split_matrix(ctx_err(), L.um, UM_SIGMA, (const float*)(const void*)L.Sigma_T, m, st())); ++launches; }
+    if (prec == AGP_PREC_TF32X3) { CKS(umma_split_matrix(ctx_err(), L.um, UM_SIGMA, (const float*)(const void*)L.SigmaV_T, m, st())); ++launches; }
     ph_end();
     return AGP_OK;
   }
@@ -723,8 +777,10 @@ struct Engine : EngineBase {
 
   // moments of the last minibatch under the UPDATED posterior (ELBO uses the post-update mu, Sigma)
   int elbo_moments() override {
-    if (!have_step && curB < 1) { ctx->err = "no minibatch to evaluate the ELBO on"; return AGP_ERR_STATE; }
-    return moments_impl(cur_from_batch, curB, false);
+    if (curB < 1) { ctx->err = "no minibatch to evaluate the ELBO on"; return AGP_ERR_STATE; }
+    bool fresh = kernel_matrices_stale;  // predict_f overwrote Knm / V: rebuild them from the retained minibatch
+    kernel_matrices_stale = false;
+    return moments_impl(cur_from_batch, curB, fresh);
   }
 
   int elbo(double rho, double* out3) override {
@@ -742,14 +798,14 @@ struct Engine : EngineBase {
     for (int q = 0; q < Ql; ++q) {
       Latent& L = lat[q];
       CK(cudaMemsetAsync(d_out + 4, 0, 2 * sizeof(double), st()));
-      gauss_kl_kernel<<<m, 128, 0, st()>>>(L.Kinv, L.Sigma, mp, m, L.mu, L.has_mu0 ? L.mu0 : nullptr, d_out + 4);
+      gauss_kl_kernel<<<1, 256, 0, st()>>>(L.SigmaV, mp, m, L.muv, L.mu0v, d_out + 4);
       ++launches;
       double t2[2], ldp;
       CK(cudaMemcpyAsync(t2, d_out + 4, 2 * sizeof(double), cudaMemcpyDeviceToHost, st()));
       CK(cudaMemcpyAsync(&ldp, L.logdetP, sizeof(double), cudaMemcpyDeviceToHost, st()));
       CK(cudaStreamSynchronize(st()));
-      // KLdivergences.jl:17 ; logdet Sigma = -logdet P
-      kl += 0.5 * (L.logdetK + ldp + t2[0] + t2[1] - (double)m);
+      // KLdivergences.jl:17 with logdet K - logdet Sigma = logdet P_v, tr(K \\ Sigma) = tr(Sigma_v), invquad = |mu_v - mu0_v|^2
+      kl += 0.5 * (ldp + t2[0] + t2[1] - (double)m);
     }
     CK(cudaMemcpyAsync(h.data(), d_out, 4 * sizeof(double), cudaMemcpyDeviceToHost, st()));
     CK(cudaStreamSynchronize(st()));
@@ -764,30 +820,35 @@ struct Engine : EngineBase {
   }
   int get_posterior(int ql, double* mu, double* Sigma, double* eta1, double* eta2) override {
     if (ql < 0 || ql >= Ql) BAD("latent index out of range");
-    CK(cudaStreamSynchronize(st()));
     Latent& L = lat[ql];
-    if (mu) CK(cudaMemcpy(mu, L.mu, m * 8, cudaMemcpyDeviceToHost));
-    if (eta1) CK(cudaMemcpy(eta1, L.eta1, m * 8, cudaMemcpyDeviceToHost));
-    if (Sigma) CKS(copy_mat(L.Sigma, Sigma));
-    if (eta2) CKS(copy_mat(L.eta2, eta2));
+    if (!L.white_valid) {  // nothing has run yet: the canonical parameters are the truth (Sigma = inv(-2 eta2) needs K only formally)
+      if (!have_K) CKS(refresh_K());
+    }
+    // canonical from whitened, fp64:  mu = L mu_v,  Sigma = L Sigma_v L^T,  eta1 = L^-T eta1_v,  eta2 = L^-T eta2_v L^-1
+    canonicalize(L);
+    if (mu) { symv_kernel<<<(m * 32 + 255) / 256, 256, 0, st()>>>(L.Lc, mp, m, L.muv, L.v1); ++launches; }
+    if (Sigma) {
+      dgemm(false, false, L.SigmaV, L.Lc, L.W, 1.0, 0.0);  // W = Sigma_v L^T   (NT)
+      dgemm(false, true, L.Lc, L.W, L.X, 1.0, 0.0);        // X = L W
+    }
+    CK(cudaStreamSynchronize(st()));
+    if (mu) CK(cudaMemcpy(mu, L.v1, m * 8, cudaMemcpyDeviceToHost));
+    if (eta1) CK(cudaMemcpy(eta1, L.eta1c, m * 8, cudaMemcpyDeviceToHost));
+    if (Sigma) CKS(copy_mat(L.X, Sigma));
+    if (eta2) CKS(copy_mat(L.eta2c, eta2));
     return AGP_OK;
   }
   int set_posterior(int ql, const double* eta1, const double* eta2) override {
     if (ql < 0 || ql >= Ql || !eta1 || !eta2) BAD("bad posterior arguments");
     Latent& L = lat[ql];
     CK(cudaStreamSynchronize(st()));
-    CK(cudaMemcpy(L.eta1, eta1, m * 8, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy2D(L.eta2, (size_t)mp * 8, eta2, (size_t)m * 8, (size_t)m * 8, m, cudaMemcpyHostToDevice));
-    // P = -2 eta2 with identity padding: reuse the combine kernel with lr = 1 on "G = 0, Kinv = -2*eta2 ..." is
-    // awkward; do it directly on the host copy instead (checkpoint restore is off the hot path).
-    std::vector<double> P((size_t)mp * mp, 0.0);
-    for (int i = 0; i < mp; ++i)
-      for (int j = 0; j < mp; ++j)
-        P[(size_t)i * mp + j] = (i < m && j < m) ? -2.0 * eta2[(size_t)i * m + j] : (i == j ? 1.0 : 0.0);
-    CK(cudaMemcpy(L.P, P.data(), P.size() * 8, cudaMemcpyHostToDevice));
-    CK(cudaMemsetAsync(L.logdetP, 0, sizeof(double), st()));
-    CKS(eta_to_moments(L));
-    return sync_status();
+    CK(cudaMemset(L.eta1c, 0, mp * 8));
+    CK(cudaMemset(L.eta2c, 0, (size_t)mp * mp * 8));
+    CK(cudaMemcpy(L.eta1c, eta1, m * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy2D(L.eta2c, (size_t)mp * 8, eta2, (size_t)m * 8, (size_t)m * 8, m, cudaMemcpyHostToDevice));
+    L.white_valid = false;
+    if (have_K) { CKS(whiten(L)); return sync_status(); }
+    return AGP_OK;
   }
   int get_counters(int64_t* t, int64_t* cur) override {
     int64_t c[2];
@@ -826,12 +887,20 @@ struct Engine : EngineBase {
   }
   int get_kernel_matrices(int ql, double* Knm, double* kappa, int B) override {
     if (ql < 0 || ql >= Ql || B < 1 || B > Bcap) BAD("bad kernel-matrix query");
+    Latent& L = lat[ql];
+    if (!pKS) CKS(dalloc(&pKS, (size_t)Bcap * ldm));
+    if (kappa) {  // kappa = Knm / K = V L^-1   (NN product with the T shadow of L^-1)
+      GemmParams<T> g{};
+      g.A = L.V; g.lda = ldm; g.B = L.Linv_T; g.ldb = ldm; g.C = pKS; g.ldc = ldm; g.M = B; g.N = m; g.K = m; g.alpha = 1.0;
+      gemm_simt_launch<T, false, true, EPI_PLAIN>(g, 1, st());
+      ++launches;
+    }
     CK(cudaStreamSynchronize(st()));
     std::vector<T> tmp((size_t)B * ldm);
     for (int w = 0; w < 2; ++w) {
       double* dst = w == 0 ? Knm : kappa;
       if (!dst) continue;
-      CK(cudaMemcpy(tmp.data(), w == 0 ? lat[ql].Knm : lat[ql].kappa, tmp.size() * sizeof(T), cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(tmp.data(), w == 0 ? L.Knm : pKS, tmp.size() * sizeof(T), cudaMemcpyDeviceToHost));
       for (int b = 0; b < B; ++b) for (int j = 0; j < m; ++j) dst[(size_t)b * m + j] = (double)tmp[(size_t)b * ldm + j];
     }
     return AGP_OK;
@@ -880,71 +949,39 @@ struct Engine : EngineBase {
   int use_graph(int on) override { want_graph = on != 0; if (!on) drop_graph(); return AGP_OK; }
 };
 
-// mean / variance rows of the predictive: mu* = k* a,  var* = kdiag + jitter - rowsum((k* Apred) .* k*)
-template <typename T>
-__global__ void predict_rows_kernel(const T* __restrict__ Ks, const T* __restrict__ KA, const double* __restrict__ a, int B, int m,
-                                    int64_t ld, double kdiag_jit, double* __restrict__ mu, double* __restrict__ var) {
-  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= B) return;
-  double s1 = 0.0, s2 = 0.0;
-  for (int j = lane; j < m; j += 32) {
-    double k = (double)Ks[(int64_t)warp * ld + j];
-    s1 += k * a[j];
-    if (KA) s2 += k * (double)KA[(int64_t)warp * ld + j];
-  }
-  s1 = warp_sum(s1); s2 = warp_sum(s2);
-  if (lane == 0) { mu[warp] = s1; if (var) var[warp] = kdiag_jit - s2; }
-}
-
+// _predict_f (training/predictions.jl:25-50, diag = true): the same row-moment pipeline as the step, on test rows.
+// NOTE: uses the step's Knm / V / VS buffers; the last minibatch's kernel matrices are saved and restored around it
+// only logically (a later ELBO call recomputes them from the retained minibatch indices).
 template <typename T>
 int Engine<T>::predict_f(const void* Xt, int x_dtype, int x_layout, int64_t nt, int want_var, double* mu_out, double* var_out) {
   if (!Xt || !mu_out || nt < 1 || (want_var && !var_out)) BAD("bad predict arguments");
   if (!have_K) CKS(refresh_K());  // predictions.jl:28-29: compute_K when no state is passed
-  double *dmu = nullptr, *dvar = nullptr, *avec = nullptr;
-  if (!pKnm) { CKS(dalloc(&pKnm, (size_t)Bcap * ldm)); CKS(dalloc(&pKS, (size_t)Bcap * ldm)); CKS(dalloc(&pA, (size_t)m * ldm)); }
-  CK(cudaMalloc(&dmu, ldB * 8)); CK(cudaMalloc(&dvar, ldB * 8)); CK(cudaMalloc(&avec, mp * 8));
+  CKS(sync_status());             // surface errors of earlier asynchronous steps before the flag is reused
+  double *dmu = nullptr, *dvar = nullptr;
+  CK(cudaMalloc(&dmu, (size_t)Ql * ldB * 8)); CK(cudaMalloc(&dvar, (size_t)Ql * ldB * 8));
+  if (!pXb) { CKS(dalloc(&pXb, (size_t)Bcap * Dp)); CKS(dalloc(&pxxb, Bcap)); }
   int rc = AGP_OK;
-  for (int q = 0; q < Ql && rc == AGP_OK; ++q) {
-    Latent& L = lat[q];
-    symv_kernel<<<(m * 32 + 255) / 256, 256, 0, st()>>>(L.Kinv, mp, m, L.mu, avec);  // K \ mu
-    ++launches;
-    T* Apred_T = pA;
-    if (want_var) {
-      // A = K^-1 (I - Sigma K^-1) = K^-1 - K^-1 Sigma K^-1   (predictions.jl:38)
-      GemmParams<double> g1{};  // W = Sigma * Kinv   (both symmetric: NT form)
-      g1.A = L.Sigma; g1.lda = mp; g1.B = L.Kinv; g1.ldb = mp; g1.C = L.W; g1.ldc = mp; g1.M = m; g1.N = m; g1.K = m; g1.alpha = 1.0;
-      gemm_simt_launch<double, false, false, EPI_PLAIN>(g1, 1, st());
-      cudaMemcpyAsync(L.X, L.Kinv, (size_t)mp * mp * 8, cudaMemcpyDeviceToDevice, st());
-      GemmParams<double> g2{};  // X = Kinv - Kinv * W
-      g2.A = L.Kinv; g2.lda = mp; g2.B = L.W; g2.ldb = mp; g2.C = L.X; g2.ldc = mp; g2.M = m; g2.N = m; g2.K = m; g2.alpha = -1.0; g2.beta = 1.0;
-      gemm_simt_launch<double, false, true, EPI_PLAIN>(g2, 1, st());
-      shadow_kernel<T><<<dim3((m + 127) / 128, m), 128, 0, st()>>>(L.X, mp, m, Apred_T, ldm);
-      launches += 3;
+  for (int64_t r0 = 0; r0 < nt && rc == AGP_OK; r0 += Bcap) {
+    int B = (int)std::min<int64_t>(Bcap, nt - r0);
+    int Bk = B;
+    if (prec == AGP_PREC_TF32X3) Bk = (int)rup(B, 128);  // tensor-core tiles: pad with (zeroed) rows
+    if (Bk != B) cudaMemsetAsync(pXb, 0, (size_t)Bcap * Dp * sizeof(T), st());
+    rc = upload_rows(Xt, x_dtype, x_layout, nt, r0, B, pXb, pxxb);
+    if (rc != AGP_OK) break;
+    int st_before = 0;
+    rc = moments_rows(pXb, pxxb, nullptr, Bk, true, dmu, dvar, ldB, want_var != 0);
+    (void)st_before;
+    if (rc != AGP_OK) break;
+    for (int q = 0; q < Ql; ++q) {
+      if (cudaMemcpyAsync(mu_out + (size_t)q * nt + r0, dmu + (size_t)q * ldB, B * 8, cudaMemcpyDeviceToHost, st()) != cudaSuccess) rc = AGP_ERR_CUDA;
+      if (want_var && cudaMemcpyAsync(var_out + (size_t)q * nt + r0, dvar + (size_t)q * ldB, B * 8, cudaMemcpyDeviceToHost, st()) != cudaSuccess) rc = AGP_ERR_CUDA;
     }
-    for (int64_t r0 = 0; r0 < nt && rc == AGP_OK; r0 += Bcap) {
-      int B = (int)std::min<int64_t>(Bcap, nt - r0);
-      rc = upload_rows(Xt, x_dtype, x_layout, nt, r0, B, Xb, xxb);
-      if (rc != AGP_OK) break;
-      GemmParams<T> g{};
-      g.A = Xb; g.lda = Dp; g.B = L.Z; g.ldb = Dp; g.C = pKnm; g.ldc = ldm; g.M = B; g.N = m; g.K = D; g.alpha = 1.0;
-      g.xx = xxb; g.zz = L.zz; g.scale2 = L.scale * L.scale; g.variance = L.variance; g.kernel_kind = L.kind;
-      gemm_simt_launch<T, false, false, EPI_KERNELFN>(g, 1, st());
-      ++launches;
-      if (want_var) {
-        GemmParams<T> s{};
-        s.A = pKnm; s.lda = ldm; s.B = Apred_T; s.ldb = ldm; s.C = pKS; s.ldc = ldm; s.M = B; s.N = m; s.K = m; s.alpha = 1.0;
-        gemm_simt_launch<T, false, false, EPI_PLAIN>(s, 1, st());
-        ++launches;
-      }
-      predict_rows_kernel<T><<<(B * 32 + 255) / 256, 256, 0, st()>>>(pKnm, want_var ? pKS : nullptr, avec, B, m, ldm,
-                                                                     L.variance + jitter, dmu, want_var ? dvar : nullptr);
-      ++launches;
-      if (cudaMemcpyAsync(mu_out + (size_t)q * nt + r0, dmu, B * 8, cudaMemcpyDeviceToHost, st()) != cudaSuccess) rc = AGP_ERR_CUDA;
-      if (want_var && cudaMemcpyAsync(var_out + (size_t)q * nt + r0, dvar, B * 8, cudaMemcpyDeviceToHost, st()) != cudaSuccess) rc = AGP_ERR_CUDA;
-      if (cudaStreamSynchronize(st()) != cudaSuccess) rc = AGP_ERR_CUDA;
-    }
+    if (cudaStreamSynchronize(st()) != cudaSuccess) rc = AGP_ERR_CUDA;
   }
-  cudaFree(dmu); cudaFree(dvar); cudaFree(avec);
+  cudaFree(dmu); cudaFree(dvar);
+  // the predictive variance of the reference is NOT checked for positivity (predictions.jl:38-44): drop a Ktilde flag
+  cudaMemsetAsync(status, 0, sizeof(int), st());
+  kernel_matrices_stale = true;
   if (rc == AGP_ERR_CUDA && ctx->err.empty()) ctx->err = "CUDA failure in predict_f";
   return rc;
 }

@@ -32,7 +32,7 @@ struct GemmParams {
   double alpha, beta;        // C = alpha * acc + beta * C
   int lower_only;            // skip tiles that lie strictly above the diagonal
   int k_from_diag;           // TN product of lower-triangular factors: start k at max(row0, col0)
-  int k_to_diag;             // NN product L21 * X11 etc.: (unused, reserved)
+  int k_to_diag;             // NT with a lower-triangular B ([N][K], zero for k > n): stop k at the tile's last column
   // EPI_KERNELFN: C = variance * base(scale2 * (xx[row] + zz[col] - 2 acc))
   const T* xx; const T* zz; double scale2, variance; int kernel_kind;
 };
@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmParams<T> p) {
   int k0 = 0, k1 = p.K;
   if (p.k_chunk > 0) { k0 = z * p.k_chunk; k1 = min(p.K, k0 + p.k_chunk); }
   if (p.k_from_diag) { int ks = max(bm, bn); k0 = max(k0, (ks / BK) * BK); }
+  if (p.k_to_diag) k1 = min(k1, bn + BN);
   const int K4 = (p.K + 3) & ~3;  // padded extent of a K-contiguous row (padding holds zeros)
 
   T acc[TM][TN];

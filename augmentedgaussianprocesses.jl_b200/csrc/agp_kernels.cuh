@@ -60,36 +60,34 @@ __global__ void idx_select_kernel(const int64_t* __restrict__ pool, int64_t n_li
 }
 
 // ------------------------------------------------------------------------------------------------
-// per-row statistics  (gpblocks/latentgp.jl:212-213 K̃; :179 mean_f; :189 var_f; functions/utils.jl:55-57)
-//   Ktilde = kdiag + jitter - rowsum(kappa .* Knm);  mean_f = kappa * mu;  var_f = rowsum((kappa Sigma) .* kappa) + Ktilde
+// per-row statistics in the whitened basis (V = Knm L^-T, q(v) = N(mu_v, Sigma_v), u = L v):
+//   Ktilde = kdiag + jitter - rowsum(V .* V)        == kdiag + jitter - diag_ABt(kappa, Knm)   latentgp.jl:212
+//   mean_f = V mu_v                                  == kappa * mu                              latentgp.jl:179
+//   var_f  = rowsum((V Sigma_v) .* V) + Ktilde       == diag_ABt(kappa*Sigma, kappa) + Ktilde   latentgp.jl:189
 // one warp per minibatch row; sums accumulate in fp64 whatever T is.
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void rowstats_kernel(const T* __restrict__ Knm, const T* __restrict__ kappa, const T* __restrict__ KS,
-                                const double* __restrict__ mu, int B, int m, int64_t ld, double kdiag_jit,
-                                double* __restrict__ Ktilde, double* __restrict__ mean_f, double* __restrict__ var_f,
-                                int* __restrict__ status, int compute_ktilde) {
-  using V = typename VecOf<T>::type;
+__global__ void rowstats_kernel(const T* __restrict__ V, const T* __restrict__ VS, const double* __restrict__ mu, int B, int m,
+                                int64_t ld, double kdiag_jit, double* __restrict__ Ktilde, double* __restrict__ mean_f,
+                                double* __restrict__ var_f, int* __restrict__ status, int compute_ktilde) {
+  using VT = typename VecOf<T>::type;
   constexpr int W = VecOf<T>::W;
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= B) return;
-  const T* kn = Knm + (int64_t)warp * ld;
-  const T* kp = kappa + (int64_t)warp * ld;
-  const T* ks = KS + (int64_t)warp * ld;
+  const T* vp = V + (int64_t)warp * ld;
+  const T* sp = VS + (int64_t)warp * ld;
   double s1 = 0.0, s2 = 0.0, s3 = 0.0;
   int m4 = (m + 3) & ~3;  // padding columns are zero
   for (int j = lane * W; j < m4; j += 32 * W) {
-    V a = *reinterpret_cast<const V*>(kp + j);
-    V c = *reinterpret_cast<const V*>(ks + j);
-    V b;
-    if (compute_ktilde) b = *reinterpret_cast<const V*>(kn + j); else b = a;
-    double av[W], bv[W], cv[W];
-    av[0] = a.x; av[1] = a.y; bv[0] = b.x; bv[1] = b.y; cv[0] = c.x; cv[1] = c.y;
-    if constexpr (W == 4) { av[2] = a.z; av[3] = a.w; bv[2] = b.z; bv[3] = b.w; cv[2] = c.z; cv[3] = c.w; }
+    VT a = *reinterpret_cast<const VT*>(vp + j);
+    VT c = *reinterpret_cast<const VT*>(sp + j);
+    double av[W], cv[W];
+    av[0] = a.x; av[1] = a.y; cv[0] = c.x; cv[1] = c.y;
+    if constexpr (W == 4) { av[2] = a.z; av[3] = a.w; cv[2] = c.z; cv[3] = c.w; }
 #pragma unroll
     for (int q = 0; q < W; ++q) {
       double muj = (j + q < m) ? mu[j + q] : 0.0;
-      s1 += av[q] * bv[q];
+      s1 += av[q] * av[q];
       s2 += av[q] * muj;
       s3 += av[q] * cv[q];
     }
@@ -332,17 +330,16 @@ __global__ void elbo_lik_kernel(const LikParams p, double* __restrict__ out) {
   }
 }
 
-// GaussianKL pieces (functions/KLdivergences.jl:11-18): out[0] += sum_ij Kinv_ij Sigma_ij  (tr(K\Sigma)),
-// out[1] += (mu-mu0)^T Kinv (mu-mu0)  (invquad)
-__global__ void gauss_kl_kernel(const double* __restrict__ Kinv, const double* __restrict__ Sigma, int64_t ld, int m,
-                                const double* __restrict__ mu, const double* __restrict__ mu0, double* __restrict__ out) {
-  int row = blockIdx.x;
+// GaussianKL (functions/KLdivergences.jl:11-18) in the whitened basis: with Sigma = L Sigma_v L^T, mu = L mu_v,
+//   logdet K - logdet Sigma = logdet P_v,  tr(K \ Sigma) = tr(Sigma_v),  invquad(K, mu - mu0) = |mu_v - L^-1 mu0|^2.
+// out[0] += tr(Sigma_v), out[1] += |mu_v - mu0_v|^2        (single block)
+__global__ void gauss_kl_kernel(const double* __restrict__ SigmaV, int64_t ld, int m, const double* __restrict__ muv,
+                                const double* __restrict__ mu0v, double* __restrict__ out) {
   double tr = 0.0, q = 0.0;
-  double di = mu[row] - (mu0 ? mu0[row] : 0.0);
   for (int j = threadIdx.x; j < m; j += blockDim.x) {
-    double kv = Kinv[(int64_t)row * ld + j];
-    tr += kv * Sigma[(int64_t)row * ld + j];
-    q += kv * di * (mu[j] - (mu0 ? mu0[j] : 0.0));
+    tr += SigmaV[(int64_t)j * ld + j];
+    double d = muv[j] - mu0v[j];
+    q += d * d;
   }
   __shared__ double s1[8], s2[8];
   tr = warp_sum(tr); q = warp_sum(q);
@@ -352,8 +349,8 @@ __global__ void gauss_kl_kernel(const double* __restrict__ Kinv, const double* _
   if (threadIdx.x == 0) {
     double a = 0.0, c = 0.0;
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += s1[i]; c += s2[i]; }
-    atomicAdd(out + 0, a);
-    atomicAdd(out + 1, c);
+    out[0] += a;
+    out[1] += c;
   }
 }
 
@@ -364,8 +361,8 @@ struct TailParams {
   int m, mp;            // logical / padded (power-of-two multiple of 64) size
   int64_t ld;           // = mp : leading dimension of every fp64 m x m matrix
   int n_split; int64_t gpart_stride; int64_t gpart_ld;  // G partials [n_split][m][gpart_ld]
-  const double* v1;     // kappa^T grad_mu (un-scaled by rho)
-  const double* Kinv; const double* Kinv_mu0;
+  const double* v1;     // V^T grad_mu (un-scaled by rho)
+  const double* mu0v;   // L^-1 mu0 (whitened prior mean)
   double* eta1; double* eta2; double* P;
   const int64_t* counters;  // [0] = Robbins-Monro t (starts at 1)
   int stochastic; double rm_kappa, rm_tau, rho;
@@ -373,8 +370,9 @@ struct TailParams {
 };
 
 // natural gradient + global update of the natural parameters (inference/analyticVI.jl:160-180, 229-246;
-// inference/optimisers.jl:14-19) and P = -2 eta2 (the matrix whose inverse is Sigma, inference.jl:26).
-// G is symmetrised from its upper triangle like Julia's Symmetric() (analyticVI.jl:238, Q5).
+// inference/optimisers.jl:14-19) in the whitened basis (eta1_v = L^T eta1, eta2_v = L^T eta2 L, so that the prior
+// precision K^-1 becomes I and K \ mu0 becomes L^-1 mu0), and P_v = -2 eta2_v whose inverse is Sigma_v
+// (inference.jl:26).  G is symmetrised from its upper triangle like Julia's Symmetric() (analyticVI.jl:238, Q5).
 template <typename TG>
 __global__ void combine_kernel(const TailParams p, const TG* __restrict__ Gpart) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -391,13 +389,13 @@ __global__ void combine_kernel(const TailParams p, const TG* __restrict__ Gpart)
   for (int s = 0; s < p.n_split; ++s) g += (double)Gpart[s * p.gpart_stride + (int64_t)a * p.gpart_ld + b];
   int64_t o = (int64_t)i * p.ld + j;
   double e2 = p.eta2[o];
-  double d2 = -(g + 0.5 * p.Kinv[o]) - e2;
+  double d2 = -(g + (i == j ? 0.5 : 0.0)) - e2;
   e2 += lr * d2;
   p.eta2[o] = e2;
   p.P[o] = -2.0 * e2;
   if (i == 0) {
     double e1 = p.eta1[j];
-    double d1 = p.rho * p.v1[j] + p.Kinv_mu0[j] - e1;
+    double d1 = p.rho * p.v1[j] + p.mu0v[j] - e1;
     p.eta1[j] = e1 + lr * d1;
     if (j == 0) *p.logdet = 0.0;
   }
@@ -487,6 +485,32 @@ __global__ void symv_kernel(const double* __restrict__ S, int64_t ld, int m, con
   for (int j = lane; j < m; j += 32) s += S[(int64_t)row * ld + j] * x[j];
   s = warp_sum(s);
   if (lane == 0) y[row] = s;
+}
+
+// y = S^T x ; one thread per output column (S is m x m, tiny, off the hot path)
+__global__ void matvec_t_kernel(const double* __restrict__ S, int64_t ld, int m, const double* __restrict__ x,
+                                double* __restrict__ y) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  double s = 0.0;
+  for (int i = 0; i < m; ++i) s += S[(int64_t)i * ld + j] * x[i];
+  y[j] = s;
+}
+
+// lower triangle (incl. diagonal) of src -> dst, zeros above; used to keep copies of L and L^-1
+__global__ void copy_lower_kernel(const double* __restrict__ src, double* __restrict__ dst, int64_t ld, int mp) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  int i = blockIdx.y;
+  if (j >= mp) return;
+  dst[(int64_t)i * ld + j] = (j <= i) ? src[(int64_t)i * ld + j] : 0.0;
+}
+
+// dst = alpha * src with identity padding outside the m x m block
+__global__ void scale_pad_kernel(const double* __restrict__ src, double* __restrict__ dst, int64_t ld, int m, int mp, double alpha) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  int i = blockIdx.y;
+  if (j >= mp) return;
+  dst[(int64_t)i * ld + j] = (i < m && j < m) ? alpha * src[(int64_t)i * ld + j] : (i == j ? 1.0 : 0.0);
 }
 
 __global__ void bump_counters_kernel(int64_t* counters, int bump_t, int bump_cursor) {

@@ -8,13 +8,13 @@
 
 namespace agp {
 
-enum UmmaMat : int { UM_KNM = 0, UM_KAPPA = 1, UM_KINV = 2, UM_SIGMA = 3, UM_COUNT = 4 };
+enum UmmaMat : int { UM_KNM = 0, UM_V = 1, UM_LINV = 2, UM_SIGMA = 3, UM_COUNT = 4 };
 
 struct UmmaLatent {
   int m = 0, ldm = 0, Bcap = 0;
   float* hi[UM_COUNT] = {nullptr, nullptr, nullptr, nullptr};  // TF32-rounded high parts
   float* lo[UM_COUNT] = {nullptr, nullptr, nullptr, nullptr};  // residuals
-  float* kT_hi = nullptr; float* kT_lo = nullptr;              // kappa^T (m x B) and diag(w)-scaled copy for the Gram product
+  float* kT_hi = nullptr; float* kT_lo = nullptr;              // V^T (m x B) and diag(w)-scaled copy for the Gram product
   float* kTw_hi = nullptr; float* kTw_lo = nullptr;
   void* tmaps = nullptr;                                        // host array of CUtensorMap
 };
