@@ -825,7 +825,7 @@ struct Engine : EngineBase {
       if (!have_K) CKS(refresh_K());
     }
     // canonical from whitened, fp64:  mu = L mu_v,  Sigma = L Sigma_v L^T,  eta1 = L^-T eta1_v,  eta2 = L^-T eta2_v L^-1
-    canonicalize(L);
+    if (eta1 || eta2) canonicalize(L);
     if (mu) { symv_kernel<<<(m * 32 + 255) / 256, 256, 0, st()>>>(L.Lc, mp, m, L.muv, L.v1); ++launches; }
     if (Sigma) {
       dgemm(false, false, L.SigmaV, L.Lc, L.W, 1.0, 0.0);  // W = Sigma_v L^T   (NT)

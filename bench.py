@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py -- natural-gradient CAVI iterations/second of the SVGP AnalyticSVI hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision f32|tf32x3|f64]
+
+Workload (BASELINE.json configs[1], "C2"): SVGP, LogisticLikelihood, SqExponentialKernel with lengthscale
+sqrt(D), n = 1e6, D = 32, m = 512 inducing points, minibatch 8192, RobbinsMonro(0.51, 1), K_mm fixed
+(optimiser=false semantics).  Synthetic data, seeded.  One "step" = one update_parameters! call
+(training/training.jl:140-144 of the reference).
+
+N > 1 (torchrun, one rank per GPU): multi-output SVGP with Q = T = N Logistic tasks of the same shape, one
+latent GP per rank, the per-sample moments all-gathered over NCCL every step (weak scaling: per-GPU work is
+fixed); value = latent-GP iterations per second summed over ranks (at N = 1 this is plain iterations/s).
+
+--impl reference: the fp64 NumPy/OpenBLAS restatement of the reference path (oracle/) timed on the host
+cores (the Julia reference itself cannot run here: no Julia in the image).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(n=1_000_000, D=32, m=512, B=8192)
+METRIC = "natural-gradient CAVI iters/sec, SVGP m=512 bs=8192"
+
+
+def make_problem(n, D, m, B, n_lists, seed=0, n_task=1):
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((n, D), dtype=np.float32)
+    W = rng.standard_normal((D, n_task)).astype(np.float32)
+    ys = [np.sign(X @ W[:, t] + 0.1 * rng.standard_normal(n, dtype=np.float32)).astype(np.float64) for t in range(n_task)]
+    for y in ys:
+        y[y == 0] = 1.0
+    Z = X[rng.permutation(n)[:m]].astype(np.float64)
+    mbs = np.stack([rng.choice(n, B, replace=False) for _ in range(n_lists)]).astype(np.int64)
+    return X, ys, Z, mbs, rng
+
+
+def flops_per_iter(B, m, D):
+    """algorithmic FLOPs of one step for one latent (SURVEY 8d / BASELINE.md section 3)."""
+    return 2.0 * B * m * D + 6.0 * B * m * m + 8.0 * B * m + (5.0 / 3.0) * m**3
+
+
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """CPU restatement of the reference path (oracle) on the host cores, rank 0 only."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import agp_oracle as O
+
+    n, D, m, B = CFG["n"], CFG["D"], CFG["m"], CFG["B"]
+    K, W = args.steps, args.warmup
+    X, ys, Z, mbs, _ = make_problem(n, D, m, B, K + W)
+    X64 = X.astype(np.float64)
+    model = O.SVGP(O.Kernel("sqexp", scale=1.0 / np.sqrt(D)), O.LogisticLikelihood(), O.AnalyticSVI(B), Z)
+    state = None
+    if W > 0:
+        model, state = O.train(model, X64, ys[0], W, minibatches=list(mbs[:W]))
+    t0 = time.perf_counter()
+    model, state = O.train(model, X64, ys[0], K, minibatches=list(mbs[W:]), state=state)
+    dt = time.perf_counter() - t0
+    v = K / dt
+    cores = os.cpu_count()
+    line = dict(metric=METRIC, value=v, unit="iters/s", n_gpus=args.gpus, steps=K, warmup=W, ms_per_step=1e3 * dt / K,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic", impl="reference",
+                config=dict(workload="C2: SVGP Logistic SqExp n=1e6 D=32 m=512 minibatch=8192", **CFG),
+                cpu_baseline=dict(value=v, unit="iters/s", cores=cores, kind="port",
+                                  sample=f"{K} full iterations of the same workload (NumPy/SciPy fp64 on OpenBLAS, all host threads)"),
+                e2e=dict(value=v, unit="iters/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_sample(n_iter=16, warm=2):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import agp_oracle as O
+
+    n, D, m, B = 200_000, CFG["D"], CFG["m"], CFG["B"]  # the step cost does not depend on n (only the gather does)
+    X, ys, Z, mbs, _ = make_problem(n, D, m, B, n_iter + warm, seed=1)
+    X64 = X.astype(np.float64)
+    model = O.SVGP(O.Kernel("sqexp", scale=1.0 / np.sqrt(D)), O.LogisticLikelihood(), O.AnalyticSVI(B), Z)
+    model, state = O.train(model, X64, ys[0], warm, minibatches=list(mbs[:warm]))
+    t0 = time.perf_counter()
+    O.train(model, X64, ys[0], n_iter, minibatches=list(mbs[warm:]), state=state)
+    dt = time.perf_counter() - t0
+    return dict(value=n_iter / dt, unit="iters/s", cores=os.cpu_count(), kind="port",
+                sample=f"{n_iter} iterations of the C2 step (D=32 m=512 B=8192; n=2e5 rows, the step cost is n-independent) "
+                       "with the fp64 NumPy/OpenBLAS oracle on all host threads")
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+
+    import agp_b200 as agp
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    n, D, m, B = CFG["n"], CFG["D"], CFG["m"], CFG["B"]
+    K, W = args.steps, max(args.warmup, 3)
+    n_lists = K + W
+    X, ys, Z, mbs, rng = make_problem(n, D, m, B, n_lists, n_task=world)
+    kern = agp.SqExponentialKernel() @ agp.ScaleTransform(1.0 / np.sqrt(D))
+    stream = torch.cuda.current_stream().cuda_stream
+    if world == 1:
+        model = agp.SVGP(kern, agp.LogisticLikelihood(), agp.AnalyticSVI(B), Z, precision=args.precision, device=local_rank, stream=stream)
+        y_arg = ys[0]
+    else:
+        A = rng.standard_normal((world, world))
+        A /= np.linalg.norm(A, axis=1, keepdims=True)
+        Zs = [X[np.random.default_rng(100 + q).permutation(n)[:m]].astype(np.float64) for q in range(world)]
+        model = agp.MOSVGP(kern, [agp.LogisticLikelihood() for _ in range(world)], agp.AnalyticSVI(B), Zs, A=A, precision=args.precision,
+                           device=local_rank, stream=stream, shard=(rank, world))
+        y_arg = ys
+    # one API-level step initialises everything (upload, compute_K) and checks the error path
+    agp.train(model, X, y_arg, 1, minibatches=[mbs[0]])
+    eng = model._eng
+    lib = eng.lib
+    L = agp._lib
+    rho = n / B
+    eng.ck(lib.agp_minibatches_upload(eng.model, mbs.ctypes.data_as(L.c_int64_p), n_lists, B, 0))
+
+    def step_async():
+        if world == 1:
+            eng.ck(lib.agp_step_async(eng.model, None, B, 0, rho))
+        else:
+            agp.api._sharded_step(model, eng, None, B, rho)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if args.graph and world == 1:
+        eng.ck(lib.agp_use_graph(eng.model, 1))
+    for _ in range(W):
+        step_async()
+    eng.ck(lib.agp_sync(eng.model))
+    # ---------------- device-resident timing ----------------
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    l0 = model.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        step_async()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    eng.ck(lib.agp_sync(eng.model))
+    launches = model.launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * K / (ms * 1e-3)
+    elbo = agp.ELBO(model)
+
+    # ---------------- per-kernel phase timers (second pass; roofline) ----------------
+    roof = None
+    phases = {}
+    if world == 1:
+        eng.ck(lib.agp_use_graph(eng.model, 0))
+        eng.ck(lib.agp_profile_enable(eng.model, 1))
+        for _ in range(K):
+            step_async()
+        import ctypes as C
+
+        names = (C.c_char_p * 32)()
+        msv = (C.c_double * 32)()
+        lv = (C.c_int64 * 32)()
+        nph = lib.agp_profile_read(eng.model, 32, names, msv, lv)
+        eng.ck(lib.agp_profile_enable(eng.model, 0))
+        for i in range(nph):
+            phases[names[i].decode()] = dict(ms_per_step=msv[i] / K, launches_per_step=lv[i] / K)
+        peaks = {}
+        pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pk):
+            peaks = json.load(open(pk))
+        # dominant contraction: the Gram product V^T diag(w) V (2*B*m^2 algorithmic FLOPs per launch)
+        cand = {k: phases[k]["ms_per_step"] for k in ("gemm_v", "gemm_v_sigma", "gemm_gram") if k in phases}
+        top = max(cand, key=cand.get)
+        fl = 2.0 * B * m * m if top != "gemm_v" else 1.0 * B * m * m  # V = Knm L^-T only needs the lower triangle of L^-1
+        dur = phases[top]["ms_per_step"] * 1e-3
+        bf16 = peaks.get("bf16_tflops_sustained")
+        peak = (bf16 / 2.0) if bf16 else 1590.0 / 2.0
+        roof = dict(bound="tensor", kernel=top, achieved=fl / dur / 1e12, peak=peak, unit="TFLOP/s", frac=fl / dur / 1e12 / peak,
+                    traffic=None,
+                    peak_source=("MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32 = half the bf16 rate), of measured" if bf16
+                                 else "fallback 1.59 PFLOP/s bf16 / 2, of fallback"),
+                    algorithmic_flops_per_launch=fl)
+        knm = phases.get("kmat_knm")
+        if knm:
+            byts = 4.0 * (B * D + m * D + B * m) + 8.0 * B
+            hbm = peaks.get("hbm_gbs", 6650.0)
+            roof["knm"] = dict(bound="hbm", achieved=byts / (knm["ms_per_step"] * 1e-3) / 1e9, peak=hbm, unit="GB/s",
+                               frac=byts / (knm["ms_per_step"] * 1e-3) / 1e9 / hbm, algorithmic_bytes_per_launch=byts)
+
+    # ---------------- end-to-end through the host-buffer API ----------------
+    e2e = None
+    if world == 1:
+        Ke = min(K, 50)
+        xb = [torch.empty((B, D), dtype=torch.float64).pin_memory() for _ in range(Ke)]
+        yb = [torch.empty((B,), dtype=torch.float64).pin_memory() for _ in range(Ke)]
+        for i in range(Ke):
+            idx = mbs[(W + i) % n_lists]
+            xb[i].numpy()[:] = X[idx]
+            yb[i].numpy()[:] = ys[0][idx]
+        import ctypes as C
+
+        mu = np.empty(m)
+        def e2e_step(i):
+            arr = (C.c_void_p * 1)(yb[i].data_ptr())
+            eng.ck(lib.agp_step_batch(eng.model, C.c_void_p(xb[i].data_ptr()), L.DTYPE_F64, L.LAYOUT_ROWMAJOR, arr, L.Y_REAL, B, rho))
+            eng.ck(lib.agp_get_posterior(eng.model, 0, L.dptr(mu), None, None, None))
+        for i in range(3):
+            e2e_step(i)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(Ke):
+            e2e_step(i)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        e2e = dict(value=Ke / dt, unit="iters/s", h2d_bytes_per_step=B * D * 8 + B * 8, d2h_bytes_per_step=m * 8 + 4,
+                   steps=Ke, call="agp_step_batch(host x[B,D] f64, host y[B]) + agp_get_posterior(mu)")
+    else:
+        e2e = dict(value=None, unit="iters/s", h2d_bytes_per_step=B * 8, d2h_bytes_per_step=0,
+                   note="latent-sharded run: measured at N=1 only")
+
+    if rank == 0:
+        cpu = cpu_baseline_sample() if (world == 1 and not args.no_cpu_baseline) else None
+        line = dict(metric=METRIC, value=value, unit="iters/s", n_gpus=world, steps=K, warmup=W, ms_per_step=ms / K,
+                    higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype={"f32": "f32 (fp32 SIMT contractions, f64 m x m tail)", "tf32x3": "tf32x3 (tcgen05, f64 m x m tail)", "f64": "f64"}[args.precision],
+                    data="synthetic",
+                    config=dict(workload=("C2: SVGP Logistic SqExp n=1e6 D=32 m=512 minibatch=8192" if world == 1 else
+                                          f"C2-shaped multi-output SVGP: {world} Logistic tasks x {world} latent GPs, one latent per GPU, moments all-gather per step"),
+                                l2="inputs larger than L2: every step gathers a new random minibatch from the resident 140 MB (X, |x|^2, y) arrays; no flush",
+                                graph=bool(args.graph and world == 1), precision=args.precision, **CFG),
+                    gpu_launches=int(launches), elbo_last=elbo, roofline=roof, cpu_baseline=cpu, e2e=e2e, clocks=clocks, phases=phases)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("AGP_BENCH_PRECISION", "f32"), choices=["f32", "tf32x3", "f64"])
+    ap.add_argument("--graph", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()
