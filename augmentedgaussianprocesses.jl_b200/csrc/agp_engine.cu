@@ -11,6 +11,7 @@
 
 #include "../../include/agp_b200.h"
 #include "agp_kernels.cuh"
+#include "agp_tail.cuh"
 #include "agp_umma.h"
 
 using namespace agp;
@@ -117,9 +118,11 @@ struct Engine : EngineBase {
     T* Linv_T = nullptr;
     double logdetK = 0.0;
     double *eta1c = nullptr, *eta2c = nullptr;               // canonical natural parameters (valid when !white_valid or after sync)
-    double *eta1v = nullptr, *eta2v = nullptr, *muv = nullptr, *SigmaV = nullptr;  // whitened state
+    double *eta1v = nullptr, *eta2v = nullptr, *muv = nullptr;  // whitened state
+    double* tvec = nullptr; bool muv_valid = false;             // t = X eta1_v ; mu_v = X^T t computed lazily
+    double *Xv = nullptr, *Dinv = nullptr;  // X = chol(P_v)^-1 (lower triangular; Sigma_v = X^T X), its diagonal blocks
     bool white_valid = false;                                // whitened state is the live one
-    T* SigmaV_T = nullptr;
+    T* Xv_T = nullptr;
     T *Knm = nullptr, *V = nullptr, *VS = nullptr;           // [Bcap][ldm]
     double* Ktilde = nullptr;
     T* Gpart = nullptr;
@@ -258,8 +261,9 @@ struct Engine : EngineBase {
       CKS(dalloc(&L.mu0, mp)); CKS(dalloc(&L.mu0v, mp));
       CKS(dalloc(&L.Linv_T, (size_t)m * ldm));
       CKS(dalloc(&L.eta1c, mp)); CKS(dalloc(&L.eta2c, (size_t)mp * mp));
-      CKS(dalloc(&L.eta1v, mp)); CKS(dalloc(&L.eta2v, (size_t)mp * mp)); CKS(dalloc(&L.muv, mp)); CKS(dalloc(&L.SigmaV, (size_t)mp * mp));
-      CKS(dalloc(&L.SigmaV_T, (size_t)m * ldm));
+      CKS(dalloc(&L.eta1v, mp)); CKS(dalloc(&L.eta2v, (size_t)mp * mp)); CKS(dalloc(&L.muv, mp)); CKS(dalloc(&L.tvec, mp));
+      CKS(dalloc(&L.Xv, (size_t)mp * mp)); CKS(dalloc(&L.Dinv, (size_t)mp * POTF2_NB));
+      CKS(dalloc(&L.Xv_T, (size_t)m * ldm));
       CKS(dalloc(&L.Knm, (size_t)Bcap * ldm)); CKS(dalloc(&L.V, (size_t)Bcap * ldm)); CKS(dalloc(&L.VS, (size_t)Bcap * ldm));
       CKS(dalloc(&L.Ktilde, ldB));
       CKS(dalloc(&L.Gpart, (size_t)n_split * m * ldm));
@@ -309,6 +313,8 @@ struct Engine : EngineBase {
     CKS(dalloc(&d_out, 8));
     CKS(reset_local_vars());
     CK(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, potf2_smem()));
+    CK(cudaFuncSetAttribute(tail_potf2_first_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM));
+    CK(cudaFuncSetAttribute(tail_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM));
     CK(cudaStreamSynchronize(st()));
     return AGP_OK;
   }
@@ -331,7 +337,7 @@ struct Engine : EngineBase {
     if (gexec) cudaGraphExecDestroy(gexec);
     for (auto& L : lat) {
       void* ps[] = {L.Z, L.zz, L.Zd, L.zzd, L.Lc, L.Linv, L.Kinv, L.mu0, L.mu0v, L.Linv_T, L.eta1c, L.eta2c, L.eta1v, L.eta2v,
-                    L.muv, L.SigmaV, L.SigmaV_T, L.Knm, L.V, L.VS, L.Ktilde, L.Gpart, L.v1, L.P, L.X, L.W, L.logdetP};
+                    L.muv, L.tvec, L.Xv, L.Dinv, L.Xv_T, L.Knm, L.V, L.VS, L.Ktilde, L.Gpart, L.v1, L.P, L.X, L.W, L.logdetP};
       for (void* p : ps) cudaFree(p);
       umma_latent_free(L.um);
     }
@@ -603,20 +609,21 @@ struct Engine : EngineBase {
           ph_end();
         }
       }
-      if (need_var) {
+      {
         ph_begin(PH_KSIGMA);
         if (prec == AGP_PREC_TF32X3) {
-          CKS(umma_gemm_nt(ctx_err(), L.um, UM_V, UM_SIGMA, (float*)(void*)L.VS, B, m, st()));
+          CKS(umma_gemm_nt(ctx_err(), L.um, UM_V, UM_X, (float*)(void*)L.VS, B, m, st()));
         } else {
-          GemmParams<T> s{};  // V Sigma_v  (kappa * Sigma of latentgp.jl:189)
-          s.A = L.V; s.lda = ldm; s.B = L.SigmaV_T; s.ldb = ldm; s.C = L.VS; s.ldc = ldm; s.M = B; s.N = m; s.K = m; s.alpha = 1.0;
+          GemmParams<T> s{};  // V X^T with Sigma_v = X^T X  (kappa * Sigma of latentgp.jl:189); X is lower triangular
+          s.A = L.V; s.lda = ldm; s.B = L.Xv_T; s.ldb = ldm; s.C = L.VS; s.ldc = ldm; s.M = B; s.N = m; s.K = m; s.alpha = 1.0;
+          s.k_to_diag = 1;
           gemm_simt_launch<T, false, false, EPI_PLAIN>(s, 1, st());
         }
         ++launches;
         ph_end();
       }
       ph_begin(PH_ROWSTATS);
-      rowstats_kernel<T><<<(B * 32 + 255) / 256, 256, 0, st()>>>(L.V, need_var ? L.VS : L.V, L.muv, B, m, ldm, L.variance + jitter,
+      rowstats_kernel<T><<<(B * 32 + 255) / 256, 256, 0, st()>>>(L.V, L.VS, L.tvec, B, m, ldm, L.variance + jitter,
                                                                  L.Ktilde, mean_out + (size_t)q * out_ld, var_out + (size_t)q * out_ld,
                                                                  status, fresh_kernel_matrices ? 1 : 0);
       ++launches;
@@ -662,7 +669,8 @@ struct Engine : EngineBase {
       Latent& L = lat[q];
       ph_begin(PH_GRADMU);
       CK(cudaMemsetAsync(L.v1, 0, m * sizeof(double), st()));
-      gemv_t_kernel<T><<<dim3((m + 127) / 128, (B + 63) / 64), 128, 0, st()>>>(L.V, ldm, gmu + (size_t)q * ldB, B, m, L.v1);
+      { int rpb = std::max(64, (int)rup((B + 15) / 16, 8));
+        gemv_t_kernel<T><<<dim3((m + 31) / 32, (B + rpb - 1) / rpb), dim3(32, 8), 0, st()>>>(L.V, ldm, gmu + (size_t)q * ldB, B, m, rpb, L.v1); }
       ++launches;
       ph_end();
       ph_begin(PH_GRAM);
@@ -699,16 +707,43 @@ struct Engine : EngineBase {
     return AGP_OK;
   }
 
-  // global_update!(gp) (inference/inference.jl:25-28) in the whitened basis: Sigma_v = inv(P_v), mu_v = Sigma_v eta1_v
-  int eta_to_moments(Latent& L) {
-    spd_inverse(L.P, L.X, L.W, L.SigmaV, L.logdetP);
-    ph_begin(PH_FINAL);
-    symmetrize_shadow_kernel<T><<<dim3((m + 127) / 128, m), 128, 0, st()>>>(L.SigmaV, mp, m, L.SigmaV_T, ldm);
-    symv_kernel<<<(m * 32 + 255) / 256, 256, 0, st()>>>(L.SigmaV, mp, m, L.eta1v, L.muv);
-    launches += 2;
-    if (prec == AGP_PREC_TF32X3) { CKS(umma_split_matrix(ctx_err(), L.um, UM_SIGMA, (const float*)(const void*)L.SigmaV_T, m, st())); ++launches; }
+  // fused blocked Cholesky + inverse of the factor (agp_tail.cuh): P (lower tiles, destroyed) -> Xv = chol(P)^-1
+  void chol_inv(Latent& L) {
+    ph_begin(PH_CHOL);
+    TailStepParams tp{};
+    tp.P = L.P; tp.W = L.W; tp.Xout = L.Xv; tp.Dinv = L.Dinv; tp.ld = mp; tp.nblk = mp / TNB; tp.logdet = L.logdetP; tp.status = status;
+    tail_potf2_first_kernel<<<1, TAIL_THREADS, TAIL_SMEM, st()>>>(tp);
+    ++launches;
+    for (int k = 0; k < tp.nblk; ++k) {
+      int r = tp.nblk - 1 - k;
+      int tiles = r * (r + 1) / 2 + r * (k + 1) + k;
+      if (tiles == 0) continue;
+      tp.k = k;
+      tail_step_kernel<<<tiles, TAIL_THREADS, TAIL_SMEM, st()>>>(tp);
+      ++launches;
+    }
     ph_end();
+  }
+
+  // global_update!(gp) (inference/inference.jl:25-28) in the whitened basis: Sigma_v = inv(P_v) = X^T X is kept in
+  // factored form (X = chol(P_v)^-1), mu_v = Sigma_v eta1_v = X^T (X eta1_v)
+  int eta_to_moments(Latent& L) {
+    chol_inv(L);
+    ph_begin(PH_FINAL);
+    float* hi = nullptr; float* lo = nullptr;
+    if (prec == AGP_PREC_TF32X3) { hi = L.um.hi[UM_X]; lo = L.um.lo[UM_X]; }
+    x_finalize_kernel<T><<<m, 128, 0, st()>>>(L.Xv, mp, m, L.eta1v, L.Xv_T, ldm, hi, lo, L.tvec);
+    ++launches;
+    ph_end();
+    L.muv_valid = false;
     return AGP_OK;
+  }
+  // mu_v = X^T t (only getters / the ELBO need it)
+  void ensure_muv(Latent& L) {
+    if (L.muv_valid) return;
+    matvec_t_kernel<<<(m + 127) / 128, 128, 0, st()>>>(L.Xv, mp, m, L.tvec, L.muv);
+    ++launches;
+    L.muv_valid = true;
   }
 
   void drop_graph() {
@@ -739,6 +774,7 @@ struct Engine : EngineBase {
       }
       CK(cudaGraphLaunch(gexec, st()));
       launches += g_launches;
+      for (auto& L : lat) L.muv_valid = false;
       curB = B; cur_from_batch = false; have_step = true;
       return AGP_OK;
     }
@@ -798,7 +834,8 @@ struct Engine : EngineBase {
     for (int q = 0; q < Ql; ++q) {
       Latent& L = lat[q];
       CK(cudaMemsetAsync(d_out + 4, 0, 2 * sizeof(double), st()));
-      gauss_kl_kernel<<<1, 256, 0, st()>>>(L.SigmaV, mp, m, L.muv, L.mu0v, d_out + 4);
+      ensure_muv(L);
+      gauss_kl_x_kernel<<<1, 1024, 0, st()>>>(L.Xv, mp, m, L.muv, L.mu0v, d_out + 4);
       ++launches;
       double t2[2], ldp;
       CK(cudaMemcpyAsync(t2, d_out + 4, 2 * sizeof(double), cudaMemcpyDeviceToHost, st()));
@@ -826,10 +863,11 @@ struct Engine : EngineBase {
     }
     // canonical from whitened, fp64:  mu = L mu_v,  Sigma = L Sigma_v L^T,  eta1 = L^-T eta1_v,  eta2 = L^-T eta2_v L^-1
     if (eta1 || eta2) canonicalize(L);
-    if (mu) { symv_kernel<<<(m * 32 + 255) / 256, 256, 0, st()>>>(L.Lc, mp, m, L.muv, L.v1); ++launches; }
+    if (mu) { ensure_muv(L); symv_kernel<<<(m * 32 + 255) / 256, 256, 0, st()>>>(L.Lc, mp, m, L.muv, L.v1); ++launches; }
     if (Sigma) {
-      dgemm(false, false, L.SigmaV, L.Lc, L.W, 1.0, 0.0);  // W = Sigma_v L^T   (NT)
-      dgemm(false, true, L.Lc, L.W, L.X, 1.0, 0.0);        // X = L W
+      dgemm(true, true, L.Xv, L.Xv, L.X, 1.0, 0.0);        // Sigma_v = X^T X
+      dgemm(false, false, L.X, L.Lc, L.W, 1.0, 0.0);       // W = Sigma_v L^T   (NT)
+      dgemm(false, true, L.Lc, L.W, L.X, 1.0, 0.0);        // Sigma = L W
     }
     CK(cudaStreamSynchronize(st()));
     if (mu) CK(cudaMemcpy(mu, L.v1, m * 8, cudaMemcpyDeviceToHost));

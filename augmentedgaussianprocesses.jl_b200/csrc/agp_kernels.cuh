@@ -62,8 +62,9 @@ __global__ void idx_select_kernel(const int64_t* __restrict__ pool, int64_t n_li
 // ------------------------------------------------------------------------------------------------
 // per-row statistics in the whitened basis (V = Knm L^-T, q(v) = N(mu_v, Sigma_v), u = L v):
 //   Ktilde = kdiag + jitter - rowsum(V .* V)        == kdiag + jitter - diag_ABt(kappa, Knm)   latentgp.jl:212
-//   mean_f = V mu_v                                  == kappa * mu                              latentgp.jl:179
-//   var_f  = rowsum((V Sigma_v) .* V) + Ktilde       == diag_ABt(kappa*Sigma, kappa) + Ktilde   latentgp.jl:189
+//   mean_f = V mu_v = (V X^T) t,  t = X eta1_v         == kappa * mu                              latentgp.jl:179
+//   var_f  = rowsum((V X^T).^2) + Ktilde, Sigma_v = X^T X  == diag_ABt(kappa*Sigma, kappa) + Ktilde   latentgp.jl:189
+//            (VS below holds V X^T, X = inverse Cholesky factor of P_v = -2 eta2_v)
 // one warp per minibatch row; sums accumulate in fp64 whatever T is.
 // ------------------------------------------------------------------------------------------------
 template <typename T>
@@ -86,10 +87,10 @@ __global__ void rowstats_kernel(const T* __restrict__ V, const T* __restrict__ V
     if constexpr (W == 4) { av[2] = a.z; av[3] = a.w; cv[2] = c.z; cv[3] = c.w; }
 #pragma unroll
     for (int q = 0; q < W; ++q) {
-      double muj = (j + q < m) ? mu[j + q] : 0.0;
+      double muj = (j + q < m) ? mu[j + q] : 0.0;   // mu holds t = X eta1_v
       s1 += av[q] * av[q];
-      s2 += av[q] * muj;
-      s3 += av[q] * cv[q];
+      s2 += cv[q] * muj;
+      s3 += cv[q] * cv[q];
     }
   }
   s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
@@ -107,16 +108,27 @@ __global__ void rowstats_kernel(const T* __restrict__ V, const T* __restrict__ V
   }
 }
 
-// out[j] += sum_b kappa[b][j] * g[b]   (transpose(kappa) * grad_mu of analyticVI.jl:168; rho applied later)
+// out[j] += sum_b V[b][j] * g[b]   (transpose(kappa) * grad_mu of analyticVI.jl:168, whitened; rho applied later)
+// block = 32 columns x 8 row lanes; grid = (ceil(m/32), row_chunks); one atomicAdd per column per block
 template <typename T>
-__global__ void gemv_t_kernel(const T* __restrict__ kappa, int64_t ld, const double* __restrict__ g, int B, int m,
+__global__ void gemv_t_kernel(const T* __restrict__ V, int64_t ld, const double* __restrict__ g, int B, int m, int rows_per_block,
                               double* __restrict__ out) {
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
-  int b0 = blockIdx.y * 64, b1 = min(B, b0 + 64);
-  if (j >= m) return;
+  const int j = blockIdx.x * 32 + threadIdx.x;
+  const int b0 = blockIdx.y * rows_per_block, b1 = min(B, b0 + rows_per_block);
   double s = 0.0;
-  for (int b = b0; b < b1; ++b) s += (double)kappa[(int64_t)b * ld + j] * g[b];
-  atomicAdd(out + j, s);
+  if (j < m) {
+#pragma unroll 4
+    for (int b = b0 + threadIdx.y; b < b1; b += 8) s += (double)V[(int64_t)b * ld + j] * g[b];
+  }
+  __shared__ double sh[8][33];
+  sh[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && j < m) {
+    double a = 0.0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) a += sh[r][threadIdx.x];
+    atomicAdd(out + j, a);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

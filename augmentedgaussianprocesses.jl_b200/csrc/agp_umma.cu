@@ -340,7 +340,7 @@ int umma_gemm_nt(std::string* err, UmmaLatent& u, int a_which, int b_which, floa
   const int total_kb = u.m / BK;
   dim3 grid(N / BN, M / BM, 1);
   umma_gemm_nt_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mp->hi[a_which], mp->lo[a_which], mp->hi[b_which], mp->lo[b_which], C,
-                                                             (int64_t)u.ldm, 0, total_kb, total_kb, b_which == UM_LINV ? 1 : 0);
+                                                             (int64_t)u.ldm, 0, total_kb, total_kb, (b_which == UM_LINV || b_which == UM_X) ? 1 : 0);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(err, "umma_gemm_nt_kernel", e);
   return 0;

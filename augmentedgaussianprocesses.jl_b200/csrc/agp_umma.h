@@ -8,7 +8,7 @@
 
 namespace agp {
 
-enum UmmaMat : int { UM_KNM = 0, UM_V = 1, UM_LINV = 2, UM_SIGMA = 3, UM_COUNT = 4 };
+enum UmmaMat : int { UM_KNM = 0, UM_V = 1, UM_LINV = 2, UM_X = 3, UM_COUNT = 4 };
 
 struct UmmaLatent {
   int m = 0, ldm = 0, Bcap = 0;
