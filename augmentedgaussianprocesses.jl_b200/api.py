@@ -663,13 +663,18 @@ def _moment_views(model, eng):
     return model._mviews[1]
 
 
-def _allgather_moments(model, eng):
+def _allgather_rows(views, q0: int, ql: int, ld: int):
+    """In-place all-gather of the owned rows [q0, q0+ql) of flat [Q*ld] arrays (every rank owns ql rows)."""
     import torch.distributed as dist
 
-    (mean_v, var_v), ld = _moment_views(model, eng)
-    q0, ql = model._latent_range()
-    for v in (mean_v, var_v):
+    for v in views:
         dist.all_gather_into_tensor(v, v[q0 * ld : (q0 + ql) * ld])
+
+
+def _allgather_moments(model, eng):
+    views, ld = _moment_views(model, eng)
+    q0, ql = model._latent_range()
+    _allgather_rows(views, q0, ql, ld)
 
 
 def _sharded_step(model, eng, ip, B, rho):

@@ -281,7 +281,9 @@ __global__ void x_finalize_kernel(const double* __restrict__ X, int64_t ld, int 
       asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(fv));
       float h = __uint_as_float(u);
       hi[(int64_t)i * lds + j] = h;
-      lo[(int64_t)i * lds + j] = fv - h;
+      float lv = fv - h;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(lv));
+      lo[(int64_t)i * lds + j] = __uint_as_float(u);
     }
   }
   __shared__ double sh[8];

@@ -210,17 +210,23 @@ umma_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   }
 }
 
-// src (rows x cols, ld) -> hi = rna_tf32(src), lo = src - hi
+// round-to-nearest fp32 -> tf32 (the tensor core would otherwise truncate the low 13 mantissa bits)
+__device__ __forceinline__ float tf32_rna(float v) {
+  uint32_t t;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v));
+  return __uint_as_float(t);
+}
+
+// src (rows x cols, ld) -> hi = rna_tf32(src), lo = rna_tf32(src - hi)
 __global__ void split_tf32_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo, int64_t n4) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n4) return;
   float4 v = reinterpret_cast<const float4*>(src)[i];
   float4 h, l;
-  uint32_t t;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.x)); h.x = __uint_as_float(t); l.x = v.x - h.x;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.y)); h.y = __uint_as_float(t); l.y = v.y - h.y;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.z)); h.z = __uint_as_float(t); l.z = v.z - h.z;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v.w)); h.w = __uint_as_float(t); l.w = v.w - h.w;
+  h.x = tf32_rna(v.x); l.x = tf32_rna(v.x - h.x);
+  h.y = tf32_rna(v.y); l.y = tf32_rna(v.y - h.y);
+  h.z = tf32_rna(v.z); l.z = tf32_rna(v.z - h.z);
+  h.w = tf32_rna(v.w); l.w = tf32_rna(v.w - h.w);
   reinterpret_cast<float4*>(hi)[i] = h;
   reinterpret_cast<float4*>(lo)[i] = l;
 }
@@ -240,11 +246,9 @@ __global__ void scale_transpose_split_kernel(const float* __restrict__ V, int64_
 #pragma unroll
   for (int r = ty; r < 32; r += 8) {
     float v = tile[tx][r];
-    uint32_t t;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v));
-    float h = __uint_as_float(t);
+    float h = tf32_rna(v);
     hi[(int64_t)(j0 + r) * ldt + b0 + tx] = h;
-    lo[(int64_t)(j0 + r) * ldt + b0 + tx] = v - h;
+    lo[(int64_t)(j0 + r) * ldt + b0 + tx] = tf32_rna(v - h);
   }
 }
 

@@ -1,0 +1,136 @@
+"""CPU tests of the oracle: the known-answer tests the reference ships for this path (test/functions/utils.jl,
+test/likelihood/multiclass.jl, test/inference/analyticVI.jl), the golden fixtures, and the reference's behavioural
+thresholds (test/testingtools.jl:223-253)."""
+import glob
+import math
+import os
+
+import numpy as np
+import pytest
+
+import agp_oracle as O
+from problems import make_data, oracle_kernel, oracle_lik, rel_fro
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_utils_identities():
+    """test/functions/utils.jl:2-49"""
+    assert O.JITTER_F64 == pytest.approx(1e-4) and O.JITTER_F32 == pytest.approx(1e-3) and O.JITTER_F16 == pytest.approx(1e-2)
+    rng = np.random.default_rng(42)
+    A, B, x = rng.random((2, 2)), rng.random((2, 2)), rng.random(2)
+    D = A @ A.T + np.eye(2)
+    L = np.linalg.cholesky(D)
+    assert O.invquad(L, x) == pytest.approx(x @ np.linalg.solve(D, x))
+    assert O.trace_ABt(A, B) == pytest.approx(np.trace(A @ B.T))
+    assert np.allclose(O.diag_ABt(A, B), np.diag(A @ B.T))
+    assert np.allclose(O.kdiagthetak(A, x), A.T @ np.diag(x) @ A)
+    assert np.allclose(O.rho_kdiagthetak(2.0, A, x), 2.0 * A.T @ np.diag(x) @ A)
+    assert O.safe_expcosh(2.0, 1.0) == pytest.approx(math.exp(2.0) / math.cosh(1.0))
+    assert O.logcosh(2.0) == pytest.approx(math.log(math.cosh(2.0)))
+    assert np.isfinite(O.safe_expcosh(800.0, 900.0))  # overflow branch
+
+
+def test_multiclass_mapping():
+    """test/likelihood/multiclass.jl:1-40 (indices are 0-based here, 1-based in Julia)"""
+    y = [1, 2, 3, 1, 1, 2, 3]
+    l = O.LogisticSoftMaxLikelihood(3)
+    O.create_mapping(l, y)
+    assert sorted(l.class_mapping) == [1, 2, 3] and l.ind_mapping == {1: 0, 2: 1, 3: 2}
+    assert np.array_equal(O.create_one_hot(l, y[:3]), np.eye(3, dtype=bool))
+    with pytest.raises(ValueError):
+        O.create_mapping(O.LogisticSoftMaxLikelihood(2), y)
+    l = O.LogisticSoftMaxLikelihood(3)
+    O.create_mapping(l, [1, 2, 1, 1])
+    assert l.class_mapping == [1, 2, 3] and l.n_latent == 3
+    assert np.array_equal(O.create_one_hot(l, [1, 2, 1, 1]), np.array([[1, 0, 0], [0, 1, 0], [1, 0, 0], [1, 0, 0]], bool))
+    ys = ["b", "a", "c", "a", "a"]
+    l = O.LogisticSoftMaxLikelihood(3)
+    O.create_mapping(l, ys)
+    assert l.class_mapping == ["b", "a", "c"] and l.ind_mapping == {"b": 0, "a": 1, "c": 2}
+    assert np.array_equal(O.create_one_hot(l, ys), np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1], [0, 1, 0], [0, 1, 0]], bool))
+    l = O.LogisticSoftMaxLikelihood(["a", "b", "c"])
+    assert l.ind_mapping == {"a": 0, "b": 1, "c": 2}
+    assert np.array_equal(O.create_one_hot(l, ys), np.array([[0, 1, 0], [1, 0, 0], [0, 0, 1], [1, 0, 0], [1, 0, 0]], bool))
+    l = O.LogisticSoftMaxLikelihood(3)
+    Y = O.treat_labels(ys, l)
+    assert l.class_mapping == ["b", "a", "c"] and Y.shape == (5, 3)
+
+
+def test_analyticvi_objects():
+    """test/inference/analyticVI.jl:1-20"""
+    i = O.AnalyticVI()
+    assert i.rho == 1.0 and i.stoch is False
+    i = O.AnalyticSVI(5)
+    i.rho = 20 / 5
+    assert i.rho == 4.0 and i.stoch is True and i.batchsize == 5
+    with pytest.raises(ValueError):
+        O.RobbinsMonro(0.4)
+    st, d = O.RobbinsMonro().apply(1, np.ones(2))
+    assert st == 2 and np.allclose(d, 2.0**-0.51)  # first step lr = (1+1)^-0.51 (quirk Q9)
+
+
+def test_kernel_forms():
+    rng = np.random.default_rng(0)
+    X, Z = rng.standard_normal((30, 5)), rng.standard_normal((7, 5))
+    for kind in ("sqexp", "matern32", "matern52"):
+        k = O.Kernel(kind, scale=0.7, variance=1.7)
+        assert np.allclose(O.kernelmatrix(k, X, Z), O.kernelmatrix_exact(k, X, Z), atol=1e-12)
+        assert np.allclose(np.diag(O.kernelmatrix(k, X)), 1.7)
+    assert O.kernelmatrix(O.Kernel("sqexp"), np.zeros((1, 2)), np.array([[1.0, 1.0]]))[0, 0] == pytest.approx(math.exp(-1.0))
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "*.npz"))))
+def test_golden_fixtures(path):
+    g = np.load(path, allow_pickle=True)
+    lik = str(g["lik"])
+    likelihood = O.GaussianLikelihood(1e-3) if lik == "gaussian_c1" else oracle_lik(O, lik, max(int(g["n_class"]), 3))
+    B, iters = int(g["B"]), int(g["iters"])
+    inf = O.AnalyticSVI(B) if bool(g["stoch"]) else O.AnalyticVI()
+    model = O.SVGP(oracle_kernel(O, str(g["kind"]), float(g["scale"]), float(g["variance"])), likelihood, inf, g["Z"])
+    model, state = O.train(model, g["X"], g["y"], iters, minibatches=list(g["minibatches"]))
+    for q, gp in enumerate(model.f):
+        assert rel_fro(gp.mu, g["mu"][q]) < 1e-9 and rel_fro(gp.Sigma, g["Sigma"][q]) < 1e-9
+    assert model.ELBO(state, state["y_batch"]) == pytest.approx(float(g["elbo"]), rel=1e-9)
+    mu_p, var_p = O.predict_f(model, g["X"][:64], cov=True)
+    assert rel_fro(mu_p, g["pred_mu"]) < 1e-9 and rel_fro(var_p, g["pred_var"]) < 1e-8
+
+
+@pytest.mark.parametrize("lik,problem", [("gaussian", "Regression"), ("studentt", "Regression"), ("logistic", "Classification"),
+                                         ("logisticsoftmax", "MultiClass")])
+def test_testconv_thresholds(lik, problem):
+    """test/testingtools.jl:223-253 thresholds on a small problem, AnalyticVI and AnalyticSVI(10)-style"""
+    X, y, Z, mbs, F, rng = make_data(lik, 100, 2, 10, 10, 6, seed=3)
+    for inf in (O.AnalyticVI(), O.AnalyticSVI(10)):
+        m = O.SVGP(oracle_kernel(O, "sqexp", 1.0, 1.0), oracle_lik(O, lik), inf, Z)
+        m, st = O.train(m, X, y, 6, minibatches=mbs)
+        yp = O.predict_y(m, X)
+        if problem == "Regression":
+            assert np.mean(np.abs(yp - F[:, 0])) < 15
+            assert np.all(O.proba_y(m, X)[1] > 0)
+        elif problem == "Classification":
+            assert np.mean(yp != (y > 0)) < 0.5
+            assert np.all(O.proba_y(m, X)[1] >= 0)
+        else:
+            assert np.mean(yp != y) < 0.9
+        assert np.isfinite(m.ELBO(st, st["y_batch"]))
+
+
+def test_gaussian_avi_is_exact_posterior():
+    """With a Gaussian likelihood one full-batch CAVI step gives the closed-form sparse posterior."""
+    X, y, Z, _, F, rng = make_data("gaussian", 200, 2, 12, 200, 1, seed=5)
+    k = oracle_kernel(O, "sqexp", 1.0, 1.0)
+    m = O.SVGP(k, O.GaussianLikelihood(1e-2), O.AnalyticVI(), Z)
+    m, st = O.train(m, X, y, 1)
+    Kmm = O.kernelmatrix(k, Z) + 1e-4 * np.eye(12)
+    Knm = O.kernelmatrix(k, X, Z)
+    kap = np.linalg.solve(Kmm, Knm.T).T
+    S = np.linalg.inv(kap.T @ kap / 1e-2 + np.linalg.inv(Kmm))
+    assert rel_fro(m.f[0].Sigma, S) < 1e-8 and rel_fro(m.f[0].mu, S @ kap.T @ y / 1e-2) < 1e-8
+
+
+def test_ktilde_error():
+    X, y, Z, mbs, F, rng = make_data("gaussian", 100, 2, 8, 20, 1)
+    m = O.SVGP(O.Kernel("sqexp"), O.GaussianLikelihood(), O.AnalyticSVI(20), Z, jitter=-0.5)
+    with pytest.raises((FloatingPointError, np.linalg.LinAlgError)):
+        O.train(m, X, y, 1, minibatches=mbs)
