@@ -1,0 +1,124 @@
+# AGPB200.jl -- reference-side binding of libagp_b200.so (UNVERIFIED: Julia is not installed in the build image).
+#
+# Overrides the one method of AugmentedGaussianProcesses.jl that the engine replaces,
+#     update_parameters!(model::SVGP, state, x, y)            (src/training/training.jl:140-144)
+# plus ELBO(model, state, y) (src/inference/analyticVI.jl:255) and _predict_f (src/training/predictions.jl:25),
+# for models built with AnalyticVI / AnalyticSVI and optimiser = false, Zoptimiser = false.
+# Data crosses the ABI exactly as the reference holds it: X as the column-major parent Matrix{Float64} of the
+# RowVecs (src/data/datacontainer.jl:64-66), minibatches as 1-based Vector{Int}, y as Vector{Float64}.
+module AGPB200
+
+using AugmentedGaussianProcesses
+const AGP = AugmentedGaussianProcesses
+using KernelFunctions
+
+const LIB = get(ENV, "AGP_B200_LIB", "libagp_b200.so")
+
+struct ModelDesc  # mirrors agp_model_desc (include/agp_b200.h)
+    model_kind::Int32; n_latent_global::Int32; latent_begin::Int32; n_latent_local::Int32
+    m::Int32; D::Int32; batch_capacity::Int32; precision::Int32; stochastic::Int32
+    rm_kappa::Float64; rm_tau::Float64; jitter::Float64
+    n_task::Int32
+    lik_kind::Ptr{Int32}; lik_p0::Ptr{Float64}; lik_p1::Ptr{Float64}; A::Ptr{Float64}
+    kernel_kind::Ptr{Int32}; kernel_scale::Ptr{Float64}; kernel_variance::Ptr{Float64}
+    Z::Ptr{Float64}; mu0::Ptr{Float64}
+end
+
+mutable struct Engine
+    ctx::Ptr{Cvoid}
+    model::Ptr{Cvoid}
+    uploaded::UInt   # objectid of the data parent currently resident
+end
+
+function check(e::Engine, rc::Cint)
+    rc == 0 && return
+    msg = unsafe_string(ccall((:agp_last_error, LIB), Cstring, (Ptr{Cvoid},), e.ctx))
+    rc == 3 && error("K̃ has negative values")                       # gpblocks/latentgp.jl:213
+    rc == 4 && throw(LinearAlgebra.PosDefException(0))                # cholesky()
+    error(msg)
+end
+
+const ENGINES = IdDict{Any,Engine}()
+
+lik_code(::AGP.GaussianLikelihood) = (Int32(0))
+lik_code(::AGP.BernoulliLikelihood{<:AGP.LogisticLink}) = Int32(1)
+lik_code(::AGP.StudentTLikelihood) = Int32(2)
+lik_code(::AGP.MultiClassLikelihood{<:AGP.LogisticSoftMaxLink}) = Int32(3)
+
+# kernel -> (kind, scale, variance); supports [σ² *] {SqExponential, Matern32, Matern52} [∘ ScaleTransform(s)]
+function kernel_params(k)
+    var = 1.0; s = 1.0
+    if k isa ScaledKernel; var = only(k.σ²); k = k.kernel; end
+    if k isa TransformedKernel; s = only(k.transform.s); k = k.kernel; end
+    kind = k isa SqExponentialKernel ? 0 : k isa Matern32Kernel ? 1 : k isa Matern52Kernel ? 2 : error("kernel not supported by AGPB200")
+    return Int32(kind), Float64(s), Float64(var)
+end
+
+function engine(model::SVGP{T}, B::Int) where {T}
+    haskey(ENGINES, model) && return ENGINES[model]
+    inf = AGP.inference(model); l = AGP.likelihood(model)
+    Q = AGP.n_latent(model); m = AGP.dim(model.f[1]); D = length(first(model.f[1].Z))
+    Z = zeros(Float64, D, m, Q)                       # row-major [Q][m][D] for C == column-major (D, m, Q) here
+    for (q, gp) in enumerate(model.f), (i, z) in enumerate(gp.Z); Z[:, i, q] .= z; end
+    kp = [kernel_params(AGP.kernel(gp)) for gp in model.f]
+    kk = Int32[p[1] for p in kp]; ks = Float64[p[2] for p in kp]; kv = Float64[p[3] for p in kp]
+    lk = Int32[lik_code(l)]
+    p0 = Float64[l isa AGP.GaussianLikelihood ? AGP.noise(l) : l isa AGP.StudentTLikelihood ? l.ν : 0.0]
+    p1 = Float64[l isa AGP.StudentTLikelihood ? l.σ : 0.0]
+    o = AGP.opt(inf).optimiser
+    κ, τ = o isa RobbinsMonro ? (Float64(o.κ), Float64(o.τ)) : (0.51, 1.0)
+    ctx = Ref{Ptr{Cvoid}}(C_NULL); mdl = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:agp_ctx_create, LIB), Cint, (Cint, Ptr{Cvoid}, Ref{Ptr{Cvoid}}), 0, C_NULL, ctx)
+    rc == 0 || error("agp_ctx_create failed (no CUDA device; there is no CPU fallback)")
+    e = Engine(ctx[], C_NULL, 0)
+    GC.@preserve Z kk ks kv lk p0 p1 begin
+        d = Ref(ModelDesc(0, Q, 0, Q, m, D, B, 2 #= tf32x3 =#, AGP.is_stochastic(inf) ? 1 : 0, κ, τ, Float64(T(AGP.jitt)), 1,
+                          pointer(lk), pointer(p0), pointer(p1), C_NULL, pointer(kk), pointer(ks), pointer(kv), pointer(Z), C_NULL))
+        check(e, ccall((:agp_model_create, LIB), Cint, (Ptr{Cvoid}, Ref{ModelDesc}, Ref{Ptr{Cvoid}}), e.ctx, d, mdl))
+    end
+    e.model = mdl[]
+    ENGINES[model] = e
+    return e
+end
+
+# ---- the override -------------------------------------------------------------------------------------
+function AGP.update_parameters!(model::SVGP{T,L,<:AnalyticVI}, state, x::SubArray, y) where {T,L}
+    rows = x.parent                                   # RowVecs over the n×D Matrix
+    idx = Int64.(x.indices[1])                        # 1-based minibatch (training.jl:51-55)
+    B = length(idx)
+    e = engine(model, AGP.batchsize(AGP.inference(model)))
+    if e.uploaded != objectid(rows.X)
+        yall = parent(y)
+        ys = Ptr{Cvoid}[pointer(yall)]
+        GC.@preserve yall ys check(e, ccall((:agp_data_upload, LIB), Cint,
+            (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Int64, Ptr{Ptr{Cvoid}}, Cint),
+            e.model, rows.X, 0 #= f64 =#, 0 #= column-major =#, size(rows.X, 1), ys, yall isa AbstractVector{Float64} ? 0 : 1))
+        e.uploaded = objectid(rows.X)
+    end
+    if AGP.isHPupdated(AGP.inference(model))
+        check(e, ccall((:agp_refresh_K, LIB), Cint, (Ptr{Cvoid},), e.model))      # compute_K
+        AGP.setHPupdated!(AGP.inference(model), false)
+    end
+    ρ = Float64(AGP.ρ(AGP.inference(model)))
+    GC.@preserve idx check(e, ccall((:agp_step, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Int32, Int32, Float64),
+                                    e.model, idx, B, 1, ρ))
+    pull_posterior!(model, e)                          # keep model.f[k].post in sync for Julia-side consumers
+    return state
+end
+
+function pull_posterior!(model, e::Engine)
+    for (q, gp) in enumerate(model.f)
+        m = AGP.dim(gp); μ = zeros(m); Σ = zeros(m, m); η₁ = zeros(m); η₂ = zeros(m, m)
+        check(e, ccall((:agp_get_posterior, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                       e.model, q - 1, μ, Σ, η₁, η₂))
+        gp.post.μ .= μ; gp.post.Σ.data .= Σ; gp.post.η₁ .= η₁; gp.post.η₂.data .= η₂   # symmetric: row/column-major agree
+    end
+end
+
+function AGP.ELBO(model::SVGP{T,L,<:AnalyticVI}, state::NamedTuple, y) where {T,L}
+    e = ENGINES[model]; out = zeros(3)
+    check(e, ccall((:agp_elbo, LIB), Cint, (Ptr{Cvoid}, Float64, Ptr{Float64}), e.model, Float64(AGP.ρ(AGP.inference(model))), out))
+    return out[1] - out[2] - out[3]
+end
+
+end # module
