@@ -125,6 +125,7 @@ struct Engine : EngineBase {
     T* Xv_T = nullptr;
     T *Knm = nullptr, *V = nullptr, *VS = nullptr;           // [Bcap][ldm]
     double* Ktilde = nullptr;
+    double* racc = nullptr;                                  // [3][ldB] fused row-statistic accumulators (tensor-core path)
     T* Gpart = nullptr;
     double* v1 = nullptr;
     double *P = nullptr, *X = nullptr, *W = nullptr;  // tail workspaces [mp][mp]
@@ -143,6 +144,7 @@ struct Engine : EngineBase {
   void* stage = nullptr; size_t stage_bytes = 0;
   int64_t* idx_pool = nullptr; int64_t n_lists = 0; int pool_B = 0;
   int64_t* idx_cur = nullptr;
+  T* xx_cur = nullptr;   // squared norms of the current minibatch rows
   int64_t* counters = nullptr;  // [0] RM t (starts 1), [1] cursor
   int* status = nullptr;
   int *d_lik_kind = nullptr; double *d_p0 = nullptr, *d_p1 = nullptr, *d_A = nullptr;
@@ -265,7 +267,7 @@ struct Engine : EngineBase {
       CKS(dalloc(&L.Xv, (size_t)mp * mp)); CKS(dalloc(&L.Dinv, (size_t)mp * POTF2_NB));
       CKS(dalloc(&L.Xv_T, (size_t)m * ldm));
       CKS(dalloc(&L.Knm, (size_t)Bcap * ldm)); CKS(dalloc(&L.V, (size_t)Bcap * ldm)); CKS(dalloc(&L.VS, (size_t)Bcap * ldm));
-      CKS(dalloc(&L.Ktilde, ldB));
+      CKS(dalloc(&L.Ktilde, ldB)); CKS(dalloc(&L.racc, 3 * ldB));
       CKS(dalloc(&L.Gpart, (size_t)n_split * m * ldm));
       CKS(dalloc(&L.v1, mp));
       CKS(dalloc(&L.P, (size_t)mp * mp)); CKS(dalloc(&L.X, (size_t)mp * mp)); CKS(dalloc(&L.W, (size_t)mp * mp));
@@ -291,10 +293,12 @@ struct Engine : EngineBase {
       CK(cudaMemcpyAsync(L.zz, znt.data(), znt.size() * sizeof(T), cudaMemcpyHostToDevice, st()));
       if (L.has_mu0) CK(cudaMemcpyAsync(L.mu0, L.hmu0.data(), m * sizeof(double), cudaMemcpyHostToDevice, st()));
       CK(cudaStreamSynchronize(st()));
-      if (prec == AGP_PREC_TF32X3) CKS(umma_latent_alloc(ctx_err(), L.um, m, (int)ldm, Bcap, st()));
+      if (prec == AGP_PREC_TF32X3)
+        CKS(umma_latent_alloc(ctx_err(), L.um, m, (int)ldm, Bcap, (const float*)(const void*)L.Knm, (const float*)(const void*)L.V,
+                              (const float*)(const void*)L.Linv_T, (const float*)(const void*)L.Xv_T, st()));
     }
     CKS(dalloc(&Xb, (size_t)Bcap * Dp)); CKS(dalloc(&xxb, Bcap));
-    CKS(dalloc(&idx_cur, Bcap));
+    CKS(dalloc(&idx_cur, Bcap)); CKS(dalloc(&xx_cur, Bcap));
     CKS(dalloc(&counters, 2)); CKS(dalloc(&status, 1));
     int64_t c0[2] = {1, 0};
     CK(cudaMemcpyAsync(counters, c0, sizeof(c0), cudaMemcpyHostToDevice, st()));
@@ -337,11 +341,11 @@ struct Engine : EngineBase {
     if (gexec) cudaGraphExecDestroy(gexec);
     for (auto& L : lat) {
       void* ps[] = {L.Z, L.zz, L.Zd, L.zzd, L.Lc, L.Linv, L.Kinv, L.mu0, L.mu0v, L.Linv_T, L.eta1c, L.eta2c, L.eta1v, L.eta2v,
-                    L.muv, L.tvec, L.Xv, L.Dinv, L.Xv_T, L.Knm, L.V, L.VS, L.Ktilde, L.Gpart, L.v1, L.P, L.X, L.W, L.logdetP};
+                    L.muv, L.tvec, L.Xv, L.Dinv, L.Xv_T, L.Knm, L.V, L.VS, L.Ktilde, L.racc, L.Gpart, L.v1, L.P, L.X, L.W, L.logdetP};
       for (void* p : ps) cudaFree(p);
       umma_latent_free(L.um);
     }
-    void* ps[] = {pKS, pXb, pxxb, X, xx, y_all, ycls_all, Xb, xxb, stage, idx_pool, idx_cur, counters, status, d_lik_kind, d_p0, d_p1, d_A,
+    void* ps[] = {xx_cur, pKS, pXb, pxxb, X, xx, y_all, ycls_all, Xb, xxb, stage, idx_pool, idx_cur, counters, status, d_lik_kind, d_p0, d_p1, d_A,
                   mean_f, var_f, gmu, gS, lc, ltheta, lgamma_, lalpha, tmu, tvar, gm, gs, yb, ycls, d_out};
     for (void* p : ps) cudaFree(p);
   }
@@ -532,7 +536,6 @@ struct Engine : EngineBase {
       symv_kernel<<<(m * 32 + 255) / 256, 256, 0, st()>>>(L.Linv, mp, m, L.mu0, L.mu0v);  // L^-1 mu0
       launches += 5;
       CK(cudaMemcpyAsync(&L.logdetK, L.logdetP + 1, sizeof(double), cudaMemcpyDeviceToHost, st()));
-      if (prec == AGP_PREC_TF32X3) { CKS(umma_split_matrix(ctx_err(), L.um, UM_LINV, (const float*)(const void*)L.Linv_T, m, st())); ++launches; }
       int s0 = sync_status();   // a failed Cholesky of K must not be hidden by the next factorisation
       if (s0 != AGP_OK) { have_K = false; return s0; }
       CKS(whiten(L));
@@ -570,9 +573,11 @@ struct Engine : EngineBase {
       CKS(ensure_stage((size_t)B * 8));
       CK(cudaMemcpyAsync(stage, idx, (size_t)B * 8, cudaMemcpyHostToDevice, st()));
       idx_rebase_kernel<<<(B + 255) / 256, 256, 0, st()>>>((const int64_t*)stage, idx_cur, B, base);
+      xx_gather_kernel<T><<<(B + 255) / 256, 256, 0, st()>>>(idx_cur, B, xx, xx_cur);
+      ++launches;
     } else {
       if (!idx_pool || pool_B != B) { ph_end(); ctx->err = "no resident minibatch lists for this batch size"; return AGP_ERR_STATE; }
-      idx_select_kernel<<<(B + 255) / 256, 256, 0, st()>>>(idx_pool, n_lists, B, counters, idx_cur);
+      idx_select_kernel<T><<<(B + 255) / 256, 256, 0, st()>>>(idx_pool, n_lists, B, counters, idx_cur, xx, xx_cur);
     }
     ++launches;
     ph_end();
@@ -591,14 +596,18 @@ struct Engine : EngineBase {
         GemmParams<T> g{};
         g.A = Xsrc; g.lda = Dp; g.a_gather = gather; g.B = L.Z; g.ldb = Dp; g.C = L.Knm; g.ldc = ldm;
         g.M = B; g.N = m; g.K = D; g.alpha = 1.0;
-        g.xx = xsrc; g.zz = L.zz; g.scale2 = L.scale * L.scale; g.variance = L.variance; g.kernel_kind = L.kind;
+        g.xx = gather ? xx_cur : xsrc; g.xx_direct = 1; g.zz = L.zz; g.scale2 = L.scale * L.scale; g.variance = L.variance; g.kernel_kind = L.kind;
         gemm_simt_launch<T, false, false, EPI_KERNELFN>(g, 1, st());
         ++launches;
         ph_end();
         if (prec == AGP_PREC_TF32X3) {
-          ph_begin(PH_SPLIT); CKS(umma_split_matrix(ctx_err(), L.um, UM_KNM, (const float*)(const void*)L.Knm, B, st())); ++launches; ph_end();
-          ph_begin(PH_KAPPA); CKS(umma_gemm_nt(ctx_err(), L.um, UM_KNM, UM_LINV, (float*)(void*)L.V, B, m, st())); ++launches; ph_end();
-          ph_begin(PH_SPLIT); CKS(umma_split_matrix(ctx_err(), L.um, UM_V, (const float*)(const void*)L.V, B, st())); ++launches; ph_end();
+          ph_begin(PH_KAPPA);
+          CK(cudaMemsetAsync(L.racc, 0, 3 * ldB * sizeof(double), st()));
+          UmmaEpilogue ep{};
+          ep.mode = UMMA_EPI_STORE_SUMSQ; ep.acc0 = L.racc;
+          CKS(umma_gemm_nt(ctx_err(), L.um, UM_KNM, UM_LINV, (float*)(void*)L.V, B, m, ep, st()));
+          ++launches;
+          ph_end();
         } else {
           ph_begin(PH_KAPPA);
           GemmParams<T> k{};  // V = Knm L^-T  (the whitened kappa of latentgp.jl:211); L^-1 is lower triangular
@@ -612,7 +621,10 @@ struct Engine : EngineBase {
       {
         ph_begin(PH_KSIGMA);
         if (prec == AGP_PREC_TF32X3) {
-          CKS(umma_gemm_nt(ctx_err(), L.um, UM_V, UM_X, (float*)(void*)L.VS, B, m, st()));
+          if (!fresh_kernel_matrices) CK(cudaMemsetAsync(L.racc + ldB, 0, 2 * ldB * sizeof(double), st()));
+          UmmaEpilogue ep{};
+          ep.mode = UMMA_EPI_STATS_ONLY; ep.acc0 = L.racc + ldB; ep.acc1 = L.racc + 2 * ldB; ep.tvec = L.tvec;
+          CKS(umma_gemm_nt(ctx_err(), L.um, UM_V, UM_X, (float*)(void*)L.VS, B, m, ep, st()));
         } else {
           GemmParams<T> s{};  // V X^T with Sigma_v = X^T X  (kappa * Sigma of latentgp.jl:189); X is lower triangular
           s.A = L.V; s.lda = ldm; s.B = L.Xv_T; s.ldb = ldm; s.C = L.VS; s.ldc = ldm; s.M = B; s.N = m; s.K = m; s.alpha = 1.0;
@@ -623,6 +635,11 @@ struct Engine : EngineBase {
         ph_end();
       }
       ph_begin(PH_ROWSTATS);
+      if (prec == AGP_PREC_TF32X3)
+        rowfinish_kernel<<<(B + 255) / 256, 256, 0, st()>>>(L.racc, L.racc + ldB, L.racc + 2 * ldB, B, L.variance + jitter, L.Ktilde,
+                                                            mean_out + (size_t)q * out_ld, var_out + (size_t)q * out_ld, status,
+                                                            fresh_kernel_matrices ? 1 : 0);
+      else
       rowstats_kernel<T><<<(B * 32 + 255) / 256, 256, 0, st()>>>(L.V, L.VS, L.tvec, B, m, ldm, L.variance + jitter,
                                                                  L.Ktilde, mean_out + (size_t)q * out_ld, var_out + (size_t)q * out_ld,
                                                                  status, fresh_kernel_matrices ? 1 : 0);
@@ -669,6 +686,7 @@ struct Engine : EngineBase {
       Latent& L = lat[q];
       ph_begin(PH_GRADMU);
       CK(cudaMemsetAsync(L.v1, 0, m * sizeof(double), st()));
+      if (prec != AGP_PREC_TF32X3)
       { int rpb = std::max(64, (int)rup((B + 15) / 16, 8));
         gemv_t_kernel<T><<<dim3((m + 31) / 32, (B + rpb - 1) / rpb), dim3(32, 8), 0, st()>>>(L.V, ldm, gmu + (size_t)q * ldB, B, m, rpb, L.v1); }
       ++launches;
@@ -676,7 +694,8 @@ struct Engine : EngineBase {
       ph_begin(PH_GRAM);
       int ns = n_split;
       if (prec == AGP_PREC_TF32X3) {
-        CKS(umma_gram(ctx_err(), L.um, (const float*)(const void*)L.V, gS + (size_t)q * ldB, rho, (float*)(void*)L.Gpart, B, m, &ns, st()));
+        CKS(umma_gram(ctx_err(), L.um, (const float*)(const void*)L.V, gS + (size_t)q * ldB, rho, gmu + (size_t)q * ldB, L.v1,
+                      (float*)(void*)L.Gpart, B, m, &ns, st()));
         launches += 2;
       } else {
         GemmParams<T> g{};  // rho * V^T diag(grad_Sigma) V  (functions/utils.jl:70-72, whitened), split over the minibatch
@@ -690,6 +709,7 @@ struct Engine : EngineBase {
       ph_begin(PH_COMBINE);
       TailParams tp{};
       tp.m = m; tp.mp = mp; tp.ld = mp; tp.n_split = ns; tp.gpart_stride = (int64_t)m * ldm; tp.gpart_ld = ldm;
+      tp.g_mirrored = (prec == AGP_PREC_TF32X3) ? 1 : 0;
       tp.v1 = L.v1; tp.mu0v = L.mu0v; tp.eta1 = L.eta1v; tp.eta2 = L.eta2v; tp.P = L.P;
       tp.counters = counters; tp.stochastic = stochastic; tp.rm_kappa = rm_kappa; tp.rm_tau = rm_tau; tp.rho = rho;
       tp.logdet = L.logdetP; tp.status = status;
@@ -731,7 +751,6 @@ struct Engine : EngineBase {
     chol_inv(L);
     ph_begin(PH_FINAL);
     float* hi = nullptr; float* lo = nullptr;
-    if (prec == AGP_PREC_TF32X3) { hi = L.um.hi[UM_X]; lo = L.um.lo[UM_X]; }
     x_finalize_kernel<T><<<m, 128, 0, st()>>>(L.Xv, mp, m, L.eta1v, L.Xv_T, ldm, hi, lo, L.tvec);
     ++launches;
     ph_end();

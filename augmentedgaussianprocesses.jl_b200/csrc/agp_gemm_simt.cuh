@@ -35,6 +35,7 @@ struct GemmParams {
   int k_to_diag;             // NT with a lower-triangular B ([N][K], zero for k > n): stop k at the tile's last column
   // EPI_KERNELFN: C = variance * base(scale2 * (xx[row] + zz[col] - 2 acc))
   const T* xx; const T* zz; double scale2, variance; int kernel_kind;
+  int xx_direct;             // 1: xx is already gathered (indexed by the logical row), 0: indexed through a_gather
 };
 
 __device__ __forceinline__ float kfn_eval(int kind, float d2, float var) {
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmParams<T> p) {
     if (row >= p.M) continue;
     T xr = T(0);
     if constexpr (EPI == EPI_KERNELFN) {
-      int64_t prow = p.a_gather ? p.a_gather[row] : (int64_t)row;
+      int64_t prow = (p.a_gather && !p.xx_direct) ? p.a_gather[row] : (int64_t)row;
       xr = p.xx[prow];
     }
 #pragma unroll

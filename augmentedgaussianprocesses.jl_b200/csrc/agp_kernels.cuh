@@ -51,12 +51,23 @@ __global__ void idx_rebase_kernel(const int64_t* __restrict__ src, int64_t* __re
 
 // copy the index list of the current cursor position into the fixed per-step buffer (so that every
 // later kernel of the step - and a captured CUDA graph - reads one fixed address)
+template <typename T>
 __global__ void idx_select_kernel(const int64_t* __restrict__ pool, int64_t n_lists, int B,
-                                  const int64_t* __restrict__ counters /*[0]=t,[1]=cursor*/, int64_t* __restrict__ dst) {
+                                  const int64_t* __restrict__ counters /*[0]=t,[1]=cursor*/, int64_t* __restrict__ dst,
+                                  const T* __restrict__ xx_all, T* __restrict__ xx_cur) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B) return;
   int64_t cur = counters[1] % n_lists;
-  dst[i] = pool[cur * B + i];
+  int64_t r = pool[cur * B + i];
+  dst[i] = r;
+  xx_cur[i] = xx_all[r];   // gather the squared norms once (the K_nm epilogue then reads them by minibatch row)
+}
+
+// same for a host-provided (already rebased) list
+template <typename T>
+__global__ void xx_gather_kernel(const int64_t* __restrict__ idx, int B, const T* __restrict__ xx_all, T* __restrict__ xx_cur) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) xx_cur[i] = xx_all[idx[i]];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -106,6 +117,24 @@ __global__ void rowstats_kernel(const T* __restrict__ V, const T* __restrict__ V
     mean_f[warp] = s2;
     var_f[warp] = s3 + kt;
   }
+}
+
+// finishing step of the fused row statistics (tensor-core path): acc = {sum V^2, sum (VX^T)^2, sum (VX^T) t}
+__global__ void rowfinish_kernel(const double* __restrict__ sumsq_v, const double* __restrict__ sumsq_vs, const double* __restrict__ dot_vs,
+                                 int B, double kdiag_jit, double* __restrict__ Ktilde, double* __restrict__ mean_f,
+                                 double* __restrict__ var_f, int* __restrict__ status, int compute_ktilde) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double kt;
+  if (compute_ktilde) {
+    kt = kdiag_jit - sumsq_v[b];
+    Ktilde[b] = kt;
+    if (!(kt > 0.0)) atomicOr(status, ST_KTILDE);  // latentgp.jl:213
+  } else {
+    kt = Ktilde[b];
+  }
+  mean_f[b] = dot_vs[b];
+  var_f[b] = sumsq_vs[b] + kt;
 }
 
 // out[j] += sum_b V[b][j] * g[b]   (transpose(kappa) * grad_mu of analyticVI.jl:168, whitened; rho applied later)
@@ -373,6 +402,7 @@ struct TailParams {
   int m, mp;            // logical / padded (power-of-two multiple of 64) size
   int64_t ld;           // = mp : leading dimension of every fp64 m x m matrix
   int n_split; int64_t gpart_stride; int64_t gpart_ld;  // G partials [n_split][m][gpart_ld]
+  int g_mirrored;       // 1: both triangles hold identical values (read coalesced); 0: take the upper triangle (Q5)
   const double* v1;     // V^T grad_mu (un-scaled by rho)
   const double* mu0v;   // L^-1 mu0 (whitened prior mean)
   double* eta1; double* eta2; double* P;
@@ -396,9 +426,13 @@ __global__ void combine_kernel(const TailParams p, const TG* __restrict__ Gpart)
     p.P[(int64_t)i * p.ld + j] = (i == j) ? 1.0 : 0.0;
     return;
   }
-  int a = min(i, j), b = max(i, j);
-  double g = 0.0;
-  for (int s = 0; s < p.n_split; ++s) g += (double)Gpart[s * p.gpart_stride + (int64_t)a * p.gpart_ld + b];
+  int a = p.g_mirrored ? i : min(i, j), b = p.g_mirrored ? j : max(i, j);
+  double g = 0.0, g2 = 0.0;
+  const TG* gp = Gpart + (int64_t)a * p.gpart_ld + b;
+  int s = 0;
+  for (; s + 1 < p.n_split; s += 2) { g += (double)gp[s * p.gpart_stride]; g2 += (double)gp[(s + 1) * p.gpart_stride]; }
+  if (s < p.n_split) g += (double)gp[s * p.gpart_stride];
+  g += g2;
   int64_t o = (int64_t)i * p.ld + j;
   double e2 = p.eta2[o];
   double d2 = -(g + (i == j ? 0.5 : 0.0)) - e2;

@@ -1,15 +1,20 @@
 // agp_umma.cu -- tcgen05 (5th-gen tensor core) path of the B x m contractions, written for sm_100a.
 //
-//   C[M x N] = A[M x K] * B[N x K]^T  in "3xTF32": every fp32 operand is pre-split into hi = tf32(a) and
-//   lo = a - hi, and the tensor cores accumulate hi*hi + hi*lo + lo*hi in fp32 TMEM (error ~2^-21, fp32 class).
+//   C[M x N] = A[M x K] * B[N x K]^T  in "3xTF32": each fp32 operand tile is split inside the CTA into
+//   hi = rna_tf32(a) and lo = rna_tf32(a - hi), and the tensor cores accumulate lo*hi + hi*lo + hi*hi in fp32 TMEM
+//   (error ~2^-22 per product, fp32 class).
 //
-// One CTA computes one 128 x 128 output tile (UMMA 128x128x8, kind::tf32, cta_group::1):
-//   warp 0      : TMA producer  (cp.async.bulk.tensor.2d, 128B swizzle, 3-stage mbarrier ring; a stage holds the
-//                 A_hi, A_lo, B_hi, B_lo tiles of one 32-wide k-block = 64 KB)
-//   warp 1      : TMEM allocator + MMA issuer (one elected lane issues 12 tcgen05.mma per k-block, tcgen05.commit
-//                 releases the smem stage / signals the epilogue)
-//   warps 2..5  : epilogue (tcgen05.ld 32x32b -> registers -> fp32 row-major global stores)
-// Used for V = Knm L^-T (k-blocks above the diagonal of the lower-triangular L^-1 are skipped), V Sigma_v, and
+// One CTA computes one 128 x 128 output tile (UMMA 128x128x8, kind::tf32, cta_group::1), 192 threads:
+//   warp 0      : TMA producer  (cp.async.bulk.tensor.2d, 128B swizzle): the RAW fp32 A and B tiles of one 32-wide
+//                 k-block (2 x 16 KB) per stage -- operands cross L2 -> SM once, not as separate hi and lo copies
+//                 (the first version streamed pre-split operands and was L2-bandwidth bound: 168 MB / launch)
+//   warps 2..5  : converters: raw tile -> hi / lo tiles at the same (swizzled) offsets, fence.proxy.async, then
+//                 hand the stage to the MMA warp; after the main loop the same warps run the epilogue
+//                 (tcgen05.ld 32x32b -> registers -> fp32 row-major global stores)
+//   warp 1      : TMEM allocator + MMA issuer (one elected lane, 12 tcgen05.mma per k-block, tcgen05.commit
+//                 releases the hi/lo buffers / signals the epilogue)
+// 2-stage ring, 96 KB per stage (raw A, raw B, A_hi, A_lo, B_hi, B_lo).
+// Used for V = Knm L^-T and V X^T (k-blocks above the diagonal of the lower-triangular right operand are skipped) and
 // the split-K Gram product U^T U with U = diag(sqrt(rho w)) V (upper-triangular tiles only).
 #include "agp_umma.h"
 
@@ -26,9 +31,11 @@ namespace {
 
 constexpr int BM = 128, BN = 128, BK = 32, STAGES = 3;
 constexpr int TILE_BYTES = BM * BK * 4;        // 16 KB : 128 rows x 128 B (one 128B-swizzle atom wide)
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;    // A_hi, A_lo, B_hi, B_lo
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;    // raw A, raw B, B_hi, B_lo   (A_hi / A_lo live in TMEM)
+constexpr int NUM_CONV_THREADS = 128;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int TMEM_COLS = 128;
+constexpr int TMEM_COLS = 512;     // [0,128) fp32 accumulator, then per stage 32 columns A_hi + 32 columns A_lo
+constexpr int TMEM_A0 = 128;
 constexpr int NUM_THREADS = 192;
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------
@@ -39,6 +46,10 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -74,6 +85,25 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]   (A operand in tensor memory: 128 lanes x 8 columns of tf32)
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+#define TMEM_ST32(taddr, r)                                                                                              \
+  asm volatile(                                                                                                          \
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "                                                                    \
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, " \
+      "%25, %26, %27, %28, %29, %30, %31, %32};"                                                                         \
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),  \
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),    \
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),   \
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])                                                     \
+      : "memory")
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
@@ -105,12 +135,18 @@ constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN 
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                      \
       : "r"(taddr))
 
+// round-to-nearest fp32 -> tf32 (the tensor core would otherwise truncate the low 13 mantissa bits)
+__device__ __forceinline__ float tf32_rna(float v) {
+  uint32_t t;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v));
+  return __uint_as_float(t);
+}
+
 // tri_mode: 0 none | 1 B operand lower-triangular (B[n][k] = 0 for k > n): stop at the tile's last column
 //           | 2 symmetric output: only tiles with tile_n >= tile_m
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-umma_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, float* __restrict__ C,
-                    int64_t ldc, int64_t c_split_stride, int total_kb, int kb_per_split, int tri_mode) {
+umma_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C,
+                    int64_t ldc, int64_t c_split_stride, int total_kb, int kb_per_split, int tri_mode, const UmmaEpilogue ep) {
   const int tile_n = blockIdx.x, tile_m = blockIdx.y, split = blockIdx.z;
   if (tri_mode == 2 && tile_n < tile_m) return;
   int kb0 = split * kb_per_split;
@@ -121,17 +157,22 @@ umma_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bars = smem_base + STAGES * STAGE_BYTES;  // full[STAGES], empty[STAGES], tmem_full, tmem_ptr
-  auto full_bar = [&](int s) { return bars + 8u * s; };
-  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
-  const uint32_t tmem_full_bar = bars + 8u * (2 * STAGES);
-  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 1));
+  const uint32_t bars = smem_base + STAGES * STAGE_BYTES;
+  auto raw_full = [&](int s) { return bars + 8u * s; };
+  auto raw_empty = [&](int s) { return bars + 8u * (STAGES + s); };
+  auto conv_full = [&](int s) { return bars + 8u * (2 * STAGES + s); };
+  auto mma_done = [&](int s) { return bars + 8u * (3 * STAGES + s); };
+  const uint32_t tmem_full_bar = bars + 8u * (4 * STAGES);
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 8 * (4 * STAGES + 1));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_hi); tma_prefetch_desc(&tmB_lo);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), NUM_CONV_THREADS);
+      mbar_init(conv_full(s), NUM_CONV_THREADS); mbar_init(mma_done(s), 1);
+    }
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -146,45 +187,95 @@ umma_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
 
   if (warp == 0) {
     if (lane == 0) {
-      // ===== TMA producer =====
+      // ===== TMA producer: raw fp32 tiles =====
       for (int i = 0; i < nkb; ++i) {
         const int s = i % STAGES;
-        mbar_wait(empty_bar(s), ((i / STAGES) & 1) ^ 1);
+        mbar_wait(raw_empty(s), ((i / STAGES) & 1) ^ 1);
         const uint32_t dst = smem_base + s * STAGE_BYTES;
-        mbar_expect_tx(full_bar(s), STAGE_BYTES);
+        mbar_expect_tx(raw_full(s), 2 * TILE_BYTES);
         const int k = (kb0 + i) * BK;
-        tma_load_2d(dst + 0 * TILE_BYTES, &tmA_hi, full_bar(s), k, tile_m * BM);
-        tma_load_2d(dst + 1 * TILE_BYTES, &tmA_lo, full_bar(s), k, tile_m * BM);
-        tma_load_2d(dst + 2 * TILE_BYTES, &tmB_hi, full_bar(s), k, tile_n * BN);
-        tma_load_2d(dst + 3 * TILE_BYTES, &tmB_lo, full_bar(s), k, tile_n * BN);
+        tma_load_2d(dst + 0 * TILE_BYTES, &tmA, raw_full(s), k, tile_m * BM);
+        tma_load_2d(dst + 1 * TILE_BYTES, &tmB, raw_full(s), k, tile_n * BN);
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     for (int i = 0; i < nkb; ++i) {
       const int s = i % STAGES;
-      mbar_wait(full_bar(s), (i / STAGES) & 1);
+      mbar_wait(conv_full(s), (i / STAGES) & 1);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + TILE_BYTES, b_hi = a_hi + 2 * TILE_BYTES, b_lo = a_hi + 3 * TILE_BYTES;
+        const uint32_t base = smem_base + s * STAGE_BYTES;
+        const uint32_t b_hi = base + 2 * TILE_BYTES, b_lo = base + 3 * TILE_BYTES;
+        const uint32_t a_hi = tmem_base + TMEM_A0 + s * 64, a_lo = a_hi + 32;
 #pragma unroll
         for (int kk = 0; kk < BK / 8; ++kk) {
-          const uint32_t off = kk * 32;  // 8 tf32 = 32 bytes along K inside the 128B swizzle atom
-          const uint64_t dah = make_desc(a_hi + off), dal = make_desc(a_lo + off), dbh = make_desc(b_hi + off), dbl = make_desc(b_lo + off);
-          tc_mma_tf32(tmem_base, dal, dbh, kIdesc, (i > 0 || kk > 0) ? 1u : 0u);  // small terms first
-          tc_mma_tf32(tmem_base, dah, dbl, kIdesc, 1u);
-          tc_mma_tf32(tmem_base, dah, dbh, kIdesc, 1u);
+          const uint32_t off = kk * 32;  // 8 tf32 = 32 bytes along K inside the 128B swizzle atom (B); 8 TMEM columns (A)
+          const uint64_t dbh = make_desc(b_hi + off), dbl = make_desc(b_lo + off);
+          tc_mma_tf32_ts(tmem_base, a_lo + kk * 8, dbh, kIdesc, (i > 0 || kk > 0) ? 1u : 0u);  // small terms first
+          tc_mma_tf32_ts(tmem_base, a_hi + kk * 8, dbl, kIdesc, 1u);
+          tc_mma_tf32_ts(tmem_base, a_hi + kk * 8, dbh, kIdesc, 1u);
         }
-        tc_commit(empty_bar(s));                       // frees the smem stage when these MMAs retire
+        tc_commit(mma_done(s));                        // frees B_hi/B_lo and the TMEM A columns of this stage
         if (i == nkb - 1) tc_commit(tmem_full_bar);    // accumulator complete
       }
       __syncwarp();
     }
   } else {
-    // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
-    const int q = warp & 3;
+    // ===== converters (raw -> hi / lo), then epilogue: warps 2..5 =====
+    const int ct = threadIdx.x - 64;  // 0..127
+    const int q = warp & 3;           // TMEM lane quarter this warp may access
+    const int arow = q * 32 + lane;   // A-tile row = TMEM lane handled by this thread
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % STAGES;
+      mbar_wait(raw_full(s), (i / STAGES) & 1);            // TMA landed the raw tiles
+      mbar_wait(mma_done(s), ((i / STAGES) & 1) ^ 1);      // previous MMAs on this stage's buffers retired
+      tc_fence_after();
+      uint8_t* base = smem_gen + s * STAGE_BYTES;
+      {
+        // A: row `arow` of the raw tile (128 B, 16-byte chunks XOR-swizzled with row & 7) -> hi / lo -> TMEM
+        const float4* rowp = reinterpret_cast<const float4*>(base + arow * 128);
+        uint32_t h[32], l[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 v = rowp[c ^ (arow & 7)];
+          float t;
+          t = tf32_rna(v.x); h[4 * c + 0] = __float_as_uint(t); l[4 * c + 0] = __float_as_uint(tf32_rna(v.x - t));
+          t = tf32_rna(v.y); h[4 * c + 1] = __float_as_uint(t); l[4 * c + 1] = __float_as_uint(tf32_rna(v.y - t));
+          t = tf32_rna(v.z); h[4 * c + 2] = __float_as_uint(t); l[4 * c + 2] = __float_as_uint(tf32_rna(v.z - t));
+          t = tf32_rna(v.w); h[4 * c + 3] = __float_as_uint(t); l[4 * c + 3] = __float_as_uint(tf32_rna(v.w - t));
+        }
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + TMEM_A0 + s * 64;
+        TMEM_ST32(ta, h);
+        TMEM_ST32(ta + 32, l);
+      }
+      {
+        // B: raw -> hi / lo tiles at the same (swizzled) offsets in shared memory
+        const float4* raw = reinterpret_cast<const float4*>(base + 1 * TILE_BYTES);
+        float4* hi = reinterpret_cast<float4*>(base + 2 * TILE_BYTES);
+        float4* lo = reinterpret_cast<float4*>(base + 3 * TILE_BYTES);
+#pragma unroll
+        for (int u = 0; u < TILE_BYTES / 16 / NUM_CONV_THREADS; ++u) {
+          const int e = ct + u * NUM_CONV_THREADS;
+          const float4 v = raw[e];
+          float4 h, l;
+          h.x = tf32_rna(v.x); l.x = tf32_rna(v.x - h.x);
+          h.y = tf32_rna(v.y); l.y = tf32_rna(v.y - h.y);
+          h.z = tf32_rna(v.z); l.z = tf32_rna(v.z - h.z);
+          h.w = tf32_rna(v.w); l.w = tf32_rna(v.w - h.w);
+          hi[e] = h; lo[e] = l;
+        }
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      mbar_arrive(raw_empty(s));    // the raw tiles may be overwritten by the next TMA
+      mbar_arrive(conv_full(s));    // operands ready for the MMA warp
+    }
     const int row = tile_m * BM + q * 32 + lane;
-    float* crow = C + (int64_t)split * c_split_stride + (int64_t)row * ldc + (int64_t)tile_n * BN;
+    float* cbase = C + (int64_t)split * c_split_stride;
+    float* crow = cbase + (int64_t)row * ldc + (int64_t)tile_n * BN;
+    double acc_sq = 0.0, acc_dot = 0.0;   // fused row statistics (fp64 sums, like rowstats_kernel)
     if (nkb > 0) {
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
@@ -194,12 +285,30 @@ umma_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
         TMEM_LD32(taddr, r);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        float4* dst = reinterpret_cast<float4*>(crow + c * 32);
+        if (ep.mode != UMMA_EPI_STATS_ONLY) {
+          float4* dst = reinterpret_cast<float4*>(crow + c * 32);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+          for (int j = 0; j < 8; ++j)
+            dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        }
+        if (ep.mode == UMMA_EPI_STORE_SUMSQ || ep.mode == UMMA_EPI_STATS_ONLY) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const double v = (double)__uint_as_float(r[j]);
+            acc_sq = fma(v, v, acc_sq);
+            if (ep.mode == UMMA_EPI_STATS_ONLY) acc_dot = fma(v, ep.tvec[tile_n * BN + c * 32 + j], acc_dot);
+          }
+        }
+        if (ep.mode == UMMA_EPI_STORE_MIRROR && tile_n != tile_m) {
+          // symmetric product: also write the transposed tile (lanes = consecutive addresses)
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            cbase[(int64_t)(tile_n * BN + c * 32 + j) * ldc + row] = __uint_as_float(r[j]);
+        }
       }
-    } else {
+      if (ep.mode == UMMA_EPI_STORE_SUMSQ) atomicAdd(ep.acc0 + row, acc_sq);
+      if (ep.mode == UMMA_EPI_STATS_ONLY) { atomicAdd(ep.acc0 + row, acc_sq); atomicAdd(ep.acc1 + row, acc_dot); }
+    } else if (ep.mode != UMMA_EPI_STATS_ONLY) {
       for (int c = 0; c < BN / 4; ++c) reinterpret_cast<float4*>(crow)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
@@ -210,45 +319,36 @@ umma_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   }
 }
 
-// round-to-nearest fp32 -> tf32 (the tensor core would otherwise truncate the low 13 mantissa bits)
-__device__ __forceinline__ float tf32_rna(float v) {
-  uint32_t t;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v));
-  return __uint_as_float(t);
-}
-
-// src (rows x cols, ld) -> hi = rna_tf32(src), lo = rna_tf32(src - hi)
-__global__ void split_tf32_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo, int64_t n4) {
-  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= n4) return;
-  float4 v = reinterpret_cast<const float4*>(src)[i];
-  float4 h, l;
-  h.x = tf32_rna(v.x); l.x = tf32_rna(v.x - h.x);
-  h.y = tf32_rna(v.y); l.y = tf32_rna(v.y - h.y);
-  h.z = tf32_rna(v.z); l.z = tf32_rna(v.z - h.z);
-  h.w = tf32_rna(v.w); l.w = tf32_rna(v.w - h.w);
-  reinterpret_cast<float4*>(hi)[i] = h;
-  reinterpret_cast<float4*>(lo)[i] = l;
-}
-
-// U^T = (diag(sqrt(rho w)) V)^T split into hi/lo:  V is [B][ldv], outputs are [m][ldt]
-__global__ void scale_transpose_split_kernel(const float* __restrict__ V, int64_t ldv, const double* __restrict__ w, double rho,
-                                             float* __restrict__ hi, float* __restrict__ lo, int64_t ldt) {
+// U^T = (diag(sqrt(rho w)) V)^T:  V is [B][ldv], output is [m][ldt] fp32 (split to hi/lo inside the GEMM); fused with
+// v1[j] += sum_b V[b][j] g[b]  (transpose(kappa) * grad_mu, analyticVI.jl:168, whitened).  Block = 32 columns x 128 rows.
+__global__ void scale_transpose_kernel(const float* __restrict__ V, int64_t ldv, const double* __restrict__ w, double rho,
+                                       float* __restrict__ UT, int64_t ldt, const double* __restrict__ g, double* __restrict__ v1) {
   __shared__ float tile[32][33];
-  const int b0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+  __shared__ double red[8][33];
+  const int j0 = blockIdx.x * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  double dot = 0.0;
+  for (int sub = 0; sub < 4; ++sub) {
+    const int b0 = blockIdx.y * 128 + sub * 32;
 #pragma unroll
-  for (int r = ty; r < 32; r += 8) {
-    float s = (float)sqrt(fmax(rho * w[b0 + r], 0.0));
-    tile[r][tx] = V[(int64_t)(b0 + r) * ldv + j0 + tx] * s;
+    for (int r = ty; r < 32; r += 8) {
+      const float v = V[(int64_t)(b0 + r) * ldv + j0 + tx];
+      const float s = (float)sqrt(fmax(rho * w[b0 + r], 0.0));
+      dot = fma((double)v, g[b0 + r], dot);
+      tile[r][tx] = v * s;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) UT[(int64_t)(j0 + r) * ldt + b0 + tx] = tile[tx][r];
+    __syncthreads();
   }
+  red[ty][tx] = dot;
   __syncthreads();
+  if (ty == 0) {
+    double a = 0.0;
 #pragma unroll
-  for (int r = ty; r < 32; r += 8) {
-    float v = tile[tx][r];
-    float h = tf32_rna(v);
-    hi[(int64_t)(j0 + r) * ldt + b0 + tx] = h;
-    lo[(int64_t)(j0 + r) * ldt + b0 + tx] = tf32_rna(v - h);
+    for (int r = 0; r < 8; ++r) a += red[r][tx];
+    atomicAdd(v1 + j0 + tx, a);
   }
 }
 
@@ -281,7 +381,7 @@ bool make_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols,
 }
 
 struct Maps {
-  CUtensorMap hi[UM_COUNT], lo[UM_COUNT], ut_hi, ut_lo;
+  CUtensorMap raw[UM_COUNT], ut;
 };
 
 int fail(std::string* err, const char* what, cudaError_t e = cudaSuccess) {
@@ -293,28 +393,18 @@ int fail(std::string* err, const char* what, cudaError_t e = cudaSuccess) {
 
 bool umma_shape_ok(int m, int Bcap) { return m >= 128 && m % 128 == 0 && Bcap >= 128 && Bcap % 128 == 0; }
 
-int umma_latent_alloc(std::string* err, UmmaLatent& u, int m, int ldm, int Bcap, cudaStream_t st) {
+int umma_latent_alloc(std::string* err, UmmaLatent& u, int m, int ldm, int Bcap, const float* Knm, const float* V, const float* Linv,
+                      const float* X, cudaStream_t st) {
   u.m = m; u.ldm = ldm; u.Bcap = Bcap;
   const size_t rows[UM_COUNT] = {(size_t)Bcap, (size_t)Bcap, (size_t)m, (size_t)m};
+  const float* ptr[UM_COUNT] = {Knm, V, Linv, X};
   cudaError_t e;
-  for (int i = 0; i < UM_COUNT; ++i) {
-    if ((e = cudaMalloc(&u.hi[i], rows[i] * ldm * sizeof(float))) != cudaSuccess) return fail(err, "cudaMalloc", e);
-    if ((e = cudaMalloc(&u.lo[i], rows[i] * ldm * sizeof(float))) != cudaSuccess) return fail(err, "cudaMalloc", e);
-    cudaMemsetAsync(u.hi[i], 0, rows[i] * ldm * sizeof(float), st);
-    cudaMemsetAsync(u.lo[i], 0, rows[i] * ldm * sizeof(float), st);
-  }
-  if ((e = cudaMalloc(&u.kT_hi, (size_t)m * Bcap * sizeof(float))) != cudaSuccess) return fail(err, "cudaMalloc", e);
-  if ((e = cudaMalloc(&u.kT_lo, (size_t)m * Bcap * sizeof(float))) != cudaSuccess) return fail(err, "cudaMalloc", e);
-  cudaMemsetAsync(u.kT_hi, 0, (size_t)m * Bcap * sizeof(float), st);
-  cudaMemsetAsync(u.kT_lo, 0, (size_t)m * Bcap * sizeof(float), st);
+  if ((e = cudaMalloc(&u.UT, (size_t)m * Bcap * sizeof(float))) != cudaSuccess) return fail(err, "cudaMalloc", e);
+  cudaMemsetAsync(u.UT, 0, (size_t)m * Bcap * sizeof(float), st);
   Maps* mp = new Maps();
   bool ok = true;
-  for (int i = 0; i < UM_COUNT; ++i) {
-    ok = ok && make_map(&mp->hi[i], u.hi[i], rows[i], m, ldm);
-    ok = ok && make_map(&mp->lo[i], u.lo[i], rows[i], m, ldm);
-  }
-  ok = ok && make_map(&mp->ut_hi, u.kT_hi, m, Bcap, Bcap);
-  ok = ok && make_map(&mp->ut_lo, u.kT_lo, m, Bcap, Bcap);
+  for (int i = 0; i < UM_COUNT; ++i) ok = ok && make_map(&mp->raw[i], ptr[i], rows[i], m, ldm);
+  ok = ok && make_map(&mp->ut, u.UT, m, Bcap, Bcap);
   u.tmaps = mp;
   if (!ok) return fail(err, "cuTensorMapEncodeTiled failed");
   if ((e = cudaFuncSetAttribute(umma_gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)) != cudaSuccess)
@@ -323,38 +413,30 @@ int umma_latent_alloc(std::string* err, UmmaLatent& u, int m, int ldm, int Bcap,
 }
 
 void umma_latent_free(UmmaLatent& u) {
-  for (int i = 0; i < UM_COUNT; ++i) { cudaFree(u.hi[i]); cudaFree(u.lo[i]); u.hi[i] = u.lo[i] = nullptr; }
-  cudaFree(u.kT_hi); cudaFree(u.kT_lo);
-  u.kT_hi = u.kT_lo = nullptr;
+  cudaFree(u.UT);
+  u.UT = nullptr;
   delete (Maps*)u.tmaps;
   u.tmaps = nullptr;
 }
 
-int umma_split_matrix(std::string* err, UmmaLatent& u, int which, const float* src, int rows, cudaStream_t st) {
-  int64_t n4 = (int64_t)rows * u.ldm / 4;
-  split_tf32_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(src, u.hi[which], u.lo[which], n4);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return fail(err, "split_tf32_kernel", e);
-  return 0;
-}
-
-int umma_gemm_nt(std::string* err, UmmaLatent& u, int a_which, int b_which, float* C, int M, int N, cudaStream_t st) {
+int umma_gemm_nt(std::string* err, UmmaLatent& u, int a_which, int b_which, float* C, int M, int N, const UmmaEpilogue& ep,
+                 cudaStream_t st) {
   Maps* mp = (Maps*)u.tmaps;
   if (M % BM || N % BN || u.m % BK) return fail(err, "shape not a multiple of the 128 x 128 x 32 tile");
   const int total_kb = u.m / BK;
   dim3 grid(N / BN, M / BM, 1);
-  umma_gemm_nt_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mp->hi[a_which], mp->lo[a_which], mp->hi[b_which], mp->lo[b_which], C,
-                                                             (int64_t)u.ldm, 0, total_kb, total_kb, (b_which == UM_LINV || b_which == UM_X) ? 1 : 0);
+  umma_gemm_nt_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mp->raw[a_which], mp->raw[b_which], C, (int64_t)u.ldm, 0, total_kb, total_kb,
+                                                             (b_which == UM_LINV || b_which == UM_X) ? 1 : 0, ep);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(err, "umma_gemm_nt_kernel", e);
   return 0;
 }
 
-int umma_gram(std::string* err, UmmaLatent& u, const float* V, const double* w, double rho, float* Gpart, int B, int m, int* n_split,
-              cudaStream_t st) {
+int umma_gram(std::string* err, UmmaLatent& u, const float* V, const double* w, double rho, const double* g, double* v1, float* Gpart,
+              int B, int m, int* n_split, cudaStream_t st) {
   Maps* mp = (Maps*)u.tmaps;
   if (B % BM || m % BN) return fail(err, "shape not a multiple of the tile");
-  scale_transpose_split_kernel<<<dim3(m / 32, B / 32), dim3(32, 8), 0, st>>>(V, u.ldm, w, rho, u.kT_hi, u.kT_lo, u.Bcap);
+  scale_transpose_kernel<<<dim3(m / 32, B / 128), dim3(32, 8), 0, st>>>(V, u.ldm, w, rho, u.UT, u.Bcap, g, v1);
   const int total_kb = B / BK;
   const int nt = m / BN, upper_tiles = nt * (nt + 1) / 2;
   int S = (148 + upper_tiles - 1) / upper_tiles;
@@ -364,8 +446,9 @@ int umma_gram(std::string* err, UmmaLatent& u, const float* V, const double* w, 
   int per = (total_kb + S - 1) / S;
   S = (total_kb + per - 1) / per;
   dim3 grid(nt, nt, S);
-  umma_gemm_nt_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mp->ut_hi, mp->ut_lo, mp->ut_hi, mp->ut_lo, Gpart, (int64_t)u.ldm,
-                                                             (int64_t)m * u.ldm, total_kb, per, 2);
+  UmmaEpilogue ep{};
+  ep.mode = UMMA_EPI_STORE_MIRROR;
+  umma_gemm_nt_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mp->ut, mp->ut, Gpart, (int64_t)u.ldm, (int64_t)m * u.ldm, total_kb, per, 2, ep);
   *n_split = S;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(err, "umma gram", e);

@@ -10,24 +10,34 @@ namespace agp {
 
 enum UmmaMat : int { UM_KNM = 0, UM_V = 1, UM_LINV = 2, UM_X = 3, UM_COUNT = 4 };
 
+// fused epilogues of the tensor-core GEMM
+enum UmmaEpiMode : int {
+  UMMA_EPI_STORE = 0,        // C = acc
+  UMMA_EPI_STORE_SUMSQ = 1,  // C = acc ; acc0[row] += sum_col acc^2                       (V = Knm L^-T -> Ktilde)
+  UMMA_EPI_STATS_ONLY = 2,   // no store ; acc0[row] += sum acc^2 ; acc1[row] += sum acc*tvec[col]   (V X^T -> var_f, mean_f)
+  UMMA_EPI_STORE_MIRROR = 3  // C = acc and C^T = acc^T for off-diagonal tiles              (symmetric Gram product)
+};
+struct UmmaEpilogue {
+  int mode = 0;
+  double* acc0 = nullptr; double* acc1 = nullptr; const double* tvec = nullptr;
+};
+
 struct UmmaLatent {
   int m = 0, ldm = 0, Bcap = 0;
-  float* hi[UM_COUNT] = {nullptr, nullptr, nullptr, nullptr};  // TF32-rounded high parts
-  float* lo[UM_COUNT] = {nullptr, nullptr, nullptr, nullptr};  // residuals
-  float* kT_hi = nullptr; float* kT_lo = nullptr;              // V^T (m x B) and diag(w)-scaled copy for the Gram product
-  float* kTw_hi = nullptr; float* kTw_lo = nullptr;
-  void* tmaps = nullptr;                                        // host array of CUtensorMap
+  float* UT = nullptr;   // U^T = (diag(sqrt(rho w)) V)^T, [m][Bcap], operand of the Gram product
+  void* tmaps = nullptr; // host array of CUtensorMap (raw fp32 operands: Knm, V, L^-1, X, U^T)
 };
 
 bool umma_shape_ok(int m, int Bcap);
-int umma_latent_alloc(std::string* err, UmmaLatent& u, int m, int ldm, int Bcap, cudaStream_t st);
+// tensor maps are built once on the engine's fp32 operand buffers (all [rows][ldm], rows = Bcap or m)
+int umma_latent_alloc(std::string* err, UmmaLatent& u, int m, int ldm, int Bcap, const float* Knm, const float* V, const float* Linv,
+                      const float* X, cudaStream_t st);
 void umma_latent_free(UmmaLatent& u);
-// split src (rows x m, ld = ldm) into hi/lo of matrix `which`
-int umma_split_matrix(std::string* err, UmmaLatent& u, int which, const float* src, int rows, cudaStream_t st);
-// C[M x N] = A[M x K] * B[N x K]^T with K = m, 3xTF32
-int umma_gemm_nt(std::string* err, UmmaLatent& u, int a_which, int b_which, float* C, int M, int N, cudaStream_t st);
-// Gpart[s] = sum_{b in split s} rho*w_b kappa_b kappa_b^T ; *n_split in: capacity, out: used
-int umma_gram(std::string* err, UmmaLatent& u, const float* kappa, const double* w, double rho, float* Gpart, int B, int m,
-              int* n_split, cudaStream_t st);
+// C[M x N] = A[M x K] * B[N x K]^T with K = m, 3xTF32 (operands split to hi/lo inside the kernel)
+int umma_gemm_nt(std::string* err, UmmaLatent& u, int a_which, int b_which, float* C, int M, int N, const UmmaEpilogue& ep,
+                 cudaStream_t st);
+// Gpart[s] = sum_{b in split s} rho*w_b V_b V_b^T (full symmetric tiles) ; v1 += V^T g ; *n_split in: capacity, out: used
+int umma_gram(std::string* err, UmmaLatent& u, const float* V, const double* w, double rho, const double* g, double* v1, float* Gpart,
+              int B, int m, int* n_split, cudaStream_t st);
 
 }  // namespace agp
