@@ -130,7 +130,8 @@ struct Engine : EngineBase {
     double* v1 = nullptr;
     double *P = nullptr, *X = nullptr, *W = nullptr;  // tail workspaces [mp][mp]
     double* logdetP = nullptr;                        // device scalars: [0] logdet P_v, [1] scratch for K
-    UmmaLatent um;                                    // tcgen05 path: hi/lo TF32 splits
+    UmmaLatent um;                                    // tcgen05 path
+    int gram_splits = 1;                              // split-K partials of the last Gram product
   };
   std::vector<Latent> lat;
 
@@ -169,7 +170,15 @@ struct Engine : EngineBase {
   bool want_graph = false; cudaGraphExec_t gexec = nullptr; int gB = -1; double grho = -1; int64_t g_launches = 0;
   bool capturing = false;
 
-  cudaStream_t st() const { return ctx->stream; }
+  // launch stream: the context's stream, or the side stream while the next minibatch is being prefetched
+  cudaStream_t cur_stream = nullptr;
+  cudaStream_t st() const { return cur_stream ? cur_stream : ctx->stream; }
+  // software pipeline (resident-list steps): while the fp64 tail of step t runs on the main stream, the side stream
+  // builds Knm and V = Knm L^-T of minibatch t+1 (V only depends on the fixed L^-1, not on the posterior)
+  cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool pipeline = true;      // AGP_PIPELINE=0 disables
+  bool prefetched = false;   // Knm / V / sum V^2 / idx_cur / xx_cur hold the minibatch at the device cursor
+  int64_t* idx_prev = nullptr;  // indices of the minibatch the last step consumed (ELBO / getters after a prefetch)
 
   template <typename U>
   int dalloc(U** p, size_t count) {
@@ -298,7 +307,10 @@ struct Engine : EngineBase {
                               (const float*)(const void*)L.Linv_T, (const float*)(const void*)L.Xv_T, st()));
     }
     CKS(dalloc(&Xb, (size_t)Bcap * Dp)); CKS(dalloc(&xxb, Bcap));
-    CKS(dalloc(&idx_cur, Bcap)); CKS(dalloc(&xx_cur, Bcap));
+    CKS(dalloc(&idx_cur, Bcap)); CKS(dalloc(&xx_cur, Bcap)); CKS(dalloc(&idx_prev, Bcap));
+    CK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    { const char* e = getenv("AGP_PIPELINE"); if (e && e[0] == '0') pipeline = false; }
     CKS(dalloc(&counters, 2)); CKS(dalloc(&status, 1));
     int64_t c0[2] = {1, 0};
     CK(cudaMemcpyAsync(counters, c0, sizeof(c0), cudaMemcpyHostToDevice, st()));
@@ -345,7 +357,10 @@ struct Engine : EngineBase {
       for (void* p : ps) cudaFree(p);
       umma_latent_free(L.um);
     }
-    void* ps[] = {xx_cur, pKS, pXb, pxxb, X, xx, y_all, ycls_all, Xb, xxb, stage, idx_pool, idx_cur, counters, status, d_lik_kind, d_p0, d_p1, d_A,
+    if (side) cudaStreamDestroy(side);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    void* ps[] = {idx_prev, xx_cur, pKS, pXb, pxxb, X, xx, y_all, ycls_all, Xb, xxb, stage, idx_pool, idx_cur, counters, status, d_lik_kind, d_p0, d_p1, d_A,
                   mean_f, var_f, gmu, gS, lc, ltheta, lgamma_, lalpha, tmu, tvar, gm, gs, yb, ycls, d_out};
     for (void* p : ps) cudaFree(p);
   }
@@ -429,7 +444,7 @@ struct Engine : EngineBase {
     int64_t zero = 0;
     CK(cudaMemcpyAsync(counters + 1, &zero, 8, cudaMemcpyHostToDevice, st()));
     CK(cudaStreamSynchronize(st()));
-    n_lists = nl; pool_B = B;
+    n_lists = nl; pool_B = B; prefetched = false;
     drop_graph();
     return AGP_OK;
   }
@@ -543,6 +558,7 @@ struct Engine : EngineBase {
     CK(cudaGetLastError());
     int s = sync_status();
     have_K = (s == AGP_OK);
+    prefetched = false;
     drop_graph();
     return s;
   }
@@ -560,13 +576,13 @@ struct Engine : EngineBase {
   int set_kernel(int ql, int kind, double scale, double variance) override {
     if (ql < 0 || ql >= Ql || kind < 0 || kind > 2 || !(scale > 0) || !(variance > 0)) BAD("bad kernel parameters");
     lat[ql].kind = kind; lat[ql].scale = scale; lat[ql].variance = variance;
-    have_K = false;
+    have_K = false; prefetched = false;
     drop_graph();
     return AGP_OK;
   }
 
   // ---- the step -------------------------------------------------------------------------------------
-  int prep_idx(const int64_t* idx, int B, int base) {
+  int prep_idx(const int64_t* idx, int B, int base, int cursor_offset = 0) {
     ph_begin(PH_IDX);
     if (idx) {
       for (int i = 0; i < B; ++i) if (idx[i] - base < 0 || idx[i] - base >= n) { ph_end(); BAD("minibatch index out of range"); }
@@ -577,7 +593,7 @@ struct Engine : EngineBase {
       ++launches;
     } else {
       if (!idx_pool || pool_B != B) { ph_end(); ctx->err = "no resident minibatch lists for this batch size"; return AGP_ERR_STATE; }
-      idx_select_kernel<T><<<(B + 255) / 256, 256, 0, st()>>>(idx_pool, n_lists, B, counters, idx_cur, xx, xx_cur);
+      idx_select_kernel<T><<<(B + 255) / 256, 256, 0, st()>>>(idx_pool, n_lists, B, counters, cursor_offset, idx_cur, xx, xx_cur);
     }
     ++launches;
     ph_end();
@@ -587,11 +603,12 @@ struct Engine : EngineBase {
   // kernel matrices + predictive moments of the owned latents for B rows of Xsrc (gathered through `gather` when given).
   // Also the whole of _predict_f (training/predictions.jl:25-50): mu* = k* (K \ mu) = V* mu_v and
   // sigma2* = kdiag + jitter - diag(k* A k*^T) = Ktilde* + rowsum((V* Sigma_v) .* V*).
+  // stages: 1 = kernel matrices (Knm, V [+ sum V^2]), 2 = V X^T + row statistics, 3 = both
   int moments_rows(const T* Xsrc, const T* xsrc, const int64_t* gather, int B, bool fresh_kernel_matrices, double* mean_out,
-                   double* var_out, int64_t out_ld, bool need_var) {
+                   double* var_out, int64_t out_ld, bool need_var, int stages = 3) {
     for (int q = 0; q < Ql; ++q) {
       Latent& L = lat[q];
-      if (fresh_kernel_matrices) {
+      if (stages & 1) {
         ph_begin(PH_KMAT);
         GemmParams<T> g{};
         g.A = Xsrc; g.lda = Dp; g.a_gather = gather; g.B = L.Z; g.ldb = Dp; g.C = L.Knm; g.ldc = ldm;
@@ -602,7 +619,7 @@ struct Engine : EngineBase {
         ph_end();
         if (prec == AGP_PREC_TF32X3) {
           ph_begin(PH_KAPPA);
-          CK(cudaMemsetAsync(L.racc, 0, 3 * ldB * sizeof(double), st()));
+          CK(cudaMemsetAsync(L.racc, 0, ldB * sizeof(double), st()));
           UmmaEpilogue ep{};
           ep.mode = UMMA_EPI_STORE_SUMSQ; ep.acc0 = L.racc;
           CKS(umma_gemm_nt(ctx_err(), L.um, UM_KNM, UM_LINV, (float*)(void*)L.V, B, m, ep, st()));
@@ -618,10 +635,11 @@ struct Engine : EngineBase {
           ph_end();
         }
       }
+      if (!(stages & 2)) continue;
       {
         ph_begin(PH_KSIGMA);
         if (prec == AGP_PREC_TF32X3) {
-          if (!fresh_kernel_matrices) CK(cudaMemsetAsync(L.racc + ldB, 0, 2 * ldB * sizeof(double), st()));
+          CK(cudaMemsetAsync(L.racc + ldB, 0, 2 * ldB * sizeof(double), st()));
           UmmaEpilogue ep{};
           ep.mode = UMMA_EPI_STATS_ONLY; ep.acc0 = L.racc + ldB; ep.acc1 = L.racc + 2 * ldB; ep.tvec = L.tvec;
           CKS(umma_gemm_nt(ctx_err(), L.um, UM_V, UM_X, (float*)(void*)L.VS, B, m, ep, st()));
@@ -649,9 +667,9 @@ struct Engine : EngineBase {
     CK(cudaGetLastError());
     return AGP_OK;
   }
-  int moments_impl(bool from_batch, int B, bool fresh) {
+  int moments_impl(bool from_batch, int B, bool fresh, int stages = 3) {
     return moments_rows(from_batch ? Xb : X, from_batch ? xxb : xx, from_batch ? nullptr : idx_cur, B, fresh,
-                        mean_f + (size_t)qbeg * ldB, var_f + (size_t)qbeg * ldB, ldB, true);
+                        mean_f + (size_t)qbeg * ldB, var_f + (size_t)qbeg * ldB, ldB, true, stages);
   }
 
   LikParams lik_params(int B, bool from_batch, int update) {
@@ -670,12 +688,17 @@ struct Engine : EngineBase {
     if (B < 1 || B > Bcap) BAD("The size of mini-batch is incorrect (negative or bigger than the batch capacity)");
     if (prec == AGP_PREC_TF32X3 && (B % 128)) BAD("TF32X3 precision needs B % 128 == 0");
     if (!from_batch) CKS(prep_idx(idx, B, base));
-    curB = B; cur_from_batch = from_batch; kernel_matrices_stale = false;
+    curB = B; cur_from_batch = from_batch; kernel_matrices_stale = false; prefetched = false;
     CKS(moments_impl(from_batch, B, true));
     return AGP_OK;
   }
 
   int step_update(double rho) override {
+    CKS(step_update_a(rho));
+    return step_update_b(rho);
+  }
+  // local updates + everything that still reads V (V^T g, Gram product)
+  int step_update_a(double rho) {
     if (curB < 1) { ctx->err = "no minibatch in flight"; return AGP_ERR_STATE; }
     const int B = curB;
     ph_begin(PH_LIK);
@@ -705,7 +728,17 @@ struct Engine : EngineBase {
         gemm_simt_launch<T, true, true, EPI_PLAIN>(g, ns, st());
         ++launches;
       }
+      L.gram_splits = ns;
       ph_end();
+    }
+    CK(cudaGetLastError());
+    return AGP_OK;
+  }
+  // natural-parameter update + the m x m tail of every owned latent
+  int step_update_b(double rho) {
+    for (int q = 0; q < Ql; ++q) {
+      Latent& L = lat[q];
+      const int ns = L.gram_splits;
       ph_begin(PH_COMBINE);
       TailParams tp{};
       tp.m = m; tp.mp = mp; tp.ld = mp; tp.n_split = ns; tp.gpart_stride = (int64_t)m * ldm; tp.gpart_ld = ldm;
@@ -770,19 +803,74 @@ struct Engine : EngineBase {
     gB = -1;
   }
 
+  // one resident-list step, software-pipelined (see `side` above)
+  int step_pool(int B, double rho) {
+    if (!have_K) { ctx->err = "agp_refresh_K must be called before a step"; return AGP_ERR_STATE; }
+    if (!have_data) { ctx->err = "upload data first"; return AGP_ERR_STATE; }
+    if (B < 1 || B > Bcap) BAD("The size of mini-batch is incorrect (negative or bigger than the batch capacity)");
+    if (prec == AGP_PREC_TF32X3 && (B % 128)) BAD("TF32X3 precision needs B % 128 == 0");
+    const bool pipe = pipeline && !prof;
+    if (!prefetched || curB != B) {          // cold start: kernel matrices of the minibatch at the cursor, on the main stream
+      CKS(prep_idx(nullptr, B, 0, 0));
+      CKS(moments_impl(false, B, true, 1));
+    }
+    curB = B; cur_from_batch = false; kernel_matrices_stale = false; prefetched = false;
+    CKS(moments_impl(false, B, true, 2));    // V X^T, row statistics (needs the posterior of the previous step)
+    CKS(step_update_a(rho));                 // local updates, V^T g, Gram product: last readers of V / idx_cur
+    if (pipe) {
+      CK(cudaEventRecord(ev_fork, ctx->stream));
+      CK(cudaStreamWaitEvent(side, ev_fork, 0));
+      cur_stream = side;
+      int s = AGP_OK;
+      if (cudaMemcpyAsync(idx_prev, idx_cur, (size_t)B * 8, cudaMemcpyDeviceToDevice, st()) != cudaSuccess) s = AGP_ERR_CUDA;
+      if (s == AGP_OK) s = prep_idx(nullptr, B, 0, 1);          // the cursor is bumped at the end of this step
+      if (s == AGP_OK) s = moments_impl(false, B, true, 1);
+      if (s == AGP_OK && cudaEventRecord(ev_join, side) != cudaSuccess) s = AGP_ERR_CUDA;
+      cur_stream = nullptr;
+      if (s != AGP_OK) { if (ctx->err.empty()) ctx->err = "CUDA failure while prefetching"; return s; }
+    }
+    CKS(step_update_b(rho));
+    if (pipe) {
+      CK(cudaStreamWaitEvent(ctx->stream, ev_join, 0));
+      prefetched = true;
+      kernel_matrices_stale = true;          // Knm / V now belong to the NEXT minibatch
+    }
+    have_step = true;
+    return AGP_OK;
+  }
+
+  // rebuild Knm / V of the minibatch the last step consumed (after a prefetch or a predict_f overwrote them)
+  int ensure_current_kernel_matrices() {
+    if (!kernel_matrices_stale) return AGP_OK;
+    if (!cur_from_batch && prefetched) {
+      CK(cudaMemcpyAsync(idx_cur, idx_prev, (size_t)curB * 8, cudaMemcpyDeviceToDevice, st()));
+      xx_gather_kernel<T><<<(curB + 255) / 256, 256, 0, st()>>>(idx_cur, curB, xx, xx_cur);
+      ++launches;
+    }
+    prefetched = false;
+    kernel_matrices_stale = false;
+    return moments_impl(cur_from_batch, curB, true, 1);
+  }
+
   int step_full(const int64_t* idx, int B, int base, double rho) override {
-    if (want_graph && !prof && !idx && !capturing) {
-      if (!gexec || gB != B || grho != rho) {
+    if (idx) {
+      CKS(step_moments(idx, B, base, false));
+      return step_update(rho);
+    }
+    if (want_graph && !prof && !capturing) {
+      const bool need_prime = pipeline && (!prefetched || curB != B);
+      if (!gexec || gB != B || grho != rho || need_prime) {
         drop_graph();
-        if (!have_K) { ctx->err = "agp_refresh_K must be called before a step"; return AGP_ERR_STATE; }
+        if (need_prime) return step_pool(B, rho);  // priming step (brings the pipeline to its steady state); later calls replay the graph
+      }
+      if (!gexec) {
         cudaGraph_t graph = nullptr;
         int64_t l0 = launches;
-        CK(cudaStreamBeginCapture(st(), cudaStreamCaptureModeRelaxed));
+        CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
         capturing = true;
-        int s = step_moments(nullptr, B, base, false);
-        if (s == AGP_OK) s = step_update(rho);
+        int s = step_pool(B, rho);
         capturing = false;
-        cudaError_t ce = cudaStreamEndCapture(st(), &graph);
+        cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
         if (s != AGP_OK) { if (graph) cudaGraphDestroy(graph); return s; }
         CK(ce);
         g_launches = launches - l0;
@@ -791,14 +879,14 @@ struct Engine : EngineBase {
         cudaGraphDestroy(graph);
         gB = B; grho = rho;
       }
-      CK(cudaGraphLaunch(gexec, st()));
+      CK(cudaGraphLaunch(gexec, ctx->stream));
       launches += g_launches;
       for (auto& L : lat) L.muv_valid = false;
       curB = B; cur_from_batch = false; have_step = true;
+      prefetched = pipeline; kernel_matrices_stale = pipeline;
       return AGP_OK;
     }
-    CKS(step_moments(idx, B, base, false));
-    return step_update(rho);
+    return step_pool(B, rho);
   }
 
   int step_batch(const void* xbh, int x_dtype, int x_layout, const void* const* ybh, int y_kind, int B, double rho) override {
@@ -833,9 +921,9 @@ struct Engine : EngineBase {
   // moments of the last minibatch under the UPDATED posterior (ELBO uses the post-update mu, Sigma)
   int elbo_moments() override {
     if (curB < 1) { ctx->err = "no minibatch to evaluate the ELBO on"; return AGP_ERR_STATE; }
-    bool fresh = kernel_matrices_stale;  // predict_f overwrote Knm / V: rebuild them from the retained minibatch
-    kernel_matrices_stale = false;
-    return moments_impl(cur_from_batch, curB, fresh);
+    const bool was_stale = kernel_matrices_stale;  // a prefetch / predict_f overwrote Knm / V: rebuild them first
+    CKS(ensure_current_kernel_matrices());
+    return moments_impl(cur_from_batch, curB, was_stale, 2);
   }
 
   int elbo(double rho, double* out3) override {
@@ -918,6 +1006,7 @@ struct Engine : EngineBase {
   int set_counters(int64_t t, int64_t cur) override {
     if (t < 1 || cur < 0) BAD("bad counters");
     int64_t c[2] = {t, cur};
+    prefetched = false; drop_graph();
     CK(cudaStreamSynchronize(st()));
     CK(cudaMemcpy(counters, c, 16, cudaMemcpyHostToDevice));
     return AGP_OK;
@@ -944,6 +1033,7 @@ struct Engine : EngineBase {
   }
   int get_kernel_matrices(int ql, double* Knm, double* kappa, int B) override {
     if (ql < 0 || ql >= Ql || B < 1 || B > Bcap) BAD("bad kernel-matrix query");
+    if (curB > 0) CKS(ensure_current_kernel_matrices());
     Latent& L = lat[ql];
     if (!pKS) CKS(dalloc(&pKS, (size_t)Bcap * ldm));
     if (kappa) {  // kappa = Knm / K = V L^-1   (NN product with the T shadow of L^-1)
@@ -1039,6 +1129,12 @@ int Engine<T>::predict_f(const void* Xt, int x_dtype, int x_layout, int64_t nt, 
   // the predictive variance of the reference is NOT checked for positivity (predictions.jl:38-44): drop a Ktilde flag
   cudaMemsetAsync(status, 0, sizeof(int), st());
   kernel_matrices_stale = true;
+  if (prefetched) {  // the prefetched kernel matrices were overwritten: fall back to the last consumed minibatch
+    prefetched = false; drop_graph();
+    cudaMemcpyAsync(idx_cur, idx_prev, (size_t)curB * 8, cudaMemcpyDeviceToDevice, st());
+    xx_gather_kernel<T><<<(curB + 255) / 256, 256, 0, st()>>>(idx_cur, curB, xx, xx_cur);
+    ++launches;
+  }
   if (rc == AGP_ERR_CUDA && ctx->err.empty()) ctx->err = "CUDA failure in predict_f";
   return rc;
 }

@@ -53,11 +53,11 @@ __global__ void idx_rebase_kernel(const int64_t* __restrict__ src, int64_t* __re
 // later kernel of the step - and a captured CUDA graph - reads one fixed address)
 template <typename T>
 __global__ void idx_select_kernel(const int64_t* __restrict__ pool, int64_t n_lists, int B,
-                                  const int64_t* __restrict__ counters /*[0]=t,[1]=cursor*/, int64_t* __restrict__ dst,
-                                  const T* __restrict__ xx_all, T* __restrict__ xx_cur) {
+                                  const int64_t* __restrict__ counters /*[0]=t,[1]=cursor*/, int cursor_offset,
+                                  int64_t* __restrict__ dst, const T* __restrict__ xx_all, T* __restrict__ xx_cur) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B) return;
-  int64_t cur = counters[1] % n_lists;
+  int64_t cur = (counters[1] + cursor_offset) % n_lists;
   int64_t r = pool[cur * B + i];
   dst[i] = r;
   xx_cur[i] = xx_all[r];   // gather the squared norms once (the K_nm epilogue then reads them by minibatch row)

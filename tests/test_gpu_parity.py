@@ -219,3 +219,36 @@ def test_full_size_properties(agp):
         assert np.allclose(S, S.T, rtol=0, atol=1e-12 * np.abs(S).max())
         assert np.all(np.linalg.eigvalsh(S) > 0)
     assert rel_fro(posts[1][0], posts[0][0]) < 1e-9 and rel_fro(posts[1][1], posts[0][1]) < 1e-9
+
+
+@pytest.mark.parametrize("precision", ["f64", "tf32x3"])
+def test_pipelined_pool_steps_match_host_list_steps(agp, precision):
+    """resident-list steps are software-pipelined (next minibatch's Knm / V built on a side stream during the tail) and
+    CUDA-graph replayed; they must give the same posterior / ELBO / state as plain host-list steps, including an ELBO
+    and a prediction in the middle of the run (which invalidate the prefetch)."""
+    n, D, m, B, iters = 4096, 8, 128, 256, 7
+    X, y, Z, mbs, F, rng = make_data("logistic", n, D, m, B, iters, seed=11)
+    kern = agp.SqExponentialKernel() @ agp.ScaleTransform(1 / np.sqrt(D))
+    ref = agp.SVGP(kern, agp.LogisticLikelihood(), agp.AnalyticSVI(B), Z, precision=precision)
+    ref, st_ref = agp.train(ref, X, y, iters, minibatches=mbs)
+    elbo_ref = agp.ELBO(ref, st_ref)
+    for graph in (0, 1):
+        mdl = agp.SVGP(kern, agp.LogisticLikelihood(), agp.AnalyticSVI(B), Z, precision=precision)
+        mdl, st = agp.train(mdl, X, y, 1, minibatches=mbs[:1])
+        e, L = mdl._eng, agp._lib
+        arr = np.ascontiguousarray(np.stack(mbs[1:]))
+        e.ck(e.lib.agp_minibatches_upload(e.model, arr.ctypes.data_as(L.c_int64_p), iters - 1, B, 0))
+        e.ck(e.lib.agp_use_graph(e.model, graph))
+        for it in range(iters - 1):
+            e.ck(e.lib.agp_step_async(e.model, None, B, 0, n / B))
+            if it == 2:
+                agp.ELBO(mdl, st)          # forces a rebuild of the consumed minibatch's kernel matrices
+            if it == 4:
+                agp.predict_f(mdl, X[:300], cov=True)
+        e.ck(e.lib.agp_sync(e.model))
+        mu, S, _, _ = mdl.posterior(0)
+        mu_r, S_r, _, _ = ref.posterior(0)
+        tol = 1e-9 if precision == "f64" else 1e-5
+        assert rel_fro(mu, mu_r) < tol and rel_fro(S, S_r) < tol, (graph, rel_fro(mu, mu_r), rel_fro(S, S_r))
+        assert abs(agp.ELBO(mdl, st) - elbo_ref) < 1e-6 * abs(elbo_ref) + (0 if precision == "f64" else 1e-4 * abs(elbo_ref))
+        assert mdl.counters() == (iters + 1, iters - 1)
