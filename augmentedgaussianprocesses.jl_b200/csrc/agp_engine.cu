@@ -51,7 +51,7 @@ enum Phase {
 };
 static const char* kPhaseNames[PH_COUNT] = {"idx_select",  "kmat_knm",   "gemm_v",     "gemm_v_sigma", "rowstats",
                                             "lik_update",  "gemv_grad1", "gemm_gram",  "combine_eta",      "chol_blocked",
-                                            "trtri",       "gemm_sigma", "finalize",   "tf32_split"};
+                                            "trtri",       "gemm_sigma", "finalize",   "scale_transpose"};
 
 // ---------------------------------------------------------------------------------------------------
 struct EngineBase {
@@ -714,12 +714,17 @@ struct Engine : EngineBase {
         gemv_t_kernel<T><<<dim3((m + 31) / 32, (B + rpb - 1) / rpb), dim3(32, 8), 0, st()>>>(L.V, ldm, gmu + (size_t)q * ldB, B, m, rpb, L.v1); }
       ++launches;
       ph_end();
+      if (prec == AGP_PREC_TF32X3) {
+        ph_begin(PH_SPLIT);
+        CKS(umma_scale_transpose(ctx_err(), L.um, (const float*)(const void*)L.V, gS + (size_t)q * ldB, rho, gmu + (size_t)q * ldB, L.v1, B, m, st()));
+        ++launches;
+        ph_end();
+      }
       ph_begin(PH_GRAM);
       int ns = n_split;
       if (prec == AGP_PREC_TF32X3) {
-        CKS(umma_gram(ctx_err(), L.um, (const float*)(const void*)L.V, gS + (size_t)q * ldB, rho, gmu + (size_t)q * ldB, L.v1,
-                      (float*)(void*)L.Gpart, B, m, &ns, st()));
-        launches += 2;
+        CKS(umma_gram(ctx_err(), L.um, (float*)(void*)L.Gpart, B, m, &ns, st()));
+        ++launches;
       } else {
         GemmParams<T> g{};  // rho * V^T diag(grad_Sigma) V  (functions/utils.jl:70-72, whitened), split over the minibatch
         g.A = L.V; g.lda = ldm; g.B = L.V; g.ldb = ldm; g.C = L.Gpart; g.ldc = ldm; g.M = m; g.N = m; g.K = B;
@@ -793,7 +798,8 @@ struct Engine : EngineBase {
   // mu_v = X^T t (only getters / the ELBO need it)
   void ensure_muv(Latent& L) {
     if (L.muv_valid) return;
-    matvec_t_kernel<<<(m + 127) / 128, 128, 0, st()>>>(L.Xv, mp, m, L.tvec, L.muv);
+    cudaMemsetAsync(L.muv, 0, m * sizeof(double), st());
+    gemv_t_kernel<double><<<dim3((m + 31) / 32, (m + 63) / 64), dim3(32, 8), 0, st()>>>(L.Xv, mp, L.tvec, m, m, 64, L.muv);
     ++launches;
     L.muv_valid = true;
   }
@@ -942,7 +948,7 @@ struct Engine : EngineBase {
       Latent& L = lat[q];
       CK(cudaMemsetAsync(d_out + 4, 0, 2 * sizeof(double), st()));
       ensure_muv(L);
-      gauss_kl_x_kernel<<<1, 1024, 0, st()>>>(L.Xv, mp, m, L.muv, L.mu0v, d_out + 4);
+      gauss_kl_x_kernel<<<(m + 7) / 8, 256, 0, st()>>>(L.Xv, mp, m, L.muv, L.mu0v, d_out + 4);
       ++launches;
       double t2[2], ldp;
       CK(cudaMemcpyAsync(t2, d_out + 4, 2 * sizeof(double), cudaMemcpyDeviceToHost, st()));

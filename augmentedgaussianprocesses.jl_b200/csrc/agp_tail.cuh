@@ -123,16 +123,23 @@ __device__ __forceinline__ void tile_potf2_inv(const double* sa, double* lcol /*
         if (lo == j) {
           double d = xa[jj];
           if (!(d > 0.0)) { atomicOr(status, ST_NOT_POSDEF); d = 1.0; }
-          double r = (double)rsqrtf((float)d);
-          r = r * (1.5 - 0.5 * d * r * r);
-          r = r * (1.5 - 0.5 * d * r * r);
-          *reinterpret_cast<double2*>(lc + 64) = make_double2(r, r * r);
+          // only 1/d sits on the pivot chain (the sqrt scaling of W's rows is applied once at the end):
+          // MUFU.RCP64H seed + two Newton steps
+          double y;
+          asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+          y = y * (2.0 - d * y);
+          y = y * (2.0 - d * y);
+          lc[64] = y;
           dvals[j] = d;
         }
       }
       __syncthreads();
+#ifdef AGP_ABL_NO_UPDATE
+      if (false) {
+#else
       if (hi >= J) {
-        const double2 rr = *reinterpret_cast<const double2*>(lc + 64);
+#endif
+        const double inv_d = lc[64];
         double l16[16];                      // column j of A at rows/cols g0 .. g0+15 (shared by both updates)
 #pragma unroll
         for (int q = 0; q < 16; q += 2) {
@@ -140,29 +147,33 @@ __device__ __forceinline__ void tile_potf2_inv(const double* sa, double* lcol /*
           l16[q] = v.x; l16[q + 1] = v.y;
         }
         // A part: a_ic -= a_ij a_cj / d   for rows i = lo > j and my columns c = g0+q > j
-        const double ga = (lo > j) ? -lc[lo] * rr.y : 0.0;
+        const double ga = (lo > j) ? -lc[lo] * inv_d : 0.0;
         // W part: w_ic -= a_ij w_jc / d   for my rows i = g0+q > j and column c = lo <= j
         const double pw = pr[lo];
-        const double gw = (lo <= j) ? -pw * rr.y : 0.0;
+        const double gw = (lo <= j) ? -pw * inv_d : 0.0;
+#ifdef AGP_ABL_NO_FMA
+        if (false) {
+#else
         if (hi > J) {
+#endif
 #pragma unroll
           for (int q = 0; q < 16; ++q) { xa[q] = fma(l16[q], ga, xa[q]); xw[q] = fma(l16[q], gw, xw[q]); }
         } else {
 #pragma unroll
           for (int q = 0; q < 16; ++q) if (q > jj) { xa[q] = fma(l16[q], ga, xa[q]); xw[q] = fma(l16[q], gw, xw[q]); }
-          if (lo <= j) xw[jj] = pw * rr.x;   // final (scaled) row j of W
+          // row j of W is final up to its scaling by 1/sqrt(d_j), applied after the loop
         }
       }
     }
   }
+  __syncthreads();                         // dvals complete
 #pragma unroll
   for (int q = 0; q < 16; ++q) {
     int i = g0 + q;
-    double v = (lo <= i) ? xw[q] : 0.0;
+    double v = (lo <= i) ? xw[q] * rsqrt(dvals[i]) : 0.0;   // X = diag(d)^-1/2 W
     Xg[(int64_t)i * ldx + lo] = v;
     Dg[i * TNB + lo] = v;
   }
-  __syncthreads();
   if (t < TNB) {  // logdet += sum_j log d_j  (= 2 sum log R_jj), off the pivot chain
     double l = warp_sum(log(dvals[t]));
     if ((t & 31) == 0) atomicAdd(logdet, l);
@@ -297,25 +308,18 @@ __global__ void x_finalize_kernel(const double* __restrict__ X, int64_t ld, int 
   }
 }
 
-// out[0] += |X|_F^2 (= tr(Sigma_v)),  out[1] += |mu_v - mu0_v|^2       (single block)
+// out[0] += |X|_F^2 (= tr(Sigma_v)),  out[1] += |mu_v - mu0_v|^2 ; one warp per row of X, 8 rows per block
 __global__ void gauss_kl_x_kernel(const double* __restrict__ X, int64_t ld, int m, const double* __restrict__ muv,
                                   const double* __restrict__ mu0v, double* __restrict__ out) {
-  double tr = 0.0, q = 0.0;
-  for (int64_t e = threadIdx.x; e < (int64_t)m * m; e += blockDim.x) {
-    int i = (int)(e / m), j = (int)(e % m);
-    if (j <= i) { double v = X[(int64_t)i * ld + j]; tr += v * v; }
-  }
-  for (int j = threadIdx.x; j < m; j += blockDim.x) { double d = muv[j] - mu0v[j]; q += d * d; }
-  __shared__ double s1[32], s2[32];
-  tr = warp_sum(tr); q = warp_sum(q);
-  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  if (l == 0) { s1[w] = tr; s2[w] = q; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double a = 0.0, c = 0.0;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += s1[i]; c += s2[i]; }
-    out[0] += a;
-    out[1] += c;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= m) return;
+  double tr = 0.0;
+  for (int j = lane; j <= i; j += 32) { double v = X[(int64_t)i * ld + j]; tr += v * v; }
+  tr = warp_sum(tr);
+  if (lane == 0) {
+    double d = muv[i] - mu0v[i];
+    atomicAdd(out + 0, tr);
+    atomicAdd(out + 1, d * d);
   }
 }
 

@@ -8,7 +8,7 @@
 //   warp 0      : TMA producer  (cp.async.bulk.tensor.2d, 128B swizzle): the RAW fp32 A and B tiles of one 32-wide
 //                 k-block (2 x 16 KB) per stage -- operands cross L2 -> SM once, not as separate hi and lo copies
 //                 (the first version streamed pre-split operands and was L2-bandwidth bound: 168 MB / launch)
-//   warps 2..5  : converters: raw tile -> hi / lo tiles at the same (swizzled) offsets, fence.proxy.async, then
+//   warps 2..9  : two converter groups (alternating k-blocks): raw tile -> hi / lo tiles at the same (swizzled) offsets, fence.proxy.async, then
 //                 hand the stage to the MMA warp; after the main loop the same warps run the epilogue
 //                 (tcgen05.ld 32x32b -> registers -> fp32 row-major global stores)
 //   warp 1      : TMEM allocator + MMA issuer (one elected lane, 12 tcgen05.mma per k-block, tcgen05.commit
@@ -29,14 +29,19 @@ namespace agp {
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 32, STAGES = 3;
+constexpr int BM = 128, BN = 128, BK = 32;
+constexpr int RS = 4;                          // raw (TMA) ring depth: prefetch distance of 4 k-blocks
+constexpr int CS = 2;                          // converted-operand ring depth (one slot per converter group)
 constexpr int TILE_BYTES = BM * BK * 4;        // 16 KB : 128 rows x 128 B (one 128B-swizzle atom wide)
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;    // raw A, raw B, B_hi, B_lo   (A_hi / A_lo live in TMEM)
+constexpr int RAW_BYTES = 2 * TILE_BYTES;      // raw A, raw B
+constexpr int CONV_BYTES = 2 * TILE_BYTES;     // B_hi, B_lo   (A_hi / A_lo live in TMEM)
+constexpr int RING_BYTES = RS * RAW_BYTES + CS * CONV_BYTES;
 constexpr int NUM_CONV_THREADS = 128;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int TMEM_COLS = 512;     // [0,128) fp32 accumulator, then per stage 32 columns A_hi + 32 columns A_lo
+constexpr int SMEM_BYTES = RING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int TMEM_COLS = 256;     // [0,128) fp32 accumulator, then per converted slot 32 columns A_hi + 32 columns A_lo
 constexpr int TMEM_A0 = 128;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_CONV_GROUPS = 2;   // converter groups (4 warps each) alternate k-blocks
+constexpr int NUM_THREADS = 64 + NUM_CONV_GROUPS * 128;
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -157,22 +162,21 @@ umma_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bars = smem_base + STAGES * STAGE_BYTES;
+  const uint32_t bars = smem_base + RING_BYTES;
   auto raw_full = [&](int s) { return bars + 8u * s; };
-  auto raw_empty = [&](int s) { return bars + 8u * (STAGES + s); };
-  auto conv_full = [&](int s) { return bars + 8u * (2 * STAGES + s); };
-  auto mma_done = [&](int s) { return bars + 8u * (3 * STAGES + s); };
-  const uint32_t tmem_full_bar = bars + 8u * (4 * STAGES);
-  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * STAGE_BYTES + 8 * (4 * STAGES + 1));
+  auto raw_empty = [&](int s) { return bars + 8u * (RS + s); };
+  auto conv_full = [&](int s) { return bars + 8u * (2 * RS + s); };
+  auto mma_done = [&](int s) { return bars + 8u * (2 * RS + CS + s); };
+  const uint32_t tmem_full_bar = bars + 8u * (2 * RS + 2 * CS);
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + RING_BYTES + 8 * (2 * RS + 2 * CS + 1));
+  const uint32_t conv_base = smem_base + RS * RAW_BYTES;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), NUM_CONV_THREADS);
-      mbar_init(conv_full(s), NUM_CONV_THREADS); mbar_init(mma_done(s), 1);
-    }
+    for (int s = 0; s < RS; ++s) { mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), NUM_CONV_THREADS); }
+    for (int s = 0; s < CS; ++s) { mbar_init(conv_full(s), NUM_CONV_THREADS); mbar_init(mma_done(s), 1); }
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -189,9 +193,9 @@ umma_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       // ===== TMA producer: raw fp32 tiles =====
       for (int i = 0; i < nkb; ++i) {
-        const int s = i % STAGES;
-        mbar_wait(raw_empty(s), ((i / STAGES) & 1) ^ 1);
-        const uint32_t dst = smem_base + s * STAGE_BYTES;
+        const int s = i % RS;
+        mbar_wait(raw_empty(s), ((i / RS) & 1) ^ 1);
+        const uint32_t dst = smem_base + s * RAW_BYTES;
         mbar_expect_tx(raw_full(s), 2 * TILE_BYTES);
         const int k = (kb0 + i) * BK;
         tma_load_2d(dst + 0 * TILE_BYTES, &tmA, raw_full(s), k, tile_m * BM);
@@ -201,12 +205,11 @@ umma_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp == 1) {
     // ===== MMA issuer =====
     for (int i = 0; i < nkb; ++i) {
-      const int s = i % STAGES;
-      mbar_wait(conv_full(s), (i / STAGES) & 1);
+      const int s = i % CS;
+      mbar_wait(conv_full(s), (i / CS) & 1);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t base = smem_base + s * STAGE_BYTES;
-        const uint32_t b_hi = base + 2 * TILE_BYTES, b_lo = base + 3 * TILE_BYTES;
+        const uint32_t b_hi = conv_base + s * CONV_BYTES, b_lo = b_hi + TILE_BYTES;
         const uint32_t a_hi = tmem_base + TMEM_A0 + s * 64, a_lo = a_hi + 32;
 #pragma unroll
         for (int kk = 0; kk < BK / 8; ++kk) {
@@ -223,15 +226,17 @@ umma_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else {
     // ===== converters (raw -> hi / lo), then epilogue: warps 2..5 =====
-    const int ct = threadIdx.x - 64;  // 0..127
-    const int q = warp & 3;           // TMEM lane quarter this warp may access
+    const int grp = (warp - 2) >> 2;                 // converter group: handles k-blocks i = grp (mod NUM_CONV_GROUPS)
+    const int ct = (threadIdx.x - 64) & 127;         // 0..127 within the group
+    const int q = warp & 3;                          // TMEM lane quarter this warp may access
     const int arow = q * 32 + lane;   // A-tile row = TMEM lane handled by this thread
-    for (int i = 0; i < nkb; ++i) {
-      const int s = i % STAGES;
-      mbar_wait(raw_full(s), (i / STAGES) & 1);            // TMA landed the raw tiles
-      mbar_wait(mma_done(s), ((i / STAGES) & 1) ^ 1);      // previous MMAs on this stage's buffers retired
+    for (int i = grp; i < nkb; i += NUM_CONV_GROUPS) {
+      const int rs = i % RS, s = i % CS;
+      mbar_wait(raw_full(rs), (i / RS) & 1);               // TMA landed the raw tiles
+      mbar_wait(mma_done(s), ((i / CS) & 1) ^ 1);          // previous MMAs on this slot's converted operands retired
       tc_fence_after();
-      uint8_t* base = smem_gen + s * STAGE_BYTES;
+      uint8_t* base = smem_gen + rs * RAW_BYTES;
+      uint8_t* cbase_s = smem_gen + RS * RAW_BYTES + s * CONV_BYTES;
       {
         // A: row `arow` of the raw tile (128 B, 16-byte chunks XOR-swizzled with row & 7) -> hi / lo -> TMEM
         const float4* rowp = reinterpret_cast<const float4*>(base + arow * 128);
@@ -252,8 +257,8 @@ umma_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       {
         // B: raw -> hi / lo tiles at the same (swizzled) offsets in shared memory
         const float4* raw = reinterpret_cast<const float4*>(base + 1 * TILE_BYTES);
-        float4* hi = reinterpret_cast<float4*>(base + 2 * TILE_BYTES);
-        float4* lo = reinterpret_cast<float4*>(base + 3 * TILE_BYTES);
+        float4* hi = reinterpret_cast<float4*>(cbase_s);
+        float4* lo = reinterpret_cast<float4*>(cbase_s + TILE_BYTES);
 #pragma unroll
         for (int u = 0; u < TILE_BYTES / 16 / NUM_CONV_THREADS; ++u) {
           const int e = ct + u * NUM_CONV_THREADS;
@@ -269,7 +274,7 @@ umma_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
       fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      mbar_arrive(raw_empty(s));    // the raw tiles may be overwritten by the next TMA
+      mbar_arrive(raw_empty(rs));   // the raw tiles may be overwritten by the next TMA
       mbar_arrive(conv_full(s));    // operands ready for the MMA warp
     }
     const int row = tile_m * BM + q * 32 + lane;
@@ -280,7 +285,7 @@ umma_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = grp; c < BN / 32; c += NUM_CONV_GROUPS) {
         uint32_t r[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
         TMEM_LD32(taddr, r);
@@ -308,7 +313,7 @@ umma_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       if (ep.mode == UMMA_EPI_STORE_SUMSQ) atomicAdd(ep.acc0 + row, acc_sq);
       if (ep.mode == UMMA_EPI_STATS_ONLY) { atomicAdd(ep.acc0 + row, acc_sq); atomicAdd(ep.acc1 + row, acc_dot); }
-    } else if (ep.mode != UMMA_EPI_STATS_ONLY) {
+    } else if (ep.mode != UMMA_EPI_STATS_ONLY && grp == 0) {
       for (int c = 0; c < BN / 4; ++c) reinterpret_cast<float4*>(crow)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
@@ -432,11 +437,18 @@ int umma_gemm_nt(std::string* err, UmmaLatent& u, int a_which, int b_which, floa
   return 0;
 }
 
-int umma_gram(std::string* err, UmmaLatent& u, const float* V, const double* w, double rho, const double* g, double* v1, float* Gpart,
-              int B, int m, int* n_split, cudaStream_t st) {
-  Maps* mp = (Maps*)u.tmaps;
+int umma_scale_transpose(std::string* err, UmmaLatent& u, const float* V, const double* w, double rho, const double* g, double* v1,
+                         int B, int m, cudaStream_t st) {
   if (B % BM || m % BN) return fail(err, "shape not a multiple of the tile");
   scale_transpose_kernel<<<dim3(m / 32, B / 128), dim3(32, 8), 0, st>>>(V, u.ldm, w, rho, u.UT, u.Bcap, g, v1);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(err, "scale_transpose_kernel", e);
+  return 0;
+}
+
+int umma_gram(std::string* err, UmmaLatent& u, float* Gpart, int B, int m, int* n_split, cudaStream_t st) {
+  Maps* mp = (Maps*)u.tmaps;
+  if (B % BM || m % BN) return fail(err, "shape not a multiple of the tile");
   const int total_kb = B / BK;
   const int nt = m / BN, upper_tiles = nt * (nt + 1) / 2;
   int S = (148 + upper_tiles - 1) / upper_tiles;

@@ -36,8 +36,10 @@ void umma_latent_free(UmmaLatent& u);
 // C[M x N] = A[M x K] * B[N x K]^T with K = m, 3xTF32 (operands split to hi/lo inside the kernel)
 int umma_gemm_nt(std::string* err, UmmaLatent& u, int a_which, int b_which, float* C, int M, int N, const UmmaEpilogue& ep,
                  cudaStream_t st);
-// Gpart[s] = sum_{b in split s} rho*w_b V_b V_b^T (full symmetric tiles) ; v1 += V^T g ; *n_split in: capacity, out: used
-int umma_gram(std::string* err, UmmaLatent& u, const float* V, const double* w, double rho, const double* g, double* v1, float* Gpart,
-              int B, int m, int* n_split, cudaStream_t st);
+// U^T = (diag(sqrt(rho w)) V)^T into u.UT, fused with v1 += V^T g
+int umma_scale_transpose(std::string* err, UmmaLatent& u, const float* V, const double* w, double rho, const double* g, double* v1,
+                         int B, int m, cudaStream_t st);
+// Gpart[s] = sum_{b in split s} U_b U_b^T (full symmetric tiles) ; *n_split in: capacity, out: used
+int umma_gram(std::string* err, UmmaLatent& u, float* Gpart, int B, int m, int* n_split, cudaStream_t st);
 
 }  // namespace agp

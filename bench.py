@@ -310,7 +310,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("AGP_BENCH_PRECISION", "f32"), choices=["f32", "tf32x3", "f64"])
+    ap.add_argument("--precision", default=os.environ.get("AGP_BENCH_PRECISION", "tf32x3"), choices=["f32", "tf32x3", "f64"])
     ap.add_argument("--graph", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

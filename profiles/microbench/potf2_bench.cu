@@ -28,10 +28,10 @@ int main() {
   for (int j = 0; j < 64; j += 1) {
     long long pre = dbg[j * 4 + 0], post = dbg[j * 4 + 1], end = dbg[j * 4 + 2];
     long long prev_end = j ? dbg[(j - 1) * 4 + 2] : pre; long long fdone = dbg[j * 4 + 3];
-    if (j < 6 || j % 8 == 0 || j > 60) printf("pivot %2d: publish %5lld  barrier-wait %5lld  lds+f %5lld fma %5lld   total %5lld\n", j, pre - prev_end, post - pre, fdone - post, end - fdone, end - prev_end);
+    if (0) printf("pivot %2d: publish %5lld  barrier-wait %5lld  lds+f %5lld fma %5lld   total %5lld\n", j, pre - prev_end, post - pre, fdone - post, end - fdone, end - prev_end);
   }
   long long own[256]; cudaMemcpyFromSymbol(own, agp_own, sizeof(own));
-  for (int j = 1; j < 64; j += 7) printf("owner pivot %2d: since prev owner-done %5lld | newton %5lld | publish r %5lld\n", j, own[j*4+0]-own[(j-1)*4+2], own[j*4+1]-own[j*4+0], own[j*4+2]-own[j*4+1]);
+  for (int j = 1; j < 1; j += 7) printf("owner pivot %2d: since prev owner-done %5lld | newton %5lld | publish r %5lld\n", j, own[j*4+0]-own[(j-1)*4+2], own[j*4+1]-own[j*4+0], own[j*4+2]-own[j*4+1]);
   // check X * A * X^T = I
   std::vector<double> X(n * n); cudaMemcpy(X.data(), dX, n * n * 8, cudaMemcpyDeviceToHost);
   double maxerr = 0;
