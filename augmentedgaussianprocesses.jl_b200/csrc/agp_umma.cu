@@ -326,29 +326,39 @@ umma_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
 // U^T = (diag(sqrt(rho w)) V)^T:  V is [B][ldv], output is [m][ldt] fp32 (split to hi/lo inside the GEMM); fused with
 // v1[j] += sum_b V[b][j] g[b]  (transpose(kappa) * grad_mu, analyticVI.jl:168, whitened).  Block = 32 columns x 128 rows.
-__global__ void scale_transpose_kernel(const float* __restrict__ V, int64_t ldv, const double* __restrict__ w, double rho,
-                                       float* __restrict__ UT, int64_t ldt, const double* __restrict__ g, double* __restrict__ v1) {
-  __shared__ float tile[32][33];
+__global__ void __launch_bounds__(256) scale_transpose_kernel(const float* __restrict__ V, int64_t ldv, const double* __restrict__ w, double rho,
+                                                              float* __restrict__ UT, int64_t ldt, const double* __restrict__ g,
+                                                              double* __restrict__ v1) {
+  __shared__ float tile[128][33];
+  __shared__ float sw[128];
+  __shared__ double sg[128];
   __shared__ double red[8][33];
-  const int j0 = blockIdx.x * 32;
-  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  const int j0 = blockIdx.x * 32, b0 = blockIdx.y * 128;
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;  // 32 x 8
+  if (tid < 128) {
+    sw[tid] = (float)sqrt(fmax(rho * w[b0 + tid], 0.0));
+    sg[tid] = g[b0 + tid];
+  }
+  float v[16];
+#pragma unroll
+  for (int u = 0; u < 16; ++u) v[u] = V[(int64_t)(b0 + ty + 8 * u) * ldv + j0 + tx];   // 16 independent coalesced loads
+  __syncthreads();
   double dot = 0.0;
-  for (int sub = 0; sub < 4; ++sub) {
-    const int b0 = blockIdx.y * 128 + sub * 32;
 #pragma unroll
-    for (int r = ty; r < 32; r += 8) {
-      const float v = V[(int64_t)(b0 + r) * ldv + j0 + tx];
-      const float s = (float)sqrt(fmax(rho * w[b0 + r], 0.0));
-      dot = fma((double)v, g[b0 + r], dot);
-      tile[r][tx] = v * s;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int r = ty; r < 32; r += 8) UT[(int64_t)(j0 + r) * ldt + b0 + tx] = tile[tx][r];
-    __syncthreads();
+  for (int u = 0; u < 16; ++u) {
+    const int r = ty + 8 * u;
+    dot = fma((double)v[u], sg[r], dot);
+    tile[r][tx] = v[u] * sw[r];
   }
   red[ty][tx] = dot;
   __syncthreads();
+  // U^T rows j0 .. j0+31, columns b0 .. b0+127: each warp writes 128 contiguous floats of one row per iteration
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int jr = ty + 8 * u;
+#pragma unroll
+    for (int sblk = 0; sblk < 4; ++sblk) UT[(int64_t)(j0 + jr) * ldt + b0 + tx + 32 * sblk] = tile[tx + 32 * sblk][jr];
+  }
   if (ty == 0) {
     double a = 0.0;
 #pragma unroll
