@@ -152,7 +152,11 @@ __device__ __forceinline__ float tf32_rna(float v) {
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 umma_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C,
                     int64_t ldc, int64_t c_split_stride, int total_kb, int kb_per_split, int tri_mode, const UmmaEpilogue ep) {
-  const int tile_n = blockIdx.x, tile_m = blockIdx.y, split = blockIdx.z;
+  // tri_mode 1: the k-extent grows with tile_n, so CTAs are numbered with the LONGEST tiles first (x = tile_m fastest,
+  // y = reversed tile_n) -- the short tiles then fill the second wave instead of trailing behind a long one
+  const int tile_n = (tri_mode == 1) ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.x;
+  const int tile_m = (tri_mode == 1) ? (int)blockIdx.x : (int)blockIdx.y;
+  const int split = blockIdx.z;
   if (tri_mode == 2 && tile_n < tile_m) return;
   int kb0 = split * kb_per_split;
   int kb1 = min(total_kb, kb0 + kb_per_split);
@@ -439,9 +443,9 @@ int umma_gemm_nt(std::string* err, UmmaLatent& u, int a_which, int b_which, floa
   Maps* mp = (Maps*)u.tmaps;
   if (M % BM || N % BN || u.m % BK) return fail(err, "shape not a multiple of the 128 x 128 x 32 tile");
   const int total_kb = u.m / BK;
-  dim3 grid(N / BN, M / BM, 1);
-  umma_gemm_nt_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mp->raw[a_which], mp->raw[b_which], C, (int64_t)u.ldm, 0, total_kb, total_kb,
-                                                             (b_which == UM_LINV || b_which == UM_X) ? 1 : 0, ep);
+  const int tri = (b_which == UM_LINV || b_which == UM_X) ? 1 : 0;
+  dim3 grid = tri ? dim3(M / BM, N / BN, 1) : dim3(N / BN, M / BM, 1);
+  umma_gemm_nt_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mp->raw[a_which], mp->raw[b_which], C, (int64_t)u.ldm, 0, total_kb, total_kb, tri, ep);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(err, "umma_gemm_nt_kernel", e);
   return 0;
