@@ -131,6 +131,7 @@ struct Engine : EngineBase {
     double *P = nullptr, *X = nullptr, *W = nullptr;  // tail workspaces [mp][mp]
     double* logdetP = nullptr;                        // device scalars: [0] logdet P_v, [1] scratch for K
     UmmaLatent um;                                    // tcgen05 path
+    UmmaKnm uk; bool knm_tc = false;                  // tcgen05 K_nm construction (D <= 128)
     int gram_splits = 1;                              // split-K partials of the last Gram product
   };
   std::vector<Latent> lat;
@@ -305,6 +306,10 @@ struct Engine : EngineBase {
       if (prec == AGP_PREC_TF32X3)
         CKS(umma_latent_alloc(ctx_err(), L.um, m, (int)ldm, Bcap, (const float*)(const void*)L.Knm, (const float*)(const void*)L.V,
                               (const float*)(const void*)L.Linv_T, (const float*)(const void*)L.Xv_T, st()));
+      if (prec == AGP_PREC_TF32X3 && umma_knm_shape_ok(m, Bcap, D) && !getenv("AGP_KNM_SIMT")) {
+        CKS(umma_knm_setup(ctx_err(), L.uk, (const float*)(const void*)L.Z, Dp, m, D, (float*)(void*)L.Knm, ldm, Bcap, st()));
+        L.knm_tc = true;
+      }
     }
     CKS(dalloc(&Xb, (size_t)Bcap * Dp)); CKS(dalloc(&xxb, Bcap));
     CKS(dalloc(&idx_cur, Bcap)); CKS(dalloc(&xx_cur, Bcap)); CKS(dalloc(&idx_prev, Bcap));
@@ -356,6 +361,7 @@ struct Engine : EngineBase {
                     L.muv, L.tvec, L.Xv, L.Dinv, L.Xv_T, L.Knm, L.V, L.VS, L.Ktilde, L.racc, L.Gpart, L.v1, L.P, L.X, L.W, L.logdetP};
       for (void* p : ps) cudaFree(p);
       umma_latent_free(L.um);
+      umma_knm_free(L.uk);
     }
     if (side) cudaStreamDestroy(side);
     if (ev_fork) cudaEventDestroy(ev_fork);
@@ -610,11 +616,16 @@ struct Engine : EngineBase {
       Latent& L = lat[q];
       if (stages & 1) {
         ph_begin(PH_KMAT);
+        if (L.knm_tc) {
+          CKS(umma_knm(ctx_err(), L.uk, (const float*)(const void*)Xsrc, Dp, Dp, gather, (const float*)(const void*)(gather ? xx_cur : xsrc),
+                       (const float*)(const void*)L.zz, B, L.kind, L.scale * L.scale, L.variance, st()));
+        } else {
         GemmParams<T> g{};
         g.A = Xsrc; g.lda = Dp; g.a_gather = gather; g.B = L.Z; g.ldb = Dp; g.C = L.Knm; g.ldc = ldm;
         g.M = B; g.N = m; g.K = D; g.alpha = 1.0;
         g.xx = gather ? xx_cur : xsrc; g.xx_direct = 1; g.zz = L.zz; g.scale2 = L.scale * L.scale; g.variance = L.variance; g.kernel_kind = L.kind;
         gemm_simt_launch<T, false, false, EPI_KERNELFN>(g, 1, st());
+        }
         ++launches;
         ph_end();
         if (prec == AGP_PREC_TF32X3) {

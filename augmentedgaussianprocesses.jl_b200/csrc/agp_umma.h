@@ -42,4 +42,20 @@ int umma_scale_transpose(std::string* err, UmmaLatent& u, const float* V, const 
 // Gpart[s] = sum_{b in split s} U_b U_b^T (full symmetric tiles) ; *n_split in: capacity, out: used
 int umma_gram(std::string* err, UmmaLatent& u, float* Gpart, int B, int m, int* n_split, cudaStream_t st);
 
+// ---- K_nm construction on the tensor core (agp_knm.cu) ----
+struct UmmaKnm {
+  int m = 0, D = 0, Kp = 0;                   // Kp = D rounded up to a multiple of 32
+  float *Zhi = nullptr, *Zlo = nullptr;       // TF32 hi / lo split of the inducing points [m][Kp]
+  void* maps = nullptr;                       // CUtensorMap: Zhi, Zlo (loads), Knm (store)
+  int force_groups = 0;                       // > 0: override the column split (tuning / microbenchmarks)
+};
+bool umma_knm_shape_ok(int m, int Bcap, int D);
+// (re)split Z and build the tensor maps (Knm: the engine's [Bcap][ldk] output buffer); call again whenever Z changes
+int umma_knm_setup(std::string* err, UmmaKnm& k, const float* Z, int64_t ldz, int m, int D, float* Knm, int64_t ldk, int Bcap,
+                   cudaStream_t st);
+void umma_knm_free(UmmaKnm& k);
+// Knm[b][j] = variance * base(scale2 * |x_b - z_j|^2) for B minibatch rows (gathered through `gather` when given)
+int umma_knm(std::string* err, UmmaKnm& k, const float* X, int64_t ldx, int Dp, const int64_t* gather, const float* xx, const float* zz,
+             int B, int kind, double scale2, double variance, cudaStream_t st);
+
 }  // namespace agp

@@ -252,3 +252,18 @@ def test_pipelined_pool_steps_match_host_list_steps(agp, precision):
         assert rel_fro(mu, mu_r) < tol and rel_fro(S, S_r) < tol, (graph, rel_fro(mu, mu_r), rel_fro(S, S_r))
         assert abs(agp.ELBO(mdl, st) - elbo_ref) < 1e-6 * abs(elbo_ref) + (0 if precision == "f64" else 1e-4 * abs(elbo_ref))
         assert mdl.counters() == (iters + 1, iters - 1)
+
+
+@pytest.mark.parametrize("D,kind", [(8, "sqexp"), (32, "sqexp"), (64, "matern32"), (100, "matern52"), (128, "sqexp")])
+def test_knm_tensor_core_kernel(agp, D, kind):
+    """K_nm construction on tcgen05 (agp_knm.cu: gathered rows -> TMEM, pre-split Z by TMA, 3xTF32, TMA store) against
+    the oracle's kernelmatrix (latentgp.jl:210) on the same gathered minibatch.  Tolerance: fp32 rounding of the
+    GEMM-form squared distance, |x|^2 + |z|^2 - 2 x.z ~ 2 D, scaled by 1/D in the exponent -> 2e-6 absolute on k in [0, var]."""
+    n, m, B = 2048, 256, 512
+    variance = 1.7
+    (mo, so), (me, se), _ = run_pair(agp, "gaussian", "tf32x3", n=n, D=D, m=m, B=B, iters=1, kind=kind, variance=variance, seed=5)
+    km = se.kernel_matrices(0)
+    ko = so["kernel_matrices"][0]
+    assert km["Knm"].shape == ko["Knm"].shape == (B, m)
+    assert np.max(np.abs(km["Knm"] - ko["Knm"])) < 4e-6 * variance
+    assert rel_fro(km["Knm"], ko["Knm"]) < 2e-6
