@@ -83,6 +83,7 @@ struct EngineBase {
   virtual int profile_enable(int on) = 0;
   virtual int profile_read(int maxp, const char** names, double* ms, int64_t* launches) = 0;
   virtual int64_t launch_count() = 0;
+  virtual int time_kernel(int which, int reps, double* ms) = 0;
   virtual int use_graph(int on) = 0;
 };
 
@@ -1110,6 +1111,64 @@ struct Engine : EngineBase {
     return PH_COUNT;
   }
   int64_t launch_count() override { return launches; }
+
+  // bench hook: one hot kernel, `reps` launches back to back between two events (see include/agp_b200.h)
+  int time_kernel(int which, int reps, double* ms_out) override {
+    if (!ms_out || reps < 1 || which < 0 || which > 3) BAD("bad time_kernel arguments");
+    if (!have_K || !have_data || !idx_pool || curB < 1 || pool_B != curB) { ctx->err = "time_kernel needs a completed resident-list step"; return AGP_ERR_STATE; }
+    if (prec != AGP_PREC_TF32X3) { ctx->err = "time_kernel measures the tcgen05 kernels (precision tf32x3)"; return AGP_ERR_STATE; }
+    const int B = curB;
+    Latent& L = lat[0];
+    CKS(sync_status());
+    int64_t c[2];
+    CK(cudaMemcpy(c, counters, 16, cudaMemcpyDeviceToHost));
+    T* xxr = nullptr;
+    if (which == 0) {
+      CKS(dalloc(&xxr, (size_t)reps * B));
+      for (int r = 0; r < reps; ++r)
+        xx_gather_kernel<T><<<(B + 255) / 256, 256, 0, st()>>>(idx_pool + ((c[1] + r) % n_lists) * B, B, xx, xxr + (size_t)r * B);
+    }
+    if (which == 3) CKS(umma_scale_transpose(ctx_err(), L.um, (const float*)(const void*)L.V, gS, 1.0, gmu, L.v1, B, m, st()));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaStreamSynchronize(st()));
+    CK(cudaEventRecord(e0, st()));
+    int rc = AGP_OK;
+    for (int r = 0; r < reps && rc == AGP_OK; ++r) {
+      if (which == 0) {
+        if (L.knm_tc)
+          rc = umma_knm(ctx_err(), L.uk, (const float*)(const void*)X, Dp, Dp, idx_pool + ((c[1] + r) % n_lists) * B,
+                        (const float*)(const void*)(xxr + (size_t)r * B), (const float*)(const void*)L.zz, B, L.kind, L.scale * L.scale, L.variance, st());
+        else { ctx->err = "K_nm tensor-core kernel not active (D > 128)"; rc = AGP_ERR_STATE; }
+      } else if (which == 1 || which == 2) {
+        UmmaEpilogue ep{};
+        ep.mode = which == 1 ? UMMA_EPI_STORE_SUMSQ : UMMA_EPI_STATS_ONLY;
+        ep.acc0 = L.racc + (which == 1 ? 0 : ldB); ep.acc1 = L.racc + 2 * ldB; ep.tvec = L.tvec;
+        rc = umma_gemm_nt(ctx_err(), L.um, which == 1 ? UM_KNM : UM_V, which == 1 ? UM_LINV : UM_X, (float*)(void*)(which == 1 ? L.V : L.VS), B, m, ep, st());
+      } else {
+        int ns = n_split;
+        rc = umma_gram(ctx_err(), L.um, (float*)(void*)L.Gpart, B, m, &ns, st());
+      }
+      ++launches;
+    }
+    CK(cudaEventRecord(e1, st()));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(xxr);
+    *ms_out = (double)ms / reps;
+    // Knm / V / accumulators now hold scratch values: re-prime the pipeline before the next step / ELBO
+    kernel_matrices_stale = true;
+    if (prefetched) {  // fall back to the last consumed minibatch (same as predict_f)
+      prefetched = false;
+      cudaMemcpyAsync(idx_cur, idx_prev, (size_t)curB * 8, cudaMemcpyDeviceToDevice, st());
+      xx_gather_kernel<T><<<(curB + 255) / 256, 256, 0, st()>>>(idx_cur, curB, xx, xx_cur);
+      ++launches;
+    }
+    drop_graph();
+    return rc;
+  }
   int use_graph(int on) override { want_graph = on != 0; if (!on) drop_graph(); return AGP_OK; }
 };
 
@@ -1271,6 +1330,7 @@ int agp_profile_enable(agp_model* model, int on) { ENG(model); return e->profile
 int agp_profile_read(agp_model* model, int32_t maxp, const char** names, double* ms, int64_t* launches) {
   ENG(model); return e->profile_read(maxp, names, ms, launches);
 }
+int agp_time_kernel(agp_model* model, int32_t which, int32_t reps, double* ms) { ENG(model); return e->time_kernel(which, reps, ms); }
 int64_t agp_launch_count(agp_model* model) { return (model && model->eng) ? model->eng->launch_count() : 0; }
 int agp_use_graph(agp_model* model, int on) { ENG(model); return e->use_graph(on); }
 

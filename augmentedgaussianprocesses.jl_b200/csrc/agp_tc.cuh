@@ -103,12 +103,12 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                      \
       : "r"(taddr))
 
-// round-to-nearest fp32 -> tf32 (the tensor core would otherwise truncate the low 13 mantissa bits)
-__device__ __forceinline__ float tf32_rna(float v) {
-  uint32_t t;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v));
-  return __uint_as_float(t);
-}
+// round-to-nearest (ties away from zero) fp32 -> tf32; the tensor core would otherwise truncate the low 13 mantissa
+// bits.  Same result as cvt.rna.tf32.f32 for finite inputs, but as two full-rate integer ops: on sm_100a the cvt goes
+// through the quarter-rate conversion pipe and made the in-kernel hi/lo split the bottleneck of the 3xTF32 GEMMs
+// (1 us per 32-wide k-block vs the 0.4 us MMA floor).  fp32 is sign-magnitude, so adding half a tf32 ulp to the bit
+// pattern rounds the magnitude; a carry into the exponent is the correct rounding to the next binade.
+__device__ __forceinline__ float tf32_rna(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) @4, a/b format TF32 (2) @7/@10,
 // a/b K-major (0) @15/@16, n_dim = N>>3 @17, m_dim = M>>4 @24

@@ -24,6 +24,7 @@
 #include <stdint.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace agp {
@@ -39,31 +40,52 @@ constexpr int CONV_BYTES = 2 * TILE_BYTES;     // B_hi, B_lo   (A_hi / A_lo live
 constexpr int RING_BYTES = RS * RAW_BYTES + CS * CONV_BYTES;
 constexpr int NUM_CONV_THREADS = 128;
 constexpr int SMEM_BYTES = RING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int TMEM_COLS = 256;     // [0,128) fp32 accumulator, then per converted slot 32 columns A_hi + 32 columns A_lo
-constexpr int TMEM_A0 = 128;
-constexpr int NUM_CONV_GROUPS = 2;   // converter groups (4 warps each) alternate k-blocks
+constexpr int TMEM_COLS = 512;     // two fp32 accumulators [0,128) [128,256), then per converted slot 32 columns A_hi + 32 columns A_lo
+constexpr int TMEM_A0 = 256;
+constexpr int NUM_CONV_GROUPS = 2;   // worker groups (4 warps each): group g converts AND drains the CTA's tiles lt = g (mod 2)
 constexpr int NUM_THREADS = 64 + NUM_CONV_GROUPS * 128;
 
 using namespace tc;
 constexpr uint32_t kIdesc = make_idesc_tf32(BM, BN);
 
+// Work decomposition of one launch.  A work unit = one 128 x 128 output tile (x one split-K slice).
+//   tri_mode 0: all tiles | 1: B operand lower-triangular (B[n][k] = 0 for k > n): the k-extent stops at the tile's last
+//   column, units are ordered longest first | 2: symmetric output, only tiles with tile_n >= tile_m (x splits)
+struct GemmWork {
+  int ntm, ntn, nsplit, total;     // tiles along M, N, split-K slices, number of units
+  int total_kb, kb_per_split, tri_mode;
+};
+struct WorkUnit { int tile_m, tile_n, split, kb0, nkb; };
 
-// tri_mode: 0 none | 1 B operand lower-triangular (B[n][k] = 0 for k > n): stop at the tile's last column
-//           | 2 symmetric output: only tiles with tile_n >= tile_m
+__device__ __forceinline__ WorkUnit get_unit(const GemmWork& w, int u) {
+  WorkUnit r;
+  if (w.tri_mode == 2) {
+    r.split = u % w.nsplit;
+    int p = u / w.nsplit;                      // p-th upper tile, row-major over (tile_m <= tile_n)
+    int tm = 0;
+    while (p >= w.ntn - tm) { p -= w.ntn - tm; ++tm; }
+    r.tile_m = tm; r.tile_n = tm + p;
+  } else if (w.tri_mode == 1) {
+    r.split = 0;
+    r.tile_n = w.ntn - 1 - u / w.ntm;          // longest k-extent first
+    r.tile_m = u % w.ntm;
+  } else {
+    r.split = 0;
+    r.tile_m = u / w.ntn; r.tile_n = u % w.ntn;
+  }
+  r.kb0 = r.split * w.kb_per_split;
+  int kb1 = min(w.total_kb, r.kb0 + w.kb_per_split);
+  if (w.tri_mode == 1) kb1 = min(kb1, (r.tile_n * BN + BN) / BK);
+  r.nkb = max(kb1 - r.kb0, 0);
+  return r;
+}
+// persistent CTAs take units in "snake" order (round r: CTA c takes r*G + c, or r*G + G-1-c on odd rounds), which pairs
+// long units with short ones when the list is sorted by length
+__device__ __forceinline__ int unit_index(int round, int cta, int G) { return round * G + ((round & 1) ? (G - 1 - cta) : cta); }
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 umma_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C,
-                    int64_t ldc, int64_t c_split_stride, int total_kb, int kb_per_split, int tri_mode, const UmmaEpilogue ep) {
-  // tri_mode 1: the k-extent grows with tile_n, so CTAs are numbered with the LONGEST tiles first (x = tile_m fastest,
-  // y = reversed tile_n) -- the short tiles then fill the second wave instead of trailing behind a long one
-  const int tile_n = (tri_mode == 1) ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.x;
-  const int tile_m = (tri_mode == 1) ? (int)blockIdx.x : (int)blockIdx.y;
-  const int split = blockIdx.z;
-  if (tri_mode == 2 && tile_n < tile_m) return;
-  int kb0 = split * kb_per_split;
-  int kb1 = min(total_kb, kb0 + kb_per_split);
-  if (tri_mode == 1) kb1 = min(kb1, (tile_n * BN + BN) / BK);
-  const int nkb = max(kb1 - kb0, 0);
-
+                    int64_t ldc, int64_t c_split_stride, const GemmWork work, const UmmaEpilogue ep) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -72,17 +94,20 @@ umma_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   auto raw_empty = [&](int s) { return bars + 8u * (RS + s); };
   auto conv_full = [&](int s) { return bars + 8u * (2 * RS + s); };
   auto mma_done = [&](int s) { return bars + 8u * (2 * RS + CS + s); };
-  const uint32_t tmem_full_bar = bars + 8u * (2 * RS + 2 * CS);
-  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + RING_BYTES + 8 * (2 * RS + 2 * CS + 1));
+  auto tmem_full = [&](int b) { return bars + 8u * (2 * RS + 2 * CS + b); };
+  auto tmem_empty = [&](int b) { return bars + 8u * (2 * RS + 2 * CS + 2 + b); };
+  auto unit_conv_done = [&](int b) { return bars + 8u * (2 * RS + 2 * CS + 4 + b); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + RING_BYTES + 8 * (2 * RS + 2 * CS + 6));
   const uint32_t conv_base = smem_base + RS * RAW_BYTES;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = gridDim.x, cta = blockIdx.x;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
     for (int s = 0; s < RS; ++s) { mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), NUM_CONV_THREADS); }
     for (int s = 0; s < CS; ++s) { mbar_init(conv_full(s), NUM_CONV_THREADS); mbar_init(mma_done(s), 1); }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(tmem_full(b), 1); mbar_init(tmem_empty(b), 4); mbar_init(unit_conv_done(b), NUM_CONV_THREADS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -96,130 +121,163 @@ umma_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == 0) {
     if (lane == 0) {
-      // ===== TMA producer: raw fp32 tiles =====
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % RS;
-        mbar_wait(raw_empty(s), ((i / RS) & 1) ^ 1);
-        const uint32_t dst = smem_base + s * RAW_BYTES;
-        mbar_expect_tx(raw_full(s), 2 * TILE_BYTES);
-        const int k = (kb0 + i) * BK;
-        tma_load_2d(dst + 0 * TILE_BYTES, &tmA, raw_full(s), k, tile_m * BM);
-        tma_load_2d(dst + 1 * TILE_BYTES, &tmB, raw_full(s), k, tile_n * BN);
+      // ===== TMA producer: raw fp32 tiles, one ring across all units of this CTA =====
+      int g = 0;
+      for (int r = 0;; ++r) {
+        const int u = unit_index(r, cta, G);
+        if (u >= work.total) break;
+        const WorkUnit wu = get_unit(work, u);
+        for (int i = 0; i < wu.nkb; ++i, ++g) {
+          const int s = g % RS;
+          mbar_wait(raw_empty(s), ((g / RS) & 1) ^ 1);
+          const uint32_t dst = smem_base + s * RAW_BYTES;
+          mbar_expect_tx(raw_full(s), 2 * TILE_BYTES);
+          const int k = (wu.kb0 + i) * BK;
+          tma_load_2d(dst + 0 * TILE_BYTES, &tmA, raw_full(s), k, wu.tile_m * BM);
+          tma_load_2d(dst + 1 * TILE_BYTES, &tmB, raw_full(s), k, wu.tile_n * BN);
+        }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    for (int i = 0; i < nkb; ++i) {
-      const int s = i % CS;
-      mbar_wait(conv_full(s), (i / CS) & 1);
+    // ===== MMA issuer: accumulator buffer lt & 1, so the epilogue of unit lt overlaps the main loop of unit lt + 1 =====
+    int g = 0, lt = 0;
+    for (int r = 0;; ++r, ++lt) {
+      const int u = unit_index(r, cta, G);
+      if (u >= work.total) break;
+      const WorkUnit wu = get_unit(work, u);
+      const int ab = lt & 1;
+      mbar_wait(tmem_empty(ab), ((lt >> 1) & 1) ^ 1);      // the epilogue two units ago has drained this accumulator
       tc_fence_after();
-      if (elect_one()) {
-        const uint32_t b_hi = conv_base + s * CONV_BYTES, b_lo = b_hi + TILE_BYTES;
-        const uint32_t a_hi = tmem_base + TMEM_A0 + s * 64, a_lo = a_hi + 32;
+      const uint32_t acc = tmem_base + ab * BN;
+      for (int i = 0; i < wu.nkb; ++i, ++g) {
+        const int s = g % CS;
+        mbar_wait(conv_full(s), (g / CS) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t b_hi = conv_base + s * CONV_BYTES, b_lo = b_hi + TILE_BYTES;
+          const uint32_t a_hi = tmem_base + TMEM_A0 + s * 64, a_lo = a_hi + 32;
 #pragma unroll
-        for (int kk = 0; kk < BK / 8; ++kk) {
-          const uint32_t off = kk * 32;  // 8 tf32 = 32 bytes along K inside the 128B swizzle atom (B); 8 TMEM columns (A)
-          const uint64_t dbh = make_desc(b_hi + off), dbl = make_desc(b_lo + off);
-          tc_mma_tf32_ts(tmem_base, a_lo + kk * 8, dbh, kIdesc, (i > 0 || kk > 0) ? 1u : 0u);  // small terms first
-          tc_mma_tf32_ts(tmem_base, a_hi + kk * 8, dbl, kIdesc, 1u);
-          tc_mma_tf32_ts(tmem_base, a_hi + kk * 8, dbh, kIdesc, 1u);
+          for (int kk = 0; kk < BK / 8; ++kk) {
+            const uint32_t off = kk * 32;  // 8 tf32 = 32 bytes along K inside the 128B swizzle atom (B); 8 TMEM columns (A)
+            const uint64_t dbh = make_desc(b_hi + off), dbl = make_desc(b_lo + off);
+            tc_mma_tf32_ts(acc, a_lo + kk * 8, dbh, kIdesc, (i > 0 || kk > 0) ? 1u : 0u);  // small terms first
+            tc_mma_tf32_ts(acc, a_hi + kk * 8, dbl, kIdesc, 1u);
+            tc_mma_tf32_ts(acc, a_hi + kk * 8, dbh, kIdesc, 1u);
+          }
+          tc_commit(mma_done(s));                          // frees B_hi/B_lo and the TMEM A columns of this slot
+          if (i == wu.nkb - 1) tc_commit(tmem_full(ab));   // accumulator complete
         }
-        tc_commit(mma_done(s));                        // frees B_hi/B_lo and the TMEM A columns of this stage
-        if (i == nkb - 1) tc_commit(tmem_full_bar);    // accumulator complete
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
-    // ===== converters (raw -> hi / lo), then epilogue: warps 2..5 =====
-    const int grp = (warp - 2) >> 2;                 // converter group: handles k-blocks i = grp (mod NUM_CONV_GROUPS)
+    // ===== worker groups: raw -> hi / lo conversion of the group's units, then their epilogue =====
+    const int grp = (warp - 2) >> 2;
     const int ct = (threadIdx.x - 64) & 127;         // 0..127 within the group
     const int q = warp & 3;                          // TMEM lane quarter this warp may access
-    const int arow = q * 32 + lane;   // A-tile row = TMEM lane handled by this thread
-    for (int i = grp; i < nkb; i += NUM_CONV_GROUPS) {
-      const int rs = i % RS, s = i % CS;
-      mbar_wait(raw_full(rs), (i / RS) & 1);               // TMA landed the raw tiles
-      mbar_wait(mma_done(s), ((i / CS) & 1) ^ 1);          // previous MMAs on this slot's converted operands retired
-      tc_fence_after();
-      uint8_t* base = smem_gen + rs * RAW_BYTES;
-      uint8_t* cbase_s = smem_gen + RS * RAW_BYTES + s * CONV_BYTES;
-      {
-        // A: row `arow` of the raw tile (128 B, 16-byte chunks XOR-swizzled with row & 7) -> hi / lo -> TMEM
-        const float4* rowp = reinterpret_cast<const float4*>(base + arow * 128);
-        uint32_t h[32], l[32];
+    const int arow = q * 32 + lane;                  // A-tile row = TMEM lane handled by this thread
+    int g = 0, lt = 0;
+    for (int r = 0;; ++r, ++lt) {
+      const int u = unit_index(r, cta, G);
+      if (u >= work.total) break;
+      const WorkUnit wu = get_unit(work, u);
+      if ((lt & 1) != grp) { g += wu.nkb; continue; }
+      // A group only sees the mbarrier phases of its own units.  Parity waits are unambiguous only within one phase, so
+      // do not start before the other group has issued every conversion of the previous unit (the TMA ring and the MMA
+      // warp are then at most one phase behind on every barrier this group is about to wait on).
+      if (lt > 0) mbar_wait(unit_conv_done(grp ^ 1), ((lt - 1) >> 1) & 1);
+      for (int i = 0; i < wu.nkb; ++i, ++g) {
+        const int rs = g % RS, s = g % CS;
+        mbar_wait(raw_full(rs), (g / RS) & 1);               // TMA landed the raw tiles
+        mbar_wait(mma_done(s), ((g / CS) & 1) ^ 1);          // previous MMAs on this slot's converted operands retired
+        tc_fence_after();
+        uint8_t* base = smem_gen + rs * RAW_BYTES;
+        uint8_t* cbase_s = smem_gen + RS * RAW_BYTES + s * CONV_BYTES;
+        {
+          // A: row `arow` of the raw tile (128 B, 16-byte chunks XOR-swizzled with row & 7) -> hi / lo -> TMEM
+          const float4* rowp = reinterpret_cast<const float4*>(base + arow * 128);
+          uint32_t h[32], l[32];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 v = rowp[c ^ (arow & 7)];
-          float t;
-          t = tf32_rna(v.x); h[4 * c + 0] = __float_as_uint(t); l[4 * c + 0] = __float_as_uint(tf32_rna(v.x - t));
-          t = tf32_rna(v.y); h[4 * c + 1] = __float_as_uint(t); l[4 * c + 1] = __float_as_uint(tf32_rna(v.y - t));
-          t = tf32_rna(v.z); h[4 * c + 2] = __float_as_uint(t); l[4 * c + 2] = __float_as_uint(tf32_rna(v.z - t));
-          t = tf32_rna(v.w); h[4 * c + 3] = __float_as_uint(t); l[4 * c + 3] = __float_as_uint(tf32_rna(v.w - t));
+          for (int c = 0; c < 8; ++c) {
+            const float4 v = rowp[c ^ (arow & 7)];
+            float t;
+            t = tf32_rna(v.x); h[4 * c + 0] = __float_as_uint(t); l[4 * c + 0] = __float_as_uint(tf32_rna(v.x - t));
+            t = tf32_rna(v.y); h[4 * c + 1] = __float_as_uint(t); l[4 * c + 1] = __float_as_uint(tf32_rna(v.y - t));
+            t = tf32_rna(v.z); h[4 * c + 2] = __float_as_uint(t); l[4 * c + 2] = __float_as_uint(tf32_rna(v.z - t));
+            t = tf32_rna(v.w); h[4 * c + 3] = __float_as_uint(t); l[4 * c + 3] = __float_as_uint(tf32_rna(v.w - t));
+          }
+          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + TMEM_A0 + s * 64;
+          TMEM_ST32(ta, h);
+          TMEM_ST32(ta + 32, l);
         }
-        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + TMEM_A0 + s * 64;
-        TMEM_ST32(ta, h);
-        TMEM_ST32(ta + 32, l);
-      }
-      {
-        // B: raw -> hi / lo tiles at the same (swizzled) offsets in shared memory
-        const float4* raw = reinterpret_cast<const float4*>(base + 1 * TILE_BYTES);
-        float4* hi = reinterpret_cast<float4*>(cbase_s);
-        float4* lo = reinterpret_cast<float4*>(cbase_s + TILE_BYTES);
+        {
+          // B: raw -> hi / lo tiles at the same (swizzled) offsets in shared memory
+          const float4* raw = reinterpret_cast<const float4*>(base + 1 * TILE_BYTES);
+          float4* hi = reinterpret_cast<float4*>(cbase_s);
+          float4* lo = reinterpret_cast<float4*>(cbase_s + TILE_BYTES);
 #pragma unroll
-        for (int u = 0; u < TILE_BYTES / 16 / NUM_CONV_THREADS; ++u) {
-          const int e = ct + u * NUM_CONV_THREADS;
-          const float4 v = raw[e];
-          float4 h, l;
-          h.x = tf32_rna(v.x); l.x = tf32_rna(v.x - h.x);
-          h.y = tf32_rna(v.y); l.y = tf32_rna(v.y - h.y);
-          h.z = tf32_rna(v.z); l.z = tf32_rna(v.z - h.z);
-          h.w = tf32_rna(v.w); l.w = tf32_rna(v.w - h.w);
-          hi[e] = h; lo[e] = l;
-        }
-      }
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      tc_fence_before();
-      fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      mbar_arrive(raw_empty(rs));   // the raw tiles may be overwritten by the next TMA
-      mbar_arrive(conv_full(s));    // operands ready for the MMA warp
-    }
-    const int row = tile_m * BM + q * 32 + lane;
-    float* cbase = C + (int64_t)split * c_split_stride;
-    float* crow = cbase + (int64_t)row * ldc + (int64_t)tile_n * BN;
-    double acc_sq = 0.0, acc_dot = 0.0;   // fused row statistics (fp64 sums, like rowstats_kernel)
-    if (nkb > 0) {
-      mbar_wait(tmem_full_bar, 0);
-      tc_fence_after();
-#pragma unroll 1
-      for (int c = grp; c < BN / 32; c += NUM_CONV_GROUPS) {
-        uint32_t r[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
-        TMEM_LD32(taddr, r);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (ep.mode != UMMA_EPI_STATS_ONLY) {
-          float4* dst = reinterpret_cast<float4*>(crow + c * 32);
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-        }
-        if (ep.mode == UMMA_EPI_STORE_SUMSQ || ep.mode == UMMA_EPI_STATS_ONLY) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const double v = (double)__uint_as_float(r[j]);
-            acc_sq = fma(v, v, acc_sq);
-            if (ep.mode == UMMA_EPI_STATS_ONLY) acc_dot = fma(v, ep.tvec[tile_n * BN + c * 32 + j], acc_dot);
+          for (int uu = 0; uu < TILE_BYTES / 16 / NUM_CONV_THREADS; ++uu) {
+            const int e = ct + uu * NUM_CONV_THREADS;
+            const float4 v = raw[e];
+            float4 h, l;
+            h.x = tf32_rna(v.x); l.x = tf32_rna(v.x - h.x);
+            h.y = tf32_rna(v.y); l.y = tf32_rna(v.y - h.y);
+            h.z = tf32_rna(v.z); l.z = tf32_rna(v.z - h.z);
+            h.w = tf32_rna(v.w); l.w = tf32_rna(v.w - h.w);
+            hi[e] = h; lo[e] = l;
           }
         }
-        if (ep.mode == UMMA_EPI_STORE_MIRROR && tile_n != tile_m) {
-          // symmetric product: also write the transposed tile (lanes = consecutive addresses)
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            cbase[(int64_t)(tile_n * BN + c * 32 + j) * ldc + row] = __uint_as_float(r[j]);
-        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        mbar_arrive(raw_empty(rs));   // the raw tiles may be overwritten by the next TMA
+        mbar_arrive(conv_full(s));    // operands ready for the MMA warp
       }
-      if (ep.mode == UMMA_EPI_STORE_SUMSQ) atomicAdd(ep.acc0 + row, acc_sq);
-      if (ep.mode == UMMA_EPI_STATS_ONLY) { atomicAdd(ep.acc0 + row, acc_sq); atomicAdd(ep.acc1 + row, acc_dot); }
-    } else if (ep.mode != UMMA_EPI_STATS_ONLY && grp == 0) {
-      for (int c = 0; c < BN / 4; ++c) reinterpret_cast<float4*>(crow)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      mbar_arrive(unit_conv_done(grp));
+      // ----- epilogue of this unit (the other group is already converting the next one) -----
+      const int ab = lt & 1;
+      const int row = wu.tile_m * BM + q * 32 + lane;
+      float* cbase = C + (int64_t)wu.split * c_split_stride;
+      float* crow = cbase + (int64_t)row * ldc + (int64_t)wu.tile_n * BN;
+      double acc_sq = 0.0, acc_dot = 0.0;   // fused row statistics (fp64 sums, like rowstats_kernel)
+      if (wu.nkb > 0) {
+        mbar_wait(tmem_full(ab), (lt >> 1) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t rr[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + c * 32);
+          TMEM_LD32(taddr, rr);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (c == BN / 32 - 1) {                            // accumulator drained: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty(ab));
+          }
+          if (ep.mode != UMMA_EPI_STATS_ONLY) {
+            float4* dst = reinterpret_cast<float4*>(crow + c * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              dst[j] = make_float4(__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1]), __uint_as_float(rr[4 * j + 2]), __uint_as_float(rr[4 * j + 3]));
+          }
+          if (ep.mode == UMMA_EPI_STORE_SUMSQ || ep.mode == UMMA_EPI_STATS_ONLY) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const double v = (double)__uint_as_float(rr[j]);
+              acc_sq = fma(v, v, acc_sq);
+              if (ep.mode == UMMA_EPI_STATS_ONLY) acc_dot = fma(v, ep.tvec[wu.tile_n * BN + c * 32 + j], acc_dot);
+            }
+          }
+          if (ep.mode == UMMA_EPI_STORE_MIRROR && wu.tile_n != wu.tile_m) {
+            // symmetric product: also write the transposed tile (lanes = consecutive addresses)
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              cbase[(int64_t)(wu.tile_n * BN + c * 32 + j) * ldc + row] = __uint_as_float(rr[j]);
+          }
+        }
+        if (ep.mode == UMMA_EPI_STORE_SUMSQ) atomicAdd(ep.acc0 + row, acc_sq);
+        if (ep.mode == UMMA_EPI_STATS_ONLY) { atomicAdd(ep.acc0 + row, acc_sq); atomicAdd(ep.acc1 + row, acc_dot); }
+      }
     }
   }
   tc_fence_before();
@@ -339,14 +397,27 @@ void umma_latent_free(UmmaLatent& u) {
   u.tmaps = nullptr;
 }
 
+static int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
+    if (const char* e = getenv("AGP_GEMM_GRID")) { int v = atoi(e); if (v > 0 && v < n) n = v; }   // tuning / experiments
+  }
+  return n;
+}
+
 int umma_gemm_nt(std::string* err, UmmaLatent& u, int a_which, int b_which, float* C, int M, int N, const UmmaEpilogue& ep,
                  cudaStream_t st) {
   Maps* mp = (Maps*)u.tmaps;
   if (M % BM || N % BN || u.m % BK) return fail(err, "shape not a multiple of the 128 x 128 x 32 tile");
-  const int total_kb = u.m / BK;
-  const int tri = (b_which == UM_LINV || b_which == UM_X) ? 1 : 0;
-  dim3 grid = tri ? dim3(M / BM, N / BN, 1) : dim3(N / BN, M / BM, 1);
-  umma_gemm_nt_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mp->raw[a_which], mp->raw[b_which], C, (int64_t)u.ldm, 0, total_kb, total_kb, tri, ep);
+  GemmWork w{};
+  w.ntm = M / BM; w.ntn = N / BN; w.nsplit = 1; w.total = w.ntm * w.ntn;
+  w.total_kb = u.m / BK; w.kb_per_split = w.total_kb;
+  w.tri_mode = (b_which == UM_LINV || b_which == UM_X) ? 1 : 0;
+  const int grid = w.total < sm_count() ? w.total : sm_count();
+  umma_gemm_nt_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mp->raw[a_which], mp->raw[b_which], C, (int64_t)u.ldm, 0, w, ep);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(err, "umma_gemm_nt_kernel", e);
   return 0;
@@ -366,16 +437,19 @@ int umma_gram(std::string* err, UmmaLatent& u, float* Gpart, int B, int m, int* 
   if (B % BM || m % BN) return fail(err, "shape not a multiple of the tile");
   const int total_kb = B / BK;
   const int nt = m / BN, upper_tiles = nt * (nt + 1) / 2;
-  int S = (148 + upper_tiles - 1) / upper_tiles;
+  int S = 148 / upper_tiles;     // one wave: tiles x splits <= SM count (a few CTAs spilling into a second wave doubled the time)
   S = S < 1 ? 1 : S;
   if (S > *n_split) S = *n_split;
   if (S > total_kb) S = total_kb;
   int per = (total_kb + S - 1) / S;
   S = (total_kb + per - 1) / per;
-  dim3 grid(nt, nt, S);
+  GemmWork w{};
+  w.ntm = nt; w.ntn = nt; w.nsplit = S; w.total = upper_tiles * S;
+  w.total_kb = total_kb; w.kb_per_split = per; w.tri_mode = 2;
+  const int grid = w.total < sm_count() ? w.total : sm_count();
   UmmaEpilogue ep{};
   ep.mode = UMMA_EPI_STORE_MIRROR;
-  umma_gemm_nt_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mp->ut, mp->ut, Gpart, (int64_t)u.ldm, (int64_t)m * u.ldm, total_kb, per, 2, ep);
+  umma_gemm_nt_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mp->ut, mp->ut, Gpart, (int64_t)u.ldm, (int64_t)m * u.ldm, w, ep);
   *n_split = S;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(err, "umma gram", e);

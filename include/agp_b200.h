@@ -194,6 +194,12 @@ int agp_profile_enable(agp_model* model, int on);
 int agp_profile_read(agp_model* model, int32_t max_phases, const char** names, double* ms, int64_t* launches);
 /* kernels launched by this model since creation (the `gpu_launches` claim of bench.py). */
 int64_t agp_launch_count(agp_model* model);
+/* measurement hook for the roofline lines of bench.py: `reps` back-to-back launches of ONE hot kernel of the step on
+ * the model's stream between two CUDA events (so the event overhead is amortised), on latent 0 with the resident
+ * minibatch lists; *ms_per_launch = elapsed / reps.  which: 0 = K_nm construction (a new minibatch per launch),
+ * 1 = V = K_nm L^-T, 2 = V X^T (+ row statistics), 3 = Gram product U^T U.  Needs a completed resident-list step
+ * (AGP_ERR_STATE otherwise).  Does not change the posterior; the step pipeline is re-primed afterwards. */
+int agp_time_kernel(agp_model* model, int32_t which, int32_t reps, double* ms_per_launch);
 /* capture the step into a CUDA graph and replay it on later agp_step*(idx == NULL) calls. */
 int agp_use_graph(agp_model* model, int on);
 
