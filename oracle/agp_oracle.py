@@ -174,6 +174,69 @@ class StudentTLikelihood:
 
 
 @dataclass
+class LaplaceLikelihood:
+    """likelihood/laplace.jl:17-28 : fields beta, a = beta^-2, p = 0.5"""
+
+    beta: float = 1.0
+    n_latent: int = 1
+    name: str = "laplace"
+
+    @property
+    def a(self):
+        return self.beta**-2
+
+    p = 0.5
+
+
+@dataclass
+class BayesianSVM:
+    """likelihood/bayesiansvm.jl:19 : BernoulliLikelihood(SVMLink())"""
+
+    n_latent: int = 1
+    name: str = "bayesiansvm"
+
+
+@dataclass
+class PoissonLikelihood:
+    """likelihood/poisson.jl:16-26 : ScaledLogistic link, lambda is STATE (re-estimated by local_updates!, :75)"""
+
+    lam: float = 1.0
+    n_latent: int = 1
+    name: str = "poisson"
+
+
+@dataclass
+class NegBinomialLikelihood:
+    """likelihood/negativebinomial.jl:22-27"""
+
+    r: float = 10
+    n_latent: int = 1
+    name: str = "negbinomial"
+
+
+@dataclass
+class HeteroscedasticLikelihood:
+    """likelihood/heteroscedastic.jl:17-25, :48 (n_latent = 2: f and the noise GP g); lambda is STATE (:78)"""
+
+    lam: float = 1.0
+    n_latent: int = 2
+    name: str = "heteroscedastic"
+
+
+def gausshermite100():
+    """training/predictions.jl:4 : nodes * sqrt2, weights / sqrt(pi) of the 100-point Gauss-Hermite rule"""
+    x, w = np.polynomial.hermite.hermgauss(100)
+    return x * math.sqrt(2.0), w / math.sqrt(math.pi)
+
+
+def expectation(f, mu, var):
+    """functions/utils.jl:16-19 (vectorised over samples)"""
+    x, w = gausshermite100()
+    pts = x[None, :] * np.sqrt(np.maximum(var, 0.0))[:, None] + mu[:, None]
+    return f(pts) @ w
+
+
+@dataclass
 class LogisticSoftMaxLikelihood:
     """likelihood/logisticsoftmax.jl:23 + multiclass.jl:1-24"""
 
@@ -227,7 +290,12 @@ def create_one_hot(l: LogisticSoftMaxLikelihood, y):
 
 def treat_labels(y, lik):
     """classification.jl:29-39, multiclass.jl:40-44, regression.jl:10-15"""
-    if lik.name == "logistic":
+    if lik.name in ("poisson", "negbinomial"):  # event.jl:7-13
+        y = np.asarray(y)
+        if not np.issubdtype(y.dtype, np.integer):
+            raise ValueError("For event count target(s) should be integers")
+        return y.astype(np.float64)
+    if lik.name in ("logistic", "bayesiansvm"):
         y = np.asarray(y)
         labels = sorted(int(v) for v in np.unique(y))
         if labels == [0, 1]:
@@ -251,6 +319,14 @@ def init_local_vars(lik, B):
         return dict(c=np.zeros(B), theta=np.zeros(B))
     if lik.name == "gaussian":
         return dict(theta=np.full(B, 1.0 / lik.sigma2))
+    if lik.name in ("bayesiansvm", "negbinomial"):  # classification.jl:10-12, negativebinomial.jl:65-67
+        return dict(c=np.zeros(B), theta=np.zeros(B))
+    if lik.name == "laplace":  # laplace.jl:57-59
+        return dict(b=np.zeros(B), theta=np.zeros(B))
+    if lik.name == "poisson":  # poisson.jl:61-63
+        return dict(c=np.zeros(B), theta=np.zeros(B), gamma=np.zeros(B))
+    if lik.name == "heteroscedastic":  # heteroscedastic.jl:50-62
+        return dict(c=np.ones(B), phi=np.ones(B), gamma=np.ones(B), theta=np.ones(B), sigma_g=np.ones(B))
     if lik.name == "logisticsoftmax":
         K = lik.n_class
         return dict(
@@ -274,6 +350,29 @@ def local_updates(lv, lik, y, mu, var):
         lv["theta"] = lik.alpha / lv["c"]
     elif lik.name == "gaussian":  # gaussian.jl:56-72 (opt_noise = nothing)
         lv["theta"] = np.full(mu.shape[1], 1.0 / lik.sigma2)
+    elif lik.name == "laplace":  # laplace.jl:61-74
+        lv["b"] = np.sqrt(np.abs(mu[0] - y) ** 2 + var[0])
+        lv["theta"] = math.sqrt(lik.a) / lv["b"]
+    elif lik.name == "bayesiansvm":  # bayesiansvm.jl:40-52  (c holds E[(1 - y f)^2], NOT its square root)
+        lv["c"] = np.abs(1.0 - y * mu[0]) ** 2 + var[0]
+        lv["theta"] = 1.0 / np.sqrt(lv["c"])
+    elif lik.name == "negbinomial":  # negativebinomial.jl:69-81
+        lv["c"] = sqrt_expec_square(mu[0], var[0])
+        lv["theta"] = (lik.r + y) * np.tanh(lv["c"] / 2.0) / lv["c"]
+    elif lik.name == "poisson":  # poisson.jl:65-82 ; lambda re-estimated AFTER the local variables used the old one
+        lam = lik.lam
+        lv["c"] = sqrt_expec_square(mu[0], var[0])
+        lv["gamma"] = lam * safe_expcosh(-mu[0] / 2.0, lv["c"] / 2.0) / 2.0
+        lv["theta"] = (y + lv["gamma"]) / lv["c"] * np.tanh(lv["c"] / 2.0)
+        lik.lam = float(np.sum(y) / np.sum(expectation(logistic, mu[0], var[0])))
+    elif lik.name == "heteroscedastic":  # heteroscedastic.jl:73-100 ; mu[0] = f, mu[1] = g
+        lam = lik.lam
+        lv["phi"] = (np.abs(mu[0] - y) ** 2 + var[0]) / 2.0
+        lv["c"] = sqrt_expec_square(mu[1], var[1])
+        lv["sigma_g"] = safe_expcosh(-mu[1] / 2.0, lv["c"] / 2.0) / 2.0
+        lv["gamma"] = lam * lv["phi"] * lv["sigma_g"]
+        lv["theta"] = (0.5 + lv["gamma"]) * np.tanh(lv["c"] / 2.0) / (2.0 * lv["c"])
+        lik.lam = float(max(len(y) / (2.0 * np.dot(lv["phi"], 1.0 - lv["sigma_g"])), lam))
     elif lik.name == "logisticsoftmax":  # logisticsoftmax.jl:55-79
         lv["c"] = sqrt_expec_square(mu, var)
         for _ in range(2):
@@ -296,13 +395,36 @@ def grad_E_mu(lik, y, lv):
         return (y / lik.sigma2)[None, :]
     if lik.name == "logisticsoftmax":
         return (y.T - lv["gamma"]) / 2.0
+    if lik.name == "laplace":  # laplace.jl:87-89
+        return (lv["theta"] * y)[None, :]
+    if lik.name == "bayesiansvm":  # bayesiansvm.jl:54-58
+        return (y * (lv["theta"] + 1.0))[None, :]
+    if lik.name == "negbinomial":  # negativebinomial.jl:94-96
+        return ((y - lik.r) / 2.0)[None, :]
+    if lik.name == "poisson":  # poisson.jl:98-102
+        return ((y - lv["gamma"]) / 2.0)[None, :]
+    if lik.name == "heteroscedastic":  # heteroscedastic.jl:111-118 (the lambda just re-estimated by local_updates!)
+        return np.stack([y * lik.lam * lv["sigma_g"] / 2.0, (0.5 - lv["gamma"]) / 2.0])
     raise ValueError(lik.name)
 
 
 def grad_E_Sigma(lik, y, lv):
     """(K, B).  logistic.jl:67-69, studentt.jl:97-99, gaussian.jl:78-80, logisticsoftmax.jl:101-103"""
+    if lik.name == "heteroscedastic":  # heteroscedastic.jl:120-127
+        return np.stack([lik.lam * lv["sigma_g"] / 2.0, lv["theta"] / 2.0])
     th = lv["theta"]
     return (th / 2.0)[None, :] if th.ndim == 1 else th / 2.0
+
+
+def GIGEntropy(a, b, p):
+    """functions/KLdivergences.jl:105-114 (the d/dp K_p term is omitted there too)"""
+    a = np.broadcast_to(np.asarray(a, dtype=np.float64), np.shape(b))
+    s = np.sqrt(a * b)
+    return float(
+        (np.sum(np.log(a)) - np.sum(np.log(b))) / 2.0
+        + np.sum(np.log(2.0 * ssp.kv(p, s)))
+        + np.sum(s / ssp.kv(p, s) * (ssp.kv(p + 1.0, s) + ssp.kv(p - 1.0, s))) / 2.0
+    )
 
 
 # ---- ELBO pieces -----------------------------------------------------------------------
@@ -348,6 +470,39 @@ def expec_loglikelihood(lik, y, mu, var, lv):
             -(len(y) * (math.log(TWOPI) + math.log(lik.sigma2)) + (np.sum((y - mu[0]) ** 2) + np.sum(var[0])) / lik.sigma2)
             / 2.0
         )
+    if lik.name == "laplace":  # laplace.jl:95-112
+        th = lv["theta"]
+        tot = -len(y) * math.log(TWOPI) / 2.0 + np.sum(np.log(th)) / 2.0
+        tot += -(np.dot(th, var[0]) + np.dot(th, mu[0] ** 2) - 2.0 * np.dot(th, mu[0] * y) + np.dot(th, y**2)) / 2.0
+        return float(tot)
+    if lik.name == "bayesiansvm":  # bayesiansvm.jl:68-80 (the last term enters with a PLUS sign and no 1/2, as written)
+        th = lv["theta"]
+        tot = -len(y) * LOGTWO / 2.0 + np.dot(mu[0], y)
+        tot += -np.dot(th, var[0]) / 2.0 + np.dot(th, (1.0 - y * mu[0]) ** 2)
+        return float(tot)
+    if lik.name == "negbinomial":  # negativebinomial.jl:113-124 (dot(theta, mu), not mu^2, as written)
+        th = lv["theta"]
+        r = lik.r
+        if isinstance(r, (int, np.integer)):  # :109-111 log(binomial(y + r - 1, y))
+            const = np.sum(ssp.gammaln(y + r) - ssp.gammaln(y + 1.0) - ssp.gammaln(float(r)))
+        else:  # :105-107
+            const = np.sum(ssp.gammaln(y + r) - ssp.gammaln(y + 1.0) - ssp.gammaln(r))
+        tot = const - LOGTWO * np.sum(y + r)
+        tot += np.dot(mu[0], y - r) / 2.0 - np.dot(th, mu[0]) / 2.0 - np.dot(th, var[0]) / 2.0
+        return float(tot)
+    if lik.name == "poisson":  # poisson.jl:110-124
+        th, g = lv["theta"], lv["gamma"]
+        tot = (np.dot(mu[0], y - g) - np.dot(th, mu[0] ** 2) - np.dot(th, var[0])) / 2.0
+        tot += np.sum(y * math.log(lik.lam)) - np.sum(ssp.gammaln(y + 1.0)) - LOGTWO * np.sum(y + g)
+        return float(tot)
+    if lik.name == "heteroscedastic":  # heteroscedastic.jl:143-159, 166-175
+        th, g = lv["theta"], lv["gamma"]
+        lam = lik.lam
+        tot = len(y) * (math.log(lam) / 2.0 - math.log(2.0 * math.sqrt(TWOPI)))
+        tot += (np.dot(mu[1], 0.5 - g) - np.dot(mu[1] ** 2, th) - np.dot(var[1], th)) / 2.0
+        lam0 = lam * ((y - mu[0]) ** 2 + var[0]) / 2.0
+        tot -= PoissonKL(g, lam0, np.log(lam0))
+        return float(tot)
     if lik.name == "logisticsoftmax":  # logisticsoftmax.jl:106-115  (Q10: length(y) = B*K)
         Y = y.T.astype(np.float64)
         g, th = lv["gamma"], lv["theta"]
@@ -366,6 +521,23 @@ def AugmentedKL(lik, lv, y):
         return GammaKL(lik.alpha, lv["c"], a_p, a_p * lik.sigma**2)
     if lik.name == "gaussian":  # gaussian.jl:95
         return 0.0
+    if lik.name == "laplace":  # laplace.jl:114-125
+        b = lv["b"]
+        ent = GIGEntropy(lik.a, b**2, lik.p)
+        ex = np.sum(-math.log(2.0 * lik.beta**2) - (lik.a * b + b**2 * math.sqrt(lik.a)) / (lik.a * b**2 * lik.beta**2) / 2.0)
+        return float(ent - ex)
+    if lik.name == "bayesiansvm":  # bayesiansvm.jl:82-89
+        c = lv["c"]
+        return float(np.sum(np.log(c)) / 2.0 + np.sum(np.log(2.0 * ssp.kv(0.5, np.sqrt(c)))) - np.sum(np.sqrt(c)) / 2.0)
+    if lik.name == "negbinomial":  # negativebinomial.jl:100, 126-128
+        return PolyaGammaKL(y + lik.r, lv["c"], lv["theta"])
+    if lik.name == "poisson":  # poisson.jl:126-136 ; KLdivergences.jl:74-76
+        g = lv["gamma"]
+        lam = lik.lam
+        po = lam * len(g) - (1.0 + math.log(lam)) * np.sum(g) + np.sum(xlogx(g))
+        return float(po + PolyaGammaKL(y + g, lv["c"], lv["theta"]))
+    if lik.name == "heteroscedastic":  # heteroscedastic.jl:161-165, 177-179
+        return PolyaGammaKL(0.5 + lv["gamma"], lv["c"], lv["theta"])
     if lik.name == "logisticsoftmax":  # logisticsoftmax.jl:117-140
         Y = y.T.astype(np.float64)
         K = lik.n_class
