@@ -10,7 +10,12 @@ from .api import (
     AnalyticSVI,
     AnalyticVI,
     ELBO,
+    BayesianSVM,
     GaussianLikelihood,
+    HeteroscedasticLikelihood,
+    LaplaceLikelihood,
+    NegBinomialLikelihood,
+    PoissonLikelihood,
     Kernel,
     LogisticLikelihood,
     LogisticSoftMaxLikelihood,

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libagp_b200.so")
 AGP_OK, AGP_ERR_BAD_ARG, AGP_ERR_CUDA, AGP_ERR_KTILDE_NONPOS, AGP_ERR_NOT_POSDEF, AGP_ERR_STATE = range(6)
 KERNEL_SQEXP, KERNEL_MATERN32, KERNEL_MATERN52 = 0, 1, 2
 LIK_GAUSSIAN, LIK_LOGISTIC, LIK_STUDENTT, LIK_LOGISTICSOFTMAX = 0, 1, 2, 3
+LIK_LAPLACE, LIK_BAYESIANSVM, LIK_NEGBINOMIAL, LIK_POISSON, LIK_HETEROSCEDASTIC = 4, 5, 6, 7, 8
 MODEL_SVGP, MODEL_MOSVGP = 0, 1
 PREC_F64, PREC_F32, PREC_TF32X3 = 0, 1, 2
 DTYPE_F64, DTYPE_F32 = 0, 1
@@ -84,6 +85,10 @@ SIGNATURES = {
     "agp_get_Kinv": (C.c_int, [C.c_void_p, C.c_int32, c_double_p, c_double_p]),
     "agp_predict_f": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, c_double_p, c_double_p]),
     "agp_proba_logistic": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int64, c_double_p, c_double_p, C.c_int32, c_double_p, c_double_p]),
+    "agp_set_quadrature": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int32]),
+    "agp_get_lik_param": (C.c_int, [C.c_void_p, C.c_int32, c_double_p]),
+    "agp_set_lik_param": (C.c_int, [C.c_void_p, C.c_int32, C.c_double]),
+    "agp_proba_link": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, c_double_p, c_double_p, C.c_int64, c_double_p, c_double_p]),
     "agp_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "agp_profile_read": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_char_p), c_double_p, c_int64_p]),
     "agp_launch_count": (C.c_int64, [C.c_void_p]),

@@ -115,6 +115,75 @@ class StudentTLikelihood(AbstractLikelihood):
         return f"Student-t likelihood (ν={self.nu}, σ={self.sigma})"
 
 
+class LaplaceLikelihood(AbstractLikelihood):
+    """likelihood/laplace.jl:17-28 (a = beta^-2, p = 1/2)"""
+
+    kind = L.LIK_LAPLACE
+
+    def __init__(self, beta: float = 1.0):
+        self.beta = float(beta)
+        self.p0 = self.beta
+
+    def __repr__(self):
+        return f"Laplace likelihood (β={self.beta})"
+
+
+class BayesianSVM(AbstractLikelihood):
+    """likelihood/bayesiansvm.jl:19 (BernoulliLikelihood(SVMLink()))"""
+
+    kind = L.LIK_BAYESIANSVM
+
+    def __repr__(self):
+        return "Bernoulli Likelihood with SVM Link"
+
+
+class NegBinomialLikelihood(AbstractLikelihood):
+    """likelihood/negativebinomial.jl:22-27"""
+
+    kind = L.LIK_NEGBINOMIAL
+
+    def __init__(self, r):
+        self.r = r
+        self.p0 = float(r)
+
+    def __repr__(self):
+        return f"Negative Binomial Likelihood (r = {self.r})"
+
+
+class PoissonLikelihood(AbstractLikelihood):
+    """likelihood/poisson.jl:16-26.  `lam` (l.invlink.λ[1]) is re-estimated by every local update (poisson.jl:80); the
+    device holds the live value, this attribute is refreshed at the end of `train`."""
+
+    kind = L.LIK_POISSON
+
+    def __init__(self, lam: float = 1.0):
+        self.lam = float(lam)
+
+    @property
+    def p0(self):
+        return self.lam
+
+    def __repr__(self):
+        return f"Poisson Likelihood (λ = {self.lam})"
+
+
+class HeteroscedasticLikelihood(AbstractLikelihood):
+    """likelihood/heteroscedastic.jl:17-48: N(y | f, (λ σ(g))^-1), two latent GPs; λ re-estimated (heteroscedastic.jl:98)."""
+
+    kind = L.LIK_HETEROSCEDASTIC
+    n_latent = 2
+
+    def __init__(self, lam: float = 1.0):
+        self.lam = float(lam)
+
+    @property
+    def p0(self):
+        return self.lam
+
+    def __repr__(self):
+        return "Gaussian likelihood with heteroscedastic noise"
+
+
 class LogisticSoftMaxLikelihood(AbstractLikelihood):
     """likelihood/logisticsoftmax.jl:23 + likelihood/multiclass.jl:1-24"""
 
@@ -171,7 +240,12 @@ def _class_indices(l: LogisticSoftMaxLikelihood, y) -> np.ndarray:
 
 def treat_labels(y, lik) -> np.ndarray:
     """likelihood/classification.jl:29-45, regression.jl:10-15, multiclass.jl:40-44"""
-    if lik.kind == L.LIK_LOGISTIC:
+    if lik.kind in (L.LIK_POISSON, L.LIK_NEGBINOMIAL):  # likelihood/event.jl:7-13
+        y = np.asarray(y)
+        if not np.issubdtype(y.dtype, np.integer):
+            raise TypeError("For event count target(s) should be integers")
+        return np.ascontiguousarray(y, dtype=np.float64)
+    if lik.kind in (L.LIK_LOGISTIC, L.LIK_BAYESIANSVM):
         y = np.asarray(y)
         if not (np.issubdtype(y.dtype, np.number) or y.dtype == bool):
             raise TypeError("For classification target(s) should be real valued (Bool, Integer or Float)")
@@ -351,6 +425,9 @@ class AbstractGPModel:
             cap = (cap + 127) // 128 * 128
         self._eng = _Engine(self._desc(cap), self.device, self.stream)
         self._data_key = None
+        if any(l.kind in (L.LIK_POISSON, L.LIK_NEGBINOMIAL, L.LIK_BAYESIANSVM) for l in self.likelihoods):
+            nodes, weights = _pred_nodes()   # `expectation` (functions/utils.jl:16-19) / compute_proba rule
+            self._eng.ck(self._eng.lib.agp_set_quadrature(self._eng.model, L.dptr(nodes), L.dptr(weights), len(nodes)))
         if saved is not None:
             for q, (mu, S, e1, e2) in enumerate(saved):
                 self._eng.ck(self._eng.lib.agp_set_posterior(self._eng.model, q, L.dptr(e1), L.dptr(e2)))
@@ -638,7 +715,17 @@ def train(model: AbstractGPModel, X, y, iterations: int = 100, *, callback=None,
         if callback is not None:
             callback(model, state, inf.n_iter)
         inf.n_iter += 1
+    _refresh_lik_params(model, eng)
     return model, state
+
+
+def _refresh_lik_params(model, eng):
+    """read the re-estimated link parameters (λ of Poisson / Heteroscedastic) back into the likelihood objects"""
+    for t, l in enumerate(model.likelihoods):
+        if l.kind in (L.LIK_POISSON, L.LIK_HETEROSCEDASTIC):
+            v = C.c_double(0.0)
+            eng.ck(eng.lib.agp_get_lik_param(eng.model, t, C.byref(v)))
+            l.lam = v.value
 
 
 train_ = train  # `train!`
@@ -759,8 +846,12 @@ def predict_f(model, X_test, state=None, *, cov: bool = False, diag: bool = True
 
 
 def _predict_y_lik(lik, mu):
-    if lik.kind == L.LIK_LOGISTIC:  # classification.jl:47
+    if lik.kind in (L.LIK_LOGISTIC, L.LIK_BAYESIANSVM):  # classification.jl:47
         return mu[0] > 0
+    if lik.kind == L.LIK_POISSON:  # poisson.jl:39-41 (predict_y = expec_count = λ σ(μ))
+        return lik.lam / (1.0 + np.exp(-mu[0]))
+    if lik.kind == L.LIK_NEGBINOMIAL:  # negativebinomial.jl (predict_y = r σ(μ) / (1 - σ(μ)) = r e^μ)
+        return lik.r * np.exp(mu[0])
     if lik.kind == L.LIK_LOGISTICSOFTMAX:  # predictions.jl:196-198
         am = np.argmax(mu, axis=0)
         return np.array([lik.class_mapping[i] for i in am])
@@ -788,6 +879,18 @@ def _compute_proba(model, lik, mu, var):
         eng.ck(eng.lib.agp_proba_logistic(eng.model, L.dptr(m_), L.dptr(v_), len(m_), L.dptr(nodes), L.dptr(weights),
                                           len(nodes), L.dptr(p), L.dptr(pv)))
         return p, pv
+    if lik.kind in (L.LIK_POISSON, L.LIK_NEGBINOMIAL, L.LIK_BAYESIANSVM):  # poisson.jl:43-55, negativebinomial.jl:47-62
+        eng = model._eng
+        link, p0 = {L.LIK_POISSON: (1, lik.p0), L.LIK_NEGBINOMIAL: (2, lik.p0), L.LIK_BAYESIANSVM: (3, 0.0)}[lik.kind]
+        m_ = np.ascontiguousarray(mu[0])
+        v_ = np.ascontiguousarray(var[0])
+        p, pv = np.empty_like(m_), np.empty_like(m_)
+        eng.ck(eng.lib.agp_proba_link(eng.model, link, float(p0), L.dptr(m_), L.dptr(v_), len(m_), L.dptr(p), L.dptr(pv)))
+        return p, pv
+    if lik.kind == L.LIK_LAPLACE:  # laplace.jl:48-52
+        return mu[0], np.maximum(var[0], 0.0) + 2.0 * lik.beta**2
+    if lik.kind == L.LIK_HETEROSCEDASTIC:  # heteroscedastic.jl:64-70 : (μ_f, σ²_f + 1 / (λ σ(μ_g)))
+        return mu[0], var[0] + (1.0 + np.exp(-mu[1])) / lik.lam
     if lik.kind == L.LIK_GAUSSIAN:  # gaussian.jl:41-45
         return mu[0], var[0] + lik.sigma2
     if lik.kind == L.LIK_STUDENTT:  # studentt.jl:57-61

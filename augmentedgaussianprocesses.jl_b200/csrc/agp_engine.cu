@@ -12,6 +12,7 @@
 #include "../../include/agp_b200.h"
 #include "agp_kernels.cuh"
 #include "agp_tail.cuh"
+#include "agp_tail2.cuh"
 #include "agp_umma.h"
 
 using namespace agp;
@@ -80,6 +81,10 @@ struct EngineBase {
   virtual int predict_f(const void* Xt, int x_dtype, int x_layout, int64_t nt, int want_var, double* mu, double* var) = 0;
   virtual int proba_logistic(const double* mu, const double* var, int64_t n, const double* nodes, const double* w, int nn,
                              double* p, double* pv) = 0;
+  virtual int set_quadrature(const double* nodes, const double* w, int nn) = 0;
+  virtual int get_lik_param(int task, double* v) = 0;
+  virtual int set_lik_param(int task, double v) = 0;
+  virtual int proba_link(int link, double p0, const double* mu, const double* var, int64_t n, double* p, double* pv) = 0;
   virtual int profile_enable(int on) = 0;
   virtual int profile_read(int maxp, const char** names, double* ms, int64_t* launches) = 0;
   virtual int64_t launch_count() = 0;
@@ -100,8 +105,12 @@ struct Engine : EngineBase {
   double rm_kappa, rm_tau, jitter;
   std::vector<int> h_lik_kind;
   std::vector<double> h_p0, h_p1, h_A;
-  bool is_lsm = false;
+  bool is_lsm = false;   // class-index labels (LogisticSoftMax)
+  bool is_het = false;   // HeteroscedasticLikelihood: 2 latents (f, g), one real-valued target
+  bool need_lam = false; // some likelihood re-estimates its link parameter lambda in local_updates! (Poisson, Heteroscedastic)
+  bool need_quad = false;
   int R = 1;  // rows of the local-variable arrays
+  double *d_lam = nullptr, *d_lamacc = nullptr, *d_qnodes = nullptr, *d_qw = nullptr; int nq = 0;
 
   // One latent GP.  The device works in the WHITENED basis u = L v (K = L L^T):
   //   V = Knm L^-T,  mu = L mu_v,  Sigma = L Sigma_v L^T,  eta1_v = L^T eta1,  eta2_v = L^T eta2 L.
@@ -157,6 +166,7 @@ struct Engine : EngineBase {
   int* ycls = nullptr;
   double* d_out = nullptr;  // [8] scratch scalars
   int n_split = 1, k_chunk = 0;
+  int tail_variant = 3;  // AGP_TAIL_VARIANT: 0-2 = agp_tail.cuh (SIMT tile products), 3 = agp_tail2.cuh (DMMA, panel potf2)
 
   // ---- step state ----
   int curB = 0; bool cur_from_batch = false; bool have_K = false; bool have_data = false; bool have_step = false;
@@ -234,19 +244,27 @@ struct Engine : EngineBase {
     for (int t = 0; t < nT; ++t) { if (d->lik_p0) h_p0[t] = d->lik_p0[t]; if (d->lik_p1) h_p1[t] = d->lik_p1[t]; }
     for (int t = 0; t < nT; ++t) {
       int k = h_lik_kind[t];
-      if (k < 0 || k > 3) BAD("unknown likelihood kind");
+      if (k < 0 || k > 8) BAD("unknown likelihood kind");
+      if (k == AGP_LIK_LAPLACE && !(h_p0[t] > 0)) BAD("Laplace scale beta must be positive");
+      if (k == AGP_LIK_NEGBINOMIAL && !(h_p0[t] > 0)) BAD("r must be positive");
+      if ((k == AGP_LIK_POISSON || k == AGP_LIK_HETEROSCEDASTIC) && !(h_p0[t] > 0)) BAD("lambda must be positive");
+      if (k == AGP_LIK_POISSON || k == AGP_LIK_HETEROSCEDASTIC) need_lam = true;
+      if (k == AGP_LIK_POISSON) need_quad = true;
       if (k == AGP_LIK_GAUSSIAN && !(h_p0[t] > 0)) BAD("Gaussian noise variance must be positive");
       if (k == AGP_LIK_STUDENTT && !(h_p0[t] > 0.5)) BAD("nu should be greater than 0.5");
     }
     if (model_kind == AGP_MODEL_SVGP) {
       if (nT != 1) BAD("SVGP takes exactly one likelihood");
       is_lsm = h_lik_kind[0] == AGP_LIK_LOGISTICSOFTMAX;
-      if (!is_lsm && Qg != 1) BAD("single-latent likelihood needs exactly one latent GP");
+      is_het = h_lik_kind[0] == AGP_LIK_HETEROSCEDASTIC;
+      if (is_het && Qg != 2) BAD("HeteroscedasticLikelihood needs exactly two latent GPs");
+      if (!is_lsm && !is_het && Qg != 1) BAD("single-latent likelihood needs exactly one latent GP");
       if (is_lsm && Qg < 2) BAD("LogisticSoftMax needs at least 2 classes");
       R = Qg;
     } else if (model_kind == AGP_MODEL_MOSVGP) {
       if (!d->A) BAD("MOSVGP needs the mixing matrix A");
-      for (int t = 0; t < nT; ++t) if (h_lik_kind[t] == AGP_LIK_LOGISTICSOFTMAX) BAD("MOSVGP tasks must be single-latent likelihoods");
+      for (int t = 0; t < nT; ++t)
+        if (h_lik_kind[t] == AGP_LIK_LOGISTICSOFTMAX || h_lik_kind[t] == AGP_LIK_HETEROSCEDASTIC) BAD("MOSVGP tasks must be single-latent likelihoods");
       h_A.assign(d->A, d->A + (size_t)nT * Qg);
       R = nT;
     } else BAD("unknown model kind");
@@ -333,10 +351,19 @@ struct Engine : EngineBase {
     CKS(dalloc(&gm, (size_t)nT * ldB)); CKS(dalloc(&gs, (size_t)nT * ldB)); CKS(dalloc(&yb, (size_t)nT * ldB));
     CKS(dalloc(&ycls, ldB));
     CKS(dalloc(&d_out, 8));
+    CKS(dalloc(&d_lam, nT)); CKS(dalloc(&d_lamacc, 2 * (size_t)nT)); CKS(dalloc(&d_qnodes, 128)); CKS(dalloc(&d_qw, 128));
+    CK(cudaMemcpyAsync(d_lam, h_p0.data(), nT * sizeof(double), cudaMemcpyHostToDevice, st()));
     CKS(reset_local_vars());
     CK(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, potf2_smem()));
-    CK(cudaFuncSetAttribute(tail_potf2_first_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM));
-    CK(cudaFuncSetAttribute(tail_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM));
+    CK(cudaFuncSetAttribute(tail_potf2_first_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM));
+    CK(cudaFuncSetAttribute(tail_step_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM));
+    CK(cudaFuncSetAttribute(tail_potf2_first_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM));
+    CK(cudaFuncSetAttribute(tail_step_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM));
+    CK(cudaFuncSetAttribute(tail_potf2_first_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM));
+    CK(cudaFuncSetAttribute(tail_step_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM));
+    CK(cudaFuncSetAttribute(tail2_potf2_first_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL2_SMEM));
+    CK(cudaFuncSetAttribute(tail2_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL2_SMEM));
+    { const char* e = getenv("AGP_TAIL_VARIANT"); if (e) tail_variant = atoi(e); if (tail_variant < 0 || tail_variant > 3) tail_variant = 3; }
     CK(cudaStreamSynchronize(st()));
     return AGP_OK;
   }
@@ -368,7 +395,7 @@ struct Engine : EngineBase {
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
     void* ps[] = {idx_prev, xx_cur, pKS, pXb, pxxb, X, xx, y_all, ycls_all, Xb, xxb, stage, idx_pool, idx_cur, counters, status, d_lik_kind, d_p0, d_p1, d_A,
-                  mean_f, var_f, gmu, gS, lc, ltheta, lgamma_, lalpha, tmu, tvar, gm, gs, yb, ycls, d_out};
+                  mean_f, var_f, gmu, gS, lc, ltheta, lgamma_, lalpha, tmu, tvar, gm, gs, yb, ycls, d_out, d_lam, d_lamacc, d_qnodes, d_qw};
     for (void* p : ps) cudaFree(p);
   }
 
@@ -426,9 +453,13 @@ struct Engine : EngineBase {
       CKS(dalloc(&y_all, (size_t)nT * n));
       for (int t = 0; t < nT; ++t) {
         if (!y[t]) BAD("null y");
-        if (h_lik_kind[t] == AGP_LIK_LOGISTIC) {
+        if (h_lik_kind[t] == AGP_LIK_LOGISTIC || h_lik_kind[t] == AGP_LIK_BAYESIANSVM) {
           const double* yt = (const double*)y[t];
           for (int64_t i = 0; i < n; ++i) if (yt[i] != 1.0 && yt[i] != -1.0) BAD("Labels of y should be binary {-1,1} or {0,1}");
+        }
+        if (h_lik_kind[t] == AGP_LIK_POISSON || h_lik_kind[t] == AGP_LIK_NEGBINOMIAL) {  // likelihood/event.jl:7-13
+          const double* yt = (const double*)y[t];
+          for (int64_t i = 0; i < n; ++i) if (!(yt[i] >= 0.0) || yt[i] != std::floor(yt[i])) BAD("For event count target(s) should be integers");
         }
         CK(cudaMemcpyAsync(y_all + (size_t)t * n, y[t], n * sizeof(double), cudaMemcpyHostToDevice, st()));
       }
@@ -691,6 +722,7 @@ struct Engine : EngineBase {
     p.y_all = y_all; p.n = n; p.ycls_all = ycls_all; p.idx = from_batch ? nullptr : idx_cur;
     p.yb = yb; p.ycls = ycls; p.c = lc; p.theta = ltheta; p.gamma = lgamma_; p.alpha = lalpha;
     p.tmu = tmu; p.tvar = tvar; p.gm = gm; p.gs = gs; p.gmu = gmu; p.gS = gS; p.update = update;
+    p.lam = d_lam; p.lamacc = d_lamacc; p.qnodes = d_qnodes; p.qweights = d_qw; p.nq = nq; p.need_reduce = need_lam ? 1 : 0;
     return p;
   }
 
@@ -714,8 +746,15 @@ struct Engine : EngineBase {
     if (curB < 1) { ctx->err = "no minibatch in flight"; return AGP_ERR_STATE; }
     const int B = curB;
     ph_begin(PH_LIK);
+    if (need_quad && nq < 1) { ph_end(); ctx->err = "agp_set_quadrature must be called before a Poisson step"; return AGP_ERR_STATE; }
     lik_update_kernel<<<(B + 127) / 128, 128, 0, st()>>>(lik_params(B, cur_from_batch, 1));
     ++launches;
+    if (need_lam) {  // lambda re-estimation closes local_updates! (poisson.jl:80, heteroscedastic.jl:98)
+      LikParams lp = lik_params(B, true, 1);
+      lik_lambda_kernel<<<1, std::max(32, (int)rup(nT, 32)), 0, st()>>>(lp);
+      ++launches;
+      if (is_het) { hetero_grad_kernel<<<(B + 127) / 128, 128, 0, st()>>>(lp); ++launches; }
+    }
     ph_end();
     for (int q = 0; q < Ql; ++q) {
       Latent& L = lat[q];
@@ -782,14 +821,20 @@ struct Engine : EngineBase {
     ph_begin(PH_CHOL);
     TailStepParams tp{};
     tp.P = L.P; tp.W = L.W; tp.Xout = L.Xv; tp.Dinv = L.Dinv; tp.ld = mp; tp.nblk = mp / TNB; tp.logdet = L.logdetP; tp.status = status;
-    tail_potf2_first_kernel<<<1, TAIL_THREADS, TAIL_SMEM, st()>>>(tp);
+    if (tail_variant == 0) tail_potf2_first_kernel<0><<<1, TAIL_THREADS, TAIL_SMEM, st()>>>(tp);
+    else if (tail_variant == 1) tail_potf2_first_kernel<1><<<1, TAIL_THREADS, TAIL_SMEM, st()>>>(tp);
+    else if (tail_variant == 2) tail_potf2_first_kernel<2><<<1, TAIL_THREADS, TAIL_SMEM, st()>>>(tp);
+    else tail2_potf2_first_kernel<0><<<1, TAIL_THREADS, TAIL2_SMEM, st()>>>(tp);
     ++launches;
     for (int k = 0; k < tp.nblk; ++k) {
       int r = tp.nblk - 1 - k;
       int tiles = r * (r + 1) / 2 + r * (k + 1) + k;
       if (tiles == 0) continue;
       tp.k = k;
-      tail_step_kernel<<<tiles, TAIL_THREADS, TAIL_SMEM, st()>>>(tp);
+      if (tail_variant == 0) tail_step_kernel<0><<<tiles, TAIL_THREADS, TAIL_SMEM, st()>>>(tp);
+      else if (tail_variant == 1) tail_step_kernel<1><<<tiles, TAIL_THREADS, TAIL_SMEM, st()>>>(tp);
+      else if (tail_variant == 2) tail_step_kernel<2><<<tiles, TAIL_THREADS, TAIL_SMEM, st()>>>(tp);
+      else tail2_step_kernel<<<tiles, TAIL_THREADS, TAIL2_SMEM, st()>>>(tp);
       ++launches;
     }
     ph_end();
@@ -1036,6 +1081,9 @@ struct Engine : EngineBase {
     if (s == "c") { base = lc; rows = R; }
     else if (s == "theta") { base = ltheta; rows = R; }
     else if (s == "gamma") { base = lgamma_; rows = R; }
+    else if (s == "b") { base = lc; rows = R; }                                   // Laplace: b lives in the c array
+    else if (s == "phi") { base = lc + ldB; rows = 1; if (!is_het) BAD("unknown local variable"); }
+    else if (s == "sigma_g") { base = lgamma_ + ldB; rows = 1; if (!is_het) BAD("unknown local variable"); }
     else if (s == "alpha") { base = lalpha; rows = 1; }
     else if (s == "mean_f") { base = mean_f; rows = Qg; }
     else if (s == "var_f") { base = var_f; rows = Qg; }
@@ -1094,6 +1142,40 @@ struct Engine : EngineBase {
     CK(cudaMemcpyAsync(p, dp, nn_ * 8, cudaMemcpyDeviceToHost, st())); CK(cudaMemcpyAsync(pv, dpv, nn_ * 8, cudaMemcpyDeviceToHost, st()));
     CK(cudaStreamSynchronize(st()));
     cudaFree(dm); cudaFree(dv); cudaFree(dn); cudaFree(dw); cudaFree(dp); cudaFree(dpv);
+    return AGP_OK;
+  }
+
+  int set_quadrature(const double* nodes, const double* w, int nn) override {
+    if (!nodes || !w || nn < 1 || nn > 128) BAD("bad quadrature rule (1..128 nodes)");
+    CK(cudaMemcpyAsync(d_qnodes, nodes, nn * 8, cudaMemcpyHostToDevice, st()));
+    CK(cudaMemcpyAsync(d_qw, w, nn * 8, cudaMemcpyHostToDevice, st()));
+    CK(cudaStreamSynchronize(st()));
+    nq = nn;
+    return AGP_OK;
+  }
+  int get_lik_param(int task, double* v) override {
+    if (task < 0 || task >= nT || !v) BAD("bad likelihood-parameter query");
+    CK(cudaStreamSynchronize(st()));
+    CK(cudaMemcpy(v, d_lam + task, 8, cudaMemcpyDeviceToHost));
+    return AGP_OK;
+  }
+  int set_lik_param(int task, double v) override {
+    if (task < 0 || task >= nT || !(v > 0)) BAD("bad likelihood parameter");
+    CK(cudaStreamSynchronize(st()));
+    CK(cudaMemcpy(d_lam + task, &v, 8, cudaMemcpyHostToDevice));
+    return AGP_OK;
+  }
+  int proba_link(int link, double p0, const double* mu, const double* var, int64_t nn_, double* p, double* pv) override {
+    if (!mu || !var || !p || !pv || nn_ < 1 || link < 0 || link > 3) BAD("bad proba arguments");
+    if (nq < 1) { ctx->err = "agp_set_quadrature has not been called"; return AGP_ERR_STATE; }
+    double *dm, *dv, *dp, *dpv;
+    CK(cudaMalloc(&dm, nn_ * 8)); CK(cudaMalloc(&dv, nn_ * 8)); CK(cudaMalloc(&dp, nn_ * 8)); CK(cudaMalloc(&dpv, nn_ * 8));
+    CK(cudaMemcpyAsync(dm, mu, nn_ * 8, cudaMemcpyHostToDevice, st())); CK(cudaMemcpyAsync(dv, var, nn_ * 8, cudaMemcpyHostToDevice, st()));
+    proba_link_kernel<<<(int)((nn_ + 127) / 128), 128, 0, st()>>>(link, p0, dm, dv, nn_, d_qnodes, d_qw, nq, dp, dpv);
+    ++launches;
+    CK(cudaMemcpyAsync(p, dp, nn_ * 8, cudaMemcpyDeviceToHost, st())); CK(cudaMemcpyAsync(pv, dpv, nn_ * 8, cudaMemcpyDeviceToHost, st()));
+    CK(cudaStreamSynchronize(st()));
+    cudaFree(dm); cudaFree(dv); cudaFree(dp); cudaFree(dpv);
     return AGP_OK;
   }
 
@@ -1321,6 +1403,14 @@ int agp_get_kernel_matrices(agp_model* model, int32_t ql, double* Knm, double* k
 int agp_get_Kinv(agp_model* model, int32_t ql, double* Kinv, double* logdetK) { ENG(model); return e->get_Kinv(ql, Kinv, logdetK); }
 int agp_predict_f(agp_model* model, const void* Xt, int x_dtype, int x_layout, int64_t nt, int want_var, double* mu, double* var) {
   ENG(model); return e->predict_f(Xt, x_dtype, x_layout, nt, want_var, mu, var);
+}
+int agp_set_quadrature(agp_model* model, const double* nodes, const double* weights, int32_t n_nodes) {
+  ENG(model); return e->set_quadrature(nodes, weights, n_nodes);
+}
+int agp_get_lik_param(agp_model* model, int32_t task, double* value) { ENG(model); return e->get_lik_param(task, value); }
+int agp_set_lik_param(agp_model* model, int32_t task, double value) { ENG(model); return e->set_lik_param(task, value); }
+int agp_proba_link(agp_model* model, int32_t link, double p0, const double* mu, const double* var, int64_t n, double* pred, double* pred_var) {
+  ENG(model); return e->proba_link(link, p0, mu, var, n, pred, pred_var);
 }
 int agp_proba_logistic(agp_model* model, const double* mu, const double* var, int64_t n, const double* nodes, const double* weights,
                        int32_t n_nodes, double* p, double* p_var) {

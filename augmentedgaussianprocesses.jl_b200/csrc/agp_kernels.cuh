@@ -198,11 +198,24 @@ struct LikParams {
   double* gm; double* gs;                                    // [T][ldB] per-task gradients (MOSVGP scratch)
   double* gmu; double* gS;                                   // [n_latent_local][ldB] outputs
   int update;                                                // 1: local_updates!, 0: only (re)compute task moments
+  // link parameters re-estimated by local_updates! (Poisson / Heteroscedastic lambda): value [T], accumulators [T][2]
+  double* lam; double* lamacc;
+  const double* qnodes; const double* qweights; int nq;      // Gauss-Hermite rule of `expectation` (functions/utils.jl:16-19)
+  int need_reduce;                                           // some task accumulates into lamacc
 };
 
-// one single-latent likelihood: c, theta and the two expectation gradients
-__device__ __forceinline__ void lik_single(int kind, double p0, double p1, double y, double mu, double var, double& c,
-                                           double& th, double& gm, double& gs) {
+// E[logistic(f)], f ~ N(mu, var), by the Gauss-Hermite rule (functions/utils.jl:16-19)
+__device__ __forceinline__ double expect_logistic(const double* __restrict__ nodes, const double* __restrict__ w, int nq, double mu, double var) {
+  const double sd = sqrt(fmax(var, 0.0));
+  double s = 0.0;
+  for (int k = 0; k < nq; ++k) s += w[k] * logistic_d(nodes[k] * sd + mu);
+  return s;
+}
+
+// one single-latent likelihood: c, theta (gamma for Poisson) and the two expectation gradients
+__device__ __forceinline__ void lik_single(int kind, double p0, double p1, double lam, double y, double mu, double var, double& c,
+                                           double& th, double& gam, double& gm, double& gs) {
+  gam = 0.0;
   if (kind == 1) {  // likelihood/logistic.jl:39-51, 64-69
     c = sqrt(mu * mu + var);
     th = tanh(0.5 * c) / (2.0 * c);
@@ -212,6 +225,25 @@ __device__ __forceinline__ void lik_single(int kind, double p0, double p1, doubl
     c = 0.5 * (d * d + var + p1 * p1 * p0);
     th = 0.5 * (p0 + 1.0) / c;
     gm = th * y;
+  } else if (kind == 4) {  // likelihood/laplace.jl:61-74, 87-92 : c holds b = sqrt(E[(f-y)^2]), theta = sqrt(a) / b, a = beta^-2
+    double d = mu - y;
+    c = sqrt(d * d + var);
+    th = (1.0 / p0) / c;
+    gm = th * y;
+  } else if (kind == 5) {  // likelihood/bayesiansvm.jl:40-64 : c = E[(1 - y f)^2] (not its root), theta = c^-1/2
+    double d = 1.0 - y * mu;
+    c = d * d + var;
+    th = 1.0 / sqrt(c);
+    gm = y * (th + 1.0);
+  } else if (kind == 6) {  // likelihood/negativebinomial.jl:69-99
+    c = sqrt(mu * mu + var);
+    th = (p0 + y) * tanh(0.5 * c) / c;
+    gm = 0.5 * (y - p0);
+  } else if (kind == 7) {  // likelihood/poisson.jl:65-108 (lambda = the value BEFORE this call's re-estimation)
+    c = sqrt(mu * mu + var);
+    gam = lam * safe_expcosh_d(-0.5 * mu, 0.5 * c) / 2.0;
+    th = (y + gam) / c * tanh(0.5 * c);
+    gm = 0.5 * (y - gam);
   } else {  // likelihood/gaussian.jl:56-80
     c = 0.0;
     th = 1.0 / p0;
@@ -220,9 +252,9 @@ __device__ __forceinline__ void lik_single(int kind, double p0, double p1, doubl
   gs = 0.5 * th;
 }
 
-__global__ void lik_update_kernel(const LikParams p) {
-  int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= p.B) return;
+// body of local_updates! for sample b; acc[2t], acc[2t+1]: this sample's contribution to the lambda statistics of task t
+// (only the FIRST reducing task is accumulated in registers: r0, r1; MOSVGP Poisson tasks use atomics directly)
+__device__ __forceinline__ void lik_update_sample(const LikParams& p, int b, double& r0, double& r1) {
   const int64_t ld = p.ldB;
   const int64_t src = p.idx ? p.idx[b] : (int64_t)b;
   if (p.model_kind == 0 && p.lik_kind[0] == 3) {
@@ -262,15 +294,41 @@ __global__ void lik_update_kernel(const LikParams p) {
     }
     return;
   }
+  if (p.model_kind == 0 && p.lik_kind[0] == 8) {
+    // ---- Heteroscedastic Gaussian (likelihood/heteroscedastic.jl:73-100): latent 0 = f, latent 1 = g.
+    // rows: c[0] = c, c[1] = phi, gamma[0] = gamma, gamma[1] = sigma_g, theta[0] = theta.  The gradients need the
+    // lambda re-estimated from this minibatch (:98, :111-127): hetero_grad_kernel, after lik_lambda_kernel.
+    double y = p.idx ? p.y_all[src] : p.yb[b];
+    if (p.idx) p.yb[b] = y;
+    if (!p.update) return;
+    const double lam = p.lam[0];
+    double m1 = p.mean_f[b], v1 = p.var_f[b], m2 = p.mean_f[ld + b], v2 = p.var_f[ld + b];
+    double d = m1 - y;
+    double phi = 0.5 * (d * d + v1);
+    double c = sqrt(m2 * m2 + v2);
+    double sg = safe_expcosh_d(-0.5 * m2, 0.5 * c) / 2.0;
+    double gam = lam * phi * sg;
+    double th = (0.5 + gam) * tanh(0.5 * c) / (2.0 * c);
+    p.c[b] = c; p.c[ld + b] = phi; p.gamma[b] = gam; p.gamma[ld + b] = sg; p.theta[b] = th;
+    r0 = phi * (1.0 - sg);
+    return;
+  }
   if (p.model_kind == 0) {
     // ---- single-latent SVGP ----
     double y = p.idx ? p.y_all[src] : p.yb[b];
     if (p.idx) p.yb[b] = y;
     if (!p.update) return;
-    double c, th, gm, gs;
-    lik_single(p.lik_kind[0], p.p0[0], p.p1[0], y, p.mean_f[b], p.var_f[b], c, th, gm, gs);
+    double c, th, gam, gm, gs;
+    const int kind = p.lik_kind[0];
+    const double mu = p.mean_f[b], var = p.var_f[b];
+    lik_single(kind, p.p0[0], p.p1[0], p.lam[0], y, mu, var, c, th, gam, gm, gs);
     p.c[b] = c; p.theta[b] = th;
     p.gmu[b] = gm; p.gS[b] = gs;
+    if (kind == 7) {  // poisson.jl:80 : lambda = sum(y) / sum(E[logistic(f)])
+      p.gamma[b] = gam;
+      r0 = y;
+      r1 = expect_logistic(p.qnodes, p.qweights, p.nq, mu, var);
+    }
     return;
   }
   // ---- MOSVGP (models/single_and_multi_output_utils.jl:24-84) ----
@@ -286,10 +344,16 @@ __global__ void lik_update_kernel(const LikParams p) {
     }
     p.tmu[t * ld + b] = mt; p.tvar[t * ld + b] = vt;
     if (p.update) {
-      double c, th, gm, gs;
-      lik_single(p.lik_kind[t], p.p0[t], p.p1[t], y, mt, vt, c, th, gm, gs);
+      double c, th, gam, gm, gs;
+      const int kind = p.lik_kind[t];
+      lik_single(kind, p.p0[t], p.p1[t], p.lam[t], y, mt, vt, c, th, gam, gm, gs);
       p.c[t * ld + b] = c; p.theta[t * ld + b] = th;
       p.gm[t * ld + b] = gm; p.gs[t * ld + b] = gs;
+      if (kind == 7) {
+        p.gamma[t * ld + b] = gam;
+        atomicAdd(p.lamacc + 2 * t, y);
+        atomicAdd(p.lamacc + 2 * t + 1, expect_logistic(p.qnodes, p.qweights, p.nq, mt, vt));
+      }
     }
   }
   if (!p.update) return;
@@ -305,6 +369,48 @@ __global__ void lik_update_kernel(const LikParams p) {
     }
     p.gmu[ql * ld + b] = a1;
     p.gS[ql * ld + b] = a2;
+  }
+}
+
+__global__ void lik_update_kernel(const LikParams p) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  double r0 = 0.0, r1 = 0.0;
+  if (b < p.B) lik_update_sample(p, b, r0, r1);
+  if (!p.need_reduce || !p.update || p.model_kind != 0) return;   // uniform
+  __shared__ double s0[8], s1[8];
+  r0 = warp_sum(r0); r1 = warp_sum(r1);
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { s0[w] = r0; s1[w] = r1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, c = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += s0[i]; c += s1[i]; }
+    atomicAdd(p.lamacc + 0, a);
+    atomicAdd(p.lamacc + 1, c);
+  }
+}
+
+// re-estimation of the link parameter lambda at the end of local_updates! (poisson.jl:80, heteroscedastic.jl:98);
+// one thread per task, accumulators cleared for the next step
+__global__ void lik_lambda_kernel(const LikParams p) {
+  int t = threadIdx.x;
+  if (t >= p.n_task) return;
+  int kind = p.lik_kind[t];
+  if (kind == 7) p.lam[t] = p.lamacc[2 * t] / p.lamacc[2 * t + 1];
+  else if (kind == 8) p.lam[t] = fmax((double)p.B / (2.0 * p.lamacc[2 * t]), p.lam[t]);
+  p.lamacc[2 * t] = 0.0; p.lamacc[2 * t + 1] = 0.0;
+}
+
+// grad_E_mu / grad_E_Sigma of the heteroscedastic likelihood (heteroscedastic.jl:111-127) with the NEW lambda
+__global__ void hetero_grad_kernel(const LikParams p) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= p.B) return;
+  const int64_t ld = p.ldB;
+  const double lam = p.lam[0], y = p.yb[b], sg = p.gamma[ld + b], gam = p.gamma[b], th = p.theta[b];
+  for (int ql = 0; ql < p.n_latent_local; ++ql) {
+    int q = p.latent_begin + ql;
+    p.gmu[ql * ld + b] = q == 0 ? 0.5 * y * lam * sg : 0.5 * (0.5 - gam);
+    p.gS[ql * ld + b] = q == 0 ? 0.5 * lam * sg : 0.5 * th;
   }
 }
 
@@ -334,6 +440,16 @@ __global__ void elbo_lik_kernel(const LikParams p, double* __restrict__ out) {
       }
       kl += -alpha - lgamma(alpha) - (1.0 - alpha) * psi;               // GammaEntropy (per-sample part)
       if (b == 0) kl += lb;                                             // Q2: log(beta[1]) once
+    } else if (p.model_kind == 0 && p.lik_kind[0] == 8) {
+      // heteroscedastic.jl:143-179 ; KLdivergences.jl:83-89, 96-98
+      const double lam = p.lam[0], y = p.yb[b];
+      double m1 = p.mean_f[b], v1 = p.var_f[b], m2 = p.mean_f[ld + b], v2 = p.var_f[ld + b];
+      double c = p.c[b], gam = p.gamma[b], th = p.theta[b];
+      e += 0.5 * log(lam) - log(2.0 * sqrt(6.283185307179586));
+      e += 0.5 * (m2 * (0.5 - gam) - m2 * m2 * th - v2 * th);
+      double lam0 = 0.5 * lam * ((y - m1) * (y - m1) + v1);
+      e -= lam0 - gam + xlogx_d(gam) - gam * log(lam0);                      // PoissonKL(gamma, lam0, log lam0)
+      kl += (0.5 + gam) * logcosh_d(0.5 * c) - 0.5 * c * c * th;            // PolyaGammaKL
     } else {
       int T = p.model_kind == 0 ? 1 : p.n_task;
       for (int t = 0; t < T; ++t) {
@@ -351,6 +467,27 @@ __global__ void elbo_lik_kernel(const LikParams p, double* __restrict__ out) {
           e += -0.5 * log(6.283185307179586 * p1 * p1) - (log(c) - digamma_pos(al)) -
                0.5 * (th * var + th * mu * mu - 2.0 * th * mu * y + th * y * y);
           kl += (al - ap) * digamma_pos(al) - log(tgamma(al)) + log(tgamma(ap)) + ap * (log(c) - log(bp)) + al * (bp - c) / c;
+        } else if (kind == 4) {  // laplace.jl:95-125 ; GIGEntropy (KLdivergences.jl:105-114) with p = 1/2 in closed form:
+          // K_{1/2}(s) = K_{-1/2}(s) = sqrt(pi / 2s) e^-s,  K_{3/2}(s) = K_{1/2}(s) (1 + 1/s)
+          double a = 1.0 / (p0 * p0), bb = c;   // c holds b
+          e += -0.5 * log(6.283185307179586) + 0.5 * log(th) - 0.5 * (th * var + th * mu * mu - 2.0 * th * mu * y + th * y * y);
+          double sq = sqrt(a) * bb;
+          double ent = 0.5 * (log(a) - 2.0 * log(bb)) + 0.6931471805599453 + 0.5 * log(3.141592653589793 / (2.0 * sq)) - sq + (sq + 0.5);
+          double ex = -log(2.0 * p0 * p0) - (a * bb + bb * bb * sqrt(a)) / (a * bb * bb * p0 * p0) / 2.0;
+          kl += ent - ex;
+        } else if (kind == 5) {  // bayesiansvm.jl:68-89 (signs as written in the reference)
+          double d = 1.0 - y * mu, sc = sqrt(c);
+          e += -0.5 * 0.6931471805599453 + mu * y - 0.5 * th * var + th * d * d;
+          kl += 0.5 * log(c) + (0.6931471805599453 + 0.5 * log(3.141592653589793 / (2.0 * sc)) - sc) - 0.5 * sc;
+        } else if (kind == 6) {  // negativebinomial.jl:102-128 (dot(theta, mu) as written)
+          e += lgamma(y + p0) - lgamma(y + 1.0) - lgamma(p0) - 0.6931471805599453 * (y + p0);
+          e += 0.5 * mu * (y - p0) - 0.5 * th * mu - 0.5 * th * var;
+          kl += (y + p0) * logcosh_d(0.5 * c) - 0.5 * c * c * th;
+        } else if (kind == 7) {  // poisson.jl:110-136 ; KLdivergences.jl:74-76
+          double lam = p.lam[t], g = p.gamma[t * ld + b];
+          e += 0.5 * (mu * (y - g) - th * mu * mu - th * var) + y * log(lam) - lgamma(y + 1.0) - 0.6931471805599453 * (y + g);
+          kl += lam - (1.0 + log(lam)) * g + xlogx_d(g);
+          kl += (y + g) * logcosh_d(0.5 * c) - 0.5 * c * c * th;
         } else {  // gaussian.jl:82-95
           double d = y - mu;
           e += -0.5 * (log(6.283185307179586) + log(p0) + (d * d + var) / p0);
@@ -603,6 +740,28 @@ __global__ void proba_logistic_kernel(const double* __restrict__ mu, const doubl
   }
   p[i] = s1;
   pv[i] = fmax(s2 - s1 * s1, 0.0);
+}
+
+// compute_proba of the count likelihoods by quadrature (poisson.jl:43-55, negativebinomial.jl:47-62, classification.jl:14-26)
+__global__ void proba_link_kernel(int link, double p0, const double* __restrict__ mu, const double* __restrict__ var, int64_t n,
+                                  const double* __restrict__ nodes, const double* __restrict__ weights, int nn,
+                                  double* __restrict__ p, double* __restrict__ pv) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double sd = sqrt(fmax(var[i], 0.0)), m = mu[i];
+  double s1 = 0.0, s2 = 0.0;
+  for (int k = 0; k < nn; ++k) {
+    double l = logistic_d(nodes[k] * sd + m);
+    double v = link == 1 ? p0 * l : (link == 2 ? l * p0 / (1.0 - l) : l);
+    if (link == 3) {  // svmlikelihood (bayesiansvm.jl:27-35)
+      double f = nodes[k] * sd + m, pos = exp(-2.0 * fmax(1.0 - f, 0.0)), neg = exp(-2.0 * fmax(1.0 + f, 0.0));
+      v = pos / (pos + neg);
+    }
+    s1 += weights[k] * v;
+    s2 += weights[k] * v * v;
+  }
+  p[i] = s1;
+  pv[i] = (link == 0 || link == 3) ? fmax(s2 - s1 * s1, 0.0) : s2 - s1 * s1;
 }
 
 }  // namespace agp

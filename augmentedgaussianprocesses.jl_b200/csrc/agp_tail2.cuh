@@ -1,0 +1,324 @@
+// agp_tail2.cuh -- second-generation m x m tail (fp64): P_v = R R^T and X = R^-1, fused, on the fp64 tensor path.
+//
+// Same block algorithm and launch structure as agp_tail.cuh (one launch per 64-wide block step, look-ahead
+// factorisation of the next diagonal tile inside the step kernel; global_update! of inference/inference.jl:25-28),
+// but every tile product runs on DMMA (mma.sync.m8n8k4.f64) from shared memory tiles with leading dimension 68
+// (68 = 4 mod 16: the 8x4 / 4x8 fragment loads are bank-conflict free), triangular operands skip their zero
+// k-range, and the 64 x 64 diagonal tile is factorised by PANELS of 16 columns:
+//   (a) one warp eliminates the 16 x 16 diagonal block (pivot chain; rank-1 updates on 16 x 16 only, lanes 0-15 hold
+//       the rows of the block, lanes 16-31 the columns of its inverse factor, one 16-double broadcast per pivot),
+//   (b) all warps: strip L_IJ = A_IJ X_JJ^T and the finished row block X_J,: = X_JJ T_J,:           (DMMA, K = 16)
+//   (c) all warps: trailing A_trail -= L L^T and T_I,: -= L_IJ X_J,: for the rows below            (DMMA, K = 16)
+// so the per-pivot work drops from a 64 x 128 register-resident rank-1 update (measured 568 cycles per pivot, bound by
+// shared-memory operand traffic and fp64 issue) to a 16 x 32 one (~110 cycles: STS -> LDS -> rcp -> FMA).
+// Measured on B200 (profiles/r1): DFMA latency 8.4 cycles, 62 DFMA/clk/SM; DMMA m8n8k4 27.5 cycles latency, 64 FMA/clk/SM.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "agp_tail.cuh"
+
+namespace agp {
+
+constexpr int T2LD = 68;                 // leading dimension of a 64 x 64 fp64 tile in shared memory
+constexpr int T2SL = 20;                 // leading dimension of the 64 x 16 panel strip (20 = 4 mod 16)
+constexpr int T2_TILE = TNB * T2LD;      // doubles per tile buffer
+constexpr int TAIL2_SMEM = (5 * T2_TILE + TNB * T2SL + 2 * 16 + 16 + TNB + 8) * (int)sizeof(double);
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// 64 x 64 tile, global (ld, 16-byte aligned rows) -> shared [64][T2LD]
+__device__ __forceinline__ void tile2_load(double* s, const double* __restrict__ g, int64_t ld) {
+  double2 v[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    int e = threadIdx.x + u * TAIL_THREADS;
+    v[u] = *reinterpret_cast<const double2*>(g + (int64_t)(e >> 5) * ld + (e & 31) * 2);
+  }
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    int e = threadIdx.x + u * TAIL_THREADS;
+    *reinterpret_cast<double2*>(s + (e >> 5) * T2LD + (e & 31) * 2) = v[u];
+  }
+}
+__device__ __forceinline__ void tile2_store(double* __restrict__ g, int64_t ld, const double* s) {
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    int e = threadIdx.x + u * TAIL_THREADS;
+    *reinterpret_cast<double2*>(g + (int64_t)(e >> 5) * ld + (e & 31) * 2) = *reinterpret_cast<const double2*>(s + (e >> 5) * T2LD + (e & 31) * 2);
+  }
+}
+
+// ---- 64 x 64 x 64 tile product on DMMA -----------------------------------------------------------------------
+// acc[t] = the 8 x 8 output tile t of the 8 tiles this warp owns.
+//   MAP 0: warp w owns output row block w  (tiles t = column block 0..7);  MAP 1: warp w owns column block w (t = row block)
+//   BT : B is stored [n][k] ("A B^T" form) / otherwise [k][n]
+//   KLIM 0: full k range; 1: k < 8 (nb + 1)  (B^T with B lower triangular); 2: k < 8 (mb + 1)  (A lower triangular);
+//        3: k >= 8 nb  (B stored [k][n], lower triangular)
+//   LOWER: only tiles with nb <= mb
+template <int MAP, bool BT, int KLIM, bool LOWER>
+__device__ __forceinline__ void tile2_prod(const double* __restrict__ A, const double* __restrict__ B, double (&acc)[8][2]) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, r = lane >> 2, kk = lane & 3;
+#pragma unroll
+  for (int t = 0; t < 8; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+#pragma unroll 2
+  for (int k4 = 0; k4 < 16; ++k4) {
+    const int k = 4 * k4;
+    if (MAP == 0) {
+      const int mb = w;
+      if (KLIM == 2 && k >= 8 * (mb + 1)) break;
+      const double a = A[(8 * mb + r) * T2LD + k + kk];
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb) {
+        if (LOWER && nb > mb) continue;
+        if (KLIM == 1 && k >= 8 * (nb + 1)) continue;
+        if (KLIM == 3 && k + 4 <= 8 * nb) continue;
+        const double b = BT ? B[(8 * nb + r) * T2LD + k + kk] : B[(k + kk) * T2LD + 8 * nb + r];
+        dmma884(acc[nb][0], acc[nb][1], a, b);
+      }
+    } else {
+      const int nb = w;
+      if (KLIM == 1 && k >= 8 * (nb + 1)) break;
+      if (KLIM == 3 && k + 4 <= 8 * nb) continue;
+      const double b = BT ? B[(8 * nb + r) * T2LD + k + kk] : B[(k + kk) * T2LD + 8 * nb + r];
+#pragma unroll
+      for (int mb = 0; mb < 8; ++mb) {
+        if (LOWER && nb > mb) continue;
+        if (KLIM == 2 && k >= 8 * (mb + 1)) continue;
+        const double a = A[(8 * mb + r) * T2LD + k + kk];
+        dmma884(acc[mb][0], acc[mb][1], a, b);
+      }
+    }
+  }
+}
+// global / shared address of this lane's two accumulator elements of tile t
+template <int MAP>
+__device__ __forceinline__ int acc_row(int t) { return 8 * (MAP == 0 ? (int)(threadIdx.x >> 5) : t) + ((threadIdx.x & 31) >> 2); }
+template <int MAP>
+__device__ __forceinline__ int acc_col(int t) { return 8 * (MAP == 0 ? t : (int)(threadIdx.x >> 5)) + 2 * (threadIdx.x & 3); }
+template <int MAP>
+__device__ __forceinline__ void acc2_to_smem(double* s, const double (&acc)[8][2]) {
+#pragma unroll
+  for (int t = 0; t < 8; ++t) *reinterpret_cast<double2*>(s + acc_row<MAP>(t) * T2LD + acc_col<MAP>(t)) = make_double2(acc[t][0], acc[t][1]);
+}
+
+// ---- Cholesky + inverse of one 64 x 64 tile, by 16-column panels -------------------------------------------------
+// sa: [64][T2LD] SPD tile (lower triangle read, destroyed).  sx: [64][T2LD] work tile -> X = chol(sa)^-1 (lower, zeros above).
+// sl: [64][T2SL] panel strip.  vec: col[2][16], rs[16], dvals[64].  Result also written to Xg (ld ldx) and densely to Dg.
+// ABL (measurement only, results wrong when != 0): bit 0 skip the pivot chain, 1 skip (b), 2 skip (c), 3 skip the result stores
+template <int ABL = 0>
+__device__ __forceinline__ void tile2_potf2_inv(double* sa, double* sx, double* sl, double* vec, double* __restrict__ Xg, int64_t ldx,
+                                                double* __restrict__ Dg, double* __restrict__ logdet, int* __restrict__ status) {
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  double* col = vec;            // [2][16]
+  double* rs = vec + 32;        // [16]
+  double* dvals = vec + 48;     // [64]
+  // T starts as the identity (only the lower triangle and the diagonal are ever read)
+  for (int e = t; e < TNB * TNB; e += TAIL_THREADS) { int i = e >> 6, c = e & 63; sx[i * T2LD + c] = (i == c) ? 1.0 : 0.0; }
+  __syncthreads();
+#pragma unroll 1
+  for (int J = 0; J < 4; ++J) {
+    const int c0 = 16 * J, nbelow = TNB - c0 - 16;
+    // ---- (a) pivot chain on the 16 x 16 diagonal block: warp 0 -------------------------------------------------
+    if (w == 0 && !(ABL & 1)) {
+      const int rr = lane & 15;
+      const bool arow = lane < 16;
+      double x[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const int hi_ = rr > q ? rr : q, lo_ = rr > q ? q : rr;
+        x[q] = arow ? sa[(c0 + hi_) * T2LD + c0 + lo_] : (q == rr ? 1.0 : 0.0);  // row rr of the block (symmetric) | column rr of W
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        double* cj = col + (j & 1) * 16;
+        if (arow) cj[rr] = x[j];                 // column j of the block: a_ij from the lane that holds row i
+        __syncwarp();
+        double d = cj[j];
+        if (!(d > 0.0)) { if (lane == 0) atomicOr(status, ST_NOT_POSDEF); d = 1.0; }
+        if (lane == j) dvals[c0 + j] = d;
+        const double inv = rcp_chain<2>(d);
+        double g = -x[j] * inv;                  // rows: -a_rj / d_j ; W columns: -w_jr / d_j
+        if (arow && rr <= j) g = 0.0;            // rows at or above the pivot are not touched
+#pragma unroll
+        for (int q = j + 1; q < 16; ++q) x[q] = fma(cj[q], g, x[q]);   // a_rq -= a_rj a_qj / d | w_qr -= a_qj w_jr / d
+      }
+      // X_JJ = diag(d)^-1/2 W  (rows of W scaled)
+      if (arow) rs[rr] = rsqrt(dvals[c0 + rr]);
+      __syncwarp();
+      if (!arow) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) sx[(c0 + q) * T2LD + c0 + rr] = (q >= rr) ? x[q] * rs[q] : 0.0;
+      }
+    }
+    __syncthreads();
+    // ---- (b) strip L_IJ = A_IJ X_JJ^T (rows below, -> sl) and X_J,0:c0 = X_JJ T_J,0:c0 (in registers until the barrier) ----
+    // 8 x 8 output tiles, K = 16: strip tiles (nbelow/8) x 2, row-block tiles 2 x (c0/8); one tile per warp per round
+    if (!(ABL & 2)) {
+      const int r = lane >> 2, kk = lane & 3;
+      const int n1 = (nbelow / 8) * 2, n2 = 2 * (c0 / 8);
+      double keep[2][2]; int keep_off[2];
+#pragma unroll
+      for (int s_ = 0; s_ < 2; ++s_) {
+        const int id = w + 8 * s_;
+        keep_off[s_] = -1;
+        if (id >= n1 + n2) continue;
+        double a0 = 0.0, a1 = 0.0;
+        if (id < n1) {
+          const int mb = id >> 1, nb = id & 1;           // rows c0+16+8mb.., strip columns 8nb..
+          const double* Ap = sa + (c0 + 16 + 8 * mb + r) * T2LD + c0;
+          const double* Bp = sx + (c0 + 8 * nb + r) * T2LD + c0;   // X_JJ[c][k], "B^T" form, k <= c
+#pragma unroll
+          for (int k = 0; k < 16; k += 4) if (k < 8 * (nb + 1)) dmma884(a0, a1, Ap[k + kk], Bp[k + kk]);
+          *reinterpret_cast<double2*>(sl + (8 * mb + r) * T2SL + 8 * nb + 2 * kk) = make_double2(a0, a1);
+        } else {
+          const int id2 = id - n1, mb = id2 / (c0 / 8), nb = id2 % (c0 / 8);   // rows c0+8mb.., columns 8nb..
+          const double* Ap = sx + (c0 + 8 * mb + r) * T2LD + c0;  // X_JJ[r][k], k <= r
+          const double* Bp = sx + c0 * T2LD + 8 * nb + r;          // T_J[k][c]
+#pragma unroll
+          for (int k = 0; k < 16; k += 4) if (k < 8 * (mb + 1)) dmma884(a0, a1, Ap[k + kk], Bp[(k + kk) * T2LD]);
+          keep[s_][0] = a0; keep[s_][1] = a1; keep_off[s_] = (c0 + 8 * mb + r) * T2LD + 8 * nb + 2 * kk;
+        }
+      }
+      __syncthreads();   // every reader of T_J is done: overwrite it with X_J,0:c0
+#pragma unroll
+      for (int s_ = 0; s_ < 2; ++s_)
+        if (keep_off[s_] >= 0) *reinterpret_cast<double2*>(sx + keep_off[s_]) = make_double2(keep[s_][0], keep[s_][1]);
+    }
+    __syncthreads();
+    if (nbelow == 0) break;
+    // ---- (c) trailing A -= L L^T (lower 8 x 8 tiles) and T_I,0:c0+16 -= L_IJ X_J,0:c0+16 for the rows below ----
+    if (!(ABL & 4)) {
+      const int r = lane >> 2, kk = lane & 3;
+      const int nb8 = nbelow / 8, n1 = nb8 * (nb8 + 1) / 2, n2 = nb8 * ((c0 + 16) / 8);
+#pragma unroll 1
+      for (int id = w; id < n1 + n2; id += 8) {
+        double a0 = 0.0, a1 = 0.0;
+        if (id < n1) {
+          int mb = 0;
+          while ((mb + 1) * (mb + 2) / 2 <= id) ++mb;
+          const int nb = id - mb * (mb + 1) / 2;
+          const double* Ap = sl + (8 * mb + r) * T2SL;
+          const double* Bp = sl + (8 * nb + r) * T2SL;
+#pragma unroll
+          for (int k = 0; k < 16; k += 4) dmma884(a0, a1, Ap[k + kk], Bp[k + kk]);
+          double2* dst = reinterpret_cast<double2*>(sa + (c0 + 16 + 8 * mb + r) * T2LD + c0 + 16 + 8 * nb + 2 * kk);
+          double2 o = *dst; o.x -= a0; o.y -= a1; *dst = o;
+        } else {
+          const int id2 = id - n1, ncb = (c0 + 16) / 8, mb = id2 / ncb, nb = id2 % ncb;
+          const double* Ap = sl + (8 * mb + r) * T2SL;
+          const double* Bp = sx + c0 * T2LD + 8 * nb + r;          // X_J[k][c]
+#pragma unroll
+          for (int k = 0; k < 16; k += 4) dmma884(a0, a1, Ap[k + kk], Bp[(k + kk) * T2LD]);
+          double2* dst = reinterpret_cast<double2*>(sx + (c0 + 16 + 8 * mb + r) * T2LD + 8 * nb + 2 * kk);
+          double2 o = *dst; o.x -= a0; o.y -= a1; *dst = o;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // ---- results ----
+  if (ABL & 8) return;
+  for (int e = t; e < TNB * TNB / 2; e += TAIL_THREADS) {
+    const int i = e >> 5, c = (e & 31) * 2;
+    double2 v = *reinterpret_cast<const double2*>(sx + i * T2LD + c);
+    if (c > i) v.x = 0.0;
+    if (c + 1 > i) v.y = 0.0;
+    *reinterpret_cast<double2*>(Xg + (int64_t)i * ldx + c) = v;
+    *reinterpret_cast<double2*>(Dg + i * TNB + c) = v;
+  }
+  if (t < TNB) {
+    double l = warp_sum(log(dvals[t]));
+    if ((t & 31) == 0) atomicAdd(logdet, l);
+  }
+}
+
+template <int ABL = 0>
+__global__ void __launch_bounds__(TAIL_THREADS, 1) tail2_potf2_first_kernel(const TailStepParams p) {
+  extern __shared__ double sm[];
+  tile2_load(sm, p.P, p.ld);
+  __syncthreads();
+  tile2_potf2_inv<ABL>(sm, sm + T2_TILE, sm + 5 * T2_TILE, sm + 5 * T2_TILE + TNB * T2SL, p.Xout, p.ld, p.Dinv, p.logdet, p.status);
+}
+
+__global__ void __launch_bounds__(TAIL_THREADS, 1) tail2_step_kernel(const TailStepParams p) {
+  extern __shared__ double sm[];
+  double* sX = sm;                  // X_kk
+  double* s1 = sm + 1 * T2_TILE;    // A_ik
+  double* s2 = sm + 2 * T2_TILE;    // A_jk / W_kc
+  double* s3 = sm + 3 * T2_TILE;    // L_ik
+  double* s4 = sm + 4 * T2_TILE;    // L_jk / Wn_kc
+  double* sl = sm + 5 * T2_TILE;
+  double* vec = sl + TNB * T2SL;
+  const int k = p.k, nblk = p.nblk, r = nblk - 1 - k;
+  const int nA = r * (r + 1) / 2, nW = r * (k + 1);
+  int b = blockIdx.x;
+  const int64_t ld = p.ld;
+  double acc[8][2];
+
+  tile2_load(sX, p.Dinv + (int64_t)k * TNB * TNB, TNB);
+
+  if (b < nA) {
+    // ---- A tile (i, j), k < j <= i :  A_ij -= L_ik L_jk^T,  L_ik = A_ik X_kk^T ----
+    int ii = 0;
+    while ((ii + 1) * (ii + 2) / 2 <= b) ++ii;
+    int jj = b - ii * (ii + 1) / 2;
+    const int i = k + 1 + ii, j = k + 1 + jj;
+    double* At = p.P + (int64_t)i * TNB * ld + (int64_t)j * TNB;
+    tile2_load(s1, p.P + (int64_t)i * TNB * ld + (int64_t)k * TNB, ld);
+    if (j != i) tile2_load(s2, p.P + (int64_t)j * TNB * ld + (int64_t)k * TNB, ld);
+    double2 old[8];   // the tile being updated, prefetched in the accumulator layout (MAP 0)
+#pragma unroll
+    for (int t = 0; t < 8; ++t) old[t] = *reinterpret_cast<const double2*>(At + (int64_t)acc_row<0>(t) * ld + acc_col<0>(t));
+    __syncthreads();
+    tile2_prod<0, true, 1, false>(s1, sX, acc); acc2_to_smem<0>(s3, acc);
+    const double* Lj = s3;
+    if (j != i) { tile2_prod<0, true, 1, false>(s2, sX, acc); acc2_to_smem<0>(s4, acc); Lj = s4; }
+    __syncthreads();
+    if (j != i) tile2_prod<0, true, 0, false>(s3, Lj, acc);
+    else tile2_prod<0, true, 0, true>(s3, Lj, acc);     // diagonal tile: lower 8 x 8 tiles only
+    const bool lookahead = (i == k + 1 && j == k + 1);
+    if (!lookahead) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t)
+        *reinterpret_cast<double2*>(At + (int64_t)acc_row<0>(t) * ld + acc_col<0>(t)) = make_double2(old[t].x - acc[t][0], old[t].y - acc[t][1]);
+    } else {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) *reinterpret_cast<double2*>(s1 + acc_row<0>(t) * T2LD + acc_col<0>(t)) = make_double2(old[t].x - acc[t][0], old[t].y - acc[t][1]);
+      __syncthreads();
+      tile2_potf2_inv(s1, s2, sl, vec, p.Xout + (int64_t)(k + 1) * TNB * (ld + 1), ld, p.Dinv + (int64_t)(k + 1) * TNB * TNB, p.logdet, p.status);
+    }
+  } else if (b < nA + nW) {
+    // ---- W tile (i, c), c <= k < i :  W_ic = [c<k] W_ic - L_ik Wn_kc,  Wn_kc = X_kk W_kc (c<k) or X_kk (c=k) ----
+    b -= nA;
+    const int i = k + 1 + b / (k + 1), c = b % (k + 1);
+    double* Wt = p.W + (int64_t)i * TNB * ld + (int64_t)c * TNB;
+    tile2_load(s1, p.P + (int64_t)i * TNB * ld + (int64_t)k * TNB, ld);
+    if (c < k) tile2_load(s2, p.W + (int64_t)k * TNB * ld + (int64_t)c * TNB, ld);
+    double2 old[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) old[t] = (c < k) ? *reinterpret_cast<const double2*>(Wt + (int64_t)acc_row<0>(t) * ld + acc_col<0>(t)) : make_double2(0.0, 0.0);
+    __syncthreads();
+    tile2_prod<0, true, 1, false>(s1, sX, acc); acc2_to_smem<0>(s3, acc);                        // L_ik
+    if (c < k) { tile2_prod<1, false, 2, false>(sX, s2, acc); acc2_to_smem<1>(s4, acc); }      // Wn_kc = X_kk W_kc
+    __syncthreads();
+    if (c < k) tile2_prod<0, false, 0, false>(s3, s4, acc);
+    else tile2_prod<0, false, 3, false>(s3, sX, acc);                                            // Wn = X_kk (lower triangular)
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+      *reinterpret_cast<double2*>(Wt + (int64_t)acc_row<0>(t) * ld + acc_col<0>(t)) = make_double2(old[t].x - acc[t][0], old[t].y - acc[t][1]);
+  } else {
+    // ---- F tile (k, c), c < k : final row block of X ----
+    const int c = b - nA - nW;
+    tile2_load(s2, p.W + (int64_t)k * TNB * ld + (int64_t)c * TNB, ld);
+    __syncthreads();
+    tile2_prod<1, false, 2, false>(sX, s2, acc);
+    double* Xt = p.Xout + (int64_t)k * TNB * ld + (int64_t)c * TNB;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) *reinterpret_cast<double2*>(Xt + (int64_t)acc_row<1>(t) * ld + acc_col<1>(t)) = make_double2(acc[t][0], acc[t][1]);
+  }
+}
+
+}  // namespace agp

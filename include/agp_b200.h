@@ -46,6 +46,13 @@ extern "C" {
 #define AGP_LIK_LOGISTIC 1        /* likelihood/logistic.jl:39-92                                  */
 #define AGP_LIK_STUDENTT 2        /* likelihood/studentt.jl:68-127       p0 = nu, p1 = sigma      */
 #define AGP_LIK_LOGISTICSOFTMAX 3 /* likelihood/logisticsoftmax.jl:43-140  (n_latent = #classes)  */
+#define AGP_LIK_LAPLACE 4         /* likelihood/laplace.jl:57-125        p0 = beta                */
+#define AGP_LIK_BAYESIANSVM 5     /* likelihood/bayesiansvm.jl:40-89                               */
+#define AGP_LIK_NEGBINOMIAL 6     /* likelihood/negativebinomial.jl:65-128  p0 = r                 */
+#define AGP_LIK_POISSON 7         /* likelihood/poisson.jl:61-136  p0 = initial lambda (re-estimated
+                                     by every local_updates!, poisson.jl:80); needs agp_set_quadrature */
+#define AGP_LIK_HETEROSCEDASTIC 8 /* likelihood/heteroscedastic.jl:50-180  p0 = initial lambda
+                                     (re-estimated, :98); n_latent = 2 (f and the noise GP g)      */
 
 #define AGP_MODEL_SVGP 0   /* models/SVGP.jl:22-80: one likelihood, n_latent(likelihood) latents */
 #define AGP_MODEL_MOSVGP 1 /* models/MOSVGP.jl:22-115: T single-latent tasks mixed from Q latents */
@@ -171,7 +178,8 @@ int agp_set_posterior(agp_model* model, int32_t latent_local, const double* eta1
 int agp_get_counters(agp_model* model, int64_t* rm_t, int64_t* cursor);
 int agp_set_counters(agp_model* model, int64_t rm_t, int64_t cursor);
 /* local variables of the last step: name in {"c","theta","gamma","alpha","mean_f","var_f",
- * "Ktilde","grad_mu","grad_Sigma"}; row = task / class / latent index; out: double[B]. */
+ * "Ktilde","grad_mu","grad_Sigma"} (+ "b" for Laplace, "phi" / "sigma_g" for Heteroscedastic);
+ * row = task / class / latent index; out: double[B]. */
 int agp_get_local(agp_model* model, const char* name, int32_t row, double* out, int32_t B);
 /* kernel matrices of the last step for one owned latent (state.kernel_matrices): B x m row-major */
 int agp_get_kernel_matrices(agp_model* model, int32_t latent_local, double* Knm, double* kappa, int32_t B);
@@ -186,6 +194,20 @@ int agp_predict_f(agp_model* model, const void* Xt, int x_dtype, int x_layout, i
  * expectation of the logistic link; nodes/weights as in predictions.jl:4 (already scaled). */
 int agp_proba_logistic(agp_model* model, const double* mu, const double* var, int64_t n, const double* nodes,
                        const double* weights, int32_t n_nodes, double* p, double* p_var);
+
+/* Gauss-Hermite rule of `expectation` (functions/utils.jl:16-19; pred_nodes / pred_weights of
+ * training/predictions.jl:4, i.e. gausshermite(100) nodes * sqrt2 and weights / sqrt(pi)).  Needed by the Poisson
+ * local update (poisson.jl:80) and by agp_proba_link; n_nodes <= 128. */
+int agp_set_quadrature(agp_model* model, const double* nodes, const double* weights, int32_t n_nodes);
+/* link parameters that local_updates! re-estimates (PoissonLikelihood / HeteroscedasticLikelihood lambda:
+ * l.invlink.lambda[1]); task = 0 for SVGP.  The value lives on the device between steps. */
+int agp_get_lik_param(agp_model* model, int32_t task, double* value);
+int agp_set_lik_param(agp_model* model, int32_t task, double value);
+/* compute_proba by quadrature for the count likelihoods: link 0 = logistic (classification.jl:14-26), 1 = scaled
+ * logistic p0 * sigma(f) (poisson.jl:43-55), 2 = negative-binomial mean sigma(f) p0 / (1 - sigma(f))
+ * (negativebinomial.jl:47-62), 3 = svmlikelihood (bayesiansvm.jl:27-35).  Uses the rule of agp_set_quadrature.  pred, pred_var: double[n]. */
+int agp_proba_link(agp_model* model, int32_t link, double p0, const double* mu, const double* var, int64_t n, double* pred,
+                   double* pred_var);
 
 /* ---- measurement hooks ------------------------------------------------------------------------ */
 /* per-phase CUDA-event timers around the kernels of a step (off by default; adds event records). */

@@ -21,6 +21,17 @@ def make_data(lik: str, n: int, D: int, m: int, B: int, iters: int, seed: int = 
         y = F[:, 0] + 0.1 * rng.standard_t(3.0, n)
     elif lik == "logisticsoftmax":
         y = np.argmax(F[:, :n_class] + 0.1 * rng.standard_normal((n, n_class)), axis=1) + 1
+    elif lik == "laplace":
+        y = F[:, 0] + rng.laplace(0.0, 0.2, n)
+    elif lik == "bayesiansvm":
+        y = np.sign(F[:, 0] + 0.1 * rng.standard_normal(n))
+        y[y == 0] = 1.0
+    elif lik == "negbinomial":
+        y = rng.negative_binomial(5, 1.0 / (1.0 + np.exp(F[:, 0]))).astype(np.int64)   # p(success) = sigma(-f)
+    elif lik == "poisson":
+        y = rng.poisson(4.0 / (1.0 + np.exp(-F[:, 0]))).astype(np.int64)
+    elif lik == "heteroscedastic":
+        y = F[:, 0] + rng.standard_normal(n) * 0.2 * np.exp(0.5 * F[:, 1])
     elif lik == "mo":
         y = None
     else:
@@ -36,6 +47,11 @@ def oracle_lik(O, lik: str, n_class: int = 3):
         "gaussian": lambda: O.GaussianLikelihood(1e-2),
         "studentt": lambda: O.StudentTLikelihood(3.0, 1.0),
         "logisticsoftmax": lambda: O.LogisticSoftMaxLikelihood(n_class),
+        "laplace": lambda: O.LaplaceLikelihood(0.5),
+        "bayesiansvm": lambda: O.BayesianSVM(),
+        "negbinomial": lambda: O.NegBinomialLikelihood(5),
+        "poisson": lambda: O.PoissonLikelihood(3.0),
+        "heteroscedastic": lambda: O.HeteroscedasticLikelihood(2.0),
     }[lik]()
 
 
@@ -45,6 +61,11 @@ def engine_lik(agp, lik: str, n_class: int = 3):
         "gaussian": lambda: agp.GaussianLikelihood(1e-2),
         "studentt": lambda: agp.StudentTLikelihood(3.0, 1.0),
         "logisticsoftmax": lambda: agp.LogisticSoftMaxLikelihood(n_class),
+        "laplace": lambda: agp.LaplaceLikelihood(0.5),
+        "bayesiansvm": lambda: agp.BayesianSVM(),
+        "negbinomial": lambda: agp.NegBinomialLikelihood(5),
+        "poisson": lambda: agp.PoissonLikelihood(3.0),
+        "heteroscedastic": lambda: agp.HeteroscedasticLikelihood(2.0),
     }[lik]()
 
 

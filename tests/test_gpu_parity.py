@@ -52,6 +52,39 @@ def test_svi_parity(agp, lik, precision):
     check_pair(agp, oracle, engine, TOL[precision])
 
 
+# the remaining AnalyticVI likelihoods (laplace.jl, bayesiansvm.jl, negativebinomial.jl, poisson.jl,
+# heteroscedastic.jl), incl. the lambda re-estimation of Poisson / Heteroscedastic inside local_updates!
+@pytest.mark.parametrize("lik", ["laplace", "bayesiansvm", "negbinomial", "poisson", "heteroscedastic"])
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_svi_parity_more_likelihoods(agp, lik, precision):
+    oracle, engine, _ = run_pair(agp, lik, precision)
+    check_pair(agp, oracle, engine, TOL[precision])
+    (mo, so), (me, se) = oracle, engine
+    if lik in ("poisson", "heteroscedastic"):
+        assert abs(me.likelihood.lam - mo.likelihood.lam) <= TOL[precision] * abs(mo.likelihood.lam), (me.likelihood.lam, mo.likelihood.lam)
+    if lik == "heteroscedastic":
+        assert rel_fro(se.local("phi"), so["local_vars"]["phi"]) < 10 * TOL[precision]
+        assert rel_fro(se.local("sigma_g"), so["local_vars"]["sigma_g"]) < 10 * TOL[precision]
+    if lik == "poisson":
+        assert rel_fro(se.local("gamma"), so["local_vars"]["gamma"]) < 10 * TOL[precision]
+
+
+def test_full_batch_avi_poisson(agp):
+    oracle, engine, _ = run_pair(agp, "poisson", "f64", n=200, B=200, iters=4, stoch=False)
+    check_pair(agp, oracle, engine, TOL["f64"])
+
+
+def test_count_predictions(agp):
+    (mo, so), (me, se), (X, y, F) = run_pair(agp, "poisson", "f64", iters=10)
+    Xt = X[:200]
+    mu_o = O.predict_f(mo, Xt, cov=False)
+    assert rel_fro(agp.predict_y(me, Xt), mo.likelihood.lam / (1.0 + np.exp(-mu_o[0]))) < 1e-7
+    p, pv = agp.proba_y(me, Xt)
+    mu_o, var_o = O.predict_f(mo, Xt, cov=True)
+    ref = mo.likelihood.lam * O.expectation(O.logistic, mu_o[0], var_o[0])
+    assert rel_fro(p, ref) < 1e-7
+
+
 @pytest.mark.parametrize("kind", ["matern32", "matern52"])
 def test_matern_kernels(agp, kind):
     oracle, engine, _ = run_pair(agp, "studentt", "f64", kind=kind, variance=2.0)
