@@ -166,6 +166,7 @@ struct Engine : EngineBase {
   int* ycls = nullptr;
   double* d_out = nullptr;  // [8] scratch scalars
   int n_split = 1, k_chunk = 0;
+  bool tail_pdl = true;  // AGP_TAIL_PDL=0 disables programmatic dependent launch of the tail kernels
   int tail_variant = 3;  // AGP_TAIL_VARIANT: 0-2 = agp_tail.cuh (SIMT tile products), 3 = agp_tail2.cuh (DMMA, panel potf2)
 
   // ---- step state ----
@@ -363,6 +364,7 @@ struct Engine : EngineBase {
     CK(cudaFuncSetAttribute(tail_step_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM));
     CK(cudaFuncSetAttribute(tail2_potf2_first_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL2_SMEM));
     CK(cudaFuncSetAttribute(tail2_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL2_SMEM));
+    { const char* e = getenv("AGP_TAIL_PDL"); if (e && e[0] == '0') tail_pdl = false; }
     { const char* e = getenv("AGP_TAIL_VARIANT"); if (e) tail_variant = atoi(e); if (tail_variant < 0 || tail_variant > 3) tail_variant = 3; }
     CK(cudaStreamSynchronize(st()));
     return AGP_OK;
@@ -816,6 +818,18 @@ struct Engine : EngineBase {
     return AGP_OK;
   }
 
+  // agp_tail2.cuh kernels are chained with programmatic dependent launch: block step k+1 becomes resident while step k
+  // runs and waits in griddepcontrol.wait, which hides most of the ~2 us launch gap between the 9 dependent launches
+  template <typename K>
+  void launch_tail2(K kern, int grid, const TailStepParams& tp) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TAIL_THREADS); cfg.dynamicSmemBytes = TAIL2_SMEM; cfg.stream = st();
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = tail_pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, tp);
+  }
+
   // fused blocked Cholesky + inverse of the factor (agp_tail.cuh): P (lower tiles, destroyed) -> Xv = chol(P)^-1
   void chol_inv(Latent& L) {
     ph_begin(PH_CHOL);
@@ -824,7 +838,7 @@ struct Engine : EngineBase {
     if (tail_variant == 0) tail_potf2_first_kernel<0><<<1, TAIL_THREADS, TAIL_SMEM, st()>>>(tp);
     else if (tail_variant == 1) tail_potf2_first_kernel<1><<<1, TAIL_THREADS, TAIL_SMEM, st()>>>(tp);
     else if (tail_variant == 2) tail_potf2_first_kernel<2><<<1, TAIL_THREADS, TAIL_SMEM, st()>>>(tp);
-    else tail2_potf2_first_kernel<0><<<1, TAIL_THREADS, TAIL2_SMEM, st()>>>(tp);
+    else launch_tail2(tail2_potf2_first_kernel<0>, 1, tp);
     ++launches;
     for (int k = 0; k < tp.nblk; ++k) {
       int r = tp.nblk - 1 - k;
@@ -834,7 +848,7 @@ struct Engine : EngineBase {
       if (tail_variant == 0) tail_step_kernel<0><<<tiles, TAIL_THREADS, TAIL_SMEM, st()>>>(tp);
       else if (tail_variant == 1) tail_step_kernel<1><<<tiles, TAIL_THREADS, TAIL_SMEM, st()>>>(tp);
       else if (tail_variant == 2) tail_step_kernel<2><<<tiles, TAIL_THREADS, TAIL_SMEM, st()>>>(tp);
-      else tail2_step_kernel<<<tiles, TAIL_THREADS, TAIL2_SMEM, st()>>>(tp);
+      else launch_tail2(tail2_step_kernel, tiles, tp);
       ++launches;
     }
     ph_end();

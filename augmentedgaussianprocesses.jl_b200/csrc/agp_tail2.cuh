@@ -25,6 +25,10 @@ constexpr int T2SL = 20;                 // leading dimension of the 64 x 16 pan
 constexpr int T2_TILE = TNB * T2LD;      // doubles per tile buffer
 constexpr int TAIL2_SMEM = (5 * T2_TILE + TNB * T2SL + 2 * 16 + 16 + TNB + 8) * (int)sizeof(double);
 
+// programmatic dependent launch (griddepcontrol): no-ops when the kernel was launched without the attribute
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
@@ -107,64 +111,136 @@ __device__ __forceinline__ void acc2_to_smem(double* s, const double (&acc)[8][2
 // ---- Cholesky + inverse of one 64 x 64 tile, by 16-column panels -------------------------------------------------
 // sa: [64][T2LD] SPD tile (lower triangle read, destroyed).  sx: [64][T2LD] work tile -> X = chol(sa)^-1 (lower, zeros above).
 // sl: [64][T2SL] panel strip.  vec: col[2][16], rs[16], dvals[64].  Result also written to Xg (ld ldx) and densely to Dg.
+//
+// Warp-specialised panel pipeline: warp 0 runs the pivot chain of panel J while warps 1-7 finish the trailing update (c)
+// of panel J-1 (the three 8 x 8 tiles of the next diagonal block first, handed over through named barrier 1) and stream
+// the finished rows of X to global memory, so only the chain and the small (b) phase are on the critical path.
 // ABL (measurement only, results wrong when != 0): bit 0 skip the pivot chain, 1 skip (b), 2 skip (c), 3 skip the result stores
+__device__ __forceinline__ void bar_arrive1() { asm volatile("bar.arrive 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void bar_sync1() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// rows [r0, r0+16) of X (lower triangular) from sx to the two global destinations; nthr threads, thread index tt
+__device__ __forceinline__ void x_rows_store(const double* sx, int r0, int tt, int nthr, double* __restrict__ Xg, int64_t ldx, double* __restrict__ Dg) {
+  for (int e = tt; e < 16 * 32; e += nthr) {
+    const int i = r0 + (e >> 5), c = (e & 31) * 2;
+    double2 v = *reinterpret_cast<const double2*>(sx + i * T2LD + c);
+    if (c > i) v.x = 0.0;
+    if (c + 1 > i) v.y = 0.0;
+    *reinterpret_cast<double2*>(Xg + (int64_t)i * ldx + c) = v;
+    *reinterpret_cast<double2*>(Dg + i * TNB + c) = v;
+  }
+}
+
 template <int ABL = 0>
 __device__ __forceinline__ void tile2_potf2_inv(double* sa, double* sx, double* sl, double* vec, double* __restrict__ Xg, int64_t ldx,
                                                 double* __restrict__ Dg, double* __restrict__ logdet, int* __restrict__ status) {
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-  double* col = vec;            // [2][16]
-  double* rs = vec + 32;        // [16]
-  double* dvals = vec + 48;     // [64]
-  // T starts as the identity (only the lower triangle and the diagonal are ever read)
-  for (int e = t; e < TNB * TNB; e += TAIL_THREADS) { int i = e >> 6, c = e & 63; sx[i * T2LD + c] = (i == c) ? 1.0 : 0.0; }
-  __syncthreads();
+  const int r = lane >> 2, kk = lane & 3;
+  double* col = vec;            // [2][20]  (16 column entries + the next diagonal element)
+  double* dvals = vec + 40;     // [64]
 #pragma unroll 1
   for (int J = 0; J < 4; ++J) {
     const int c0 = 16 * J, nbelow = TNB - c0 - 16;
-    // ---- (a) pivot chain on the 16 x 16 diagonal block: warp 0 -------------------------------------------------
-    if (w == 0 && !(ABL & 1)) {
+    if (w == 0) {
+      // ---- (a) pivot chain on the 16 x 16 diagonal block ---------------------------------------------------------
+      if (J > 0) bar_sync1();                    // the diagonal block has received the trailing update of panel J-1
+      if (!(ABL & 1)) {
       const int rr = lane & 15;
       const bool arow = lane < 16;
-      double x[16];
+      bool bad = false;
+      double x[16], rsv[16];
 #pragma unroll
       for (int q = 0; q < 16; ++q) {
         const int hi_ = rr > q ? rr : q, lo_ = rr > q ? q : rr;
         x[q] = arow ? sa[(c0 + hi_) * T2LD + c0 + lo_] : (q == rr ? 1.0 : 0.0);  // row rr of the block (symmetric) | column rr of W
       }
+      // Two interleaved reciprocal chains: 1/d_{j+1} = d_j / (a_{j+1,j+1} d_j - a_{j+1,j}^2) only needs the state BEFORE pivot j,
+      // so the reciprocal for pivot j+1 is started one pivot ahead and a pivot costs max(exchange, rcp / 2) instead of rcp.
+      double dprev = 0.0, Rprev = 0.0;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        double* cj = col + (j & 1) * 16;
-        if (arow) cj[rr] = x[j];                 // column j of the block: a_ij from the lane that holds row i
+        double* cj = col + (j & 1) * 20;
+        if (arow) cj[rr] = x[j];                                  // column j of the block: a_ij from the lane that holds row i
+        if (j < 15 && arow && rr == j + 1) cj[16] = x[j + 1];     // a_{j+1,j+1} before pivot j
         __syncwarp();
         double d = cj[j];
-        if (!(d > 0.0)) { if (lane == 0) atomicOr(status, ST_NOT_POSDEF); d = 1.0; }
-        if (lane == j) dvals[c0 + j] = d;
-        const double inv = rcp_chain<2>(d);
+        if (!(d > 0.0)) { bad = true; d = 1.0; }                  // PosDefException is raised after the chain (no branch on the chain)
+        const double inv = (j == 0) ? rcp_chain<1>(d) : dprev * Rprev;   // MUFU.RCP64H + one Newton step: relative error ~1e-14
+        if (j < 15) {
+          const double q1 = cj[j + 1], p1 = cj[16];
+          Rprev = rcp_chain<1>(fma(p1, d, -q1 * q1));
+          dprev = d;
+        }
         double g = -x[j] * inv;                  // rows: -a_rj / d_j ; W columns: -w_jr / d_j
         if (arow && rr <= j) g = 0.0;            // rows at or above the pivot are not touched
 #pragma unroll
         for (int q = j + 1; q < 16; ++q) x[q] = fma(cj[q], g, x[q]);   // a_rq -= a_rj a_qj / d | w_qr -= a_qj w_jr / d
+        rsv[j] = rsqrt(d);                       // off the chain: fills the latency bubbles
+        if (lane == j) dvals[c0 + j] = d;
       }
+      if (bad && lane == 0) atomicOr(status, ST_NOT_POSDEF);
       // X_JJ = diag(d)^-1/2 W  (rows of W scaled)
-      if (arow) rs[rr] = rsqrt(dvals[c0 + rr]);
-      __syncwarp();
       if (!arow) {
 #pragma unroll
-        for (int q = 0; q < 16; ++q) sx[(c0 + q) * T2LD + c0 + rr] = (q >= rr) ? x[q] * rs[q] : 0.0;
+        for (int q = 0; q < 16; ++q) sx[(c0 + q) * T2LD + c0 + rr] = (q >= rr) ? x[q] * rsv[q] : 0.0;
+      }
+      }
+    } else {
+      const int tt = t - 32;
+      if (J == 0) {
+        // T starts as the identity; the 16 x 16 diagonal blocks are written whole by the chains and never read before
+        for (int e = tt; e < TNB * TNB; e += TAIL_THREADS - 32) {
+          const int i = e >> 6, c = e & 63;
+          if ((i >> 4) != (c >> 4)) sx[i * T2LD + c] = 0.0;
+        }
+      } else {
+        // ---- (c) of panel J-1: trailing A -= L L^T (lower 8 x 8 tiles) and T_I,0:c0 -= L_I,J-1 X_J-1,0:c0 for the rows below ----
+        const int cp = c0 - 16, nbel = TNB - c0;          // previous panel start, rows below it
+        const int nb8 = nbel / 8, n1 = nb8 * (nb8 + 1) / 2, ncb = c0 / 8, n2 = nb8 * ncb;
+        bool arrived = false;
+        if (w > 3) { bar_arrive1(); arrived = true; }     // only warps 1-3 touch the next diagonal block (tiles 0..2)
+        if (!(ABL & 4)) {
+#pragma unroll 1
+        for (int id = w - 1; id < n1 + n2; id += 7) {
+          double a0 = 0.0, a1 = 0.0;
+          if (id < n1) {
+            int mb = 0;
+            while ((mb + 1) * (mb + 2) / 2 <= id) ++mb;
+            const int nb = id - mb * (mb + 1) / 2;
+            const double* Ap = sl + (8 * mb + r) * T2SL;
+            const double* Bp = sl + (8 * nb + r) * T2SL;
+#pragma unroll
+            for (int k = 0; k < 16; k += 4) dmma884(a0, a1, Ap[k + kk], Bp[k + kk]);
+            double2* dst = reinterpret_cast<double2*>(sa + (c0 + 8 * mb + r) * T2LD + c0 + 8 * nb + 2 * kk);
+            double2 o = *dst; o.x -= a0; o.y -= a1; *dst = o;
+          } else {
+            const int id2 = id - n1, mb = id2 / ncb, nb = id2 % ncb;
+            const double* Ap = sl + (8 * mb + r) * T2SL;
+            const double* Bp = sx + cp * T2LD + 8 * nb + r;          // X_J-1[k][c]
+#pragma unroll
+            for (int k = 0; k < 16; k += 4) dmma884(a0, a1, Ap[k + kk], Bp[(k + kk) * T2LD]);
+            double2* dst = reinterpret_cast<double2*>(sx + (c0 + 8 * mb + r) * T2LD + 8 * nb + 2 * kk);
+            double2 o = *dst; o.x -= a0; o.y -= a1; *dst = o;
+          }
+          if (!arrived) { bar_arrive1(); arrived = true; }   // tiles 0..2 (first round of warps 1-3) are the next diagonal block
+        }
+        }
+        if (!arrived) bar_arrive1();
+        // rows of panel J-1 of X are final: stream them out while the chain runs
+        if (!(ABL & 8)) x_rows_store(sx, cp, tt, TAIL_THREADS - 32, Xg, ldx, Dg);
       }
     }
     __syncthreads();
     // ---- (b) strip L_IJ = A_IJ X_JJ^T (rows below, -> sl) and X_J,0:c0 = X_JJ T_J,0:c0 (in registers until the barrier) ----
-    // 8 x 8 output tiles, K = 16: strip tiles (nbelow/8) x 2, row-block tiles 2 x (c0/8); one tile per warp per round
-    if (!(ABL & 2)) {
-      const int r = lane >> 2, kk = lane & 3;
+    // 8 x 8 output tiles, K = 16: strip tiles (nbelow/8) x 2, row-block tiles 2 x (c0/8); at most two tiles per warp
+    {
       const int n1 = (nbelow / 8) * 2, n2 = 2 * (c0 / 8);
       double keep[2][2]; int keep_off[2];
 #pragma unroll
       for (int s_ = 0; s_ < 2; ++s_) {
         const int id = w + 8 * s_;
         keep_off[s_] = -1;
-        if (id >= n1 + n2) continue;
+        if (id >= n1 + n2 || (ABL & 2)) continue;
         double a0 = 0.0, a1 = 0.0;
         if (id < n1) {
           const int mb = id >> 1, nb = id & 1;           // rows c0+16+8mb.., strip columns 8nb..
@@ -182,53 +258,17 @@ __device__ __forceinline__ void tile2_potf2_inv(double* sa, double* sx, double* 
           keep[s_][0] = a0; keep[s_][1] = a1; keep_off[s_] = (c0 + 8 * mb + r) * T2LD + 8 * nb + 2 * kk;
         }
       }
-      __syncthreads();   // every reader of T_J is done: overwrite it with X_J,0:c0
+      if (c0 > 0) {
+        __syncthreads();   // every reader of T_J is done: overwrite it with X_J,0:c0
 #pragma unroll
-      for (int s_ = 0; s_ < 2; ++s_)
-        if (keep_off[s_] >= 0) *reinterpret_cast<double2*>(sx + keep_off[s_]) = make_double2(keep[s_][0], keep[s_][1]);
-    }
-    __syncthreads();
-    if (nbelow == 0) break;
-    // ---- (c) trailing A -= L L^T (lower 8 x 8 tiles) and T_I,0:c0+16 -= L_IJ X_J,0:c0+16 for the rows below ----
-    if (!(ABL & 4)) {
-      const int r = lane >> 2, kk = lane & 3;
-      const int nb8 = nbelow / 8, n1 = nb8 * (nb8 + 1) / 2, n2 = nb8 * ((c0 + 16) / 8);
-#pragma unroll 1
-      for (int id = w; id < n1 + n2; id += 8) {
-        double a0 = 0.0, a1 = 0.0;
-        if (id < n1) {
-          int mb = 0;
-          while ((mb + 1) * (mb + 2) / 2 <= id) ++mb;
-          const int nb = id - mb * (mb + 1) / 2;
-          const double* Ap = sl + (8 * mb + r) * T2SL;
-          const double* Bp = sl + (8 * nb + r) * T2SL;
-#pragma unroll
-          for (int k = 0; k < 16; k += 4) dmma884(a0, a1, Ap[k + kk], Bp[k + kk]);
-          double2* dst = reinterpret_cast<double2*>(sa + (c0 + 16 + 8 * mb + r) * T2LD + c0 + 16 + 8 * nb + 2 * kk);
-          double2 o = *dst; o.x -= a0; o.y -= a1; *dst = o;
-        } else {
-          const int id2 = id - n1, ncb = (c0 + 16) / 8, mb = id2 / ncb, nb = id2 % ncb;
-          const double* Ap = sl + (8 * mb + r) * T2SL;
-          const double* Bp = sx + c0 * T2LD + 8 * nb + r;          // X_J[k][c]
-#pragma unroll
-          for (int k = 0; k < 16; k += 4) dmma884(a0, a1, Ap[k + kk], Bp[(k + kk) * T2LD]);
-          double2* dst = reinterpret_cast<double2*>(sx + (c0 + 16 + 8 * mb + r) * T2LD + 8 * nb + 2 * kk);
-          double2 o = *dst; o.x -= a0; o.y -= a1; *dst = o;
-        }
+        for (int s_ = 0; s_ < 2; ++s_)
+          if (keep_off[s_] >= 0) *reinterpret_cast<double2*>(sx + keep_off[s_]) = make_double2(keep[s_][0], keep[s_][1]);
       }
     }
     __syncthreads();
   }
-  // ---- results ----
-  if (ABL & 8) return;
-  for (int e = t; e < TNB * TNB / 2; e += TAIL_THREADS) {
-    const int i = e >> 5, c = (e & 31) * 2;
-    double2 v = *reinterpret_cast<const double2*>(sx + i * T2LD + c);
-    if (c > i) v.x = 0.0;
-    if (c + 1 > i) v.y = 0.0;
-    *reinterpret_cast<double2*>(Xg + (int64_t)i * ldx + c) = v;
-    *reinterpret_cast<double2*>(Dg + i * TNB + c) = v;
-  }
+  // ---- last row block of X, logdet ----
+  if (!(ABL & 8)) x_rows_store(sx, 48, t, TAIL_THREADS, Xg, ldx, Dg);
   if (t < TNB) {
     double l = warp_sum(log(dvals[t]));
     if ((t & 31) == 0) atomicAdd(logdet, l);
@@ -238,6 +278,8 @@ __device__ __forceinline__ void tile2_potf2_inv(double* sa, double* sx, double* 
 template <int ABL = 0>
 __global__ void __launch_bounds__(TAIL_THREADS, 1) tail2_potf2_first_kernel(const TailStepParams p) {
   extern __shared__ double sm[];
+  pdl_launch_dependents();   // let the next block step get resident while this one runs; it waits in pdl_wait()
+  pdl_wait();
   tile2_load(sm, p.P, p.ld);
   __syncthreads();
   tile2_potf2_inv<ABL>(sm, sm + T2_TILE, sm + 5 * T2_TILE, sm + 5 * T2_TILE + TNB * T2SL, p.Xout, p.ld, p.Dinv, p.logdet, p.status);
@@ -258,6 +300,8 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) tail2_step_kernel(const TailS
   const int64_t ld = p.ld;
   double acc[8][2];
 
+  pdl_launch_dependents();
+  pdl_wait();                // everything below reads what the previous block step wrote
   tile2_load(sX, p.Dinv + (int64_t)k * TNB * TNB, TNB);
 
   if (b < nA) {

@@ -6,15 +6,25 @@
 #include <vector>
 #include <cmath>
 using namespace agp;
+static bool g_pdl = false;
+template <typename K>
+static void launch2(K kern, int grid, TailStepParams tp, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TAIL_THREADS); cfg.dynamicSmemBytes = TAIL2_SMEM; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = g_pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, tp);
+}
 static void launch_seq(int gen, TailStepParams tp, cudaStream_t st) {
   if (gen == 0) tail_potf2_first_kernel<0><<<1, TAIL_THREADS, TAIL_SMEM, st>>>(tp);
-  else tail2_potf2_first_kernel<0><<<1, TAIL_THREADS, TAIL2_SMEM, st>>>(tp);
+  else launch2(tail2_potf2_first_kernel<0>, 1, tp, st);
   for (int k = 0; k < tp.nblk; ++k) {
     int r = tp.nblk - 1 - k, tiles = r * (r + 1) / 2 + r * (k + 1) + k;
     if (!tiles) continue;
     tp.k = k;
     if (gen == 0) tail_step_kernel<0><<<tiles, TAIL_THREADS, TAIL_SMEM, st>>>(tp);
-    else tail2_step_kernel<<<tiles, TAIL_THREADS, TAIL2_SMEM, st>>>(tp);
+    else launch2(tail2_step_kernel, tiles, tp, st);
   }
 }
 int main(int argc, char** argv) {
@@ -48,7 +58,9 @@ int main(int argc, char** argv) {
   cudaFuncSetAttribute(tail2_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL2_SMEM);
   cudaStream_t st; cudaStreamCreate(&st);
   TailStepParams tp{}; tp.P = dP; tp.W = dW; tp.Xout = dX; tp.Dinv = dD; tp.ld = m; tp.nblk = nblk; tp.logdet = dl; tp.status = ds;
-  for (int gen = 0; gen < 2; ++gen) {
+  for (int gen = 0; gen < 3; ++gen) {
+    g_pdl = gen == 2;
+    if (gen == 2) printf("(gen 2 = gen 1 launched with programmatic dependent launch)\n");
     cudaMemset(dX, 0, bytes); cudaMemset(dW, 0, bytes); cudaMemset(dl, 0, 8); cudaMemset(ds, 0, 4);
     cudaMemcpyAsync(dP, dA, bytes, cudaMemcpyDeviceToDevice, st);
     launch_seq(gen, tp, st);
