@@ -166,7 +166,9 @@ struct Engine : EngineBase {
   int* ycls = nullptr;
   double* d_out = nullptr;  // [8] scratch scalars
   int n_split = 1, k_chunk = 0;
-  bool tail_pdl = true;  // AGP_TAIL_PDL=0 disables programmatic dependent launch of the tail kernels
+  bool tail_pdl = true;  // AGP_TAIL_PDL=0 disables programmatic dependent launch along the per-step kernel chain
+  double* d_lr = nullptr;          // Robbins-Monro step size of the current iteration (lik_update_kernel -> combine_kernel)
+  bool racc2_precleared = false;   // the V X^T row-statistic accumulators were cleared off the critical chain (side stream)
   int tail_variant = 3;  // AGP_TAIL_VARIANT: 0-2 = agp_tail.cuh (SIMT tile products), 3 = agp_tail2.cuh (DMMA, panel potf2)
 
   // ---- step state ----
@@ -182,6 +184,7 @@ struct Engine : EngineBase {
   // graph
   bool want_graph = false; cudaGraphExec_t gexec = nullptr; int gB = -1; double grho = -1; int64_t g_launches = 0;
   bool capturing = false;
+  cudaGraphExec_t gexec_b = nullptr; int gB_b = -1, gkey_b = -1; double grho_b = -1; int64_t g_launches_b = 0;   // host-batch step graph
 
   // launch stream: the context's stream, or the side stream while the next minibatch is being prefetched
   cudaStream_t cur_stream = nullptr;
@@ -290,7 +293,7 @@ struct Engine : EngineBase {
       CKS(dalloc(&L.Z, (size_t)m * Dp)); CKS(dalloc(&L.zz, m));
       CKS(dalloc(&L.Zd, (size_t)m * Dp)); CKS(dalloc(&L.zzd, m));
       CKS(dalloc(&L.Lc, (size_t)mp * mp)); CKS(dalloc(&L.Linv, (size_t)mp * mp)); CKS(dalloc(&L.Kinv, (size_t)mp * mp));
-      CKS(dalloc(&L.mu0, mp)); CKS(dalloc(&L.mu0v, mp));
+      CKS(dalloc(&L.mu0, 2 * (size_t)mp)); CKS(dalloc(&L.mu0v, mp));   // mu0: [0, mp) prior mean, [mp, 2mp) scratch for the canonical mean
       CKS(dalloc(&L.Linv_T, (size_t)m * ldm));
       CKS(dalloc(&L.eta1c, mp)); CKS(dalloc(&L.eta2c, (size_t)mp * mp));
       CKS(dalloc(&L.eta1v, mp)); CKS(dalloc(&L.eta2v, (size_t)mp * mp)); CKS(dalloc(&L.muv, mp)); CKS(dalloc(&L.tvec, mp));
@@ -352,6 +355,8 @@ struct Engine : EngineBase {
     CKS(dalloc(&gm, (size_t)nT * ldB)); CKS(dalloc(&gs, (size_t)nT * ldB)); CKS(dalloc(&yb, (size_t)nT * ldB));
     CKS(dalloc(&ycls, ldB));
     CKS(dalloc(&d_out, 8));
+    CKS(dalloc(&d_lr, 1));
+    { double one = 1.0; CK(cudaMemcpyAsync(d_lr, &one, 8, cudaMemcpyHostToDevice, st())); }
     CKS(dalloc(&d_lam, nT)); CKS(dalloc(&d_lamacc, 2 * (size_t)nT)); CKS(dalloc(&d_qnodes, 128)); CKS(dalloc(&d_qw, 128));
     CK(cudaMemcpyAsync(d_lam, h_p0.data(), nT * sizeof(double), cudaMemcpyHostToDevice, st()));
     CKS(reset_local_vars());
@@ -386,6 +391,8 @@ struct Engine : EngineBase {
     resolve_pending();
     for (auto e : ev_pool) cudaEventDestroy(e);
     if (gexec) cudaGraphExecDestroy(gexec);
+    if (gexec_b) cudaGraphExecDestroy(gexec_b);
+    if (h_status) cudaFreeHost(h_status);
     for (auto& L : lat) {
       void* ps[] = {L.Z, L.zz, L.Zd, L.zzd, L.Lc, L.Linv, L.Kinv, L.mu0, L.mu0v, L.Linv_T, L.eta1c, L.eta2c, L.eta1v, L.eta2v,
                     L.muv, L.tvec, L.Xv, L.Dinv, L.Xv_T, L.Knm, L.V, L.VS, L.Ktilde, L.racc, L.Gpart, L.v1, L.P, L.X, L.W, L.logdetP};
@@ -397,13 +404,14 @@ struct Engine : EngineBase {
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
     void* ps[] = {idx_prev, xx_cur, pKS, pXb, pxxb, X, xx, y_all, ycls_all, Xb, xxb, stage, idx_pool, idx_cur, counters, status, d_lik_kind, d_p0, d_p1, d_A,
-                  mean_f, var_f, gmu, gS, lc, ltheta, lgamma_, lalpha, tmu, tvar, gm, gs, yb, ycls, d_out, d_lam, d_lamacc, d_qnodes, d_qw};
+                  mean_f, var_f, gmu, gS, lc, ltheta, lgamma_, lalpha, tmu, tvar, gm, gs, yb, ycls, d_out, d_lam, d_lamacc, d_qnodes, d_qw, d_lr};
     for (void* p : ps) cudaFree(p);
   }
 
   int ensure_stage(size_t bytes) {
     if (bytes <= stage_bytes) return AGP_OK;
     if (stage) cudaFree(stage);
+    if (gexec_b) { cudaGraphExecDestroy(gexec_b); gexec_b = nullptr; }   // the host-batch graph reads from the staging buffer
     stage = nullptr; stage_bytes = 0;
     CK(cudaMalloc(&stage, bytes));
     stage_bytes = bytes;
@@ -684,7 +692,8 @@ struct Engine : EngineBase {
       {
         ph_begin(PH_KSIGMA);
         if (prec == AGP_PREC_TF32X3) {
-          CK(cudaMemsetAsync(L.racc + ldB, 0, 2 * ldB * sizeof(double), st()));
+          if (!(racc2_precleared && Ql == 1)) CK(cudaMemsetAsync(L.racc + ldB, 0, 2 * ldB * sizeof(double), st()));
+          racc2_precleared = false;
           UmmaEpilogue ep{};
           ep.mode = UMMA_EPI_STATS_ONLY; ep.acc0 = L.racc + ldB; ep.acc1 = L.racc + 2 * ldB; ep.tvec = L.tvec;
           CKS(umma_gemm_nt(ctx_err(), L.um, UM_V, UM_X, (float*)(void*)L.VS, B, m, ep, st()));
@@ -699,9 +708,9 @@ struct Engine : EngineBase {
       }
       ph_begin(PH_ROWSTATS);
       if (prec == AGP_PREC_TF32X3)
-        rowfinish_kernel<<<(B + 255) / 256, 256, 0, st()>>>(L.racc, L.racc + ldB, L.racc + 2 * ldB, B, L.variance + jitter, L.Ktilde,
-                                                            mean_out + (size_t)q * out_ld, var_out + (size_t)q * out_ld, status,
-                                                            fresh_kernel_matrices ? 1 : 0);
+        launch_chain(rowfinish_kernel, dim3((B + 255) / 256), dim3(256), 0, (const double*)L.racc, (const double*)(L.racc + ldB),
+                     (const double*)(L.racc + 2 * ldB), B, L.variance + jitter, L.Ktilde, mean_out + (size_t)q * out_ld,
+                     var_out + (size_t)q * out_ld, status, fresh_kernel_matrices ? 1 : 0);
       else
       rowstats_kernel<T><<<(B * 32 + 255) / 256, 256, 0, st()>>>(L.V, L.VS, L.tvec, B, m, ldm, L.variance + jitter,
                                                                  L.Ktilde, mean_out + (size_t)q * out_ld, var_out + (size_t)q * out_ld,
@@ -724,6 +733,7 @@ struct Engine : EngineBase {
     p.y_all = y_all; p.n = n; p.ycls_all = ycls_all; p.idx = from_batch ? nullptr : idx_cur;
     p.yb = yb; p.ycls = ycls; p.c = lc; p.theta = ltheta; p.gamma = lgamma_; p.alpha = lalpha;
     p.tmu = tmu; p.tvar = tvar; p.gm = gm; p.gs = gs; p.gmu = gmu; p.gS = gS; p.update = update;
+    p.lr_out = d_lr; p.counters = counters; p.stochastic = stochastic; p.rm_kappa = rm_kappa; p.rm_tau = rm_tau;
     p.lam = d_lam; p.lamacc = d_lamacc; p.qnodes = d_qnodes; p.qweights = d_qw; p.nq = nq; p.need_reduce = need_lam ? 1 : 0;
     return p;
   }
@@ -749,19 +759,20 @@ struct Engine : EngineBase {
     const int B = curB;
     ph_begin(PH_LIK);
     if (need_quad && nq < 1) { ph_end(); ctx->err = "agp_set_quadrature must be called before a Poisson step"; return AGP_ERR_STATE; }
-    lik_update_kernel<<<(B + 127) / 128, 128, 0, st()>>>(lik_params(B, cur_from_batch, 1));
+    launch_chain(lik_update_kernel, dim3((B + 127) / 128), dim3(128), 0, lik_params(B, cur_from_batch, 1));
     ++launches;
     if (need_lam) {  // lambda re-estimation closes local_updates! (poisson.jl:80, heteroscedastic.jl:98)
       LikParams lp = lik_params(B, true, 1);
-      lik_lambda_kernel<<<1, std::max(32, (int)rup(nT, 32)), 0, st()>>>(lp);
+      launch_chain(lik_lambda_kernel, dim3(1), dim3(std::max(32, (int)rup(nT, 32))), 0, lp);
       ++launches;
-      if (is_het) { hetero_grad_kernel<<<(B + 127) / 128, 128, 0, st()>>>(lp); ++launches; }
+      if (is_het) { launch_chain(hetero_grad_kernel, dim3((B + 127) / 128), dim3(128), 0, lp); ++launches; }
     }
     ph_end();
     for (int q = 0; q < Ql; ++q) {
       Latent& L = lat[q];
       ph_begin(PH_GRADMU);
-      CK(cudaMemsetAsync(L.v1, 0, m * sizeof(double), st()));
+      // tf32x3: V^T grad_mu is accumulated by the scale-transpose kernel into v1, which combine_kernel clears after use
+      if (prec != AGP_PREC_TF32X3) CK(cudaMemsetAsync(L.v1, 0, m * sizeof(double), st()));
       if (prec != AGP_PREC_TF32X3)
       { int rpb = std::max(64, (int)rup((B + 15) / 16, 8));
         gemv_t_kernel<T><<<dim3((m + 31) / 32, (B + rpb - 1) / rpb), dim3(32, 8), 0, st()>>>(L.V, ldm, gmu + (size_t)q * ldB, B, m, rpb, L.v1); }
@@ -769,6 +780,7 @@ struct Engine : EngineBase {
       ph_end();
       if (prec == AGP_PREC_TF32X3) {
         ph_begin(PH_SPLIT);
+        umma_set_pdl(tail_pdl && !prof);
         CKS(umma_scale_transpose(ctx_err(), L.um, (const float*)(const void*)L.V, gS + (size_t)q * ldB, rho, gmu + (size_t)q * ldB, L.v1, B, m, st()));
         ++launches;
         ph_end();
@@ -777,6 +789,7 @@ struct Engine : EngineBase {
       int ns = n_split;
       if (prec == AGP_PREC_TF32X3) {
         CKS(umma_gram(ctx_err(), L.um, (float*)(void*)L.Gpart, B, m, &ns, st()));
+        umma_set_pdl(false);
         ++launches;
       } else {
         GemmParams<T> g{};  // rho * V^T diag(grad_Sigma) V  (functions/utils.jl:70-72, whitened), split over the minibatch
@@ -804,13 +817,14 @@ struct Engine : EngineBase {
       tp.v1 = L.v1; tp.mu0v = L.mu0v; tp.eta1 = L.eta1v; tp.eta2 = L.eta2v; tp.P = L.P;
       tp.counters = counters; tp.stochastic = stochastic; tp.rm_kappa = rm_kappa; tp.rm_tau = rm_tau; tp.rho = rho;
       tp.logdet = L.logdetP; tp.status = status;
-      combine_kernel<T><<<grid_mp(), 128, 0, st()>>>(tp, L.Gpart);
+      tp.lr = d_lr; tp.v1_zero = (prec == AGP_PREC_TF32X3) ? L.v1 : nullptr;
+      launch_chain(combine_kernel<T>, grid_mp(), dim3(128), 0, tp, (const T*)L.Gpart);
       ++launches;
       ph_end();
       CKS(eta_to_moments(L));
     }
     ph_begin(PH_FINAL);
-    bump_counters_kernel<<<1, 32, 0, st()>>>(counters, 1, 1);
+    launch_chain(bump_counters_kernel, dim3(1), dim3(32), 0, counters, 1, 1);
     ++launches;
     ph_end();
     CK(cudaGetLastError());
@@ -820,6 +834,17 @@ struct Engine : EngineBase {
 
   // agp_tail2.cuh kernels are chained with programmatic dependent launch: block step k+1 becomes resident while step k
   // runs and waits in griddepcontrol.wait, which hides most of the ~2 us launch gap between the 9 dependent launches
+  // kernels of the per-step critical chain whose in-stream predecessor is a kernel: launched with the programmatic
+  // stream serialization attribute (they all start with pdl_prologue())
+  template <typename K, typename... Args>
+  void launch_chain(K kern, dim3 grid, dim3 block, size_t smem, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st();
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = (tail_pdl && !prof) ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, args...);
+  }
   template <typename K>
   void launch_tail2(K kern, int grid, const TailStepParams& tp) {
     cudaLaunchConfig_t cfg = {};
@@ -860,7 +885,8 @@ struct Engine : EngineBase {
     chol_inv(L);
     ph_begin(PH_FINAL);
     float* hi = nullptr; float* lo = nullptr;
-    x_finalize_kernel<T><<<m, 128, 0, st()>>>(L.Xv, mp, m, L.eta1v, L.Xv_T, ldm, hi, lo, L.tvec);
+    launch_chain(x_finalize_kernel<T>, dim3(m), dim3(128), 0, (const double*)L.Xv, (int64_t)mp, m, (const double*)L.eta1v, L.Xv_T, (int64_t)ldm, hi, lo,
+                 L.tvec);
     ++launches;
     ph_end();
     L.muv_valid = false;
@@ -877,6 +903,7 @@ struct Engine : EngineBase {
 
   void drop_graph() {
     if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
+    if (gexec_b) { cudaGraphExecDestroy(gexec_b); gexec_b = nullptr; }
     gB = -1;
   }
 
@@ -902,6 +929,10 @@ struct Engine : EngineBase {
       if (cudaMemcpyAsync(idx_prev, idx_cur, (size_t)B * 8, cudaMemcpyDeviceToDevice, st()) != cudaSuccess) s = AGP_ERR_CUDA;
       if (s == AGP_OK) s = prep_idx(nullptr, B, 0, 1);          // the cursor is bumped at the end of this step
       if (s == AGP_OK) s = moments_impl(false, B, true, 1);
+      if (s == AGP_OK && prec == AGP_PREC_TF32X3 && Ql == 1) {   // clear the next step's V X^T accumulators off the critical chain
+        if (cudaMemsetAsync(lat[0].racc + ldB, 0, 2 * ldB * sizeof(double), st()) != cudaSuccess) s = AGP_ERR_CUDA;
+        else racc2_precleared = true;
+      }
       if (s == AGP_OK && cudaEventRecord(ev_join, side) != cudaSuccess) s = AGP_ERR_CUDA;
       cur_stream = nullptr;
       if (s != AGP_OK) { if (ctx->err.empty()) ctx->err = "CUDA failure while prefetching"; return s; }
@@ -935,7 +966,7 @@ struct Engine : EngineBase {
       return step_update(rho);
     }
     if (want_graph && !prof && !capturing) {
-      const bool need_prime = pipeline && (!prefetched || curB != B);
+      const bool need_prime = pipeline && (!prefetched || curB != B || (prec == AGP_PREC_TF32X3 && Ql == 1 && !racc2_precleared));
       if (!gexec || gB != B || grho != rho || need_prime) {
         drop_graph();
         if (need_prime) return step_pool(B, rho);  // priming step (brings the pipeline to its steady state); later calls replay the graph
@@ -966,21 +997,64 @@ struct Engine : EngineBase {
     return step_pool(B, rho);
   }
 
+  // host-batch step: the host->device copies are issued eagerly (the source pointers change every call), everything after
+  // them (row conversion, kernel matrices, moments, local updates, natural gradient, tail) is one CUDA graph per
+  // (B, rho, dtype, layout) when agp_use_graph is on
+  int batch_compute(int x_dtype, int x_layout, int B, double rho) {
+    int64_t sld = x_layout == AGP_LAYOUT_ROWMAJOR ? D : B;
+    int bl = (B + 255) / 256;
+    if (x_dtype == AGP_DTYPE_F64) convert_rows_kernel<double, T><<<bl, 256, 0, st()>>>((const double*)stage, x_layout, sld, B, D, Xb, Dp, xxb);
+    else convert_rows_kernel<float, T><<<bl, 256, 0, st()>>>((const float*)stage, x_layout, sld, B, D, Xb, Dp, xxb);
+    ++launches;
+    CKS(step_moments(nullptr, B, 0, true));
+    return step_update(rho);
+  }
   int step_batch(const void* xbh, int x_dtype, int x_layout, const void* const* ybh, int y_kind, int B, double rho) override {
     if (!xbh || !ybh) BAD("null batch");
     if (B < 1 || B > Bcap) BAD("The size of mini-batch is incorrect (negative or bigger than the batch capacity)");
     if (is_lsm != (y_kind == AGP_Y_CLASS)) BAD("label kind does not match the likelihood");
-    CKS(upload_rows(xbh, x_dtype, x_layout, B, 0, B, Xb, xxb));
+    if ((x_dtype != 0 && x_dtype != 1) || (x_layout != 0 && x_layout != 1)) BAD("bad dtype/layout");
+    if (!have_K) { ctx->err = "agp_refresh_K must be called before a step"; return AGP_ERR_STATE; }
+    if (prec == AGP_PREC_TF32X3 && (B % 128)) BAD("TF32X3 precision needs B % 128 == 0");
+    const size_t es = x_dtype == AGP_DTYPE_F64 ? 8 : 4;
+    CKS(ensure_stage((size_t)Bcap * D * 8));     // fixed staging address: the captured graph stays valid
+    CK(cudaMemcpyAsync(stage, xbh, (size_t)B * D * es, cudaMemcpyHostToDevice, st()));
     if (y_kind == AGP_Y_CLASS) CK(cudaMemcpyAsync(ycls, ybh[0], B * sizeof(int), cudaMemcpyHostToDevice, st()));
     else for (int t = 0; t < nT; ++t) CK(cudaMemcpyAsync(yb + (size_t)t * ldB, ybh[t], B * sizeof(double), cudaMemcpyHostToDevice, st()));
-    CKS(step_moments(nullptr, B, 0, true));
-    return step_update(rho);
+    const int key = x_dtype * 2 + x_layout;
+    if (want_graph && !prof && !capturing) {
+      if (gexec_b && (gB_b != B || grho_b != rho || gkey_b != key)) { cudaGraphExecDestroy(gexec_b); gexec_b = nullptr; }
+      if (!gexec_b) {
+        cudaGraph_t graph = nullptr;
+        int64_t l0 = launches;
+        CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+        capturing = true;
+        int s = batch_compute(x_dtype, x_layout, B, rho);
+        capturing = false;
+        cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+        if (s != AGP_OK) { if (graph) cudaGraphDestroy(graph); return s; }
+        CK(ce);
+        g_launches_b = launches - l0;
+        launches = l0;
+        CK(cudaGraphInstantiate(&gexec_b, graph, 0));
+        cudaGraphDestroy(graph);
+        gB_b = B; grho_b = rho; gkey_b = key;
+      }
+      CK(cudaGraphLaunch(gexec_b, ctx->stream));
+      launches += g_launches_b;
+      for (auto& L : lat) L.muv_valid = false;
+      curB = B; cur_from_batch = true; kernel_matrices_stale = false; prefetched = false; have_step = true;
+      return AGP_OK;
+    }
+    return batch_compute(x_dtype, x_layout, B, rho);
   }
 
+  int* h_status = nullptr;   // pinned: one stream synchronisation reads the sticky device status
   int sync_status() override {
+    if (!h_status) CK(cudaMallocHost((void**)&h_status, sizeof(int)));
+    CK(cudaMemcpyAsync(h_status, status, sizeof(int), cudaMemcpyDeviceToHost, st()));
     CK(cudaStreamSynchronize(st()));
-    int s = 0;
-    CK(cudaMemcpy(&s, status, sizeof(int), cudaMemcpyDeviceToHost));
+    int s = *h_status;
     if (s) {
       CK(cudaMemset(status, 0, sizeof(int)));
       if (s & ST_NOT_POSDEF) { ctx->err = "PosDefException: matrix is not positive definite; Cholesky factorization failed."; return AGP_ERR_NOT_POSDEF; }
@@ -1047,14 +1121,14 @@ struct Engine : EngineBase {
     }
     // canonical from whitened, fp64:  mu = L mu_v,  Sigma = L Sigma_v L^T,  eta1 = L^-T eta1_v,  eta2 = L^-T eta2_v L^-1
     if (eta1 || eta2) canonicalize(L);
-    if (mu) { ensure_muv(L); symv_kernel<<<(m * 32 + 255) / 256, 256, 0, st()>>>(L.Lc, mp, m, L.muv, L.v1); ++launches; }
+    if (mu) { ensure_muv(L); symv_kernel<<<(m * 32 + 255) / 256, 256, 0, st()>>>(L.Lc, mp, m, L.muv, L.mu0 + mp); ++launches; }  // scratch behind mu0
     if (Sigma) {
       dgemm(true, true, L.Xv, L.Xv, L.X, 1.0, 0.0);        // Sigma_v = X^T X
       dgemm(false, false, L.X, L.Lc, L.W, 1.0, 0.0);       // W = Sigma_v L^T   (NT)
       dgemm(false, true, L.Lc, L.W, L.X, 1.0, 0.0);        // Sigma = L W
     }
     CK(cudaStreamSynchronize(st()));
-    if (mu) CK(cudaMemcpy(mu, L.v1, m * 8, cudaMemcpyDeviceToHost));
+    if (mu) CK(cudaMemcpy(mu, L.mu0 + mp, m * 8, cudaMemcpyDeviceToHost));
     if (eta1) CK(cudaMemcpy(eta1, L.eta1c, m * 8, cudaMemcpyDeviceToHost));
     if (Sigma) CKS(copy_mat(L.X, Sigma));
     if (eta2) CKS(copy_mat(L.eta2c, eta2));
@@ -1255,6 +1329,8 @@ struct Engine : EngineBase {
     cudaFree(xxr);
     *ms_out = (double)ms / reps;
     // Knm / V / accumulators now hold scratch values: re-prime the pipeline before the next step / ELBO
+    cudaMemsetAsync(L.v1, 0, m * sizeof(double), st());
+    racc2_precleared = false;
     kernel_matrices_stale = true;
     if (prefetched) {  // fall back to the last consumed minibatch (same as predict_f)
       prefetched = false;

@@ -12,6 +12,13 @@ namespace agp {
 // sticky device status bits (read back by agp_sync)
 enum : int { ST_KTILDE = 1, ST_NOT_POSDEF = 2 };
 
+// Programmatic dependent launch (griddepcontrol).  Kernels on the per-step critical chain call pdl_prologue() first:
+// launch_dependents lets the NEXT kernel of the chain become resident while this one runs, wait blocks until the
+// PREVIOUS kernel has completed and its writes are visible.  Both are no-ops for a launch without the PDL attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() { pdl_launch_dependents(); pdl_wait(); }
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -123,6 +130,7 @@ __global__ void rowstats_kernel(const T* __restrict__ V, const T* __restrict__ V
 __global__ void rowfinish_kernel(const double* __restrict__ sumsq_v, const double* __restrict__ sumsq_vs, const double* __restrict__ dot_vs,
                                  int B, double kdiag_jit, double* __restrict__ Ktilde, double* __restrict__ mean_f,
                                  double* __restrict__ var_f, int* __restrict__ status, int compute_ktilde) {
+  pdl_prologue();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   double kt;
@@ -202,6 +210,8 @@ struct LikParams {
   double* lam; double* lamacc;
   const double* qnodes; const double* qweights; int nq;      // Gauss-Hermite rule of `expectation` (functions/utils.jl:16-19)
   int need_reduce;                                           // some task accumulates into lamacc
+  // Robbins-Monro step size of THIS iteration (inference/optimisers.jl:14-19), written once per step for combine_kernel
+  double* lr_out; const int64_t* counters; int stochastic; double rm_kappa, rm_tau;
 };
 
 // E[logistic(f)], f ~ N(mu, var), by the Gauss-Hermite rule (functions/utils.jl:16-19)
@@ -373,7 +383,9 @@ __device__ __forceinline__ void lik_update_sample(const LikParams& p, int b, dou
 }
 
 __global__ void lik_update_kernel(const LikParams p) {
+  pdl_prologue();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b == 0 && p.lr_out && p.update) *p.lr_out = p.stochastic ? pow(p.rm_tau + (double)p.counters[0], -p.rm_kappa) : 1.0;
   double r0 = 0.0, r1 = 0.0;
   if (b < p.B) lik_update_sample(p, b, r0, r1);
   if (!p.need_reduce || !p.update || p.model_kind != 0) return;   // uniform
@@ -393,6 +405,7 @@ __global__ void lik_update_kernel(const LikParams p) {
 // re-estimation of the link parameter lambda at the end of local_updates! (poisson.jl:80, heteroscedastic.jl:98);
 // one thread per task, accumulators cleared for the next step
 __global__ void lik_lambda_kernel(const LikParams p) {
+  pdl_prologue();
   int t = threadIdx.x;
   if (t >= p.n_task) return;
   int kind = p.lik_kind[t];
@@ -403,6 +416,7 @@ __global__ void lik_lambda_kernel(const LikParams p) {
 
 // grad_E_mu / grad_E_Sigma of the heteroscedastic likelihood (heteroscedastic.jl:111-127) with the NEW lambda
 __global__ void hetero_grad_kernel(const LikParams p) {
+  pdl_prologue();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= p.B) return;
   const int64_t ld = p.ldB;
@@ -544,6 +558,8 @@ struct TailParams {
   const double* mu0v;   // L^-1 mu0 (whitened prior mean)
   double* eta1; double* eta2; double* P;
   const int64_t* counters;  // [0] = Robbins-Monro t (starts at 1)
+  const double* lr;         // step size of this iteration (written by lik_update_kernel)
+  double* v1_zero;          // non-null: clear V^T grad_mu after use (the next step accumulates into it without a memset)
   int stochastic; double rm_kappa, rm_tau, rho;
   double* logdet; int* status;
 };
@@ -554,11 +570,11 @@ struct TailParams {
 // (inference.jl:26).  G is symmetrised from its upper triangle like Julia's Symmetric() (analyticVI.jl:238, Q5).
 template <typename TG>
 __global__ void combine_kernel(const TailParams p, const TG* __restrict__ Gpart) {
+  pdl_prologue();
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   int i = blockIdx.y;
   if (j >= p.mp) return;
-  double lr = 1.0;
-  if (p.stochastic) lr = pow(p.rm_tau + (double)p.counters[0], -p.rm_kappa);
+  const double lr = *p.lr;
   if (i >= p.m || j >= p.m) {
     p.P[(int64_t)i * p.ld + j] = (i == j) ? 1.0 : 0.0;
     return;
@@ -580,6 +596,7 @@ __global__ void combine_kernel(const TailParams p, const TG* __restrict__ Gpart)
     double e1 = p.eta1[j];
     double d1 = p.rho * p.v1[j] + p.mu0v[j] - e1;
     p.eta1[j] = e1 + lr * d1;
+    if (p.v1_zero) p.v1_zero[j] = 0.0;
     if (j == 0) *p.logdet = 0.0;
   }
 }
@@ -706,6 +723,7 @@ __global__ void scale_pad_kernel(const double* __restrict__ src, double* __restr
 }
 
 __global__ void bump_counters_kernel(int64_t* counters, int bump_t, int bump_cursor) {
+  pdl_prologue();
   if (threadIdx.x == 0 && blockIdx.x == 0) { counters[0] += bump_t; counters[1] += bump_cursor; }
 }
 

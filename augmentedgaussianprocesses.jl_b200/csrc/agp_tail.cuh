@@ -386,6 +386,7 @@ template <typename T>
 __global__ void x_finalize_kernel(const double* __restrict__ X, int64_t ld, int m, const double* __restrict__ eta1v,
                                   T* __restrict__ shadow, int64_t lds, float* __restrict__ hi, float* __restrict__ lo,
                                   double* __restrict__ tvec) {
+  pdl_prologue();
   const int i = blockIdx.x;
   double s = 0.0;
   for (int j = threadIdx.x; j < m; j += blockDim.x) {

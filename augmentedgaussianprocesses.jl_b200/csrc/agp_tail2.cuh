@@ -25,10 +25,6 @@ constexpr int T2SL = 20;                 // leading dimension of the 64 x 16 pan
 constexpr int T2_TILE = TNB * T2LD;      // doubles per tile buffer
 constexpr int TAIL2_SMEM = (5 * T2_TILE + TNB * T2SL + 2 * 16 + 16 + TNB + 8) * (int)sizeof(double);
 
-// programmatic dependent launch (griddepcontrol): no-ops when the kernel was launched without the attribute
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }

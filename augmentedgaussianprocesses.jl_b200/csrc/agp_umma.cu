@@ -118,6 +118,9 @@ umma_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // programmatic dependent launch: barrier init / TMEM allocation above overlap the previous kernel of the chain
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == 0) {
     if (lane == 0) {
@@ -296,6 +299,8 @@ __global__ void __launch_bounds__(256) scale_transpose_kernel(const float* __res
   __shared__ float sw[128];
   __shared__ double sg[128];
   __shared__ double red[8][33];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int j0 = blockIdx.x * 32, b0 = blockIdx.y * 128;
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;  // 32 x 8
   if (tid < 128) {
@@ -397,6 +402,19 @@ void umma_latent_free(UmmaLatent& u) {
   u.tmaps = nullptr;
 }
 
+// launches of the per-step chain carry the programmatic-stream-serialization attribute (umma_set_pdl)
+static bool g_pdl = false;
+void umma_set_pdl(bool on) { g_pdl = on; }
+template <typename K, typename... Args>
+static void launch_chain(K kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = g_pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 static int sm_count() {
   static int n = 0;
   if (!n) {
@@ -417,7 +435,7 @@ int umma_gemm_nt(std::string* err, UmmaLatent& u, int a_which, int b_which, floa
   w.total_kb = u.m / BK; w.kb_per_split = w.total_kb;
   w.tri_mode = (b_which == UM_LINV || b_which == UM_X) ? 1 : 0;
   const int grid = w.total < sm_count() ? w.total : sm_count();
-  umma_gemm_nt_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mp->raw[a_which], mp->raw[b_which], C, (int64_t)u.ldm, 0, w, ep);
+  launch_chain(umma_gemm_nt_kernel, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, mp->raw[a_which], mp->raw[b_which], C, (int64_t)u.ldm, (int64_t)0, w, ep);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(err, "umma_gemm_nt_kernel", e);
   return 0;
@@ -426,7 +444,7 @@ int umma_gemm_nt(std::string* err, UmmaLatent& u, int a_which, int b_which, floa
 int umma_scale_transpose(std::string* err, UmmaLatent& u, const float* V, const double* w, double rho, const double* g, double* v1,
                          int B, int m, cudaStream_t st) {
   if (B % BM || m % BN) return fail(err, "shape not a multiple of the tile");
-  scale_transpose_kernel<<<dim3(m / 32, B / 128), dim3(32, 8), 0, st>>>(V, u.ldm, w, rho, u.UT, u.Bcap, g, v1);
+  launch_chain(scale_transpose_kernel, dim3(m / 32, B / 128), dim3(32, 8), 0, st, V, (int64_t)u.ldm, w, rho, u.UT, (int64_t)u.Bcap, g, v1);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(err, "scale_transpose_kernel", e);
   return 0;
@@ -449,7 +467,7 @@ int umma_gram(std::string* err, UmmaLatent& u, float* Gpart, int B, int m, int* 
   const int grid = w.total < sm_count() ? w.total : sm_count();
   UmmaEpilogue ep{};
   ep.mode = UMMA_EPI_STORE_MIRROR;
-  umma_gemm_nt_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mp->ut, mp->ut, Gpart, (int64_t)u.ldm, (int64_t)m * u.ldm, w, ep);
+  launch_chain(umma_gemm_nt_kernel, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, mp->ut, mp->ut, Gpart, (int64_t)u.ldm, (int64_t)m * u.ldm, w, ep);
   *n_split = S;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(err, "umma gram", e);

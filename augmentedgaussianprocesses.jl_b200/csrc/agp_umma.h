@@ -40,6 +40,8 @@ int umma_gemm_nt(std::string* err, UmmaLatent& u, int a_which, int b_which, floa
 int umma_scale_transpose(std::string* err, UmmaLatent& u, const float* V, const double* w, double rho, const double* g, double* v1,
                          int B, int m, cudaStream_t st);
 // Gpart[s] = sum_{b in split s} U_b U_b^T (full symmetric tiles) ; *n_split in: capacity, out: used
+// per-step chain launches carry the programmatic-dependent-launch attribute when on (set per call site by the engine)
+void umma_set_pdl(bool on);
 int umma_gram(std::string* err, UmmaLatent& u, float* Gpart, int B, int m, int* n_split, cudaStream_t st);
 
 // ---- K_nm construction on the tensor core (agp_knm.cu) ----

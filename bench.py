@@ -287,6 +287,7 @@ def run_ours(args, rank, world, local_rank):
         import ctypes as C
 
         mu = np.empty(m)
+        eng.ck(lib.agp_use_graph(eng.model, 1 if args.graph else 0))   # public switch: the compute part of a host-batch step replays one CUDA graph
         def e2e_step(i):
             arr = (C.c_void_p * 1)(yb[i].data_ptr())
             eng.ck(lib.agp_step_batch(eng.model, C.c_void_p(xb[i].data_ptr()), L.DTYPE_F64, L.LAYOUT_ROWMAJOR, arr, L.Y_REAL, B, rho))

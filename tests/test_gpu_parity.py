@@ -254,6 +254,54 @@ def test_full_size_properties(agp):
     assert rel_fro(posts[1][0], posts[0][0]) < 1e-9 and rel_fro(posts[1][1], posts[0][1]) < 1e-9
 
 
+@pytest.mark.parametrize("cfg", ["C3", "C4", "C5"])
+def test_baseline_configs_full_step_size_vs_oracle(agp, cfg):
+    """BASELINE.json configs[2..4] at their full per-step sizes (m, D, B, likelihood, kernel; fewer rows n, the step cost is
+    n-independent), tcgen05 path, 2 stochastic iterations against the fp64 oracle.  Tolerance 5e-4 (tf32x3) on mu, Sigma, ELBO.
+      C3: SVGP StudentT(nu=3) Matern-3/2, D=64, m=1024, minibatch=16384
+      C4: LogisticSoftMax 8 classes, D=128, m=256 per class, minibatch=8192
+      C5: multi-output SVGP, Logistic tasks, D=32, m=512, minibatch=8192 -- 8 latents / 8 tasks = one GPU's share of the 64"""
+    rng = np.random.default_rng(5)
+    iters, tol = 2, TOL["tf32x3"]
+    if cfg == "C3":
+        n, D, m, B = 40_000, 64, 1024, 16384
+        X = rng.standard_normal((n, D)).astype(np.float32).astype(np.float64)
+        f = np.sin(X[:, 0]) + 0.5 * X[:, 1]
+        y = f + 0.1 * rng.standard_t(3.0, n)
+        Z = X[rng.permutation(n)[:m]].copy()
+        mbs = [rng.choice(n, B, replace=False).astype(np.int64) for _ in range(iters)]
+        sc = 1.0 / np.sqrt(D)
+        mo = O.SVGP(O.Kernel("matern32", scale=sc), O.StudentTLikelihood(3.0, 1.0), O.AnalyticSVI(B), Z)
+        me = agp.SVGP(agp.Matern32Kernel() @ agp.ScaleTransform(sc), agp.StudentTLikelihood(3.0, 1.0), agp.AnalyticSVI(B), Z, precision="tf32x3")
+        ydat = y
+    elif cfg == "C4":
+        n, D, m, B, K = 30_000, 128, 256, 8192, 8
+        X = rng.standard_normal((n, D)).astype(np.float32).astype(np.float64)
+        y = np.argmax(X @ rng.standard_normal((D, K)) + 0.1 * rng.standard_normal((n, K)), axis=1) + 1
+        Z = X[rng.permutation(n)[:m]].copy()
+        mbs = [rng.choice(n, B, replace=False).astype(np.int64) for _ in range(iters)]
+        sc = 1.0 / np.sqrt(D)
+        mo = O.SVGP(O.Kernel("sqexp", scale=sc), O.LogisticSoftMaxLikelihood(K), O.AnalyticSVI(B), Z)
+        me = agp.SVGP(agp.SqExponentialKernel() @ agp.ScaleTransform(sc), agp.LogisticSoftMaxLikelihood(K), agp.AnalyticSVI(B), Z, precision="tf32x3")
+        ydat = y
+    else:
+        n, D, m, B, Q = 30_000, 32, 512, 8192, 8
+        X = rng.standard_normal((n, D)).astype(np.float32).astype(np.float64)
+        W = rng.standard_normal((D, Q))
+        ydat = [np.where(X @ W[:, t] + 0.1 * rng.standard_normal(n) >= 0, 1.0, -1.0) for t in range(Q)]
+        Zs = [X[rng.permutation(n)[:m]].copy() for _ in range(Q)]
+        A = rng.standard_normal((Q, Q))
+        A /= np.linalg.norm(A, axis=1, keepdims=True)
+        mbs = [rng.choice(n, B, replace=False).astype(np.int64) for _ in range(iters)]
+        sc = 1.0 / np.sqrt(D)
+        mo = O.MOSVGP(O.Kernel("sqexp", scale=sc), [O.LogisticLikelihood() for _ in range(Q)], O.AnalyticSVI(B), Zs, A)
+        me = agp.MOSVGP(agp.SqExponentialKernel() @ agp.ScaleTransform(sc), [agp.LogisticLikelihood() for _ in range(Q)], agp.AnalyticSVI(B),
+                        Zs, A=A, precision="tf32x3")
+    mo, so = O.train(mo, X, ydat, iters, minibatches=mbs)
+    me, se = agp.train(me, X.astype(np.float32), ydat, iters, minibatches=mbs)
+    check_pair(agp, (mo, so), (me, se), tol)
+
+
 @pytest.mark.parametrize("precision", ["f64", "tf32x3"])
 def test_pipelined_pool_steps_match_host_list_steps(agp, precision):
     """resident-list steps are software-pipelined (next minibatch's Knm / V built on a side stream during the tail) and
