@@ -356,7 +356,8 @@ struct Engine : EngineBase {
     CKS(dalloc(&ycls, ldB));
     CKS(dalloc(&d_out, 8));
     CKS(dalloc(&d_lr, 1));
-    { double one = 1.0; CK(cudaMemcpyAsync(d_lr, &one, 8, cudaMemcpyHostToDevice, st())); }
+    CK(cudaStreamSynchronize(st()));
+    CKS(upload_lr(1));
     CKS(dalloc(&d_lam, nT)); CKS(dalloc(&d_lamacc, 2 * (size_t)nT)); CKS(dalloc(&d_qnodes, 128)); CKS(dalloc(&d_qw, 128));
     CK(cudaMemcpyAsync(d_lam, h_p0.data(), nT * sizeof(double), cudaMemcpyHostToDevice, st()));
     CKS(reset_local_vars());
@@ -611,12 +612,19 @@ struct Engine : EngineBase {
     return s;
   }
 
+  // d_lr holds the step size of the UPCOMING iteration: lr = (tau + t)^-kappa (optimisers.jl:14-19), 1 for AnalyticVI
+  int upload_lr(int64_t t) {
+    double lr = stochastic ? std::pow(rm_tau + (double)t, -rm_kappa) : 1.0;
+    CK(cudaMemcpy(d_lr, &lr, 8, cudaMemcpyHostToDevice));
+    return AGP_OK;
+  }
   int state_reset() override {
     int64_t c[2];
     CK(cudaStreamSynchronize(st()));
     CK(cudaMemcpy(c, counters, 16, cudaMemcpyDeviceToHost));
     c[0] = 1;
     CK(cudaMemcpy(counters, c, 16, cudaMemcpyHostToDevice));
+    CKS(upload_lr(1));
     curB = 0; have_step = false;
     return reset_local_vars();
   }
@@ -733,7 +741,6 @@ struct Engine : EngineBase {
     p.y_all = y_all; p.n = n; p.ycls_all = ycls_all; p.idx = from_batch ? nullptr : idx_cur;
     p.yb = yb; p.ycls = ycls; p.c = lc; p.theta = ltheta; p.gamma = lgamma_; p.alpha = lalpha;
     p.tmu = tmu; p.tvar = tvar; p.gm = gm; p.gs = gs; p.gmu = gmu; p.gS = gS; p.update = update;
-    p.lr_out = d_lr; p.counters = counters; p.stochastic = stochastic; p.rm_kappa = rm_kappa; p.rm_tau = rm_tau;
     p.lam = d_lam; p.lamacc = d_lamacc; p.qnodes = d_qnodes; p.qweights = d_qw; p.nq = nq; p.need_reduce = need_lam ? 1 : 0;
     return p;
   }
@@ -821,7 +828,7 @@ struct Engine : EngineBase {
       launch_chain(combine_kernel<T>, grid_mp(), dim3(128), 0, tp, (const T*)L.Gpart);
       ++launches;
       ph_end();
-      CKS(eta_to_moments(L));
+      CKS(eta_to_moments(L, q == Ql - 1));   // the last latent's finalize kernel also prepares the next step size
     }
     ph_begin(PH_FINAL);
     launch_chain(bump_counters_kernel, dim3(1), dim3(32), 0, counters, 1, 1);
@@ -881,12 +888,12 @@ struct Engine : EngineBase {
 
   // global_update!(gp) (inference/inference.jl:25-28) in the whitened basis: Sigma_v = inv(P_v) = X^T X is kept in
   // factored form (X = chol(P_v)^-1), mu_v = Sigma_v eta1_v = X^T (X eta1_v)
-  int eta_to_moments(Latent& L) {
+  int eta_to_moments(Latent& L, bool in_step = false) {
     chol_inv(L);
     ph_begin(PH_FINAL);
     float* hi = nullptr; float* lo = nullptr;
     launch_chain(x_finalize_kernel<T>, dim3(m), dim3(128), 0, (const double*)L.Xv, (int64_t)mp, m, (const double*)L.eta1v, L.Xv_T, (int64_t)ldm, hi, lo,
-                 L.tvec);
+                 L.tvec, (in_step && stochastic) ? d_lr : (double*)nullptr, (const int64_t*)counters, rm_kappa, rm_tau);
     ++launches;
     ph_end();
     L.muv_valid = false;
@@ -1160,6 +1167,7 @@ struct Engine : EngineBase {
     prefetched = false; drop_graph();
     CK(cudaStreamSynchronize(st()));
     CK(cudaMemcpy(counters, c, 16, cudaMemcpyHostToDevice));
+    CKS(upload_lr(t));
     return AGP_OK;
   }
   int get_local(const char* name, int row, double* out, int B) override {

@@ -210,8 +210,6 @@ struct LikParams {
   double* lam; double* lamacc;
   const double* qnodes; const double* qweights; int nq;      // Gauss-Hermite rule of `expectation` (functions/utils.jl:16-19)
   int need_reduce;                                           // some task accumulates into lamacc
-  // Robbins-Monro step size of THIS iteration (inference/optimisers.jl:14-19), written once per step for combine_kernel
-  double* lr_out; const int64_t* counters; int stochastic; double rm_kappa, rm_tau;
 };
 
 // E[logistic(f)], f ~ N(mu, var), by the Gauss-Hermite rule (functions/utils.jl:16-19)
@@ -385,7 +383,6 @@ __device__ __forceinline__ void lik_update_sample(const LikParams& p, int b, dou
 __global__ void lik_update_kernel(const LikParams p) {
   pdl_prologue();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b == 0 && p.lr_out && p.update) *p.lr_out = p.stochastic ? pow(p.rm_tau + (double)p.counters[0], -p.rm_kappa) : 1.0;
   double r0 = 0.0, r1 = 0.0;
   if (b < p.B) lik_update_sample(p, b, r0, r1);
   if (!p.need_reduce || !p.update || p.model_kind != 0) return;   // uniform

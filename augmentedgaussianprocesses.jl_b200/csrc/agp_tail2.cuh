@@ -171,10 +171,21 @@ __device__ __forceinline__ void tile2_potf2_inv(double* sa, double* sx, double* 
         if (arow && rr <= j) g = 0.0;            // rows at or above the pivot are not touched
 #pragma unroll
         for (int q = j + 1; q < 16; ++q) x[q] = fma(cj[q], g, x[q]);   // a_rq -= a_rj a_qj / d | w_qr -= a_qj w_jr / d
-        rsv[j] = rsqrt(d);                       // off the chain: fills the latency bubbles
+        rsv[j] = d;
         if (lane == j) dvals[c0 + j] = d;
       }
       if (bad && lane == 0) atomicOr(status, ST_NOT_POSDEF);
+      // d^-1/2 for the row scaling, branch-free (library rsqrt() carries a slow-path branch per call, and basic-block
+      // boundaries inside the pivot loop stop the scheduler from interleaving the chains): MUFU.RSQ64H + two Newton steps
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        double y;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(rsv[q]));
+        double e = fma(-rsv[q] * y, y, 1.0);
+        y = fma(0.5 * y, e, y);
+        e = fma(-rsv[q] * y, y, 1.0);
+        rsv[q] = fma(0.5 * y, e, y);
+      }
       // X_JJ = diag(d)^-1/2 W  (rows of W scaled)
       if (!arow) {
 #pragma unroll

@@ -263,16 +263,29 @@ def run_ours(args, rank, world, local_rank):
         kern = {k: dict(seconds_per_launch=tk[k], algorithmic_flops_per_launch=fl[k], achieved=fl[k] / tk[k] / 1e12, peak=peak,
                         unit="TFLOP/s", frac=fl[k] / tk[k] / 1e12 / peak, tensor_pipe_frac_3xtf32=3 * fl[k] / tk[k] / 1e12 / peak *
                         ((m // 128 + 1) / (2.0 * (m // 128)) if k == "gemm_gram" else 1.0)) for k in fl}
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this same command
+        # (profiles/r1/ncu_traffic.json, written by profiles/extract_ncu.py); null when the file is absent
+        traffic = {}
+        tf = os.path.join(ROOT, "profiles", "r1", "ncu_traffic.json")
+        if os.path.exists(tf):
+            try:
+                traffic = json.load(open(tf))
+            except Exception:
+                traffic = {}
+        for k_ in kern:
+            kern[k_]["traffic"] = traffic.get(k_)
         top = max(fl, key=lambda k: tk[k])
         roof = dict(bound="tensor", kernel=top, achieved=kern[top]["achieved"], peak=peak, unit="TFLOP/s", frac=kern[top]["frac"],
-                    traffic=None, peak_source=psrc, algorithmic_flops_per_launch=fl[top],
+                    traffic=traffic.get(top), traffic_source="profiles/r1/ncu_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)" if traffic else None,
+                    peak_source=psrc, algorithmic_flops_per_launch=fl[top],
                     timing=f"{reps} back-to-back launches between one CUDA-event pair on the launching stream", kernels=kern)
         byts = 4.0 * (B * D + m * D + B * m) + 8.0 * B
         hbm = peaks.get("hbm_gbs", 6650.0)
         roof["knm"] = dict(bound="hbm", kernel="knm_umma_kernel", seconds_per_launch=tk["kmat_knm"], achieved=byts / tk["kmat_knm"] / 1e9, peak=hbm,
                            unit="GB/s", frac=byts / tk["kmat_knm"] / 1e9 / hbm, algorithmic_bytes_per_launch=byts,
                            peak_source="MEASURED_PEAKS.json hbm_gbs, of measured" if "hbm_gbs" in peaks else "fallback 6.65 TB/s, of fallback",
-                           traffic=None)
+                           traffic=traffic.get("kmat_knm"),
+                           note="at C2 the 16.8 MB K_nm output stays in the 126 MB L2 (write-back), so DRAM traffic is far below the algorithmic bytes")
 
     # ---------------- end-to-end through the host-buffer API ----------------
     e2e = None

@@ -15,6 +15,6 @@ cat $OUT/bench.json
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 150 -c 210 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 14 --warmup 3 --graph 0 --timed-only > $OUT/ncu_launch.log 2>&1; echo "ncu launches rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on \
-    -k regex:'tail_step_kernel|umma_gemm_nt_kernel|knm_umma_kernel|tail_potf2_first_kernel|combine_kernel' -s 60 -c 14 \
+    -k regex:'tail2_step_kernel|umma_gemm_nt_kernel|knm_umma_kernel|tail2_potf2_first_kernel|combine_kernel|scale_transpose_kernel' -s 60 -c 15 \
     -o $OUT/prof python bench.py --steps 6 --warmup 3 --graph 0 --timed-only > $OUT/ncu_full.log 2>&1; echo "ncu full rc=$?"
 ls -la $OUT
