@@ -44,6 +44,18 @@ lik_code(::AGP.GaussianLikelihood) = (Int32(0))
 lik_code(::AGP.BernoulliLikelihood{<:AGP.LogisticLink}) = Int32(1)
 lik_code(::AGP.StudentTLikelihood) = Int32(2)
 lik_code(::AGP.MultiClassLikelihood{<:AGP.LogisticSoftMaxLink}) = Int32(3)
+lik_code(::AGP.LaplaceLikelihood) = Int32(4)
+lik_code(::AGP.BernoulliLikelihood{<:AGP.SVMLink}) = Int32(5)
+lik_code(::AGP.NegBinomialLikelihood) = Int32(6)
+lik_code(::AGP.PoissonLikelihood{<:AGP.ScaledLogistic}) = Int32(7)
+lik_code(::AGP.HeteroscedasticGaussianLikelihood{<:AGP.InvScaledLogistic}) = Int32(8)
+# first likelihood parameter crossing the ABI (include/agp_b200.h: AGP_LIK_* comments)
+lik_p0(l) = 0.0
+lik_p0(l::AGP.GaussianLikelihood) = Float64(AGP.noise(l))
+lik_p0(l::AGP.StudentTLikelihood) = Float64(l.ν)
+lik_p0(l::AGP.LaplaceLikelihood) = Float64(l.β)
+lik_p0(l::AGP.NegBinomialLikelihood) = Float64(l.r)
+lik_p0(l::Union{AGP.PoissonLikelihood,AGP.HeteroscedasticGaussianLikelihood}) = Float64(only(l.invlink.λ))
 
 # kernel -> (kind, scale, variance); supports [σ² *] {SqExponential, Matern32, Matern52} [∘ ScaleTransform(s)]
 function kernel_params(k)
@@ -63,7 +75,7 @@ function engine(model::SVGP{T}, B::Int) where {T}
     kp = [kernel_params(AGP.kernel(gp)) for gp in model.f]
     kk = Int32[p[1] for p in kp]; ks = Float64[p[2] for p in kp]; kv = Float64[p[3] for p in kp]
     lk = Int32[lik_code(l)]
-    p0 = Float64[l isa AGP.GaussianLikelihood ? AGP.noise(l) : l isa AGP.StudentTLikelihood ? l.ν : 0.0]
+    p0 = Float64[lik_p0(l)]
     p1 = Float64[l isa AGP.StudentTLikelihood ? l.σ : 0.0]
     o = AGP.opt(inf).optimiser
     κ, τ = o isa RobbinsMonro ? (Float64(o.κ), Float64(o.τ)) : (0.51, 1.0)
@@ -77,6 +89,11 @@ function engine(model::SVGP{T}, B::Int) where {T}
         check(e, ccall((:agp_model_create, LIB), Cint, (Ptr{Cvoid}, Ref{ModelDesc}, Ref{Ptr{Cvoid}}), e.ctx, d, mdl))
     end
     e.model = mdl[]
+    if l isa AGP.PoissonLikelihood      # `expectation` rule of functions/utils.jl:16-19 (pred_nodes, pred_weights of predictions.jl:4)
+        nodes = collect(Float64, AGP.pred_nodes); w = collect(Float64, AGP.pred_weights)
+        GC.@preserve nodes w check(e, ccall((:agp_set_quadrature, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int32),
+                                            e.model, nodes, w, length(nodes)))
+    end
     ENGINES[model] = e
     return e
 end
@@ -102,8 +119,19 @@ function AGP.update_parameters!(model::SVGP{T,L,<:AnalyticVI}, state, x::SubArra
     ρ = Float64(AGP.ρ(AGP.inference(model)))
     GC.@preserve idx check(e, ccall((:agp_step, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Int32, Int32, Float64),
                                     e.model, idx, B, 1, ρ))
-    pull_posterior!(model, e)                          # keep model.f[k].post in sync for Julia-side consumers
+    pull_posterior!(model, e); pull_lik_params!(model, e)                          # keep model.f[k].post in sync for Julia-side consumers
     return state
+end
+
+# λ of PoissonLikelihood / HeteroscedasticLikelihood is re-estimated on the device by every step (poisson.jl:80,
+# heteroscedastic.jl:98): mirror it back into l.invlink.λ
+function pull_lik_params!(model, e::Engine)
+    l = AGP.likelihood(model)
+    if l isa Union{AGP.PoissonLikelihood,AGP.HeteroscedasticGaussianLikelihood}
+        v = Ref{Float64}(0.0)
+        check(e, ccall((:agp_get_lik_param, LIB), Cint, (Ptr{Cvoid}, Int32, Ref{Float64}), e.model, 0, v))
+        l.invlink.λ .= v[]
+    end
 end
 
 function pull_posterior!(model, e::Engine)
