@@ -9,6 +9,7 @@ fallback.  Reference citations are paths under /root/reference/src.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import math
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
@@ -406,6 +407,15 @@ class AbstractGPModel:
         self.device = device
         self.stream = stream
         self.rank, self.world = shard if shard is not None else (0, 1)
+        if self.world > 1 and self.stream is None:
+            # a sharded model shares the host framework's stream, so that its collectives (NCCL fallback, ELBO all-reduce)
+            # are ordered with the engine's kernels without extra synchronisation
+            try:
+                import torch
+
+                self.stream = torch.cuda.current_stream(device).cuda_stream
+            except Exception:
+                pass
         self._eng: Optional[_Engine] = None
         self._data_key = None
         self._n = 0
@@ -425,6 +435,9 @@ class AbstractGPModel:
             cap = (cap + 127) // 128 * 128
         self._eng = _Engine(self._desc(cap), self.device, self.stream)
         self._data_key = None
+        self._peer = False
+        if self.world > 1 and os.environ.get("AGP_NO_PEER", "0") != "1":
+            self._peer = _attach_peers(self, self._eng)
         if any(l.kind in (L.LIK_POISSON, L.LIK_NEGBINOMIAL, L.LIK_BAYESIANSVM) for l in self.likelihoods):
             nodes, weights = _pred_nodes()   # `expectation` (functions/utils.jl:16-19) / compute_proba rule
             self._eng.ck(self._eng.lib.agp_set_quadrature(self._eng.model, L.dptr(nodes), L.dptr(weights), len(nodes)))
@@ -764,8 +777,32 @@ def _allgather_moments(model, eng):
     _allgather_rows(views, q0, ql, ld)
 
 
+def _attach_peers(model, eng) -> bool:
+    """Exchange the CUDA IPC handles of every rank's moment block over the host process group and attach them
+    (agp_peer_export / agp_peer_attach): afterwards the per-step exchange of (mean_f, var_f) rows runs device-side
+    over NVLink peer memory inside the step.  Returns False (NCCL all-gather fallback) when no process group exists."""
+    try:
+        import torch.distributed as dist
+    except Exception:
+        return False
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() != model.world:
+        return False
+    h = C.create_string_buffer(64)
+    eng.ck(eng.lib.agp_peer_export(eng.model, h))
+    hs = [None] * model.world
+    dist.all_gather_object(hs, bytes(h.raw))
+    blob = C.create_string_buffer(b"".join(hs), 64 * model.world)
+    eng.ck(eng.lib.agp_peer_attach(eng.model, model.world, model.rank, blob))
+    dist.barrier()
+    return True
+
+
 def _sharded_step(model, eng, ip, B, rho):
-    """one-latent(-group)-per-rank step: moments -> NCCL all-gather of (mean_f, var_f) rows -> update."""
+    """one-latent(-group)-per-rank step.  Peer mode: one agp_step_async, the moment rows cross NVLink inside the step.
+    Fallback: moments -> NCCL all-gather of (mean_f, var_f) rows -> update."""
+    if getattr(model, "_peer", False):
+        eng.ck(eng.lib.agp_step_async(eng.model, ip, B, 0, rho))
+        return
     eng.ck(eng.lib.agp_step_moments_async(eng.model, ip, B, 0))
     _allgather_moments(model, eng)
     eng.ck(eng.lib.agp_step_update_async(eng.model, rho))
@@ -786,7 +823,8 @@ def ELBO(model: AbstractGPModel, state: Optional[State] = None, y=None) -> float
         import torch.distributed as dist
 
         eng.ck(eng.lib.agp_elbo_moments_async(eng.model))
-        _allgather_moments(model, eng)
+        if not getattr(model, "_peer", False):
+            _allgather_moments(model, eng)
         eng.ck(eng.lib.agp_elbo(eng.model, rho, L.dptr(out)))
         kl = torch.tensor([out[1]], dtype=torch.float64, device=f"cuda:{model.device}")
         dist.all_reduce(kl)  # the single scalar all-reduce of the north star

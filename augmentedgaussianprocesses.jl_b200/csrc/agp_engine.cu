@@ -85,6 +85,8 @@ struct EngineBase {
   virtual int get_lik_param(int task, double* v) = 0;
   virtual int set_lik_param(int task, double v) = 0;
   virtual int proba_link(int link, double p0, const double* mu, const double* var, int64_t n, double* p, double* pv) = 0;
+  virtual int peer_export(void* handle64) = 0;
+  virtual int peer_attach(int world, int rank, const void* handles) = 0;
   virtual int profile_enable(int on) = 0;
   virtual int profile_read(int maxp, const char** names, double* ms, int64_t* launches) = 0;
   virtual int64_t launch_count() = 0;
@@ -167,6 +169,9 @@ struct Engine : EngineBase {
   double* d_out = nullptr;  // [8] scratch scalars
   int n_split = 1, k_chunk = 0;
   bool tail_pdl = true;  // AGP_TAIL_PDL=0 disables programmatic dependent launch along the per-step kernel chain
+  // latent-sharded peer exchange (agp_peer_export / agp_peer_attach): one exported block [mean 2Q ldB | var 2Q ldB | flags]
+  double* xchg = nullptr; int64_t par_stride = 0; bool peer = false; int peer_world = 1, peer_rank = 0;
+  int64_t* d_xepoch = nullptr; double** d_peers = nullptr; std::vector<void*> peer_opened;
   double* d_lr = nullptr;          // Robbins-Monro step size of the current iteration (lik_update_kernel -> combine_kernel)
   bool racc2_precleared = false;   // the V X^T row-statistic accumulators were cleared off the critical chain (side stream)
   int tail_variant = 3;  // AGP_TAIL_VARIANT: 0-2 = agp_tail.cuh (SIMT tile products), 3 = agp_tail2.cuh (DMMA, panel potf2)
@@ -347,7 +352,10 @@ struct Engine : EngineBase {
     CK(cudaMemcpyAsync(d_p0, h_p0.data(), nT * sizeof(double), cudaMemcpyHostToDevice, st()));
     CK(cudaMemcpyAsync(d_p1, h_p1.data(), nT * sizeof(double), cudaMemcpyHostToDevice, st()));
     if (!h_A.empty()) CK(cudaMemcpyAsync(d_A, h_A.data(), h_A.size() * sizeof(double), cudaMemcpyHostToDevice, st()));
-    CKS(dalloc(&mean_f, (size_t)Qg * ldB)); CKS(dalloc(&var_f, (size_t)Qg * ldB));
+    par_stride = (int64_t)Qg * ldB;
+    CKS(dalloc(&xchg, 4 * (size_t)par_stride + 64));
+    mean_f = xchg; var_f = xchg + 2 * par_stride;   // parity 0 halves; parity 1 (peer mode only) follows each at + par_stride
+    CKS(dalloc(&d_xepoch, 1));
     CKS(dalloc(&gmu, (size_t)Ql * ldB)); CKS(dalloc(&gS, (size_t)Ql * ldB));
     CKS(dalloc(&lc, (size_t)R * ldB)); CKS(dalloc(&ltheta, (size_t)R * ldB)); CKS(dalloc(&lgamma_, (size_t)R * ldB));
     CKS(dalloc(&lalpha, ldB));
@@ -401,11 +409,12 @@ struct Engine : EngineBase {
       umma_latent_free(L.um);
       umma_knm_free(L.uk);
     }
+    for (void* q : peer_opened) cudaIpcCloseMemHandle(q);
     if (side) cudaStreamDestroy(side);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
     void* ps[] = {idx_prev, xx_cur, pKS, pXb, pxxb, X, xx, y_all, ycls_all, Xb, xxb, stage, idx_pool, idx_cur, counters, status, d_lik_kind, d_p0, d_p1, d_A,
-                  mean_f, var_f, gmu, gS, lc, ltheta, lgamma_, lalpha, tmu, tvar, gm, gs, yb, ycls, d_out, d_lam, d_lamacc, d_qnodes, d_qw, d_lr};
+                  xchg, d_xepoch, d_peers, gmu, gS, lc, ltheta, lgamma_, lalpha, tmu, tvar, gm, gs, yb, ycls, d_out, d_lam, d_lamacc, d_qnodes, d_qw, d_lr};
     for (void* p : ps) cudaFree(p);
   }
 
@@ -718,11 +727,13 @@ struct Engine : EngineBase {
       if (prec == AGP_PREC_TF32X3)
         launch_chain(rowfinish_kernel, dim3((B + 255) / 256), dim3(256), 0, (const double*)L.racc, (const double*)(L.racc + ldB),
                      (const double*)(L.racc + 2 * ldB), B, L.variance + jitter, L.Ktilde, mean_out + (size_t)q * out_ld,
-                     var_out + (size_t)q * out_ld, status, fresh_kernel_matrices ? 1 : 0);
+                     var_out + (size_t)q * out_ld, status, fresh_kernel_matrices ? 1 : 0,
+                     (const int64_t*)((peer && mean_out == mean_f + (size_t)qbeg * ldB) ? d_xepoch : nullptr), par_stride);
       else
       rowstats_kernel<T><<<(B * 32 + 255) / 256, 256, 0, st()>>>(L.V, L.VS, L.tvec, B, m, ldm, L.variance + jitter,
                                                                  L.Ktilde, mean_out + (size_t)q * out_ld, var_out + (size_t)q * out_ld,
-                                                                 status, fresh_kernel_matrices ? 1 : 0);
+                                                                 status, fresh_kernel_matrices ? 1 : 0,
+                                                                 (const int64_t*)((peer && mean_out == mean_f + (size_t)qbeg * ldB) ? d_xepoch : nullptr), par_stride);
       ++launches;
       ph_end();
     }
@@ -730,8 +741,46 @@ struct Engine : EngineBase {
     return AGP_OK;
   }
   int moments_impl(bool from_batch, int B, bool fresh, int stages = 3) {
-    return moments_rows(from_batch ? Xb : X, from_batch ? xxb : xx, from_batch ? nullptr : idx_cur, B, fresh,
-                        mean_f + (size_t)qbeg * ldB, var_f + (size_t)qbeg * ldB, ldB, true, stages);
+    CKS(moments_rows(from_batch ? Xb : X, from_batch ? xxb : xx, from_batch ? nullptr : idx_cur, B, fresh,
+                     mean_f + (size_t)qbeg * ldB, var_f + (size_t)qbeg * ldB, ldB, true, stages));
+    if (peer && (stages & 2)) {   // publish the owned rows to every peer, then wait for theirs (device-side, graph-capturable)
+      ph_begin(PH_ROWSTATS);
+      peer_publish_kernel<<<(int)(((int64_t)Ql * B + 255) / 256), 256, 0, st()>>>(d_peers, peer_world, peer_rank, d_xepoch, par_stride, qbeg, Ql, ldB, B);
+      peer_sync_kernel<<<1, 32 * ((peer_world + 31) / 32), 0, st()>>>(d_peers, peer_world, peer_rank, d_xepoch, 4 * par_stride, status);
+      launches += 2;
+      ph_end();
+      CK(cudaGetLastError());
+    }
+    return AGP_OK;
+  }
+
+  // ---- peer exchange set-up (one process per GPU, same node; handles travel through the host's process group) -----------
+  int peer_export(void* handle64) override {
+    if (!handle64) BAD("null handle buffer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, xchg));
+    memcpy(handle64, &h, 64);
+    return AGP_OK;
+  }
+  int peer_attach(int world, int rank, const void* handles) override {
+    if (world < 2 || world > 64 || rank < 0 || rank >= world || !handles) BAD("bad peer group");
+    if (peer) BAD("peers already attached");
+    std::vector<double*> ptrs(world, nullptr);
+    for (int p = 0; p < world; ++p) {
+      if (p == rank) { ptrs[p] = xchg; continue; }
+      cudaIpcMemHandle_t h;
+      memcpy(&h, (const char*)handles + 64 * (size_t)p, 64);
+      void* q = nullptr;
+      CK(cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess));
+      peer_opened.push_back(q);
+      ptrs[p] = (double*)q;
+    }
+    CKS(dalloc(&d_peers, world));
+    CK(cudaMemcpy(d_peers, ptrs.data(), world * sizeof(double*), cudaMemcpyHostToDevice));
+    peer_world = world; peer_rank = rank; peer = true;
+    drop_graph();
+    return AGP_OK;
   }
 
   LikParams lik_params(int B, bool from_batch, int update) {
@@ -741,6 +790,7 @@ struct Engine : EngineBase {
     p.y_all = y_all; p.n = n; p.ycls_all = ycls_all; p.idx = from_batch ? nullptr : idx_cur;
     p.yb = yb; p.ycls = ycls; p.c = lc; p.theta = ltheta; p.gamma = lgamma_; p.alpha = lalpha;
     p.tmu = tmu; p.tvar = tvar; p.gm = gm; p.gs = gs; p.gmu = gmu; p.gS = gS; p.update = update;
+    p.xepoch = peer ? d_xepoch : nullptr; p.par_stride = par_stride;
     p.lam = d_lam; p.lamacc = d_lamacc; p.qnodes = d_qnodes; p.qweights = d_qw; p.nq = nq; p.need_reduce = need_lam ? 1 : 0;
     return p;
   }
@@ -1064,6 +1114,7 @@ struct Engine : EngineBase {
     int s = *h_status;
     if (s) {
       CK(cudaMemset(status, 0, sizeof(int)));
+      if (s & ST_PEER_TIMEOUT) { ctx->err = "peer exchange timed out (a rank of the latent-sharded group did not publish its moments)"; return AGP_ERR_STATE; }
       if (s & ST_NOT_POSDEF) { ctx->err = "PosDefException: matrix is not positive definite; Cholesky factorization failed."; return AGP_ERR_NOT_POSDEF; }
       ctx->err = "K̃ has negative values";
       return AGP_ERR_KTILDE_NONPOS;
@@ -1181,8 +1232,11 @@ struct Engine : EngineBase {
     else if (s == "phi") { base = lc + ldB; rows = 1; if (!is_het) BAD("unknown local variable"); }
     else if (s == "sigma_g") { base = lgamma_ + ldB; rows = 1; if (!is_het) BAD("unknown local variable"); }
     else if (s == "alpha") { base = lalpha; rows = 1; }
-    else if (s == "mean_f") { base = mean_f; rows = Qg; }
-    else if (s == "var_f") { base = var_f; rows = Qg; }
+    else if (s == "mean_f" || s == "var_f") {
+      int64_t xe = 0;
+      if (peer) { CK(cudaStreamSynchronize(st())); CK(cudaMemcpy(&xe, d_xepoch, 8, cudaMemcpyDeviceToHost)); }
+      base = (s == "mean_f" ? mean_f : var_f) + (xe & 1) * par_stride; rows = Qg;
+    }
     else if (s == "grad_mu") { base = gmu; rows = Ql; }
     else if (s == "grad_Sigma") { base = gS; rows = Ql; }
     else if (s == "y") { base = yb; rows = nT; }
@@ -1502,6 +1556,8 @@ int agp_get_Kinv(agp_model* model, int32_t ql, double* Kinv, double* logdetK) { 
 int agp_predict_f(agp_model* model, const void* Xt, int x_dtype, int x_layout, int64_t nt, int want_var, double* mu, double* var) {
   ENG(model); return e->predict_f(Xt, x_dtype, x_layout, nt, want_var, mu, var);
 }
+int agp_peer_export(agp_model* model, void* handle64) { ENG(model); return e->peer_export(handle64); }
+int agp_peer_attach(agp_model* model, int32_t world, int32_t rank, const void* handles) { ENG(model); return e->peer_attach(world, rank, handles); }
 int agp_set_quadrature(agp_model* model, const double* nodes, const double* weights, int32_t n_nodes) {
   ENG(model); return e->set_quadrature(nodes, weights, n_nodes);
 }

@@ -10,7 +10,7 @@
 namespace agp {
 
 // sticky device status bits (read back by agp_sync)
-enum : int { ST_KTILDE = 1, ST_NOT_POSDEF = 2 };
+enum : int { ST_KTILDE = 1, ST_NOT_POSDEF = 2, ST_PEER_TIMEOUT = 4 };
 
 // Programmatic dependent launch (griddepcontrol).  Kernels on the per-step critical chain call pdl_prologue() first:
 // launch_dependents lets the NEXT kernel of the chain become resident while this one runs, wait blocks until the
@@ -88,7 +88,9 @@ __global__ void xx_gather_kernel(const int64_t* __restrict__ idx, int B, const T
 template <typename T>
 __global__ void rowstats_kernel(const T* __restrict__ V, const T* __restrict__ VS, const double* __restrict__ mu, int B, int m,
                                 int64_t ld, double kdiag_jit, double* __restrict__ Ktilde, double* __restrict__ mean_f,
-                                double* __restrict__ var_f, int* __restrict__ status, int compute_ktilde) {
+                                double* __restrict__ var_f, int* __restrict__ status, int compute_ktilde,
+                                const int64_t* __restrict__ xepoch, int64_t par_stride) {
+  if (xepoch) { const int64_t off = ((*xepoch + 1) & 1) * par_stride; mean_f += off; var_f += off; }   // next exchange's buffer
   using VT = typename VecOf<T>::type;
   constexpr int W = VecOf<T>::W;
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -129,8 +131,10 @@ __global__ void rowstats_kernel(const T* __restrict__ V, const T* __restrict__ V
 // finishing step of the fused row statistics (tensor-core path): acc = {sum V^2, sum (VX^T)^2, sum (VX^T) t}
 __global__ void rowfinish_kernel(const double* __restrict__ sumsq_v, const double* __restrict__ sumsq_vs, const double* __restrict__ dot_vs,
                                  int B, double kdiag_jit, double* __restrict__ Ktilde, double* __restrict__ mean_f,
-                                 double* __restrict__ var_f, int* __restrict__ status, int compute_ktilde) {
+                                 double* __restrict__ var_f, int* __restrict__ status, int compute_ktilde,
+                                 const int64_t* __restrict__ xepoch, int64_t par_stride) {
   pdl_prologue();
+  if (xepoch) { const int64_t off = ((*xepoch + 1) & 1) * par_stride; mean_f += off; var_f += off; }   // next exchange's buffer
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   double kt;
@@ -210,7 +214,14 @@ struct LikParams {
   double* lam; double* lamacc;
   const double* qnodes; const double* qweights; int nq;      // Gauss-Hermite rule of `expectation` (functions/utils.jl:16-19)
   int need_reduce;                                           // some task accumulates into lamacc
+  // latent-sharded peer exchange: the moment arrays are double-buffered by exchange parity (see peer_sync_kernel)
+  const int64_t* xepoch; int64_t par_stride;
 };
+__device__ __forceinline__ LikParams lik_resolve(const LikParams& in) {
+  LikParams p = in;
+  if (p.xepoch) { const int64_t off = (*p.xepoch & 1) * p.par_stride; p.mean_f += off; p.var_f += off; }
+  return p;
+}
 
 // E[logistic(f)], f ~ N(mu, var), by the Gauss-Hermite rule (functions/utils.jl:16-19)
 __device__ __forceinline__ double expect_logistic(const double* __restrict__ nodes, const double* __restrict__ w, int nq, double mu, double var) {
@@ -380,8 +391,9 @@ __device__ __forceinline__ void lik_update_sample(const LikParams& p, int b, dou
   }
 }
 
-__global__ void lik_update_kernel(const LikParams p) {
+__global__ void lik_update_kernel(const LikParams p_in) {
   pdl_prologue();
+  const LikParams p = lik_resolve(p_in);
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   double r0 = 0.0, r1 = 0.0;
   if (b < p.B) lik_update_sample(p, b, r0, r1);
@@ -426,10 +438,58 @@ __global__ void hetero_grad_kernel(const LikParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Latent-sharded exchange of the per-sample moments over NVLink peer memory (the only data that crosses GPUs).
+// Every rank owns rows [qbeg, qbeg+Ql) of the [Q][ldB] arrays mean_f / var_f.  The arrays live in one exported allocation
+// per rank:  [mean: 2 x Q x ldB][var: 2 x Q x ldB][flags: 64 x int64], double-buffered by the exchange counter's parity so
+// a rank that runs ahead cannot overwrite moments a slower peer is still reading.
+//   peer_publish_kernel: store my rows of the NEXT parity into every peer's arrays (plain st.global on mapped peer pointers)
+//   peer_sync_kernel   : release-store the new exchange number into my slot of every peer's flag array, bump my counter,
+//                        then acquire-spin until every peer's number has arrived in MY flag array (bounded: ~2 s)
+// No host involvement, no NCCL call on the step path: both kernels are ordinary nodes of the step's CUDA graph.
+// ------------------------------------------------------------------------------------------------
+__global__ void peer_publish_kernel(double* const* __restrict__ peers, int world, int rank, const int64_t* __restrict__ xepoch,
+                                    int64_t par_stride, int qbeg, int Ql, int64_t ldB, int B) {
+  const int64_t par = ((*xepoch + 1) & 1) * par_stride;
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= (int64_t)Ql * B) return;
+  const int64_t off = par + (int64_t)(qbeg + e / B) * ldB + e % B;
+  const double* mine = peers[rank];
+  const double mu = mine[off], var = mine[2 * par_stride + off];
+  for (int p = 0; p < world; ++p) {
+    if (p == rank) continue;
+    double* dst = peers[p];
+    dst[off] = mu;
+    dst[2 * par_stride + off] = var;
+  }
+}
+__global__ void peer_sync_kernel(double* const* __restrict__ peers, int world, int rank, int64_t* __restrict__ xepoch, int64_t flag_off,
+                                 int* __restrict__ status) {
+  const int p = threadIdx.x;
+  const int64_t e = *xepoch + 1;
+  if (p < world && p != rank) {
+    __threadfence_system();
+    int64_t* f = reinterpret_cast<int64_t*>(peers[p] + flag_off) + rank;
+    asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(f), "l"(e) : "memory");
+  }
+  __syncthreads();
+  if (p == 0) *xepoch = e;
+  if (p < world && p != rank) {
+    const int64_t* f = reinterpret_cast<const int64_t*>(peers[rank] + flag_off) + p;
+    const long long t0 = clock64();
+    int64_t v;
+    do {
+      asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+      if (v < e && clock64() - t0 > 4000000000LL) { atomicOr(status, ST_PEER_TIMEOUT); break; }
+    } while (v < e);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // ELBO likelihood terms (inference/analyticVI.jl:255-297): out[0] += expec_loglikelihood (un-scaled),
 // out[2] += AugmentedKL (un-scaled).  Block-reduced, one atomicAdd pair per block.
 // ------------------------------------------------------------------------------------------------
-__global__ void elbo_lik_kernel(const LikParams p, double* __restrict__ out) {
+__global__ void elbo_lik_kernel(const LikParams p_in, double* __restrict__ out) {
+  const LikParams p = lik_resolve(p_in);
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   double e = 0.0, kl = 0.0;
   const int64_t ld = p.ldB;

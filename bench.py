@@ -190,7 +190,8 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    if args.graph and world == 1:
+    peer = bool(getattr(model, "_peer", False))
+    if args.graph and (world == 1 or peer):   # peer mode: the whole sharded step (incl. the NVLink exchange) is one CUDA graph
         eng.ck(lib.agp_use_graph(eng.model, 1))
     for _ in range(W):
         step_async()
@@ -326,9 +327,10 @@ def run_ours(args, rank, world, local_rank):
                     dtype={"f32": "f32 (fp32 SIMT contractions, f64 m x m tail)", "tf32x3": "tf32x3 (tcgen05, f64 m x m tail)", "f64": "f64"}[args.precision],
                     data="synthetic",
                     config=dict(workload=("C2: SVGP Logistic SqExp n=1e6 D=32 m=512 minibatch=8192" if world == 1 else
-                                          f"C2-shaped multi-output SVGP: {world} Logistic tasks x {world} latent GPs, one latent per GPU, moments all-gather per step"),
+                                          f"C2-shaped multi-output SVGP: {world} Logistic tasks x {world} latent GPs, one latent per GPU, "
+                                          + ("per-sample moments exchanged over NVLink peer memory inside the step" if peer else "moments NCCL all-gather per step")),
                                 l2="inputs larger than L2: every step gathers a new random minibatch from the resident 140 MB (X, |x|^2, y) arrays; no flush",
-                                graph=bool(args.graph and world == 1), precision=args.precision, **CFG),
+                                graph=bool(args.graph and (world == 1 or peer)), precision=args.precision, **CFG),
                     gpu_launches=int(launches), elbo_last=elbo, roofline=roof, cpu_baseline=cpu, e2e=e2e, clocks=clocks, phases=phases)
         print(json.dumps(line), flush=True)
     if dist is not None:

@@ -161,6 +161,14 @@ int agp_step_update_async(agp_model* model, double rho);
 /* device pointers + leading dimension of the moment arrays (which: 0 = mean_f, 1 = var_f). */
 void* agp_moments_devptr(agp_model* model, int32_t which, int64_t* ld_out);
 
+/* Device-side exchange over NVLink peer memory (same node, one process per GPU): every rank exports the IPC handle of its
+ * moment block (64 bytes), the host gathers the handles over its process group (rank order) and attaches them.  Afterwards
+ * every agp_step* / agp_elbo_moments_async call publishes the owned rows into all peers' arrays and waits for theirs inside
+ * the step (two small kernels, CUDA-graph capturable): no NCCL call and no host round trip on the step path, and
+ * agp_step / agp_step_async (incl. resident lists + agp_use_graph) become usable on a sharded model. */
+int agp_peer_export(agp_model* model, void* handle64);
+int agp_peer_attach(agp_model* model, int32_t world, int32_t rank, const void* handles /* [world][64] */);
+
 /* ---- ELBO(model, state, y) (inference/analyticVI.jl:255-297) on the last minibatch -----------
  * out[0] = rho * expec_loglikelihood, out[1] = GaussianKL summed over OWNED latents
  * (functions/KLdivergences.jl:2-18), out[2] = rho * AugmentedKL;  ELBO = out[0] - out[1] - out[2]

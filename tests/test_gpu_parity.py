@@ -348,3 +348,23 @@ def test_knm_tensor_core_kernel(agp, D, kind):
     assert km["Knm"].shape == ko["Knm"].shape == (B, m)
     assert np.max(np.abs(km["Knm"] - ko["Knm"])) < 4e-6 * variance
     assert rel_fro(km["Knm"], ko["Knm"]) < 2e-6
+
+
+def test_latent_sharded_two_gpus_match_single_gpu():
+    """latent-sharded run (one rank per GPU, moments exchanged over NVLink peer memory inside the step, and the
+    NCCL all-gather fallback) against the same model on one GPU.  Needs two visible GPUs (skipped otherwise)."""
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for i, extra in enumerate(({}, {"AGP_NO_PEER": "1"})):
+        env = dict(os.environ, **extra)
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                            "--master-port", str(29530 + i), os.path.join(root, "tools", "sharded_parity.py")], env=env, capture_output=True, text=True,
+                           timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        assert r.stdout.count("-> OK") == 2, r.stdout
