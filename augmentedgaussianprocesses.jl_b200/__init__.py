@@ -7,6 +7,7 @@ sm_100a behind the C ABI of include/agp_b200.h); there is no CPU fallback.
 from . import _lib
 from ._lib import AGPError, KtildeError, PosDefException
 from .api import (
+    ADAM,
     AnalyticSVI,
     AnalyticVI,
     ELBO,

@@ -276,6 +276,13 @@ class RobbinsMonro:
         self.kappa, self.tau = float(kappa), float(tau)
 
 
+class ADAM:
+    """Optimisers.jl ADAM(eta = 0.001, beta = (0.9, 0.999)) as accepted by `MOSVGP(...; Aoptimiser)` (MOSVGP.jl:51)."""
+
+    def __init__(self, eta: float = 0.001, beta=(0.9, 0.999), epsilon: float = 1e-8):
+        self.eta, self.beta, self.epsilon = float(eta), (float(beta[0]), float(beta[1])), float(epsilon)
+
+
 class AnalyticVI:
     """inference/analyticVI.jl:1-14.  `AnalyticVI()` = full batch, `AnalyticSVI(B)` = stochastic."""
 
@@ -435,6 +442,9 @@ class AbstractGPModel:
             cap = (cap + 127) // 128 * 128
         self._eng = _Engine(self._desc(cap), self.device, self.stream)
         self._data_key = None
+        ao = getattr(self, "A_opt", None)
+        if ao is not None:
+            self._eng.ck(self._eng.lib.agp_set_A_optimiser(self._eng.model, 1, ao.eta, ao.beta[0], ao.beta[1], ao.epsilon))
         self._peer = False
         if self.world > 1 and os.environ.get("AGP_NO_PEER", "0") != "1":
             self._peer = _attach_peers(self, self._eng)
@@ -535,8 +545,11 @@ class MOSVGP(AbstractGPModel):
                  verbose: int = 0, atfrequency: int = 1, mean=None, optimiser=False, Aoptimiser=False, Zoptimiser=False,
                  T=np.float64, precision: str = "f32", device: int = 0, stream=None, shard=None, rng=None):
         self._common_init(inference, verbose, atfrequency, optimiser, Zoptimiser, T, precision, device, stream, shard)
-        if Aoptimiser not in (None, False):
-            raise NotImplementedError("update_A! (single_and_multi_output_utils.jl:87-118) is not accelerated: pass Aoptimiser=False")
+        if isinstance(Aoptimiser, bool) or Aoptimiser is None:   # MOSVGP.jl:79-81
+            Aoptimiser = ADAM(0.01) if Aoptimiser else None
+        if Aoptimiser is not None and not isinstance(Aoptimiser, ADAM):
+            raise NotImplementedError("only ADAM (the reference default) is implemented for the mixing-matrix optimiser")
+        self.A_opt = Aoptimiser
         if mean is not None:
             raise NotImplementedError("MOSVGP with a non-zero prior mean is not supported")
         self.likelihoods = list(likelihoods)
@@ -558,7 +571,7 @@ class MOSVGP(AbstractGPModel):
             rng = rng or np.random.default_rng()
             A = rng.standard_normal((self.n_task, self.n_latent))
             A /= np.linalg.norm(A, axis=1, keepdims=True)
-        self.A = np.ascontiguousarray(np.asarray(A, dtype=np.float64))
+        self.A = np.array(A, dtype=np.float64, order="C")   # own copy: update_A! refreshes it in place
         if self.A.shape != (self.n_task, self.n_latent):
             raise ValueError("A must be (n_task, n_latent)")
         self.mu0 = None
@@ -733,7 +746,10 @@ def train(model: AbstractGPModel, X, y, iterations: int = 100, *, callback=None,
 
 
 def _refresh_lik_params(model, eng):
-    """read the re-estimated link parameters (λ of Poisson / Heteroscedastic) back into the likelihood objects"""
+    """read the re-estimated link parameters (λ of Poisson / Heteroscedastic) back into the likelihood objects, and the
+    mixing matrix when update_A! is on"""
+    if getattr(model, "A_opt", None) is not None:
+        eng.ck(eng.lib.agp_get_A(eng.model, L.dptr(model.A)))
     for t, l in enumerate(model.likelihoods):
         if l.kind in (L.LIK_POISSON, L.LIK_HETEROSCEDASTIC):
             v = C.c_double(0.0)

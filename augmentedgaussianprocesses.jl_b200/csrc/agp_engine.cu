@@ -85,6 +85,8 @@ struct EngineBase {
   virtual int get_lik_param(int task, double* v) = 0;
   virtual int set_lik_param(int task, double v) = 0;
   virtual int proba_link(int link, double p0, const double* mu, const double* var, int64_t n, double* p, double* pv) = 0;
+  virtual int set_A_optimiser(int kind, double eta, double b1, double b2, double eps) = 0;
+  virtual int get_A(double* A) = 0;
   virtual int peer_export(void* handle64) = 0;
   virtual int peer_attach(int world, int rank, const void* handles) = 0;
   virtual int profile_enable(int on) = 0;
@@ -172,6 +174,9 @@ struct Engine : EngineBase {
   // latent-sharded peer exchange (agp_peer_export / agp_peer_attach): one exported block [mean 2Q ldB | var 2Q ldB | flags]
   double* xchg = nullptr; int64_t par_stride = 0; bool peer = false; int peer_world = 1, peer_rank = 0;
   int64_t* d_xepoch = nullptr; double** d_peers = nullptr; std::vector<void*> peer_opened;
+  // update_A! (MOSVGP Aoptimiser): ADAM state on the device
+  bool a_opt = false; double a_eta = 0.01, a_b1 = 0.9, a_b2 = 0.999, a_eps = 1e-8;
+  double *d_gradA = nullptr, *d_Amt = nullptr, *d_Avt = nullptr, *d_Abt = nullptr;
   double* d_lr = nullptr;          // Robbins-Monro step size of the current iteration (lik_update_kernel -> combine_kernel)
   bool racc2_precleared = false;   // the V X^T row-statistic accumulators were cleared off the critical chain (side stream)
   int tail_variant = 3;  // AGP_TAIL_VARIANT: 0-2 = agp_tail.cuh (SIMT tile products), 3 = agp_tail2.cuh (DMMA, panel potf2)
@@ -414,7 +419,7 @@ struct Engine : EngineBase {
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
     void* ps[] = {idx_prev, xx_cur, pKS, pXb, pxxb, X, xx, y_all, ycls_all, Xb, xxb, stage, idx_pool, idx_cur, counters, status, d_lik_kind, d_p0, d_p1, d_A,
-                  xchg, d_xepoch, d_peers, gmu, gS, lc, ltheta, lgamma_, lalpha, tmu, tvar, gm, gs, yb, ycls, d_out, d_lam, d_lamacc, d_qnodes, d_qw, d_lr};
+                  xchg, d_xepoch, d_peers, gmu, gS, lc, ltheta, lgamma_, lalpha, tmu, tvar, gm, gs, yb, ycls, d_out, d_lam, d_lamacc, d_qnodes, d_qw, d_lr, d_gradA, d_Amt, d_Avt, d_Abt};
     for (void* p : ps) cudaFree(p);
   }
 
@@ -635,6 +640,7 @@ struct Engine : EngineBase {
     CK(cudaMemcpy(counters, c, 16, cudaMemcpyHostToDevice));
     CKS(upload_lr(1));
     curB = 0; have_step = false;
+    CKS(reset_A_state());     // init_state_A (training/states.jl:100-105)
     return reset_local_vars();
   }
 
@@ -754,6 +760,36 @@ struct Engine : EngineBase {
     return AGP_OK;
   }
 
+  // ---- update_A! switch (MOSVGP.jl:51,79-81 `Aoptimiser`); kind 0 = off, 1 = ADAM ------------------------------------------
+  int reset_A_state() {
+    if (!a_opt) return AGP_OK;
+    std::vector<double> bt(2 * (size_t)nT);
+    for (int t = 0; t < nT; ++t) { bt[2 * t] = a_b1; bt[2 * t + 1] = a_b2; }
+    CK(cudaMemsetAsync(d_Amt, 0, (size_t)nT * Qg * 8, st())); CK(cudaMemsetAsync(d_Avt, 0, (size_t)nT * Qg * 8, st()));
+    CK(cudaMemcpyAsync(d_Abt, bt.data(), bt.size() * 8, cudaMemcpyHostToDevice, st()));
+    CK(cudaStreamSynchronize(st()));
+    return AGP_OK;
+  }
+  int set_A_optimiser(int kind, double eta, double b1, double b2, double eps) override {
+    if (model_kind != AGP_MODEL_MOSVGP) BAD("the mixing matrix A only exists for MOSVGP");
+    if (kind != 0 && kind != 1) BAD("unknown A optimiser (0 = none, 1 = ADAM)");
+    if (kind == 1 && !(eta > 0 && b1 > 0 && b1 < 1 && b2 > 0 && b2 < 1 && eps > 0)) BAD("bad ADAM parameters");
+    drop_graph();
+    a_opt = kind == 1;
+    if (!a_opt) return AGP_OK;
+    a_eta = eta; a_b1 = b1; a_b2 = b2; a_eps = eps;
+    if (!d_gradA) {
+      CKS(dalloc(&d_gradA, (size_t)nT * Qg)); CKS(dalloc(&d_Amt, (size_t)nT * Qg)); CKS(dalloc(&d_Avt, (size_t)nT * Qg)); CKS(dalloc(&d_Abt, 2 * (size_t)nT));
+    }
+    return reset_A_state();
+  }
+  int get_A(double* A) override {
+    if (model_kind != AGP_MODEL_MOSVGP || !A) BAD("no mixing matrix");
+    CK(cudaStreamSynchronize(st()));
+    CK(cudaMemcpy(A, d_A, (size_t)nT * Qg * 8, cudaMemcpyDeviceToHost));
+    return AGP_OK;
+  }
+
   // ---- peer exchange set-up (one process per GPU, same node; handles travel through the host's process group) -----------
   int peer_export(void* handle64) override {
     if (!handle64) BAD("null handle buffer");
@@ -815,6 +851,13 @@ struct Engine : EngineBase {
     if (curB < 1) { ctx->err = "no minibatch in flight"; return AGP_ERR_STATE; }
     const int B = curB;
     ph_begin(PH_LIK);
+    if (a_opt) {   // update_A! precedes variational_updates (training/training.jl:153-158)
+      LikParams lp0 = lik_params(B, cur_from_batch, 0);
+      lik_update_kernel<<<(B + 127) / 128, 128, 0, st()>>>(lp0);                        // labels of this batch + task means with the current A
+      update_A_grad_kernel<<<nT * Qg, 256, 0, st()>>>(lik_params(B, true, 0), d_gradA);
+      update_A_adam_kernel<<<nT, 32 * ((Qg + 31) / 32), 0, st()>>>(d_A, d_gradA, d_Amt, d_Avt, d_Abt, Qg, a_eta, a_b1, a_b2, a_eps);
+      launches += 3;
+    }
     if (need_quad && nq < 1) { ph_end(); ctx->err = "agp_set_quadrature must be called before a Poisson step"; return AGP_ERR_STATE; }
     launch_chain(lik_update_kernel, dim3((B + 127) / 128), dim3(128), 0, lik_params(B, cur_from_batch, 1));
     ++launches;
@@ -1556,6 +1599,10 @@ int agp_get_Kinv(agp_model* model, int32_t ql, double* Kinv, double* logdetK) { 
 int agp_predict_f(agp_model* model, const void* Xt, int x_dtype, int x_layout, int64_t nt, int want_var, double* mu, double* var) {
   ENG(model); return e->predict_f(Xt, x_dtype, x_layout, nt, want_var, mu, var);
 }
+int agp_set_A_optimiser(agp_model* model, int32_t kind, double eta, double beta1, double beta2, double eps) {
+  ENG(model); return e->set_A_optimiser(kind, eta, beta1, beta2, eps);
+}
+int agp_get_A(agp_model* model, double* A) { ENG(model); return e->get_A(A); }
 int agp_peer_export(agp_model* model, void* handle64) { ENG(model); return e->peer_export(handle64); }
 int agp_peer_attach(agp_model* model, int32_t world, int32_t rank, const void* handles) { ENG(model); return e->peer_attach(world, rank, handles); }
 int agp_set_quadrature(agp_model* model, const double* nodes, const double* weights, int32_t n_nodes) {

@@ -411,6 +411,74 @@ __global__ void lik_update_kernel(const LikParams p_in) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// update_A! (models/single_and_multi_output_utils.jl:87-118) for MOSVGP with an A optimiser: runs between the latent
+// moments and local_updates!, i.e. with the local variables of the PREVIOUS iteration and the labels of the current batch.
+// ------------------------------------------------------------------------------------------------
+// expectation gradients from stored local variables (grad_E_mu / grad_E_Sigma of likelihood/*.jl)
+__device__ __forceinline__ void lik_grads_from_state(int kind, double p0, double y, double th, double gam, double& gm, double& gs) {
+  if (kind == 0) { th = 1.0 / p0; gm = y / p0; }       // gaussian.jl:74-80 (theta = 1/sigma^2 from init_local_vars on)
+  else if (kind == 1) gm = 0.5 * y;                    // logistic.jl:64-66
+  else if (kind == 2 || kind == 4) gm = th * y;        // studentt.jl:96, laplace.jl:87-89
+  else if (kind == 5) gm = y * (th + 1.0);             // bayesiansvm.jl:54-58
+  else if (kind == 6) gm = 0.5 * (y - p0);             // negativebinomial.jl:94-96
+  else gm = 0.5 * (y - gam);                           // poisson.jl:98-102
+  gs = 0.5 * th;
+}
+// one block per (task t, latent q): gradA[t][q] = x1 - 2 A_tq x2 (:96-107), deterministic in-block reduction
+__global__ void update_A_grad_kernel(const LikParams p_in, double* __restrict__ gradA) {
+  const LikParams p = lik_resolve(p_in);
+  const int t = blockIdx.x / p.Q, q = blockIdx.x % p.Q;
+  const int64_t ld = p.ldB;
+  const double a = p.A[t * p.Q + q];
+  const int kind = p.lik_kind[t];
+  const double p0 = p.p0[t];
+  double x1 = 0.0, x2 = 0.0;
+  for (int b = threadIdx.x; b < p.B; b += blockDim.x) {
+    const double y = p.yb[t * ld + b];                  // gathered by the preceding lik_update_kernel(update = 0) pass
+    double gm, gs;
+    lik_grads_from_state(kind, p0, y, p.theta[t * ld + b], p.gamma[t * ld + b], gm, gs);
+    const double mq = p.mean_f[q * ld + b], vq = p.var_f[q * ld + b];
+    const double others = p.tmu[t * ld + b] - a * mq;   // sum over q' != q of A_tq' mu_q'
+    x1 += gm * mq - 2.0 * gs * mq * others;
+    x2 += gs * (mq * mq + vq);
+  }
+  __shared__ double s1[8], s2[8];
+  x1 = warp_sum(x1); x2 = warp_sum(x2);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { s1[w] = x1; s2[w] = x2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double u = 0.0, v = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { u += s1[i]; v += s2[i]; }
+    gradA[t * p.Q + q] = u - 2.0 * a * v;
+  }
+}
+// ADAM step of Optimisers.jl (apply: mt, vt, beta_t) followed by A_t += step and the projection on the unit circle (:109-113);
+// one block per task, thread q
+__global__ void update_A_adam_kernel(double* __restrict__ A, const double* __restrict__ gradA, double* __restrict__ mt, double* __restrict__ vt,
+                                     double* __restrict__ bt /*[T][2]*/, int Q, double eta, double b1, double b2, double eps) {
+  const int t = blockIdx.x, q = threadIdx.x;
+  __shared__ double red[32];
+  double an = 0.0;
+  if (q < Q) {
+    const double g = gradA[t * Q + q];
+    const double m_ = b1 * mt[t * Q + q] + (1.0 - b1) * g;
+    const double v_ = b2 * vt[t * Q + q] + (1.0 - b2) * g * g;
+    mt[t * Q + q] = m_; vt[t * Q + q] = v_;
+    const double step = m_ / (1.0 - bt[2 * t]) / (sqrt(v_ / (1.0 - bt[2 * t + 1])) + eps) * eta;
+    an = A[t * Q + q] + step;
+  }
+  double ss = warp_sum(an * an);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  double tot = 0.0;
+  for (int i = 0; i < (int)((blockDim.x + 31) >> 5); ++i) tot += red[i];
+  if (q < Q) A[t * Q + q] = an / sqrt(tot);
+  __syncthreads();
+  if (q == 0) { bt[2 * t] *= b1; bt[2 * t + 1] *= b2; }
+}
+
 // re-estimation of the link parameter lambda at the end of local_updates! (poisson.jl:80, heteroscedastic.jl:98);
 // one thread per task, accumulators cleared for the next step
 __global__ void lik_lambda_kernel(const LikParams p) {

@@ -161,6 +161,14 @@ int agp_step_update_async(agp_model* model, double rho);
 /* device pointers + leading dimension of the moment arrays (which: 0 = mean_f, 1 = var_f). */
 void* agp_moments_devptr(agp_model* model, int32_t which, int64_t* ld_out);
 
+/* update_A! (models/single_and_multi_output_utils.jl:87-118; MOSVGP `Aoptimiser`, MOSVGP.jl:51,79-81): kind 0 = A fixed
+ * (Aoptimiser = false), 1 = ADAM(eta, (beta1, beta2)) of Optimisers.jl with epsilon.  When on, every step first moves each
+ * task's mixing row along the ADAM step of its ELBO gradient (local variables of the previous iteration) and renormalises
+ * it, then runs variational_updates (training/training.jl:153-158).  agp_state_reset re-initialises the ADAM state
+ * (init_state_A, training/states.jl:100-105).  agp_get_A: the current T x Q matrix, row-major. */
+int agp_set_A_optimiser(agp_model* model, int32_t kind, double eta, double beta1, double beta2, double eps);
+int agp_get_A(agp_model* model, double* A);
+
 /* Device-side exchange over NVLink peer memory (same node, one process per GPU): every rank exports the IPC handle of its
  * moment block (64 bytes), the host gathers the handles over its process group (rank order) and attaches them.  Afterwards
  * every agp_step* / agp_elbo_moments_async call publishes the owned rows into all peers' arrays and waits for theirs inside

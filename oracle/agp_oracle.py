@@ -798,28 +798,80 @@ def _view_y(y, idx):
 
 
 # --------------------------------------------------------------------------------------
-# MOSVGP (models/MOSVGP.jl, single_and_multi_output_utils.jl:24-84), A fixed (Aoptimiser=false)
+# MOSVGP (models/MOSVGP.jl, single_and_multi_output_utils.jl:24-118)
 # --------------------------------------------------------------------------------------
-class MOSVGP:
-    """Each task has a single-latent likelihood (nf_per_task = 1).  A: (T, Q)."""
+@dataclass
+class ADAM:
+    """Optimisers.jl (un-vendored; compat 0.1 / 0.3) ADAM(eta, beta = (0.9, 0.999)), epsilon = 1e-8, as used by
+    update_A! through Optimisers.init / Optimisers.apply (states.jl:100-105, single_and_multi_output_utils.jl:109-110):
+      init  -> (mt = 0, vt = 0, beta_t = beta)
+      apply -> mt = b1 mt + (1-b1) g ; vt = b2 vt + (1-b2) g^2 ; step = mt / (1-bt1) / (sqrt(vt / (1-bt2)) + eps) * eta ;
+               beta_t <- beta_t .* beta"""
 
-    def __init__(self, kernels, likelihoods, inference: AnalyticVI, Zs, A, jitter=JITTER_F64):
+    eta: float = 0.01
+    beta: tuple = (0.9, 0.999)
+    eps: float = 1e-8
+
+    def init(self, x):
+        return dict(mt=np.zeros_like(x), vt=np.zeros_like(x), bt=np.array(self.beta, dtype=np.float64))
+
+    def apply(self, st, g):
+        b1, b2 = self.beta
+        st["mt"] = b1 * st["mt"] + (1.0 - b1) * g
+        st["vt"] = b2 * st["vt"] + (1.0 - b2) * g**2
+        step = st["mt"] / (1.0 - st["bt"][0]) / (np.sqrt(st["vt"] / (1.0 - st["bt"][1])) + self.eps) * self.eta
+        st["bt"] = st["bt"] * np.array(self.beta)
+        return st, step
+
+
+class MOSVGP:
+    """Each task has a single-latent likelihood (nf_per_task = 1).  A: (T, Q).  Aoptimiser: None (fixed A) or ADAM
+    (MOSVGP.jl:51,79-81: the reference default is ADAM(0.01))."""
+
+    def __init__(self, kernels, likelihoods, inference: AnalyticVI, Zs, A, jitter=JITTER_F64, Aoptimiser=None):
+        self.A_opt = Aoptimiser
         self.likelihoods = list(likelihoods)
         self.inference = inference
         self.jitter = jitter
         kernels = [kernels] if isinstance(kernels, Kernel) else list(kernels)
         self.f = [SparseVarLatent(Z, kernels[i % len(kernels)]) for i, Z in enumerate(Zs)]
-        self.A = np.asarray(A, dtype=np.float64)
+        self.A = np.array(A, dtype=np.float64)
         assert self.A.shape == (len(self.likelihoods), len(self.f))
         self.trained = False
 
     def init_state(self):
         B = self.inference.batchsize
-        return dict(
+        st = dict(
             local_vars=[init_local_vars(l, B) for l in self.likelihoods],
             opt_state=[dict(t1=1, t2=1) for _ in self.f],
             kernel_matrices=None,
         )
+        if self.A_opt is not None:  # states.jl:100-105
+            st["A_state"] = [self.A_opt.init(self.A[t]) for t in range(self.A.shape[0])]
+        return st
+
+    def update_A(self, state, ys):
+        """single_and_multi_output_utils.jl:87-118: runs BEFORE variational_updates (training.jl:153-156), i.e. with the new
+        kernel matrices, the posterior of the previous iteration and the local variables of the previous iteration
+        (init_local_vars at the first one: theta = 0 except Gaussian)."""
+        if self.A_opt is None:
+            return state
+        mu_q, var_q = self.latent_moments(state)
+        T, Q = self.A.shape
+        for t, l in enumerate(self.likelihoods):
+            lv = state["local_vars"][t]
+            gm = grad_E_mu(l, ys[t], lv)[0]
+            gs = grad_E_Sigma(l, ys[t], lv)[0]
+            gA = np.zeros(Q)
+            for q in range(Q):
+                others = self.A[t] @ mu_q - self.A[t, q] * mu_q[q]
+                x1 = np.dot(gm, mu_q[q]) - 2.0 * np.dot(gs, mu_q[q] * others)
+                x2 = np.dot(gs, mu_q[q] ** 2 + var_q[q])
+                gA[q] = x1 - 2.0 * self.A[t, q] * x2
+            state["A_state"][t], dA = self.A_opt.apply(state["A_state"][t], gA)
+            self.A[t] = self.A[t] + dA
+            self.A[t] = self.A[t] / math.sqrt(np.sum(self.A[t] ** 2))  # projection on the unit circle (:112)
+        return state
 
     compute_kernel_matrices = SVGP.compute_kernel_matrices
     _natgrad_and_update = SVGP._natgrad_and_update
@@ -855,7 +907,9 @@ class MOSVGP:
         return state
 
     def update_parameters(self, state, x, ys):
+        """training/training.jl:153-158"""
         state = self.compute_kernel_matrices(state, x)
+        state = self.update_A(state, ys)
         return self.variational_updates(state, ys)
 
     def ELBO(self, state, ys):

@@ -350,6 +350,35 @@ def test_knm_tensor_core_kernel(agp, D, kind):
     assert rel_fro(km["Knm"], ko["Knm"]) < 2e-6
 
 
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_mosvgp_update_A_parity(agp, precision):
+    """update_A! (single_and_multi_output_utils.jl:87-118) with the reference's default ADAM(0.01): mixing matrix, posterior
+    and ELBO against the oracle; a second train call continues from the returned state (ADAM moments persist)."""
+    n, D, m, B, iters, Q, T = 500, 3, 20, 100, 8, 3, 4
+    X, _, Z, mbs, F, rng = make_data("mo", n, D, m, B, iters, seed=9, n_task=max(Q, T))
+    ys = [np.sign(F[:, 0] + 1e-3), F[:, 1] + 0.1 * rng.standard_normal(n), F[:, 2] + 0.1 * rng.standard_t(3.0, n),
+          rng.poisson(3.0 / (1.0 + np.exp(-F[:, 3]))).astype(np.int64)]
+    A = rng.standard_normal((T, Q))
+    A /= np.linalg.norm(A, axis=1, keepdims=True)
+    A0 = A.copy()
+    Zs = [X[rng.permutation(n)[:m]].copy() for _ in range(Q)]
+    sc = 1.0 / np.sqrt(D)
+    mo = O.MOSVGP(O.Kernel("sqexp", scale=sc), [O.LogisticLikelihood(), O.GaussianLikelihood(1e-2), O.StudentTLikelihood(3.0), O.PoissonLikelihood(2.0)],
+                  O.AnalyticSVI(B), Zs, A, Aoptimiser=O.ADAM(0.01))
+    me = agp.MOSVGP(agp.SqExponentialKernel() @ agp.ScaleTransform(sc),
+                    [agp.LogisticLikelihood(), agp.GaussianLikelihood(1e-2), agp.StudentTLikelihood(3.0), agp.PoissonLikelihood(2.0)],
+                    agp.AnalyticSVI(B), Zs, A=A, Aoptimiser=True, precision=precision)
+    so = se = None
+    for part in (mbs[:5], mbs[5:]):
+        mo, so = O.train(mo, X, ys, len(part), minibatches=part, state=so)
+        me, se = agp.train(me, X, ys, len(part), minibatches=part, state=se)
+    tol = TOL[precision]
+    assert rel_fro(me.A, mo.A) < tol, rel_fro(me.A, mo.A)
+    assert np.allclose(np.linalg.norm(me.A, axis=1), 1.0, atol=1e-12)
+    assert not np.allclose(me.A, A0, atol=1e-3)         # it moved
+    check_pair(agp, (mo, so), (me, se), 10 * tol if precision == "f32" else tol)
+
+
 def test_latent_sharded_two_gpus_match_single_gpu():
     """latent-sharded run (one rank per GPU, moments exchanged over NVLink peer memory inside the step, and the
     NCCL all-gather fallback) against the same model on one GPU.  Needs two visible GPUs (skipped otherwise)."""
