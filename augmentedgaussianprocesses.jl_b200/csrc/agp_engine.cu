@@ -178,6 +178,7 @@ struct Engine : EngineBase {
   bool a_opt = false; double a_eta = 0.01, a_b1 = 0.9, a_b2 = 0.999, a_eps = 1e-8;
   double *d_gradA = nullptr, *d_Amt = nullptr, *d_Avt = nullptr, *d_Abt = nullptr;
   double* d_lr = nullptr;          // Robbins-Monro step size of the current iteration (lik_update_kernel -> combine_kernel)
+  bool fuse_lik_next = false, fuse_from_batch = false, lik_fused = false;   // rowfinish + local-update fusion (set by the step paths)
   bool racc2_precleared = false;   // the V X^T row-statistic accumulators were cleared off the critical chain (side stream)
   int tail_variant = 3;  // AGP_TAIL_VARIANT: 0-2 = agp_tail.cuh (SIMT tile products), 3 = agp_tail2.cuh (DMMA, panel potf2)
 
@@ -730,7 +731,12 @@ struct Engine : EngineBase {
         ph_end();
       }
       ph_begin(PH_ROWSTATS);
-      if (prec == AGP_PREC_TF32X3)
+      if (prec == AGP_PREC_TF32X3 && fuse_lik_next) {
+        // single-latent SVGP step: local updates fused into the row-statistics kernel (step_update_a skips its lik launch)
+        launch_chain(rowfinish_lik_kernel, dim3((B + 255) / 256), dim3(256), 0, (const double*)L.racc, (const double*)(L.racc + ldB),
+                     (const double*)(L.racc + 2 * ldB), B, L.variance + jitter, L.Ktilde, status, lik_params(B, fuse_from_batch, 1));
+        lik_fused = true;
+      } else if (prec == AGP_PREC_TF32X3)
         launch_chain(rowfinish_kernel, dim3((B + 255) / 256), dim3(256), 0, (const double*)L.racc, (const double*)(L.racc + ldB),
                      (const double*)(L.racc + 2 * ldB), B, L.variance + jitter, L.Ktilde, mean_out + (size_t)q * out_ld,
                      var_out + (size_t)q * out_ld, status, fresh_kernel_matrices ? 1 : 0,
@@ -819,6 +825,10 @@ struct Engine : EngineBase {
     return AGP_OK;
   }
 
+  bool can_fuse_lik() const {
+    return prec == AGP_PREC_TF32X3 && model_kind == AGP_MODEL_SVGP && Qg == 1 && Ql == 1 && !need_lam && !peer && !a_opt && !prof &&
+           !getenv("AGP_NO_FUSE_LIK");
+  }
   LikParams lik_params(int B, bool from_batch, int update) {
     LikParams p{};
     p.model_kind = model_kind; p.n_task = nT; p.Q = Qg; p.B = B; p.ldB = ldB; p.latent_begin = qbeg; p.n_latent_local = Ql;
@@ -838,9 +848,12 @@ struct Engine : EngineBase {
     if (prec == AGP_PREC_TF32X3 && (B % 128)) BAD("TF32X3 precision needs B % 128 == 0");
     if (!from_batch) CKS(prep_idx(idx, B, base));
     curB = B; cur_from_batch = from_batch; kernel_matrices_stale = false; prefetched = false;
-    CKS(moments_impl(from_batch, B, true));
-    return AGP_OK;
+    fuse_lik_next = fuse_in_step_moments && can_fuse_lik(); fuse_from_batch = from_batch; lik_fused = false;
+    int sm = moments_impl(from_batch, B, true);
+    fuse_lik_next = false;
+    return sm;
   }
+  bool fuse_in_step_moments = false;   // true only when step_update follows immediately (step_full / step_batch, not the sharded API)
 
   int step_update(double rho) override {
     CKS(step_update_a(rho));
@@ -859,8 +872,8 @@ struct Engine : EngineBase {
       launches += 3;
     }
     if (need_quad && nq < 1) { ph_end(); ctx->err = "agp_set_quadrature must be called before a Poisson step"; return AGP_ERR_STATE; }
-    launch_chain(lik_update_kernel, dim3((B + 127) / 128), dim3(128), 0, lik_params(B, cur_from_batch, 1));
-    ++launches;
+    if (!lik_fused) { launch_chain(lik_update_kernel, dim3((B + 127) / 128), dim3(128), 0, lik_params(B, cur_from_batch, 1)); ++launches; }
+    lik_fused = false;
     if (need_lam) {  // lambda re-estimation closes local_updates! (poisson.jl:80, heteroscedastic.jl:98)
       LikParams lp = lik_params(B, true, 1);
       launch_chain(lik_lambda_kernel, dim3(1), dim3(std::max(32, (int)rup(nT, 32))), 0, lp);
@@ -923,10 +936,7 @@ struct Engine : EngineBase {
       ph_end();
       CKS(eta_to_moments(L, q == Ql - 1));   // the last latent's finalize kernel also prepares the next step size
     }
-    ph_begin(PH_FINAL);
-    launch_chain(bump_counters_kernel, dim3(1), dim3(32), 0, counters, 1, 1);
-    ++launches;
-    ph_end();
+    // (the counters are bumped by the last latent's finalize kernel)
     CK(cudaGetLastError());
     have_step = true;
     return AGP_OK;
@@ -986,7 +996,7 @@ struct Engine : EngineBase {
     ph_begin(PH_FINAL);
     float* hi = nullptr; float* lo = nullptr;
     launch_chain(x_finalize_kernel<T>, dim3(m), dim3(128), 0, (const double*)L.Xv, (int64_t)mp, m, (const double*)L.eta1v, L.Xv_T, (int64_t)ldm, hi, lo,
-                 L.tvec, (in_step && stochastic) ? d_lr : (double*)nullptr, (const int64_t*)counters, rm_kappa, rm_tau);
+                 L.tvec, (in_step && stochastic) ? d_lr : (double*)nullptr, counters, rm_kappa, rm_tau, in_step ? 1 : 0);
     ++launches;
     ph_end();
     L.muv_valid = false;
@@ -1019,7 +1029,10 @@ struct Engine : EngineBase {
       CKS(moments_impl(false, B, true, 1));
     }
     curB = B; cur_from_batch = false; kernel_matrices_stale = false; prefetched = false;
-    CKS(moments_impl(false, B, true, 2));    // V X^T, row statistics (needs the posterior of the previous step)
+    fuse_lik_next = can_fuse_lik(); fuse_from_batch = false; lik_fused = false;
+    int sm2 = moments_impl(false, B, true, 2);    // V X^T, row statistics (needs the posterior of the previous step)
+    fuse_lik_next = false;
+    CKS(sm2);
     CKS(step_update_a(rho));                 // local updates, V^T g, Gram product: last readers of V / idx_cur
     if (pipe) {
       CK(cudaEventRecord(ev_fork, ctx->stream));
@@ -1062,7 +1075,10 @@ struct Engine : EngineBase {
 
   int step_full(const int64_t* idx, int B, int base, double rho) override {
     if (idx) {
-      CKS(step_moments(idx, B, base, false));
+      fuse_in_step_moments = true;
+      int s1 = step_moments(idx, B, base, false);
+      fuse_in_step_moments = false;
+      CKS(s1);
       return step_update(rho);
     }
     if (want_graph && !prof && !capturing) {
@@ -1106,7 +1122,10 @@ struct Engine : EngineBase {
     if (x_dtype == AGP_DTYPE_F64) convert_rows_kernel<double, T><<<bl, 256, 0, st()>>>((const double*)stage, x_layout, sld, B, D, Xb, Dp, xxb);
     else convert_rows_kernel<float, T><<<bl, 256, 0, st()>>>((const float*)stage, x_layout, sld, B, D, Xb, Dp, xxb);
     ++launches;
-    CKS(step_moments(nullptr, B, 0, true));
+    fuse_in_step_moments = true;
+    int s1 = step_moments(nullptr, B, 0, true);
+    fuse_in_step_moments = false;
+    CKS(s1);
     return step_update(rho);
   }
   int step_batch(const void* xbh, int x_dtype, int x_layout, const void* const* ybh, int y_kind, int B, double rho) override {

@@ -479,6 +479,22 @@ __global__ void update_A_adam_kernel(double* __restrict__ A, const double* __res
   if (q == 0) { bt[2 * t] *= b1; bt[2 * t + 1] *= b2; }
 }
 
+// rowfinish_kernel + lik_update_kernel in one launch for the common single-latent case (SVGP, one latent, no lambda
+// re-estimation, not sharded): the thread that finishes (mu_f, sigma2_f) of a sample runs its local update right away
+__global__ void rowfinish_lik_kernel(const double* __restrict__ sumsq_v, const double* __restrict__ sumsq_vs, const double* __restrict__ dot_vs,
+                                     int B, double kdiag_jit, double* __restrict__ Ktilde, int* __restrict__ status, const LikParams p) {
+  pdl_prologue();
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double kt = kdiag_jit - sumsq_v[b];
+  Ktilde[b] = kt;
+  if (!(kt > 0.0)) atomicOr(status, ST_KTILDE);  // latentgp.jl:213
+  const_cast<double*>(p.mean_f)[b] = dot_vs[b];
+  const_cast<double*>(p.var_f)[b] = sumsq_vs[b] + kt;
+  double r0 = 0.0, r1 = 0.0;
+  lik_update_sample(p, b, r0, r1);
+}
+
 // re-estimation of the link parameter lambda at the end of local_updates! (poisson.jl:80, heteroscedastic.jl:98);
 // one thread per task, accumulators cleared for the next step
 __global__ void lik_lambda_kernel(const LikParams p) {
@@ -705,12 +721,15 @@ __global__ void combine_kernel(const TailParams p, const TG* __restrict__ Gpart)
     return;
   }
   int a = p.g_mirrored ? i : min(i, j), b = p.g_mirrored ? j : max(i, j);
-  double g = 0.0, g2 = 0.0;
+  double g = 0.0;
   const TG* gp = Gpart + (int64_t)a * p.gpart_ld + b;
-  int s = 0;
-  for (; s + 1 < p.n_split; s += 2) { g += (double)gp[s * p.gpart_stride]; g2 += (double)gp[(s + 1) * p.gpart_stride]; }
-  if (s < p.n_split) g += (double)gp[s * p.gpart_stride];
-  g += g2;
+  for (int s0 = 0; s0 < p.n_split; s0 += 16) {   // up to 16 independent loads in flight (the split-K partials are 1 MB apart)
+    TG v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) v[u] = (s0 + u < p.n_split) ? gp[(int64_t)(s0 + u) * p.gpart_stride] : TG(0);
+#pragma unroll
+    for (int u = 0; u < 16; ++u) g += (double)v[u];
+  }
   int64_t o = (int64_t)i * p.ld + j;
   double e2 = p.eta2[o];
   double d2 = -(g + (i == j ? 0.5 : 0.0)) - e2;

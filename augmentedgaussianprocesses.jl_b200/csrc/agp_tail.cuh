@@ -385,13 +385,16 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) tail_step_kernel(const TailSt
 template <typename T>
 __global__ void x_finalize_kernel(const double* __restrict__ X, int64_t ld, int m, const double* __restrict__ eta1v,
                                   T* __restrict__ shadow, int64_t lds, float* __restrict__ hi, float* __restrict__ lo,
-                                  double* __restrict__ tvec, double* __restrict__ lr_next, const int64_t* __restrict__ counters,
-                                  double rm_kappa, double rm_tau) {
+                                  double* __restrict__ tvec, double* __restrict__ lr_next, int64_t* __restrict__ counters,
+                                  double rm_kappa, double rm_tau, int bump) {
   pdl_prologue();
   const int i = blockIdx.x;
   // Robbins-Monro step size of the NEXT iteration (inference/optimisers.jl:14-19; the counter is bumped after this kernel):
   // one thread of one block, hidden behind the rest of the grid instead of sitting on the next step's chain
-  if (lr_next && i == 0 && threadIdx.x == 0) *lr_next = pow(rm_tau + (double)(counters[0] + 1), -rm_kappa);
+  if (i == 0 && threadIdx.x == 0) {
+    if (lr_next) *lr_next = pow(rm_tau + (double)(counters[0] + 1), -rm_kappa);
+    if (bump) { counters[0] += 1; counters[1] += 1; }   // end of the step: Robbins-Monro counter and minibatch-list cursor
+  }
   double s = 0.0;
   for (int j = threadIdx.x; j < m; j += blockDim.x) {
     double v = (j <= i) ? X[(int64_t)i * ld + j] : 0.0;

@@ -32,6 +32,10 @@ sys.path.insert(0, ROOT)
 
 CFG = dict(n=1_000_000, D=32, m=512, B=8192)
 METRIC = "natural-gradient CAVI iters/sec, SVGP m=512 bs=8192"
+# --config C3 (BASELINE.json configs[2], an extra evidence run, NOT the contract line): SVGP StudentT(nu=3) Matern-3/2,
+# n=1e7 D=64 m=1024 minibatch=16384.  n is cut to 2e6 rows (512 MB resident, still >> L2; the step cost is n-independent)
+# to keep host-side data generation short.
+CFG_C3 = dict(n=2_000_000, D=64, m=1024, B=16384)
 
 
 def make_problem(n, D, m, B, n_lists, seed=0, n_task=1):
@@ -152,17 +156,22 @@ def run_ours(args, rank, world, local_rank):
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=dev)
-    n, D, m, B = CFG["n"], CFG["D"], CFG["m"], CFG["B"]
+    c3 = args.config == "C3"
+    cfg = CFG_C3 if c3 else CFG
+    n, D, m, B = cfg["n"], cfg["D"], cfg["m"], cfg["B"]
     K, W = args.steps, max(args.warmup, 3)
     n_lists = K + W
     X, ys, Z, mbs, rng = make_problem(n, D, m, B, n_lists, n_task=world)
-    kern = agp.SqExponentialKernel() @ agp.ScaleTransform(1.0 / np.sqrt(D))
+    if c3:   # regression targets with Student-t noise
+        ys = [(np.sin(X[:, 0]) + 0.5 * X[:, 1] + 0.1 * rng.standard_t(3.0, n)).astype(np.float64)]
+    kern = (agp.Matern32Kernel() if c3 else agp.SqExponentialKernel()) @ agp.ScaleTransform(1.0 / np.sqrt(D))
     # a dedicated non-default stream: the engine launches on it, torch events / NCCL are ordered on it
     tstream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
     if world == 1:
-        model = agp.SVGP(kern, agp.LogisticLikelihood(), agp.AnalyticSVI(B), Z, precision=args.precision, device=local_rank, stream=stream)
+        model = agp.SVGP(kern, agp.StudentTLikelihood(3.0, 1.0) if c3 else agp.LogisticLikelihood(), agp.AnalyticSVI(B), Z, precision=args.precision,
+                         device=local_rank, stream=stream)
         y_arg = ys[0]
     else:
         A = rng.standard_normal((world, world))
@@ -268,7 +277,7 @@ def run_ours(args, rank, world, local_rank):
         # (profiles/r1/ncu_traffic.json, written by profiles/extract_ncu.py); null when the file is absent
         traffic = {}
         tf = os.path.join(ROOT, "profiles", "r1", "ncu_traffic.json")
-        if os.path.exists(tf):
+        if os.path.exists(tf) and not c3:
             try:
                 traffic = json.load(open(tf))
             except Exception:
@@ -321,16 +330,17 @@ def run_ours(args, rank, world, local_rank):
                    note="latent-sharded run: measured at N=1 only")
 
     if rank == 0:
-        cpu = cpu_baseline_sample() if (world == 1 and not args.no_cpu_baseline) else None
+        cpu = cpu_baseline_sample() if (world == 1 and not args.no_cpu_baseline and not c3) else None
         line = dict(metric=METRIC, value=value, unit="iters/s", n_gpus=world, steps=K, warmup=W, ms_per_step=ms / K,
                     higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype={"f32": "f32 (fp32 SIMT contractions, f64 m x m tail)", "tf32x3": "tf32x3 (tcgen05, f64 m x m tail)", "f64": "f64"}[args.precision],
                     data="synthetic",
-                    config=dict(workload=("C2: SVGP Logistic SqExp n=1e6 D=32 m=512 minibatch=8192" if world == 1 else
+                    config=dict(workload=("C3 (extra evidence run): SVGP StudentT(3) Matern-3/2 n=2e6 (of 1e7) D=64 m=1024 minibatch=16384" if c3 else
+                                          "C2: SVGP Logistic SqExp n=1e6 D=32 m=512 minibatch=8192" if world == 1 else
                                           f"C2-shaped multi-output SVGP: {world} Logistic tasks x {world} latent GPs, one latent per GPU, "
                                           + ("per-sample moments exchanged over NVLink peer memory inside the step" if peer else "moments NCCL all-gather per step")),
-                                l2="inputs larger than L2: every step gathers a new random minibatch from the resident 140 MB (X, |x|^2, y) arrays; no flush",
-                                graph=bool(args.graph and (world == 1 or peer)), precision=args.precision, **CFG),
+                                l2=f"inputs larger than L2: every step gathers a new random minibatch from the resident {int(n * (4 * D + 12) / 1e6)} MB (X, |x|^2, y) arrays; no flush",
+                                graph=bool(args.graph and (world == 1 or peer)), precision=args.precision, **cfg),
                     gpu_launches=int(launches), elbo_last=elbo, roofline=roof, cpu_baseline=cpu, e2e=e2e, clocks=clocks, phases=phases)
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -347,6 +357,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("AGP_BENCH_PRECISION", "tf32x3"), choices=["f32", "tf32x3", "f64"])
     ap.add_argument("--graph", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="C2", choices=["C2", "C3"], help="C2 = the contract workload (default); C3 = extra evidence run at the larger configuration")
     ap.add_argument("--timed-only", action="store_true", help="profiling aid: run only warm-up + the timed loop")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
