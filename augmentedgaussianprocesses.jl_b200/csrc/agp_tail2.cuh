@@ -93,6 +93,41 @@ __device__ __forceinline__ void tile2_prod(const double* __restrict__ A, const d
     }
   }
 }
+// Lower triangle of L L^T (36 of the 64 8 x 8 tiles), balanced: tile id = warp + 8 s (row-major enumeration of the lower
+// tiles), 4 or 5 tiles per warp instead of 1..8 with the row-owner mapping, so the diagonal-tile update on the critical path
+// costs 72-80 DMMAs per warp instead of 128.
+struct SyrkTiles { int row[5], col[5]; bool live[5]; };
+__device__ __forceinline__ SyrkTiles syrk_tiles() {
+  SyrkTiles tl;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int s_ = 0; s_ < 5; ++s_) {
+    const int id = w + 8 * s_;
+    int mb = 0;
+    while ((mb + 1) * (mb + 2) / 2 <= id) ++mb;
+    const int nb = id - mb * (mb + 1) / 2;
+    tl.live[s_] = id < 36;
+    tl.row[s_] = 8 * mb + (lane >> 2);     // accumulator row of this lane; also the A-fragment row
+    tl.col[s_] = 8 * nb;                   // first column of the tile (B-fragment row block)
+  }
+  return tl;
+}
+__device__ __forceinline__ void tile2_syrk_lower(const double* __restrict__ Lm, const SyrkTiles& tl, double (&acc)[5][2]) {
+  const int lane = threadIdx.x & 31, r = lane >> 2, kk = lane & 3;
+#pragma unroll
+  for (int s_ = 0; s_ < 5; ++s_) { acc[s_][0] = 0.0; acc[s_][1] = 0.0; }
+#pragma unroll 2
+  for (int k = 0; k < TNB; k += 4) {
+#pragma unroll
+    for (int s_ = 0; s_ < 5; ++s_) {
+      if (!tl.live[s_]) continue;
+      const double a = Lm[tl.row[s_] * T2LD + k + kk];
+      const double b = Lm[(tl.col[s_] + r) * T2LD + k + kk];
+      dmma884(acc[s_][0], acc[s_][1], a, b);
+    }
+  }
+}
+
 // global / shared address of this lane's two accumulator elements of tile t
 template <int MAP>
 __device__ __forceinline__ int acc_row(int t) { return 8 * (MAP == 0 ? (int)(threadIdx.x >> 5) : t) + ((threadIdx.x & 31) >> 2); }
@@ -320,26 +355,43 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) tail2_step_kernel(const TailS
     double* At = p.P + (int64_t)i * TNB * ld + (int64_t)j * TNB;
     tile2_load(s1, p.P + (int64_t)i * TNB * ld + (int64_t)k * TNB, ld);
     if (j != i) tile2_load(s2, p.P + (int64_t)j * TNB * ld + (int64_t)k * TNB, ld);
-    double2 old[8];   // the tile being updated, prefetched in the accumulator layout (MAP 0)
-#pragma unroll
-    for (int t = 0; t < 8; ++t) old[t] = *reinterpret_cast<const double2*>(At + (int64_t)acc_row<0>(t) * ld + acc_col<0>(t));
-    __syncthreads();
-    tile2_prod<0, true, 1, false>(s1, sX, acc); acc2_to_smem<0>(s3, acc);
-    const double* Lj = s3;
-    if (j != i) { tile2_prod<0, true, 1, false>(s2, sX, acc); acc2_to_smem<0>(s4, acc); Lj = s4; }
-    __syncthreads();
-    if (j != i) tile2_prod<0, true, 0, false>(s3, Lj, acc);
-    else tile2_prod<0, true, 0, true>(s3, Lj, acc);     // diagonal tile: lower 8 x 8 tiles only
     const bool lookahead = (i == k + 1 && j == k + 1);
-    if (!lookahead) {
+    if (j != i) {
+      double2 old[8];   // the tile being updated, prefetched in the accumulator layout (MAP 0)
+#pragma unroll
+      for (int t = 0; t < 8; ++t) old[t] = *reinterpret_cast<const double2*>(At + (int64_t)acc_row<0>(t) * ld + acc_col<0>(t));
+      __syncthreads();
+      tile2_prod<0, true, 1, false>(s1, sX, acc); acc2_to_smem<0>(s3, acc);
+      tile2_prod<0, true, 1, false>(s2, sX, acc); acc2_to_smem<0>(s4, acc);
+      __syncthreads();
+      tile2_prod<0, true, 0, false>(s3, s4, acc);
 #pragma unroll
       for (int t = 0; t < 8; ++t)
         *reinterpret_cast<double2*>(At + (int64_t)acc_row<0>(t) * ld + acc_col<0>(t)) = make_double2(old[t].x - acc[t][0], old[t].y - acc[t][1]);
     } else {
+      // diagonal tile: lower 8 x 8 tiles only, balanced over the warps (this is the critical path of the block step)
+      const SyrkTiles tl = syrk_tiles();
+      const int c2 = 2 * (threadIdx.x & 3);
+      double2 old5[5];
+      double acc5[5][2];
 #pragma unroll
-      for (int t = 0; t < 8; ++t) *reinterpret_cast<double2*>(s1 + acc_row<0>(t) * T2LD + acc_col<0>(t)) = make_double2(old[t].x - acc[t][0], old[t].y - acc[t][1]);
+      for (int s_ = 0; s_ < 5; ++s_)
+        old5[s_] = tl.live[s_] ? *reinterpret_cast<const double2*>(At + (int64_t)tl.row[s_] * ld + tl.col[s_] + c2) : make_double2(0.0, 0.0);
       __syncthreads();
-      tile2_potf2_inv(s1, s2, sl, vec, p.Xout + (int64_t)(k + 1) * TNB * (ld + 1), ld, p.Dinv + (int64_t)(k + 1) * TNB * TNB, p.logdet, p.status);
+      tile2_prod<0, true, 1, false>(s1, sX, acc); acc2_to_smem<0>(s3, acc);
+      __syncthreads();
+      tile2_syrk_lower(s3, tl, acc5);
+      if (!lookahead) {
+#pragma unroll
+        for (int s_ = 0; s_ < 5; ++s_)
+          if (tl.live[s_]) *reinterpret_cast<double2*>(At + (int64_t)tl.row[s_] * ld + tl.col[s_] + c2) = make_double2(old5[s_].x - acc5[s_][0], old5[s_].y - acc5[s_][1]);
+      } else {
+#pragma unroll
+        for (int s_ = 0; s_ < 5; ++s_)
+          if (tl.live[s_]) *reinterpret_cast<double2*>(s1 + tl.row[s_] * T2LD + tl.col[s_] + c2) = make_double2(old5[s_].x - acc5[s_][0], old5[s_].y - acc5[s_][1]);
+        __syncthreads();
+        tile2_potf2_inv(s1, s2, sl, vec, p.Xout + (int64_t)(k + 1) * TNB * (ld + 1), ld, p.Dinv + (int64_t)(k + 1) * TNB * TNB, p.logdet, p.status);
+      }
     }
   } else if (b < nA + nW) {
     // ---- W tile (i, c), c <= k < i :  W_ic = [c<k] W_ic - L_ik Wn_kc,  Wn_kc = X_kk W_kc (c<k) or X_kk (c=k) ----
