@@ -963,8 +963,12 @@ def predict_y(model, X_test):
 
 
 def _predict_y_lik(lik, mu):
-    if lik.name == "logistic":
+    if lik.name in ("logistic", "bayesiansvm"):
         return mu[0] > 0
+    if lik.name == "poisson":  # predictions.jl:207 : mean(Poisson(lambda sigma(f)))
+        return lik.lam * logistic(mu[0])
+    if lik.name == "negbinomial":  # predictions.jl:207 : mean(NegativeBinomial(r, sigma(-f))) = r e^f
+        return lik.r * np.exp(mu[0])
     if lik.name == "logisticsoftmax":
         am = np.argmax(mu, axis=0)
         return np.array([lik.class_mapping[i] for i in am])
@@ -979,6 +983,23 @@ def compute_proba(lik, mu, var):
         pred = p @ PRED_WEIGHTS
         v = np.maximum((p**2) @ PRED_WEIGHTS - pred**2, 0.0)
         return pred, v
+    if lik.name in ("poisson", "negbinomial", "bayesiansvm"):  # poisson.jl:43-55, negativebinomial.jl:47-62, classification.jl:14-26
+        sd = np.sqrt(np.maximum(var[0], 0.0))
+        x = PRED_NODES[None, :] * sd[:, None] + mu[0][:, None]
+        if lik.name == "poisson":
+            v = lik.lam * logistic(x)
+        elif lik.name == "negbinomial":
+            v = logistic(x) * lik.r / (1.0 - logistic(x))
+        else:  # svmlikelihood, bayesiansvm.jl:27-35
+            pos, neg = np.exp(-2.0 * np.maximum(1.0 - x, 0.0)), np.exp(-2.0 * np.maximum(1.0 + x, 0.0))
+            v = pos / (pos + neg)
+        pred = v @ PRED_WEIGHTS
+        pv = (v**2) @ PRED_WEIGHTS - pred**2
+        return pred, (np.maximum(pv, 0.0) if lik.name == "bayesiansvm" else pv)
+    if lik.name == "laplace":  # laplace.jl:48-52
+        return mu[0], np.maximum(var[0], 0.0) + 2.0 * lik.beta**2
+    if lik.name == "heteroscedastic":  # heteroscedastic.jl:64-70
+        return mu[0], var[0] + 1.0 / (lik.lam * logistic(mu[1]))
     if lik.name == "gaussian":  # gaussian.jl:41-45
         return mu[0], var[0] + lik.sigma2
     if lik.name == "studentt":  # studentt.jl:57-61

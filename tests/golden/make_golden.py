@@ -29,6 +29,12 @@ CASES = [
     ("logisticsoftmax_svi", "logisticsoftmax", 800, 4, 32, 128, 10, "sqexp", 0.5, 1.0, True, 4),
     ("logistic_avi", "logistic", 300, 3, 24, 300, 5, "matern52", 0.6, 1.0, False, 0),
     ("tf32_logistic_svi", "logistic", 4096, 8, 128, 256, 6, "sqexp", 1.0 / np.sqrt(8.0), 1.0, True, 0),
+    # SURVEY 8 f2 likelihoods
+    ("laplace_svi", "laplace", 600, 3, 24, 128, 8, "sqexp", 0.6, 1.0, True, 0),
+    ("bayesiansvm_svi", "bayesiansvm", 600, 3, 24, 128, 8, "matern32", 0.6, 1.0, True, 0),
+    ("negbinomial_svi", "negbinomial", 600, 3, 24, 128, 8, "sqexp", 0.6, 1.0, True, 0),
+    ("poisson_svi", "poisson", 600, 3, 24, 128, 8, "sqexp", 0.6, 1.5, True, 0),
+    ("heteroscedastic_svi", "heteroscedastic", 600, 3, 24, 128, 8, "sqexp", 0.6, 1.0, True, 0),
 ]
 
 
@@ -52,5 +58,7 @@ def run_case(name, lik, n, D, m, B, iters, kind, scale, variance, stoch, n_class
 
 
 if __name__ == "__main__":
+    only = sys.argv[1:]
     for c in CASES:
-        run_case(*c)
+        if not only or c[0] in only:
+            run_case(*c)

@@ -97,7 +97,8 @@ def test_golden_fixtures(path):
 
 
 @pytest.mark.parametrize("lik,problem", [("gaussian", "Regression"), ("studentt", "Regression"), ("logistic", "Classification"),
-                                         ("logisticsoftmax", "MultiClass")])
+                                         ("logisticsoftmax", "MultiClass"), ("laplace", "Regression"), ("heteroscedastic", "Regression"),
+                                         ("bayesiansvm", "Classification"), ("poisson", "Event"), ("negbinomial", "Event")])
 def test_testconv_thresholds(lik, problem):
     """test/testingtools.jl:223-253 thresholds on a small problem, AnalyticVI and AnalyticSVI(10)-style"""
     X, y, Z, mbs, F, rng = make_data(lik, 100, 2, 10, 10, 6, seed=3)
@@ -111,9 +112,56 @@ def test_testconv_thresholds(lik, problem):
         elif problem == "Classification":
             assert np.mean(yp != (y > 0)) < 0.5
             assert np.all(O.proba_y(m, X)[1] >= 0)
+        elif problem == "Event":  # testingtools.jl:245-248
+            assert np.mean(np.abs(yp - y)) < 20.0
         else:
             assert np.mean(yp != y) < 0.9
         assert np.isfinite(m.ELBO(st, st["y_batch"]))
+
+
+def test_f2_likelihood_closed_forms():
+    """known answers for the pieces the extra likelihoods add: GIG entropy at p = 1/2 (Bessel closed forms), the
+    Gauss-Hermite `expectation` (functions/utils.jl:16-19), the Laplace / SVM local updates, ADAM of Optimisers.jl"""
+    rng = np.random.default_rng(0)
+    a, b = 2.5, rng.uniform(0.3, 3.0, 7)
+    s = np.sqrt(a * b)
+    # K_{1/2}(s) = sqrt(pi/2s) e^-s, K_{3/2} = K_{1/2}(1 + 1/s), K_{-1/2} = K_{1/2}
+    closed = 0.5 * np.sum(np.log(a) - np.log(b)) + np.sum(np.log(2.0) + 0.5 * np.log(np.pi / (2 * s)) - s) + np.sum(s + 0.5)
+    assert O.GIGEntropy(a, b, 0.5) == pytest.approx(closed, rel=1e-12)
+    mu, var = rng.standard_normal(5), rng.uniform(0.1, 2.0, 5)
+    assert np.allclose(O.expectation(lambda x: x, mu, var), mu, atol=1e-12)
+    assert np.allclose(O.expectation(lambda x: x**2, mu, var), mu**2 + var, atol=1e-10)
+    assert np.allclose(O.expectation(O.logistic, np.zeros(3), np.ones(3)), 0.5, atol=1e-12)
+    y = rng.standard_normal(5)
+    lv = O.local_updates(O.init_local_vars(O.LaplaceLikelihood(0.5), 5), O.LaplaceLikelihood(0.5), y, mu[None], var[None])
+    assert np.allclose(lv["theta"], 2.0 / np.sqrt((mu - y) ** 2 + var))          # sqrt(a) / b, a = beta^-2
+    ys = np.sign(y)
+    lv = O.local_updates(O.init_local_vars(O.BayesianSVM(), 5), O.BayesianSVM(), ys, mu[None], var[None])
+    assert np.allclose(lv["theta"], 1.0 / np.sqrt((1 - ys * mu) ** 2 + var))
+    opt = O.ADAM(0.1)
+    st = opt.init(np.zeros(2))
+    g = np.array([1.0, -2.0])
+    st, d1 = opt.apply(st, g)
+    assert np.allclose(d1, 0.1 * np.sign(g), rtol=1e-6)                          # first ADAM step = eta * sign(g)
+    st, d2 = opt.apply(st, g)
+    assert np.allclose(d2, 0.1 * np.sign(g), rtol=1e-6) and np.allclose(st["bt"], [0.9**3, 0.999**3])
+    with pytest.raises(ValueError):
+        O.treat_labels(np.array([0.5, 1.0]), O.PoissonLikelihood(1.0))            # event.jl:11-13
+
+
+def test_poisson_lambda_reestimation_and_hetero_two_latents():
+    X, y, Z, mbs, F, rng = make_data("poisson", 300, 2, 10, 60, 5, seed=2)
+    lik = O.PoissonLikelihood(3.0)
+    m = O.SVGP(oracle_kernel(O, "sqexp", 1.0, 1.0), lik, O.AnalyticSVI(60), Z)
+    m, st = O.train(m, X, y, 5, minibatches=mbs)
+    mu, var = m.moments(st)
+    # poisson.jl:80 applied to the moments local_updates! saw = the ones before the last update; at least: positive, moved
+    assert lik.lam > 0 and lik.lam != 3.0
+    X, y, Z, mbs, F, rng = make_data("heteroscedastic", 300, 2, 10, 60, 5, seed=2)
+    lik = O.HeteroscedasticLikelihood(1.0)
+    m = O.SVGP(oracle_kernel(O, "sqexp", 1.0, 1.0), lik, O.AnalyticSVI(60), Z)
+    m, st = O.train(m, X, y, 5, minibatches=mbs)
+    assert len(m.f) == 2 and lik.lam >= 1.0                                      # heteroscedastic.jl:98 : max(..., lambda)
 
 
 def test_gaussian_avi_is_exact_posterior():
