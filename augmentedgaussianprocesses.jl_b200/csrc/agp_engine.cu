@@ -180,7 +180,7 @@ struct Engine : EngineBase {
   double* d_lr = nullptr;          // Robbins-Monro step size of the current iteration (lik_update_kernel -> combine_kernel)
   bool fuse_lik_next = false, fuse_from_batch = false, lik_fused = false;   // rowfinish + local-update fusion (set by the step paths)
   bool racc2_precleared = false;   // the V X^T row-statistic accumulators were cleared off the critical chain (side stream)
-  int tail_variant = 3;  // AGP_TAIL_VARIANT: 0-2 = agp_tail.cuh (SIMT tile products), 3 = agp_tail2.cuh (DMMA, panel potf2)
+  int tail_variant = 3;  // AGP_TAIL_VARIANT: 0 = agp_tail.cuh (generation 1, SIMT tile products), otherwise agp_tail2.cuh (DMMA, panel potf2)
 
   // ---- step state ----
   int curB = 0; bool cur_from_batch = false; bool have_K = false; bool have_data = false; bool have_step = false;
@@ -378,14 +378,10 @@ struct Engine : EngineBase {
     CK(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, potf2_smem()));
     CK(cudaFuncSetAttribute(tail_potf2_first_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM));
     CK(cudaFuncSetAttribute(tail_step_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM));
-    CK(cudaFuncSetAttribute(tail_potf2_first_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM));
-    CK(cudaFuncSetAttribute(tail_step_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM));
-    CK(cudaFuncSetAttribute(tail_potf2_first_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM));
-    CK(cudaFuncSetAttribute(tail_step_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM));
     CK(cudaFuncSetAttribute(tail2_potf2_first_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL2_SMEM));
     CK(cudaFuncSetAttribute(tail2_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL2_SMEM));
     { const char* e = getenv("AGP_TAIL_PDL"); if (e && e[0] == '0') tail_pdl = false; }
-    { const char* e = getenv("AGP_TAIL_VARIANT"); if (e) tail_variant = atoi(e); if (tail_variant < 0 || tail_variant > 3) tail_variant = 3; }
+    { const char* e = getenv("AGP_TAIL_VARIANT"); if (e) tail_variant = atoi(e); if (tail_variant != 0) tail_variant = 3; }
     CK(cudaStreamSynchronize(st()));
     return AGP_OK;
   }
@@ -971,8 +967,6 @@ struct Engine : EngineBase {
     TailStepParams tp{};
     tp.P = L.P; tp.W = L.W; tp.Xout = L.Xv; tp.Dinv = L.Dinv; tp.ld = mp; tp.nblk = mp / TNB; tp.logdet = L.logdetP; tp.status = status;
     if (tail_variant == 0) tail_potf2_first_kernel<0><<<1, TAIL_THREADS, TAIL_SMEM, st()>>>(tp);
-    else if (tail_variant == 1) tail_potf2_first_kernel<1><<<1, TAIL_THREADS, TAIL_SMEM, st()>>>(tp);
-    else if (tail_variant == 2) tail_potf2_first_kernel<2><<<1, TAIL_THREADS, TAIL_SMEM, st()>>>(tp);
     else launch_tail2(tail2_potf2_first_kernel<0>, 1, tp);
     ++launches;
     for (int k = 0; k < tp.nblk; ++k) {
@@ -981,8 +975,6 @@ struct Engine : EngineBase {
       if (tiles == 0) continue;
       tp.k = k;
       if (tail_variant == 0) tail_step_kernel<0><<<tiles, TAIL_THREADS, TAIL_SMEM, st()>>>(tp);
-      else if (tail_variant == 1) tail_step_kernel<1><<<tiles, TAIL_THREADS, TAIL_SMEM, st()>>>(tp);
-      else if (tail_variant == 2) tail_step_kernel<2><<<tiles, TAIL_THREADS, TAIL_SMEM, st()>>>(tp);
       else launch_tail2(tail2_step_kernel, tiles, tp);
       ++launches;
     }

@@ -180,13 +180,7 @@ __device__ __forceinline__ void tile_potf2_inv(const double* sa, double* lcol /*
   }
 }
 
-// ---- pipelined variant ---------------------------------------------------------------------------------------
-// Same state layout as tile_potf2_inv, but the pivot chain is software-pipelined: right after the barrier of pivot j
-// the threads that hold column j+1 of A / row j+1 of W apply pivot j to THAT element first and publish it (and the
-// owner of d_{j+1} its reciprocal) before the remaining 30 FMAs of pivot j, so the chain per pivot is
-//   LDS -> DMUL -> DFMA -> (rcp) -> STS -> BAR   instead of   LDS -> DMUL -> 32 x DFMA -> rcp -> STS -> BAR,
-// and the bulk of the rank-1 update overlaps the owner's reciprocal.  The reciprocal is computed by every lane of the
-// owning group (no divergent branch); only the store is predicated.  NEWTON = Newton steps after MUFU.RCP64H.
+// reciprocal on the pivot chain: MUFU.RCP64H seed + NEWTON Newton steps (branch-free)
 template <int NEWTON>
 __device__ __forceinline__ double rcp_chain(double d) {
   double y;
@@ -195,95 +189,11 @@ __device__ __forceinline__ double rcp_chain(double d) {
   for (int it = 0; it < NEWTON; ++it) y = fma(y, fma(-d, y, 1.0), y);
   return y;
 }
-template <int NEWTON>
-__device__ __forceinline__ void tile_potf2_inv_pipe(const double* sa, double* lcol /*[2][72]*/, double* prow /*[2][64]*/, double* dvals /*[64]*/,
-                                                    double* __restrict__ Xg, int64_t ldx, double* __restrict__ Dg,
-                                                    double* __restrict__ logdet, int* __restrict__ status) {
-  constexpr int LCS = 72;
-  const int t = threadIdx.x, lo = t & 63, hi = t >> 6, g0 = hi * 16;
-  double xa[16], xw[16];
-#pragma unroll
-  for (int q = 0; q < 16; ++q) {
-    xa[q] = sa[lo * TLD + g0 + q];
-    xw[q] = (g0 + q == lo) ? 1.0 : 0.0;
-  }
-  if (hi == 0) {  // publish pivot 0
-    lcol[lo] = xa[0];
-    prow[lo] = xw[0];
-    double d = xa[0];
-    if (lo == 0) {
-      if (!(d > 0.0)) { atomicOr(status, ST_NOT_POSDEF); d = 1.0; }
-      lcol[64] = rcp_chain<NEWTON>(d);
-      dvals[0] = d;
-    }
-  }
-  __syncthreads();
-#pragma unroll 1
-  for (int J = 0; J < 4; ++J) {
-#pragma unroll
-    for (int jj = 0; jj < 16; ++jj) {
-      const int j = J * 16 + jj;
-      constexpr int dummy = 0; (void)dummy;
-      const int jn = (jj + 1) & 15;               // register index of column / row j+1 (compile-time)
-      const int Jn = J + (jj == 15 ? 1 : 0);      // group that holds it (warp-uniform)
-      const double* lc = lcol + (jj & 1) * LCS;
-      const double* pr = prow + (jj & 1) * TNB;
-      double* lcn = lcol + ((jj + 1) & 1) * LCS;
-      double* prn = prow + ((jj + 1) & 1) * TNB;
-      if (hi >= J) {
-        const double inv_d = lc[64];
-        const double ga = (lo > j) ? -lc[lo] * inv_d : 0.0;
-        const double gw = (lo <= j) ? -pr[lo] * inv_d : 0.0;
-        double l16[16];
-#pragma unroll
-        for (int q = 0; q < 16; q += 2) {
-          double2 v = *reinterpret_cast<const double2*>(lc + g0 + q);
-          l16[q] = v.x; l16[q + 1] = v.y;
-        }
-        if (hi == Jn && j < TNB - 1) {            // critical element first, then publish pivot j+1
-          xa[jn] = fma(l16[jn], ga, xa[jn]);
-          xw[jn] = fma(l16[jn], gw, xw[jn]);
-          lcn[lo] = xa[jn];
-          prn[lo] = xw[jn];
-          double d = xa[jn];
-          const bool own = (lo == j + 1);
-          if (own && !(d > 0.0)) { atomicOr(status, ST_NOT_POSDEF); d = 1.0; }
-          const double y = rcp_chain<NEWTON>(d);
-          if (own) { lcn[64] = y; dvals[j + 1] = d; }
-        }
-        if (hi > J) {
-#pragma unroll
-          for (int q = 0; q < 16; ++q)
-            if (!(hi == Jn && q == jn)) { xa[q] = fma(l16[q], ga, xa[q]); xw[q] = fma(l16[q], gw, xw[q]); }
-        } else {
-#pragma unroll
-          for (int q = 0; q < 16; ++q)
-            if (q > jj && q != jn) { xa[q] = fma(l16[q], ga, xa[q]); xw[q] = fma(l16[q], gw, xw[q]); }
-        }
-      }
-      __syncthreads();
-    }
-  }
-#pragma unroll
-  for (int q = 0; q < 16; ++q) {
-    int i = g0 + q;
-    double v = (lo <= i) ? xw[q] * rsqrt(dvals[i]) : 0.0;   // X = diag(d)^-1/2 W
-    Xg[(int64_t)i * ldx + lo] = v;
-    Dg[i * TNB + lo] = v;
-  }
-  if (t < TNB) {
-    double l = warp_sum(log(dvals[t]));
-    if ((t & 31) == 0) atomicAdd(logdet, l);
-  }
-}
-
-// VAR: 0 = barrier-per-pivot reference version, 1 = pipelined publish with 2 Newton steps, 2 = pipelined, 1 Newton step
+// generation-1 tail (kept selectable with AGP_TAIL_VARIANT=0 as the A/B reference of agp_tail2.cuh); VAR is 0
 template <int VAR>
 __device__ __forceinline__ void tile_potf2_dispatch(const double* sa, double* vec, double* __restrict__ Xg, int64_t ldx,
                                                     double* __restrict__ Dg, double* __restrict__ logdet, int* __restrict__ status) {
-  if (VAR == 0) tile_potf2_inv(sa, vec, vec + 2 * 72, vec + 2 * 72 + 2 * TNB, Xg, ldx, Dg, logdet, status);
-  else if (VAR == 1) tile_potf2_inv_pipe<2>(sa, vec, vec + 2 * 72, vec + 2 * 72 + 2 * TNB, Xg, ldx, Dg, logdet, status);
-  else tile_potf2_inv_pipe<1>(sa, vec, vec + 2 * 72, vec + 2 * 72 + 2 * TNB, Xg, ldx, Dg, logdet, status);
+  tile_potf2_inv(sa, vec, vec + 2 * 72, vec + 2 * 72 + 2 * TNB, Xg, ldx, Dg, logdet, status);
 }
 
 // first diagonal block (no update precedes it)

@@ -1,17 +1,25 @@
 // standalone timing / correctness harness for the 64 x 64 Cholesky+inverse tile variants of agp_tail.cuh (run on the B200 box)
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 potf2_bench.cu -o potf2_bench
-#include "../../augmentedgaussianprocesses.jl_b200/csrc/agp_tail.cuh"
+#include "potf2_variants.cuh"
 #include <cstdio>
 #include <vector>
 #include <cmath>
 using namespace agp;
 template <int VAR>
+void launch1(const TailStepParams& p) {
+  if (VAR == 0) tail_potf2_first_kernel<0><<<1, POTF2_THREADS, TAIL_SMEM>>>(p);
+  else if (VAR == 1) potf2_pipe_kernel<2><<<1, POTF2_THREADS, TAIL_SMEM>>>(p);
+  else potf2_pipe_kernel<1><<<1, POTF2_THREADS, TAIL_SMEM>>>(p);
+}
+template <int VAR>
 void run(const char* name, const TailStepParams& p, const std::vector<double>& A, int n) {
-  cudaFuncSetAttribute(tail_potf2_first_kernel<VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM);
+  cudaFuncSetAttribute(tail_potf2_first_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM);
+  cudaFuncSetAttribute(potf2_pipe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM);
+  cudaFuncSetAttribute(potf2_pipe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  for (int w = 0; w < 3; ++w) tail_potf2_first_kernel<VAR><<<1, POTF2_THREADS, TAIL_SMEM>>>(p);
+  for (int w = 0; w < 3; ++w) launch1<VAR>(p);
   cudaEventRecord(e0);
-  for (int w = 0; w < 50; ++w) tail_potf2_first_kernel<VAR><<<1, POTF2_THREADS, TAIL_SMEM>>>(p);
+  for (int w = 0; w < 50; ++w) launch1<VAR>(p);
   cudaEventRecord(e1); cudaEventSynchronize(e1);
   float ms; cudaEventElapsedTime(&ms, e0, e1);
   std::vector<double> X(n * n); cudaMemcpy(X.data(), p.Xout, n * n * 8, cudaMemcpyDeviceToHost);
