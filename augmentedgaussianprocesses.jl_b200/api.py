@@ -583,9 +583,50 @@ class MOSVGP(AbstractGPModel):
         return f"Multioutput Sparse Variational Gaussian Process with the likelihoods {self.likelihoods} infered by {self.inference} "
 
 
-def VGP(*a, **k):
-    """models/VGP.jl -- the full (non-sparse) variational GP is O(n^3) and outside the accelerated hot path."""
-    raise NotImplementedError("VGP (full variational GP) is out of scope of the B200 engine; use SVGP")
+class VGP(AbstractGPModel):
+    """models/VGP.jl:22-75.  `VGP(X, y, kernel, likelihood, inference; optimiser=false)`: the full variational GP, trained with
+    `train(model, iterations)` on its own data.  On the device it is the SVGP algebra with Z = X, κ = I, K̃ = 0
+    (natural_gradient!(::VarLatent), analyticVI.jl:126-140); O(n³), so meant for n up to a few thousand."""
+
+    model_kind = L.MODEL_VGP
+
+    def __init__(self, X, y, kernel: Kernel, likelihood: AbstractLikelihood, inference: AnalyticVI, *, verbose: int = 0, optimiser=False,
+                 atfrequency: int = 1, mean=None, obsdim: int = 1, T=np.float64, precision: str = "f32", device: int = 0, stream=None):
+        if not isinstance(likelihood, AbstractLikelihood):
+            raise TypeError(f"The {likelihood} is not compatible or implemented with the {inference}")
+        self._common_init(inference, verbose, atfrequency, optimiser, False, T, precision, device, stream, None)
+        if inference.stoch:
+            raise ValueError("VGP is a full-batch model: use AnalyticVI()")
+        X = np.asarray(X, dtype=np.float64)
+        if X.ndim == 1:
+            X = X[:, None]
+        if X.ndim == 2 and obsdim == 2:
+            X = X.T
+        self.X = np.ascontiguousarray(X)
+        self.y = y
+        if len(y) != len(self.X):
+            raise ValueError(f"There is not the same number of samples in X ({len(self.X)}) and y ({len(y)})")
+        self.likelihood = likelihood
+        self.likelihoods = [likelihood]
+        self.kernel = kernel
+        self.Z = self.X
+        self.m, self.D = self.X.shape
+        self.n_latent = likelihood.n_latent
+        self.kernels = [kernel] * self.n_latent
+        self.Zs = [self.X] * self.n_latent
+        if mean is None:
+            self.mu0 = None
+        elif np.isscalar(mean):
+            self.mu0 = np.full(self.m, float(mean))
+        else:
+            raise NotImplementedError("only ZeroMean / ConstantMean priors cross the boundary (mu0 evaluated at X)")
+        self.A = None
+
+    def _desc(self, capacity: int) -> dict:
+        return _make_desc(self, capacity)
+
+    def __repr__(self):
+        return f"Variational Gaussian Process with a {self.likelihood} infered by {self.inference} "
 
 
 def _make_desc(model, capacity: int) -> dict:
@@ -680,7 +721,7 @@ def _upload(model, eng, X, ys, key):
     model._n = n
 
 
-def train(model: AbstractGPModel, X, y, iterations: int = 100, *, callback=None, convergence=None, state: Optional[State] = None,
+def train(model: AbstractGPModel, X=None, y=None, iterations: int = 100, *, callback=None, convergence=None, state: Optional[State] = None,
           obsdim: int = 1, minibatches: Optional[Sequence[np.ndarray]] = None, rng=None, check_every: int = 1):
     """`train!(model, X, y, iterations; callback, state)`.
 
@@ -689,6 +730,13 @@ def train(model: AbstractGPModel, X, y, iterations: int = 100, *, callback=None,
     inject the lists).  check_every: read the device status back every k iterations (1 = after every
     step, like the reference's immediate error).
     """
+    if isinstance(model, VGP):   # train!(model::VGP, iterations): the model carries its data (models/VGP.jl)
+        if isinstance(X, (int, np.integer)) and y is None:
+            iterations, X = int(X), None
+        if X is None:
+            X, y = model.X, model.y
+    elif X is None or y is None:
+        raise TypeError("train(model, X, y, iterations) needs the data for sparse models")
     if iterations <= 0:
         raise ValueError("Number of iterations should be positive")
     X = np.asarray(X)

@@ -109,6 +109,8 @@ struct Engine : EngineBase {
   double rm_kappa, rm_tau, jitter;
   std::vector<int> h_lik_kind;
   std::vector<double> h_p0, h_p1, h_A;
+  bool is_vgp = false;   // AGP_MODEL_VGP: full variational GP = the SVGP algebra with Z = X, kappa = I, Ktilde = 0
+  bool vgp_identity = false;   // set around the step / ELBO moment passes (prediction uses the ordinary sparse formulas)
   bool is_lsm = false;   // class-index labels (LogisticSoftMax)
   bool is_het = false;   // HeteroscedasticLikelihood: 2 latents (f, g), one real-valued target
   bool need_lam = false; // some likelihood re-estimates its link parameter lambda in local_updates! (Poisson, Heteroscedastic)
@@ -244,11 +246,14 @@ struct Engine : EngineBase {
   // ---- construction ---------------------------------------------------------------------------------
   int init(agp_ctx* c, const agp_model_desc* d) {
     ctx = c;
-    model_kind = d->model_kind; Qg = d->n_latent_global; qbeg = d->latent_begin; Ql = d->n_latent_local;
+    model_kind = d->model_kind;
+    if (model_kind == AGP_MODEL_VGP) { is_vgp = true; model_kind = AGP_MODEL_SVGP; }
+    Qg = d->n_latent_global; qbeg = d->latent_begin; Ql = d->n_latent_local;
     m = d->m; D = d->D; Bcap = d->batch_capacity; prec = d->precision; stochastic = d->stochastic;
     rm_kappa = d->rm_kappa; rm_tau = d->rm_tau; jitter = d->jitter; nT = d->n_task;
     if (Qg < 1 || Ql < 1 || qbeg < 0 || qbeg + Ql > Qg || m < 1 || D < 1 || Bcap < 1 || nT < 1) BAD("bad model sizes");
     if (!d->lik_kind || !d->kernel_kind || !d->kernel_scale || !d->kernel_variance || !d->Z) BAD("null descriptor array");
+    if (is_vgp && stochastic) BAD("VGP is a full-batch model: use AnalyticVI (models/VGP.jl)");
     if (stochastic && !(rm_kappa > 0.5 && rm_kappa <= 1.0 && rm_tau > 0)) BAD("kappa should be in the interval (0.5,1], tau positive");
     Dp = (int)rup(D, 4); ldm = rup(m, 4); ldB = rup(Bcap, 4);
     int nblk = (m + POTF2_NB - 1) / POTF2_NB, pw = 1;
@@ -283,6 +288,7 @@ struct Engine : EngineBase {
       h_A.assign(d->A, d->A + (size_t)nT * Qg);
       R = nT;
     } else BAD("unknown model kind");
+    if (is_vgp && Ql != Qg) BAD("VGP latents are not sharded");
     if (prec < 0 || prec > 2) BAD("unknown precision");
     if (prec == AGP_PREC_TF32X3 && !umma_shape_ok(m, Bcap)) BAD("TF32X3 precision needs m % 128 == 0 and batch_capacity % 128 == 0");
 
@@ -676,7 +682,15 @@ struct Engine : EngineBase {
                    double* var_out, int64_t out_ld, bool need_var, int stages = 3) {
     for (int q = 0; q < Ql; ++q) {
       Latent& L = lat[q];
-      if (stages & 1) {
+      if ((stages & 1) && vgp_identity) {
+        // full VGP: V = chol(K) (see vgp_fill_v_kernel); Ktilde = 0 is forced in the row statistics below
+        ph_begin(PH_KMAT);
+        if (B != m) { ph_end(); BAD("VGP steps are full-batch: B must equal the number of training points"); }
+        vgp_fill_v_kernel<T><<<dim3((int)((ldm + 127) / 128), B), 128, 0, st()>>>(L.Lc, mp, m, L.V, ldm);
+        ++launches;
+        if (prec == AGP_PREC_TF32X3) CK(cudaMemsetAsync(L.racc, 0, ldB * sizeof(double), st()));
+        ph_end();
+      } else if (stages & 1) {
         ph_begin(PH_KMAT);
         if (L.knm_tc) {
           CKS(umma_knm(ctx_err(), L.uk, (const float*)(const void*)Xsrc, Dp, Dp, gather, (const float*)(const void*)(gather ? xx_cur : xsrc),
@@ -735,12 +749,12 @@ struct Engine : EngineBase {
       } else if (prec == AGP_PREC_TF32X3)
         launch_chain(rowfinish_kernel, dim3((B + 255) / 256), dim3(256), 0, (const double*)L.racc, (const double*)(L.racc + ldB),
                      (const double*)(L.racc + 2 * ldB), B, L.variance + jitter, L.Ktilde, mean_out + (size_t)q * out_ld,
-                     var_out + (size_t)q * out_ld, status, fresh_kernel_matrices ? 1 : 0,
+                     var_out + (size_t)q * out_ld, status, vgp_identity ? 2 : (fresh_kernel_matrices ? 1 : 0),
                      (const int64_t*)((peer && mean_out == mean_f + (size_t)qbeg * ldB) ? d_xepoch : nullptr), par_stride);
       else
       rowstats_kernel<T><<<(B * 32 + 255) / 256, 256, 0, st()>>>(L.V, L.VS, L.tvec, B, m, ldm, L.variance + jitter,
                                                                  L.Ktilde, mean_out + (size_t)q * out_ld, var_out + (size_t)q * out_ld,
-                                                                 status, fresh_kernel_matrices ? 1 : 0,
+                                                                 status, vgp_identity ? 2 : (fresh_kernel_matrices ? 1 : 0),
                                                                  (const int64_t*)((peer && mean_out == mean_f + (size_t)qbeg * ldB) ? d_xepoch : nullptr), par_stride);
       ++launches;
       ph_end();
@@ -749,8 +763,11 @@ struct Engine : EngineBase {
     return AGP_OK;
   }
   int moments_impl(bool from_batch, int B, bool fresh, int stages = 3) {
-    CKS(moments_rows(from_batch ? Xb : X, from_batch ? xxb : xx, from_batch ? nullptr : idx_cur, B, fresh,
-                     mean_f + (size_t)qbeg * ldB, var_f + (size_t)qbeg * ldB, ldB, true, stages));
+    vgp_identity = is_vgp;
+    int sm_ = moments_rows(from_batch ? Xb : X, from_batch ? xxb : xx, from_batch ? nullptr : idx_cur, B, fresh,
+                           mean_f + (size_t)qbeg * ldB, var_f + (size_t)qbeg * ldB, ldB, true, stages);
+    vgp_identity = false;
+    CKS(sm_);
     if (peer && (stages & 2)) {   // publish the owned rows to every peer, then wait for theirs (device-side, graph-capturable)
       ph_begin(PH_ROWSTATS);
       peer_publish_kernel<<<(int)(((int64_t)Ql * B + 255) / 256), 256, 0, st()>>>(d_peers, peer_world, peer_rank, d_xepoch, par_stride, qbeg, Ql, ldB, B);
@@ -822,7 +839,7 @@ struct Engine : EngineBase {
   }
 
   bool can_fuse_lik() const {
-    return prec == AGP_PREC_TF32X3 && model_kind == AGP_MODEL_SVGP && Qg == 1 && Ql == 1 && !need_lam && !peer && !a_opt && !prof &&
+    return !is_vgp && prec == AGP_PREC_TF32X3 && model_kind == AGP_MODEL_SVGP && Qg == 1 && Ql == 1 && !need_lam && !peer && !a_opt && !prof &&
            !getenv("AGP_NO_FUSE_LIK");
   }
   LikParams lik_params(int B, bool from_batch, int update) {

@@ -116,7 +116,10 @@ __global__ void rowstats_kernel(const T* __restrict__ V, const T* __restrict__ V
   s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
   if (lane == 0) {
     double kt;
-    if (compute_ktilde) {
+    if (compute_ktilde == 2) {   // full VGP (kappa = I): var_f = diag(Sigma), no Ktilde (latentgp.jl:182-186)
+      kt = 0.0;
+      Ktilde[warp] = 0.0;
+    } else if (compute_ktilde) {
       kt = kdiag_jit - s1;
       Ktilde[warp] = kt;
       if (!(kt > 0.0)) atomicOr(status, ST_KTILDE);  // latentgp.jl:213
@@ -138,7 +141,10 @@ __global__ void rowfinish_kernel(const double* __restrict__ sumsq_v, const doubl
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   double kt;
-  if (compute_ktilde) {
+  if (compute_ktilde == 2) {     // full VGP (kappa = I)
+    kt = 0.0;
+    Ktilde[b] = 0.0;
+  } else if (compute_ktilde) {
     kt = kdiag_jit - sumsq_v[b];
     Ktilde[b] = kt;
     if (!(kt > 0.0)) atomicOr(status, ST_KTILDE);  // latentgp.jl:213
@@ -477,6 +483,15 @@ __global__ void update_A_adam_kernel(double* __restrict__ A, const double* __res
   if (q < Q) A[t * Q + q] = an / sqrt(tot);
   __syncthreads();
   if (q == 0) { bt[2 * t] *= b1; bt[2 * t + 1] *= b2; }
+}
+
+// Full VGP (models/VGP.jl; natural_gradient!(::VarLatent) analyticVI.jl:126-140): with Z = X and kappa = I the whitened
+// "kappa" is V = K L^-T = L itself, so the step's V buffer is just the T shadow of chol(K) (zeros above the diagonal)
+template <typename T>
+__global__ void vgp_fill_v_kernel(const double* __restrict__ Lc, int64_t ldl, int n, T* __restrict__ V, int64_t ldv) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (j >= (int)ldv || i >= n) return;
+  V[(int64_t)i * ldv + j] = (j <= i && j < n) ? (T)Lc[(int64_t)i * ldl + j] : T(0);
 }
 
 // rowfinish_kernel + lik_update_kernel in one launch for the common single-latent case (SVGP, one latent, no lambda

@@ -56,6 +56,9 @@ extern "C" {
 
 #define AGP_MODEL_SVGP 0   /* models/SVGP.jl:22-80: one likelihood, n_latent(likelihood) latents */
 #define AGP_MODEL_MOSVGP 1 /* models/MOSVGP.jl:22-115: T single-latent tasks mixed from Q latents */
+#define AGP_MODEL_VGP 2    /* models/VGP.jl: full variational GP (natural_gradient!(::VarLatent), analyticVI.jl:126-140):
+                              pass Z = the n training inputs (m = n), AnalyticVI (stochastic = 0), and step with the full
+                              index list (B = n); the engine then runs the SVGP algebra with kappa = I, Ktilde = 0 */
 
 /* arithmetic of the B x m contractions; the m x m tail (eta update, Cholesky, inverse) is always f64 */
 #define AGP_PREC_F64 0    /* everything in fp64 SIMT: bit-for-bit algorithm of the oracle        */

@@ -798,6 +798,63 @@ def _view_y(y, idx):
 
 
 # --------------------------------------------------------------------------------------
+# VGP (models/VGP.jl): full variational GP, AnalyticVI only (n x n)
+# --------------------------------------------------------------------------------------
+class VGP:
+    """models/VGP.jl:22-75; natural_gradient!(::VarLatent) analyticVI.jl:126-140; mean_f / var_f of a full latent
+    (gpblocks/latentgp.jl:174-186: mean, diag(cov)); global_update! inference.jl:25-28; ELBO analyticVI.jl:255-274."""
+
+    def __init__(self, X, y, kernel: Kernel, likelihood, inference: AnalyticVI, mean=None, jitter=JITTER_F64):
+        if inference.stoch:
+            raise ValueError("VGP takes a full-batch inference (AnalyticVI)")
+        self.X = np.asarray(X, dtype=np.float64)
+        self.likelihood = likelihood
+        self.y = treat_labels(y, likelihood)
+        self.inference = inference
+        self.jitter = jitter
+        n = self.X.shape[0]
+        inference.batchsize = n
+        inference.rho = 1.0
+        self.f = [SparseVarLatent(self.X, kernel, mean) for _ in range(likelihood.n_latent)]  # container: Z = X, posterior init identical
+        self.local_vars = init_local_vars(likelihood, n)
+        self.L = None
+        self.trained = False
+
+    def moments(self):
+        return np.stack([gp.mu for gp in self.f]), np.stack([np.diag(gp.Sigma) for gp in self.f])
+
+    def step(self):
+        if self.L is None:  # compute_K (latentgp.jl:205-207), once (hyper-parameters fixed)
+            self.L = [compute_K(gp, self.jitter) for gp in self.f]
+        mu, var = self.moments()
+        lv = local_updates(self.local_vars, self.likelihood, self.y, mu, var)
+        gmu, gS = grad_E_mu(self.likelihood, self.y, lv), grad_E_Sigma(self.likelihood, self.y, lv)
+        for k, (gp, L) in enumerate(zip(self.f, self.L)):
+            Kinv = sla.cho_solve((L, True), np.eye(gp.dim))
+            gp.eta1 = gmu[k] + sla.cho_solve((L, True), gp.mu0)
+            gp.eta2 = -_symmetric_upper(np.diag(gS[k]) + Kinv / 2.0)
+            global_update(gp)
+
+    def ELBO(self):
+        mu, var = self.moments()
+        tot = expec_loglikelihood(self.likelihood, self.y, mu, var, self.local_vars)
+        tot -= sum(GaussianKL(gp.mu, gp.mu0, gp.Sigma, L) for gp, L in zip(self.f, self.L))
+        tot -= AugmentedKL(self.likelihood, self.local_vars, self.y)
+        return float(tot)
+
+
+def train_vgp(model: VGP, iterations=100):
+    """train!(model::VGP, iterations) (training/training.jl:13-111 with the model's own data)"""
+    if iterations <= 0:
+        raise ValueError("Number of iterations should be positive")
+    for _ in range(iterations):
+        model.step()
+        model.trained = True
+        model.inference.n_iter += 1
+    return model
+
+
+# --------------------------------------------------------------------------------------
 # MOSVGP (models/MOSVGP.jl, single_and_multi_output_utils.jl:24-118)
 # --------------------------------------------------------------------------------------
 @dataclass

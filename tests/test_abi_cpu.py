@@ -85,5 +85,7 @@ def test_constructor_and_argument_errors(agp):
         agp.treat_labels([1, 2, 3, 4], agp.LogisticSoftMaxLikelihood(3))
     mu, S, e1, e2 = m.posterior(0)  # posterior.jl:29-37 before any training
     assert np.all(mu == 0) and np.array_equal(S, np.eye(5)) and np.array_equal(e2, -0.5 * np.eye(5))
-    with pytest.raises(NotImplementedError):
-        agp.VGP()
+    with pytest.raises(ValueError):   # VGP is full-batch (models/VGP.jl)
+        agp.VGP(np.random.randn(6, 2), np.ones(6), k, agp.GaussianLikelihood(), agp.AnalyticSVI(3))
+    with pytest.raises(ValueError):   # sample-count check (data/utils.jl)
+        agp.VGP(np.random.randn(6, 2), np.ones(5), k, agp.GaussianLikelihood(), agp.AnalyticVI())

@@ -379,6 +379,28 @@ def test_mosvgp_update_A_parity(agp, precision):
     check_pair(agp, (mo, so), (me, se), 10 * tol if precision == "f32" else tol)
 
 
+@pytest.mark.parametrize("lik,precision", [("gaussian", "f64"), ("logistic", "f64"), ("studentt", "f32"), ("logisticsoftmax", "f64"), ("poisson", "f64")])
+def test_vgp_parity(agp, lik, precision):
+    """SURVEY 8 f4: the full VGP with AnalyticVI (natural_gradient!(::VarLatent), analyticVI.jl:126-140) against the oracle."""
+    n, D, iters = 160, 3, 6
+    X, y, _, _, F, rng = make_data(lik, n, D, 8, n, 1, seed=4)
+    sc = 1.0 / np.sqrt(D)
+    mo = O.VGP(X, y, oracle_kernel(O, "sqexp", sc, 1.5), oracle_lik(O, lik), O.AnalyticVI())
+    mo = O.train_vgp(mo, iters)
+    me = agp.VGP(X, y, engine_kernel(agp, "sqexp", sc, 1.5), engine_lik(agp, lik), agp.AnalyticVI(), precision=precision)
+    me, se = agp.train(me, iters)
+    tol = TOL[precision] if precision == "f64" else 20 * TOL[precision]   # cond(K) ~ 1e4 at jitter 1e-4 amplifies fp32 rounding
+    for q, gp in enumerate(mo.f):
+        mu, S, e1, e2 = me.posterior(q)
+        assert rel_fro(mu, gp.mu) < tol, ("mu", q, rel_fro(mu, gp.mu))
+        assert rel_fro(S, gp.Sigma) < tol, ("Sigma", q, rel_fro(S, gp.Sigma))
+    assert abs(agp.ELBO(me, se) - mo.ELBO()) <= 5 * tol * max(1.0, abs(mo.ELBO()))
+    Xt = rng.standard_normal((40, D))
+    mu_o, var_o = O.predict_f(mo, Xt, cov=True)
+    mu_e, var_e = agp.predict_f(me, Xt, cov=True)
+    assert rel_fro(np.atleast_2d(np.asarray(mu_e)), mu_o) < 10 * tol and rel_fro(np.atleast_2d(np.asarray(var_e)), var_o) < 10 * tol
+
+
 def test_latent_sharded_two_gpus_match_single_gpu():
     """latent-sharded run (one rank per GPU, moments exchanged over NVLink peer memory inside the step, and the
     NCCL all-gather fallback) against the same model on one GPU.  Needs two visible GPUs (skipped otherwise)."""

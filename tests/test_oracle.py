@@ -177,6 +177,20 @@ def test_gaussian_avi_is_exact_posterior():
     assert rel_fro(m.f[0].Sigma, S) < 1e-8 and rel_fro(m.f[0].mu, S @ kap.T @ y / 1e-2) < 1e-8
 
 
+def test_vgp_gaussian_is_exact_gp_posterior():
+    """VGP + Gaussian likelihood: one CAVI step gives the exact GP posterior N(K (K + s2 I)^-1 y, K - K (K + s2 I)^-1 K)."""
+    X, y, _, _, F, rng = make_data("gaussian", 60, 2, 5, 60, 1, seed=6)
+    k = oracle_kernel(O, "sqexp", 1.0, 1.0)
+    m = O.train_vgp(O.VGP(X, y, k, O.GaussianLikelihood(1e-2), O.AnalyticVI()), 1)
+    K = O.kernelmatrix(k, X) + 1e-4 * np.eye(60)
+    S = K - K @ np.linalg.solve(K + 1e-2 * np.eye(60), K)
+    assert rel_fro(m.f[0].mu, K @ np.linalg.solve(K + 1e-2 * np.eye(60), y)) < 1e-8
+    assert rel_fro(m.f[0].Sigma, S) < 1e-6
+    assert np.isfinite(m.ELBO())
+    with pytest.raises(ValueError):
+        O.VGP(X, y, k, O.GaussianLikelihood(1e-2), O.AnalyticSVI(10))
+
+
 def test_ktilde_error():
     X, y, Z, mbs, F, rng = make_data("gaussian", 100, 2, 8, 20, 1)
     m = O.SVGP(O.Kernel("sqexp"), O.GaussianLikelihood(), O.AnalyticSVI(20), Z, jitter=-0.5)
