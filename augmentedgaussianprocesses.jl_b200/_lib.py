@@ -89,6 +89,7 @@ SIGNATURES = {
     "agp_get_A": (C.c_int, [C.c_void_p, c_double_p]),
     "agp_peer_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "agp_peer_attach": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "agp_peer_detach": (C.c_int, [C.c_void_p]),
     "agp_set_quadrature": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int32]),
     "agp_get_lik_param": (C.c_int, [C.c_void_p, C.c_int32, c_double_p]),
     "agp_set_lik_param": (C.c_int, [C.c_void_p, C.c_int32, C.c_double]),

@@ -852,12 +852,20 @@ def _attach_peers(model, eng) -> bool:
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() != model.world:
         return False
     h = C.create_string_buffer(64)
-    eng.ck(eng.lib.agp_peer_export(eng.model, h))
+    ok = eng.lib.agp_peer_export(eng.model, h) == L.AGP_OK
     hs = [None] * model.world
-    dist.all_gather_object(hs, bytes(h.raw))
-    blob = C.create_string_buffer(b"".join(hs), 64 * model.world)
-    eng.ck(eng.lib.agp_peer_attach(eng.model, model.world, model.rank, blob))
-    dist.barrier()
+    dist.all_gather_object(hs, bytes(h.raw) if ok else b"")
+    attached = False
+    if all(len(x) == 64 for x in hs):
+        blob = C.create_string_buffer(b"".join(hs), 64 * model.world)
+        attached = eng.lib.agp_peer_attach(eng.model, model.world, model.rank, blob) == L.AGP_OK
+    # every rank must end up in the same mode: one failure (IPC not permitted, no P2P path) sends everybody to the NCCL fallback
+    votes = [None] * model.world
+    dist.all_gather_object(votes, bool(attached))
+    if not all(votes):
+        if attached:
+            eng.ck(eng.lib.agp_peer_detach(eng.model))
+        return False
     return True
 
 

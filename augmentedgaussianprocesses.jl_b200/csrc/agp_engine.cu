@@ -89,6 +89,7 @@ struct EngineBase {
   virtual int get_A(double* A) = 0;
   virtual int peer_export(void* handle64) = 0;
   virtual int peer_attach(int world, int rank, const void* handles) = 0;
+  virtual int peer_detach() = 0;
   virtual int profile_enable(int on) = 0;
   virtual int profile_read(int maxp, const char** names, double* ms, int64_t* launches) = 0;
   virtual int64_t launch_count() = 0;
@@ -834,6 +835,15 @@ struct Engine : EngineBase {
     CKS(dalloc(&d_peers, world));
     CK(cudaMemcpy(d_peers, ptrs.data(), world * sizeof(double*), cudaMemcpyHostToDevice));
     peer_world = world; peer_rank = rank; peer = true;
+    drop_graph();
+    return AGP_OK;
+  }
+  int peer_detach() override {   // back to the host-driven (NCCL) exchange, e.g. when another rank could not map the peers
+    CK(cudaStreamSynchronize(st()));
+    for (void* q : peer_opened) cudaIpcCloseMemHandle(q);
+    peer_opened.clear();
+    if (d_peers) { cudaFree(d_peers); d_peers = nullptr; }
+    peer = false; peer_world = 1; peer_rank = 0;
     drop_graph();
     return AGP_OK;
   }
@@ -1633,6 +1643,7 @@ int agp_set_A_optimiser(agp_model* model, int32_t kind, double eta, double beta1
 int agp_get_A(agp_model* model, double* A) { ENG(model); return e->get_A(A); }
 int agp_peer_export(agp_model* model, void* handle64) { ENG(model); return e->peer_export(handle64); }
 int agp_peer_attach(agp_model* model, int32_t world, int32_t rank, const void* handles) { ENG(model); return e->peer_attach(world, rank, handles); }
+int agp_peer_detach(agp_model* model) { ENG(model); return e->peer_detach(); }
 int agp_set_quadrature(agp_model* model, const double* nodes, const double* weights, int32_t n_nodes) {
   ENG(model); return e->set_quadrature(nodes, weights, n_nodes);
 }

@@ -179,6 +179,8 @@ int agp_get_A(agp_model* model, double* A);
  * agp_step / agp_step_async (incl. resident lists + agp_use_graph) become usable on a sharded model. */
 int agp_peer_export(agp_model* model, void* handle64);
 int agp_peer_attach(agp_model* model, int32_t world, int32_t rank, const void* handles /* [world][64] */);
+/* undo agp_peer_attach (all ranks must agree: a rank that failed to map its peers makes everybody fall back) */
+int agp_peer_detach(agp_model* model);
 
 /* ---- ELBO(model, state, y) (inference/analyticVI.jl:255-297) on the last minibatch -----------
  * out[0] = rho * expec_loglikelihood, out[1] = GaussianKL summed over OWNED latents
