@@ -379,6 +379,58 @@ def test_mosvgp_update_A_parity(agp, precision):
     check_pair(agp, (mo, so), (me, se), 10 * tol if precision == "f32" else tol)
 
 
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_ragged_sizes_layouts_and_host_batch_path(agp, precision):
+    """Edge cases of the boundary: m, B, D that are multiples of nothing (padding paths), Julia's column-major X, float32 X,
+    1-based index lists, and the host-batch entry point agp_step_batch (the x, y views update_parameters! receives) with and
+    without the CUDA graph -- all against the same oracle run."""
+    import ctypes as C
+
+    n, D, m, B, iters = 333, 5, 37, 101, 5
+    X, y, Z, mbs, F, rng = make_data("logistic", n, D, m, B, iters, seed=12)
+    sc = 1.0 / np.sqrt(D)
+    mo = O.SVGP(O.Kernel("matern32", scale=sc), O.LogisticLikelihood(), O.AnalyticSVI(B), Z)
+    mo, so = O.train(mo, X, y, iters, minibatches=mbs)
+    tol = TOL[precision]
+    L = agp._lib
+
+    def fresh():
+        return agp.SVGP(agp.Matern32Kernel() @ agp.ScaleTransform(sc), agp.LogisticLikelihood(), agp.AnalyticSVI(B), Z, precision=precision)
+
+    # (1) column-major (Fortran / Julia) X through train
+    m1, s1 = agp.train(fresh(), np.asfortranarray(X), y, iters, minibatches=mbs)
+    assert rel_fro(m1.posterior(0)[0], mo.f[0].mu) < tol and rel_fro(m1.posterior(0)[1], mo.f[0].Sigma) < tol
+    # (2) float32 X (the oracle sees the same rounded values)
+    X32 = X.astype(np.float32)
+    mo32 = O.SVGP(O.Kernel("matern32", scale=sc), O.LogisticLikelihood(), O.AnalyticSVI(B), Z)
+    mo32, _ = O.train(mo32, X32.astype(np.float64), y, iters, minibatches=mbs)
+    m2, s2 = agp.train(fresh(), X32, y, iters, minibatches=mbs)
+    assert rel_fro(m2.posterior(0)[0], mo32.f[0].mu) < tol
+    # (3) 1-based index lists + (4) host-batch steps, graph off then on
+    for use_graph in (0, 1):
+        m3 = fresh()
+        m3, s3 = agp.train(m3, X, y, 1, minibatches=mbs[:1])
+        e = m3._eng
+        e.ck(e.lib.agp_use_graph(e.model, use_graph))
+        idx1 = (mbs[1] + 1).astype(np.int64)
+        e.ck(e.lib.agp_step(e.model, idx1.ctypes.data_as(L.c_int64_p), B, 1, n / B))          # iteration 2 by 1-based indices
+        for it in range(2, iters):                                                             # iterations 3.. from host arrays
+            xb = np.ascontiguousarray(X[mbs[it]]) if it % 2 else np.asfortranarray(X[mbs[it]])
+            yb = np.ascontiguousarray(y[mbs[it]], dtype=np.float64)
+            arr = (C.c_void_p * 1)(yb.ctypes.data)
+            e.ck(e.lib.agp_step_batch(e.model, C.c_void_p(xb.ctypes.data), L.DTYPE_F64, L.LAYOUT_ROWMAJOR if it % 2 else L.LAYOUT_COLMAJOR,
+                                      arr, L.Y_REAL, B, n / B))
+        assert rel_fro(m3.posterior(0)[0], mo.f[0].mu) < tol, use_graph
+        assert rel_fro(m3.posterior(0)[1], mo.f[0].Sigma) < tol, use_graph
+    # argument errors surface as AGP_ERR_BAD_ARG with the reference's message (training/training.jl:27-29)
+    bad = np.array([n + 5] * B, dtype=np.int64)
+    with pytest.raises(agp.AGPError) as ei:
+        e.ck(e.lib.agp_step(e.model, bad.ctypes.data_as(L.c_int64_p), B, 0, n / B))
+    assert ei.value.code == L.AGP_ERR_BAD_ARG
+    with pytest.raises(agp.AGPError):
+        e.ck(e.lib.agp_step(e.model, idx1.ctypes.data_as(L.c_int64_p), 10 * B, 1, n / B))
+
+
 @pytest.mark.parametrize("lik,precision", [("gaussian", "f64"), ("logistic", "f64"), ("studentt", "f32"), ("logisticsoftmax", "f64"), ("poisson", "f64")])
 def test_vgp_parity(agp, lik, precision):
     """SURVEY 8 f4: the full VGP with AnalyticVI (natural_gradient!(::VarLatent), analyticVI.jl:126-140) against the oracle."""
