@@ -31,6 +31,7 @@ from .api import (
     SVGP,
     VGP,
     create_mapping,
+    hyper_grads,
     is_stochastic,
     objective,
     predict_f,

@@ -282,6 +282,18 @@ class ADAM:
     def __init__(self, eta: float = 0.001, beta=(0.9, 0.999), epsilon: float = 1e-8):
         self.eta, self.beta, self.epsilon = float(eta), (float(beta[0]), float(beta[1])), float(epsilon)
 
+    # Optimisers.init / Optimisers.apply (host side: used for the handful of kernel parameters and the m x D inducing points)
+    def init(self, x):
+        return dict(mt=np.zeros_like(x, dtype=np.float64), vt=np.zeros_like(x, dtype=np.float64), bt=np.array(self.beta))
+
+    def apply(self, st, g):
+        b1, b2 = self.beta
+        st["mt"] = b1 * st["mt"] + (1.0 - b1) * g
+        st["vt"] = b2 * st["vt"] + (1.0 - b2) * g**2
+        step = st["mt"] / (1.0 - st["bt"][0]) / (np.sqrt(st["vt"] / (1.0 - st["bt"][1])) + self.epsilon) * self.eta
+        st["bt"] = st["bt"] * np.array(self.beta)
+        return st, step
+
 
 class AnalyticVI:
     """inference/analyticVI.jl:1-14.  `AnalyticVI()` = full batch, `AnalyticSVI(B)` = stochastic."""
@@ -395,11 +407,17 @@ class AbstractGPModel:
                 "The inference object should be of type `VariationalInference` : either `AnalyticVI` or `NumericalVI`"
                 " (only AnalyticVI / AnalyticSVI are accelerated)"
             )
-        if optimiser not in (None, False) or Zoptimiser not in (None, False):
-            raise NotImplementedError(
-                "kernel / inducing-point hyper-parameter optimisation (Zygote path, hyperparameter/autotuning.jl) "
-                "is outside the accelerated path: pass optimiser=False, Zoptimiser=False"
-            )
+        # optimiser / Zoptimiser (SVGP.jl:33-44): `true` means ADAM(0.01) like the reference; only ADAM is implemented
+        def _opt(o):
+            if o is None or o is False:
+                return None
+            if o is True:
+                return ADAM(0.01)
+            if isinstance(o, ADAM):
+                return o
+            raise NotImplementedError("only ADAM is implemented for the hyper-parameter optimisers")
+        self.optimiser, self.Zoptimiser = _opt(optimiser), _opt(Zoptimiser)
+        self._hyperopt_state = None
         if T not in JITTER:
             raise TypeError("T must be np.float64 / np.float32 / np.float16")
         if precision not in L.PRECISIONS:
@@ -788,9 +806,58 @@ def train(model: AbstractGPModel, X=None, y=None, iterations: int = 100, *, call
         model.trained = True
         if callback is not None:
             callback(model, state, inf.n_iter)
+        # training/training.jl:65-69 : hyper-parameters every `atfrequency` iterations, from the 4th on, never on the last one
+        if (model.optimiser is not None or model.Zoptimiser is not None) and inf.n_iter % model.atfrequency == 0 and inf.n_iter >= 3 \
+                and it != iterations - 1:
+            update_hyperparameters(model, eng)
+            eng.ck(lib.agp_refresh_K(eng.model))   # compute_kernel_matrices with HPupdated (training.jl:187-208)
         inf.n_iter += 1
     _refresh_lik_params(model, eng)
     return model, state
+
+
+def hyper_grads(model, eng=None):
+    """ELBO gradients w.r.t. kernel scale / variance / inducing points of the owned latents on the last minibatch (agp_hyper_grads).
+    Returns a list of dict(scale=, variance=, Z=(m, D))."""
+    eng = eng or model._eng
+    ql = model.n_latent_local
+    ds, dv, dZ = np.zeros(ql), np.zeros(ql), np.zeros((ql, model.m, model.D))
+    eng.ck(eng.lib.agp_hyper_grads(eng.model, float(model.inference.rho), L.dptr(ds), L.dptr(dv), L.dptr(dZ)))
+    return [dict(scale=float(ds[q]), variance=float(dv[q]), Z=dZ[q]) for q in range(ql)]
+
+
+def update_hyperparameters(model, eng):
+    """update_hyperparameters! for sparse models (hyperparameter/autotuning.jl:86-140): gradients from the device, ADAM on the log
+    of the positive kernel parameters (update_kernel!, autotuning_utils.jl:63-67) and on the inducing points (update_Z!, :78-82)
+    on the host, new values pushed with agp_set_kernel / agp_set_Z."""
+    grads = hyper_grads(model, eng)
+    q0, ql = model._latent_range()
+    if model._hyperopt_state is None:
+        model._hyperopt_state = [None] * ql
+    for q, g in enumerate(grads):
+        k = model.kernels[q0 + q]
+        st = model._hyperopt_state[q]
+        if st is None:
+            st = model._hyperopt_state[q] = dict(
+                scale=model.optimiser.init(np.zeros(1)) if model.optimiser else None,
+                variance=model.optimiser.init(np.zeros(1)) if model.optimiser else None,
+                Z=model.Zoptimiser.init(np.zeros((model.m, model.D))) if model.Zoptimiser else None)
+        new_scale, new_var = k.scale, k.variance
+        if model.optimiser is not None:
+            st["variance"], d = model.optimiser.apply(st["variance"], np.array([k.variance * g["variance"]]))
+            new_var = float(np.exp(np.log(k.variance) + d[0]))
+            st["scale"], d = model.optimiser.apply(st["scale"], np.array([k.scale * g["scale"]]))
+            new_scale = float(np.exp(np.log(k.scale) + d[0]))
+            model.kernels = list(model.kernels)
+            model.kernels[q0 + q] = Kernel(k.kind, new_scale, new_var)
+            eng.ck(eng.lib.agp_set_kernel(eng.model, q, k.kind, new_scale, new_var))
+        if model.Zoptimiser is not None:
+            st["Z"], dZ = model.Zoptimiser.apply(st["Z"], g["Z"])
+            model.Zs = list(model.Zs)
+            model.Zs[q0 + q] = np.ascontiguousarray(model.Zs[q0 + q] + dZ)
+            eng.ck(eng.lib.agp_set_Z(eng.model, q, L.dptr(model.Zs[q0 + q])))
+    if isinstance(model, SVGP):
+        model.kernel, model.Z = model.kernels[0], model.Zs[0]
 
 
 def _refresh_lik_params(model, eng):

@@ -13,6 +13,7 @@
 #include "agp_kernels.cuh"
 #include "agp_tail.cuh"
 #include "agp_tail2.cuh"
+#include "agp_hyper.cuh"
 #include "agp_umma.h"
 
 using namespace agp;
@@ -85,6 +86,8 @@ struct EngineBase {
   virtual int get_lik_param(int task, double* v) = 0;
   virtual int set_lik_param(int task, double v) = 0;
   virtual int proba_link(int link, double p0, const double* mu, const double* var, int64_t n, double* p, double* pv) = 0;
+  virtual int hyper_grads(double rho, double* d_scale, double* d_variance, double* dZ) = 0;
+  virtual int set_Z(int ql, const double* Z) = 0;
   virtual int set_A_optimiser(int kind, double eta, double b1, double b2, double eps) = 0;
   virtual int get_A(double* A) = 0;
   virtual int peer_export(void* handle64) = 0;
@@ -423,7 +426,8 @@ struct Engine : EngineBase {
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
     void* ps[] = {idx_prev, xx_cur, pKS, pXb, pxxb, X, xx, y_all, ycls_all, Xb, xxb, stage, idx_pool, idx_cur, counters, status, d_lik_kind, d_p0, d_p1, d_A,
-                  xchg, d_xepoch, d_peers, gmu, gS, lc, ltheta, lgamma_, lalpha, tmu, tvar, gm, gs, yb, ycls, d_out, d_lam, d_lamacc, d_qnodes, d_qw, d_lr, d_gradA, d_Amt, d_Avt, d_Abt};
+                  xchg, d_xepoch, d_peers, gmu, gS, lc, ltheta, lgamma_, lalpha, tmu, tvar, gm, gs, yb, ycls, d_out, d_lam, d_lamacc, d_qnodes, d_qw, d_lr, d_gradA, d_Amt, d_Avt, d_Abt,
+                  hgH[0], hgH[1], hgH[2], hgH[3], hgX, hgA, hgB, hgM1, hgM2, hgV, hgP};
     for (void* p : ps) cudaFree(p);
   }
 
@@ -777,6 +781,117 @@ struct Engine : EngineBase {
       ph_end();
       CK(cudaGetLastError());
     }
+    return AGP_OK;
+  }
+
+  // ---- hyper-parameter / inducing-point gradients of the ELBO (agp_hyper.cuh) -----------------------------------
+  double *hgH[4] = {nullptr, nullptr, nullptr, nullptr}, *hgX = nullptr, *hgA = nullptr, *hgB = nullptr, *hgM1 = nullptr, *hgM2 = nullptr,
+         *hgV = nullptr, *hgP = nullptr;
+  void dgemm_bm(bool a_t, bool b_t, const double* A, int64_t lda, const double* Bm, int64_t ldb, double* Cc, int64_t ldc, int M, int N, int K,
+                double alpha) {
+    GemmParams<double> g{};
+    g.A = A; g.lda = lda; g.B = Bm; g.ldb = ldb; g.C = Cc; g.ldc = ldc; g.M = M; g.N = N; g.K = K; g.alpha = alpha; g.beta = 0.0;
+    if (!a_t && !b_t) gemm_simt_launch<double, false, false, EPI_PLAIN>(g, 1, st());
+    else if (!a_t && b_t) gemm_simt_launch<double, false, true, EPI_PLAIN>(g, 1, st());
+    else gemm_simt_launch<double, true, true, EPI_PLAIN>(g, 1, st());
+    ++launches;
+  }
+  int hyper_grads(double rho, double* d_scale, double* d_variance, double* dZ) override {
+    if (!d_scale || !d_variance) BAD("null output");
+    if (curB < 1 || !have_step) { ctx->err = "hyper-parameter gradients need a completed step (the last minibatch is differentiated)"; return AGP_ERR_STATE; }
+    const int B = curB;
+    const int64_t ldh = rup(m, 4);
+    // moments under the updated posterior (like ELBO(model, state, y)); sharded models exchange them here (collective call)
+    CKS(elbo_moments());
+    LikParams lp = lik_params(B, true, 0);
+    if (model_kind == AGP_MODEL_MOSVGP) { lik_update_kernel<<<(B + 127) / 128, 128, 0, st()>>>(lp); ++launches; }
+    if (!hgA) {
+      for (int i = 0; i < 4; ++i) CKS(dalloc(&hgH[i], (size_t)Bcap * ldh));
+      CKS(dalloc(&hgX, (size_t)Bcap * Dp)); CKS(dalloc(&hgA, (size_t)Ql * ldB)); CKS(dalloc(&hgB, (size_t)Ql * ldB));
+      CKS(dalloc(&hgM1, (size_t)mp * mp)); CKS(dalloc(&hgM2, (size_t)mp * mp)); CKS(dalloc(&hgV, 8 * (size_t)mp + 16)); CKS(dalloc(&hgP, 2 * (size_t)mp * Dp));
+    }
+    hg_ab_kernel<<<(B + 127) / 128, 128, 0, st()>>>(lp, hgA, hgB);
+    hg_gather_x_kernel<T><<<(B + 7) / 8, dim3(32, 8), 0, st()>>>(cur_from_batch ? Xb : X, Dp, cur_from_batch ? nullptr : idx_cur, B, D, hgX, Dp);
+    launches += 2;
+    double *Knm = hgH[0], *kap = hgH[1], *Tm = hgH[2], *MK = hgH[3];
+    double *mu_c = hgV, *dvec = hgV + mp, *vvec = hgV + 2 * mp, *cs1 = hgV + 3 * mp, *cs2 = hgV + 4 * mp, *rs2 = hgV + 5 * mp, *sc = hgV + 6 * mp;  // sc: scalars
+    std::vector<double> hz((size_t)m * D);
+    for (int q = 0; q < Ql; ++q) {
+      Latent& L = lat[q];
+      // canonical mu, Sigma (fp64): mu = L mu_v, Sigma = L (X^T X) L^T
+      ensure_muv(L);
+      symv_kernel<<<(m * 32 + 255) / 256, 256, 0, st()>>>(L.Lc, mp, m, L.muv, mu_c); ++launches;
+      dgemm(true, true, L.Xv, L.Xv, L.X, 1.0, 0.0);
+      dgemm(false, false, L.X, L.Lc, L.W, 1.0, 0.0);
+      dgemm(false, true, L.Lc, L.W, L.X, 1.0, 0.0);                       // L.X = Sigma
+      // K_nm in fp64 from row differences is not needed for the products: GEMM form with exact fp64 norms
+      { GemmParams<double> g{};
+        g.A = hgX; g.lda = Dp; g.B = L.Zd; g.ldb = Dp; g.C = Knm; g.ldc = ldh; g.M = B; g.N = m; g.K = D; g.alpha = 1.0;
+        CK(cudaMemsetAsync(sc, 0, 16 * sizeof(double), st()));
+        hg_rownorm_kernel<<<(B + 127) / 128, 128, 0, st()>>>(hgX, Dp, B, D, Tm);                 // |x|^2 (Tm as scratch vector)
+        g.xx = Tm; g.xx_direct = 1; g.zz = L.zzd; g.scale2 = L.scale * L.scale; g.variance = L.variance; g.kernel_kind = L.kind;
+        gemm_simt_launch<double, false, false, EPI_KERNELFN>(g, 1, st()); launches += 2; }
+      dgemm_bm(false, true, Knm, ldh, L.Kinv, mp, kap, ldh, B, m, m, 1.0);                         // kappa = Knm K^-1
+      dgemm_bm(false, true, kap, ldh, L.X, mp, Tm, ldh, B, m, m, 1.0);                             // T = kappa Sigma
+      hg_M_kernel<<<dim3((m + 127) / 128, B), 128, 0, st()>>>(Tm, Knm, ldh, B, m, hgA + (size_t)q * ldB, hgB + (size_t)q * ldB, mu_c); ++launches;
+      dgemm_bm(false, true, Tm, ldh, L.Kinv, mp, MK, ldh, B, m, m, 1.0);                           // MK = M K^-1
+      dgemm_bm(true, true, kap, ldh, MK, ldh, hgM1, mp, m, m, B, -rho);                            // Acc = -rho kappa^T MK
+      hg_Anm_kernel<<<dim3((m + 127) / 128, B), 128, 0, st()>>>(Tm, MK, kap, ldh, B, m, hgB + (size_t)q * ldB, rho); ++launches;   // Tm = A_nm
+      // KL part: Kinv Sigma Kinv and v = Kinv (mu - mu0)
+      dgemm(false, true, L.Kinv, L.X, L.W, 1.0, 0.0);                     // W = Kinv Sigma
+      dgemm(false, true, L.W, L.Kinv, L.P, 1.0, 0.0);                     // P = Kinv Sigma Kinv
+      hg_sub_kernel<<<(m + 127) / 128, 128, 0, st()>>>(mu_c, L.mu0, m, dvec);
+      symv_kernel<<<(m * 32 + 255) / 256, 256, 0, st()>>>(L.Kinv, mp, m, dvec, vvec);
+      hg_Amm_kernel<<<dim3((m + 127) / 128, m), 128, 0, st()>>>(hgM2, hgM1, L.Kinv, L.P, vvec, mp, m);
+      launches += 3;
+      // contractions with the kernel derivatives
+      CK(cudaMemsetAsync(cs1, 0, 3 * (size_t)mp * sizeof(double), st()));
+      const size_t shb = 8 * (size_t)D * sizeof(double);
+      hg_contract_kernel<<<dim3((m + 127) / 128, (B + 7) / 8), 128, shb, st()>>>(Tm, ldh, B, m, hgX, Dp, L.Zd, Dp, D, L.kind, L.scale, L.variance, sc, cs1, nullptr);
+      hg_contract_kernel<<<dim3((m + 127) / 128, (m + 7) / 8), 128, shb, st()>>>(hgM2, mp, m, m, L.Zd, Dp, L.Zd, Dp, D, L.kind, L.scale, L.variance, sc + 2, cs2, rs2);
+      hg_sum_kernel<<<1, 256, 0, st()>>>(hgB + (size_t)q * ldB, B, sc + 4);
+      launches += 3;
+      double h[6];
+      CK(cudaMemcpyAsync(h, sc, 6 * sizeof(double), cudaMemcpyDeviceToHost, st()));
+      if (dZ) {
+        dgemm_bm(true, true, Tm, ldh, hgX, Dp, hgP, Dp, m, D, B, 1.0);                              // G1^T X_b
+        dgemm_bm(true, true, hgM2, mp, L.Zd, Dp, hgP + (size_t)mp * Dp, Dp, m, D, m, 1.0);          // G^T Z  (G symmetric: counted twice)
+        hg_dz_kernel<<<(m * D + 255) / 256, 256, 0, st()>>>(hgM1, D, m, hgP, hgP + (size_t)mp * Dp, hgP + (size_t)mp * Dp, Dp, cs1, cs2, cs2, L.Zd, Dp, L.scale);
+        ++launches;
+        CK(cudaMemcpyAsync(hz.data(), hgM1, (size_t)m * D * sizeof(double), cudaMemcpyDeviceToHost, st()));
+      }
+      CK(cudaStreamSynchronize(st()));
+      d_scale[q] = h[0] + h[2];
+      d_variance[q] = (h[1] + h[3]) / L.variance + rho * h[4];
+      if (dZ) memcpy(dZ + (size_t)q * m * D, hz.data(), (size_t)m * D * sizeof(double));
+    }
+    CK(cudaGetLastError());
+    return AGP_OK;
+  }
+  // setZ! (gpblocks/latentgp.jl:197): new inducing points for one owned latent; follow with agp_refresh_K
+  int set_Z(int ql, const double* Zn) override {
+    if (ql < 0 || ql >= Ql || !Zn) BAD("bad inducing-point update");
+    Latent& L = lat[ql];
+    L.hZ.assign(Zn, Zn + (size_t)m * D);
+    std::vector<double> zp((size_t)m * Dp, 0.0), zn(m, 0.0);
+    std::vector<T> zt((size_t)m * Dp, T(0)), znt(m, T(0));
+    for (int i = 0; i < m; ++i) {
+      double s_ = 0, s_t = 0;
+      for (int k = 0; k < D; ++k) {
+        double v = L.hZ[(size_t)i * D + k];
+        zp[(size_t)i * Dp + k] = v; zt[(size_t)i * Dp + k] = (T)v;
+        s_ += v * v; double vt = (double)(T)v; s_t += vt * vt;
+      }
+      zn[i] = s_; znt[i] = (T)s_t;
+    }
+    CK(cudaStreamSynchronize(st()));
+    CK(cudaMemcpy(L.Zd, zp.data(), zp.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(L.zzd, zn.data(), zn.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(L.Z, zt.data(), zt.size() * sizeof(T), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(L.zz, znt.data(), znt.size() * sizeof(T), cudaMemcpyHostToDevice));
+    if (L.knm_tc) CKS(umma_knm_setup(ctx_err(), L.uk, (const float*)(const void*)L.Z, Dp, m, D, (float*)(void*)L.Knm, ldm, Bcap, st()));
+    have_K = false; prefetched = false;
+    drop_graph();
     return AGP_OK;
   }
 
@@ -1637,6 +1752,10 @@ int agp_get_Kinv(agp_model* model, int32_t ql, double* Kinv, double* logdetK) { 
 int agp_predict_f(agp_model* model, const void* Xt, int x_dtype, int x_layout, int64_t nt, int want_var, double* mu, double* var) {
   ENG(model); return e->predict_f(Xt, x_dtype, x_layout, nt, want_var, mu, var);
 }
+int agp_hyper_grads(agp_model* model, double rho, double* d_scale, double* d_variance, double* dZ) {
+  ENG(model); return e->hyper_grads(rho, d_scale, d_variance, dZ);
+}
+int agp_set_Z(agp_model* model, int32_t latent_local, const double* Z) { ENG(model); return e->set_Z(latent_local, Z); }
 int agp_set_A_optimiser(agp_model* model, int32_t kind, double eta, double beta1, double beta2, double eps) {
   ENG(model); return e->set_A_optimiser(kind, eta, beta1, beta2, eps);
 }

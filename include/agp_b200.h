@@ -164,6 +164,14 @@ int agp_step_update_async(agp_model* model, double rho);
 /* device pointers + leading dimension of the moment arrays (which: 0 = mean_f, 1 = var_f). */
 void* agp_moments_devptr(agp_model* model, int32_t which, int64_t* ld_out);
 
+/* Gradient of ELBO(model, x, y, pr_means, kernels, Zs, state) (functions/ELBO.jl:15-21) w.r.t. each owned latent's kernel scale
+ * (ScaleTransform s), kernel variance and inducing points, on the last minibatch with the posterior and local variables fixed:
+ * what update_hyperparameters! (hyperparameter/autotuning.jl:86-140) obtains from Zygote.  d_scale, d_variance: [n_latent_local];
+ * dZ: [n_latent_local][m][D] or NULL.  The host applies its optimiser (update_kernel! / update_Z!, autotuning_utils.jl:47-82),
+ * pushes the new values with agp_set_kernel / agp_set_Z and calls agp_refresh_K.  Collective on a sharded model. */
+int agp_hyper_grads(agp_model* model, double rho, double* d_scale, double* d_variance, double* dZ);
+int agp_set_Z(agp_model* model, int32_t latent_local, const double* Z /* [m][D] row-major */);
+
 /* update_A! (models/single_and_multi_output_utils.jl:87-118; MOSVGP `Aoptimiser`, MOSVGP.jl:51,79-81): kind 0 = A fixed
  * (Aoptimiser = false), 1 = ADAM(eta, (beta1, beta2)) of Optimisers.jl with epsilon.  When on, every step first moves each
  * task's mixing row along the ADAM step of its ELBO gradient (local variables of the previous iteration) and renormalises

@@ -139,6 +139,33 @@ def kernelmatrix_diag(k: Kernel, X):
     return np.full(len(X), k.variance, dtype=np.float64)
 
 
+def kernel_derivs(k: Kernel, X, Z):
+    """K = variance * base(scale^2 |x - z|^2) with  dK/dscale  and  W = dK/d(d2) (d2 = scale^2 |x-z|^2), all (n, m).
+    Used by the hand-derived ELBO gradients (what Zygote computes through KernelFunctions in hyperparameter/autotuning.jl:86-140);
+    dK/dz_j = -2 scale^2 W_ij (x_i - z_j)... see hyper_grads."""
+    X = np.asarray(X, dtype=np.float64)
+    Z = np.asarray(Z, dtype=np.float64)
+    diff2 = np.maximum(np.sum(X * X, 1)[:, None] + np.sum(Z * Z, 1)[None, :] - 2.0 * X @ Z.T, 0.0)   # |x - z|^2 (unscaled)
+    d2 = k.scale**2 * diff2
+    if k.kind == "sqexp":
+        base = np.exp(-0.5 * d2)
+        dbase = -0.5 * base                                            # d base / d d2
+    else:
+        d = np.sqrt(d2)
+        if k.kind == "matern32":
+            c = math.sqrt(3.0)
+            base = (1.0 + c * d) * np.exp(-c * d)
+            dbase = -1.5 * np.exp(-c * d)                                # d/dd2 = (d/dd) / (2 d) = -3 d e^{-c d} / (2 d)
+        else:
+            c = math.sqrt(5.0)
+            base = (1.0 + c * d + 5.0 * d2 / 3.0) * np.exp(-c * d)
+            dbase = -(5.0 / 6.0) * (1.0 + c * d) * np.exp(-c * d)
+    K = k.variance * base
+    W = k.variance * dbase                                             # dK / d d2
+    dK_dscale = W * 2.0 * k.scale * diff2
+    return K, dK_dscale, W
+
+
 # --------------------------------------------------------------------------------------
 # Likelihood descriptors (likelihood/*.jl)
 # --------------------------------------------------------------------------------------
@@ -513,6 +540,35 @@ def expec_loglikelihood(lik, y, mu, var, lv):
     raise ValueError(lik.name)
 
 
+def expec_loglik_grads(lik, y, mu, var, lv):
+    """(a, b) = d expec_loglikelihood / d (mu_f, var_f), both (K, B): derivatives of the reference's own formulas (quirks included),
+    i.e. what Zygote differentiates in ELBO(model, x, y, pr_means, kernels, Zs, state) (functions/ELBO.jl:15-21)."""
+    th = lv.get("theta")
+    if lik.name == "gaussian":
+        return ((y - mu[0]) / lik.sigma2)[None], np.full((1, len(y)), -0.5 / lik.sigma2)
+    if lik.name == "logistic":        # Q1: the dot(theta, mu) term
+        return ((y - th) / 2.0)[None], (-th / 2.0)[None]
+    if lik.name in ("studentt", "laplace"):
+        return (th * (y - mu[0]))[None], (-th / 2.0)[None]
+    if lik.name == "bayesiansvm":     # + dot(theta, (1 - y mu)^2) as written
+        return (y - 2.0 * th * y * (1.0 - y * mu[0]))[None], (-th / 2.0)[None]
+    if lik.name == "negbinomial":     # dot(theta, mu) as written
+        return ((y - lik.r) / 2.0 - th / 2.0)[None], (-th / 2.0)[None]
+    if lik.name == "poisson":
+        return ((y - lv["gamma"]) / 2.0 - th * mu[0])[None], (-th / 2.0)[None]
+    if lik.name == "logisticsoftmax":
+        Y = y.T.astype(np.float64)
+        return (Y - lv["gamma"]) / 2.0 - th * mu, -th / 2.0
+    if lik.name == "heteroscedastic":
+        g, lam = lv["gamma"], lik.lam
+        lam0 = lam * ((y - mu[0]) ** 2 + var[0]) / 2.0
+        w = 1.0 - g / lam0                                   # d PoissonKL / d lam0
+        a1 = -lam * (mu[0] - y) * w
+        b1 = -0.5 * lam * w
+        return np.stack([a1, (0.5 - g) / 2.0 - th * mu[1]]), np.stack([b1, -th / 2.0])
+    raise ValueError(lik.name)
+
+
 def AugmentedKL(lik, lv, y):
     if lik.name == "logistic":  # logistic.jl:86-92
         return PolyaGammaKL(np.ones_like(lv["c"]), lv["c"], lv["theta"])
@@ -663,7 +719,9 @@ def _symmetric_upper(A):
 class SVGP:
     """models/SVGP.jl:22-80 with `optimiser=false, Zoptimiser=false` semantics."""
 
-    def __init__(self, kernel: Kernel, likelihood, inference: AnalyticVI, Z, mean=None, jitter=JITTER_F64):
+    def __init__(self, kernel: Kernel, likelihood, inference: AnalyticVI, Z, mean=None, jitter=JITTER_F64, optimiser=None,
+                 Zoptimiser=None, atfrequency=1):
+        self.optimiser, self.Zoptimiser, self.atfrequency = optimiser, Zoptimiser, atfrequency   # SVGP.jl:33-44 (ADAM(0.01) when `true`)
         self.likelihood = likelihood
         self.inference = inference
         self.jitter = jitter
@@ -749,6 +807,104 @@ class SVGP:
         return self.ELBO(state, y)
 
 
+# --------------------------------------------------------------------------------------
+# Hyper-parameter / inducing-point optimisation (hyperparameter/autotuning.jl:86-140, autotuning_utils.jl:47-82)
+# --------------------------------------------------------------------------------------
+def elbo_given_kernels(model, state, x, y, kernels, Zs):
+    """ELBO(model, x, y, pr_means, kernels, Zs, state) (functions/ELBO.jl:15-21): kernel matrices recomputed from (kernels, Zs),
+    posterior and local variables of `state` kept."""
+    old = [(gp.kernel, gp.Z) for gp in model.f]
+    for gp, k, Z in zip(model.f, kernels, Zs):
+        gp.kernel, gp.Z = k, np.asarray(Z, dtype=np.float64)
+    st2 = dict(state)
+    st2["kernel_matrices"] = None
+    st2 = model.compute_kernel_matrices(st2, x, update=True)
+    val = model.ELBO(st2, y)
+    for gp, (k, Z) in zip(model.f, old):
+        gp.kernel, gp.Z = k, Z
+    return val
+
+
+def hyper_grads(model, state, x, y):
+    """Analytic gradient of elbo_given_kernels w.r.t. each latent's kernel scale, kernel variance and inducing points (what the
+    reference obtains from Zygote).  With K = K_mm + jitter I, kappa = K_nm K^-1, (a, b) = d E / d (mu_f, var_f) and
+    M = a mu^T + diag(b) (2 kappa Sigma - K_nm):
+        dELBO = <A_nm, dK_nm> + <A_mm, dK_mm> + rho sum_i b_i dk_ii
+        A_nm = rho (M K^-1 - diag(b) kappa)
+        A_mm = -rho sym(kappa^T M K^-1) - K^-1/2 + K^-1 (Sigma + (mu - mu0)(mu - mu0)^T) K^-1 / 2
+    Returns a list of dict(scale=, variance=, Z=(m, D))."""
+    inf = model.inference
+    x = np.asarray(x, dtype=np.float64)
+    st2 = dict(state)
+    st2["kernel_matrices"] = None
+    st2 = model.compute_kernel_matrices(st2, x, update=True)
+    kms = st2["kernel_matrices"]
+    if isinstance(model, MOSVGP):
+        mu_t, var_t, mu_q = model.task_moments(st2)
+        T, Q = model.A.shape
+        a_q, b_q = np.zeros_like(mu_q), np.zeros_like(mu_q)
+        for t, l in enumerate(model.likelihoods):
+            a, b = expec_loglik_grads(l, y[t], mu_t[t : t + 1], var_t[t : t + 1], state["local_vars"][t])
+            a_q += model.A[t][:, None] * a[0][None, :]
+            b_q += (model.A[t] ** 2)[:, None] * b[0][None, :]
+    else:
+        mu, var = model.moments(st2)
+        a_q, b_q = expec_loglik_grads(model.likelihood, y, mu, var, state["local_vars"])
+    out = []
+    for q, (gp, km) in enumerate(zip(model.f, kms)):
+        L, Knm, kappa = km["L"], km["Knm"], km["kappa"]
+        m = gp.dim
+        Kinv = sla.cho_solve((L, True), np.eye(m))
+        a, b = a_q[q], b_q[q]
+        M = np.outer(a, gp.mu) + b[:, None] * (2.0 * kappa @ gp.Sigma - Knm)
+        MK = M @ Kinv
+        A_nm = inf.rho * (MK - b[:, None] * kappa)
+        S = gp.Sigma + np.outer(gp.mu - gp.mu0, gp.mu - gp.mu0)
+        A_mm = -inf.rho * (kappa.T @ MK)
+        A_mm = 0.5 * (A_mm + A_mm.T) - 0.5 * Kinv + 0.5 * Kinv @ S @ Kinv
+        k = gp.kernel
+        Knm_, dKnm_ds, Wnm = kernel_derivs(k, x, gp.Z)
+        Kmm_, dKmm_ds, Wmm = kernel_derivs(k, gp.Z, gp.Z)
+        g_scale = np.sum(A_nm * dKnm_ds) + np.sum(A_mm * dKmm_ds)
+        g_var = (np.sum(A_nm * Knm_) + np.sum(A_mm * Kmm_)) / k.variance + inf.rho * np.sum(b)   # k_ii = variance
+        # d K_ij / d z_j = W_ij d(d2)/dz_j = W_ij scale^2 (-2)(x_i - z_j)  ;  K_mm: both arguments move (symmetric A_mm)
+        G1 = A_nm * Wnm                                               # (B, m)
+        dZ = -2.0 * k.scale**2 * (G1.T @ x - np.sum(G1, 0)[:, None] * gp.Z)
+        G2 = A_mm * Wmm
+        G2 = G2 + G2.T
+        dZ += -2.0 * k.scale**2 * (G2.T @ gp.Z - np.sum(G2, 0)[:, None] * gp.Z)
+        out.append(dict(scale=float(g_scale), variance=float(g_var), Z=dZ))
+    return out
+
+
+def update_hyperparameters(model, state, x, y):
+    """update_hyperparameters!(m, state, x, y) for sparse models (autotuning.jl:86-140): ADAM on the log of every positive
+    kernel parameter (update_kernel!, autotuning_utils.jl:63-67: step on x .* g, x = exp(log x + step)) and plain ADAM ascent on
+    the inducing points (update_Z!, :78-82); K_mm is refactorised at the next iteration."""
+    if model.optimiser is None and model.Zoptimiser is None:
+        return state
+    grads = hyper_grads(model, state, x, y)
+    hs = state.setdefault("hyperopt_state", [None] * len(model.f))
+    for q, (gp, g) in enumerate(zip(model.f, grads)):
+        if hs[q] is None:
+            hs[q] = dict(scale=model.optimiser.init(np.zeros(1)) if model.optimiser else None,
+                         variance=model.optimiser.init(np.zeros(1)) if model.optimiser else None,
+                         Z=model.Zoptimiser.init(np.zeros_like(gp.Z)) if model.Zoptimiser else None)
+        k = gp.kernel
+        new_scale, new_var = k.scale, k.variance
+        if model.optimiser is not None:
+            hs[q]["variance"], d = model.optimiser.apply(hs[q]["variance"], np.array([k.variance * g["variance"]]))
+            new_var = float(np.exp(np.log(k.variance) + d[0]))
+            hs[q]["scale"], d = model.optimiser.apply(hs[q]["scale"], np.array([k.scale * g["scale"]]))
+            new_scale = float(np.exp(np.log(k.scale) + d[0]))
+        if model.Zoptimiser is not None:
+            hs[q]["Z"], dZ = model.Zoptimiser.apply(hs[q]["Z"], g["Z"])
+            gp.Z = gp.Z + dZ
+        gp.kernel = Kernel(k.kind, scale=new_scale, variance=new_var)
+    model.inference.HyperParametersUpdated = True
+    return state
+
+
 def train(model, X, y, iterations=100, state=None, minibatches: Optional[Sequence[np.ndarray]] = None,
           callback=None, rng=None):
     """training/training.jl:13-111.  `minibatches[i]` = 0-based row indices of iteration i
@@ -781,6 +937,10 @@ def train(model, X, y, iterations=100, state=None, minibatches: Optional[Sequenc
         model.trained = True
         if callback is not None:
             callback(model, state, inf.n_iter)
+        # training/training.jl:65-69
+        if (getattr(model, "optimiser", None) is not None or getattr(model, "Zoptimiser", None) is not None) and \
+                inf.n_iter % getattr(model, "atfrequency", 1) == 0 and inf.n_iter >= 3 and it != iterations - 1:
+            state = update_hyperparameters(model, state, x, yb)
         inf.n_iter += 1
     return model, state
 
@@ -885,7 +1045,9 @@ class MOSVGP:
     """Each task has a single-latent likelihood (nf_per_task = 1).  A: (T, Q).  Aoptimiser: None (fixed A) or ADAM
     (MOSVGP.jl:51,79-81: the reference default is ADAM(0.01))."""
 
-    def __init__(self, kernels, likelihoods, inference: AnalyticVI, Zs, A, jitter=JITTER_F64, Aoptimiser=None):
+    def __init__(self, kernels, likelihoods, inference: AnalyticVI, Zs, A, jitter=JITTER_F64, Aoptimiser=None, optimiser=None,
+                 Zoptimiser=None, atfrequency=1):
+        self.optimiser, self.Zoptimiser, self.atfrequency = optimiser, Zoptimiser, atfrequency
         self.A_opt = Aoptimiser
         self.likelihoods = list(likelihoods)
         self.inference = inference

@@ -61,8 +61,10 @@ def test_constructor_and_argument_errors(agp):
     assert agp.with_lengthscale(agp.Matern32Kernel(), 4.0).scale == 0.25
     with pytest.raises(TypeError):
         agp.SVGP(k, agp.LogisticLikelihood(), "not an inference", Z)
+    mopt = agp.SVGP(k, agp.LogisticLikelihood(), agp.AnalyticVI(), Z, optimiser=True)     # SVGP.jl:33-44: `true` -> ADAM(0.01)
+    assert isinstance(mopt.optimiser, agp.ADAM) and mopt.optimiser.eta == 0.01 and mopt.Zoptimiser is None
     with pytest.raises(NotImplementedError):
-        agp.SVGP(k, agp.LogisticLikelihood(), agp.AnalyticVI(), Z, optimiser=True)
+        agp.SVGP(k, agp.LogisticLikelihood(), agp.AnalyticVI(), Z, optimiser="descent")
     with pytest.raises(ValueError):
         agp.StudentTLikelihood(0.3)
     with pytest.raises(ValueError):

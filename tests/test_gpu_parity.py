@@ -379,6 +379,41 @@ def test_mosvgp_update_A_parity(agp, precision):
     check_pair(agp, (mo, so), (me, se), 10 * tol if precision == "f32" else tol)
 
 
+@pytest.mark.parametrize("lik,kind,precision", [("logistic", "sqexp", "f64"), ("studentt", "matern32", "f64"), ("logisticsoftmax", "matern52", "f64"),
+                                                 ("poisson", "sqexp", "f64"), ("heteroscedastic", "sqexp", "f64"), ("logistic", "sqexp", "f32")])
+def test_hyper_grads_parity(agp, lik, kind, precision):
+    """agp_hyper_grads (ELBO gradient w.r.t. kernel scale / variance / inducing points, fp64 on the device) against
+    the oracle's closed form (itself checked against finite differences in tests/test_oracle.py)."""
+    oracle, engine, (X, y, F) = run_pair(agp, lik, precision, n=500, D=3, m=20, B=100, iters=5, kind=kind, scale=0.7, variance=1.3)
+    (mo, so), (me, se) = oracle, engine
+    # the oracle needs the rows of the last minibatch: run_pair's make_data is deterministic, rebuild the lists
+    _, _, _, mbs, _, _ = make_data(lik, 500, 3, 20, 100, 5, seed=0, n_class=3)
+    go = O.hyper_grads(mo, so, X[mbs[-1]], so["y_batch"])
+    ge = agp.hyper_grads(me)
+    tol = 1e-7 if precision == "f64" else 5e-3
+    for q in range(len(go)):
+        for name in ("scale", "variance"):
+            assert abs(ge[q][name] - go[q][name]) <= tol * max(1.0, abs(go[q][name])), (q, name, ge[q][name], go[q][name])
+        assert rel_fro(ge[q]["Z"], go[q]["Z"]) < (1e-7 if precision == "f64" else 5e-3), (q, rel_fro(ge[q]["Z"], go[q]["Z"]))
+
+
+def test_hyperparameter_training_parity(agp):
+    """train! with optimiser / Zoptimiser = ADAM(0.01) (training.jl:65-69: every iteration from the 4th, never the last): kernel
+    parameters, inducing points, posterior and ELBO follow the oracle."""
+    n, D, m, B, iters = 500, 3, 20, 100, 9
+    X, y, Z, mbs, F, rng = make_data("logistic", n, D, m, B, iters, seed=2)
+    mo = O.SVGP(O.Kernel("sqexp", scale=0.5, variance=1.5), O.LogisticLikelihood(), O.AnalyticSVI(B), Z, optimiser=O.ADAM(0.01), Zoptimiser=O.ADAM(0.01))
+    mo, so = O.train(mo, X, y, iters, minibatches=mbs)
+    me = agp.SVGP(1.5 * agp.SqExponentialKernel() @ agp.ScaleTransform(0.5), agp.LogisticLikelihood(), agp.AnalyticSVI(B), Z, optimiser=True,
+                  Zoptimiser=True, precision="f64")
+    me, se = agp.train(me, X, y, iters, minibatches=mbs)
+    ko = mo.f[0].kernel
+    assert abs(me.kernel.scale - ko.scale) < 1e-8 * ko.scale and abs(me.kernel.variance - ko.variance) < 1e-8 * ko.variance
+    assert abs(ko.scale - 0.5) > 1e-3                                    # it moved
+    assert rel_fro(me.Z, mo.f[0].Z) < 1e-8
+    check_pair(agp, (mo, so), (me, se), 1e-6)
+
+
 @pytest.mark.parametrize("precision", ["f64", "f32"])
 def test_ragged_sizes_layouts_and_host_batch_path(agp, precision):
     """Edge cases of the boundary: m, B, D that are multiples of nothing (padding paths), Julia's column-major X, float32 X,

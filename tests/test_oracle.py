@@ -177,6 +177,50 @@ def test_gaussian_avi_is_exact_posterior():
     assert rel_fro(m.f[0].Sigma, S) < 1e-8 and rel_fro(m.f[0].mu, S @ kap.T @ y / 1e-2) < 1e-8
 
 
+@pytest.mark.parametrize("lik,kind", [("logistic", "sqexp"), ("studentt", "matern32"), ("logisticsoftmax", "matern52"), ("poisson", "sqexp"),
+                                      ("heteroscedastic", "sqexp"), ("bayesiansvm", "sqexp")])
+def test_hyper_grads_match_finite_differences(lik, kind):
+    """the closed-form gradient of ELBO(model, x, y, pr_means, kernels, Zs, state) (functions/ELBO.jl:15-21; what
+    Zygote gives update_hyperparameters!) against central finite differences of the oracle's own ELBO."""
+    n, D, m, B, iters = 240, 3, 10, 60, 4
+    X, y, Z, mbs, F, rng = make_data(lik, n, D, m, B, iters, seed=5)
+    model = O.SVGP(O.Kernel(kind, scale=0.7, variance=1.3), oracle_lik(O, lik), O.AnalyticSVI(B), Z)
+    model, st = O.train(model, X, y, iters, minibatches=mbs)
+    x, yb = X[mbs[-1]], st["y_batch"]
+    g = O.hyper_grads(model, st, x, yb)
+    ks, Zs = [gp.kernel for gp in model.f], [gp.Z for gp in model.f]
+    h = 1e-6
+    for q in range(len(model.f)):
+        for name in ("scale", "variance"):
+            def val(d):
+                k2 = list(ks)
+                k2[q] = O.Kernel(ks[q].kind, scale=ks[q].scale + (d if name == "scale" else 0.0), variance=ks[q].variance + (d if name == "variance" else 0.0))
+                return O.elbo_given_kernels(model, st, x, yb, k2, Zs)
+            fd = (val(h) - val(-h)) / (2 * h)
+            assert abs(fd - g[q][name]) <= 1e-5 * max(1.0, abs(fd)), (q, name, fd, g[q][name])
+        for j, d in ((0, 0), (m - 1, D - 1)):
+            def valz(e):
+                Z2 = [z.copy() for z in Zs]
+                Z2[q][j, d] += e
+                return O.elbo_given_kernels(model, st, x, yb, ks, Z2)
+            fd = (valz(h) - valz(-h)) / (2 * h)
+            assert abs(fd - g[q]["Z"][j, d]) <= 1e-5 * max(1.0, abs(fd))
+
+
+def test_hyperparameter_optimisation_improves_elbo():
+    """train! with optimiser = ADAM (training.jl:65-69 schedule): kernel parameters move, stay positive, and the full-data ELBO of
+    the optimised model beats the fixed-kernel one started from a poor lengthscale."""
+    X, y, Z, mbs, F, rng = make_data("gaussian", 300, 2, 15, 300, 40, seed=8)
+    res = {}
+    for opt in (None, O.ADAM(0.05)):
+        m = O.SVGP(O.Kernel("sqexp", scale=0.2, variance=0.5), O.GaussianLikelihood(1e-2), O.AnalyticVI(), Z, optimiser=opt, Zoptimiser=opt)
+        m, st = O.train(m, X, y, 40)
+        res[opt is None] = (m.ELBO_external(X, y), m.f[0].kernel)
+    assert res[False][0] > res[True][0]
+    k = res[False][1]
+    assert k.scale > 0 and k.variance > 0 and (abs(k.scale - 0.2) > 1e-3 or abs(k.variance - 0.5) > 1e-3)
+
+
 def test_vgp_gaussian_is_exact_gp_posterior():
     """VGP + Gaussian likelihood: one CAVI step gives the exact GP posterior N(K (K + s2 I)^-1 y, K - K (K + s2 I)^-1 K)."""
     X, y, _, _, F, rng = make_data("gaussian", 60, 2, 5, 60, 1, seed=6)
