@@ -397,6 +397,26 @@ def test_hyper_grads_parity(agp, lik, kind, precision):
         assert rel_fro(ge[q]["Z"], go[q]["Z"]) < (1e-7 if precision == "f64" else 5e-3), (q, rel_fro(ge[q]["Z"], go[q]["Z"]))
 
 
+def test_hyper_grads_mosvgp_parity(agp):
+    n, D, m, B, iters, Q, T = 500, 3, 20, 100, 5, 2, 3
+    X, _, Z, mbs, F, rng = make_data("mo", n, D, m, B, iters, seed=13, n_task=3)
+    ys = [np.sign(F[:, 0] + 1e-3), F[:, 1] + 0.1 * rng.standard_normal(n), rng.poisson(3.0 / (1.0 + np.exp(-F[:, 2]))).astype(np.int64)]
+    A = rng.standard_normal((T, Q))
+    A /= np.linalg.norm(A, axis=1, keepdims=True)
+    Zs = [X[rng.permutation(n)[:m]].copy() for _ in range(Q)]
+    mo = O.MOSVGP(O.Kernel("matern32", scale=0.6, variance=1.2), [O.LogisticLikelihood(), O.GaussianLikelihood(1e-1), O.PoissonLikelihood(2.0)],
+                  O.AnalyticSVI(B), Zs, A)
+    mo, so = O.train(mo, X, ys, iters, minibatches=mbs)
+    me = agp.MOSVGP(1.2 * agp.Matern32Kernel() @ agp.ScaleTransform(0.6), [agp.LogisticLikelihood(), agp.GaussianLikelihood(1e-1), agp.PoissonLikelihood(2.0)],
+                    agp.AnalyticSVI(B), Zs, A=A, precision="f64")
+    me, se = agp.train(me, X, ys, iters, minibatches=mbs)
+    go, ge = O.hyper_grads(mo, so, X[mbs[-1]], so["y_batch"]), agp.hyper_grads(me)
+    for q in range(Q):
+        for name in ("scale", "variance"):
+            assert abs(ge[q][name] - go[q][name]) <= 1e-7 * max(1.0, abs(go[q][name])), (q, name)
+        assert rel_fro(ge[q]["Z"], go[q]["Z"]) < 1e-7
+
+
 def test_hyperparameter_training_parity(agp):
     """train! with optimiser / Zoptimiser = ADAM(0.01) (training.jl:65-69: every iteration from the 4th, never the last): kernel
     parameters, inducing points, posterior and ELBO follow the oracle."""
