@@ -201,6 +201,9 @@ struct Engine : EngineBase {
   // graph
   bool want_graph = false; cudaGraphExec_t gexec = nullptr; int gB = -1; double grho = -1; int64_t g_launches = 0;
   bool capturing = false;
+  // host-batch steps also leave the canonical posterior mean of latent 0 in a pinned host buffer (computed and copied inside
+  // the step's graph), so the per-step read-back of the end-to-end loop is a host memcpy after the step's one synchronisation
+  double* h_mu = nullptr; bool h_mu_valid = false;
   cudaGraphExec_t gexec_b = nullptr; int gB_b = -1, gkey_b = -1; double grho_b = -1; int64_t g_launches_b = 0;   // host-batch step graph
 
   // launch stream: the context's stream, or the side stream while the next minibatch is being prefetched
@@ -414,6 +417,7 @@ struct Engine : EngineBase {
     if (gexec) cudaGraphExecDestroy(gexec);
     if (gexec_b) cudaGraphExecDestroy(gexec_b);
     if (h_status) cudaFreeHost(h_status);
+    if (h_mu) cudaFreeHost(h_mu);
     for (auto& L : lat) {
       void* ps[] = {L.Z, L.zz, L.Zd, L.zzd, L.Lc, L.Linv, L.Kinv, L.mu0, L.mu0v, L.Linv_T, L.eta1c, L.eta2c, L.eta1v, L.eta2v,
                     L.muv, L.tvec, L.Xv, L.Dinv, L.Xv_T, L.Knm, L.V, L.VS, L.Ktilde, L.racc, L.Gpart, L.v1, L.P, L.X, L.W, L.logdetP};
@@ -604,6 +608,7 @@ struct Engine : EngineBase {
   }
 
   int refresh_K() override {
+    h_mu_valid = false;
     for (auto& L : lat) {
       if (L.white_valid) { canonicalize(L); L.white_valid = false; }  // K changes: carry the posterior over in canonical form
       // K_mm in fp64 (GEMM form of the squared distance is exact enough in fp64), then the exact diagonal
@@ -980,6 +985,7 @@ struct Engine : EngineBase {
   }
 
   int step_moments(const int64_t* idx, int B, int base, bool from_batch) override {
+    h_mu_valid = false;
     if (!have_K) { ctx->err = "agp_refresh_K must be called before a step"; return AGP_ERR_STATE; }
     if (!from_batch && !have_data) { ctx->err = "upload data first"; return AGP_ERR_STATE; }
     if (B < 1 || B > Bcap) BAD("The size of mini-batch is incorrect (negative or bigger than the batch capacity)");
@@ -1153,6 +1159,7 @@ struct Engine : EngineBase {
 
   // one resident-list step, software-pipelined (see `side` above)
   int step_pool(int B, double rho) {
+    h_mu_valid = false;
     if (!have_K) { ctx->err = "agp_refresh_K must be called before a step"; return AGP_ERR_STATE; }
     if (!have_data) { ctx->err = "upload data first"; return AGP_ERR_STATE; }
     if (B < 1 || B > Bcap) BAD("The size of mini-batch is incorrect (negative or bigger than the batch capacity)");
@@ -1260,7 +1267,15 @@ struct Engine : EngineBase {
     int s1 = step_moments(nullptr, B, 0, true);
     fuse_in_step_moments = false;
     CKS(s1);
-    return step_update(rho);
+    CKS(step_update(rho));
+    {   // canonical mean of latent 0 -> pinned host buffer, in stream order behind the step
+      Latent& L = lat[0];
+      ensure_muv(L);
+      symv_kernel<<<(m * 32 + 255) / 256, 256, 0, st()>>>(L.Lc, mp, m, L.muv, L.mu0 + mp);
+      ++launches;
+      CK(cudaMemcpyAsync(h_mu, L.mu0 + mp, m * sizeof(double), cudaMemcpyDeviceToHost, st()));
+    }
+    return AGP_OK;
   }
   int step_batch(const void* xbh, int x_dtype, int x_layout, const void* const* ybh, int y_kind, int B, double rho) override {
     if (!xbh || !ybh) BAD("null batch");
@@ -1270,6 +1285,8 @@ struct Engine : EngineBase {
     if (!have_K) { ctx->err = "agp_refresh_K must be called before a step"; return AGP_ERR_STATE; }
     if (prec == AGP_PREC_TF32X3 && (B % 128)) BAD("TF32X3 precision needs B % 128 == 0");
     const size_t es = x_dtype == AGP_DTYPE_F64 ? 8 : 4;
+    if (!h_mu) CK(cudaMallocHost((void**)&h_mu, (size_t)mp * sizeof(double)));
+    h_mu_valid = false;
     CKS(ensure_stage((size_t)Bcap * D * 8));     // fixed staging address: the captured graph stays valid
     CK(cudaMemcpyAsync(stage, xbh, (size_t)B * D * es, cudaMemcpyHostToDevice, st()));
     if (y_kind == AGP_Y_CLASS) CK(cudaMemcpyAsync(ycls, ybh[0], B * sizeof(int), cudaMemcpyHostToDevice, st()));
@@ -1296,10 +1313,14 @@ struct Engine : EngineBase {
       CK(cudaGraphLaunch(gexec_b, ctx->stream));
       launches += g_launches_b;
       for (auto& L : lat) L.muv_valid = false;
+      lat[0].muv_valid = true;     // the graph recomputed mu_v of latent 0
       curB = B; cur_from_batch = true; kernel_matrices_stale = false; prefetched = false; have_step = true;
+      h_mu_valid = true;
       return AGP_OK;
     }
-    return batch_compute(x_dtype, x_layout, B, rho);
+    CKS(batch_compute(x_dtype, x_layout, B, rho));
+    h_mu_valid = true;
+    return AGP_OK;
   }
 
   int* h_status = nullptr;   // pinned: one stream synchronisation reads the sticky device status
@@ -1369,6 +1390,11 @@ struct Engine : EngineBase {
   }
   int get_posterior(int ql, double* mu, double* Sigma, double* eta1, double* eta2) override {
     if (ql < 0 || ql >= Ql) BAD("latent index out of range");
+    if (ql == 0 && mu && !Sigma && !eta1 && !eta2 && h_mu_valid) {   // mean already on the host (host-batch step)
+      CK(cudaStreamSynchronize(st()));
+      memcpy(mu, h_mu, m * sizeof(double));
+      return AGP_OK;
+    }
     Latent& L = lat[ql];
     if (!L.white_valid) {  // nothing has run yet: the canonical parameters are the truth (Sigma = inv(-2 eta2) needs K only formally)
       if (!have_K) CKS(refresh_K());
@@ -1389,6 +1415,7 @@ struct Engine : EngineBase {
     return AGP_OK;
   }
   int set_posterior(int ql, const double* eta1, const double* eta2) override {
+    h_mu_valid = false;
     if (ql < 0 || ql >= Ql || !eta1 || !eta2) BAD("bad posterior arguments");
     Latent& L = lat[ql];
     CK(cudaStreamSynchronize(st()));

@@ -289,6 +289,16 @@ def run_ours(args, rank, world, local_rank):
                     traffic=traffic.get(top), traffic_source="profiles/r1/ncu_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)" if traffic else None,
                     peak_source=psrc, algorithmic_flops_per_launch=fl[top],
                     timing=f"{reps} back-to-back launches between one CUDA-event pair on the launching stream", kernels=kern)
+        # the fp64 m x m tail (largest share of the step): latency-bound by the 512-pivot chain, reported for completeness
+        if "chol_blocked" in phases and phases["chol_blocked"]["ms_per_step"] > 0:
+            t_tail = phases["chol_blocked"]["ms_per_step"] * 1e-3
+            fl_tail = 2.0 * (2.0 / 3.0) * m**3          # Cholesky (m^3/3 FMA) + inverse factor (m^3/3 FMA), 2 flops per FMA
+            roof["tail"] = dict(bound="latency (fp64 pivot chain)", kernels="tail2_potf2_first_kernel + tail2_step_kernel x m/64",
+                                seconds_per_step=t_tail, algorithmic_flops=fl_tail, achieved=fl_tail / t_tail / 1e12, unit="TFLOP/s",
+                                peak=36.0, peak_source="measured DFMA/DMMA rate on this part: 62-64 FMA/clk/SM x 148 SMs x 1.965 GHz (profiles/r1/microbench_out)",
+                                frac=fl_tail / t_tail / 1e12 / 36.0,
+                                note="m sequential pivots x ~114 cycles (measured) = %.0f us is the floor of any Cholesky-based update at this m; "
+                                     "timed by the phase timers (graph off)" % (m * 114 / 1.965e3))
         byts = 4.0 * (B * D + m * D + B * m) + 8.0 * B
         hbm = peaks.get("hbm_gbs", 6650.0)
         roof["knm"] = dict(bound="hbm", kernel="knm_umma_kernel", seconds_per_launch=tk["kmat_knm"], achieved=byts / tk["kmat_knm"] / 1e9, peak=hbm,
