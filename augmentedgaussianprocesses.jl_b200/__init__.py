@@ -23,6 +23,7 @@ from .api import (
     Matern32Kernel,
     Matern52Kernel,
     MOSVGP,
+    MOVGP,
     RobbinsMonro,
     ScaleTransform,
     SqExponentialKernel,

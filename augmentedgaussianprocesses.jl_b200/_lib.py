@@ -15,7 +15,7 @@ AGP_OK, AGP_ERR_BAD_ARG, AGP_ERR_CUDA, AGP_ERR_KTILDE_NONPOS, AGP_ERR_NOT_POSDEF
 KERNEL_SQEXP, KERNEL_MATERN32, KERNEL_MATERN52 = 0, 1, 2
 LIK_GAUSSIAN, LIK_LOGISTIC, LIK_STUDENTT, LIK_LOGISTICSOFTMAX = 0, 1, 2, 3
 LIK_LAPLACE, LIK_BAYESIANSVM, LIK_NEGBINOMIAL, LIK_POISSON, LIK_HETEROSCEDASTIC = 4, 5, 6, 7, 8
-MODEL_SVGP, MODEL_MOSVGP, MODEL_VGP = 0, 1, 2
+MODEL_SVGP, MODEL_MOSVGP, MODEL_VGP, MODEL_MOVGP = 0, 1, 2, 3
 PREC_F64, PREC_F32, PREC_TF32X3 = 0, 1, 2
 DTYPE_F64, DTYPE_F32 = 0, 1
 LAYOUT_COLMAJOR, LAYOUT_ROWMAJOR = 0, 1

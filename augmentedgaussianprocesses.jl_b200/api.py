@@ -647,6 +647,60 @@ class VGP(AbstractGPModel):
         return f"Variational Gaussian Process with a {self.likelihood} infered by {self.inference} "
 
 
+class MOVGP(AbstractGPModel):
+    """models/MOVGP.jl:22-120.  `MOVGP(X, ys, kernel, likelihoods, inference, num_latent; Aoptimiser)`: multi-output full GP, the
+    MOSVGP algebra with Z = X, κ = I, K̃ = 0 for every latent (update_parameters!(::MOVGP), training/training.jl:146-151)."""
+
+    model_kind = L.MODEL_MOVGP
+
+    def __init__(self, X, ys, kernel, likelihoods: Sequence[AbstractLikelihood], inference: AnalyticVI, num_latent: int, *, A=None,
+                 verbose: int = 0, atfrequency: int = 1, optimiser=False, Aoptimiser=False, obsdim: int = 1, T=np.float64,
+                 precision: str = "f32", device: int = 0, stream=None, rng=None):
+        self._common_init(inference, verbose, atfrequency, optimiser, False, T, precision, device, stream, None)
+        if self.optimiser is not None:
+            raise NotImplementedError("hyper-parameter optimisation of full (non-sparse) models is outside the accelerated path")
+        if inference.stoch:
+            raise ValueError("MOVGP is a full-batch model: use AnalyticVI()")
+        if isinstance(Aoptimiser, bool) or Aoptimiser is None:
+            Aoptimiser = ADAM(0.01) if Aoptimiser else None
+        if Aoptimiser is not None and not isinstance(Aoptimiser, ADAM):
+            raise NotImplementedError("only ADAM (the reference default) is implemented for the mixing-matrix optimiser")
+        self.A_opt = Aoptimiser
+        X = np.asarray(X, dtype=np.float64)
+        if X.ndim == 1:
+            X = X[:, None]
+        if X.ndim == 2 and obsdim == 2:
+            X = X.T
+        self.X = np.ascontiguousarray(X)
+        self.y = list(ys)
+        self.likelihoods = list(likelihoods)
+        for l in self.likelihoods:
+            if not isinstance(l, AbstractLikelihood) or l.n_latent != 1:
+                raise TypeError(f"One (or more) of the likelihoods {likelihoods} are not compatible or implemented with the {inference}")
+        if len(self.y) != len(self.likelihoods) or any(len(yt) != len(self.X) for yt in self.y):
+            raise ValueError("one target vector of length n per task is required")
+        self.likelihood = self.likelihoods
+        kernels = [kernel] if isinstance(kernel, Kernel) else list(kernel)
+        self.n_latent, self.n_task = int(num_latent), len(self.likelihoods)
+        self.kernels = [kernels[i % len(kernels)] for i in range(self.n_latent)]
+        self.Zs = [self.X] * self.n_latent
+        self.m, self.D = self.X.shape
+        if A is None:
+            rng = rng or np.random.default_rng()
+            A = rng.standard_normal((self.n_task, self.n_latent))
+            A /= np.linalg.norm(A, axis=1, keepdims=True)
+        self.A = np.array(A, dtype=np.float64, order="C")
+        if self.A.shape != (self.n_task, self.n_latent):
+            raise ValueError("A must be (n_task, n_latent)")
+        self.mu0 = None
+
+    def _desc(self, capacity: int) -> dict:
+        return _make_desc(self, capacity)
+
+    def __repr__(self):
+        return f"Multioutput Variational Gaussian Process with the likelihoods {self.likelihoods} infered by {self.inference} "
+
+
 def _make_desc(model, capacity: int) -> dict:
     q0, ql = model._latent_range()
     inf = model.inference
@@ -716,7 +770,7 @@ class State:
 # train!  (training/training.jl:13-111)
 # --------------------------------------------------------------------------------------------------
 def _wrap_y(model, y):
-    if isinstance(model, MOSVGP):
+    if isinstance(model, (MOSVGP, MOVGP)):
         if len(y) != model.n_task:
             raise ValueError("one target vector per task is required")
         return [treat_labels(yt, l) for yt, l in zip(y, model.likelihoods)]
@@ -748,7 +802,7 @@ def train(model: AbstractGPModel, X=None, y=None, iterations: int = 100, *, call
     inject the lists).  check_every: read the device status back every k iterations (1 = after every
     step, like the reference's immediate error).
     """
-    if isinstance(model, VGP):   # train!(model::VGP, iterations): the model carries its data (models/VGP.jl)
+    if isinstance(model, (VGP, MOVGP)):   # train!(model::VGP, iterations): the model carries its data (models/VGP.jl, MOVGP.jl)
         if isinstance(X, (int, np.integer)) and y is None:
             iterations, X = int(X), None
         if X is None:

@@ -255,6 +255,7 @@ struct Engine : EngineBase {
     ctx = c;
     model_kind = d->model_kind;
     if (model_kind == AGP_MODEL_VGP) { is_vgp = true; model_kind = AGP_MODEL_SVGP; }
+    if (model_kind == AGP_MODEL_MOVGP) { is_vgp = true; model_kind = AGP_MODEL_MOSVGP; }
     Qg = d->n_latent_global; qbeg = d->latent_begin; Ql = d->n_latent_local;
     m = d->m; D = d->D; Bcap = d->batch_capacity; prec = d->precision; stochastic = d->stochastic;
     rm_kappa = d->rm_kappa; rm_tau = d->rm_tau; jitter = d->jitter; nT = d->n_task;

@@ -59,6 +59,7 @@ extern "C" {
 #define AGP_MODEL_VGP 2    /* models/VGP.jl: full variational GP (natural_gradient!(::VarLatent), analyticVI.jl:126-140):
                               pass Z = the n training inputs (m = n), AnalyticVI (stochastic = 0), and step with the full
                               index list (B = n); the engine then runs the SVGP algebra with kappa = I, Ktilde = 0 */
+#define AGP_MODEL_MOVGP 3  /* models/MOVGP.jl: the multi-output full GP = AGP_MODEL_MOSVGP with the same Z = X convention  */
 
 /* arithmetic of the B x m contractions; the m x m tail (eta update, Cholesky, inverse) is always f64 */
 #define AGP_PREC_F64 0    /* everything in fp64 SIMT: bit-for-bit algorithm of the oracle        */

@@ -1003,7 +1003,74 @@ class VGP:
         return float(tot)
 
 
-def train_vgp(model: VGP, iterations=100):
+class MOVGP:
+    """models/MOVGP.jl: T single-latent tasks mixed from Q full latent GPs on the same inputs (update_parameters!(::MOVGP),
+    training/training.jl:146-151: update_A! then variational_updates; mixing single_and_multi_output_utils.jl:24-118)."""
+
+    def __init__(self, X, ys, kernels, likelihoods, inference: AnalyticVI, num_latent, A, jitter=JITTER_F64, Aoptimiser=None):
+        if inference.stoch:
+            raise ValueError("MOVGP takes a full-batch inference (AnalyticVI)")
+        self.X = np.asarray(X, dtype=np.float64)
+        self.likelihoods = list(likelihoods)
+        self.y = [treat_labels(yt, l) for yt, l in zip(ys, self.likelihoods)]
+        self.inference = inference
+        self.jitter = jitter
+        n = self.X.shape[0]
+        inference.batchsize, inference.rho = n, 1.0
+        kernels = [kernels] if isinstance(kernels, Kernel) else list(kernels)
+        self.f = [SparseVarLatent(self.X, kernels[i % len(kernels)]) for i in range(num_latent)]
+        self.A = np.array(A, dtype=np.float64)
+        self.A_opt = Aoptimiser
+        self.A_state = [Aoptimiser.init(self.A[t]) for t in range(len(self.likelihoods))] if Aoptimiser else None
+        self.local_vars = [init_local_vars(l, n) for l in self.likelihoods]
+        self.L = None
+        self.trained = False
+
+    def latent_moments(self):
+        return np.stack([gp.mu for gp in self.f]), np.stack([np.diag(gp.Sigma) for gp in self.f])
+
+    def step(self):
+        if self.L is None:
+            self.L = [compute_K(gp, self.jitter) for gp in self.f]
+        T, Q = self.A.shape
+        mu_q, var_q = self.latent_moments()
+        if self.A_opt is not None:  # update_A! (single_and_multi_output_utils.jl:87-118)
+            for t, l in enumerate(self.likelihoods):
+                lv = self.local_vars[t]
+                gm, gs = grad_E_mu(l, self.y[t], lv)[0], grad_E_Sigma(l, self.y[t], lv)[0]
+                gA = np.zeros(Q)
+                for q in range(Q):
+                    others = self.A[t] @ mu_q - self.A[t, q] * mu_q[q]
+                    gA[q] = np.dot(gm, mu_q[q]) - 2.0 * np.dot(gs, mu_q[q] * others) - 2.0 * self.A[t, q] * np.dot(gs, mu_q[q] ** 2 + var_q[q])
+                self.A_state[t], dA = self.A_opt.apply(self.A_state[t], gA)
+                self.A[t] = self.A[t] + dA
+                self.A[t] = self.A[t] / math.sqrt(np.sum(self.A[t] ** 2))
+        mu_t, var_t = self.A @ mu_q, (self.A**2) @ var_q
+        gm, gs = [], []
+        for t, l in enumerate(self.likelihoods):
+            lv = local_updates(self.local_vars[t], l, self.y[t], mu_t[t : t + 1], var_t[t : t + 1])
+            gm.append(grad_E_mu(l, self.y[t], lv)[0])
+            gs.append(grad_E_Sigma(l, self.y[t], lv)[0])
+        for q, (gp, L) in enumerate(zip(self.f, self.L)):
+            gmu = sum(self.A[t, q] * (gm[t] - 2.0 * gs[t] * (mu_t[t] - self.A[t, q] * mu_q[q])) for t in range(T))
+            gS = sum(self.A[t, q] ** 2 * gs[t] for t in range(T))
+            Kinv = sla.cho_solve((L, True), np.eye(gp.dim))
+            gp.eta1 = gmu + sla.cho_solve((L, True), gp.mu0)                  # analyticVI.jl:126-140
+            gp.eta2 = -_symmetric_upper(np.diag(gS) + Kinv / 2.0)
+            global_update(gp)
+
+    def ELBO(self):
+        mu_q, var_q = self.latent_moments()
+        mu_t, var_t = self.A @ mu_q, (self.A**2) @ var_q
+        tot = 0.0
+        for t, l in enumerate(self.likelihoods):
+            tot += expec_loglikelihood(l, self.y[t], mu_t[t : t + 1], var_t[t : t + 1], self.local_vars[t])
+            tot -= AugmentedKL(l, self.local_vars[t], self.y[t])
+        tot -= sum(GaussianKL(gp.mu, gp.mu0, gp.Sigma, L) for gp, L in zip(self.f, self.L))
+        return float(tot)
+
+
+def train_vgp(model, iterations=100):
     """train!(model::VGP, iterations) (training/training.jl:13-111 with the model's own data)"""
     if iterations <= 0:
         raise ValueError("Number of iterations should be positive")
@@ -1165,7 +1232,7 @@ def predict_f(model, X_test, cov=True):
             A = sla.cho_solve((L, True), np.eye(m) - SK)
             vars_.append(kernelmatrix_diag(gp.kernel, X_test) + model.jitter - diag_ABt(ks @ A, ks))
     mu = np.stack(mus)
-    if isinstance(model, MOSVGP):
+    if isinstance(model, (MOSVGP, MOVGP)):
         mu_t = model.A @ mu
         if not cov:
             return mu_t

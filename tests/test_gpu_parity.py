@@ -508,6 +508,29 @@ def test_vgp_parity(agp, lik, precision):
     assert rel_fro(np.atleast_2d(np.asarray(mu_e)), mu_o) < 10 * tol and rel_fro(np.atleast_2d(np.asarray(var_e)), var_o) < 10 * tol
 
 
+@pytest.mark.parametrize("aopt", [False, True])
+def test_movgp_parity(agp, aopt):
+    """models/MOVGP.jl: multi-output full GP (MOSVGP algebra with Z = X, kappa = I), with and without update_A!."""
+    n, D, iters, Q = 150, 3, 6, 2
+    X, _, _, _, F, rng = make_data("mo", n, D, 8, n, 1, seed=21, n_task=3)
+    ys = [np.sign(F[:, 0] + 1e-3), F[:, 1] + 0.1 * rng.standard_normal(n), F[:, 2] + 0.1 * rng.standard_t(3.0, n)]
+    A = rng.standard_normal((3, Q))
+    A /= np.linalg.norm(A, axis=1, keepdims=True)
+    sc = 1.0 / np.sqrt(D)
+    mo = O.MOVGP(X, ys, O.Kernel("sqexp", scale=sc), [O.LogisticLikelihood(), O.GaussianLikelihood(1e-2), O.StudentTLikelihood(3.0)], O.AnalyticVI(), Q, A,
+                 Aoptimiser=O.ADAM(0.01) if aopt else None)
+    mo = O.train_vgp(mo, iters)
+    me = agp.MOVGP(X, ys, agp.SqExponentialKernel() @ agp.ScaleTransform(sc), [agp.LogisticLikelihood(), agp.GaussianLikelihood(1e-2), agp.StudentTLikelihood(3.0)],
+                   agp.AnalyticVI(), Q, A=A, Aoptimiser=aopt, precision="f64")
+    me, se = agp.train(me, iters)
+    for q, gp in enumerate(mo.f):
+        mu, S, _, _ = me.posterior(q)
+        assert rel_fro(mu, gp.mu) < 1e-8 and rel_fro(S, gp.Sigma) < 1e-8, (q, rel_fro(mu, gp.mu), rel_fro(S, gp.Sigma))
+    assert abs(agp.ELBO(me, se) - mo.ELBO()) <= 1e-7 * max(1.0, abs(mo.ELBO()))
+    if aopt:
+        assert rel_fro(me.A, mo.A) < 1e-8
+
+
 def test_latent_sharded_two_gpus_match_single_gpu():
     """latent-sharded run (one rank per GPU, moments exchanged over NVLink peer memory inside the step, and the
     NCCL all-gather fallback) against the same model on one GPU.  Needs two visible GPUs (skipped otherwise)."""
