@@ -83,10 +83,16 @@ class GaussianLikelihood(AbstractLikelihood):
     kind = L.LIK_GAUSSIAN
 
     def __init__(self, sigma2: float = 1e-3, opt_noise=False):
-        if opt_noise:
-            raise NotImplementedError("opt_noise (noise optimisation) is outside the accelerated path")
+        if isinstance(opt_noise, bool) or opt_noise is None:   # gaussian.jl:18-24
+            opt_noise = ADAM(0.05) if opt_noise else None
+        if opt_noise is not None and not isinstance(opt_noise, ADAM):
+            raise NotImplementedError("only ADAM is implemented for the noise optimiser")
+        self.opt_noise = opt_noise
         self.sigma2 = float(sigma2)
-        self.p0 = self.sigma2
+
+    @property
+    def p0(self):
+        return self.sigma2
 
     def __repr__(self):
         return f"Gaussian likelihood (σ² = {self.sigma2})"
@@ -460,6 +466,10 @@ class AbstractGPModel:
             cap = (cap + 127) // 128 * 128
         self._eng = _Engine(self._desc(cap), self.device, self.stream)
         self._data_key = None
+        for t, l in enumerate(self.likelihoods):
+            on = getattr(l, "opt_noise", None)
+            if on is not None:
+                self._eng.ck(self._eng.lib.agp_set_noise_optimiser(self._eng.model, t, 1, on.eta, on.beta[0], on.beta[1], on.epsilon))
         ao = getattr(self, "A_opt", None)
         if ao is not None:
             self._eng.ck(self._eng.lib.agp_set_A_optimiser(self._eng.model, 1, ao.eta, ao.beta[0], ao.beta[1], ao.epsilon))
@@ -924,6 +934,10 @@ def _refresh_lik_params(model, eng):
             v = C.c_double(0.0)
             eng.ck(eng.lib.agp_get_lik_param(eng.model, t, C.byref(v)))
             l.lam = v.value
+        if l.kind == L.LIK_GAUSSIAN and getattr(l, "opt_noise", None) is not None:
+            v = C.c_double(0.0)
+            eng.ck(eng.lib.agp_get_lik_param(eng.model, t, C.byref(v)))
+            l.sigma2 = v.value
 
 
 train_ = train  # `train!`

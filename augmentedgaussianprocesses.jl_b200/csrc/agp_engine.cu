@@ -86,6 +86,7 @@ struct EngineBase {
   virtual int get_lik_param(int task, double* v) = 0;
   virtual int set_lik_param(int task, double v) = 0;
   virtual int proba_link(int link, double p0, const double* mu, const double* var, int64_t n, double* p, double* pv) = 0;
+  virtual int set_noise_optimiser(int task, int kind, double eta, double b1, double b2, double eps) = 0;
   virtual int hyper_grads(double rho, double* d_scale, double* d_variance, double* dZ) = 0;
   virtual int set_Z(int ql, const double* Z) = 0;
   virtual int set_A_optimiser(int kind, double eta, double b1, double b2, double eps) = 0;
@@ -180,6 +181,9 @@ struct Engine : EngineBase {
   // latent-sharded peer exchange (agp_peer_export / agp_peer_attach): one exported block [mean 2Q ldB | var 2Q ldB | flags]
   double* xchg = nullptr; int64_t par_stride = 0; bool peer = false; int peer_world = 1, peer_rank = 0;
   int64_t* d_xepoch = nullptr; double** d_peers = nullptr; std::vector<void*> peer_opened;
+  // GaussianLikelihood(opt_noise): ADAM on log sigma^2 inside local_updates! (gaussian.jl:56-72)
+  bool noise_any = false; std::vector<int> h_noise_opt; int* d_noise_opt = nullptr; double* d_noise_state = nullptr;
+  double n_eta = 0.05, n_b1 = 0.9, n_b2 = 0.999, n_eps = 1e-8;
   // update_A! (MOSVGP Aoptimiser): ADAM state on the device
   bool a_opt = false; double a_eta = 0.01, a_b1 = 0.9, a_b2 = 0.999, a_eps = 1e-8;
   double *d_gradA = nullptr, *d_Amt = nullptr, *d_Avt = nullptr, *d_Abt = nullptr;
@@ -431,7 +435,7 @@ struct Engine : EngineBase {
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
     void* ps[] = {idx_prev, xx_cur, pKS, pXb, pxxb, X, xx, y_all, ycls_all, Xb, xxb, stage, idx_pool, idx_cur, counters, status, d_lik_kind, d_p0, d_p1, d_A,
-                  xchg, d_xepoch, d_peers, gmu, gS, lc, ltheta, lgamma_, lalpha, tmu, tvar, gm, gs, yb, ycls, d_out, d_lam, d_lamacc, d_qnodes, d_qw, d_lr, d_gradA, d_Amt, d_Avt, d_Abt,
+                  xchg, d_xepoch, d_peers, gmu, gS, lc, ltheta, lgamma_, lalpha, tmu, tvar, gm, gs, yb, ycls, d_out, d_lam, d_lamacc, d_qnodes, d_qw, d_lr, d_gradA, d_Amt, d_Avt, d_Abt, d_noise_opt, d_noise_state,
                   hgH[0], hgH[1], hgH[2], hgH[3], hgX, hgA, hgB, hgM1, hgM2, hgV, hgP};
     for (void* p : ps) cudaFree(p);
   }
@@ -655,6 +659,7 @@ struct Engine : EngineBase {
     CKS(upload_lr(1));
     curB = 0; have_step = false;
     CKS(reset_A_state());     // init_state_A (training/states.jl:100-105)
+    CKS(reset_noise_state()); // init_local_vars(::GaussianLikelihood) re-creates state_sigma2 (gaussian.jl:47-54)
     return reset_local_vars();
   }
 
@@ -901,6 +906,29 @@ struct Engine : EngineBase {
     return AGP_OK;
   }
 
+  // ---- GaussianLikelihood(opt_noise = ADAM(..)) switch ------------------------------------------------------------------
+  int reset_noise_state() {
+    if (!noise_any) return AGP_OK;
+    std::vector<double> st(4 * (size_t)nT, 0.0);
+    for (int t = 0; t < nT; ++t) { st[4 * t + 2] = n_b1; st[4 * t + 3] = n_b2; }
+    CK(cudaMemcpy(d_noise_state, st.data(), st.size() * 8, cudaMemcpyHostToDevice));
+    return AGP_OK;
+  }
+  int set_noise_optimiser(int task, int kind, double eta, double b1, double b2, double eps) override {
+    if (task < 0 || task >= nT || h_lik_kind[task] != AGP_LIK_GAUSSIAN) BAD("opt_noise applies to a GaussianLikelihood task");
+    if (kind != 0 && kind != 1) BAD("unknown noise optimiser (0 = none, 1 = ADAM)");
+    if (kind == 1 && !(eta > 0 && b1 > 0 && b1 < 1 && b2 > 0 && b2 < 1 && eps > 0)) BAD("bad ADAM parameters");
+    CK(cudaStreamSynchronize(st()));
+    drop_graph();
+    if (!d_noise_opt) { CKS(dalloc(&d_noise_opt, nT)); CKS(dalloc(&d_noise_state, 4 * (size_t)nT)); h_noise_opt.assign(nT, 0); CK(cudaStreamSynchronize(st())); }
+    h_noise_opt[task] = kind;
+    if (kind == 1) { n_eta = eta; n_b1 = b1; n_b2 = b2; n_eps = eps; }
+    noise_any = false;
+    for (int v : h_noise_opt) noise_any = noise_any || v != 0;
+    CK(cudaMemcpy(d_noise_opt, h_noise_opt.data(), nT * sizeof(int), cudaMemcpyHostToDevice));
+    return reset_noise_state();
+  }
+
   // ---- update_A! switch (MOSVGP.jl:51,79-81 `Aoptimiser`); kind 0 = off, 1 = ADAM ------------------------------------------
   int reset_A_state() {
     if (!a_opt) return AGP_OK;
@@ -970,7 +998,7 @@ struct Engine : EngineBase {
   }
 
   bool can_fuse_lik() const {
-    return !is_vgp && prec == AGP_PREC_TF32X3 && model_kind == AGP_MODEL_SVGP && Qg == 1 && Ql == 1 && !need_lam && !peer && !a_opt && !prof &&
+    return !noise_any && !is_vgp && prec == AGP_PREC_TF32X3 && model_kind == AGP_MODEL_SVGP && Qg == 1 && Ql == 1 && !need_lam && !peer && !a_opt && !prof &&
            !getenv("AGP_NO_FUSE_LIK");
   }
   LikParams lik_params(int B, bool from_batch, int update) {
@@ -981,7 +1009,8 @@ struct Engine : EngineBase {
     p.yb = yb; p.ycls = ycls; p.c = lc; p.theta = ltheta; p.gamma = lgamma_; p.alpha = lalpha;
     p.tmu = tmu; p.tvar = tvar; p.gm = gm; p.gs = gs; p.gmu = gmu; p.gS = gS; p.update = update;
     p.xepoch = peer ? d_xepoch : nullptr; p.par_stride = par_stride;
-    p.lam = d_lam; p.lamacc = d_lamacc; p.qnodes = d_qnodes; p.qweights = d_qw; p.nq = nq; p.need_reduce = need_lam ? 1 : 0;
+    p.noise_opt = noise_any ? d_noise_opt : nullptr; p.noise_state = d_noise_state; p.n_eta = n_eta; p.n_b1 = n_b1; p.n_b2 = n_b2; p.n_eps = n_eps;
+    p.lam = d_lam; p.lamacc = d_lamacc; p.qnodes = d_qnodes; p.qweights = d_qw; p.nq = nq; p.need_reduce = (need_lam || noise_any) ? 1 : 0;
     return p;
   }
 
@@ -1019,11 +1048,16 @@ struct Engine : EngineBase {
     if (need_quad && nq < 1) { ph_end(); ctx->err = "agp_set_quadrature must be called before a Poisson step"; return AGP_ERR_STATE; }
     if (!lik_fused) { launch_chain(lik_update_kernel, dim3((B + 127) / 128), dim3(128), 0, lik_params(B, cur_from_batch, 1)); ++launches; }
     lik_fused = false;
-    if (need_lam) {  // lambda re-estimation closes local_updates! (poisson.jl:80, heteroscedastic.jl:98)
+    if (need_lam || noise_any) {  // lambda / noise re-estimation closes local_updates! (poisson.jl:80, heteroscedastic.jl:98, gaussian.jl:62-70)
       LikParams lp = lik_params(B, true, 1);
       launch_chain(lik_lambda_kernel, dim3(1), dim3(std::max(32, (int)rup(nT, 32))), 0, lp);
       ++launches;
       if (is_het) { launch_chain(hetero_grad_kernel, dim3((B + 127) / 128), dim3(128), 0, lp); ++launches; }
+      if (noise_any) {   // theta = 1 / sigma^2 and the Gaussian gradients with the NEW noise (gaussian.jl:70-80)
+        LikParams lp2 = lik_params(B, true, 2);
+        launch_chain(lik_update_kernel, dim3((B + 127) / 128), dim3(128), 0, lp2);
+        ++launches;
+      }
     }
     ph_end();
     for (int q = 0; q < Ql; ++q) {
@@ -1530,7 +1564,7 @@ struct Engine : EngineBase {
   int get_lik_param(int task, double* v) override {
     if (task < 0 || task >= nT || !v) BAD("bad likelihood-parameter query");
     CK(cudaStreamSynchronize(st()));
-    CK(cudaMemcpy(v, d_lam + task, 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(v, (h_lik_kind[task] == AGP_LIK_GAUSSIAN ? d_p0 : d_lam) + task, 8, cudaMemcpyDeviceToHost));   // Gaussian: the live sigma^2
     return AGP_OK;
   }
   int set_lik_param(int task, double v) override {
@@ -1779,6 +1813,9 @@ int agp_get_kernel_matrices(agp_model* model, int32_t ql, double* Knm, double* k
 int agp_get_Kinv(agp_model* model, int32_t ql, double* Kinv, double* logdetK) { ENG(model); return e->get_Kinv(ql, Kinv, logdetK); }
 int agp_predict_f(agp_model* model, const void* Xt, int x_dtype, int x_layout, int64_t nt, int want_var, double* mu, double* var) {
   ENG(model); return e->predict_f(Xt, x_dtype, x_layout, nt, want_var, mu, var);
+}
+int agp_set_noise_optimiser(agp_model* model, int32_t task, int32_t kind, double eta, double beta1, double beta2, double eps) {
+  ENG(model); return e->set_noise_optimiser(task, kind, eta, beta1, beta2, eps);
 }
 int agp_hyper_grads(agp_model* model, double rho, double* d_scale, double* d_variance, double* dZ) {
   ENG(model); return e->hyper_grads(rho, d_scale, d_variance, dZ);

@@ -220,6 +220,9 @@ struct LikParams {
   double* lam; double* lamacc;
   const double* qnodes; const double* qweights; int nq;      // Gauss-Hermite rule of `expectation` (functions/utils.jl:16-19)
   int need_reduce;                                           // some task accumulates into lamacc
+  // GaussianLikelihood(opt_noise) (gaussian.jl:56-72): per-task ADAM state [T][4] = (mt, vt, beta1^t, beta2^t), flags [T], and
+  // (eta, beta1, beta2, eps); the re-estimated sigma^2 is written back into p0[t] (every kernel reads p0 live)
+  const int* noise_opt; double* noise_state; double n_eta, n_b1, n_b2, n_eps;
   // latent-sharded peer exchange: the moment arrays are double-buffered by exchange parity (see peer_sync_kernel)
   const int64_t* xepoch; int64_t par_stride;
 };
@@ -349,7 +352,8 @@ __device__ __forceinline__ void lik_update_sample(const LikParams& p, int b, dou
     lik_single(kind, p.p0[0], p.p1[0], p.lam[0], y, mu, var, c, th, gam, gm, gs);
     p.c[b] = c; p.theta[b] = th;
     p.gmu[b] = gm; p.gS[b] = gs;
-    if (kind == 7) {  // poisson.jl:80 : lambda = sum(y) / sum(E[logistic(f)])
+    if (kind == 0 && p.noise_opt && p.noise_opt[0] && p.update == 1) r0 = (y - mu) * (y - mu) + var;   // gaussian.jl:63
+    if (kind == 7 && p.update == 1) {  // poisson.jl:80 : lambda = sum(y) / sum(E[logistic(f)])
       p.gamma[b] = gam;
       r0 = y;
       r1 = expect_logistic(p.qnodes, p.qweights, p.nq, mu, var);
@@ -368,13 +372,15 @@ __device__ __forceinline__ void lik_update_sample(const LikParams& p, int b, dou
       vt += a * a * p.var_f[q * ld + b];
     }
     p.tmu[t * ld + b] = mt; p.tvar[t * ld + b] = vt;
-    if (p.update) {
+    const int kind_t = p.lik_kind[t];
+    if (p.update == 1 || (p.update == 2 && kind_t == 0)) {   // update == 2: second pass after the noise re-estimation, Gaussian tasks only
       double c, th, gam, gm, gs;
-      const int kind = p.lik_kind[t];
+      const int kind = kind_t;
       lik_single(kind, p.p0[t], p.p1[t], p.lam[t], y, mt, vt, c, th, gam, gm, gs);
       p.c[t * ld + b] = c; p.theta[t * ld + b] = th;
       p.gm[t * ld + b] = gm; p.gs[t * ld + b] = gs;
-      if (kind == 7) {
+      if (kind == 0 && p.noise_opt && p.noise_opt[t] && p.update == 1) atomicAdd(p.lamacc + 2 * t, (y - mt) * (y - mt) + vt);
+      if (kind == 7 && p.update == 1) {
         p.gamma[t * ld + b] = gam;
         atomicAdd(p.lamacc + 2 * t, y);
         atomicAdd(p.lamacc + 2 * t + 1, expect_logistic(p.qnodes, p.qweights, p.nq, mt, vt));
@@ -403,7 +409,7 @@ __global__ void lik_update_kernel(const LikParams p_in) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   double r0 = 0.0, r1 = 0.0;
   if (b < p.B) lik_update_sample(p, b, r0, r1);
-  if (!p.need_reduce || !p.update || p.model_kind != 0) return;   // uniform
+  if (!p.need_reduce || p.update != 1 || p.model_kind != 0) return;   // uniform
   __shared__ double s0[8], s1[8];
   r0 = warp_sum(r0); r1 = warp_sum(r1);
   int w = threadIdx.x >> 5, l = threadIdx.x & 31;
@@ -519,6 +525,17 @@ __global__ void lik_lambda_kernel(const LikParams p) {
   int kind = p.lik_kind[t];
   if (kind == 7) p.lam[t] = p.lamacc[2 * t] / p.lamacc[2 * t + 1];
   else if (kind == 8) p.lam[t] = fmax((double)p.B / (2.0 * p.lamacc[2 * t]), p.lam[t]);
+  else if (kind == 0 && p.noise_opt && p.noise_opt[t]) {
+    // gaussian.jl:62-68: grad = ((sum (y - mu)^2 + sum var_f) / sigma^2 - B) / 2, ADAM step, sigma^2 <- exp(log sigma^2 + step)
+    double* st = p.noise_state + 4 * t;
+    double* s2 = const_cast<double*>(p.p0) + t;
+    const double g = 0.5 * (p.lamacc[2 * t] / *s2 - (double)p.B);
+    st[0] = p.n_b1 * st[0] + (1.0 - p.n_b1) * g;
+    st[1] = p.n_b2 * st[1] + (1.0 - p.n_b2) * g * g;
+    const double step = st[0] / (1.0 - st[2]) / (sqrt(st[1] / (1.0 - st[3])) + p.n_eps) * p.n_eta;
+    st[2] *= p.n_b1; st[3] *= p.n_b2;
+    *s2 = exp(log(*s2) + step);
+  }
   p.lamacc[2 * t] = 0.0; p.lamacc[2 * t + 1] = 0.0;
 }
 

@@ -165,6 +165,11 @@ int agp_step_update_async(agp_model* model, double rho);
 /* device pointers + leading dimension of the moment arrays (which: 0 = mean_f, 1 = var_f). */
 void* agp_moments_devptr(agp_model* model, int32_t which, int64_t* ld_out);
 
+/* GaussianLikelihood(sigma2; opt_noise) (likelihood/gaussian.jl:18-24, 56-72): kind 1 = ADAM(eta, (beta1, beta2)) on log sigma^2
+ * inside every local update (the reference default for opt_noise = true is ADAM(0.05)); 0 = fixed noise.  The live sigma^2 is
+ * read with agp_get_lik_param(task). */
+int agp_set_noise_optimiser(agp_model* model, int32_t task, int32_t kind, double eta, double beta1, double beta2, double eps);
+
 /* Gradient of ELBO(model, x, y, pr_means, kernels, Zs, state) (functions/ELBO.jl:15-21) w.r.t. each owned latent's kernel scale
  * (ScaleTransform s), kernel variance and inducing points, on the last minibatch with the posterior and local variables fixed:
  * what update_hyperparameters! (hyperparameter/autotuning.jl:86-140) obtains from Zygote.  d_scale, d_variance: [n_latent_local];

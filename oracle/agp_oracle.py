@@ -176,6 +176,7 @@ class GaussianLikelihood:
     sigma2: float = 1e-3
     n_latent: int = 1
     name: str = "gaussian"
+    opt_noise: object = None  # ADAM(0.05) when `opt_noise = true` (gaussian.jl:18-24)
 
 
 @dataclass
@@ -345,7 +346,10 @@ def init_local_vars(lik, B):
     if lik.name in ("logistic", "studentt"):
         return dict(c=np.zeros(B), theta=np.zeros(B))
     if lik.name == "gaussian":
-        return dict(theta=np.full(B, 1.0 / lik.sigma2))
+        lv = dict(theta=np.full(B, 1.0 / lik.sigma2))
+        if lik.opt_noise is not None:  # gaussian.jl:49-52
+            lv["state_sigma2"] = lik.opt_noise.init(np.zeros(1))
+        return lv
     if lik.name in ("bayesiansvm", "negbinomial"):  # classification.jl:10-12, negativebinomial.jl:65-67
         return dict(c=np.zeros(B), theta=np.zeros(B))
     if lik.name == "laplace":  # laplace.jl:57-59
@@ -375,7 +379,13 @@ def local_updates(lv, lik, y, mu, var):
     elif lik.name == "studentt":  # studentt.jl:68-82
         lv["c"] = (np.abs(mu[0] - y) ** 2 + var[0] + lik.sigma**2 * lik.nu) / 2.0
         lv["theta"] = lik.alpha / lv["c"]
-    elif lik.name == "gaussian":  # gaussian.jl:56-72 (opt_noise = nothing)
+    elif lik.name == "gaussian":  # gaussian.jl:56-72
+        if lik.opt_noise is not None:
+            # (the reference's call is Optimisers.apply!(opt, state, x, [grad]) with the results unpacked as (step, state); the
+            #  argument / result order differs between the Optimisers versions it allows -- restated as: ADAM step on grad)
+            grad = ((np.sum((y - mu[0]) ** 2) + np.sum(var[0])) / lik.sigma2 - len(y)) / 2.0
+            lv["state_sigma2"], step = lik.opt_noise.apply(lv["state_sigma2"], np.array([grad]))
+            lik.sigma2 = float(np.exp(np.log(lik.sigma2) + step[0]))
         lv["theta"] = np.full(mu.shape[1], 1.0 / lik.sigma2)
     elif lik.name == "laplace":  # laplace.jl:61-74
         lv["b"] = np.sqrt(np.abs(mu[0] - y) ** 2 + var[0])

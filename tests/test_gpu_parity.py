@@ -508,6 +508,38 @@ def test_vgp_parity(agp, lik, precision):
     assert rel_fro(np.atleast_2d(np.asarray(mu_e)), mu_o) < 10 * tol and rel_fro(np.atleast_2d(np.asarray(var_e)), var_o) < 10 * tol
 
 
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_gaussian_opt_noise_parity(agp, precision):
+    """GaussianLikelihood(opt_noise = true) (gaussian.jl:18-24, 56-72): ADAM(0.05) on log sigma^2 inside every local update, for an
+    SVGP and as one task of a MOSVGP (together with a Poisson task whose lambda is re-estimated in the same pass)."""
+    n, D, m, B, iters = 500, 3, 20, 100, 8
+    X, y, Z, mbs, F, rng = make_data("gaussian", n, D, m, B, iters, seed=17)
+    sc = 1.0 / np.sqrt(D)
+    lo = O.GaussianLikelihood(0.5, opt_noise=O.ADAM(0.05))
+    mo = O.SVGP(O.Kernel("sqexp", scale=sc), lo, O.AnalyticSVI(B), Z)
+    mo, so = O.train(mo, X, y, iters, minibatches=mbs)
+    le = agp.GaussianLikelihood(0.5, opt_noise=True)
+    me = agp.SVGP(agp.SqExponentialKernel() @ agp.ScaleTransform(sc), le, agp.AnalyticSVI(B), Z, precision=precision)
+    me, se = agp.train(me, X, y, iters, minibatches=mbs)
+    tol = TOL[precision]
+    assert abs(le.sigma2 - lo.sigma2) <= tol * lo.sigma2 and abs(lo.sigma2 - 0.5) > 1e-2, (le.sigma2, lo.sigma2)
+    check_pair(agp, (mo, so), (me, se), tol)
+    # multi-output: Gaussian(opt_noise) + Poisson + Logistic tasks
+    ys = [F[:, 0] + 0.3 * rng.standard_normal(n), rng.poisson(3.0 / (1.0 + np.exp(-F[:, 1]))).astype(np.int64), np.sign(F[:, 2] + 1e-3)]
+    A = rng.standard_normal((3, 2))
+    A /= np.linalg.norm(A, axis=1, keepdims=True)
+    Zs = [X[rng.permutation(n)[:m]].copy() for _ in range(2)]
+    lo2 = O.GaussianLikelihood(0.5, opt_noise=O.ADAM(0.05))
+    mo2 = O.MOSVGP(O.Kernel("sqexp", scale=sc), [lo2, O.PoissonLikelihood(2.0), O.LogisticLikelihood()], O.AnalyticSVI(B), Zs, A)
+    mo2, so2 = O.train(mo2, X, ys, iters, minibatches=mbs)
+    le2 = agp.GaussianLikelihood(0.5, opt_noise=True)
+    me2 = agp.MOSVGP(agp.SqExponentialKernel() @ agp.ScaleTransform(sc), [le2, agp.PoissonLikelihood(2.0), agp.LogisticLikelihood()], agp.AnalyticSVI(B), Zs,
+                     A=A, precision=precision)
+    me2, se2 = agp.train(me2, X, ys, iters, minibatches=mbs)
+    assert abs(le2.sigma2 - lo2.sigma2) <= tol * lo2.sigma2
+    check_pair(agp, (mo2, so2), (me2, se2), tol)
+
+
 @pytest.mark.parametrize("aopt", [False, True])
 def test_movgp_parity(agp, aopt):
     """models/MOVGP.jl: multi-output full GP (MOSVGP algebra with Z = X, kappa = I), with and without update_A!."""

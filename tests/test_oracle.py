@@ -221,6 +221,18 @@ def test_hyperparameter_optimisation_improves_elbo():
     assert k.scale > 0 and k.variance > 0 and (abs(k.scale - 0.2) > 1e-3 or abs(k.variance - 0.5) > 1e-3)
 
 
+def test_gaussian_opt_noise_moves_towards_the_data_noise():
+    """gaussian.jl:56-72: ADAM on log sigma^2 with grad = ((|y - mu|^2 + sum var_f) / sigma^2 - B) / 2."""
+    X, y, Z, mbs, F, rng = make_data("gaussian", 400, 2, 15, 400, 60, seed=3)     # data noise 0.1^2 = 1e-2
+    lik = O.GaussianLikelihood(1.0, opt_noise=O.ADAM(0.05))
+    m = O.SVGP(oracle_kernel(O, "sqexp", 1.0, 1.0), lik, O.AnalyticVI(), Z)
+    tr = []
+    m, st = O.train(m, X, y, 200, callback=lambda mm, s_, i: tr.append(lik.sigma2))
+    # first the fit is poor (residuals >> sigma^2: the noise grows), then it shrinks towards the data noise
+    assert tr[10] > 1.0 and 0 < lik.sigma2 < 0.25 and all(b < a for a, b in zip(tr[100:], tr[101:]))
+    assert np.allclose(st["local_vars"]["theta"], 1.0 / lik.sigma2)
+
+
 def test_vgp_gaussian_is_exact_gp_posterior():
     """VGP + Gaussian likelihood: one CAVI step gives the exact GP posterior N(K (K + s2 I)^-1 y, K - K (K + s2 I)^-1 K)."""
     X, y, _, _, F, rng = make_data("gaussian", 60, 2, 5, 60, 1, seed=6)
