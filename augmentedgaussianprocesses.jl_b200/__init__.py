@@ -8,6 +8,7 @@ from . import _lib
 from ._lib import AGPError, KtildeError, PosDefException
 from .api import (
     ADAM,
+    Descent,
     AnalyticSVI,
     AnalyticVI,
     ELBO,

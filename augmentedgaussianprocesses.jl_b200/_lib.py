@@ -85,6 +85,7 @@ SIGNATURES = {
     "agp_get_Kinv": (C.c_int, [C.c_void_p, C.c_int32, c_double_p, c_double_p]),
     "agp_predict_f": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, c_double_p, c_double_p]),
     "agp_proba_logistic": (C.c_int, [C.c_void_p, c_double_p, c_double_p, C.c_int64, c_double_p, c_double_p, C.c_int32, c_double_p, c_double_p]),
+    "agp_set_step_size": (C.c_int, [C.c_void_p, C.c_double]),
     "agp_set_noise_optimiser": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double]),
     "agp_hyper_grads": (C.c_int, [C.c_void_p, C.c_double, c_double_p, c_double_p, c_double_p]),
     "agp_set_Z": (C.c_int, [C.c_void_p, C.c_int32, c_double_p]),

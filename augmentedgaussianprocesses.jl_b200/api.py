@@ -282,6 +282,16 @@ class RobbinsMonro:
         self.kappa, self.tau = float(kappa), float(tau)
 
 
+class Descent:
+    """Optimisers.jl Descent(eta): constant step for the stochastic natural-gradient update (`AnalyticSVI(B; optimiser=Descent(0.1))`)."""
+
+    def __init__(self, eta: float = 0.1):
+        if not 0.0 < eta <= 1.0:
+            raise ValueError("eta should be in (0, 1]")
+        self.eta = float(eta)
+        self.kappa, self.tau = 0.51, 1.0   # unused by the device when a constant step is set
+
+
 class ADAM:
     """Optimisers.jl ADAM(eta = 0.001, beta = (0.9, 0.999)) as accepted by `MOSVGP(...; Aoptimiser)` (MOSVGP.jl:51)."""
 
@@ -320,8 +330,8 @@ class AnalyticVI:
 def AnalyticSVI(nMinibatch: int, eps: float = 1e-5, optimiser: Optional[RobbinsMonro] = None):
     """inference/analyticVI.jl:48-52"""
     optimiser = optimiser if optimiser is not None else RobbinsMonro()
-    if not isinstance(optimiser, RobbinsMonro):
-        raise NotImplementedError("only the RobbinsMonro variational optimiser is accelerated")
+    if not isinstance(optimiser, (RobbinsMonro, Descent)):
+        raise NotImplementedError("only the RobbinsMonro and Descent variational optimisers are accelerated")
     return AnalyticVI(eps, _optimiser=optimiser, _batchsize=int(nMinibatch), _stoch=True)
 
 
@@ -466,6 +476,8 @@ class AbstractGPModel:
             cap = (cap + 127) // 128 * 128
         self._eng = _Engine(self._desc(cap), self.device, self.stream)
         self._data_key = None
+        if self.inference.stoch and isinstance(self.inference.optimiser, Descent):
+            self._eng.ck(self._eng.lib.agp_set_step_size(self._eng.model, self.inference.optimiser.eta))
         for t, l in enumerate(self.likelihoods):
             on = getattr(l, "opt_noise", None)
             if on is not None:

@@ -86,6 +86,7 @@ struct EngineBase {
   virtual int get_lik_param(int task, double* v) = 0;
   virtual int set_lik_param(int task, double v) = 0;
   virtual int proba_link(int link, double p0, const double* mu, const double* var, int64_t n, double* p, double* pv) = 0;
+  virtual int set_step_size(double eta) = 0;
   virtual int set_noise_optimiser(int task, int kind, double eta, double b1, double b2, double eps) = 0;
   virtual int hyper_grads(double rho, double* d_scale, double* d_variance, double* dZ) = 0;
   virtual int set_Z(int ql, const double* Z) = 0;
@@ -645,8 +646,18 @@ struct Engine : EngineBase {
   }
 
   // d_lr holds the step size of the UPCOMING iteration: lr = (tau + t)^-kappa (optimisers.jl:14-19), 1 for AnalyticVI
+  double fixed_lr = 0.0;   // > 0: Descent(eta) instead of Robbins-Monro for the stochastic natural-gradient step (agp_set_step_size)
+  int set_step_size(double eta) override {
+    if (!(eta >= 0.0) || eta > 1.0) BAD("step size must be in [0, 1] (0 = back to Robbins-Monro)");
+    fixed_lr = eta;
+    drop_graph();
+    int64_t c[2];
+    CK(cudaStreamSynchronize(st()));
+    CK(cudaMemcpy(c, counters, 16, cudaMemcpyDeviceToHost));
+    return upload_lr(c[0]);
+  }
   int upload_lr(int64_t t) {
-    double lr = stochastic ? std::pow(rm_tau + (double)t, -rm_kappa) : 1.0;
+    double lr = stochastic ? (fixed_lr > 0.0 ? fixed_lr : std::pow(rm_tau + (double)t, -rm_kappa)) : 1.0;
     CK(cudaMemcpy(d_lr, &lr, 8, cudaMemcpyHostToDevice));
     return AGP_OK;
   }
@@ -1171,7 +1182,7 @@ struct Engine : EngineBase {
     ph_begin(PH_FINAL);
     float* hi = nullptr; float* lo = nullptr;
     launch_chain(x_finalize_kernel<T>, dim3(m), dim3(128), 0, (const double*)L.Xv, (int64_t)mp, m, (const double*)L.eta1v, L.Xv_T, (int64_t)ldm, hi, lo,
-                 L.tvec, (in_step && stochastic) ? d_lr : (double*)nullptr, counters, rm_kappa, rm_tau, in_step ? 1 : 0);
+                 L.tvec, (in_step && stochastic && !(fixed_lr > 0.0)) ? d_lr : (double*)nullptr, counters, rm_kappa, rm_tau, in_step ? 1 : 0);
     ++launches;
     ph_end();
     L.muv_valid = false;
@@ -1814,6 +1825,7 @@ int agp_get_Kinv(agp_model* model, int32_t ql, double* Kinv, double* logdetK) { 
 int agp_predict_f(agp_model* model, const void* Xt, int x_dtype, int x_layout, int64_t nt, int want_var, double* mu, double* var) {
   ENG(model); return e->predict_f(Xt, x_dtype, x_layout, nt, want_var, mu, var);
 }
+int agp_set_step_size(agp_model* model, double eta) { ENG(model); return e->set_step_size(eta); }
 int agp_set_noise_optimiser(agp_model* model, int32_t task, int32_t kind, double eta, double beta1, double beta2, double eps) {
   ENG(model); return e->set_noise_optimiser(task, kind, eta, beta1, beta2, eps);
 }

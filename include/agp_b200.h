@@ -165,6 +165,10 @@ int agp_step_update_async(agp_model* model, double rho);
 /* device pointers + leading dimension of the moment arrays (which: 0 = mean_f, 1 = var_f). */
 void* agp_moments_devptr(agp_model* model, int32_t which, int64_t* ld_out);
 
+/* AnalyticSVI(B; optimiser = Descent(eta)) (inference/analyticVI.jl:28-52, global_update! :229-246): a constant step eta in (0, 1]
+ * for the stochastic natural-gradient update instead of the default RobbinsMonro schedule; eta = 0 restores Robbins-Monro. */
+int agp_set_step_size(agp_model* model, double eta);
+
 /* GaussianLikelihood(sigma2; opt_noise) (likelihood/gaussian.jl:18-24, 56-72): kind 1 = ADAM(eta, (beta1, beta2)) on log sigma^2
  * inside every local update (the reference default for opt_noise = true is ADAM(0.05)); 0 = fixed noise.  The live sigma^2 is
  * read with agp_get_lik_param(task). */

@@ -652,6 +652,19 @@ class RobbinsMonro:
 
 
 @dataclass
+class Descent:
+    """Optimisers.jl Descent(eta) as the `optimiser` of AnalyticSVI (analyticVI.jl:28-52): Delta = eta * gradient."""
+
+    eta: float = 0.1
+
+    def init(self):
+        return 1
+
+    def apply(self, st, delta):
+        return st + 1, delta * self.eta
+
+
+@dataclass
 class AnalyticVI:
     """inference/analyticVI.jl:1-52"""
 

@@ -540,6 +540,19 @@ def test_gaussian_opt_noise_parity(agp, precision):
     check_pair(agp, (mo2, so2), (me2, se2), tol)
 
 
+def test_descent_optimiser_parity(agp):
+    """AnalyticSVI(B; optimiser = Descent(0.3)): constant natural-gradient step (analyticVI.jl:229-246 with Optimisers.Descent)."""
+    n, D, m, B, iters = 500, 3, 20, 100, 6
+    X, y, Z, mbs, F, rng = make_data("logistic", n, D, m, B, iters, seed=4)
+    sc = 1.0 / np.sqrt(D)
+    mo = O.SVGP(O.Kernel("sqexp", scale=sc), O.LogisticLikelihood(), O.AnalyticSVI(B, optimiser=O.Descent(0.3)), Z)
+    mo, so = O.train(mo, X, y, iters, minibatches=mbs)
+    me = agp.SVGP(agp.SqExponentialKernel() @ agp.ScaleTransform(sc), agp.LogisticLikelihood(), agp.AnalyticSVI(B, optimiser=agp.Descent(0.3)), Z,
+                  precision="f64")
+    me, se = agp.train(me, X, y, iters, minibatches=mbs)
+    check_pair(agp, (mo, so), (me, se), TOL["f64"])
+
+
 @pytest.mark.parametrize("aopt", [False, True])
 def test_movgp_parity(agp, aopt):
     """models/MOVGP.jl: multi-output full GP (MOSVGP algebra with Z = X, kappa = I), with and without update_A!."""
