@@ -577,7 +577,7 @@ class SVGP(AbstractGPModel):
 
 class MOSVGP(AbstractGPModel):
     """models/MOSVGP.jl:22-115 with single-latent task likelihoods; A is T x Q (rows normalised like
-    MOSVGP.jl:100-103).  `Aoptimiser` must be False (update_A! is not accelerated yet)."""
+    MOSVGP.jl:100-103).  `Aoptimiser=True` (ADAM(0.01), the reference default) runs update_A! on the device; default here: fixed A."""
 
     model_kind = L.MODEL_MOSVGP
 
