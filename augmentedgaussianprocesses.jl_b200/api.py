@@ -1073,8 +1073,6 @@ def _pred_nodes():
 
 def _predict_f(model, X_test, cov: bool):
     """(Q_local, N*) latent moments of the owned latents, then multi-output mixing on the host."""
-    if model.world > 1:
-        raise NotImplementedError("prediction on a latent-sharded model: gather the posterior on one rank first")
     eng = model._engine(max(model.inference.batchsize, 1) if model._eng is None else 1)
     Xk, xp, dt, layout, nt, D = _x_args(X_test)
     if D != model.D:
@@ -1083,7 +1081,14 @@ def _predict_f(model, X_test, cov: bool):
     mu = np.empty((ql, nt))
     var = np.empty((ql, nt)) if cov else None
     eng.ck(eng.lib.agp_predict_f(eng.model, xp, dt, layout, nt, 1 if cov else 0, L.dptr(mu), L.dptr(var) if cov else None))
-    if isinstance(model, MOSVGP):  # predictions.jl:63-84
+    if model.world > 1:   # latent-sharded model: every rank predicts its own latents, the rows are gathered on the host (collective call)
+        import torch.distributed as dist
+
+        parts = [None] * model.world
+        dist.all_gather_object(parts, (mu, var))
+        mu = np.concatenate([p[0] for p in parts], axis=0)
+        var = np.concatenate([p[1] for p in parts], axis=0) if cov else None
+    if isinstance(model, (MOSVGP, MOVGP)):  # predictions.jl:63-84
         mu_t = model.A @ mu
         return (mu_t, (model.A**2) @ var) if cov else (mu_t, None)
     return mu, var

@@ -40,6 +40,7 @@ def main():
         ms = mk(shard=(rank, world))
         ms, ss = agp.train(ms, X, y, iters, minibatches=mbs)
         e_s = agp.ELBO(ms, ss)
+        yp_s = agp.predict_y(ms, X[:500])                      # collective: rows of the owned latents gathered on the host
         q0, ql = ms._latent_range()
         mine = [ms.posterior(q) for q in range(ql)]
         if rank == 0:
@@ -47,7 +48,9 @@ def main():
             m1, s1 = agp.train(m1, X, y, iters, minibatches=mbs)
             e_1 = agp.ELBO(m1, s1)
             errs = [max(rel_fro(mine[q][0], m1.posterior(q0 + q)[0]), rel_fro(mine[q][1], m1.posterior(q0 + q)[1])) for q in range(ql)]
-            good = max(errs) < 1e-9 and abs(e_s - e_1) <= 1e-9 * abs(e_1)
+            yp_1 = agp.predict_y(m1, X[:500])
+            same_pred = all(np.array_equal(a, b) for a, b in zip(yp_s, yp_1)) if isinstance(yp_1, list) else np.array_equal(yp_s, yp_1)
+            good = max(errs) < 1e-9 and abs(e_s - e_1) <= 1e-9 * abs(e_1) and same_pred
             ok = ok and good
             print(f"[{case}] world={world} peer={getattr(ms, '_peer', False)}: max rel err (mu, Sigma) {max(errs):.2e}, ELBO {e_s:.6f} vs {e_1:.6f} -> {'OK' if good else 'MISMATCH'}", flush=True)
         dist.barrier()
