@@ -149,4 +149,33 @@ function AGP.ELBO(model::SVGP{T,L,<:AnalyticVI}, state::NamedTuple, y) where {T,
     return out[1] - out[2] - out[3]
 end
 
+# update_hyperparameters! (hyperparameter/autotuning.jl:86-140): the Zygote call is replaced by agp_hyper_grads (closed-form gradient
+# of ELBO(m, x, y, μ₀, ks, Zs, state) on the device); update_kernel! / update_Z! (autotuning_utils.jl:47-82) stay in Julia and their
+# results are pushed back with agp_set_kernel / agp_set_Z; K_mm is refactorised by the next update_parameters! (HPupdated flag).
+function AGP.update_hyperparameters!(m::SVGP{T,L,<:AnalyticVI}, state, x, y) where {T,L}
+    any(!isnothing ∘ AGP.opt, m.f) || any(!isnothing ∘ AGP.Zopt, m.f) || return state
+    e = ENGINES[m]; Q = length(m.f); M = AGP.dim(m.f[1]); D = length(first(m.f[1].Z))
+    ds = zeros(Q); dv = zeros(Q); dZ = zeros(D, M, Q)               # [Q][m][D] row-major == (D, M, Q) column-major
+    check(e, ccall((:agp_hyper_grads, LIB), Cint, (Ptr{Cvoid}, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                   e.model, Float64(AGP.ρ(AGP.inference(m))), ds, dv, dZ))
+    hp = state.hyperopt_state
+    hp = map(enumerate(m.f), hp) do (q, gp), st
+        if !isnothing(AGP.opt(gp))   # NamedTuple gradient in the shape Zygote would return for σ² * (k ∘ ScaleTransform(s))
+            Δ = (kernel=(kernel=nothing, transform=(s=[ds[q]],)), σ²=[dv[q]])
+            st = merge(st, (; state_k=AGP.update_kernel!(AGP.opt(gp), AGP.kernel(gp), Δ, st.state_k)))
+            kind, s, var = kernel_params(AGP.kernel(gp))
+            check(e, ccall((:agp_set_kernel, LIB), Cint, (Ptr{Cvoid}, Int32, Int32, Float64, Float64), e.model, q - 1, kind, s, var))
+        end
+        if !isnothing(AGP.Zopt(gp))
+            ΔZ = [dZ[:, i, q] for i in 1:M]
+            st = merge(st, (; state_Z=AGP.update_Z!(AGP.Zopt(gp), AGP.Zview(gp), ΔZ, st.state_Z)))
+            Zn = reduce(hcat, AGP.Zview(gp))                          # (D, M) column-major == [m][D] row-major
+            check(e, ccall((:agp_set_Z, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}), e.model, q - 1, Zn))
+        end
+        st
+    end
+    AGP.setHPupdated!(AGP.inference(m), true)                         # -> agp_refresh_K at the next update_parameters!
+    return merge(state, (; hyperopt_state=hp))
+end
+
 end # module
