@@ -630,6 +630,7 @@ struct Engine : EngineBase {
       copy_lower_kernel<<<grid_mp(), 128, 0, st()>>>(L.X, L.Linv, mp, mp);
       symmetrize_shadow_kernel<T><<<dim3((m + 127) / 128, m), 128, 0, st()>>>(L.Kinv, mp, m, (T*)nullptr, ldm);
       shadow_kernel<T><<<dim3((m + 127) / 128, m), 128, 0, st()>>>(L.Linv, mp, m, L.Linv_T, ldm);
+      if (L.um.v2) { CKS(umma_presplit(ctx_err(), L.um, UM_LINV, (const float*)(const void*)L.Linv_T, st())); ++launches; }
       symv_kernel<<<(m * 32 + 255) / 256, 256, 0, st()>>>(L.Linv, mp, m, L.mu0, L.mu0v);  // L^-1 mu0
       launches += 5;
       CK(cudaMemcpyAsync(&L.logdetK, L.logdetP + 1, sizeof(double), cudaMemcpyDeviceToHost, st()));
@@ -1180,7 +1181,8 @@ struct Engine : EngineBase {
   int eta_to_moments(Latent& L, bool in_step = false) {
     chol_inv(L);
     ph_begin(PH_FINAL);
-    float* hi = nullptr; float* lo = nullptr;
+    float* hi = umma_split_ptr(L.um, UM_X, 0);   // non-null only with the opt-in v2 GEMM: X leaves this kernel pre-split
+    float* lo = umma_split_ptr(L.um, UM_X, 1);
     launch_chain(x_finalize_kernel<T>, dim3(m), dim3(128), 0, (const double*)L.Xv, (int64_t)mp, m, (const double*)L.eta1v, L.Xv_T, (int64_t)ldm, hi, lo,
                  L.tvec, (in_step && stochastic && !(fixed_lr > 0.0)) ? d_lr : (double*)nullptr, counters, rm_kappa, rm_tau, in_step ? 1 : 0);
     ++launches;

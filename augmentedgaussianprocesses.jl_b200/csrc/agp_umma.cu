@@ -290,6 +290,269 @@ umma_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
+// =====================================================================================================
+// Second-generation kernel (opt-in: AGP_UMMA_V2=1; NOT yet measured or parity-checked on a B200 -- written
+// after the round's GPU budget was spent, from the line-level stall profile profiles/r1/umma_stalls_by_line.txt).
+// What the profile showed for the kernel above: the two worker groups alternate by UNIT, so one group converts
+// while the other drains an accumulator and then idles -- a single 4-warp group cannot hide the shared-memory /
+// tcgen05.st latency of a k-block (~2000 cycles per k-block against 768 cycles of tcgen05.mma), and half of the
+// conversion work is the m x m operand that every CTA splits again.  Changes:
+//   * roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 a dedicated epilogue group, warps 6..13 two
+//     converter groups that alternate by K-BLOCK (two conversions in flight at any time)
+//   * the B operand may arrive pre-split (L^-1 once per refresh_K, X by x_finalize_kernel): its hi / lo tiles go
+//     from TMA straight to the tensor core and the converters only split the A rows into TMEM.  Without a
+//     pre-split copy (Gram product) the raw B tile is converted in place (hi) with lo beside it.
+//   * rings: raw A 4 x 16 KB (freed by the converters), B 4 x 32 KB and 4 TMEM A slots (both freed by
+//     tcgen05.commit), so A prefetch is not gated by the MMA
+//   * every mbarrier wait is bounded (about a second) and traps, so a protocol error is a launch failure, not a hang
+// The barrier protocol is model-checked on the CPU by tools/umma_v2_protocol_sim.py.
+namespace v2 {
+constexpr int RA = 4, RB = 4, TS = 4;             // raw-A stages, B stages, TMEM A slots (RB == TS: one release barrier)
+constexpr int A_BYTES = TILE_BYTES, B_BYTES = 2 * TILE_BYTES;
+constexpr int RING_BYTES = RA * A_BYTES + RB * B_BYTES;   // 192 KB
+constexpr int NCG = 2;                            // converter groups; must divide RA and TS
+constexpr int EPI_WARP0 = 2, CONV_WARP0 = 6;
+constexpr int NUM_THREADS = 64 + 128 + NCG * 128; // 448
+constexpr int SMEM_BYTES = RING_BYTES + 1024 + 256;
+static_assert(RB == TS && RA % NCG == 0 && TS % NCG == 0, "ring / group shape");
+static_assert(TMEM_A0 + TS * 64 <= TMEM_COLS, "TMEM budget");
+
+__device__ __forceinline__ void wait_bounded(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t n = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++n & 1023u) == 0 && clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+}  // namespace v2
+
+__global__ void __launch_bounds__(v2::NUM_THREADS, 1)
+umma_gemm_nt_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
+                       const __grid_constant__ CUtensorMap tmB1, float* __restrict__ C, int64_t ldc, int64_t c_split_stride,
+                       const GemmWork work, const UmmaEpilogue ep, const int b_presplit) {
+  using namespace v2;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bars = smem_base + v2::RING_BYTES;
+  auto a_full = [&](int s) { return bars + 8u * s; };
+  auto a_empty = [&](int s) { return bars + 8u * (RA + s); };
+  auto b_full = [&](int s) { return bars + 8u * (2 * RA + s); };
+  auto conv_done = [&](int s) { return bars + 8u * (2 * RA + RB + s); };
+  auto mma_done = [&](int s) { return bars + 8u * (2 * RA + RB + TS + s); };
+  auto tmem_full = [&](int b) { return bars + 8u * (2 * RA + RB + 2 * TS + b); };
+  auto tmem_empty = [&](int b) { return bars + 8u * (2 * RA + RB + 2 * TS + 2 + b); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + v2::RING_BYTES + 8 * (2 * RA + RB + 2 * TS + 4));
+  const uint32_t b_base = smem_base + RA * A_BYTES;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = gridDim.x, cta = blockIdx.x;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB0);
+    if (b_presplit) tma_prefetch_desc(&tmB1);
+    for (int s = 0; s < RA; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), NUM_CONV_THREADS); }
+    for (int s = 0; s < RB; ++s) mbar_init(b_full(s), 1);
+    for (int s = 0; s < TS; ++s) { mbar_init(conv_done(s), NUM_CONV_THREADS); mbar_init(mma_done(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tmem_full(b), 1); mbar_init(tmem_empty(b), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_ptr_smem)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer: raw A tiles (ring freed by the converters) and B tiles (ring freed by the MMA) =====
+      int g = 0;
+      for (int r = 0;; ++r) {
+        const int u = unit_index(r, cta, G);
+        if (u >= work.total) break;
+        const WorkUnit wu = get_unit(work, u);
+        for (int i = 0; i < wu.nkb; ++i, ++g) {
+          const int k = (wu.kb0 + i) * BK;
+          const int sa = g % RA, sb = g % RB;
+          wait_bounded(a_empty(sa), ((g / RA) & 1) ^ 1);
+          mbar_expect_tx(a_full(sa), A_BYTES);
+          tma_load_2d(smem_base + sa * A_BYTES, &tmA, a_full(sa), k, wu.tile_m * BM);
+          wait_bounded(mma_done(sb), ((g / RB) & 1) ^ 1);         // the MMAs of k-block g - RB have read this stage
+          const uint32_t dst = b_base + sb * B_BYTES;
+          mbar_expect_tx(b_full(sb), b_presplit ? 2 * TILE_BYTES : TILE_BYTES);
+          tma_load_2d(dst, &tmB0, b_full(sb), k, wu.tile_n * BN);                                   // hi (or raw)
+          if (b_presplit) tma_load_2d(dst + TILE_BYTES, &tmB1, b_full(sb), k, wu.tile_n * BN);      // lo
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    int g = 0, lt = 0;
+    for (int r = 0;; ++r, ++lt) {
+      const int u = unit_index(r, cta, G);
+      if (u >= work.total) break;
+      const WorkUnit wu = get_unit(work, u);
+      const int ab = lt & 1;
+      wait_bounded(tmem_empty(ab), ((lt >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + ab * BN;
+      for (int i = 0; i < wu.nkb; ++i, ++g) {
+        const int s = g % TS;
+        wait_bounded(conv_done(s), (g / TS) & 1);                 // A hi / lo in TMEM (and B converted when not pre-split)
+        if (b_presplit) wait_bounded(b_full(s), (g / RB) & 1);    // B hi / lo landed by TMA
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t b_hi = b_base + s * B_BYTES, b_lo = b_hi + TILE_BYTES;
+          const uint32_t a_hi = tmem_base + TMEM_A0 + s * 64, a_lo = a_hi + 32;
+#pragma unroll
+          for (int kk = 0; kk < BK / 8; ++kk) {
+            const uint32_t off = kk * 32;
+            const uint64_t dbh = make_desc(b_hi + off), dbl = make_desc(b_lo + off);
+            tc_mma_tf32_ts(acc, a_lo + kk * 8, dbh, kIdesc, (i > 0 || kk > 0) ? 1u : 0u);
+            tc_mma_tf32_ts(acc, a_hi + kk * 8, dbl, kIdesc, 1u);
+            tc_mma_tf32_ts(acc, a_hi + kk * 8, dbh, kIdesc, 1u);
+          }
+          tc_commit(mma_done(s));                                 // frees the B stage and the TMEM A slot
+          if (i == wu.nkb - 1) tc_commit(tmem_full(ab));
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < CONV_WARP0) {
+    // ===== epilogue group: drains accumulator lt & 1 while the main loop of unit lt + 1 runs =====
+    const int q = warp & 3;
+    int lt = 0;
+    for (int r = 0;; ++r, ++lt) {
+      const int u = unit_index(r, cta, G);
+      if (u >= work.total) break;
+      const WorkUnit wu = get_unit(work, u);
+      if (wu.nkb <= 0) continue;
+      const int ab = lt & 1;
+      const int row = wu.tile_m * BM + q * 32 + lane;
+      float* cbase = C + (int64_t)wu.split * c_split_stride;
+      float* crow = cbase + (int64_t)row * ldc + (int64_t)wu.tile_n * BN;
+      double acc_sq = 0.0, acc_dot = 0.0;
+      wait_bounded(tmem_full(ab), (lt >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t rr[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + c * 32);
+        TMEM_LD32(taddr, rr);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (c == BN / 32 - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty(ab));
+        }
+        if (ep.mode != UMMA_EPI_STATS_ONLY) {
+          float4* dst = reinterpret_cast<float4*>(crow + c * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            dst[j] = make_float4(__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1]), __uint_as_float(rr[4 * j + 2]), __uint_as_float(rr[4 * j + 3]));
+        }
+        if (ep.mode == UMMA_EPI_STORE_SUMSQ || ep.mode == UMMA_EPI_STATS_ONLY) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const double v = (double)__uint_as_float(rr[j]);
+            acc_sq = fma(v, v, acc_sq);
+            if (ep.mode == UMMA_EPI_STATS_ONLY) acc_dot = fma(v, ep.tvec[wu.tile_n * BN + c * 32 + j], acc_dot);
+          }
+        }
+        if (ep.mode == UMMA_EPI_STORE_MIRROR && wu.tile_n != wu.tile_m) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            cbase[(int64_t)(wu.tile_n * BN + c * 32 + j) * ldc + row] = __uint_as_float(rr[j]);
+        }
+      }
+      if (ep.mode == UMMA_EPI_STORE_SUMSQ) atomicAdd(ep.acc0 + row, acc_sq);
+      if (ep.mode == UMMA_EPI_STATS_ONLY) { atomicAdd(ep.acc0 + row, acc_sq); atomicAdd(ep.acc1 + row, acc_dot); }
+    }
+  } else {
+    // ===== converter groups: group c splits the k-blocks g = c (mod NCG) =====
+    const int grp = (warp - CONV_WARP0) >> 2;
+    const int ct = (threadIdx.x - CONV_WARP0 * 32) & 127;
+    const int q = warp & 3;
+    const int arow = q * 32 + lane;
+    int g = 0;
+    for (int r = 0;; ++r) {
+      const int u = unit_index(r, cta, G);
+      if (u >= work.total) break;
+      const WorkUnit wu = get_unit(work, u);
+      for (int i = 0; i < wu.nkb; ++i, ++g) {
+        if (g % NCG != grp) continue;
+        const int sa = g % RA, s = g % TS;
+        wait_bounded(mma_done(s), ((g / TS) & 1) ^ 1);            // TMEM A slot (and B stage) of k-block g - TS released
+        wait_bounded(a_full(sa), (g / RA) & 1);
+        tc_fence_after();
+        {
+          const float4* rowp = reinterpret_cast<const float4*>(smem_gen + sa * A_BYTES + arow * 128);
+          uint32_t h[32], l[32];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 v = rowp[c ^ (arow & 7)];
+            float t;
+            t = tf32_rna(v.x); h[4 * c + 0] = __float_as_uint(t); l[4 * c + 0] = __float_as_uint(tf32_rna(v.x - t));
+            t = tf32_rna(v.y); h[4 * c + 1] = __float_as_uint(t); l[4 * c + 1] = __float_as_uint(tf32_rna(v.y - t));
+            t = tf32_rna(v.z); h[4 * c + 2] = __float_as_uint(t); l[4 * c + 2] = __float_as_uint(tf32_rna(v.z - t));
+            t = tf32_rna(v.w); h[4 * c + 3] = __float_as_uint(t); l[4 * c + 3] = __float_as_uint(tf32_rna(v.w - t));
+          }
+          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + TMEM_A0 + s * 64;
+          TMEM_ST32(ta, h);
+          TMEM_ST32(ta + 32, l);
+        }
+        if (!b_presplit) {
+          wait_bounded(b_full(s), (g / RB) & 1);
+          float4* hi = reinterpret_cast<float4*>(smem_gen + RA * A_BYTES + s * B_BYTES);   // raw tile, split in place
+          float4* lo = reinterpret_cast<float4*>(smem_gen + RA * A_BYTES + s * B_BYTES + TILE_BYTES);
+#pragma unroll
+          for (int uu = 0; uu < TILE_BYTES / 16 / NUM_CONV_THREADS; ++uu) {
+            const int e = ct + uu * NUM_CONV_THREADS;
+            const float4 v = hi[e];
+            float4 hh, ll;
+            hh.x = tf32_rna(v.x); ll.x = tf32_rna(v.x - hh.x);
+            hh.y = tf32_rna(v.y); ll.y = tf32_rna(v.y - hh.y);
+            hh.z = tf32_rna(v.z); ll.z = tf32_rna(v.z - hh.z);
+            hh.w = tf32_rna(v.w); ll.w = tf32_rna(v.w - hh.w);
+            hi[e] = hh; lo[e] = ll;
+          }
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        if (!b_presplit) fence_proxy_async();
+        mbar_arrive(a_empty(sa));
+        mbar_arrive(conv_done(s));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// hi = rna_tf32(src), lo = rna_tf32(src - hi) for an m x m operand that every CTA of the v2 GEMM would otherwise split again
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo,
+                                                         int64_t n4) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    float4 h, l;
+    h.x = tf32_rna(v.x); l.x = tf32_rna(v.x - h.x);
+    h.y = tf32_rna(v.y); l.y = tf32_rna(v.y - h.y);
+    h.z = tf32_rna(v.z); l.z = tf32_rna(v.z - h.z);
+    h.w = tf32_rna(v.w); l.w = tf32_rna(v.w - h.w);
+    reinterpret_cast<float4*>(hi)[i] = h;
+    reinterpret_cast<float4*>(lo)[i] = l;
+  }
+}
+
 // U^T = (diag(sqrt(rho w)) V)^T:  V is [B][ldv], output is [m][ldt] fp32 (split to hi/lo inside the GEMM); fused with
 // v1[j] += sum_b V[b][j] g[b]  (transpose(kappa) * grad_mu, analyticVI.jl:168, whitened).  Block = 32 columns x 128 rows.
 __global__ void __launch_bounds__(256) scale_transpose_kernel(const float* __restrict__ V, int64_t ldv, const double* __restrict__ w, double rho,
@@ -365,6 +628,7 @@ bool make_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols,
 
 struct Maps {
   CUtensorMap raw[UM_COUNT], ut;
+  CUtensorMap split[2][2];   // v2: [0] = L^-1, [1] = X ; [.][0] = hi, [.][1] = lo
 };
 
 int fail(std::string* err, const char* what, cudaError_t e = cudaSuccess) {
@@ -392,12 +656,44 @@ int umma_latent_alloc(std::string* err, UmmaLatent& u, int m, int ldm, int Bcap,
   if (!ok) return fail(err, "cuTensorMapEncodeTiled failed");
   if ((e = cudaFuncSetAttribute(umma_gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)) != cudaSuccess)
     return fail(err, "cudaFuncSetAttribute", e);
+  if (const char* env = getenv("AGP_UMMA_V2")) u.v2 = atoi(env);
+  if (u.v2) {
+    // pre-split copies of the two m x m right operands: [L^-1 hi | L^-1 lo | X hi | X lo], each [m][ldm]
+    const size_t each = (size_t)m * ldm;
+    if (each % 4) return fail(err, "v2: m * ldm must be a multiple of 4");
+    if ((e = cudaMalloc(&u.Bsplit, 4 * each * sizeof(float))) != cudaSuccess) return fail(err, "cudaMalloc", e);
+    cudaMemsetAsync(u.Bsplit, 0, 4 * each * sizeof(float), st);
+    for (int w = 0; w < 2; ++w)
+      for (int h = 0; h < 2; ++h) ok = ok && make_map(&mp->split[w][h], u.Bsplit + (size_t)(2 * w + h) * each, m, m, ldm);
+    if (!ok) return fail(err, "cuTensorMapEncodeTiled failed (v2)");
+    if ((e = cudaFuncSetAttribute(umma_gemm_nt_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SMEM_BYTES)) != cudaSuccess)
+      return fail(err, "cudaFuncSetAttribute (v2)", e);
+  }
+  return 0;
+}
+
+float* umma_split_ptr(const UmmaLatent& u, int which, int lo) {
+  if (!u.Bsplit || (which != UM_LINV && which != UM_X)) return nullptr;
+  return u.Bsplit + (size_t)(2 * (which == UM_X ? 1 : 0) + (lo ? 1 : 0)) * (size_t)u.m * u.ldm;
+}
+
+int umma_presplit(std::string* err, UmmaLatent& u, int which, const float* src, cudaStream_t st) {
+  if (!u.v2) return 0;
+  float* hi = umma_split_ptr(u, which, 0);
+  float* lo = umma_split_ptr(u, which, 1);
+  if (!hi) return fail(err, "v2: no pre-split buffer for this operand");
+  const int64_t n4 = (int64_t)u.m * u.ldm / 4;
+  split_tf32_kernel<<<(unsigned)((n4 + 255) / 256 < 592 ? (n4 + 255) / 256 : 592), 256, 0, st>>>(src, hi, lo, n4);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(err, "split_tf32_kernel", e);
   return 0;
 }
 
 void umma_latent_free(UmmaLatent& u) {
   cudaFree(u.UT);
   u.UT = nullptr;
+  cudaFree(u.Bsplit);
+  u.Bsplit = nullptr;
   delete (Maps*)u.tmaps;
   u.tmaps = nullptr;
 }
@@ -435,6 +731,17 @@ int umma_gemm_nt(std::string* err, UmmaLatent& u, int a_which, int b_which, floa
   w.total_kb = u.m / BK; w.kb_per_split = w.total_kb;
   w.tri_mode = (b_which == UM_LINV || b_which == UM_X) ? 1 : 0;
   const int grid = w.total < sm_count() ? w.total : sm_count();
+  if (u.v2) {
+    // v2 & 2: keep the in-kernel split of the right operand (A/B experiment); otherwise L^-1 / X arrive pre-split
+    const int sp = (b_which == UM_LINV) ? 0 : (b_which == UM_X) ? 1 : -1;
+    const int presplit = (sp >= 0 && !(u.v2 & 2)) ? 1 : 0;
+    launch_chain(umma_gemm_nt_v2_kernel, dim3(grid), dim3(v2::NUM_THREADS), v2::SMEM_BYTES, st, mp->raw[a_which],
+                 presplit ? mp->split[sp][0] : mp->raw[b_which], presplit ? mp->split[sp][1] : mp->raw[b_which], C, (int64_t)u.ldm,
+                 (int64_t)0, w, ep, presplit);
+    cudaError_t e2 = cudaGetLastError();
+    if (e2 != cudaSuccess) return fail(err, "umma_gemm_nt_v2_kernel", e2);
+    return 0;
+  }
   launch_chain(umma_gemm_nt_kernel, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, mp->raw[a_which], mp->raw[b_which], C, (int64_t)u.ldm, (int64_t)0, w, ep);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(err, "umma_gemm_nt_kernel", e);
@@ -467,7 +774,11 @@ int umma_gram(std::string* err, UmmaLatent& u, float* Gpart, int B, int m, int* 
   const int grid = w.total < sm_count() ? w.total : sm_count();
   UmmaEpilogue ep{};
   ep.mode = UMMA_EPI_STORE_MIRROR;
-  launch_chain(umma_gemm_nt_kernel, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, mp->ut, mp->ut, Gpart, (int64_t)u.ldm, (int64_t)m * u.ldm, w, ep);
+  if (u.v2)
+    launch_chain(umma_gemm_nt_v2_kernel, dim3(grid), dim3(v2::NUM_THREADS), v2::SMEM_BYTES, st, mp->ut, mp->ut, mp->ut, Gpart, (int64_t)u.ldm,
+                 (int64_t)m * u.ldm, w, ep, 0);
+  else
+    launch_chain(umma_gemm_nt_kernel, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, mp->ut, mp->ut, Gpart, (int64_t)u.ldm, (int64_t)m * u.ldm, w, ep);
   *n_split = S;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(err, "umma gram", e);

@@ -26,6 +26,10 @@ struct UmmaLatent {
   int m = 0, ldm = 0, Bcap = 0;
   float* UT = nullptr;   // U^T = (diag(sqrt(rho w)) V)^T, [m][Bcap], operand of the Gram product
   void* tmaps = nullptr; // host array of CUtensorMap (raw fp32 operands: Knm, V, L^-1, X, U^T)
+  // second-generation GEMM kernel (opt-in through the environment variable AGP_UMMA_V2; see agp_umma.cu): bit 0 = on,
+  // bit 1 = keep splitting the m x m operand inside the kernel.  Bsplit = TF32 hi / lo copies of L^-1 and X.
+  int v2 = 0;
+  float* Bsplit = nullptr;
 };
 
 bool umma_shape_ok(int m, int Bcap);
@@ -36,6 +40,10 @@ void umma_latent_free(UmmaLatent& u);
 // C[M x N] = A[M x K] * B[N x K]^T with K = m, 3xTF32 (operands split to hi/lo inside the kernel)
 int umma_gemm_nt(std::string* err, UmmaLatent& u, int a_which, int b_which, float* C, int M, int N, const UmmaEpilogue& ep,
                  cudaStream_t st);
+// v2 only (no-ops / null otherwise): refresh the pre-split copy of an m x m right operand (which = UM_LINV or UM_X) from its fp32
+// matrix [m][ldm]; pointer to the hi (lo = 0) or lo (lo = 1) copy, for producers that write the split themselves
+int umma_presplit(std::string* err, UmmaLatent& u, int which, const float* src, cudaStream_t st);
+float* umma_split_ptr(const UmmaLatent& u, int which, int lo);
 // U^T = (diag(sqrt(rho w)) V)^T into u.UT, fused with v1 += V^T g
 int umma_scale_transpose(std::string* err, UmmaLatent& u, const float* V, const double* w, double rho, const double* g, double* v1,
                          int B, int m, cudaStream_t st);

@@ -1,0 +1,28 @@
+#!/bin/bash
+# First GPU contact of the opt-in second-generation tcgen05 GEMM (AGP_UMMA_V2, csrc/agp_umma.cu): written without a GPU, so
+# everything runs under short timeouts (its mbarrier waits trap after ~2 s instead of hanging).
+# usage: gpurun --timeout 900 -- 'bash tools/umma_v2_check.sh [tag]'
+#   AGP_UMMA_V2=1  v2 kernel, L^-1 / X pre-split        AGP_UMMA_V2=3  v2 kernel, right operand split inside the kernel
+export TAG=${1:-umma_v2}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+for V in 1 3; do
+  # the tf32x3 parity tests exercise all three GEMM launches (V, V X^T statistics, Gram)
+  AGP_UMMA_V2=$V timeout 240 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "tf32x3 or full_size or baseline_configs or pipelined_pool or ragged_sizes or knm_tensor_core" \
+      > $OUT/pytest_v2_$V.log 2>&1; echo "v2=$V pytest rc=$?" | tee -a $OUT/pytest_v2_$V.log
+  tail -4 $OUT/pytest_v2_$V.log
+done
+timeout 300 python bench.py --steps 100 --warmup 5 > $OUT/bench_v1.json 2> $OUT/bench_v1.err; echo "bench v1 rc=$?"
+for V in 1 3; do
+  AGP_UMMA_V2=$V timeout 300 python bench.py --steps 100 --warmup 5 > $OUT/bench_v2_$V.json 2> $OUT/bench_v2_$V.err; echo "bench v2=$V rc=$?"
+done
+python - <<'PY'
+import json, glob, os
+for f in sorted(glob.glob(os.path.join("gpurun_out", os.environ.get("TAG", "umma_v2"), "bench_*.json"))):
+    try:
+        d = json.loads(open(f).read().strip().splitlines()[-1])
+        k = d["roofline"]["kernels"]
+        print(os.path.basename(f), round(d["value"]), "it/s;", {n: round(v["seconds_per_launch"] * 1e6, 1) for n, v in k.items()})
+    except Exception as e:
+        print(f, "unreadable:", e)
+PY
