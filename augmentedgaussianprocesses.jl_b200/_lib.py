@@ -103,6 +103,7 @@ SIGNATURES = {
     "agp_launch_count": (C.c_int64, [C.c_void_p]),
     "agp_time_kernel": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_double_p]),
     "agp_use_graph": (C.c_int, [C.c_void_p, C.c_int]),
+    "agp_experimental_ns_refine": (C.c_int, [C.c_void_p, C.c_int32, c_double_p, c_double_p, C.c_int32, C.c_int32, c_double_p, c_double_p]),
 }
 
 _lib = None

@@ -1862,4 +1862,43 @@ int agp_time_kernel(agp_model* model, int32_t which, int32_t reps, double* ms) {
 int64_t agp_launch_count(agp_model* model) { return (model && model->eng) ? model->eng->launch_count() : 0; }
 int agp_use_graph(agp_model* model, int on) { ENG(model); return e->use_graph(on); }
 
+// EXPERIMENTAL (see include/agp_b200.h): self-contained, does not touch any model
+int agp_experimental_ns_refine(agp_ctx* ctx, int32_t m, const double* P, double* Y, int32_t iters, int32_t mode, double* resid, double* ms) {
+  if (!ctx || !P || !Y || m < 128 || m % 128 || iters < 0 || iters > 64) {
+    if (ctx) ctx->err = "agp_experimental_ns_refine: needs m % 128 == 0, 0 <= iters <= 64 and non-null P, Y";
+    return AGP_ERR_BAD_ARG;
+  }
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return AGP_ERR_CUDA;
+  agp::UmmaNs ns;
+  int rc = agp::umma_ns_alloc(&ctx->err, ns, m, ctx->stream);
+  if (rc) { agp::umma_ns_free(ns); return rc; }
+  const size_t nn = (size_t)m * m;
+  std::vector<float> hp(nn), hy(nn);
+  for (size_t i = 0; i < nn; ++i) { hp[i] = (float)P[i]; hy[i] = (float)Y[i]; }
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  float t_ms = 0.f;
+  cudaError_t ce = cudaMemcpyAsync(ns.P(), hp.data(), nn * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(ns.Y(0), hy.data(), nn * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(ns.P64, P, nn * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+  if (ce == cudaSuccess) ce = cudaEventCreate(&e0);
+  if (ce == cudaSuccess) ce = cudaEventCreate(&e1);
+  if (ce == cudaSuccess) ce = cudaEventRecord(e0, ctx->stream);
+  if (ce == cudaSuccess) rc = agp::umma_ns_iterate(&ctx->err, ns, iters, mode, ctx->stream);
+  if (ce == cudaSuccess && !rc) ce = cudaEventRecord(e1, ctx->stream);
+  if (ce == cudaSuccess && !rc) ce = cudaMemcpyAsync(hy.data(), ns.Y(ns.cur), nn * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+  std::vector<double> hr(64, 0.0);
+  if (ce == cudaSuccess && !rc) ce = cudaMemcpyAsync(hr.data(), ns.resid, 64 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+  if (ce == cudaSuccess && !rc) ce = cudaStreamSynchronize(ctx->stream);
+  if (ce == cudaSuccess && !rc) ce = cudaEventElapsedTime(&t_ms, e0, e1);
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  agp::umma_ns_free(ns);
+  if (rc) return rc;
+  if (ce != cudaSuccess) { ctx->err = std::string("agp_experimental_ns_refine: ") + cudaGetErrorString(ce); return AGP_ERR_CUDA; }
+  for (size_t i = 0; i < nn; ++i) Y[i] = (double)hy[i];
+  if (resid) for (int i = 0; i < iters; ++i) resid[i] = std::sqrt(hr[i]);
+  if (ms) *ms = (double)t_ms;
+  return AGP_OK;
+}
+
 }  // extern "C"

@@ -438,6 +438,7 @@ umma_gemm_nt_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       float* cbase = C + (int64_t)wu.split * c_split_stride;
       float* crow = cbase + (int64_t)row * ldc + (int64_t)wu.tile_n * BN;
       double acc_sq = 0.0, acc_dot = 0.0;
+      float fsq = 0.f;
       wait_bounded(tmem_full(ab), (lt >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
@@ -450,6 +451,26 @@ umma_gemm_nt_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tmem_empty(ab));
+        }
+        if (ep.mode == UMMA_EPI_EYE_MINUS) {
+          const int col0 = wu.tile_n * BN + c * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float v = -__uint_as_float(rr[j]);
+            if (col0 + j == row) v += 1.f;
+            fsq = fmaf(v, v, fsq);
+            rr[j] = __float_as_uint(v);
+          }
+        } else if (ep.mode == UMMA_EPI_ADD) {
+          const float4* src = reinterpret_cast<const float4*>(ep.cin + (int64_t)row * ldc + (int64_t)wu.tile_n * BN + c * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 a = src[j];
+            rr[4 * j + 0] = __float_as_uint(__uint_as_float(rr[4 * j + 0]) + a.x);
+            rr[4 * j + 1] = __float_as_uint(__uint_as_float(rr[4 * j + 1]) + a.y);
+            rr[4 * j + 2] = __float_as_uint(__uint_as_float(rr[4 * j + 2]) + a.z);
+            rr[4 * j + 3] = __float_as_uint(__uint_as_float(rr[4 * j + 3]) + a.w);
+          }
         }
         if (ep.mode != UMMA_EPI_STATS_ONLY) {
           float4* dst = reinterpret_cast<float4*>(crow + c * 32);
@@ -473,6 +494,12 @@ umma_gemm_nt_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       }
       if (ep.mode == UMMA_EPI_STORE_SUMSQ) atomicAdd(ep.acc0 + row, acc_sq);
       if (ep.mode == UMMA_EPI_STATS_ONLY) { atomicAdd(ep.acc0 + row, acc_sq); atomicAdd(ep.acc1 + row, acc_dot); }
+      if (ep.mode == UMMA_EPI_EYE_MINUS) {
+        double sq = (double)fsq;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        if (lane == 0) atomicAdd(ep.acc0, sq);
+      }
     }
   } else {
     // ===== converter groups: group c splits the k-blocks g = c (mod NCG) =====
@@ -782,6 +809,134 @@ int umma_gram(std::string* err, UmmaLatent& u, float* Gpart, int B, int m, int* 
   *n_split = S;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(err, "umma gram", e);
+  return 0;
+}
+
+// ---- experimental Newton-Schulz refinement (see agp_umma.h) ----
+struct NsMaps { CUtensorMap P, Y[2], T; };
+
+// T = I - Y P with the product in fp64 on DMMA (mma.sync.m8n8k4.f64): Y fp32 [m][ldy], P fp64 [m][ldp] symmetric, T fp32 [m][ldt];
+// *resid2 += |T|_F^2.  The residual is where the accuracy of the refinement is decided (an fp32 / 3xTF32 residual floors at
+// eps_fp32 * cond(P), profiles/r1/studies/newton_schulz_precision_study.txt), the correction product may be low precision.
+// One CTA (8 warps) per 64 x 64 tile of T, 32-deep k-steps staged in shared memory (leading dimension 36 = 4 mod 16: conflict-free
+// 8x4 fragment loads, as in agp_tail2.cuh); warp w owns rows 8w..8w+7 of the tile.
+constexpr int NSLD = 36, NSK = 32;
+__global__ void __launch_bounds__(256) ns_resid_f64_kernel(const float* __restrict__ Y, int64_t ldy, const double* __restrict__ P, int64_t ldp,
+                                                           float* __restrict__ T, int64_t ldt, int m, double* __restrict__ resid2) {
+  __shared__ double sA[64 * NSLD], sB[64 * NSLD];
+  const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5, r = lane >> 2, kk = lane & 3;
+  double acc[8][2];
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) { acc[nb][0] = 0.0; acc[nb][1] = 0.0; }
+  for (int k0 = 0; k0 < m; k0 += NSK) {
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {                 // 64 x 32 elements as 1024 pairs
+      const int e = t + u * 256, row = e >> 4, c2 = (e & 15) * 2;
+      const float2 y = *reinterpret_cast<const float2*>(Y + (int64_t)(i0 + row) * ldy + k0 + c2);
+      *reinterpret_cast<double2*>(sA + row * NSLD + c2) = make_double2((double)y.x, (double)y.y);
+      *reinterpret_cast<double2*>(sB + row * NSLD + c2) = *reinterpret_cast<const double2*>(P + (int64_t)(j0 + row) * ldp + k0 + c2);
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int k = 0; k < NSK; k += 4) {
+      const double a = sA[(8 * w + r) * NSLD + k + kk];
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb) {
+        const double b = sB[(8 * nb + r) * NSLD + k + kk];   // P[j][k] = P[k][j]
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(acc[nb][0]), "+d"(acc[nb][1]) : "d"(a), "d"(b));
+      }
+    }
+  }
+  double sq = 0.0;
+  const int row = i0 + 8 * w + r;
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+    const int col = j0 + 8 * nb + 2 * kk;
+    const double v0 = (row == col ? 1.0 : 0.0) - acc[nb][0], v1 = (row == col + 1 ? 1.0 : 0.0) - acc[nb][1];
+    sq = fma(v0, v0, fma(v1, v1, sq));
+    *reinterpret_cast<float2*>(T + (int64_t)row * ldt + col) = make_float2((float)v0, (float)v1);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  if (lane == 0) atomicAdd(resid2, sq);
+}
+
+// Y <- (Y + Y^T) / 2 in place, 32 x 32 tiles, one CTA per tile pair (bi <= bj).  Rounding leaves an antisymmetric part in Y that
+// the Newton-Schulz map doubles every iteration; removed once per refinement it never gets past ~1e-6.
+__global__ void __launch_bounds__(256) ns_symmetrize_kernel(float* __restrict__ Y, int64_t ld, int m) {
+  __shared__ float a[32][33], b[32][33];
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bi > bj) return;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int rr = ty; rr < 32; rr += 8) {
+    a[rr][tx] = Y[(int64_t)(bi * 32 + rr) * ld + bj * 32 + tx];
+    b[rr][tx] = Y[(int64_t)(bj * 32 + rr) * ld + bi * 32 + tx];
+  }
+  __syncthreads();
+  for (int rr = ty; rr < 32; rr += 8) {
+    Y[(int64_t)(bi * 32 + rr) * ld + bj * 32 + tx] = 0.5f * (a[rr][tx] + b[tx][rr]);
+    Y[(int64_t)(bj * 32 + rr) * ld + bi * 32 + tx] = 0.5f * (b[rr][tx] + a[tx][rr]);
+  }
+}
+
+int umma_ns_alloc(std::string* err, UmmaNs& ns, int m, cudaStream_t st) {
+  if (m < 128 || m % 128) return fail(err, "Newton-Schulz path needs m % 128 == 0");
+  ns.m = m; ns.ldm = m; ns.cur = 0;
+  const size_t each = (size_t)m * ns.ldm;
+  cudaError_t e;
+  if ((e = cudaMalloc(&ns.buf, 4 * each * sizeof(float))) != cudaSuccess) return fail(err, "cudaMalloc", e);
+  if ((e = cudaMalloc(&ns.resid, 64 * sizeof(double))) != cudaSuccess) return fail(err, "cudaMalloc", e);
+  if ((e = cudaMalloc(&ns.P64, each * sizeof(double))) != cudaSuccess) return fail(err, "cudaMalloc", e);
+  cudaMemsetAsync(ns.buf, 0, 4 * each * sizeof(float), st);
+  cudaMemsetAsync(ns.resid, 0, 64 * sizeof(double), st);
+  NsMaps* mp = new NsMaps();
+  ns.maps = mp;
+  bool ok = make_map(&mp->P, ns.P(), m, m, ns.ldm) && make_map(&mp->Y[0], ns.Y(0), m, m, ns.ldm) &&
+            make_map(&mp->Y[1], ns.Y(1), m, m, ns.ldm) && make_map(&mp->T, ns.T(), m, m, ns.ldm);
+  if (!ok) return fail(err, "cuTensorMapEncodeTiled failed (ns)");
+  if ((e = cudaFuncSetAttribute(umma_gemm_nt_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SMEM_BYTES)) != cudaSuccess)
+    return fail(err, "cudaFuncSetAttribute (v2)", e);
+  return 0;
+}
+
+void umma_ns_free(UmmaNs& ns) {
+  cudaFree(ns.buf); ns.buf = nullptr;
+  cudaFree(ns.resid); ns.resid = nullptr;
+  cudaFree(ns.P64); ns.P64 = nullptr;
+  delete (NsMaps*)ns.maps; ns.maps = nullptr;
+}
+
+int umma_ns_iterate(std::string* err, UmmaNs& ns, int iters, int mode, cudaStream_t st) {
+  NsMaps* mp = (NsMaps*)ns.maps;
+  if (!mp || iters < 0 || iters > 64) return fail(err, "umma_ns_iterate: bad state / iteration count");
+  GemmWork w{};
+  w.ntm = ns.m / BM; w.ntn = ns.m / BN; w.nsplit = 1; w.total = w.ntm * w.ntn;
+  w.total_kb = ns.m / BK; w.kb_per_split = w.total_kb; w.tri_mode = 0;
+  const int grid = w.total < sm_count() ? w.total : sm_count();
+  cudaMemsetAsync(ns.resid, 0, 64 * sizeof(double), st);
+  for (int it = 0; it < iters; ++it) {
+    // T = I - Y P   (= (I - P Y)^T for symmetric P, Y: exactly the [n][k] operand the second product needs)
+    if (mode & 1) {
+      ns_resid_f64_kernel<<<dim3(ns.m / 64, ns.m / 64), 256, 0, st>>>(ns.Y(ns.cur), (int64_t)ns.ldm, ns.P64, (int64_t)ns.m, ns.T(), (int64_t)ns.ldm,
+                                                                    ns.m, ns.resid + it);
+    } else {
+      UmmaEpilogue e1{};
+      e1.mode = UMMA_EPI_EYE_MINUS; e1.acc0 = ns.resid + it;
+      launch_chain(umma_gemm_nt_v2_kernel, dim3(grid), dim3(v2::NUM_THREADS), v2::SMEM_BYTES, st, mp->Y[ns.cur], mp->P, mp->P, ns.T(),
+                   (int64_t)ns.ldm, (int64_t)0, w, e1, 0);
+    }
+    UmmaEpilogue e2{};   // Y' = Y + Y (I - P Y)
+    e2.mode = UMMA_EPI_ADD; e2.cin = ns.Y(ns.cur);
+    launch_chain(umma_gemm_nt_v2_kernel, dim3(grid), dim3(v2::NUM_THREADS), v2::SMEM_BYTES, st, mp->Y[ns.cur], mp->T, mp->T, ns.Y(ns.cur ^ 1),
+                 (int64_t)ns.ldm, (int64_t)0, w, e2, 0);
+    ns.cur ^= 1;
+  }
+  if ((mode & 2) && iters > 0) ns_symmetrize_kernel<<<dim3(ns.m / 32, ns.m / 32), 256, 0, st>>>(ns.Y(ns.cur), (int64_t)ns.ldm, ns.m);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(err, "umma_ns_iterate", e);
   return 0;
 }
 

@@ -15,11 +15,15 @@ enum UmmaEpiMode : int {
   UMMA_EPI_STORE = 0,        // C = acc
   UMMA_EPI_STORE_SUMSQ = 1,  // C = acc ; acc0[row] += sum_col acc^2                       (V = Knm L^-T -> Ktilde)
   UMMA_EPI_STATS_ONLY = 2,   // no store ; acc0[row] += sum acc^2 ; acc1[row] += sum acc*tvec[col]   (V X^T -> var_f, mean_f)
-  UMMA_EPI_STORE_MIRROR = 3  // C = acc and C^T = acc^T for off-diagonal tiles              (symmetric Gram product)
+  UMMA_EPI_STORE_MIRROR = 3, // C = acc and C^T = acc^T for off-diagonal tiles              (symmetric Gram product)
+  // second-generation kernel only (experimental Newton-Schulz tail, see UmmaNs):
+  UMMA_EPI_EYE_MINUS = 4,    // C = I - acc ; acc0[0] += |C|_F^2
+  UMMA_EPI_ADD = 5           // C = cin + acc   (cin: same shape / leading dimension as C)
 };
 struct UmmaEpilogue {
   int mode = 0;
   double* acc0 = nullptr; double* acc1 = nullptr; const double* tvec = nullptr;
+  const float* cin = nullptr;
 };
 
 struct UmmaLatent {
@@ -51,6 +55,25 @@ int umma_scale_transpose(std::string* err, UmmaLatent& u, const float* V, const 
 // per-step chain launches carry the programmatic-dependent-launch attribute when on (set per call site by the engine)
 void umma_set_pdl(bool on);
 int umma_gram(std::string* err, UmmaLatent& u, float* Gpart, int B, int m, int* n_split, cudaStream_t st);
+
+// ---- EXPERIMENTAL, not on the product path (never run on a GPU yet): Newton-Schulz refinement of an m x m inverse ----
+// Y <- Y + Y (I - P Y) as two 3xTF32 tensor-core products per iteration (T = I - Y P, then Y' = Y + Y T^T), the candidate
+// replacement of the fp64 Cholesky tail once the Robbins-Monro step is small (profiles/r1/studies/newton_schulz_*.txt:
+// spectral radius of I - P_new Sigma_old ~ 0.1-0.3 after the first iterations of C2, 3 iterations reach the fp32 floor).
+struct UmmaNs {
+  int m = 0, ldm = 0, cur = 0;       // cur: which Y buffer holds the current iterate
+  float* buf = nullptr;              // [P | Y0 | Y1 | T], each [m][ldm] fp32
+  double* resid = nullptr;           // [64] |I - Y P|_F^2 at the start of each iteration of the last umma_ns_iterate call
+  double* P64 = nullptr;             // [m][m] fp64 copy of P for the DMMA residual
+  void* maps = nullptr;
+  float* P() const { return buf; }
+  float* Y(int i) const { return buf + (size_t)(1 + i) * m * ldm; }
+  float* T() const { return buf + (size_t)3 * m * ldm; }
+};
+int umma_ns_alloc(std::string* err, UmmaNs& ns, int m, cudaStream_t st);
+void umma_ns_free(UmmaNs& ns);
+// mode bit 0: residual T = I - Y P in fp64 on DMMA (ns_resid_f64_kernel) instead of 3xTF32; bit 1: symmetrise Y at the end
+int umma_ns_iterate(std::string* err, UmmaNs& ns, int iters, int mode, cudaStream_t st);
 
 // ---- K_nm construction on the tensor core (agp_knm.cu) ----
 struct UmmaKnm {

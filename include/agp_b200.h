@@ -264,6 +264,17 @@ int agp_time_kernel(agp_model* model, int32_t which, int32_t reps, double* ms_pe
 /* capture the step into a CUDA graph and replay it on later agp_step*(idx == NULL) calls. */
 int agp_use_graph(agp_model* model, int on);
 
+/* EXPERIMENTAL -- NOT on the product path and not yet run on a GPU (written after the round's GPU budget was spent).
+ * Building block of the planned replacement of the fp64 Cholesky tail of global_update! (inference/inference.jl:25-28,
+ * Sigma = -1/2 eta2^-1): Newton-Schulz refinement  Y <- Y + Y (I - P Y)  of an approximate inverse Y of the SPD m x m
+ * matrix P, `iters` times, as 3xTF32 tcgen05 products (m % 128 == 0).  P, Y: row-major fp64 host [m][m], Y is updated in
+ * place (through an fp32 round trip).  mode bit 0: residual I - Y P in fp64 on DMMA instead of 3xTF32 (an fp32-class
+ * residual floors at eps_fp32 * cond(P)); bit 1: symmetrise Y at the end (the iteration doubles the antisymmetric
+ * rounding residue every pass).  resid[i] (may be NULL) = |I - Y P|_F at the start of iteration i; *ms (may be
+ * NULL) = device time of the whole refinement.  Self-contained: allocates and frees its own buffers, touches no model.
+ * Feasibility numbers: profiles/r1/studies/. */
+int agp_experimental_ns_refine(agp_ctx* ctx, int32_t m, const double* P, double* Y, int32_t iters, int32_t mode, double* resid, double* ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,3 +26,6 @@ for f in sorted(glob.glob(os.path.join("gpurun_out", os.environ.get("TAG", "umma
     except Exception as e:
         print(f, "unreadable:", e)
 PY
+# Newton-Schulz refinement on the v2 kernel (experimental C-ABI hook), parity against the fp64 inverse + device time
+AGP_EXPERIMENTAL=1 timeout 240 python -m pytest tests/test_experimental_gpu.py -m gpu -x -q -s > $OUT/pytest_ns.log 2>&1; echo "ns pytest rc=$?" | tee -a $OUT/pytest_ns.log
+grep -E "rel err|passed|failed|rror" $OUT/pytest_ns.log | head -20
