@@ -823,7 +823,7 @@ struct NsMaps { CUtensorMap P, Y[2], T; };
 constexpr int NSLD = 36, NSK = 32;
 __global__ void __launch_bounds__(256) ns_resid_f64_kernel(const float* __restrict__ Y, int64_t ldy, const double* __restrict__ P, int64_t ldp,
                                                            float* __restrict__ T, int64_t ldt, int m, double* __restrict__ resid2) {
-  __shared__ double sA[64 * NSLD], sB[64 * NSLD];
+  __shared__ __align__(16) double sA[64 * NSLD], sB[64 * NSLD];
   const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
   const int t = threadIdx.x, lane = t & 31, w = t >> 5, r = lane >> 2, kk = lane & 3;
   double acc[8][2];
