@@ -6,7 +6,7 @@ inexact Y only perturbs the local variables of the following step.  Prints, afte
 (n = 1e6, D = 32, m = 512, B = 8192, Logistic), the deviation of mu, Sigma (both recomputed exactly from eta at the
 end, as the getters do) and of the ELBO from the exact oracle run.
 
-    python profiles/r1/studies/newton_schulz_parity_study.py [iters] [t0] [k_ns]
+    python tests/studies/newton_schulz_parity_study.py [iters] [t0] [k_ns]
 """
 import os
 import sys
@@ -14,7 +14,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import agp_oracle as O  # noqa: E402

@@ -2,7 +2,7 @@
 P = identity + decaying spectrum up to cond(P) (the shape of the whitened precision P_v = I + rho V^T theta V), start
 20 % off in every direction.  Columns: relative Frobenius error of Y after 1..5 iterations for
   residual in fp32 | fp64,   Y symmetrised after every iteration: no | yes.
-    python profiles/r1/studies/newton_schulz_precision_study.py
+    python tests/studies/newton_schulz_precision_study.py
 """
 import numpy as np
 

@@ -5,7 +5,7 @@ Converges iff the spectral radius of E0 = I - P_new Sigma_old is < 1; the error 
 For every SVI iteration of a C2-shaped run this prints rho(E0), the Robbins-Monro step, and the iterations needed
 for |I - P Y|_F / sqrt(m) < 1e-9 with the residual in fp64 and the correction product Y E in fp32.
 
-    python profiles/r1/studies/newton_schulz_tail_study.py [iters]
+    python tests/studies/newton_schulz_tail_study.py [iters]
 """
 import os
 import sys
@@ -13,7 +13,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import agp_oracle as O  # noqa: E402
