@@ -1878,14 +1878,14 @@ int agp_experimental_ns_refine(agp_ctx* ctx, int32_t m, const double* P, double*
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   float t_ms = 0.f;
   cudaError_t ce = cudaMemcpyAsync(ns.P(), hp.data(), nn * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
-  if (ce == cudaSuccess) ce = cudaMemcpyAsync(ns.Y(0), hy.data(), nn * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(ns.Y(), hy.data(), nn * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
   if (ce == cudaSuccess) ce = cudaMemcpyAsync(ns.P64, P, nn * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
   if (ce == cudaSuccess) ce = cudaEventCreate(&e0);
   if (ce == cudaSuccess) ce = cudaEventCreate(&e1);
   if (ce == cudaSuccess) ce = cudaEventRecord(e0, ctx->stream);
-  if (ce == cudaSuccess) rc = agp::umma_ns_iterate(&ctx->err, ns, iters, mode, ctx->stream);
+  if (ce == cudaSuccess) rc = agp::umma_ns_iterate(&ctx->err, ns, iters, mode, nullptr, 0, ctx->stream);
   if (ce == cudaSuccess && !rc) ce = cudaEventRecord(e1, ctx->stream);
-  if (ce == cudaSuccess && !rc) ce = cudaMemcpyAsync(hy.data(), ns.Y(ns.cur), nn * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+  if (ce == cudaSuccess && !rc) ce = cudaMemcpyAsync(hy.data(), ns.Y(), nn * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
   std::vector<double> hr(64, 0.0);
   if (ce == cudaSuccess && !rc) ce = cudaMemcpyAsync(hr.data(), ns.resid, 64 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
   if (ce == cudaSuccess && !rc) ce = cudaStreamSynchronize(ctx->stream);

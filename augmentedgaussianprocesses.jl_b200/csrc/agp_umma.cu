@@ -472,7 +472,7 @@ umma_gemm_nt_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             rr[4 * j + 3] = __float_as_uint(__uint_as_float(rr[4 * j + 3]) + a.w);
           }
         }
-        if (ep.mode != UMMA_EPI_STATS_ONLY) {
+        if (ep.mode != UMMA_EPI_STATS_ONLY && ep.mode != UMMA_EPI_STATS_SIGMA) {
           float4* dst = reinterpret_cast<float4*>(crow + c * 32);
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -486,6 +486,20 @@ umma_gemm_nt_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             if (ep.mode == UMMA_EPI_STATS_ONLY) acc_dot = fma(v, ep.tvec[wu.tile_n * BN + c * 32 + j], acc_dot);
           }
         }
+        if (ep.mode == UMMA_EPI_STATS_SIGMA) {
+          const float4* vrow = reinterpret_cast<const float4*>(ep.cin + (int64_t)row * ldc + (int64_t)wu.tile_n * BN + c * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 a = vrow[j];
+            const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const double v = (double)__uint_as_float(rr[4 * j + e]);
+              acc_sq = fma(v, (double)av[e], acc_sq);
+              acc_dot = fma(v, ep.tvec[wu.tile_n * BN + c * 32 + 4 * j + e], acc_dot);
+            }
+          }
+        }
         if (ep.mode == UMMA_EPI_STORE_MIRROR && wu.tile_n != wu.tile_m) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
@@ -493,7 +507,7 @@ umma_gemm_nt_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         }
       }
       if (ep.mode == UMMA_EPI_STORE_SUMSQ) atomicAdd(ep.acc0 + row, acc_sq);
-      if (ep.mode == UMMA_EPI_STATS_ONLY) { atomicAdd(ep.acc0 + row, acc_sq); atomicAdd(ep.acc1 + row, acc_dot); }
+      if (ep.mode == UMMA_EPI_STATS_ONLY || ep.mode == UMMA_EPI_STATS_SIGMA) { atomicAdd(ep.acc0 + row, acc_sq); atomicAdd(ep.acc1 + row, acc_dot); }
       if (ep.mode == UMMA_EPI_EYE_MINUS) {
         double sq = (double)fsq;
 #pragma unroll
@@ -813,7 +827,7 @@ int umma_gram(std::string* err, UmmaLatent& u, float* Gpart, int B, int m, int* 
 }
 
 // ---- experimental Newton-Schulz refinement (see agp_umma.h) ----
-struct NsMaps { CUtensorMap P, Y[2], T; };
+struct NsMaps { CUtensorMap P, Y, W[2], T; };
 
 // T = I - Y P with the product in fp64 on DMMA (mma.sync.m8n8k4.f64): Y fp32 [m][ldy], P fp64 [m][ldp] symmetric, T fp32 [m][ldt];
 // *resid2 += |T|_F^2.  The residual is where the accuracy of the refinement is decided (an fp32 / 3xTF32 residual floors at
@@ -864,38 +878,39 @@ __global__ void __launch_bounds__(256) ns_resid_f64_kernel(const float* __restri
   if (lane == 0) atomicAdd(resid2, sq);
 }
 
-// Y <- (Y + Y^T) / 2 in place, 32 x 32 tiles, one CTA per tile pair (bi <= bj).  Rounding leaves an antisymmetric part in Y that
-// the Newton-Schulz map doubles every iteration; removed once per refinement it never gets past ~1e-6.
-__global__ void __launch_bounds__(256) ns_symmetrize_kernel(float* __restrict__ Y, int64_t ld, int m) {
+// Out = (S + S^T) / 2, 32 x 32 tiles, one CTA per tile pair (bi <= bj); Out != S.  Rounding leaves an antisymmetric part in the
+// iterate that the Newton-Schulz map doubles every pass; removed once per refinement it never gets past ~1e-6.
+__global__ void __launch_bounds__(256) ns_symmetrize_kernel(const float* __restrict__ S, float* __restrict__ Out, int64_t ld, int m) {
   __shared__ float a[32][33], b[32][33];
   const int bi = blockIdx.y, bj = blockIdx.x;
   if (bi > bj) return;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   for (int rr = ty; rr < 32; rr += 8) {
-    a[rr][tx] = Y[(int64_t)(bi * 32 + rr) * ld + bj * 32 + tx];
-    b[rr][tx] = Y[(int64_t)(bj * 32 + rr) * ld + bi * 32 + tx];
+    a[rr][tx] = S[(int64_t)(bi * 32 + rr) * ld + bj * 32 + tx];
+    b[rr][tx] = S[(int64_t)(bj * 32 + rr) * ld + bi * 32 + tx];
   }
   __syncthreads();
   for (int rr = ty; rr < 32; rr += 8) {
-    Y[(int64_t)(bi * 32 + rr) * ld + bj * 32 + tx] = 0.5f * (a[rr][tx] + b[tx][rr]);
-    Y[(int64_t)(bj * 32 + rr) * ld + bi * 32 + tx] = 0.5f * (b[rr][tx] + a[tx][rr]);
+    Out[(int64_t)(bi * 32 + rr) * ld + bj * 32 + tx] = 0.5f * (a[rr][tx] + b[tx][rr]);
+    Out[(int64_t)(bj * 32 + rr) * ld + bi * 32 + tx] = 0.5f * (b[rr][tx] + a[tx][rr]);
   }
 }
 
 int umma_ns_alloc(std::string* err, UmmaNs& ns, int m, cudaStream_t st) {
   if (m < 128 || m % 128) return fail(err, "Newton-Schulz path needs m % 128 == 0");
-  ns.m = m; ns.ldm = m; ns.cur = 0;
+  ns.m = m; ns.ldm = m;
   const size_t each = (size_t)m * ns.ldm;
   cudaError_t e;
-  if ((e = cudaMalloc(&ns.buf, 4 * each * sizeof(float))) != cudaSuccess) return fail(err, "cudaMalloc", e);
+  if ((e = cudaMalloc(&ns.buf, 5 * each * sizeof(float))) != cudaSuccess) return fail(err, "cudaMalloc", e);
   if ((e = cudaMalloc(&ns.resid, 64 * sizeof(double))) != cudaSuccess) return fail(err, "cudaMalloc", e);
   if ((e = cudaMalloc(&ns.P64, each * sizeof(double))) != cudaSuccess) return fail(err, "cudaMalloc", e);
-  cudaMemsetAsync(ns.buf, 0, 4 * each * sizeof(float), st);
+  cudaMemsetAsync(ns.buf, 0, 5 * each * sizeof(float), st);
   cudaMemsetAsync(ns.resid, 0, 64 * sizeof(double), st);
   NsMaps* mp = new NsMaps();
   ns.maps = mp;
-  bool ok = make_map(&mp->P, ns.P(), m, m, ns.ldm) && make_map(&mp->Y[0], ns.Y(0), m, m, ns.ldm) &&
-            make_map(&mp->Y[1], ns.Y(1), m, m, ns.ldm) && make_map(&mp->T, ns.T(), m, m, ns.ldm);
+  bool ok = make_map(&mp->P, ns.P(), m, m, ns.ldm) && make_map(&mp->Y, ns.Y(), m, m, ns.ldm) &&
+            make_map(&mp->W[0], ns.W(0), m, m, ns.ldm) && make_map(&mp->W[1], ns.W(1), m, m, ns.ldm) &&
+            make_map(&mp->T, ns.T(), m, m, ns.ldm);
   if (!ok) return fail(err, "cuTensorMapEncodeTiled failed (ns)");
   if ((e = cudaFuncSetAttribute(umma_gemm_nt_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SMEM_BYTES)) != cudaSuccess)
     return fail(err, "cudaFuncSetAttribute (v2)", e);
@@ -909,32 +924,40 @@ void umma_ns_free(UmmaNs& ns) {
   delete (NsMaps*)ns.maps; ns.maps = nullptr;
 }
 
-int umma_ns_iterate(std::string* err, UmmaNs& ns, int iters, int mode, cudaStream_t st) {
+int umma_ns_iterate(std::string* err, UmmaNs& ns, int iters, int mode, const double* P64, int64_t ldp, cudaStream_t st) {
   NsMaps* mp = (NsMaps*)ns.maps;
   if (!mp || iters < 0 || iters > 64) return fail(err, "umma_ns_iterate: bad state / iteration count");
+  if (!P64) { P64 = ns.P64; ldp = ns.m; }
   GemmWork w{};
   w.ntm = ns.m / BM; w.ntn = ns.m / BN; w.nsplit = 1; w.total = w.ntm * w.ntn;
   w.total_kb = ns.m / BK; w.kb_per_split = w.total_kb; w.tri_mode = 0;
   const int grid = w.total < sm_count() ? w.total : sm_count();
   cudaMemsetAsync(ns.resid, 0, 64 * sizeof(double), st);
+  // the iterate travels Y -> W0 -> W1 -> W0 ... and returns to Y at the end: every launch sees the same addresses on every call
+  const float* src = ns.Y();
+  const CUtensorMap* src_map = &mp->Y;
   for (int it = 0; it < iters; ++it) {
+    float* dst = ns.W(it & 1);
     // T = I - Y P   (= (I - P Y)^T for symmetric P, Y: exactly the [n][k] operand the second product needs)
     if (mode & 1) {
-      ns_resid_f64_kernel<<<dim3(ns.m / 64, ns.m / 64), 256, 0, st>>>(ns.Y(ns.cur), (int64_t)ns.ldm, ns.P64, (int64_t)ns.m, ns.T(), (int64_t)ns.ldm,
-                                                                    ns.m, ns.resid + it);
+      ns_resid_f64_kernel<<<dim3(ns.m / 64, ns.m / 64), 256, 0, st>>>(src, (int64_t)ns.ldm, P64, ldp, ns.T(), (int64_t)ns.ldm, ns.m, ns.resid + it);
     } else {
       UmmaEpilogue e1{};
       e1.mode = UMMA_EPI_EYE_MINUS; e1.acc0 = ns.resid + it;
-      launch_chain(umma_gemm_nt_v2_kernel, dim3(grid), dim3(v2::NUM_THREADS), v2::SMEM_BYTES, st, mp->Y[ns.cur], mp->P, mp->P, ns.T(),
+      launch_chain(umma_gemm_nt_v2_kernel, dim3(grid), dim3(v2::NUM_THREADS), v2::SMEM_BYTES, st, *src_map, mp->P, mp->P, ns.T(),
                    (int64_t)ns.ldm, (int64_t)0, w, e1, 0);
     }
     UmmaEpilogue e2{};   // Y' = Y + Y (I - P Y)
-    e2.mode = UMMA_EPI_ADD; e2.cin = ns.Y(ns.cur);
-    launch_chain(umma_gemm_nt_v2_kernel, dim3(grid), dim3(v2::NUM_THREADS), v2::SMEM_BYTES, st, mp->Y[ns.cur], mp->T, mp->T, ns.Y(ns.cur ^ 1),
+    e2.mode = UMMA_EPI_ADD; e2.cin = src;
+    launch_chain(umma_gemm_nt_v2_kernel, dim3(grid), dim3(v2::NUM_THREADS), v2::SMEM_BYTES, st, *src_map, mp->T, mp->T, dst,
                  (int64_t)ns.ldm, (int64_t)0, w, e2, 0);
-    ns.cur ^= 1;
+    src = dst;
+    src_map = &mp->W[it & 1];
   }
-  if ((mode & 2) && iters > 0) ns_symmetrize_kernel<<<dim3(ns.m / 32, ns.m / 32), 256, 0, st>>>(ns.Y(ns.cur), (int64_t)ns.ldm, ns.m);
+  if (iters > 0) {
+    if (mode & 2) ns_symmetrize_kernel<<<dim3(ns.m / 32, ns.m / 32), 256, 0, st>>>(src, ns.Y(), (int64_t)ns.ldm, ns.m);
+    else cudaMemcpyAsync(ns.Y(), src, (size_t)ns.m * ns.ldm * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(err, "umma_ns_iterate", e);
   return 0;

@@ -18,7 +18,9 @@ enum UmmaEpiMode : int {
   UMMA_EPI_STORE_MIRROR = 3, // C = acc and C^T = acc^T for off-diagonal tiles              (symmetric Gram product)
   // second-generation kernel only (experimental Newton-Schulz tail, see UmmaNs):
   UMMA_EPI_EYE_MINUS = 4,    // C = I - acc ; acc0[0] += |C|_F^2
-  UMMA_EPI_ADD = 5           // C = cin + acc   (cin: same shape / leading dimension as C)
+  UMMA_EPI_ADD = 5,          // C = cin + acc   (cin: same shape / leading dimension as C)
+  UMMA_EPI_STATS_SIGMA = 6   // no store ; acc0[row] += sum acc*cin[row][col] ; acc1[row] += sum acc*tvec[col]
+                             //   (V Sigma_v -> var_f = rowsum((V Sigma_v) o V), mean_f = (V Sigma_v) eta1_v: statistics against the full covariance)
 };
 struct UmmaEpilogue {
   int mode = 0;
@@ -61,19 +63,21 @@ int umma_gram(std::string* err, UmmaLatent& u, float* Gpart, int B, int m, int* 
 // replacement of the fp64 Cholesky tail once the Robbins-Monro step is small (profiles/r1/studies/newton_schulz_*.txt:
 // spectral radius of I - P_new Sigma_old ~ 0.1-0.3 after the first iterations of C2, 3 iterations reach the fp32 floor).
 struct UmmaNs {
-  int m = 0, ldm = 0, cur = 0;       // cur: which Y buffer holds the current iterate
-  float* buf = nullptr;              // [P | Y0 | Y1 | T], each [m][ldm] fp32
+  int m = 0, ldm = 0;
+  float* buf = nullptr;              // [P | Y | W0 | W1 | T], each [m][ldm] fp32
   double* resid = nullptr;           // [64] |I - Y P|_F^2 at the start of each iteration of the last umma_ns_iterate call
-  double* P64 = nullptr;             // [m][m] fp64 copy of P for the DMMA residual
+  double* P64 = nullptr;             // [m][m] fp64 P for the DMMA residual (the caller may pass its own matrix instead)
   void* maps = nullptr;
-  float* P() const { return buf; }
-  float* Y(int i) const { return buf + (size_t)(1 + i) * m * ldm; }
-  float* T() const { return buf + (size_t)3 * m * ldm; }
+  float* P() const { return buf; }                                   // fp32 P, only read by the 3xTF32 residual (mode bit 0 clear)
+  float* Y() const { return buf + (size_t)1 * m * ldm; }             // the iterate: read at entry, rewritten at exit (fixed address,
+  float* W(int i) const { return buf + (size_t)(2 + i) * m * ldm; }  //   so a captured CUDA graph stays valid); W0 / W1: ping-pong work buffers
+  float* T() const { return buf + (size_t)4 * m * ldm; }
 };
 int umma_ns_alloc(std::string* err, UmmaNs& ns, int m, cudaStream_t st);
 void umma_ns_free(UmmaNs& ns);
-// mode bit 0: residual T = I - Y P in fp64 on DMMA (ns_resid_f64_kernel) instead of 3xTF32; bit 1: symmetrise Y at the end
-int umma_ns_iterate(std::string* err, UmmaNs& ns, int iters, int mode, cudaStream_t st);
+// `iters` refinements of ns.Y() in place.  mode bit 0: residual T = I - Y P in fp64 on DMMA (ns_resid_f64_kernel, reads P64 with
+// leading dimension ldp; P64 == nullptr -> ns.P64, ldp = m) instead of 3xTF32 (reads ns.P()); bit 1: symmetrise the result
+int umma_ns_iterate(std::string* err, UmmaNs& ns, int iters, int mode, const double* P64, int64_t ldp, cudaStream_t st);
 
 // ---- K_nm construction on the tensor core (agp_knm.cu) ----
 struct UmmaKnm {
