@@ -155,6 +155,10 @@ struct Engine : EngineBase {
     UmmaLatent um;                                    // tcgen05 path
     UmmaKnm uk; bool knm_tc = false;                  // tcgen05 K_nm construction (D <= 128)
     int gram_splits = 1;                              // split-K partials of the last Gram product
+    // experimental Newton-Schulz tail (AGP_TAIL_NS): ns.Y() = Sigma_v (fp32, full symmetric) refined from step to step
+    UmmaNs ns; bool ns_alloc = false;
+    bool ns_seeded = false;      // ns.Y() is the covariance of the current eta2_v
+    bool factor_valid = true;    // Xv / Xv_T / tvec describe the current natural parameters
   };
   std::vector<Latent> lat;
 
@@ -400,6 +404,13 @@ struct Engine : EngineBase {
     CK(cudaFuncSetAttribute(tail2_potf2_first_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL2_SMEM));
     CK(cudaFuncSetAttribute(tail2_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL2_SMEM));
     { const char* e = getenv("AGP_TAIL_PDL"); if (e && e[0] == '0') tail_pdl = false; }
+    { const char* e = getenv("AGP_TAIL_NS"); if (e) ns_iters = std::max(0, std::min(8, atoi(e))); }
+    { const char* e = getenv("AGP_TAIL_NS_AFTER"); if (e) ns_after = std::max(1, atoi(e)); }
+    { const char* e = getenv("AGP_TAIL_NS_TOL"); if (e && atof(e) > 0.0) ns_tol = atof(e); }
+    if (ns_iters > 0 && ns_eligible()) {
+      CKS(umma_ns_alloc(ctx_err(), lat[0].ns, m, st()));
+      lat[0].ns_alloc = true;
+    } else ns_iters = 0;
     { const char* e = getenv("AGP_TAIL_VARIANT"); if (e) tail_variant = atoi(e); if (tail_variant != 0) tail_variant = 3; }
     CK(cudaStreamSynchronize(st()));
     return AGP_OK;
@@ -429,6 +440,7 @@ struct Engine : EngineBase {
                     L.muv, L.tvec, L.Xv, L.Dinv, L.Xv_T, L.Knm, L.V, L.VS, L.Ktilde, L.racc, L.Gpart, L.v1, L.P, L.X, L.W, L.logdetP};
       for (void* p : ps) cudaFree(p);
       umma_latent_free(L.um);
+      if (L.ns_alloc) umma_ns_free(L.ns);
       umma_knm_free(L.uk);
     }
     for (void* q : peer_opened) cudaIpcCloseMemHandle(q);
@@ -610,6 +622,7 @@ struct Engine : EngineBase {
     CK(cudaMemsetAsync(L.logdetP, 0, sizeof(double), st()));
     CKS(eta_to_moments(L));
     L.white_valid = true;
+    L.factor_valid = true; L.ns_seeded = false;   // new basis / new natural parameters: the refined covariance is stale
     return AGP_OK;
   }
 
@@ -667,6 +680,7 @@ struct Engine : EngineBase {
     CK(cudaStreamSynchronize(st()));
     CK(cudaMemcpy(c, counters, 16, cudaMemcpyDeviceToHost));
     c[0] = 1;
+    h_steps = 0;
     CK(cudaMemcpy(counters, c, 16, cudaMemcpyHostToDevice));
     CKS(upload_lr(1));
     curB = 0; have_step = false;
@@ -758,6 +772,12 @@ struct Engine : EngineBase {
           racc2_precleared = false;
           UmmaEpilogue ep{};
           ep.mode = UMMA_EPI_STATS_ONLY; ep.acc0 = L.racc + ldB; ep.acc1 = L.racc + 2 * ldB; ep.tvec = L.tvec;
+          if (!L.factor_valid) {
+            // the previous tail was a Newton-Schulz refinement: no factor, statistics against the full Sigma_v = ns.Y():
+            // var_f - Ktilde = rowsum((V Sigma_v) o V),  mean_f = (V Sigma_v) eta1_v
+            ep.mode = UMMA_EPI_STATS_SIGMA; ep.cin = (const float*)(const void*)L.V; ep.tvec = L.eta1v;
+            CKS(umma_gemm_sigma(ctx_err(), L.um, L.ns, UM_V, B, ep, st()));
+          } else
           CKS(umma_gemm_nt(ctx_err(), L.um, UM_V, UM_X, (float*)(void*)L.VS, B, m, ep, st()));
         } else {
           GemmParams<T> s{};  // V X^T with Sigma_v = X^T X  (kappa * Sigma of latentgp.jl:189); X is lower triangular
@@ -822,6 +842,7 @@ struct Engine : EngineBase {
   int hyper_grads(double rho, double* d_scale, double* d_variance, double* dZ) override {
     if (!d_scale || !d_variance) BAD("null output");
     if (curB < 1 || !have_step) { ctx->err = "hyper-parameter gradients need a completed step (the last minibatch is differentiated)"; return AGP_ERR_STATE; }
+    CKS(ensure_factors());
     const int B = curB;
     const int64_t ldh = rup(m, 4);
     // moments under the updated posterior (like ELBO(model, state, y)); sharded models exchange them here (collective call)
@@ -1125,7 +1146,11 @@ struct Engine : EngineBase {
       launch_chain(combine_kernel<T>, grid_mp(), dim3(128), 0, tp, (const T*)L.Gpart);
       ++launches;
       ph_end();
-      CKS(eta_to_moments(L, q == Ql - 1));   // the last latent's finalize kernel also prepares the next step size
+      if (ns_tail_now) CKS(eta_to_moments_ns(L));
+      else {
+        CKS(eta_to_moments(L, q == Ql - 1));   // the last latent's finalize kernel also prepares the next step size
+        L.factor_valid = true; L.ns_seeded = false;
+      }
     }
     // (the counters are bumped by the last latent's finalize kernel)
     CK(cudaGetLastError());
@@ -1190,9 +1215,81 @@ struct Engine : EngineBase {
     L.muv_valid = false;
     return AGP_OK;
   }
+  // ---- experimental Newton-Schulz tail (AGP_TAIL_NS=<iterations per step>, needs AGP_UMMA_V2) ----
+  int ns_iters = 0, ns_after = 8;
+  double ns_tol = 0.3;
+  int64_t h_steps = 0;          // steps taken since the posterior was last (re)initialised: the first ns_after steps keep the Cholesky tail
+  bool ns_tail_now = false;     // this step's tail is the refinement (decided by ns_begin_step, constant during a capture)
+  int ns_key = 0, g_nskey = -1, g_nskey_b = -1;   // bit 0: statistics against ns.Y(), bit 1: refinement tail -- part of the graph keys
+  bool ns_eligible() const {
+    return prec == AGP_PREC_TF32X3 && stochastic && model_kind == AGP_MODEL_SVGP && Ql == 1 && Qg == 1 && !is_vgp && !peer && !prof &&
+           !lat.empty() && lat[0].um.v2 != 0 && mp == m;
+  }
+  // entry of every whole step (step_full / step_batch), outside any capture
+  int ns_begin_step() {
+    ns_tail_now = false; ns_key = 0;
+    if (ns_iters <= 0 || !ns_eligible()) return AGP_OK;
+    Latent& L = lat[0];
+    if (h_steps >= ns_after) {
+      if (!L.ns_seeded) {        // Y0 = Sigma_v of the current natural parameters = X^T X
+        CKS(ensure_factor(L));
+        dgemm(true, true, L.Xv, L.Xv, L.X, 1.0, 0.0);
+        shadow_kernel<float><<<dim3((m + 127) / 128, m), 128, 0, st()>>>(L.X, mp, m, L.ns.Y(), (int64_t)L.ns.ldm);
+        ++launches;
+        L.ns_seeded = true;
+      }
+      ns_tail_now = true;
+    }
+    ns_key = (L.factor_valid ? 0 : 1) | (ns_tail_now ? 2 : 0);
+    return AGP_OK;
+  }
+  void ns_end_step() {
+    ++h_steps;
+    if (ns_iters <= 0) return;
+    Latent& L = lat[0];
+    if (ns_tail_now) { L.factor_valid = false; L.ns_seeded = true; }
+    else { L.factor_valid = true; L.ns_seeded = false; }
+    ns_tail_now = false;
+  }
+  // the refinement tail: P_v = -2 eta2_v (written by combine_kernel, left intact) -> ns.Y() ~ P_v^-1
+  int eta_to_moments_ns(Latent& L) {
+    ph_begin(PH_CHOL);
+    CKS(umma_ns_iterate(ctx_err(), L.ns, ns_iters, 3, L.P, (int64_t)mp, st()));
+    launches += 2 * ns_iters + 1;
+    ph_end();
+    ph_begin(PH_FINAL);
+    // accepted when |I - Y P|_F < ns_tol (0.3) at the START of the last iteration: |.|_2 <= |.|_F, so the map is still contracting
+    // and the last pass squares the error (typically |.|_2 ~ |.|_F / 20 at m = 512: final error < 1e-3); a diverging run shows >= 1
+    launch_chain(ns_finalize_kernel, dim3(1), dim3(32), 0, (const double*)L.ns.resid, ns_iters, ns_tol * ns_tol, status,
+                 (stochastic && !(fixed_lr > 0.0)) ? d_lr : (double*)nullptr, counters, rm_kappa, rm_tau, 1);
+    ++launches;
+    ph_end();
+    L.muv_valid = false; L.factor_valid = false; L.ns_seeded = true;
+    return AGP_OK;
+  }
+  // everything off the hot step that reads the factor X (getters, ELBO, hyper-gradients, prediction) goes through here
+  int ensure_factor(Latent& L) {
+    if (L.factor_valid) return AGP_OK;
+    CK(cudaMemsetAsync(L.logdetP, 0, sizeof(double), st()));
+    CKS(eta_to_moments(L));        // Cholesky tail on the intact P_v; no counter bump
+    L.factor_valid = true;
+    return AGP_OK;
+  }
+  int ensure_factors() {
+    for (auto& L : lat) CKS(ensure_factor(L));
+    return AGP_OK;
+  }
+
   // mu_v = X^T t (only getters / the ELBO need it)
   void ensure_muv(Latent& L) {
     if (L.muv_valid) return;
+    if (!L.factor_valid && L.ns_seeded) {      // mu_v = Sigma_v eta1_v with the refined covariance
+      cudaMemsetAsync(L.muv, 0, m * sizeof(double), st());
+      gemv_t_kernel<float><<<dim3((m + 31) / 32, (m + 63) / 64), dim3(32, 8), 0, st()>>>(L.ns.Y(), (int64_t)L.ns.ldm, L.eta1v, m, m, 64, L.muv);
+      ++launches;
+      L.muv_valid = true;
+      return;
+    }
     cudaMemsetAsync(L.muv, 0, m * sizeof(double), st());
     gemv_t_kernel<double><<<dim3((m + 31) / 32, (m + 63) / 64), dim3(32, 8), 0, st()>>>(L.Xv, mp, L.tvec, m, m, 64, L.muv);
     ++launches;
@@ -1263,6 +1360,13 @@ struct Engine : EngineBase {
   }
 
   int step_full(const int64_t* idx, int B, int base, double rho) override {
+    CKS(ns_begin_step());
+    int rc = step_full_impl(idx, B, base, rho);
+    if (rc == AGP_OK) ns_end_step();
+    else ns_tail_now = false;
+    return rc;
+  }
+  int step_full_impl(const int64_t* idx, int B, int base, double rho) {
     if (idx) {
       fuse_in_step_moments = true;
       int s1 = step_moments(idx, B, base, false);
@@ -1272,7 +1376,7 @@ struct Engine : EngineBase {
     }
     if (want_graph && !prof && !capturing) {
       const bool need_prime = pipeline && (!prefetched || curB != B || (prec == AGP_PREC_TF32X3 && Ql == 1 && !racc2_precleared));
-      if (!gexec || gB != B || grho != rho || need_prime) {
+      if (!gexec || gB != B || grho != rho || g_nskey != ns_key || need_prime) {
         drop_graph();
         if (need_prime) return step_pool(B, rho);  // priming step (brings the pipeline to its steady state); later calls replay the graph
       }
@@ -1290,7 +1394,7 @@ struct Engine : EngineBase {
         launches = l0;
         CK(cudaGraphInstantiate(&gexec, graph, 0));
         cudaGraphDestroy(graph);
-        gB = B; grho = rho;
+        gB = B; grho = rho; g_nskey = ns_key;
       }
       CK(cudaGraphLaunch(gexec, ctx->stream));
       launches += g_launches;
@@ -1326,6 +1430,13 @@ struct Engine : EngineBase {
     return AGP_OK;
   }
   int step_batch(const void* xbh, int x_dtype, int x_layout, const void* const* ybh, int y_kind, int B, double rho) override {
+    CKS(ns_begin_step());
+    int rc = step_batch_impl(xbh, x_dtype, x_layout, ybh, y_kind, B, rho);
+    if (rc == AGP_OK) ns_end_step();
+    else ns_tail_now = false;
+    return rc;
+  }
+  int step_batch_impl(const void* xbh, int x_dtype, int x_layout, const void* const* ybh, int y_kind, int B, double rho) {
     if (!xbh || !ybh) BAD("null batch");
     if (B < 1 || B > Bcap) BAD("The size of mini-batch is incorrect (negative or bigger than the batch capacity)");
     if (is_lsm != (y_kind == AGP_Y_CLASS)) BAD("label kind does not match the likelihood");
@@ -1341,7 +1452,7 @@ struct Engine : EngineBase {
     else for (int t = 0; t < nT; ++t) CK(cudaMemcpyAsync(yb + (size_t)t * ldB, ybh[t], B * sizeof(double), cudaMemcpyHostToDevice, st()));
     const int key = x_dtype * 2 + x_layout;
     if (want_graph && !prof && !capturing) {
-      if (gexec_b && (gB_b != B || grho_b != rho || gkey_b != key)) { cudaGraphExecDestroy(gexec_b); gexec_b = nullptr; }
+      if (gexec_b && (gB_b != B || grho_b != rho || gkey_b != key || g_nskey_b != ns_key)) { cudaGraphExecDestroy(gexec_b); gexec_b = nullptr; }
       if (!gexec_b) {
         cudaGraph_t graph = nullptr;
         int64_t l0 = launches;
@@ -1356,7 +1467,7 @@ struct Engine : EngineBase {
         launches = l0;
         CK(cudaGraphInstantiate(&gexec_b, graph, 0));
         cudaGraphDestroy(graph);
-        gB_b = B; grho_b = rho; gkey_b = key;
+        gB_b = B; grho_b = rho; gkey_b = key; g_nskey_b = ns_key;
       }
       CK(cudaGraphLaunch(gexec_b, ctx->stream));
       launches += g_launches_b;
@@ -1380,6 +1491,7 @@ struct Engine : EngineBase {
     if (s) {
       CK(cudaMemset(status, 0, sizeof(int)));
       if (s & ST_PEER_TIMEOUT) { ctx->err = "peer exchange timed out (a rank of the latent-sharded group did not publish its moments)"; return AGP_ERR_STATE; }
+      if (s & ST_NS_NOCONV) { ctx->err = "experimental Newton-Schulz tail (AGP_TAIL_NS) did not converge: raise AGP_TAIL_NS_AFTER or the iteration count"; return AGP_ERR_STATE; }
       if (s & ST_NOT_POSDEF) { ctx->err = "PosDefException: matrix is not positive definite; Cholesky factorization failed."; return AGP_ERR_NOT_POSDEF; }
       ctx->err = "K̃ has negative values";
       return AGP_ERR_KTILDE_NONPOS;
@@ -1395,6 +1507,7 @@ struct Engine : EngineBase {
   // moments of the last minibatch under the UPDATED posterior (ELBO uses the post-update mu, Sigma)
   int elbo_moments() override {
     if (curB < 1) { ctx->err = "no minibatch to evaluate the ELBO on"; return AGP_ERR_STATE; }
+    CKS(ensure_factors());
     const bool was_stale = kernel_matrices_stale;  // a prefetch / predict_f overwrote Knm / V: rebuild them first
     CKS(ensure_current_kernel_matrices());
     return moments_impl(cur_from_batch, curB, was_stale, 2);
@@ -1403,6 +1516,7 @@ struct Engine : EngineBase {
   int elbo(double rho, double* out3) override {
     if (!out3) BAD("null output");
     if (curB < 1) { ctx->err = "no minibatch to evaluate the ELBO on"; return AGP_ERR_STATE; }
+    CKS(ensure_factors());
     if (Ql == Qg) CKS(elbo_moments());
     const int B = curB;
     CK(cudaMemsetAsync(d_out, 0, 8 * sizeof(double), st()));
@@ -1447,6 +1561,7 @@ struct Engine : EngineBase {
     if (!L.white_valid) {  // nothing has run yet: the canonical parameters are the truth (Sigma = inv(-2 eta2) needs K only formally)
       if (!have_K) CKS(refresh_K());
     }
+    if (Sigma || eta1 || eta2) CKS(ensure_factor(L));   // (the mean alone is served from the refined covariance, see ensure_muv)
     // canonical from whitened, fp64:  mu = L mu_v,  Sigma = L Sigma_v L^T,  eta1 = L^-T eta1_v,  eta2 = L^-T eta2_v L^-1
     if (eta1 || eta2) canonicalize(L);
     if (mu) { ensure_muv(L); symv_kernel<<<(m * 32 + 255) / 256, 256, 0, st()>>>(L.Lc, mp, m, L.muv, L.mu0 + mp); ++launches; }  // scratch behind mu0
@@ -1463,7 +1578,7 @@ struct Engine : EngineBase {
     return AGP_OK;
   }
   int set_posterior(int ql, const double* eta1, const double* eta2) override {
-    h_mu_valid = false;
+    h_mu_valid = false; h_steps = 0;
     if (ql < 0 || ql >= Ql || !eta1 || !eta2) BAD("bad posterior arguments");
     Latent& L = lat[ql];
     CK(cudaStreamSynchronize(st()));
@@ -1487,6 +1602,7 @@ struct Engine : EngineBase {
     if (t < 1 || cur < 0) BAD("bad counters");
     int64_t c[2] = {t, cur};
     prefetched = false; drop_graph();
+    h_steps = t - 1;
     CK(cudaStreamSynchronize(st()));
     CK(cudaMemcpy(counters, c, 16, cudaMemcpyHostToDevice));
     CKS(upload_lr(t));
@@ -1622,6 +1738,7 @@ struct Engine : EngineBase {
     if (prec != AGP_PREC_TF32X3) { ctx->err = "time_kernel measures the tcgen05 kernels (precision tf32x3)"; return AGP_ERR_STATE; }
     const int B = curB;
     Latent& L = lat[0];
+    CKS(ensure_factors());
     CKS(sync_status());
     int64_t c[2];
     CK(cudaMemcpy(c, counters, 16, cudaMemcpyDeviceToHost));
@@ -1684,6 +1801,7 @@ template <typename T>
 int Engine<T>::predict_f(const void* Xt, int x_dtype, int x_layout, int64_t nt, int want_var, double* mu_out, double* var_out) {
   if (!Xt || !mu_out || nt < 1 || (want_var && !var_out)) BAD("bad predict arguments");
   if (!have_K) CKS(refresh_K());  // predictions.jl:28-29: compute_K when no state is passed
+  CKS(ensure_factors());
   CKS(sync_status());             // surface errors of earlier asynchronous steps before the flag is reused
   double *dmu = nullptr, *dvar = nullptr;
   CK(cudaMalloc(&dmu, (size_t)Ql * ldB * 8)); CK(cudaMalloc(&dvar, (size_t)Ql * ldB * 8));

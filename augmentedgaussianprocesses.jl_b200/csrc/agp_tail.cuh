@@ -333,6 +333,18 @@ __global__ void x_finalize_kernel(const double* __restrict__ X, int64_t ld, int 
   }
 }
 
+// End of a step whose tail was the experimental Newton-Schulz refinement (no factor X, so no x_finalize_kernel): the step-size /
+// counter duties of x_finalize_kernel, plus the convergence check: resid2[i] = |I - Y P|_F^2 at the START of iteration i, the
+// error squares per iteration, so the result is accepted when the last recorded residual is below sqrt-tolerance.
+__global__ void ns_finalize_kernel(const double* __restrict__ resid2, int iters, double thr2, int* __restrict__ status,
+                                   double* __restrict__ lr_next, int64_t* __restrict__ counters, double rm_kappa, double rm_tau, int bump) {
+  pdl_prologue();
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  if (lr_next) *lr_next = pow(rm_tau + (double)(counters[0] + 1), -rm_kappa);
+  if (bump) { counters[0] += 1; counters[1] += 1; }
+  if (iters > 0 && !(resid2[iters - 1] < thr2)) atomicOr(status, ST_NS_NOCONV);
+}
+
 // out[0] += |X|_F^2 (= tr(Sigma_v)),  out[1] += |mu_v - mu0_v|^2 ; one warp per row of X, 8 rows per block
 __global__ void gauss_kl_x_kernel(const double* __restrict__ X, int64_t ld, int m, const double* __restrict__ muv,
                                   const double* __restrict__ mu0v, double* __restrict__ out) {

@@ -311,7 +311,7 @@ constexpr int RA = 4, RB = 4, TS = 4;             // raw-A stages, B stages, TME
 constexpr int A_BYTES = TILE_BYTES, B_BYTES = 2 * TILE_BYTES;
 constexpr int RING_BYTES = RA * A_BYTES + RB * B_BYTES;   // 192 KB
 constexpr int NCG = 2;                            // converter groups; must divide RA and TS
-constexpr int EPI_WARP0 = 2, CONV_WARP0 = 6;
+constexpr int CONV_WARP0 = 6;                     // warps 2 .. CONV_WARP0-1: epilogue group
 constexpr int NUM_THREADS = 64 + 128 + NCG * 128; // 448
 constexpr int SMEM_BYTES = RING_BYTES + 1024 + 256;
 static_assert(RB == TS && RA % NCG == 0 && TS % NCG == 0, "ring / group shape");
@@ -922,6 +922,22 @@ void umma_ns_free(UmmaNs& ns) {
   cudaFree(ns.resid); ns.resid = nullptr;
   cudaFree(ns.P64); ns.P64 = nullptr;
   delete (NsMaps*)ns.maps; ns.maps = nullptr;
+}
+
+int umma_gemm_sigma(std::string* err, UmmaLatent& u, UmmaNs& ns, int a_which, int M, const UmmaEpilogue& ep, cudaStream_t st) {
+  Maps* mp = (Maps*)u.tmaps;
+  NsMaps* nm = (NsMaps*)ns.maps;
+  if (!mp || !nm || !u.v2) return fail(err, "umma_gemm_sigma needs the v2 kernel (AGP_UMMA_V2) and an allocated Newton-Schulz state");
+  if (M % BM || ns.m != u.m || ns.ldm != u.ldm) return fail(err, "umma_gemm_sigma: shape mismatch");
+  GemmWork w{};
+  w.ntm = M / BM; w.ntn = u.m / BN; w.nsplit = 1; w.total = w.ntm * w.ntn;
+  w.total_kb = u.m / BK; w.kb_per_split = w.total_kb; w.tri_mode = 0;
+  const int grid = w.total < sm_count() ? w.total : sm_count();
+  launch_chain(umma_gemm_nt_v2_kernel, dim3(grid), dim3(v2::NUM_THREADS), v2::SMEM_BYTES, st, mp->raw[a_which], nm->Y, nm->Y, (float*)nullptr,
+               (int64_t)u.ldm, (int64_t)0, w, ep, 0);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(err, "umma_gemm_sigma", e);
+  return 0;
 }
 
 int umma_ns_iterate(std::string* err, UmmaNs& ns, int iters, int mode, const double* P64, int64_t ldp, cudaStream_t st) {

@@ -74,6 +74,8 @@ struct UmmaNs {
   float* T() const { return buf + (size_t)4 * m * ldm; }
 };
 int umma_ns_alloc(std::string* err, UmmaNs& ns, int m, cudaStream_t st);
+// statistics of A (a_which, [M][m]) against the full symmetric ns.Y() on the v2 kernel: ep.mode = UMMA_EPI_STATS_SIGMA, ep.cin = A's matrix
+int umma_gemm_sigma(std::string* err, UmmaLatent& u, UmmaNs& ns, int a_which, int M, const UmmaEpilogue& ep, cudaStream_t st);
 void umma_ns_free(UmmaNs& ns);
 // `iters` refinements of ns.Y() in place.  mode bit 0: residual T = I - Y P in fp64 on DMMA (ns_resid_f64_kernel, reads P64 with
 // leading dimension ldp; P64 == nullptr -> ns.P64, ldp = m) instead of 3xTF32 (reads ns.P()); bit 1: symmetrise the result

@@ -55,3 +55,32 @@ def test_newton_schulz_refine_matches_fp64_inverse(agp, m, cond, mode, tol):
     print(f"m={m} cond={cond:g} mode={mode}: residuals {resid}, rel err {err:.2e}, {ms.value * 1e3:.1f} us for 3 iterations")
     assert resid[0] > resid[1]
     assert err < tol
+
+
+@pytest.mark.parametrize("lik", ["logistic", "studentt"])
+def test_newton_schulz_tail_parity(agp, lik, monkeypatch):
+    """AnalyticSVI with the experimental tail (AGP_UMMA_V2=1, AGP_TAIL_NS=4: Cholesky for the first 8 steps, then four
+    Newton-Schulz refinements of the previous Sigma_v per step, statistics against the full covariance) against the fp64
+    oracle, same tolerance as the product tf32x3 path.  The environment is read when the engine is created."""
+    from problems import make_data, oracle_lik, engine_lik, oracle_kernel, engine_kernel, rel_fro
+    import agp_oracle as O
+
+    monkeypatch.setenv("AGP_UMMA_V2", "1")
+    # B = 1024 is noisy: the spectral radius of I - P_new Sigma_old is still 0.3 (logistic) / 0.5 (studentt) after step 8
+    # (CPU check with the oracle), so 4 refinements per step and a loose Frobenius acceptance threshold
+    monkeypatch.setenv("AGP_TAIL_NS", "4")
+    monkeypatch.setenv("AGP_TAIL_NS_TOL", "1.0")
+    n, D, m, B, iters = 8192, 8, 256, 1024, 24
+    scale = 1.0 / np.sqrt(D)
+    X, y, Z, mbs, F, rng = make_data(lik, n, D, m, B, iters, seed=0)
+    mo = O.SVGP(oracle_kernel(O, "sqexp", scale, 1.0), oracle_lik(O, lik), O.AnalyticSVI(B), Z)
+    mo, so = O.train(mo, X, y, iters, minibatches=mbs)
+    me = agp.SVGP(engine_kernel(agp, "sqexp", scale, 1.0), engine_lik(agp, lik), agp.AnalyticSVI(B), Z, precision="tf32x3")
+    me, se = agp.train(me, X, y, iters, minibatches=mbs)
+    mu, S, e1, e2 = me.posterior(0)
+    gp = mo.f[0]
+    print(lik, "mu", rel_fro(mu, gp.mu), "Sigma", rel_fro(S, gp.Sigma))
+    assert rel_fro(mu, gp.mu) < 5e-4
+    assert rel_fro(S, gp.Sigma) < 5e-4
+    elbo_o, elbo_e = mo.ELBO(so, so["y_batch"]), agp.ELBO(me, se)
+    assert abs(elbo_e - elbo_o) <= 5e-4 * max(1.0, abs(elbo_o)) * 5, (elbo_e, elbo_o)

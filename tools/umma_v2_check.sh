@@ -29,3 +29,6 @@ PY
 # Newton-Schulz refinement on the v2 kernel (experimental C-ABI hook), parity against the fp64 inverse + device time
 AGP_EXPERIMENTAL=1 timeout 240 python -m pytest tests/test_experimental_gpu.py -m gpu -x -q -s > $OUT/pytest_ns.log 2>&1; echo "ns pytest rc=$?" | tee -a $OUT/pytest_ns.log
 grep -E "rel err|passed|failed|rror" $OUT/pytest_ns.log | head -20
+# whole C2 bench with the experimental Newton-Schulz tail (Cholesky for the first 8 steps, then 3 refinements per step)
+AGP_UMMA_V2=1 AGP_TAIL_NS=3 timeout 300 python bench.py --steps 100 --warmup 10 > $OUT/bench_ns3.json 2> $OUT/bench_ns3.err; echo "bench ns3 rc=$?"
+tail -c 600 $OUT/bench_ns3.err
