@@ -1228,9 +1228,9 @@ struct Engine : EngineBase {
   // entry of every whole step (step_full / step_batch), outside any capture
   int ns_begin_step() {
     ns_tail_now = false; ns_key = 0;
-    if (ns_iters <= 0 || !ns_eligible()) return AGP_OK;
+    if (ns_iters <= 0) return AGP_OK;
     Latent& L = lat[0];
-    if (h_steps >= ns_after) {
+    if (ns_eligible() && h_steps >= ns_after) {
       if (!L.ns_seeded) {        // Y0 = Sigma_v of the current natural parameters = X^T X
         CKS(ensure_factor(L));
         dgemm(true, true, L.Xv, L.Xv, L.X, 1.0, 0.0);
