@@ -832,24 +832,28 @@ struct NsMaps { CUtensorMap P, Y, W[2], T; };
 // T = I - Y P with the product in fp64 on DMMA (mma.sync.m8n8k4.f64): Y fp32 [m][ldy], P fp64 [m][ldp] symmetric, T fp32 [m][ldt];
 // *resid2 += |T|_F^2.  The residual is where the accuracy of the refinement is decided (an fp32 / 3xTF32 residual floors at
 // eps_fp32 * cond(P), profiles/r1/studies/newton_schulz_precision_study.txt), the correction product may be low precision.
-// One CTA (8 warps) per 64 x 64 tile of T, 32-deep k-steps staged in shared memory (leading dimension 36 = 4 mod 16: conflict-free
+// One CTA (8 warps) per 64 x 32 tile of T, 32-deep k-steps staged in shared memory (leading dimension 36 = 4 mod 16: conflict-free
 // 8x4 fragment loads, as in agp_tail2.cuh); warp w owns rows 8w..8w+7 of the tile.
-constexpr int NSLD = 36, NSK = 32;
+constexpr int NSLD = 36, NSK = 32, NSTN = 32;   // 64 x 32 tiles of T: 128 CTAs at m = 512 (a 64 x 64 tiling would leave 84 SMs idle)
 __global__ void __launch_bounds__(256) ns_resid_f64_kernel(const float* __restrict__ Y, int64_t ldy, const double* __restrict__ P, int64_t ldp,
                                                            float* __restrict__ T, int64_t ldt, int m, double* __restrict__ resid2) {
-  __shared__ __align__(16) double sA[64 * NSLD], sB[64 * NSLD];
-  const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+  __shared__ __align__(16) double sA[64 * NSLD], sB[NSTN * NSLD];
+  const int i0 = blockIdx.y * 64, j0 = blockIdx.x * NSTN;
   const int t = threadIdx.x, lane = t & 31, w = t >> 5, r = lane >> 2, kk = lane & 3;
-  double acc[8][2];
+  double acc[NSTN / 8][2];
 #pragma unroll
-  for (int nb = 0; nb < 8; ++nb) { acc[nb][0] = 0.0; acc[nb][1] = 0.0; }
+  for (int nb = 0; nb < NSTN / 8; ++nb) { acc[nb][0] = 0.0; acc[nb][1] = 0.0; }
   for (int k0 = 0; k0 < m; k0 += NSK) {
     __syncthreads();
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {                 // 64 x 32 elements as 1024 pairs
+    for (int u = 0; u < 4; ++u) {                 // Y tile: 64 x 32 elements as 1024 pairs
       const int e = t + u * 256, row = e >> 4, c2 = (e & 15) * 2;
       const float2 y = *reinterpret_cast<const float2*>(Y + (int64_t)(i0 + row) * ldy + k0 + c2);
       *reinterpret_cast<double2*>(sA + row * NSLD + c2) = make_double2((double)y.x, (double)y.y);
+    }
+#pragma unroll
+    for (int u = 0; u < NSTN / 16; ++u) {         // P tile: NSTN x 32 elements
+      const int e = t + u * 256, row = e >> 4, c2 = (e & 15) * 2;
       *reinterpret_cast<double2*>(sB + row * NSLD + c2) = *reinterpret_cast<const double2*>(P + (int64_t)(j0 + row) * ldp + k0 + c2);
     }
     __syncthreads();
@@ -857,7 +861,7 @@ __global__ void __launch_bounds__(256) ns_resid_f64_kernel(const float* __restri
     for (int k = 0; k < NSK; k += 4) {
       const double a = sA[(8 * w + r) * NSLD + k + kk];
 #pragma unroll
-      for (int nb = 0; nb < 8; ++nb) {
+      for (int nb = 0; nb < NSTN / 8; ++nb) {
         const double b = sB[(8 * nb + r) * NSLD + k + kk];   // P[j][k] = P[k][j]
         asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                      : "+d"(acc[nb][0]), "+d"(acc[nb][1]) : "d"(a), "d"(b));
@@ -867,7 +871,7 @@ __global__ void __launch_bounds__(256) ns_resid_f64_kernel(const float* __restri
   double sq = 0.0;
   const int row = i0 + 8 * w + r;
 #pragma unroll
-  for (int nb = 0; nb < 8; ++nb) {
+  for (int nb = 0; nb < NSTN / 8; ++nb) {
     const int col = j0 + 8 * nb + 2 * kk;
     const double v0 = (row == col ? 1.0 : 0.0) - acc[nb][0], v1 = (row == col + 1 ? 1.0 : 0.0) - acc[nb][1];
     sq = fma(v0, v0, fma(v1, v1, sq));
@@ -956,7 +960,7 @@ int umma_ns_iterate(std::string* err, UmmaNs& ns, int iters, int mode, const dou
     float* dst = ns.W(it & 1);
     // T = I - Y P   (= (I - P Y)^T for symmetric P, Y: exactly the [n][k] operand the second product needs)
     if (mode & 1) {
-      ns_resid_f64_kernel<<<dim3(ns.m / 64, ns.m / 64), 256, 0, st>>>(src, (int64_t)ns.ldm, P64, ldp, ns.T(), (int64_t)ns.ldm, ns.m, ns.resid + it);
+      ns_resid_f64_kernel<<<dim3(ns.m / NSTN, ns.m / 64), 256, 0, st>>>(src, (int64_t)ns.ldm, P64, ldp, ns.T(), (int64_t)ns.ldm, ns.m, ns.resid + it);
     } else {
       UmmaEpilogue e1{};
       e1.mode = UMMA_EPI_EYE_MINUS; e1.acc0 = ns.resid + it;
