@@ -350,7 +350,9 @@ def run_ours(args, rank, world, local_rank):
                                           f"C2-shaped multi-output SVGP: {world} Logistic tasks x {world} latent GPs, one latent per GPU, "
                                           + ("per-sample moments exchanged over NVLink peer memory inside the step" if peer else "moments NCCL all-gather per step")),
                                 l2=f"inputs larger than L2: every step gathers a new random minibatch from the resident {int(n * (4 * D + 12) / 1e6)} MB (X, |x|^2, y) arrays; no flush",
-                                graph=bool(args.graph and (world == 1 or peer)), precision=args.precision, **cfg),
+                                graph=bool(args.graph and (world == 1 or peer)), precision=args.precision,
+                                **({"experimental_env": {k: os.environ[k] for k in ("AGP_UMMA_V2", "AGP_TAIL_NS", "AGP_TAIL_NS_AFTER", "AGP_TAIL_NS_TOL") if k in os.environ}}
+                                   if any(k in os.environ for k in ("AGP_UMMA_V2", "AGP_TAIL_NS")) else {}), **cfg),
                     gpu_launches=int(launches), elbo_last=elbo, roofline=roof, cpu_baseline=cpu, e2e=e2e, clocks=clocks, phases=phases)
         print(json.dumps(line), flush=True)
     if dist is not None:
