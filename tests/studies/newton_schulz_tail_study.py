@@ -5,7 +5,7 @@ Converges iff the spectral radius of E0 = I - P_new Sigma_old is < 1; the error 
 For every SVI iteration of a C2-shaped run this prints rho(E0), the Robbins-Monro step, and the iterations needed
 for |I - P Y|_F / sqrt(m) < 1e-9 with the residual in fp64 and the correction product Y E in fp32.
 
-    python tests/studies/newton_schulz_tail_study.py [iters]
+    python tests/studies/newton_schulz_tail_study.py [iters] [C2|C3]
 """
 import os
 import sys
@@ -20,10 +20,18 @@ import agp_oracle as O  # noqa: E402
 from bench import make_problem  # noqa: E402
 
 iters = int(sys.argv[1]) if len(sys.argv) > 1 else 40
-n, D, m, B = 200_000, 32, 512, 8192
-X, ys, Z, mbs, _ = make_problem(n, D, m, B, iters, seed=1)
+cfg = sys.argv[2] if len(sys.argv) > 2 else "C2"
+if cfg == "C3":      # StudentT(3), Matern-3/2, D = 64, m = 1024, B = 16384 (BASELINE configs[2]); labels: f(X) + t_3 noise
+    n, D, m, B = 200_000, 64, 1024, 16384
+    X, ys, Z, mbs, rng = make_problem(n, D, m, B, iters, seed=1)
+    y = X @ rng.standard_normal(D) / np.sqrt(D) + 0.3 * rng.standard_t(3, n)
+    model = O.SVGP(O.Kernel("matern32", scale=1.0 / np.sqrt(D)), O.StudentTLikelihood(3.0), O.AnalyticSVI(B), Z)
+    ys = [y]
+else:
+    n, D, m, B = 200_000, 32, 512, 8192
+    X, ys, Z, mbs, _ = make_problem(n, D, m, B, iters, seed=1)
+    model = O.SVGP(O.Kernel("sqexp", scale=1.0 / np.sqrt(D)), O.LogisticLikelihood(), O.AnalyticSVI(B), Z)
 X64 = X.astype(np.float64)
-model = O.SVGP(O.Kernel("sqexp", scale=1.0 / np.sqrt(D)), O.LogisticLikelihood(), O.AnalyticSVI(B), Z)
 
 rows = []
 orig = O.global_update
