@@ -70,6 +70,9 @@ SIGNATURES = {
     "agp_step": (C.c_int, [C.c_void_p, c_int64_p, C.c_int32, C.c_int32, C.c_double]),
     "agp_step_async": (C.c_int, [C.c_void_p, c_int64_p, C.c_int32, C.c_int32, C.c_double]),
     "agp_step_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int32, C.c_double]),
+    "agp_step_batch_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int32, C.c_double,
+                                       c_int64_p]),
+    "agp_result_wait": (C.c_int, [C.c_void_p, C.c_int64, c_double_p]),
     "agp_sync": (C.c_int, [C.c_void_p]),
     "agp_step_moments_async": (C.c_int, [C.c_void_p, c_int64_p, C.c_int32, C.c_int32]),
     "agp_step_update_async": (C.c_int, [C.c_void_p, C.c_double]),

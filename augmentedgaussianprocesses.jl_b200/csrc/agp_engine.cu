@@ -68,6 +68,8 @@ struct EngineBase {
   virtual int step_update(double rho) = 0;
   virtual int step_full(const int64_t* idx, int B, int base, double rho) = 0;
   virtual int step_batch(const void* xb, int x_dtype, int x_layout, const void* const* yb, int y_kind, int B, double rho) = 0;
+  virtual int step_batch_async(const void* xb, int x_dtype, int x_layout, const void* const* yb, int y_kind, int B, double rho, int64_t* ticket) = 0;
+  virtual int result_wait(int64_t ticket, double* mu) = 0;
   virtual int sync_status() = 0;
   virtual void* moments_ptr(int which, int64_t* ld) = 0;
   virtual int elbo_moments() = 0;
@@ -445,6 +447,17 @@ struct Engine : EngineBase {
     }
     for (void* q : peer_opened) cudaIpcCloseMemHandle(q);
     if (side) cudaStreamDestroy(side);
+    if (copy_stream) {
+      cudaStreamDestroy(copy_stream);
+      if (h_stat) cudaFreeHost(h_stat);
+      for (int s = 0; s < 2; ++s) {
+        cudaFree(pre_x[s]); cudaFree(pre_y[s]); cudaFree(pre_ycls[s]);
+        if (h_res[s]) cudaFreeHost(h_res[s]);
+        if (ev_h2d[s]) cudaEventDestroy(ev_h2d[s]);
+        if (ev_free[s]) cudaEventDestroy(ev_free[s]);
+        if (ev_done[s]) cudaEventDestroy(ev_done[s]);
+      }
+    }
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
     void* ps[] = {idx_prev, xx_cur, pKS, pXb, pxxb, X, xx, y_all, ycls_all, Xb, xxb, stage, idx_pool, idx_cur, counters, status, d_lik_kind, d_p0, d_p1, d_A,
@@ -1436,7 +1449,9 @@ struct Engine : EngineBase {
     else ns_tail_now = false;
     return rc;
   }
-  int step_batch_impl(const void* xbh, int x_dtype, int x_layout, const void* const* ybh, int y_kind, int B, double rho) {
+  // kind = cudaMemcpyDeviceToDevice: the batch already sits in the device pre-staging buffers of step_batch_async
+  int step_batch_impl(const void* xbh, int x_dtype, int x_layout, const void* const* ybh, int y_kind, int B, double rho,
+                      cudaMemcpyKind kind = cudaMemcpyHostToDevice) {
     if (!xbh || !ybh) BAD("null batch");
     if (B < 1 || B > Bcap) BAD("The size of mini-batch is incorrect (negative or bigger than the batch capacity)");
     if (is_lsm != (y_kind == AGP_Y_CLASS)) BAD("label kind does not match the likelihood");
@@ -1447,9 +1462,9 @@ struct Engine : EngineBase {
     if (!h_mu) CK(cudaMallocHost((void**)&h_mu, (size_t)mp * sizeof(double)));
     h_mu_valid = false;
     CKS(ensure_stage((size_t)Bcap * D * 8));     // fixed staging address: the captured graph stays valid
-    CK(cudaMemcpyAsync(stage, xbh, (size_t)B * D * es, cudaMemcpyHostToDevice, st()));
-    if (y_kind == AGP_Y_CLASS) CK(cudaMemcpyAsync(ycls, ybh[0], B * sizeof(int), cudaMemcpyHostToDevice, st()));
-    else for (int t = 0; t < nT; ++t) CK(cudaMemcpyAsync(yb + (size_t)t * ldB, ybh[t], B * sizeof(double), cudaMemcpyHostToDevice, st()));
+    CK(cudaMemcpyAsync(stage, xbh, (size_t)B * D * es, kind, st()));
+    if (y_kind == AGP_Y_CLASS) CK(cudaMemcpyAsync(ycls, ybh[0], B * sizeof(int), kind, st()));
+    else for (int t = 0; t < nT; ++t) CK(cudaMemcpyAsync(yb + (size_t)t * ldB, ybh[t], B * sizeof(double), kind, st()));
     const int key = x_dtype * 2 + x_layout;
     if (want_graph && !prof && !capturing) {
       if (gexec_b && (gB_b != B || grho_b != rho || gkey_b != key || g_nskey_b != ns_key)) { cudaGraphExecDestroy(gexec_b); gexec_b = nullptr; }
@@ -1479,6 +1494,83 @@ struct Engine : EngineBase {
     }
     CKS(batch_compute(x_dtype, x_layout, B, rho));
     h_mu_valid = true;
+    return AGP_OK;
+  }
+
+  // ---- host-batch steps without a per-step synchronisation (untested on a GPU yet) ----
+  // Two slots: the host->device copy of batch i+1 runs on a copy stream while step i computes; each step leaves its result
+  // (canonical mean of latent 0 + the sticky status word) in a pinned slot that agp_result_wait(ticket) reads later.
+  void* pre_x[2] = {nullptr, nullptr}; double* pre_y[2] = {nullptr, nullptr}; int* pre_ycls[2] = {nullptr, nullptr};
+  double* h_res[2] = {nullptr, nullptr}; int* h_stat = nullptr;
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  cudaStream_t copy_stream = nullptr;
+  int64_t n_tickets = 0;
+  int async_init() {
+    if (copy_stream) return AGP_OK;
+    CK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    CK(cudaMallocHost((void**)&h_stat, 2 * sizeof(int)));
+    h_stat[0] = h_stat[1] = 0;
+    for (int s = 0; s < 2; ++s) {
+      CK(cudaMalloc(&pre_x[s], (size_t)Bcap * D * 8));
+      CK(cudaMalloc((void**)&pre_y[s], (size_t)nT * ldB * sizeof(double)));
+      CK(cudaMalloc((void**)&pre_ycls[s], (size_t)ldB * sizeof(int)));
+      CK(cudaMallocHost((void**)&h_res[s], (size_t)mp * sizeof(double)));
+      CK(cudaEventCreateWithFlags(&ev_h2d[s], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&ev_free[s], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&ev_done[s], cudaEventDisableTiming));
+    }
+    return AGP_OK;
+  }
+  int step_batch_async(const void* xbh, int x_dtype, int x_layout, const void* const* ybh, int y_kind, int B, double rho, int64_t* ticket) override {
+    if (!xbh || !ybh || !ticket) BAD("null batch / ticket");
+    if (B < 1 || B > Bcap) BAD("The size of mini-batch is incorrect (negative or bigger than the batch capacity)");
+    if (is_lsm != (y_kind == AGP_Y_CLASS)) BAD("label kind does not match the likelihood");
+    if ((x_dtype != 0 && x_dtype != 1) || (x_layout != 0 && x_layout != 1)) BAD("bad dtype/layout");
+    CKS(async_init());
+    const int slot = (int)(n_tickets & 1);
+    const size_t es = x_dtype == AGP_DTYPE_F64 ? 8 : 4;
+    // copy stream: this slot's previous batch has been consumed (its step finished), then host -> pre-staging
+    CK(cudaStreamWaitEvent(copy_stream, ev_free[slot], 0));
+    CK(cudaMemcpyAsync(pre_x[slot], xbh, (size_t)B * D * es, cudaMemcpyHostToDevice, copy_stream));
+    std::vector<const void*> yp((size_t)std::max(nT, 1));
+    if (y_kind == AGP_Y_CLASS) {
+      CK(cudaMemcpyAsync(pre_ycls[slot], ybh[0], B * sizeof(int), cudaMemcpyHostToDevice, copy_stream));
+      yp[0] = pre_ycls[slot];
+    } else {
+      for (int t = 0; t < nT; ++t) {
+        CK(cudaMemcpyAsync(pre_y[slot] + (size_t)t * ldB, ybh[t], B * sizeof(double), cudaMemcpyHostToDevice, copy_stream));
+        yp[t] = pre_y[slot] + (size_t)t * ldB;
+      }
+    }
+    CK(cudaEventRecord(ev_h2d[slot], copy_stream));
+    // main stream: device -> staging copies + the step, in order behind the previous step
+    CK(cudaStreamWaitEvent(ctx->stream, ev_h2d[slot], 0));
+    CKS(ns_begin_step());
+    int rc = step_batch_impl(pre_x[slot], x_dtype, x_layout, yp.data(), y_kind, B, rho, cudaMemcpyDeviceToDevice);
+    if (rc != AGP_OK) { ns_tail_now = false; return rc; }
+    ns_end_step();
+    CK(cudaEventRecord(ev_free[slot], ctx->stream));
+    // result slot: batch_compute left the canonical mean of latent 0 behind mu0 (also copied to h_mu by the step itself)
+    CK(cudaMemcpyAsync(h_res[slot], lat[0].mu0 + mp, m * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h_stat + slot, status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaEventRecord(ev_done[slot], ctx->stream));
+    *ticket = n_tickets++;
+    return AGP_OK;
+  }
+  int result_wait(int64_t ticket, double* mu) override {
+    if (!mu || ticket < 0 || ticket >= n_tickets) BAD("unknown ticket");
+    if (ticket < n_tickets - 2) BAD("ticket expired: only the results of the last two asynchronous steps are kept");
+    const int slot = (int)(ticket & 1);
+    CK(cudaEventSynchronize(ev_done[slot]));
+    const int s = h_stat[slot];
+    if (s) {
+      CK(cudaMemsetAsync(status, 0, sizeof(int), ctx->stream));
+      if (s & ST_NS_NOCONV) { ctx->err = "experimental Newton-Schulz tail (AGP_TAIL_NS) did not converge"; return AGP_ERR_STATE; }
+      if (s & ST_NOT_POSDEF) { ctx->err = "PosDefException: matrix is not positive definite; Cholesky factorization failed."; return AGP_ERR_NOT_POSDEF; }
+      ctx->err = "K̃ has negative values";
+      return AGP_ERR_KTILDE_NONPOS;
+    }
+    memcpy(mu, h_res[slot], m * sizeof(double));
     return AGP_OK;
   }
 
@@ -1917,6 +2009,11 @@ int agp_step_batch(agp_model* model, const void* xb, int x_dtype, int x_layout, 
   return e->sync_status();
 }
 int agp_sync(agp_model* model) { ENG(model); return e->sync_status(); }
+int agp_step_batch_async(agp_model* model, const void* xb, int x_dtype, int x_layout, const void* const* yb, int y_kind, int32_t B,
+                         double rho, int64_t* ticket) {
+  ENG(model); return e->step_batch_async(xb, x_dtype, x_layout, yb, y_kind, B, rho, ticket);
+}
+int agp_result_wait(agp_model* model, int64_t ticket, double* mu) { ENG(model); return e->result_wait(ticket, mu); }
 int agp_step_moments_async(agp_model* model, const int64_t* idx, int32_t B, int32_t base) {
   ENG(model); return e->step_moments(idx, B, base, false);
 }

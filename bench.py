@@ -321,20 +321,39 @@ def run_ours(args, rank, world, local_rank):
 
         mu = np.empty(m)
         eng.ck(lib.agp_use_graph(eng.model, 1 if args.graph else 0))   # public switch: the compute part of a host-batch step replays one CUDA graph
+        pending = []   # --e2e-async: ticket of the step whose result has not been read yet
+
         def e2e_step(i):
             arr = (C.c_void_p * 1)(yb[i].data_ptr())
+            if args.e2e_async:
+                # opt-in (untested on a GPU at the time of writing): no per-step synchronisation; the result of step i-1 is
+                # read while step i runs, the H2D copy of step i overlaps the computation of step i-1
+                tk = C.c_int64(0)
+                eng.ck(lib.agp_step_batch_async(eng.model, C.c_void_p(xb[i].data_ptr()), L.DTYPE_F64, L.LAYOUT_ROWMAJOR, arr, L.Y_REAL, B, rho,
+                                                C.byref(tk)))
+                if pending:
+                    eng.ck(lib.agp_result_wait(eng.model, pending.pop(), L.dptr(mu)))
+                pending.append(tk.value)
+                return
             eng.ck(lib.agp_step_batch(eng.model, C.c_void_p(xb[i].data_ptr()), L.DTYPE_F64, L.LAYOUT_ROWMAJOR, arr, L.Y_REAL, B, rho))
             eng.ck(lib.agp_get_posterior(eng.model, 0, L.dptr(mu), None, None, None))
+
+        def e2e_drain():
+            while pending:
+                eng.ck(lib.agp_result_wait(eng.model, pending.pop(), L.dptr(mu)))
         for i in range(3):
             e2e_step(i)
+        e2e_drain()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for i in range(Ke):
             e2e_step(i)
+        e2e_drain()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         e2e = dict(value=Ke / dt, unit="iters/s", h2d_bytes_per_step=B * D * 8 + B * 8, d2h_bytes_per_step=m * 8 + 4,
-                   steps=Ke, call="agp_step_batch(host x[B,D] f64, host y[B]) + agp_get_posterior(mu)")
+                   steps=Ke, call=("agp_step_batch_async(host x[B,D] f64, host y[B]) + agp_result_wait(previous step's mu)" if args.e2e_async
+                                   else "agp_step_batch(host x[B,D] f64, host y[B]) + agp_get_posterior(mu)"))
     else:
         e2e = dict(value=None, unit="iters/s", h2d_bytes_per_step=B * 8, d2h_bytes_per_step=0,
                    note="latent-sharded run: measured at N=1 only")
@@ -368,6 +387,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("AGP_BENCH_PRECISION", "tf32x3"), choices=["f32", "tf32x3", "f64"])
     ap.add_argument("--graph", type=int, default=1)
+    ap.add_argument("--e2e-async", action="store_true", help="end-to-end leg through agp_step_batch_async / agp_result_wait (opt-in)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--config", default="C2", choices=["C2", "C3"], help="C2 = the contract workload (default); C3 = extra evidence run at the larger configuration")
     ap.add_argument("--timed-only", action="store_true", help="profiling aid: run only warm-up + the timed loop")

@@ -151,6 +151,15 @@ int agp_step_async(agp_model* model, const int64_t* idx, int32_t B, int32_t idx_
  * xb: B x D, yb: array of T pointers of length-B vectors.  Copies host->device inside the call. */
 int agp_step_batch(agp_model* model, const void* xb, int x_dtype, int x_layout, const void* const* yb,
                    int y_kind, int32_t B, double rho);
+/* agp_step_batch without the trailing synchronisation (NOT yet run on a GPU -- written after the round's GPU budget was spent;
+ * bench.py uses it only with --e2e-async).  The host->device copy of the batch runs on a copy stream into one of two
+ * pre-staging slots, so the copy of batch i+1 overlaps the computation of step i; the host buffers may be reused once the
+ * ticket of that step has been waited for (or after agp_sync).  *ticket identifies the step; agp_result_wait(ticket, mu)
+ * blocks until that step is done, returns its sticky status like agp_sync and the posterior mean (length m) of latent 0
+ * after that step.  Only the last two tickets are kept. */
+int agp_step_batch_async(agp_model* model, const void* xb, int x_dtype, int x_layout, const void* const* yb,
+                         int y_kind, int32_t B, double rho, int64_t* ticket);
+int agp_result_wait(agp_model* model, int64_t ticket, double* mu);
 /* wait for the stream and return the sticky device status (AGP_ERR_KTILDE_NONPOS / NOT_POSDEF). */
 int agp_sync(agp_model* model);
 

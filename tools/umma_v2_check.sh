@@ -32,3 +32,8 @@ grep -E "rel err|passed|failed|rror" $OUT/pytest_ns.log | head -20
 # whole C2 bench with the experimental Newton-Schulz tail (Cholesky for the first 8 steps, then 3 refinements per step)
 AGP_UMMA_V2=1 AGP_TAIL_NS=3 timeout 300 python bench.py --steps 100 --warmup 10 > $OUT/bench_ns3.json 2> $OUT/bench_ns3.err; echo "bench ns3 rc=$?"
 tail -c 600 $OUT/bench_ns3.err
+# host-batch steps without a per-step synchronisation (agp_step_batch_async / agp_result_wait): parity test + e2e bench leg
+AGP_EXPERIMENTAL=1 timeout 240 python -m pytest tests/test_experimental_gpu.py -m gpu -x -q -k async > $OUT/pytest_async.log 2>&1; echo "async pytest rc=$?" | tee -a $OUT/pytest_async.log
+tail -3 $OUT/pytest_async.log
+timeout 300 python bench.py --steps 100 --warmup 5 --e2e-async --no-cpu-baseline > $OUT/bench_e2e_async.json 2> $OUT/bench_e2e_async.err; echo "bench e2e-async rc=$?"
+python -c "import json,sys; d=json.loads(open('$OUT/bench_e2e_async.json').read().strip().splitlines()[-1]); print('e2e async', d['e2e'])" 2>&1 | tail -1
