@@ -41,7 +41,7 @@ extern "C" {
 #define AGP_KERNEL_MATERN32 1 /* Matern32Kernel: (1+sqrt3 d) exp(-sqrt3 d)      */
 #define AGP_KERNEL_MATERN52 2 /* Matern52Kernel                                 */
 
-/* likelihood/*.jl (AnalyticVI methods only) */
+/* the files under likelihood/ (AnalyticVI methods only) */
 #define AGP_LIK_GAUSSIAN 0        /* likelihood/gaussian.jl:56-95        p0 = sigma^2            */
 #define AGP_LIK_LOGISTIC 1        /* likelihood/logistic.jl:39-92                                  */
 #define AGP_LIK_STUDENTT 2        /* likelihood/studentt.jl:68-127       p0 = nu, p1 = sigma      */
