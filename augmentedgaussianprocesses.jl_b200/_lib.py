@@ -92,6 +92,7 @@ SIGNATURES = {
     "agp_set_noise_optimiser": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double]),
     "agp_hyper_grads": (C.c_int, [C.c_void_p, C.c_double, c_double_p, c_double_p, c_double_p]),
     "agp_set_Z": (C.c_int, [C.c_void_p, C.c_int32, c_double_p]),
+    "agp_keep_stale_K": (C.c_int, [C.c_void_p, C.c_int32]),
     "agp_set_A_optimiser": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double]),
     "agp_get_A": (C.c_int, [C.c_void_p, c_double_p]),
     "agp_peer_export": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -436,14 +436,15 @@ class AbstractGPModel:
         self._hyperopt_state = None
         if T not in JITTER:
             raise TypeError("T must be np.float64 / np.float32 / np.float16")
-        if precision not in L.PRECISIONS:
-            raise ValueError(f"precision must be one of {sorted(L.PRECISIONS)}")
+        if precision != "auto" and precision not in L.PRECISIONS:
+            raise ValueError(f"precision must be 'auto' or one of {sorted(L.PRECISIONS)}")
         self.inference = inference
         self.verbose = verbose
         self.atfrequency = atfrequency
         self.trained = False
         self.T = T
         self.jitter = JITTER[T]
+        self.precision_requested = precision   # "auto": tcgen05 (tf32x3) when the shapes allow it, fp32 SIMT otherwise -- resolved per engine
         self.precision = precision
         self.device = device
         self.stream = stream
@@ -463,7 +464,8 @@ class AbstractGPModel:
 
     # ---- lazily (re)create the engine with enough batch capacity, carrying the posterior over
     def _engine(self, capacity: int) -> _Engine:
-        if self._eng is not None and capacity <= self._eng.capacity:
+        if self._eng is not None and capacity <= self._eng.capacity and not (
+                self.precision_requested == "auto" and self.precision == "tf32x3" and capacity % 128):
             return self._eng
         old = self._eng
         saved = None
@@ -472,6 +474,9 @@ class AbstractGPModel:
             cnt = self.counters()
             old.close()
         cap = int(capacity)
+        if self.precision_requested == "auto":
+            # the tcgen05 kernels tile m and B by 128; other shapes (e.g. the reference's 10-inducing-point tests) take the fp32 SIMT path
+            self.precision = "tf32x3" if (self.m % 128 == 0 and cap % 128 == 0) else "f32"
         if self.precision == "tf32x3":
             cap = (cap + 127) // 128 * 128
         self._eng = _Engine(self._desc(cap), self.device, self.stream)
@@ -495,6 +500,7 @@ class AbstractGPModel:
             for q, (mu, S, e1, e2) in enumerate(saved):
                 self._eng.ck(self._eng.lib.agp_set_posterior(self._eng.model, q, L.dptr(e1), L.dptr(e2)))
             self._eng.ck(self._eng.lib.agp_set_counters(self._eng.model, cnt[0], cnt[1]))
+            self.inference.HyperParametersUpdated = True   # the new engine has no K_mm factor yet: the next train() call refreshes it
         return self._eng
 
     def _latent_range(self):
@@ -537,14 +543,15 @@ class AbstractGPModel:
 class SVGP(AbstractGPModel):
     """models/SVGP.jl:22-80.  `SVGP(kernel, likelihood, inference, Z; optimiser=false, Zoptimiser=false)`.
 
-    precision: "f64" (fp64 SIMT, exact mode), "f32" (fp32 SIMT) or "tf32x3" (tcgen05 tensor cores).
+    precision: "auto" (default: "tf32x3" when m and the batch size are multiples of 128, else "f32"), "f64" (fp64 SIMT, exact
+    mode), "f32" (fp32 SIMT) or "tf32x3" (tcgen05 tensor cores).
     shard=(rank, world): own n_latent/world latents (LogisticSoftMax classes) on this process.
     """
 
     model_kind = L.MODEL_SVGP
 
     def __init__(self, kernel: Kernel, likelihood: AbstractLikelihood, inference: AnalyticVI, Z, *, verbose: int = 0,
-                 optimiser=False, atfrequency: int = 1, mean=None, Zoptimiser=False, T=np.float64, precision: str = "f32",
+                 optimiser=False, atfrequency: int = 1, mean=None, Zoptimiser=False, T=np.float64, precision: str = "auto",
                  device: int = 0, stream=None, shard=None):
         if not isinstance(likelihood, AbstractLikelihood):
             raise TypeError(f"The {likelihood} is not compatible or implemented with the {inference}")
@@ -583,7 +590,7 @@ class MOSVGP(AbstractGPModel):
 
     def __init__(self, kernel, likelihoods: Sequence[AbstractLikelihood], inference: AnalyticVI, Zs: Sequence, *, A=None,
                  verbose: int = 0, atfrequency: int = 1, mean=None, optimiser=False, Aoptimiser=False, Zoptimiser=False,
-                 T=np.float64, precision: str = "f32", device: int = 0, stream=None, shard=None, rng=None):
+                 T=np.float64, precision: str = "auto", device: int = 0, stream=None, shard=None, rng=None):
         self._common_init(inference, verbose, atfrequency, optimiser, Zoptimiser, T, precision, device, stream, shard)
         if isinstance(Aoptimiser, bool) or Aoptimiser is None:   # MOSVGP.jl:79-81
             Aoptimiser = ADAM(0.01) if Aoptimiser else None
@@ -631,10 +638,14 @@ class VGP(AbstractGPModel):
     model_kind = L.MODEL_VGP
 
     def __init__(self, X, y, kernel: Kernel, likelihood: AbstractLikelihood, inference: AnalyticVI, *, verbose: int = 0, optimiser=False,
-                 atfrequency: int = 1, mean=None, obsdim: int = 1, T=np.float64, precision: str = "f32", device: int = 0, stream=None):
+                 atfrequency: int = 1, mean=None, obsdim: int = 1, T=np.float64, precision: str = "auto", device: int = 0, stream=None):
         if not isinstance(likelihood, AbstractLikelihood):
             raise TypeError(f"The {likelihood} is not compatible or implemented with the {inference}")
         self._common_init(inference, verbose, atfrequency, optimiser, False, T, precision, device, stream, None)
+        if self.optimiser is not None:
+            # update_hyperparameters! of full models (autotuning.jl:48-84) differentiates an ELBO whose kernel dependence is the
+            # GaussianKL only (mean_f = mu, var_f = diag(Sigma)); agp_hyper_grads implements the sparse ELBO gradient
+            raise NotImplementedError("hyper-parameter optimisation of full (non-sparse) models is outside the accelerated path")
         if inference.stoch:
             raise ValueError("VGP is a full-batch model: use AnalyticVI()")
         X = np.asarray(X, dtype=np.float64)
@@ -677,7 +688,7 @@ class MOVGP(AbstractGPModel):
 
     def __init__(self, X, ys, kernel, likelihoods: Sequence[AbstractLikelihood], inference: AnalyticVI, num_latent: int, *, A=None,
                  verbose: int = 0, atfrequency: int = 1, optimiser=False, Aoptimiser=False, obsdim: int = 1, T=np.float64,
-                 precision: str = "f32", device: int = 0, stream=None, rng=None):
+                 precision: str = "auto", device: int = 0, stream=None, rng=None):
         self._common_init(inference, verbose, atfrequency, optimiser, False, T, precision, device, stream, None)
         if self.optimiser is not None:
             raise NotImplementedError("hyper-parameter optimisation of full (non-sparse) models is outside the accelerated path")
@@ -816,8 +827,15 @@ def _upload(model, eng, X, ys, key):
 
 
 def train(model: AbstractGPModel, X=None, y=None, iterations: int = 100, *, callback=None, convergence=None, state: Optional[State] = None,
-          obsdim: int = 1, minibatches: Optional[Sequence[np.ndarray]] = None, rng=None, check_every: int = 1):
+          obsdim: int = 1, minibatches: Optional[Sequence[np.ndarray]] = None, rng=None, check_every: int = 1,
+          refresh_K_after_hyper: bool = False, reupload: bool = False):
     """`train!(model, X, y, iterations; callback, state)`.
+
+    refresh_K_after_hyper: False (default) reproduces the reference (quirk Q3): after `update_hyperparameters!` the K_mm
+    factor of this call's first iteration stays in use until the next `train!` call without a state (autotuning.jl:45 is
+    commented out; training.jl:187-208 clears the flag), while K_nm follows the new kernel / Z.  True = refactorise K_mm after
+    every hyper-parameter update (the conscious fix).
+    reupload: the resident copy of (X, y) is keyed on the identity of the arrays; pass True after refilling them in place.
 
     minibatches: optional list of 0-based index arrays, one per iteration (the reference draws them with
     StatsBase.sample on Julia's global RNG, training.jl:51-53, which cannot be reproduced; parity runs
@@ -850,8 +868,12 @@ def train(model: AbstractGPModel, X=None, y=None, iterations: int = 100, *, call
         inf.batchsize = n
     B = inf.batchsize
     eng = model._engine(B)
+    if reupload:
+        model._data_key = None
     _upload(model, eng, X, ys, (id(X), tuple(id(v) for v in ys), X.shape))
+    model._data_refs = (X, ys)   # keep the keyed arrays alive: a freed array's id() can be reused by a new one
     lib = eng.lib
+    eng.ck(lib.agp_keep_stale_K(eng.model, 0 if refresh_K_after_hyper else 1))
     if state is None:
         inf.HyperParametersUpdated = True
         eng.ck(lib.agp_state_reset(eng.model))
@@ -886,7 +908,8 @@ def train(model: AbstractGPModel, X=None, y=None, iterations: int = 100, *, call
         if (model.optimiser is not None or model.Zoptimiser is not None) and inf.n_iter % model.atfrequency == 0 and inf.n_iter >= 3 \
                 and it != iterations - 1:
             update_hyperparameters(model, eng)
-            eng.ck(lib.agp_refresh_K(eng.model))   # compute_kernel_matrices with HPupdated (training.jl:187-208)
+            if refresh_K_after_hyper:
+                eng.ck(lib.agp_refresh_K(eng.model))   # the fix: compute_kernel_matrices as if HPupdated had been raised
         inf.n_iter += 1
     _refresh_lik_params(model, eng)
     return model, state
@@ -1126,7 +1149,7 @@ def predict_y(model, X_test, state=None, *, obsdim: int = 1):
     if X_test.ndim == 2 and obsdim == 2:
         X_test = X_test.T
     mu, _ = _predict_f(model, X_test, False)
-    if isinstance(model, MOSVGP):
+    if isinstance(model, (MOSVGP, MOVGP)):
         return [_predict_y_lik(l, mu[t : t + 1]) for t, l in enumerate(model.likelihoods)]
     return _predict_y_lik(model.likelihood, mu)
 
@@ -1169,6 +1192,6 @@ def proba_y(model, X_test, state=None, *, obsdim: int = 1):
     if X_test.ndim == 2 and obsdim == 2:
         X_test = X_test.T
     mu, var = _predict_f(model, X_test, True)
-    if isinstance(model, MOSVGP):
+    if isinstance(model, (MOSVGP, MOVGP)):
         return [_compute_proba(model, l, mu[t : t + 1], var[t : t + 1]) for t, l in enumerate(model.likelihoods)]
     return _compute_proba(model, model.likelihood, mu, var)

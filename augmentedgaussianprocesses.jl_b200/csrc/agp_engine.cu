@@ -92,6 +92,7 @@ struct EngineBase {
   virtual int set_noise_optimiser(int task, int kind, double eta, double b1, double b2, double eps) = 0;
   virtual int hyper_grads(double rho, double* d_scale, double* d_variance, double* dZ) = 0;
   virtual int set_Z(int ql, const double* Z) = 0;
+  virtual int keep_stale_K(int on) = 0;
   virtual int set_A_optimiser(int kind, double eta, double b1, double b2, double eps) = 0;
   virtual int get_A(double* A) = 0;
   virtual int peer_export(void* handle64) = 0;
@@ -161,6 +162,8 @@ struct Engine : EngineBase {
     UmmaNs ns; bool ns_alloc = false;
     bool ns_seeded = false;      // ns.Y() is the covariance of the current eta2_v
     bool factor_valid = true;    // Xv / Xv_T / tvec describe the current natural parameters
+    // quirk Q3 (agp_keep_stale_K): the factor of the last agp_refresh_K, parked while agp_hyper_grads works with a fresh one
+    double *bkLc = nullptr, *bkLinv = nullptr, *bkKinv = nullptr, *bkmu0v = nullptr; T* bkLinvT = nullptr; double bklogdetK = 0.0;
   };
   std::vector<Latent> lat;
 
@@ -439,7 +442,7 @@ struct Engine : EngineBase {
     if (h_mu) cudaFreeHost(h_mu);
     for (auto& L : lat) {
       void* ps[] = {L.Z, L.zz, L.Zd, L.zzd, L.Lc, L.Linv, L.Kinv, L.mu0, L.mu0v, L.Linv_T, L.eta1c, L.eta2c, L.eta1v, L.eta2v,
-                    L.muv, L.tvec, L.Xv, L.Dinv, L.Xv_T, L.Knm, L.V, L.VS, L.Ktilde, L.racc, L.Gpart, L.v1, L.P, L.X, L.W, L.logdetP};
+                    L.muv, L.tvec, L.Xv, L.Dinv, L.Xv_T, L.Knm, L.V, L.VS, L.Ktilde, L.racc, L.Gpart, L.v1, L.P, L.X, L.W, L.logdetP, L.bkLc, L.bkLinv, L.bkKinv, L.bkmu0v, L.bkLinvT};
       for (void* p : ps) cudaFree(p);
       umma_latent_free(L.um);
       if (L.ns_alloc) umma_ns_free(L.ns);
@@ -667,6 +670,7 @@ struct Engine : EngineBase {
     CK(cudaGetLastError());
     int s = sync_status();
     have_K = (s == AGP_OK);
+    K_dirty = false;
     prefetched = false;
     drop_graph();
     return s;
@@ -705,7 +709,8 @@ struct Engine : EngineBase {
   int set_kernel(int ql, int kind, double scale, double variance) override {
     if (ql < 0 || ql >= Ql || kind < 0 || kind > 2 || !(scale > 0) || !(variance > 0)) BAD("bad kernel parameters");
     lat[ql].kind = kind; lat[ql].scale = scale; lat[ql].variance = variance;
-    have_K = false; prefetched = false;
+    if (stale_K_ok && have_K) K_dirty = true; else have_K = false;
+    prefetched = false;
     drop_graph();
     return AGP_OK;
   }
@@ -853,6 +858,16 @@ struct Engine : EngineBase {
     ++launches;
   }
   int hyper_grads(double rho, double* d_scale, double* d_variance, double* dZ) override {
+    if (is_vgp) BAD("hyper-parameter gradients of full (non-sparse) models are outside the accelerated path (autotuning.jl:48-84 differentiates a different ELBO)");
+    if (have_K && K_dirty && stale_K_ok) {
+      CKS(swap_in_fresh_K());
+      int rc = hyper_grads_impl(rho, d_scale, d_variance, dZ);
+      int rb = swap_back_stale_K();
+      return rc != AGP_OK ? rc : rb;
+    }
+    return hyper_grads_impl(rho, d_scale, d_variance, dZ);
+  }
+  int hyper_grads_impl(double rho, double* d_scale, double* d_variance, double* dZ) {
     if (!d_scale || !d_variance) BAD("null output");
     if (curB < 1 || !have_step) { ctx->err = "hyper-parameter gradients need a completed step (the last minibatch is differentiated)"; return AGP_ERR_STATE; }
     CKS(ensure_factors());
@@ -947,9 +962,59 @@ struct Engine : EngineBase {
     CK(cudaMemcpy(L.Z, zt.data(), zt.size() * sizeof(T), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(L.zz, znt.data(), znt.size() * sizeof(T), cudaMemcpyHostToDevice));
     if (L.knm_tc) CKS(umma_knm_setup(ctx_err(), L.uk, (const float*)(const void*)L.Z, Dp, m, D, (float*)(void*)L.Knm, ldm, Bcap, st()));
-    have_K = false; prefetched = false;
+    if (stale_K_ok && have_K) K_dirty = true; else have_K = false;
+    prefetched = false;
     drop_graph();
     return AGP_OK;
+  }
+
+  // ---- quirk Q3 of the reference (agp_keep_stale_K) -------------------------------------------------------------------------
+  // The reference's sparse update_hyperparameters! never raises the HyperParametersUpdated flag (hyperparameter/autotuning.jl:45
+  // is commented out; compute_kernel_matrices clears it, training/training.jl:187-208): after a kernel / Z update the steps of
+  // the same train! call keep the K_mm factor of the call's first iteration next to a K_nm built from the new kernel and Z, while
+  // the next gradient evaluates ELBO(model, x, y, mu0, ks, Zs, state) with everything recomputed (functions/ELBO.jl:15-21).
+  // With the policy on, agp_set_kernel / agp_set_Z leave the factor in place (K_dirty) and agp_hyper_grads swaps a fresh
+  // factorisation in for the duration of the call: the posterior travels through its canonical form (fp64) both ways.
+  bool stale_K_ok = false, K_dirty = false;
+  int keep_stale_K(int on) override { stale_K_ok = on != 0; return AGP_OK; }
+  int swap_in_fresh_K() {
+    const size_t mm = (size_t)mp * mp;
+    for (auto& L : lat) {
+      if (!L.bkLc) {
+        CKS(dalloc(&L.bkLc, mm)); CKS(dalloc(&L.bkLinv, mm)); CKS(dalloc(&L.bkKinv, mm)); CKS(dalloc(&L.bkmu0v, mp));
+        CKS(dalloc(&L.bkLinvT, (size_t)m * ldm));
+      }
+      CK(cudaMemcpyAsync(L.bkLc, L.Lc, mm * 8, cudaMemcpyDeviceToDevice, st()));
+      CK(cudaMemcpyAsync(L.bkLinv, L.Linv, mm * 8, cudaMemcpyDeviceToDevice, st()));
+      CK(cudaMemcpyAsync(L.bkKinv, L.Kinv, mm * 8, cudaMemcpyDeviceToDevice, st()));
+      CK(cudaMemcpyAsync(L.bkmu0v, L.mu0v, (size_t)mp * 8, cudaMemcpyDeviceToDevice, st()));
+      CK(cudaMemcpyAsync(L.bkLinvT, L.Linv_T, (size_t)m * ldm * sizeof(T), cudaMemcpyDeviceToDevice, st()));
+      L.bklogdetK = L.logdetK;
+    }
+    CKS(ensure_factors());
+    CKS(refresh_K());               // canonicalises with the parked factor, factorises the current kernel / Z, whitens again
+    kernel_matrices_stale = true;   // V = Knm L^-T of the last minibatch belongs to the parked factor
+    return AGP_OK;
+  }
+  int swap_back_stale_K() {
+    const size_t mm = (size_t)mp * mp;
+    for (auto& L : lat) {
+      if (L.white_valid) { canonicalize(L); L.white_valid = false; }
+      CK(cudaMemcpyAsync(L.Lc, L.bkLc, mm * 8, cudaMemcpyDeviceToDevice, st()));
+      CK(cudaMemcpyAsync(L.Linv, L.bkLinv, mm * 8, cudaMemcpyDeviceToDevice, st()));
+      CK(cudaMemcpyAsync(L.Kinv, L.bkKinv, mm * 8, cudaMemcpyDeviceToDevice, st()));
+      CK(cudaMemcpyAsync(L.mu0v, L.bkmu0v, (size_t)mp * 8, cudaMemcpyDeviceToDevice, st()));
+      CK(cudaMemcpyAsync(L.Linv_T, L.bkLinvT, (size_t)m * ldm * sizeof(T), cudaMemcpyDeviceToDevice, st()));
+      if (L.um.v2) { CKS(umma_presplit(ctx_err(), L.um, UM_LINV, (const float*)(const void*)L.Linv_T, st())); ++launches; }
+      L.logdetK = L.bklogdetK;
+      CKS(whiten(L));
+    }
+    kernel_matrices_stale = true; prefetched = false;
+    drop_graph();
+    int s_ = sync_status();
+    have_K = (s_ == AGP_OK);
+    K_dirty = true;                 // the kernel / Z still differ from the factor
+    return s_;
   }
 
   // ---- GaussianLikelihood(opt_noise = ADAM(..)) switch ------------------------------------------------------------------
@@ -2050,6 +2115,7 @@ int agp_hyper_grads(agp_model* model, double rho, double* d_scale, double* d_var
   ENG(model); return e->hyper_grads(rho, d_scale, d_variance, dZ);
 }
 int agp_set_Z(agp_model* model, int32_t latent_local, const double* Z) { ENG(model); return e->set_Z(latent_local, Z); }
+int agp_keep_stale_K(agp_model* model, int32_t on) { ENG(model); return e->keep_stale_K(on); }
 int agp_set_A_optimiser(agp_model* model, int32_t kind, double eta, double beta1, double beta2, double eps) {
   ENG(model); return e->set_A_optimiser(kind, eta, beta1, beta2, eps);
 }

@@ -190,6 +190,13 @@ int agp_set_noise_optimiser(agp_model* model, int32_t task, int32_t kind, double
  * pushes the new values with agp_set_kernel / agp_set_Z and calls agp_refresh_K.  Collective on a sharded model. */
 int agp_hyper_grads(agp_model* model, double rho, double* d_scale, double* d_variance, double* dZ);
 int agp_set_Z(agp_model* model, int32_t latent_local, const double* Z /* [m][D] row-major */);
+/* Reference quirk Q3 switch.  on = 1 (what the reference does): the sparse update_hyperparameters! never raises
+ * HyperParametersUpdated (its only setHPupdated!(.., true) call site, hyperparameter/autotuning.jl:45, is commented out, and
+ * compute_kernel_matrices clears the flag, training/training.jl:187-208), so after agp_set_kernel / agp_set_Z the steps keep the
+ * K_mm factor of the last agp_refresh_K next to a K_nm built from the new kernel / Z, and agp_hyper_grads evaluates its ELBO with
+ * a fresh factorisation (functions/ELBO.jl:15-21) that it discards afterwards.  on = 0 (default of the bare ABI): a kernel / Z
+ * change invalidates the factor and agp_refresh_K must follow. */
+int agp_keep_stale_K(agp_model* model, int32_t on);
 
 /* update_A! (models/single_and_multi_output_utils.jl:87-118; MOSVGP `Aoptimiser`, MOSVGP.jl:51,79-81): kind 0 = A fixed
  * (Aoptimiser = false), 1 = ADAM(eta, (beta1, beta2)) of Optimisers.jl with epsilon.  When on, every step first moves each

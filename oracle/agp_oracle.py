@@ -16,7 +16,8 @@ file in tests/test_oracle.py.
 
 Reference quirks reproduced on purpose: Q1 logistic ELBO uses
 dot(theta, mu); Q2 GammaEntropy uses log(beta[0]) only; Q3 K_mm factorised once per
-train call; Q6 LogisticSoftMax local variables persist across minibatches; Q9
+train call -- also after update_hyperparameters! (stale K_mm next to a fresh K_nm; the
+fix is the opt-in `model.refresh_K_after_hyper`); Q6 LogisticSoftMax local variables persist across minibatches; Q9
 Robbins-Monro counter starts at 1; Q10 length(y) of a one-hot y is B*K.
 """
 from __future__ import annotations
@@ -903,7 +904,13 @@ def hyper_grads(model, state, x, y):
 def update_hyperparameters(model, state, x, y):
     """update_hyperparameters!(m, state, x, y) for sparse models (autotuning.jl:86-140): ADAM on the log of every positive
     kernel parameter (update_kernel!, autotuning_utils.jl:63-67: step on x .* g, x = exp(log x + step)) and plain ADAM ascent on
-    the inducing points (update_Z!, :78-82); K_mm is refactorised at the next iteration."""
+    the inducing points (update_Z!, :78-82).
+
+    Quirk Q3, reproduced by default: the reference never raises the HyperParametersUpdated flag after a sparse update (its only
+    `setHPupdated!(…, true)` call site, autotuning.jl:45, is commented out) and compute_kernel_matrices clears the flag
+    (training.jl:187-208), so for the rest of the train! call K_mm and its Cholesky factor stay those of the call's first
+    iteration while K_nm (and the next gradient, whose ELBO recomputes everything with update=true, functions/ELBO.jl:15-21)
+    use the new kernel and Z.  `model.refresh_K_after_hyper = True` is the conscious fix (refactorise at the next iteration)."""
     if model.optimiser is None and model.Zoptimiser is None:
         return state
     grads = hyper_grads(model, state, x, y)
@@ -924,7 +931,8 @@ def update_hyperparameters(model, state, x, y):
             hs[q]["Z"], dZ = model.Zoptimiser.apply(hs[q]["Z"], g["Z"])
             gp.Z = gp.Z + dZ
         gp.kernel = Kernel(k.kind, scale=new_scale, variance=new_var)
-    model.inference.HyperParametersUpdated = True
+    if getattr(model, "refresh_K_after_hyper", False):
+        model.inference.HyperParametersUpdated = True
     return state
 
 

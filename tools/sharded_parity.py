@@ -1,6 +1,8 @@
 """Latent-sharded run (torchrun, one rank per GPU) against the same model on one GPU: posterior / ELBO must agree.
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/sharded_parity.py
-Covers the NVLink peer-memory exchange (default) and, with AGP_NO_PEER=1, the NCCL all-gather fallback."""
+Covers the NVLink peer-memory exchange (default) and, with AGP_NO_PEER=1, the NCCL all-gather fallback.
+EVERY rank checks its own latents: (a) against the unsharded engine model run on its own GPU (1e-9: same arithmetic), and
+(b) against the fp64 oracle (oracle/agp_oracle.py, tf32x3 tolerance 5e-4 on mu / Sigma / ELBO); rank 0 prints the verdict."""
 import os, sys
 import numpy as np
 import torch
@@ -8,7 +10,9 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import agp_b200 as agp
+import agp_oracle as O
 from problems import rel_fro
 
 
@@ -43,16 +47,33 @@ def main():
         yp_s = agp.predict_y(ms, X[:500])                      # collective: rows of the owned latents gathered on the host
         q0, ql = ms._latent_range()
         mine = [ms.posterior(q) for q in range(ql)]
+        # (a) the same model, unsharded, on this rank's own GPU
+        m1 = mk()
+        m1, s1 = agp.train(m1, X, y, iters, minibatches=mbs)
+        e_1 = agp.ELBO(m1, s1)
+        errs = [max(rel_fro(mine[q][0], m1.posterior(q0 + q)[0]), rel_fro(mine[q][1], m1.posterior(q0 + q)[1])) for q in range(ql)]
+        yp_1 = agp.predict_y(m1, X[:500])
+        same_pred = all(np.array_equal(a, b) for a, b in zip(yp_s, yp_1)) if isinstance(yp_1, list) else np.array_equal(yp_s, yp_1)
+        good = max(errs) < 1e-9 and abs(e_s - e_1) <= 1e-9 * abs(e_1) and same_pred
+        # (b) the fp64 oracle (every rank computes it: the check of rank r's latents must not depend on rank 0)
+        X64 = X.astype(np.float64)
+        if case == "mosvgp":
+            mo = O.MOSVGP(O.Kernel("sqexp", scale=sc), [O.LogisticLikelihood() for _ in range(Q)], O.AnalyticSVI(B), Zs, A)
+        else:
+            mo = O.SVGP(O.Kernel("sqexp", scale=sc), O.LogisticSoftMaxLikelihood(Q), O.AnalyticSVI(B), Z)
+        mo, so = O.train(mo, X64, y, iters, minibatches=mbs)
+        e_o = mo.ELBO(so, so["y_batch"])
+        errs_o = [max(rel_fro(mine[q][0], mo.f[q0 + q].mu), rel_fro(mine[q][1], mo.f[q0 + q].Sigma)) for q in range(ql)]
+        good_o = max(errs_o) < 5e-4 and abs(e_s - e_o) <= 25e-4 * max(1.0, abs(e_o))
+        res = torch.tensor([1.0 if good else 0.0, 1.0 if good_o else 0.0, max(errs), max(errs_o)], dtype=torch.float64, device=f"cuda:{lr}")
+        allres = [torch.zeros_like(res) for _ in range(world)]
+        dist.all_gather(allres, res)
+        allres = torch.stack(allres).cpu().numpy()
+        good_all = bool(allres[:, 0].min() > 0.5 and allres[:, 1].min() > 0.5)
+        ok = ok and good_all
         if rank == 0:
-            m1 = mk()
-            m1, s1 = agp.train(m1, X, y, iters, minibatches=mbs)
-            e_1 = agp.ELBO(m1, s1)
-            errs = [max(rel_fro(mine[q][0], m1.posterior(q0 + q)[0]), rel_fro(mine[q][1], m1.posterior(q0 + q)[1])) for q in range(ql)]
-            yp_1 = agp.predict_y(m1, X[:500])
-            same_pred = all(np.array_equal(a, b) for a, b in zip(yp_s, yp_1)) if isinstance(yp_1, list) else np.array_equal(yp_s, yp_1)
-            good = max(errs) < 1e-9 and abs(e_s - e_1) <= 1e-9 * abs(e_1) and same_pred
-            ok = ok and good
-            print(f"[{case}] world={world} peer={getattr(ms, '_peer', False)}: max rel err (mu, Sigma) {max(errs):.2e}, ELBO {e_s:.6f} vs {e_1:.6f} -> {'OK' if good else 'MISMATCH'}", flush=True)
+            print(f"[{case}] world={world} peer={getattr(ms, '_peer', False)}: every rank vs unsharded engine: max rel err (mu, Sigma) {allres[:, 2].max():.2e}; "
+                  f"vs fp64 oracle: {allres[:, 3].max():.2e}; ELBO {e_s:.6f} / engine {e_1:.6f} / oracle {e_o:.6f} -> {'OK' if good_all else 'MISMATCH'}", flush=True)
         dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
