@@ -13,6 +13,7 @@
 #include "agp_kernels.cuh"
 #include "agp_tail.cuh"
 #include "agp_tail2.cuh"
+#include "agp_tail3.cuh"
 #include "agp_hyper.cuh"
 #include "agp_umma.h"
 
@@ -200,7 +201,10 @@ struct Engine : EngineBase {
   double* d_lr = nullptr;          // Robbins-Monro step size of the current iteration (lik_update_kernel -> combine_kernel)
   bool fuse_lik_next = false, fuse_from_batch = false, lik_fused = false;   // rowfinish + local-update fusion (set by the step paths)
   bool racc2_precleared = false;   // the V X^T row-statistic accumulators were cleared off the critical chain (side stream)
-  int tail_variant = 3;  // AGP_TAIL_VARIANT: 0 = agp_tail.cuh (generation 1, SIMT tile products), otherwise agp_tail2.cuh (DMMA, panel potf2)
+  int tail_variant = 3;  // AGP_TAIL_VARIANT: 0 = agp_tail.cuh (generation 1, SIMT tile products), 2 = agp_tail2.cuh (DMMA, panel potf2, one
+                         // launch per block step and latent), 3 (default) = agp_tail3.cuh (one persistent launch for all owned latents)
+  Tail3Lat* d_t3lat = nullptr; u64* d_t3flags = nullptr;
+  int t3_sm_budget = 148;   // AGP_TAIL3_SMS: CTAs (= SMs) the persistent tail may occupy
 
   // ---- step state ----
   int curB = 0; bool cur_from_batch = false; bool have_K = false; bool have_data = false; bool have_step = false;
@@ -416,7 +420,24 @@ struct Engine : EngineBase {
       CKS(umma_ns_alloc(ctx_err(), lat[0].ns, m, st()));
       lat[0].ns_alloc = true;
     } else ns_iters = 0;
-    { const char* e = getenv("AGP_TAIL_VARIANT"); if (e) tail_variant = atoi(e); if (tail_variant != 0) tail_variant = 3; }
+    // default: the persistent tail for two or more owned latents (one launch, the chains run side by side), the multi-launch tail2
+    // chain for a single latent (126 vs 138 us at m = 512: see agp_tail3.cuh)
+    tail_variant = Ql >= 2 ? 3 : 2;
+    { const char* e = getenv("AGP_TAIL_VARIANT"); if (e) { tail_variant = atoi(e); if (tail_variant != 0 && tail_variant != 2) tail_variant = 3; } }
+    { const char* e = getenv("AGP_TAIL3_SMS"); if (e && atoi(e) >= 2) t3_sm_budget = std::min(148, atoi(e)); }
+    {   // per-latent descriptors + dependency words of the persistent tail (zero-initialised: epoch 0)
+      const int nblk = mp / TNB;
+      const size_t fw = tail3_flag_words(nblk);
+      CKS(dalloc(&d_t3flags, fw * Ql)); CKS(dalloc(&d_t3lat, Ql));
+      std::vector<Tail3Lat> h(Ql);
+      for (int q = 0; q < Ql; ++q) {
+        Latent& L = lat[q];
+        h[q].P = L.P; h[q].W = L.W; h[q].Xout = L.Xv; h[q].Dinv = L.Dinv; h[q].logdet = L.logdetP; h[q].flags = d_t3flags + fw * q;
+      }
+      CK(cudaMemcpyAsync(d_t3lat, h.data(), Ql * sizeof(Tail3Lat), cudaMemcpyHostToDevice, st()));
+      CK(cudaStreamSynchronize(st()));
+      CK(cudaFuncSetAttribute(tail3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL3_SMEM));
+    }
     CK(cudaStreamSynchronize(st()));
     return AGP_OK;
   }
@@ -465,7 +486,7 @@ struct Engine : EngineBase {
     if (ev_join) cudaEventDestroy(ev_join);
     void* ps[] = {idx_prev, xx_cur, pKS, pXb, pxxb, X, xx, y_all, ycls_all, Xb, xxb, stage, idx_pool, idx_cur, counters, status, d_lik_kind, d_p0, d_p1, d_A,
                   xchg, d_xepoch, d_peers, gmu, gS, lc, ltheta, lgamma_, lalpha, tmu, tvar, gm, gs, yb, ycls, d_out, d_lam, d_lamacc, d_qnodes, d_qw, d_lr, d_gradA, d_Amt, d_Avt, d_Abt, d_noise_opt, d_noise_state,
-                  hgH[0], hgH[1], hgH[2], hgH[3], hgX, hgA, hgB, hgM1, hgM2, hgV, hgP};
+                  hgH[0], hgH[1], hgH[2], hgH[3], hgX, hgA, hgB, hgM1, hgM2, hgV, hgP, d_t3lat, d_t3flags};
     for (void* p : ps) cudaFree(p);
   }
 
@@ -1225,9 +1246,16 @@ struct Engine : EngineBase {
       ++launches;
       ph_end();
       if (ns_tail_now) CKS(eta_to_moments_ns(L));
-      else {
+      else if (tail_variant != 3) {
         CKS(eta_to_moments(L, q == Ql - 1));   // the last latent's finalize kernel also prepares the next step size
         L.factor_valid = true; L.ns_seeded = false;
+      }
+    }
+    if (!ns_tail_now && tail_variant == 3) {   // every owned latent's Cholesky + inverse factor in one persistent launch
+      chol_inv_many(0, Ql);
+      for (int q = 0; q < Ql; ++q) {
+        CKS(finalize_factor(lat[q], q == Ql - 1));
+        lat[q].factor_valid = true; lat[q].ns_seeded = false;
       }
     }
     // (the counters are bumped by the last latent's finalize kernel)
@@ -1259,8 +1287,41 @@ struct Engine : EngineBase {
     cudaLaunchKernelEx(&cfg, kern, tp);
   }
 
-  // fused blocked Cholesky + inverse of the factor (agp_tail.cuh): P (lower tiles, destroyed) -> Xv = chol(P)^-1
+  // fused blocked Cholesky + inverse of the factor: P (lower tiles, destroyed) -> Xv = chol(P)^-1, for latents [q0, q0 + count)
+  // tail_variant 3: one persistent launch per group of latents (agp_tail3.cuh); otherwise nblk + 1 launches per latent
+  int tail3_ctas(int count) const {      // CTAs the persistent tail of `count` latents occupies (first launch)
+    const int nblk = mp / TNB;
+    if (nblk == 1) return std::min(count, t3_sm_budget);
+    const int nl = std::min(count, std::max(1, t3_sm_budget / 4));
+    return nl * std::max(2, std::min(tail3_team(nblk), t3_sm_budget / nl));
+  }
+  // CTAs per latent: the chain CTA + enough helpers that no helper has more than ~2 tile tasks per block step (a helper task takes
+  // about half a chain step; measured with profiles/microbench/tail3_test.cu: 20 and 35 CTAs give the same time at m = 512)
+  static int tail3_team(int nblk) { return (tail3_max_tasks(nblk) * 13 + 19) / 20 + 1; }
+  void chol_inv_many(int q0, int count) {
+    if (tail_variant != 3) { for (int q = q0; q < q0 + count; ++q) chol_inv(lat[q]); return; }
+    ph_begin(PH_CHOL);
+    const int nblk = mp / TNB;
+    const int gcap = tail3_team(nblk);
+    int done = 0;
+    while (done < count) {
+      const int nl = std::min(count - done, std::max(1, t3_sm_budget / (nblk == 1 ? 1 : 4)));   // at least 4 CTAs per latent
+      const int G = nblk == 1 ? 1 : std::max(2, std::min(gcap, t3_sm_budget / nl));
+      Tail3Params tp{};
+      tp.lat = d_t3lat + q0 + done; tp.nlat = nl; tp.G = G; tp.nblk = nblk; tp.ld = mp; tp.status = status;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(nl * G); cfg.blockDim = dim3(TAIL_THREADS); cfg.dynamicSmemBytes = TAIL3_SMEM; cfg.stream = st();
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at; cfg.numAttrs = (tail_pdl && !prof) ? 1 : 0;
+      cudaLaunchKernelEx(&cfg, tail3_kernel, tp);
+      ++launches;
+      done += nl;
+    }
+    ph_end();
+  }
   void chol_inv(Latent& L) {
+    if (tail_variant == 3) { chol_inv_many((int)(&L - lat.data()), 1); return; }
     ph_begin(PH_CHOL);
     TailStepParams tp{};
     tp.P = L.P; tp.W = L.W; tp.Xout = L.Xv; tp.Dinv = L.Dinv; tp.ld = mp; tp.nblk = mp / TNB; tp.logdet = L.logdetP; tp.status = status;
@@ -1283,6 +1344,10 @@ struct Engine : EngineBase {
   // factored form (X = chol(P_v)^-1), mu_v = Sigma_v eta1_v = X^T (X eta1_v)
   int eta_to_moments(Latent& L, bool in_step = false) {
     chol_inv(L);
+    return finalize_factor(L, in_step);
+  }
+  // after the tail: fp32 shadow (+ TF32 split) of X, t = X eta1_v; the last latent's kernel also prepares the next step size
+  int finalize_factor(Latent& L, bool in_step) {
     ph_begin(PH_FINAL);
     float* hi = umma_split_ptr(L.um, UM_X, 0);   // non-null only with the opt-in v2 GEMM: X leaves this kernel pre-split
     float* lo = umma_split_ptr(L.um, UM_X, 1);
@@ -1405,7 +1470,10 @@ struct Engine : EngineBase {
       int s = AGP_OK;
       if (cudaMemcpyAsync(idx_prev, idx_cur, (size_t)B * 8, cudaMemcpyDeviceToDevice, st()) != cudaSuccess) s = AGP_ERR_CUDA;
       if (s == AGP_OK) s = prep_idx(nullptr, B, 0, 1);          // the cursor is bumped at the end of this step
+      // the persistent tail holds one SM per CTA for its whole duration: keep the prefetch GEMM's persistent grid off those SMs
+      if (tail_variant == 3 && !ns_tail_now) umma_set_grid_cap(std::max(32, 148 - tail3_ctas(Ql)));
       if (s == AGP_OK) s = moments_impl(false, B, true, 1);
+      umma_set_grid_cap(0);
       if (s == AGP_OK && prec == AGP_PREC_TF32X3 && Ql == 1) {   // clear the next step's V X^T accumulators off the critical chain
         if (cudaMemsetAsync(lat[0].racc + ldB, 0, 2 * ldB * sizeof(double), st()) != cudaSuccess) s = AGP_ERR_CUDA;
         else racc2_precleared = true;
@@ -1630,6 +1698,7 @@ struct Engine : EngineBase {
     const int s = h_stat[slot];
     if (s) {
       CK(cudaMemsetAsync(status, 0, sizeof(int), ctx->stream));
+      if (s & ST_TAIL_TIMEOUT) { ctx->err = "persistent m x m tail timed out waiting for a tile"; return AGP_ERR_STATE; }
       if (s & ST_NS_NOCONV) { ctx->err = "experimental Newton-Schulz tail (AGP_TAIL_NS) did not converge"; return AGP_ERR_STATE; }
       if (s & ST_NOT_POSDEF) { ctx->err = "PosDefException: matrix is not positive definite; Cholesky factorization failed."; return AGP_ERR_NOT_POSDEF; }
       ctx->err = "K̃ has negative values";
@@ -1648,6 +1717,7 @@ struct Engine : EngineBase {
     if (s) {
       CK(cudaMemset(status, 0, sizeof(int)));
       if (s & ST_PEER_TIMEOUT) { ctx->err = "peer exchange timed out (a rank of the latent-sharded group did not publish its moments)"; return AGP_ERR_STATE; }
+      if (s & ST_TAIL_TIMEOUT) { ctx->err = "persistent m x m tail timed out waiting for a tile (CTAs of one launch not co-resident?); AGP_TAIL_VARIANT=2 selects the multi-launch tail"; return AGP_ERR_STATE; }
       if (s & ST_NS_NOCONV) { ctx->err = "experimental Newton-Schulz tail (AGP_TAIL_NS) did not converge: raise AGP_TAIL_NS_AFTER or the iteration count"; return AGP_ERR_STATE; }
       if (s & ST_NOT_POSDEF) { ctx->err = "PosDefException: matrix is not positive definite; Cholesky factorization failed."; return AGP_ERR_NOT_POSDEF; }
       ctx->err = "K̃ has negative values";

@@ -10,7 +10,7 @@
 namespace agp {
 
 // sticky device status bits (read back by agp_sync)
-enum : int { ST_KTILDE = 1, ST_NOT_POSDEF = 2, ST_PEER_TIMEOUT = 4, ST_NS_NOCONV = 8 };
+enum : int { ST_KTILDE = 1, ST_NOT_POSDEF = 2, ST_PEER_TIMEOUT = 4, ST_NS_NOCONV = 8, ST_TAIL_TIMEOUT = 16 };
 
 // Programmatic dependent launch (griddepcontrol).  Kernels on the per-step critical chain call pdl_prologue() first:
 // launch_dependents lets the NEXT kernel of the chain become resident while this one runs, wait blocks until the

@@ -763,6 +763,12 @@ static int sm_count() {
   return n;
 }
 
+// persistent-grid cap for GEMMs launched next to a resident kernel that needs its own SMs (the prefetch of the next minibatch's
+// V = Knm L^-T runs on a side stream while the persistent m x m tail occupies one SM per CTA): 0 = all SMs
+static int g_grid_cap = 0;
+void umma_set_grid_cap(int n) { g_grid_cap = n; }
+static int grid_cap() { const int n = sm_count(); return (g_grid_cap > 0 && g_grid_cap < n) ? g_grid_cap : n; }
+
 int umma_gemm_nt(std::string* err, UmmaLatent& u, int a_which, int b_which, float* C, int M, int N, const UmmaEpilogue& ep,
                  cudaStream_t st) {
   Maps* mp = (Maps*)u.tmaps;
@@ -771,7 +777,7 @@ int umma_gemm_nt(std::string* err, UmmaLatent& u, int a_which, int b_which, floa
   w.ntm = M / BM; w.ntn = N / BN; w.nsplit = 1; w.total = w.ntm * w.ntn;
   w.total_kb = u.m / BK; w.kb_per_split = w.total_kb;
   w.tri_mode = (b_which == UM_LINV || b_which == UM_X) ? 1 : 0;
-  const int grid = w.total < sm_count() ? w.total : sm_count();
+  const int grid = w.total < grid_cap() ? w.total : grid_cap();
   if (u.v2) {
     // v2 & 2: keep the in-kernel split of the right operand (A/B experiment); otherwise L^-1 / X arrive pre-split
     const int sp = (b_which == UM_LINV) ? 0 : (b_which == UM_X) ? 1 : -1;

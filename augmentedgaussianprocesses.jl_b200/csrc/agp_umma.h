@@ -56,6 +56,8 @@ int umma_scale_transpose(std::string* err, UmmaLatent& u, const float* V, const 
 // Gpart[s] = sum_{b in split s} U_b U_b^T (full symmetric tiles) ; *n_split in: capacity, out: used
 // per-step chain launches carry the programmatic-dependent-launch attribute when on (set per call site by the engine)
 void umma_set_pdl(bool on);
+// cap of the persistent grid of umma_gemm_nt (0 = every SM): set around launches that run beside the persistent m x m tail
+void umma_set_grid_cap(int n);
 int umma_gram(std::string* err, UmmaLatent& u, float* Gpart, int B, int m, int* n_split, cudaStream_t st);
 
 // ---- EXPERIMENTAL, not on the product path (never run on a GPU yet): Newton-Schulz refinement of an m x m inverse ----
