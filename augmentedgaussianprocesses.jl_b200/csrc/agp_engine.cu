@@ -1471,7 +1471,8 @@ struct Engine : EngineBase {
       if (cudaMemcpyAsync(idx_prev, idx_cur, (size_t)B * 8, cudaMemcpyDeviceToDevice, st()) != cudaSuccess) s = AGP_ERR_CUDA;
       if (s == AGP_OK) s = prep_idx(nullptr, B, 0, 1);          // the cursor is bumped at the end of this step
       // the persistent tail holds one SM per CTA for its whole duration: keep the prefetch GEMM's persistent grid off those SMs
-      if (tail_variant == 3 && !ns_tail_now) umma_set_grid_cap(std::max(32, 148 - tail3_ctas(Ql)));
+      // (single latent only: with several latents the tail is a small share of the step and wants every SM itself)
+      if (tail_variant == 3 && Ql == 1 && !ns_tail_now) umma_set_grid_cap(std::max(32, 148 - tail3_ctas(Ql)));
       if (s == AGP_OK) s = moments_impl(false, B, true, 1);
       umma_set_grid_cap(0);
       if (s == AGP_OK && prec == AGP_PREC_TF32X3 && Ql == 1) {   // clear the next step's V X^T accumulators off the critical chain
