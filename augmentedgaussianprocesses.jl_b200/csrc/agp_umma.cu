@@ -26,6 +26,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 namespace agp {
 
@@ -241,6 +242,245 @@ umma_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int ab = lt & 1;
       const int row = wu.tile_m * BM + q * 32 + lane;
       float* cbase = C + (int64_t)wu.split * c_split_stride;
+      float* crow = cbase + (int64_t)row * ldc + (int64_t)wu.tile_n * BN;
+      double acc_sq = 0.0, acc_dot = 0.0;   // fused row statistics (fp64 sums, like rowstats_kernel)
+      if (wu.nkb > 0) {
+        mbar_wait(tmem_full(ab), (lt >> 1) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t rr[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + c * 32);
+          TMEM_LD32(taddr, rr);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (c == BN / 32 - 1) {                            // accumulator drained: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty(ab));
+          }
+          if (ep.mode != UMMA_EPI_STATS_ONLY) {
+            float4* dst = reinterpret_cast<float4*>(crow + c * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              dst[j] = make_float4(__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1]), __uint_as_float(rr[4 * j + 2]), __uint_as_float(rr[4 * j + 3]));
+          }
+          if (ep.mode == UMMA_EPI_STORE_SUMSQ || ep.mode == UMMA_EPI_STATS_ONLY) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const double v = (double)__uint_as_float(rr[j]);
+              acc_sq = fma(v, v, acc_sq);
+              if (ep.mode == UMMA_EPI_STATS_ONLY) acc_dot = fma(v, ep.tvec[wu.tile_n * BN + c * 32 + j], acc_dot);
+            }
+          }
+          if (ep.mode == UMMA_EPI_STORE_MIRROR && wu.tile_n != wu.tile_m) {
+            // symmetric product: also write the transposed tile (lanes = consecutive addresses)
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              cbase[(int64_t)(wu.tile_n * BN + c * 32 + j) * ldc + row] = __uint_as_float(rr[j]);
+          }
+        }
+        if (ep.mode == UMMA_EPI_STORE_SUMSQ) atomicAdd(ep.acc0 + row, acc_sq);
+        if (ep.mode == UMMA_EPI_STATS_ONLY) { atomicAdd(ep.acc0 + row, acc_sq); atomicAdd(ep.acc1 + row, acc_dot); }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+
+// One entry per latent GP of a grouped launch (device array): the operands' tensor maps and the epilogue targets.
+struct alignas(64) GemmGroup {
+  CUtensorMap tmA, tmB;
+  float* C; double* acc0; double* acc1; const double* tvec;
+};
+// work unit u of a grouped launch: `work` describes ONE group; units are ordered so that the longest k-extents of every group
+// come first (tri_mode 1) and the groups interleave, which keeps the persistent CTAs balanced under the snake order
+__device__ __forceinline__ WorkUnit get_unit_grouped(const GemmWork& w, int ngroups, int u, int& grp) {
+  int ul;
+  if (w.tri_mode == 1) {
+    const int per = w.ntm * ngroups;
+    const int p = u / per, rem = u - p * per;
+    grp = rem / w.ntm;
+    ul = p * w.ntm + (rem - grp * w.ntm);          // get_unit: tile_n = ntn - 1 - ul / ntm, tile_m = ul % ntm
+  } else if (w.tri_mode == 2) {
+    const int per = w.nsplit * ngroups;            // all splits of all groups' p-th upper tile are neighbours
+    const int p = u / per, rem = u - p * per;
+    grp = rem / w.nsplit;
+    ul = p * w.nsplit + (rem - grp * w.nsplit);    // get_unit: split = ul % nsplit, tile = ul / nsplit
+  } else {
+    grp = u / w.total;
+    ul = u - grp * w.total;
+  }
+  return get_unit(w, ul);
+}
+
+// Grouped variant of umma_gemm_nt_kernel: the same pipeline, one launch for the same-shaped products of several latent GPs
+// (tensor maps and epilogue targets come from a device array instead of kernel parameters).  Launch-bound products (C2 / C4
+// sized: ~8 us of fixed cost per launch against 0.65 us per k-block) become one long persistent loop.
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+umma_gemm_grouped_kernel(const GemmGroup* __restrict__ groups, const int ngroups, int64_t ldc, int64_t c_split_stride, const GemmWork work,
+                         const int epi_mode) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bars = smem_base + RING_BYTES;
+  auto raw_full = [&](int s) { return bars + 8u * s; };
+  auto raw_empty = [&](int s) { return bars + 8u * (RS + s); };
+  auto conv_full = [&](int s) { return bars + 8u * (2 * RS + s); };
+  auto mma_done = [&](int s) { return bars + 8u * (2 * RS + CS + s); };
+  auto tmem_full = [&](int b) { return bars + 8u * (2 * RS + 2 * CS + b); };
+  auto tmem_empty = [&](int b) { return bars + 8u * (2 * RS + 2 * CS + 2 + b); };
+  auto unit_conv_done = [&](int b) { return bars + 8u * (2 * RS + 2 * CS + 4 + b); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + RING_BYTES + 8 * (2 * RS + 2 * CS + 6));
+  const uint32_t conv_base = smem_base + RS * RAW_BYTES;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = gridDim.x, cta = blockIdx.x;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&groups[0].tmA); tma_prefetch_desc(&groups[0].tmB);
+    for (int s = 0; s < RS; ++s) { mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), NUM_CONV_THREADS); }
+    for (int s = 0; s < CS; ++s) { mbar_init(conv_full(s), NUM_CONV_THREADS); mbar_init(mma_done(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tmem_full(b), 1); mbar_init(tmem_empty(b), 4); mbar_init(unit_conv_done(b), NUM_CONV_THREADS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_ptr_smem)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  // programmatic dependent launch: barrier init / TMEM allocation above overlap the previous kernel of the chain
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer: raw fp32 tiles, one ring across all units of this CTA =====
+      int g = 0;
+      for (int r = 0;; ++r) {
+        const int u = unit_index(r, cta, G);
+        if (u >= work.total * ngroups) break;
+        int gq; const WorkUnit wu = get_unit_grouped(work, ngroups, u, gq);
+        for (int i = 0; i < wu.nkb; ++i, ++g) {
+          const int s = g % RS;
+          mbar_wait(raw_empty(s), ((g / RS) & 1) ^ 1);
+          const uint32_t dst = smem_base + s * RAW_BYTES;
+          mbar_expect_tx(raw_full(s), 2 * TILE_BYTES);
+          const int k = (wu.kb0 + i) * BK;
+          tma_load_2d(dst + 0 * TILE_BYTES, &groups[gq].tmA, raw_full(s), k, wu.tile_m * BM);
+          tma_load_2d(dst + 1 * TILE_BYTES, &groups[gq].tmB, raw_full(s), k, wu.tile_n * BN);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: accumulator buffer lt & 1, so the epilogue of unit lt overlaps the main loop of unit lt + 1 =====
+    int g = 0, lt = 0;
+    for (int r = 0;; ++r, ++lt) {
+      const int u = unit_index(r, cta, G);
+      if (u >= work.total * ngroups) break;
+      int gq; const WorkUnit wu = get_unit_grouped(work, ngroups, u, gq);
+      const int ab = lt & 1;
+      mbar_wait(tmem_empty(ab), ((lt >> 1) & 1) ^ 1);      // the epilogue two units ago has drained this accumulator
+      tc_fence_after();
+      const uint32_t acc = tmem_base + ab * BN;
+      for (int i = 0; i < wu.nkb; ++i, ++g) {
+        const int s = g % CS;
+        mbar_wait(conv_full(s), (g / CS) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t b_hi = conv_base + s * CONV_BYTES, b_lo = b_hi + TILE_BYTES;
+          const uint32_t a_hi = tmem_base + TMEM_A0 + s * 64, a_lo = a_hi + 32;
+#pragma unroll
+          for (int kk = 0; kk < BK / 8; ++kk) {
+            const uint32_t off = kk * 32;  // 8 tf32 = 32 bytes along K inside the 128B swizzle atom (B); 8 TMEM columns (A)
+            const uint64_t dbh = make_desc(b_hi + off), dbl = make_desc(b_lo + off);
+            tc_mma_tf32_ts(acc, a_lo + kk * 8, dbh, kIdesc, (i > 0 || kk > 0) ? 1u : 0u);  // small terms first
+            tc_mma_tf32_ts(acc, a_hi + kk * 8, dbl, kIdesc, 1u);
+            tc_mma_tf32_ts(acc, a_hi + kk * 8, dbh, kIdesc, 1u);
+          }
+          tc_commit(mma_done(s));                          // frees B_hi/B_lo and the TMEM A columns of this slot
+          if (i == wu.nkb - 1) tc_commit(tmem_full(ab));   // accumulator complete
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===== worker groups: raw -> hi / lo conversion of the group's units, then their epilogue =====
+    const int grp = (warp - 2) >> 2;
+    const int ct = (threadIdx.x - 64) & 127;         // 0..127 within the group
+    const int q = warp & 3;                          // TMEM lane quarter this warp may access
+    const int arow = q * 32 + lane;                  // A-tile row = TMEM lane handled by this thread
+    int g = 0, lt = 0;
+    for (int r = 0;; ++r, ++lt) {
+      const int u = unit_index(r, cta, G);
+      if (u >= work.total * ngroups) break;
+      int gq; const WorkUnit wu = get_unit_grouped(work, ngroups, u, gq);
+      if ((lt & 1) != grp) { g += wu.nkb; continue; }
+      // A group only sees the mbarrier phases of its own units.  Parity waits are unambiguous only within one phase, so
+      // do not start before the other group has issued every conversion of the previous unit (the TMA ring and the MMA
+      // warp are then at most one phase behind on every barrier this group is about to wait on).
+      if (lt > 0) mbar_wait(unit_conv_done(grp ^ 1), ((lt - 1) >> 1) & 1);
+      for (int i = 0; i < wu.nkb; ++i, ++g) {
+        const int rs = g % RS, s = g % CS;
+        mbar_wait(raw_full(rs), (g / RS) & 1);               // TMA landed the raw tiles
+        mbar_wait(mma_done(s), ((g / CS) & 1) ^ 1);          // previous MMAs on this slot's converted operands retired
+        tc_fence_after();
+        uint8_t* base = smem_gen + rs * RAW_BYTES;
+        uint8_t* cbase_s = smem_gen + RS * RAW_BYTES + s * CONV_BYTES;
+        {
+          // A: row `arow` of the raw tile (128 B, 16-byte chunks XOR-swizzled with row & 7) -> hi / lo -> TMEM
+          const float4* rowp = reinterpret_cast<const float4*>(base + arow * 128);
+          uint32_t h[32], l[32];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 v = rowp[c ^ (arow & 7)];
+            float t;
+            t = tf32_rna(v.x); h[4 * c + 0] = __float_as_uint(t); l[4 * c + 0] = __float_as_uint(tf32_rna(v.x - t));
+            t = tf32_rna(v.y); h[4 * c + 1] = __float_as_uint(t); l[4 * c + 1] = __float_as_uint(tf32_rna(v.y - t));
+            t = tf32_rna(v.z); h[4 * c + 2] = __float_as_uint(t); l[4 * c + 2] = __float_as_uint(tf32_rna(v.z - t));
+            t = tf32_rna(v.w); h[4 * c + 3] = __float_as_uint(t); l[4 * c + 3] = __float_as_uint(tf32_rna(v.w - t));
+          }
+          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + TMEM_A0 + s * 64;
+          TMEM_ST32(ta, h);
+          TMEM_ST32(ta + 32, l);
+        }
+        {
+          // B: raw -> hi / lo tiles at the same (swizzled) offsets in shared memory
+          const float4* raw = reinterpret_cast<const float4*>(base + 1 * TILE_BYTES);
+          float4* hi = reinterpret_cast<float4*>(cbase_s);
+          float4* lo = reinterpret_cast<float4*>(cbase_s + TILE_BYTES);
+#pragma unroll
+          for (int uu = 0; uu < TILE_BYTES / 16 / NUM_CONV_THREADS; ++uu) {
+            const int e = ct + uu * NUM_CONV_THREADS;
+            const float4 v = raw[e];
+            float4 h, l;
+            h.x = tf32_rna(v.x); l.x = tf32_rna(v.x - h.x);
+            h.y = tf32_rna(v.y); l.y = tf32_rna(v.y - h.y);
+            h.z = tf32_rna(v.z); l.z = tf32_rna(v.z - h.z);
+            h.w = tf32_rna(v.w); l.w = tf32_rna(v.w - h.w);
+            hi[e] = h; lo[e] = l;
+          }
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        mbar_arrive(raw_empty(rs));   // the raw tiles may be overwritten by the next TMA
+        mbar_arrive(conv_full(s));    // operands ready for the MMA warp
+      }
+      mbar_arrive(unit_conv_done(grp));
+      // ----- epilogue of this unit (the other group is already converting the next one) -----
+      const int ab = lt & 1;
+      const int row = wu.tile_m * BM + q * 32 + lane;
+      UmmaEpilogue ep;
+      ep.mode = epi_mode; ep.acc0 = groups[gq].acc0; ep.acc1 = groups[gq].acc1; ep.tvec = groups[gq].tvec; ep.cin = nullptr;
+      float* cbase = groups[gq].C + (int64_t)wu.split * c_split_stride;
       float* crow = cbase + (int64_t)row * ldc + (int64_t)wu.tile_n * BN;
       double acc_sq = 0.0, acc_dot = 0.0;   // fused row statistics (fp64 sums, like rowstats_kernel)
       if (wu.nkb > 0) {
@@ -829,6 +1069,78 @@ int umma_gram(std::string* err, UmmaLatent& u, float* Gpart, int B, int m, int* 
   *n_split = S;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(err, "umma gram", e);
+  return 0;
+}
+
+// ---- grouped launches (several latent GPs per launch) ----
+int umma_groups_build(std::string* err, UmmaGroups& gs, UmmaLatent* const* lats, int n, int a_which, int b_which, float* const* C,
+                      double* const* acc0, double* const* acc1, const double* const* tvec, cudaStream_t st) {
+  std::vector<GemmGroup> h((size_t)n);
+  for (int q = 0; q < n; ++q) {
+    Maps* mp = (Maps*)lats[q]->tmaps;
+    if (!mp) return fail(err, "grouped launch: latent without tensor maps");
+    h[q].tmA = a_which < 0 ? mp->ut : mp->raw[a_which];
+    h[q].tmB = b_which < 0 ? mp->ut : mp->raw[b_which];
+    h[q].C = C ? C[q] : nullptr;
+    h[q].acc0 = acc0 ? acc0[q] : nullptr; h[q].acc1 = acc1 ? acc1[q] : nullptr; h[q].tvec = tvec ? tvec[q] : nullptr;
+  }
+  cudaError_t e;
+  if (!gs.dev || gs.n != n) {
+    if (gs.dev) cudaFree(gs.dev);
+    gs.dev = nullptr;
+    if ((e = cudaMalloc(&gs.dev, (size_t)n * sizeof(GemmGroup))) != cudaSuccess) return fail(err, "cudaMalloc", e);
+  }
+  gs.n = n;
+  if ((e = cudaMemcpyAsync(gs.dev, h.data(), (size_t)n * sizeof(GemmGroup), cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail(err, "cudaMemcpy", e);
+  if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail(err, "cudaStreamSynchronize", e);
+  if ((e = cudaFuncSetAttribute(umma_gemm_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)) != cudaSuccess)
+    return fail(err, "cudaFuncSetAttribute", e);
+  return 0;
+}
+void umma_groups_free(UmmaGroups& gs) { if (gs.dev) cudaFree(gs.dev); gs.dev = nullptr; gs.n = 0; }
+
+int umma_gemm_nt_grouped(std::string* err, const UmmaGroups& gs, const UmmaLatent& u, int b_tri, int M, int N, int epi_mode, cudaStream_t st) {
+  if (!gs.dev || gs.n < 1) return fail(err, "grouped launch without groups");
+  if (M % BM || N % BN || u.m % BK) return fail(err, "shape not a multiple of the 128 x 128 x 32 tile");
+  GemmWork w{};
+  w.ntm = M / BM; w.ntn = N / BN; w.nsplit = 1; w.total = w.ntm * w.ntn;
+  w.total_kb = u.m / BK; w.kb_per_split = w.total_kb;
+  w.tri_mode = b_tri ? 1 : 0;
+  const int all = w.total * gs.n;
+  const int grid = all < grid_cap() ? all : grid_cap();
+  launch_chain(umma_gemm_grouped_kernel, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, (const GemmGroup*)gs.dev, gs.n, (int64_t)u.ldm, (int64_t)0, w, epi_mode);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(err, "umma_gemm_grouped_kernel", e);
+  return 0;
+}
+
+int umma_gram_grouped(std::string* err, const UmmaGroups& gs, const UmmaLatent& u, int B, int m, int* n_split, cudaStream_t st) {
+  if (!gs.dev || gs.n < 1) return fail(err, "grouped launch without groups");
+  if (B % BM || m % BN) return fail(err, "shape not a multiple of the tile");
+  const int total_kb = B / BK;
+  const int nt = m / BN, upper_tiles = nt * (nt + 1) / 2;
+  // split-K: wave-quantised cost of S slices per tile over all groups (+ a small charge per partial that combine_kernel re-reads)
+  const int sms = sm_count();
+  int bestS = 1; long best = -1;
+  for (int S = 1; S <= *n_split && S <= total_kb; ++S) {
+    const int per = (total_kb + S - 1) / S;
+    const int Su = (total_kb + per - 1) / per;
+    const long units = (long)upper_tiles * gs.n * Su;
+    const long cost = ((units + sms - 1) / sms) * (long)per + 2L * Su;
+    if (best < 0 || cost < best) { best = cost; bestS = Su; }
+  }
+  const int per = (total_kb + bestS - 1) / bestS;
+  const int S = (total_kb + per - 1) / per;
+  GemmWork w{};
+  w.ntm = nt; w.ntn = nt; w.nsplit = S; w.total = upper_tiles * S;
+  w.total_kb = total_kb; w.kb_per_split = per; w.tri_mode = 2;
+  const int all = w.total * gs.n;
+  const int grid = all < sms ? all : sms;
+  launch_chain(umma_gemm_grouped_kernel, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, (const GemmGroup*)gs.dev, gs.n, (int64_t)u.ldm, (int64_t)m * u.ldm, w,
+               (int)UMMA_EPI_STORE_MIRROR);
+  *n_split = S;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(err, "umma gram (grouped)", e);
   return 0;
 }
 

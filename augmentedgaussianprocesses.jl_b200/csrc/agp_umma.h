@@ -60,6 +60,19 @@ void umma_set_pdl(bool on);
 void umma_set_grid_cap(int n);
 int umma_gram(std::string* err, UmmaLatent& u, float* Gpart, int B, int m, int* n_split, cudaStream_t st);
 
+// ---- grouped launches: the same-shaped product of several latent GPs in ONE persistent launch (multi-latent models: the per-launch
+// fixed cost of a C2 / C4 sized product, ~8 us, is paid once; the persistent CTAs stay balanced over n x tiles work units) ----
+struct UmmaGroups { void* dev = nullptr; int n = 0; };   // device array, one entry (tensor maps + epilogue targets) per latent
+// a_which / b_which: UmmaMat of the operands (-1 = the latent's U^T buffer: Gram product); C / acc0 / acc1 / tvec: per-latent epilogue
+// targets (null arrays allowed).  Call again after a latent's buffers or tensor maps change.
+int umma_groups_build(std::string* err, UmmaGroups& gs, UmmaLatent* const* lats, int n, int a_which, int b_which, float* const* C,
+                      double* const* acc0, double* const* acc1, const double* const* tvec, cudaStream_t st);
+void umma_groups_free(UmmaGroups& gs);
+// C_q[M x N] = A_q B_q^T for every group q (b_tri: B_q lower triangular, k-blocks above the diagonal skipped); epi_mode: UmmaEpiMode
+int umma_gemm_nt_grouped(std::string* err, const UmmaGroups& gs, const UmmaLatent& shape, int b_tri, int M, int N, int epi_mode, cudaStream_t st);
+// Gpart_q[s] = split-K partials of U_q^T U_q for every group; *n_split in: capacity of the partial buffers, out: slices used
+int umma_gram_grouped(std::string* err, const UmmaGroups& gs, const UmmaLatent& shape, int B, int m, int* n_split, cudaStream_t st);
+
 // ---- EXPERIMENTAL, not on the product path (never run on a GPU yet): Newton-Schulz refinement of an m x m inverse ----
 // Y <- Y + Y (I - P Y) as two 3xTF32 tensor-core products per iteration (T = I - Y P, then Y' = Y + Y T^T), the candidate
 // replacement of the fp64 Cholesky tail once the Robbins-Monro step is small (profiles/r1/studies/newton_schulz_*.txt:
