@@ -104,6 +104,7 @@ struct EngineBase {
   virtual int64_t launch_count() = 0;
   virtual int time_kernel(int which, int reps, double* ms) = 0;
   virtual int use_graph(int on) = 0;
+  virtual void join_async() {}   // order the main stream behind the result stream of the pipelined asynchronous host-batch steps
 };
 
 struct agp_model {
@@ -377,6 +378,7 @@ struct Engine : EngineBase {
         L.knm_tc = true;
       }
     }
+    CKS(groups_init());
     CKS(dalloc(&Xb, (size_t)Bcap * Dp)); CKS(dalloc(&xxb, Bcap));
     CKS(dalloc(&idx_cur, Bcap)); CKS(dalloc(&xx_cur, Bcap)); CKS(dalloc(&idx_prev, Bcap));
     CK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
@@ -469,10 +471,15 @@ struct Engine : EngineBase {
       if (L.ns_alloc) umma_ns_free(L.ns);
       umma_knm_free(L.uk);
     }
+    umma_groups_free(grpV); umma_groups_free(grpS); umma_groups_free(grpG);
     for (void* q : peer_opened) cudaIpcCloseMemHandle(q);
     if (side) cudaStreamDestroy(side);
+    drop_graph_p();
     if (copy_stream) {
       cudaStreamDestroy(copy_stream);
+      if (res_stream) cudaStreamDestroy(res_stream);
+      if (ev_vfree) cudaEventDestroy(ev_vfree);
+      if (ev_p1) cudaEventDestroy(ev_p1);
       if (h_stat) cudaFreeHost(h_stat);
       for (int s = 0; s < 2; ++s) {
         cudaFree(pre_x[s]); cudaFree(pre_y[s]); cudaFree(pre_ycls[s]);
@@ -480,6 +487,8 @@ struct Engine : EngineBase {
         if (ev_h2d[s]) cudaEventDestroy(ev_h2d[s]);
         if (ev_free[s]) cudaEventDestroy(ev_free[s]);
         if (ev_done[s]) cudaEventDestroy(ev_done[s]);
+        if (ev_xfree[s]) cudaEventDestroy(ev_xfree[s]);
+        if (ev_step[s]) cudaEventDestroy(ev_step[s]);
       }
     }
     if (ev_fork) cudaEventDestroy(ev_fork);
@@ -494,6 +503,7 @@ struct Engine : EngineBase {
     if (bytes <= stage_bytes) return AGP_OK;
     if (stage) cudaFree(stage);
     if (gexec_b) { cudaGraphExecDestroy(gexec_b); gexec_b = nullptr; }   // the host-batch graph reads from the staging buffer
+    drop_graph_p();
     stage = nullptr; stage_bytes = 0;
     CK(cudaMalloc(&stage, bytes));
     stage_bytes = bytes;
@@ -759,8 +769,77 @@ struct Engine : EngineBase {
   // Also the whole of _predict_f (training/predictions.jl:25-50): mu* = k* (K \ mu) = V* mu_v and
   // sigma2* = kdiag + jitter - diag(k* A k*^T) = Ktilde* + rowsum((V* Sigma_v) .* V*).
   // stages: 1 = kernel matrices (Knm, V [+ sum V^2]), 2 = V X^T + row statistics, 3 = both
+  // ---- grouped tcgen05 launches: with >= 2 owned latents (tf32x3) each of the three B x m x m products of a step is ONE persistent
+  // launch over all owned latents (umma_gemm_grouped_kernel) instead of one launch per latent ----
+  UmmaGroups grpV, grpS, grpG;
+  bool use_groups = false;
+  int groups_init() {
+    use_groups = false;
+    if (prec != AGP_PREC_TF32X3 || Ql < 2 || is_vgp || getenv("AGP_NO_GROUPED")) return AGP_OK;
+    std::vector<UmmaLatent*> lp; std::vector<float*> cV, cG; std::vector<double*> a0V, a0S, a1S; std::vector<const double*> tv;
+    for (auto& L : lat) {
+      lp.push_back(&L.um); cV.push_back((float*)(void*)L.V); cG.push_back((float*)(void*)L.Gpart);
+      a0V.push_back(L.racc); a0S.push_back(L.racc + ldB); a1S.push_back(L.racc + 2 * ldB); tv.push_back(L.tvec);
+    }
+    CKS(umma_groups_build(ctx_err(), grpV, lp.data(), Ql, UM_KNM, UM_LINV, cV.data(), a0V.data(), nullptr, nullptr, st()));
+    CKS(umma_groups_build(ctx_err(), grpS, lp.data(), Ql, UM_V, UM_X, nullptr, a0S.data(), a1S.data(), tv.data(), st()));
+    CKS(umma_groups_build(ctx_err(), grpG, lp.data(), Ql, -1, -1, cG.data(), nullptr, nullptr, nullptr, st()));
+    use_groups = true;
+    return AGP_OK;
+  }
+  int moments_rows_grouped(const T* Xsrc, const T* xsrc, const int64_t* gather, int B, bool fresh_kernel_matrices, double* mean_out,
+                           double* var_out, int64_t out_ld, int stages) {
+    if (stages & 1) {
+      ph_begin(PH_KMAT);
+      for (int q = 0; q < Ql; ++q) {
+        Latent& L = lat[q];
+        if (L.knm_tc) {
+          CKS(umma_knm(ctx_err(), L.uk, (const float*)(const void*)Xsrc, Dp, Dp, gather, (const float*)(const void*)(gather ? xx_cur : xsrc),
+                       (const float*)(const void*)L.zz, B, L.kind, L.scale * L.scale, L.variance, st()));
+        } else {
+          GemmParams<T> g{};
+          g.A = Xsrc; g.lda = Dp; g.a_gather = gather; g.B = L.Z; g.ldb = Dp; g.C = L.Knm; g.ldc = ldm;
+          g.M = B; g.N = m; g.K = D; g.alpha = 1.0;
+          g.xx = gather ? xx_cur : xsrc; g.xx_direct = 1; g.zz = L.zz; g.scale2 = L.scale * L.scale; g.variance = L.variance; g.kernel_kind = L.kind;
+          gemm_simt_launch<T, false, false, EPI_KERNELFN>(g, 1, st());
+        }
+        ++launches;
+        CK(cudaMemsetAsync(L.racc, 0, ldB * sizeof(double), st()));
+      }
+      ph_end();
+      ph_begin(PH_KAPPA);
+      CKS(umma_gemm_nt_grouped(ctx_err(), grpV, lat[0].um, 1, B, m, UMMA_EPI_STORE_SUMSQ, st()));
+      ++launches;
+      ph_end();
+    }
+    if (!(stages & 2)) { CK(cudaGetLastError()); return AGP_OK; }
+    ph_begin(PH_KSIGMA);
+    for (int q = 0; q < Ql; ++q) CK(cudaMemsetAsync(lat[q].racc + ldB, 0, 2 * ldB * sizeof(double), st()));
+    racc2_precleared = false;
+    CKS(umma_gemm_nt_grouped(ctx_err(), grpS, lat[0].um, 1, B, m, UMMA_EPI_STATS_ONLY, st()));
+    ++launches;
+    ph_end();
+    ph_begin(PH_ROWSTATS);
+    for (int q = 0; q < Ql; ++q) {
+      Latent& L = lat[q];
+      launch_chain(rowfinish_kernel, dim3((B + 255) / 256), dim3(256), 0, (const double*)L.racc, (const double*)(L.racc + ldB),
+                   (const double*)(L.racc + 2 * ldB), B, L.variance + jitter, L.Ktilde, mean_out + (size_t)q * out_ld,
+                   var_out + (size_t)q * out_ld, status, fresh_kernel_matrices ? 1 : 0,
+                   (const int64_t*)((peer && mean_out == mean_f + (size_t)qbeg * ldB) ? d_xepoch : nullptr), par_stride);
+      ++launches;
+    }
+    ph_end();
+    CK(cudaGetLastError());
+    return AGP_OK;
+  }
+  bool groups_now() const {
+    if (!use_groups || vgp_identity) return false;
+    for (auto& L : lat) if (!L.factor_valid) return false;
+    return true;
+  }
   int moments_rows(const T* Xsrc, const T* xsrc, const int64_t* gather, int B, bool fresh_kernel_matrices, double* mean_out,
                    double* var_out, int64_t out_ld, bool need_var, int stages = 3) {
+    if (groups_now()) return moments_rows_grouped(Xsrc, xsrc, gather, B, fresh_kernel_matrices, mean_out, var_out, out_ld, stages);
     for (int q = 0; q < Ql; ++q) {
       Latent& L = lat[q];
       if ((stages & 1) && vgp_identity) {
@@ -1192,6 +1271,7 @@ struct Engine : EngineBase {
       }
     }
     ph_end();
+    const bool grp = use_groups && prec == AGP_PREC_TF32X3;
     for (int q = 0; q < Ql; ++q) {
       Latent& L = lat[q];
       ph_begin(PH_GRADMU);
@@ -1209,6 +1289,7 @@ struct Engine : EngineBase {
         ++launches;
         ph_end();
       }
+      if (grp) { umma_set_pdl(false); continue; }     // the Gram products of all owned latents follow in one grouped launch
       ph_begin(PH_GRAM);
       int ns = n_split;
       if (prec == AGP_PREC_TF32X3) {
@@ -1224,6 +1305,16 @@ struct Engine : EngineBase {
         ++launches;
       }
       L.gram_splits = ns;
+      ph_end();
+    }
+    if (grp) {
+      ph_begin(PH_GRAM);
+      int ns = n_split;
+      umma_set_pdl(tail_pdl && !prof);
+      CKS(umma_gram_grouped(ctx_err(), grpG, lat[0].um, B, m, &ns, st()));
+      umma_set_pdl(false);
+      ++launches;
+      for (auto& L : lat) L.gram_splits = ns;
       ph_end();
     }
     CK(cudaGetLastError());
@@ -1274,7 +1365,8 @@ struct Engine : EngineBase {
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st();
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = (tail_pdl && !prof) ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = (tail_pdl && !prof && !chain_break) ? 1 : 0;
+    chain_break = false;
     cudaLaunchKernelEx(&cfg, kern, args...);
   }
   template <typename K>
@@ -1442,6 +1534,7 @@ struct Engine : EngineBase {
   void drop_graph() {
     if (gexec) { cudaGraphExecDestroy(gexec); gexec = nullptr; }
     if (gexec_b) { cudaGraphExecDestroy(gexec_b); gexec_b = nullptr; }
+    drop_graph_p();
     gB = -1;
   }
 
@@ -1637,13 +1730,26 @@ struct Engine : EngineBase {
   void* pre_x[2] = {nullptr, nullptr}; double* pre_y[2] = {nullptr, nullptr}; int* pre_ycls[2] = {nullptr, nullptr};
   double* h_res[2] = {nullptr, nullptr}; int* h_stat = nullptr;
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
-  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_xfree[2] = {nullptr, nullptr}, ev_step[2] = {nullptr, nullptr}, ev_vfree = nullptr, ev_p1 = nullptr;
+  cudaStream_t copy_stream = nullptr, res_stream = nullptr;
   int64_t n_tickets = 0;
+  int res_pending = -1;    // slot whose result kernels (result stream) the main stream has not been ordered behind yet
+  // pipelined variant: three graphs -- [0] stage 1 on the side stream, [1] statistics + local updates + Gram, [2] natural-parameter update + tail
+  cudaGraphExec_t gexec_p[3] = {nullptr, nullptr, nullptr}; int64_t g_launches_p[3] = {0, 0, 0};
+  int gB_p = -1, gkey_p = -1; double grho_p = -1;
+  bool chain_break = false;   // the next launch_chain call has no kernel predecessor in its graph: no programmatic edge
+  void drop_graph_p() {
+    for (int i = 0; i < 3; ++i) if (gexec_p[i]) { cudaGraphExecDestroy(gexec_p[i]); gexec_p[i] = nullptr; }
+    gB_p = -1;
+  }
   int async_init() {
     if (copy_stream) return AGP_OK;
     CK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&res_stream, cudaStreamNonBlocking));
     CK(cudaMallocHost((void**)&h_stat, 2 * sizeof(int)));
     h_stat[0] = h_stat[1] = 0;
+    CK(cudaEventCreateWithFlags(&ev_vfree, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ev_p1, cudaEventDisableTiming));
     for (int s = 0; s < 2; ++s) {
       CK(cudaMalloc(&pre_x[s], (size_t)Bcap * D * 8));
       CK(cudaMalloc((void**)&pre_y[s], (size_t)nT * ldB * sizeof(double)));
@@ -1652,19 +1758,145 @@ struct Engine : EngineBase {
       CK(cudaEventCreateWithFlags(&ev_h2d[s], cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&ev_free[s], cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&ev_done[s], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&ev_xfree[s], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&ev_step[s], cudaEventDisableTiming));
     }
     return AGP_OK;
   }
+  void join_async() override {
+    if (res_pending < 0) return;
+    cudaStreamWaitEvent(ctx->stream, ev_done[res_pending], 0);
+    res_pending = -1;
+  }
+  // one piece of the pipelined step on stream s: replayed from its graph when agp_use_graph is on, launched eagerly otherwise
+  template <typename F>
+  int run_piece(int which, cudaStream_t s, F body) {
+    cudaStream_t saved = cur_stream;
+    cur_stream = (s == ctx->stream) ? nullptr : s;
+    int rc = AGP_OK;
+    if (want_graph && !prof) {
+      if (!gexec_p[which]) {
+        cudaGraph_t graph = nullptr;
+        const int64_t l0 = launches;
+        cudaError_t ce = cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed);
+        if (ce != cudaSuccess) { cur_stream = saved; ctx->err = std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(ce); return AGP_ERR_CUDA; }
+        capturing = true; chain_break = (which == 2);   // combine_kernel is the first node of graph 2
+        rc = body();
+        capturing = false; chain_break = false;
+        ce = cudaStreamEndCapture(s, &graph);
+        if (rc == AGP_OK && ce != cudaSuccess) { ctx->err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce); rc = AGP_ERR_CUDA; }
+        if (rc == AGP_OK) {
+          g_launches_p[which] = launches - l0;
+          launches = l0;
+          ce = cudaGraphInstantiate(&gexec_p[which], graph, 0);
+          if (ce != cudaSuccess) { ctx->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce); rc = AGP_ERR_CUDA; gexec_p[which] = nullptr; }
+        }
+        if (graph) cudaGraphDestroy(graph);
+        if (rc != AGP_OK) { cur_stream = saved; return rc; }
+      }
+      cudaError_t ce = cudaGraphLaunch(gexec_p[which], s);
+      if (ce != cudaSuccess) { ctx->err = std::string("cudaGraphLaunch: ") + cudaGetErrorString(ce); rc = AGP_ERR_CUDA; }
+      launches += g_launches_p[which];
+    } else {
+      rc = body();
+    }
+    cur_stream = saved;
+    return rc;
+  }
+  // Pipelined form (default): the kernel matrices of batch i (row conversion, K_nm, V = K_nm L^-T: they do not depend on the
+  // posterior) are built on the side stream while the m x m tail of step i-1 still runs on the main stream -- the host-batch
+  // counterpart of step_pool's prefetch -- and the result read-back (mu_v = X^T t, mu = L mu_v, device -> pinned host) runs on a
+  // third stream beside the next step's statistics product.  Ordering:
+  //   copy stream : wait(x, y slot free) -> H2D x, y -> ev_h2d
+  //   side stream : wait(ev_h2d, ev_vfree = step i-1 is done reading V) -> x slot -> staging -> [graph 0] -> ev_p1
+  //   main stream : y slot -> yb; wait(ev_p1) -> [graph 1] -> ev_vfree -> wait(result kernels of step i-1) -> [graph 2] -> ev_step
+  //   result strm : wait(ev_step) -> mu -> h_res[slot], status -> h_stat[slot] -> ev_done
+  int step_batch_async_pipelined(const void* xbh, int x_dtype, int x_layout, const void* const* ybh, int y_kind, int B, double rho, int64_t* ticket) {
+    const int slot = (int)(n_tickets & 1);
+    const size_t es = x_dtype == AGP_DTYPE_F64 ? 8 : 4;
+    const int key = x_dtype * 2 + x_layout;
+    if (!have_K) { ctx->err = "agp_refresh_K must be called before a step"; return AGP_ERR_STATE; }
+    if (prec == AGP_PREC_TF32X3 && (B % 128)) BAD("TF32X3 precision needs B % 128 == 0");
+    CKS(ensure_stage((size_t)Bcap * D * 8));
+    if (gB_p != B || grho_p != rho || gkey_p != key) { drop_graph_p(); gB_p = B; grho_p = rho; gkey_p = key; }
+    h_mu_valid = false;
+    // copy stream
+    CK(cudaStreamWaitEvent(copy_stream, ev_free[slot], 0));
+    CK(cudaStreamWaitEvent(copy_stream, ev_xfree[slot], 0));
+    CK(cudaMemcpyAsync(pre_x[slot], xbh, (size_t)B * D * es, cudaMemcpyHostToDevice, copy_stream));
+    if (y_kind == AGP_Y_CLASS) CK(cudaMemcpyAsync(pre_ycls[slot], ybh[0], B * sizeof(int), cudaMemcpyHostToDevice, copy_stream));
+    else for (int t = 0; t < nT; ++t) CK(cudaMemcpyAsync(pre_y[slot] + (size_t)t * ldB, ybh[t], B * sizeof(double), cudaMemcpyHostToDevice, copy_stream));
+    CK(cudaEventRecord(ev_h2d[slot], copy_stream));
+    // side stream: stage 1
+    CK(cudaStreamWaitEvent(side, ev_h2d[slot], 0));
+    CK(cudaStreamWaitEvent(side, ev_vfree, 0));
+    CK(cudaMemcpyAsync(stage, pre_x[slot], (size_t)B * D * es, cudaMemcpyDeviceToDevice, side));
+    CK(cudaEventRecord(ev_xfree[slot], side));
+    CKS(run_piece(0, side, [&]() -> int {
+      const int64_t sld = x_layout == AGP_LAYOUT_ROWMAJOR ? D : B;
+      const int bl = (B + 255) / 256;
+      if (x_dtype == AGP_DTYPE_F64) convert_rows_kernel<double, T><<<bl, 256, 0, st()>>>((const double*)stage, x_layout, sld, B, D, Xb, Dp, xxb);
+      else convert_rows_kernel<float, T><<<bl, 256, 0, st()>>>((const float*)stage, x_layout, sld, B, D, Xb, Dp, xxb);
+      ++launches;
+      CKS(moments_impl(true, B, true, 1));
+      if (prec == AGP_PREC_TF32X3 && Ql == 1) CK(cudaMemsetAsync(lat[0].racc + ldB, 0, 2 * ldB * sizeof(double), st()));   // the V X^T accumulators, off the critical chain
+      return AGP_OK;
+    }));
+    CK(cudaEventRecord(ev_p1, side));
+    // main stream
+    if (y_kind == AGP_Y_CLASS) CK(cudaMemcpyAsync(ycls, pre_ycls[slot], B * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+    else for (int t = 0; t < nT; ++t) CK(cudaMemcpyAsync(yb + (size_t)t * ldB, pre_y[slot] + (size_t)t * ldB, B * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaEventRecord(ev_free[slot], ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->stream, ev_p1, 0));
+    curB = B; cur_from_batch = true; kernel_matrices_stale = false; prefetched = false;
+    CKS(run_piece(1, ctx->stream, [&]() -> int {
+      fuse_lik_next = can_fuse_lik(); fuse_from_batch = true; lik_fused = false;
+      racc2_precleared = (prec == AGP_PREC_TF32X3 && Ql == 1);
+      int s2 = moments_impl(true, B, true, 2);
+      fuse_lik_next = false;
+      CKS(s2);
+      return step_update_a(rho);
+    }));
+    CK(cudaEventRecord(ev_vfree, ctx->stream));
+    join_async();                                   // the result kernels of the previous step still read X / t
+    CKS(run_piece(2, ctx->stream, [&]() -> int { return step_update_b(rho); }));
+    CK(cudaEventRecord(ev_step[slot], ctx->stream));
+    for (auto& L : lat) L.muv_valid = false;
+    have_step = true;
+    // result stream
+    CK(cudaStreamWaitEvent(res_stream, ev_step[slot], 0));
+    {
+      Latent& L = lat[0];
+      cudaStream_t saved = cur_stream;
+      cur_stream = res_stream;
+      ensure_muv(L);
+      symv_kernel<<<(m * 32 + 255) / 256, 256, 0, st()>>>(L.Lc, mp, m, L.muv, L.mu0 + mp);
+      ++launches;
+      cur_stream = saved;
+      CK(cudaMemcpyAsync(h_res[slot], L.mu0 + mp, m * sizeof(double), cudaMemcpyDeviceToHost, res_stream));
+      CK(cudaMemcpyAsync(h_stat + slot, status, sizeof(int), cudaMemcpyDeviceToHost, res_stream));
+    }
+    CK(cudaEventRecord(ev_done[slot], res_stream));
+    res_pending = slot;
+    CK(cudaGetLastError());
+    *ticket = n_tickets++;
+    ++h_steps;
+    return AGP_OK;
+  }
+  bool async_pipelined_ok() const { return pipeline && !prof && ns_iters <= 0 && !peer && !getenv("AGP_ASYNC_SERIAL"); }
   int step_batch_async(const void* xbh, int x_dtype, int x_layout, const void* const* ybh, int y_kind, int B, double rho, int64_t* ticket) override {
     if (!xbh || !ybh || !ticket) BAD("null batch / ticket");
     if (B < 1 || B > Bcap) BAD("The size of mini-batch is incorrect (negative or bigger than the batch capacity)");
     if (is_lsm != (y_kind == AGP_Y_CLASS)) BAD("label kind does not match the likelihood");
     if ((x_dtype != 0 && x_dtype != 1) || (x_layout != 0 && x_layout != 1)) BAD("bad dtype/layout");
     CKS(async_init());
+    if (async_pipelined_ok()) return step_batch_async_pipelined(xbh, x_dtype, x_layout, ybh, y_kind, B, rho, ticket);
+    join_async();
     const int slot = (int)(n_tickets & 1);
     const size_t es = x_dtype == AGP_DTYPE_F64 ? 8 : 4;
     // copy stream: this slot's previous batch has been consumed (its step finished), then host -> pre-staging
     CK(cudaStreamWaitEvent(copy_stream, ev_free[slot], 0));
+    CK(cudaStreamWaitEvent(copy_stream, ev_xfree[slot], 0));
     CK(cudaMemcpyAsync(pre_x[slot], xbh, (size_t)B * D * es, cudaMemcpyHostToDevice, copy_stream));
     std::vector<const void*> yp((size_t)std::max(nT, 1));
     if (y_kind == AGP_Y_CLASS) {
@@ -2115,7 +2347,8 @@ void agp_model_destroy(agp_model* model) {
   delete model;
 }
 
-#define ENG(m) if (!(m) || !(m)->eng) return AGP_ERR_BAD_ARG; EngineBase* e = (m)->eng; cudaSetDevice(e->ctx->device)
+#define ENG0(m) if (!(m) || !(m)->eng) return AGP_ERR_BAD_ARG; EngineBase* e = (m)->eng; cudaSetDevice(e->ctx->device)
+#define ENG(m) ENG0(m); e->join_async()
 
 int agp_data_upload(agp_model* model, const void* X, int x_dtype, int x_layout, int64_t n, const void* const* y, int y_kind) {
   ENG(model); return e->data_upload(X, x_dtype, x_layout, n, y, y_kind);
@@ -2147,9 +2380,9 @@ int agp_step_batch(agp_model* model, const void* xb, int x_dtype, int x_layout, 
 int agp_sync(agp_model* model) { ENG(model); return e->sync_status(); }
 int agp_step_batch_async(agp_model* model, const void* xb, int x_dtype, int x_layout, const void* const* yb, int y_kind, int32_t B,
                          double rho, int64_t* ticket) {
-  ENG(model); return e->step_batch_async(xb, x_dtype, x_layout, yb, y_kind, B, rho, ticket);
+  ENG0(model); return e->step_batch_async(xb, x_dtype, x_layout, yb, y_kind, B, rho, ticket);
 }
-int agp_result_wait(agp_model* model, int64_t ticket, double* mu) { ENG(model); return e->result_wait(ticket, mu); }
+int agp_result_wait(agp_model* model, int64_t ticket, double* mu) { ENG0(model); return e->result_wait(ticket, mu); }
 int agp_step_moments_async(agp_model* model, const int64_t* idx, int32_t B, int32_t base) {
   ENG(model); return e->step_moments(idx, B, base, false);
 }

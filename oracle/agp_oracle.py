@@ -989,6 +989,173 @@ def _view_y(y, idx):
 
 
 # --------------------------------------------------------------------------------------
+# OnlineSVGP (models/OnlineSVGP.jl, training/onlinetraining.jl, analyticVI.jl:183-218, KLdivergences.jl:37-54)
+# --------------------------------------------------------------------------------------
+class OnlineVarLatent:
+    """gpblocks/latentgp.jl:92-131 + posterior.jl:39-55 (OnlineVarPosterior).  Z / Za start empty (OnlineSVGP.jl:60-62)."""
+
+    def __init__(self, kernel: Kernel, mu0=None):
+        self.kernel = kernel
+        self.mu0_const = 0.0 if mu0 is None else float(mu0)     # ZeroMean / ConstantMean evaluated at Z
+        self.Z = np.zeros((0, 0))
+        self.Za = np.zeros((0, 0))
+        self.dim = 0
+        self.mu = np.zeros(0); self.Sigma = np.zeros((0, 0)); self.eta1 = np.zeros(0); self.eta2 = np.zeros((0, 0))
+
+    @property
+    def mu0(self):
+        return np.full(self.dim, self.mu0_const)
+
+
+class OnlineSVGP:
+    """models/OnlineSVGP.jl:1-78 with `optimiser = nothing` semantics, AnalyticVI only (OnlineSVGP.jl:46; the stochastic branch of
+    train! refers to an undefined variable, onlinetraining.jl:54, so it cannot run in the reference either).
+
+    INJECTED: the inducing set.  The reference picks it with the un-vendored InducingPoints.jl (`inducingpoints(Zalg, x)`,
+    `updateZ`, and `remove_point(Random.GLOBAL_RNG, ...)` -- onlinetraining.jl:157,175,193), i.e. from Julia's global RNG; like the
+    minibatch indices of `train`, the set to use for a batch is an argument of `train_online` (the result of those calls)."""
+
+    def __init__(self, kernel: Kernel, likelihood, inference: AnalyticVI, mean=None, jitter=JITTER_F64):
+        if inference.stoch:
+            raise ValueError("The inference object should be of type `AnalyticVI`")
+        self.likelihood = likelihood
+        self.inference = inference
+        self.jitter = jitter
+        self.f = [OnlineVarLatent(kernel, mean) for _ in range(likelihood.n_latent)]
+        self.trained = False
+
+    # -- states.jl:61-71,86-98
+    def init_state(self):
+        B = self.inference.batchsize
+        opt_state = [dict(prevL=0.0, invD=np.eye(gp.dim), preveta1=np.zeros(gp.dim)) for gp in self.f]
+        return dict(local_vars=init_local_vars(self.likelihood, B), opt_state=opt_state, kernel_matrices=None)
+
+    # -- latentgp.jl:217-237 (compute_kappa of an OnlineVarLatent) behind training.jl:187-208
+    def compute_kernel_matrices(self, state, x, update=False):
+        inf = self.inference
+        if inf.HyperParametersUpdated or update:
+            kms = []
+            for gp in self.f:
+                L = compute_K(gp, self.jitter)
+                k = gp.dim
+                if gp.Za.shape[0] == 0:
+                    Kab = np.zeros((k, k)); kappa_a = np.eye(k); Ktilde_a = np.zeros((k, k))
+                else:
+                    Kab = kernelmatrix(gp.kernel, gp.Za, gp.Z)
+                    kappa_a = sla.cho_solve((L, True), Kab.T).T
+                    Ka = kernelmatrix(gp.kernel, gp.Za) + self.jitter * np.eye(gp.Za.shape[0])
+                    Ktilde_a = Ka - kappa_a @ Kab.T
+                kms.append({"L": L, "Kab": Kab, "kappa_a": kappa_a, "Ktilde_a": Ktilde_a, **compute_kappa(gp, x, L, self.jitter)})
+            state["kernel_matrices"] = kms
+        inf.HyperParametersUpdated = False
+        return state
+
+    # -- onlinetraining.jl:217-236: K, Knm, kappa, Ktilde against the PREVIOUS inducing set (merged over the existing entries)
+    def compute_old_matrices(self, state, x):
+        kms = state["kernel_matrices"] or [dict() for _ in self.f]
+        out = []
+        for gp, km in zip(self.f, kms):
+            old = SparseVarLatent(gp.Za, gp.kernel)
+            L = compute_K(old, self.jitter)
+            out.append({**km, "L": L, **compute_kappa(old, x, L, self.jitter)})
+        state["kernel_matrices"] = out
+        return state
+
+    def moments(self, state):
+        kms = state["kernel_matrices"]
+        return (np.stack([mean_f(gp, km) for gp, km in zip(self.f, kms)]), np.stack([var_f(gp, km) for gp, km in zip(self.f, kms)]))
+
+    # -- analyticVI.jl:183-203 + 215-218, inference.jl:25-28
+    def natural_gradient_and_update(self, state, gmu, gS):
+        for k, (gp, km, os_) in enumerate(zip(self.f, state["kernel_matrices"], state["opt_state"])):
+            L, kappa, kappa_a = km["L"], km["kappa"], km["kappa_a"]
+            Kinv = sla.cho_solve((L, True), np.eye(gp.dim))
+            gp.eta1 = sla.cho_solve((L, True), gp.mu0) + kappa.T @ gmu[k] + kappa_a.T @ os_["preveta1"]
+            gp.eta2 = -_symmetric_upper(rho_kdiagthetak(1.0, kappa, gS[k]) + kappa_a.T @ os_["invD"] @ kappa_a / 2.0 + Kinv / 2.0)
+            global_update(gp)
+
+    # -- onlinetraining.jl:146-152 -> analyticVI.jl:62-111
+    def update_parameters(self, state, x, y):
+        state = self.compute_kernel_matrices(state, x)
+        mu, var = self.moments(state)
+        lv = local_updates(state["local_vars"], self.likelihood, y, mu, var)
+        self.natural_gradient_and_update(state, grad_E_mu(self.likelihood, y, lv), grad_E_Sigma(self.likelihood, y, lv))
+        return state
+
+    # -- KLdivergences.jl:37-54
+    def extraKL(self, state):
+        tot = 0.0
+        for gp, os_, km in zip(self.f, state["opt_state"], state["kernel_matrices"]):
+            ka_mu = km["kappa_a"] @ gp.mu
+            KLa = os_["prevL"]
+            KLa += -(trace_ABt(os_["invD"], km["Ktilde_a"]) + trace_ABt(os_["invD"], km["kappa_a"] @ gp.Sigma @ km["kappa_a"].T)) / 2.0
+            KLa += float(os_["preveta1"] @ ka_mu) - float(ka_mu @ (os_["invD"] @ ka_mu)) / 2.0
+            tot += KLa
+        return float(tot)
+
+    # -- analyticVI.jl:255-274
+    def ELBO(self, state, y):
+        inf = self.inference
+        mu, var = self.moments(state)
+        tot = inf.rho * expec_loglikelihood(self.likelihood, y, mu, var, state["local_vars"])
+        tot -= sum(GaussianKL(gp.mu, gp.mu0, gp.Sigma, km["L"]) for gp, km in zip(self.f, state["kernel_matrices"]))
+        tot -= inf.rho * AugmentedKL(self.likelihood, state["local_vars"], y)
+        tot -= self.extraKL(state)
+        return float(tot)
+
+
+def train_online(model: OnlineSVGP, X, y, Z, state=None, iterations=20):
+    """training/onlinetraining.jl:36-144 for one batch (X, y).  `Z` = the inducing set the reference's InducingPoints calls would
+    return for this batch (injected, see OnlineSVGP)."""
+    if iterations <= 0:
+        raise ValueError("Number of iterations should be positive")
+    X = np.asarray(X, dtype=np.float64)
+    Z = np.asarray(Z, dtype=np.float64)
+    y = treat_labels(y, model.likelihood)
+    inf = model.inference
+    inf.batchsize = X.shape[0]                                     # onlinetraining.jl:57 (non-stochastic)
+    if inf.n_iter == 0:
+        # init_online_model (onlinetraining.jl:185-203): fresh posterior of the size of Z, no previous set
+        for gp in model.f:
+            gp.Z = Z.copy(); gp.dim = Z.shape[0]; gp.Za = np.zeros((0, Z.shape[1]))
+            gp.mu = np.zeros(gp.dim); gp.Sigma = np.eye(gp.dim); gp.eta1 = np.zeros(gp.dim); gp.eta2 = -0.5 * np.eye(gp.dim)
+        inf.HyperParametersUpdated = False
+    else:
+        # save_old_parameters! (onlinetraining.jl:164-183), then updateZs! (154-162)
+        for gp, os_, km in zip(model.f, state["opt_state"], state["kernel_matrices"]):
+            L = km["L"]
+            Kinv = sla.cho_solve((L, True), np.eye(L.shape[0]))
+            gp.Za = gp.Z.copy()
+            os_["invD"] = _symmetric_upper(-2.0 * gp.eta2 - Kinv)
+            os_["preveta1"] = gp.eta1.copy()
+            logdetK = 2.0 * np.sum(np.log(np.diag(L)))
+            os_["prevL"] = float((-np.linalg.slogdet(gp.Sigma)[1] + logdetK - gp.mu @ gp.eta1) / 2.0)
+            gp.Z = Z.copy(); gp.dim = Z.shape[0]
+        inf.HyperParametersUpdated = True
+    if state is None:
+        state = model.init_state()
+    for local_iter in range(1, iterations + 1):
+        if local_iter == 1:
+            # onlinetraining.jl:75-104: local updates with the PREVIOUS inducing set / posterior, natural gradient with the new one
+            if inf.n_iter == 0:
+                state = model.compute_kernel_matrices(state, X, True)
+            else:
+                state = model.compute_old_matrices(state, X)
+            mu, var = model.moments(state)
+            lv = local_updates(state["local_vars"], model.likelihood, y, mu, var)
+            gmu, gS = grad_E_mu(model.likelihood, y, lv), grad_E_Sigma(model.likelihood, y, lv)
+            state = model.compute_kernel_matrices(state, X, True)
+            model.natural_gradient_and_update(state, gmu, gS)
+        else:
+            state = model.update_parameters(state, X, y)
+        model.trained = True
+        inf.n_iter += 1
+    state = model.compute_kernel_matrices(state, X, True)
+    state["y_batch"] = y
+    return model, state
+
+
+# --------------------------------------------------------------------------------------
 # VGP (models/VGP.jl): full variational GP, AnalyticVI only (n x n)
 # --------------------------------------------------------------------------------------
 class VGP:

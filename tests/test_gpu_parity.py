@@ -654,3 +654,59 @@ def test_latent_sharded_two_gpus_match_single_gpu():
                            timeout=600)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         assert r.stdout.count("-> OK") == 2, r.stdout
+
+
+@pytest.mark.parametrize("use_graph,serial,prec", [(0, 0, "f64"), (1, 0, "f64"), (0, 1, "f64"), (1, 1, "f64"), (1, 0, "tf32x3"), (0, 0, "tf32x3")])
+def test_step_batch_async_matches_oracle_and_lagged_results(agp, use_graph, serial, prec, monkeypatch):
+    """agp_step_batch_async / agp_result_wait: host batches streamed without a per-step synchronisation must give the same
+    posterior as the oracle (f64 engine, 1e-8; tf32x3 2e-4), and every ticket must return the posterior mean AFTER its own step.
+    serial = 0: the pipelined form (stage 1 of batch i on the side stream under the tail of step i-1, results on a third stream);
+    serial = 1 (AGP_ASYNC_SERIAL): everything on the main stream."""
+    import ctypes as C
+    from problems import make_data, rel_fro
+    import agp_oracle as O
+
+    if serial:
+        monkeypatch.setenv("AGP_ASYNC_SERIAL", "1")
+    else:
+        monkeypatch.delenv("AGP_ASYNC_SERIAL", raising=False)
+    n, D, m, B, iters = (400, 4, 32, 128, 7) if prec == "f64" else (4000, 8, 128, 256, 9)
+    tol = 1e-8 if prec == "f64" else 2e-4
+    X, y, Z, mbs, F, rng = make_data("logistic", n, D, m, B, iters, seed=3)
+    sc = 1.0 / np.sqrt(D)
+    L = agp._lib
+    # oracle means after every iteration
+    mo = O.SVGP(O.Kernel("sqexp", scale=sc), O.LogisticLikelihood(), O.AnalyticSVI(B), Z)
+    st, mus = None, []
+    for it in range(iters):
+        mo, st = O.train(mo, X, y, 1, minibatches=[mbs[it]], state=st)
+        mus.append(mo.f[0].mu.copy())
+    me = agp.SVGP(agp.SqExponentialKernel() @ agp.ScaleTransform(sc), agp.LogisticLikelihood(), agp.AnalyticSVI(B), Z, precision=prec)
+    me, se = agp.train(me, X, y, 1, minibatches=mbs[:1])          # creates the engine, uploads, iteration 1
+    e = me._eng
+    e.ck(e.lib.agp_use_graph(e.model, use_graph))
+    keep, tickets, got = [], [], {}
+    mu = np.empty(m)
+    for it in range(1, iters):
+        xb = np.ascontiguousarray(X[mbs[it]])
+        yb = np.ascontiguousarray(y[mbs[it]], dtype=np.float64)
+        keep.append((xb, yb))                                       # the host buffers must stay alive until their ticket is waited for
+        arr = (C.c_void_p * 1)(yb.ctypes.data)
+        tk = C.c_int64(-1)
+        e.ck(e.lib.agp_step_batch_async(e.model, C.c_void_p(xb.ctypes.data), L.DTYPE_F64, L.LAYOUT_ROWMAJOR, arr, L.Y_REAL, B, n / B, C.byref(tk)))
+        tickets.append((it, tk.value))
+        if len(tickets) >= 2:                                        # read the previous step's result while this one runs
+            pit, ptk = tickets[-2]
+            e.ck(e.lib.agp_result_wait(e.model, ptk, L.dptr(mu)))
+            got[pit] = mu.copy()
+    pit, ptk = tickets[-1]
+    e.ck(e.lib.agp_result_wait(e.model, ptk, L.dptr(mu)))
+    got[pit] = mu.copy()
+    for it in range(1, iters):
+        assert rel_fro(got[it], mus[it]) < tol, (it, rel_fro(got[it], mus[it]))
+    assert rel_fro(me.posterior(0)[1], mo.f[0].Sigma) < tol
+    # a synchronous call after the asynchronous steps sees their state (the main stream is ordered behind the result stream)
+    assert rel_fro(me.posterior(0)[0], mus[-1]) < tol
+    # an expired ticket is refused
+    with pytest.raises(agp.AGPError):
+        e.ck(e.lib.agp_result_wait(e.model, tickets[0][1], L.dptr(mu)))
