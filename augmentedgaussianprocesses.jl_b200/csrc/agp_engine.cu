@@ -104,6 +104,10 @@ struct EngineBase {
   virtual int64_t launch_count() = 0;
   virtual int time_kernel(int which, int reps, double* ms) = 0;
   virtual int use_graph(int on) = 0;
+  virtual int online_carry(int ql, const double* Za, int ma, const double* invDa, const double* prev_eta1, double prev_L) = 0;
+  virtual int online_extra_kl(double* out) = 0;
+  virtual int local_updates_only() = 0;
+  virtual int step_with_gradients(const int64_t* idx, int B, int base, const double* gmu_h, const double* gS_h) = 0;
   virtual void join_async() {}   // order the main stream behind the result stream of the pipelined asynchronous host-batch steps
 };
 
@@ -160,6 +164,10 @@ struct Engine : EngineBase {
     UmmaLatent um;                                    // tcgen05 path
     UmmaKnm uk; bool knm_tc = false;                  // tcgen05 K_nm construction (D <= 128)
     int gram_splits = 1;                              // split-K partials of the last Gram product
+    // OnlineSVGP carry-over (agp_online_carry): whitened offsets of the natural gradient + what extraKL needs
+    bool online = false; int on_ma = 0;
+    double *on_c1v = nullptr, *on_C2v = nullptr, *on_Va = nullptr;    // [mp], [mp][mp], [ma_p][mp]  (V_a = kappa_a L = K_ab L^-T)
+    std::vector<double> on_invD, on_preveta1; double on_prevL = 0.0, on_trDK = 0.0;
     // experimental Newton-Schulz tail (AGP_TAIL_NS): ns.Y() = Sigma_v (fp32, full symmetric) refined from step to step
     UmmaNs ns; bool ns_alloc = false;
     bool ns_seeded = false;      // ns.Y() is the covariance of the current eta2_v
@@ -465,7 +473,7 @@ struct Engine : EngineBase {
     if (h_mu) cudaFreeHost(h_mu);
     for (auto& L : lat) {
       void* ps[] = {L.Z, L.zz, L.Zd, L.zzd, L.Lc, L.Linv, L.Kinv, L.mu0, L.mu0v, L.Linv_T, L.eta1c, L.eta2c, L.eta1v, L.eta2v,
-                    L.muv, L.tvec, L.Xv, L.Dinv, L.Xv_T, L.Knm, L.V, L.VS, L.Ktilde, L.racc, L.Gpart, L.v1, L.P, L.X, L.W, L.logdetP, L.bkLc, L.bkLinv, L.bkKinv, L.bkmu0v, L.bkLinvT};
+                    L.muv, L.tvec, L.Xv, L.Dinv, L.Xv_T, L.Knm, L.V, L.VS, L.Ktilde, L.racc, L.Gpart, L.v1, L.P, L.X, L.W, L.logdetP, L.on_c1v, L.on_C2v, L.on_Va, L.bkLc, L.bkLinv, L.bkKinv, L.bkmu0v, L.bkLinvT};
       for (void* p : ps) cudaFree(p);
       umma_latent_free(L.um);
       if (L.ns_alloc) umma_ns_free(L.ns);
@@ -480,6 +488,7 @@ struct Engine : EngineBase {
       if (res_stream) cudaStreamDestroy(res_stream);
       if (ev_vfree) cudaEventDestroy(ev_vfree);
       if (ev_p1) cudaEventDestroy(ev_p1);
+      if (ev_res) cudaEventDestroy(ev_res);
       if (h_stat) cudaFreeHost(h_stat);
       for (int s = 0; s < 2; ++s) {
         cudaFree(pre_x[s]); cudaFree(pre_y[s]); cudaFree(pre_ycls[s]);
@@ -1208,6 +1217,131 @@ struct Engine : EngineBase {
     return AGP_OK;
   }
 
+  // ---- OnlineSVGP (models/OnlineSVGP.jl, training/onlinetraining.jl) ---------------------------------------------------------
+  // Carry-over of the previous inducing set Z_a into the natural gradient of the current one (analyticVI.jl:183-203):
+  //   eta1 = K^-1 mu0 + kappa^T grad_mu + kappa_a^T prev_eta1,   eta2 = -(kappa^T diag(grad_Sigma) kappa + kappa_a^T invD_a kappa_a / 2 + K^-1 / 2)
+  // with kappa_a = K_ab K^-1 (gpblocks/latentgp.jl:225-226).  In the whitened basis (eta_v = L^T eta [L]) the two constant terms become
+  //   c1_v = V_a^T prev_eta1,  C2_v = V_a^T invD_a V_a / 2,  V_a = kappa_a L = K_ab L^-T,
+  // added by combine_kernel.  invD_a, prev_eta1, prev_L are the outputs of save_old_gp! (onlinetraining.jl:171-183), passed in
+  // canonical form; ma = 0 is the first batch (kappa_a = I, invD_a = I, prev_eta1 = 0: states.jl:86-98, latentgp.jl:220-223).
+  int online_carry(int ql, const double* Za, int ma, const double* invDa, const double* prev_eta1, double prev_L) override {
+    if (ql < 0 || ql >= Ql || ma < 0 || (ma > 0 && (!Za || !invDa || !prev_eta1))) BAD("bad online carry-over");
+    if (stochastic) BAD("The inference object should be of type `AnalyticVI`");   // models/OnlineSVGP.jl:46
+    if (!have_K) { ctx->err = "agp_refresh_K must be called before agp_online_carry"; return AGP_ERR_STATE; }
+    Latent& L = lat[ql];
+    drop_graph();
+    CK(cudaStreamSynchronize(st()));
+    cudaFree(L.on_c1v); cudaFree(L.on_C2v); cudaFree(L.on_Va);
+    L.on_c1v = L.on_C2v = L.on_Va = nullptr;
+    const int rows = ma > 0 ? (int)rup(ma, 4) : mp;
+    CKS(dalloc(&L.on_c1v, (size_t)mp)); CKS(dalloc(&L.on_C2v, (size_t)mp * mp)); CKS(dalloc(&L.on_Va, (size_t)rows * mp));
+    L.on_ma = ma; L.on_prevL = ma > 0 ? prev_L : 0.0; L.on_trDK = 0.0;
+    L.on_invD.clear(); L.on_preveta1.clear();
+    if (ma == 0) {
+      CK(cudaMemcpyAsync(L.on_Va, L.Lc, (size_t)mp * mp * sizeof(double), cudaMemcpyDeviceToDevice, st()));   // V_a = I L
+      dgemm(true, true, L.Lc, L.Lc, L.on_C2v, 0.5, 0.0);                                                        // L^T I L / 2
+    } else {
+      L.on_invD.assign(invDa, invDa + (size_t)ma * ma);
+      L.on_preveta1.assign(prev_eta1, prev_eta1 + ma);
+      const int64_t lda_ = rows;      // leading dimension of the ma x ma matrices
+      std::vector<double> zp((size_t)rows * Dp, 0.0), zn(rows, 0.0), dpad((size_t)rows * lda_, 0.0), e1(rows, 0.0);
+      for (int i = 0; i < ma; ++i) {
+        double s_ = 0;
+        for (int k = 0; k < D; ++k) { double v = Za[(size_t)i * D + k]; zp[(size_t)i * Dp + k] = v; s_ += v * v; }
+        zn[i] = s_; e1[i] = prev_eta1[i];
+        for (int j = 0; j < ma; ++j) dpad[(size_t)i * lda_ + j] = invDa[(size_t)i * ma + j];
+      }
+      double *dZa = nullptr, *dzn = nullptr, *dKab = nullptr, *dKa = nullptr, *dD = nullptr, *dTmp = nullptr, *de1 = nullptr;
+      CKS(dalloc(&dZa, zp.size())); CKS(dalloc(&dzn, (size_t)rows)); CKS(dalloc(&dKab, (size_t)rows * mp)); CKS(dalloc(&dKa, (size_t)rows * lda_));
+      CKS(dalloc(&dD, (size_t)rows * lda_)); CKS(dalloc(&dTmp, (size_t)rows * mp)); CKS(dalloc(&de1, (size_t)rows));
+      CK(cudaMemcpyAsync(dZa, zp.data(), zp.size() * 8, cudaMemcpyHostToDevice, st()));
+      CK(cudaMemcpyAsync(dzn, zn.data(), zn.size() * 8, cudaMemcpyHostToDevice, st()));
+      CK(cudaMemcpyAsync(dD, dpad.data(), dpad.size() * 8, cudaMemcpyHostToDevice, st()));
+      CK(cudaMemcpyAsync(de1, e1.data(), e1.size() * 8, cudaMemcpyHostToDevice, st()));
+      GemmParams<double> g{};   // K_ab = k(Z_a, Z)
+      g.A = dZa; g.lda = Dp; g.B = L.Zd; g.ldb = Dp; g.C = dKab; g.ldc = mp; g.M = ma; g.N = m; g.K = D;
+      g.alpha = 1.0; g.xx = dzn; g.xx_direct = 1; g.zz = L.zzd; g.scale2 = L.scale * L.scale; g.variance = L.variance; g.kernel_kind = L.kind;
+      gemm_simt_launch<double, false, false, EPI_KERNELFN>(g, 1, st());
+      GemmParams<double> ga = g;   // K_a = k(Z_a, Z_a) + jitter I (exact diagonal)
+      ga.B = dZa; ga.C = dKa; ga.ldc = lda_; ga.N = ma; ga.zz = dzn;
+      gemm_simt_launch<double, false, false, EPI_KERNELFN>(ga, 1, st());
+      kmm_fix_kernel<<<dim3((rows + 127) / 128, rows), 128, 0, st()>>>(dKa, lda_, ma, rows, L.variance + jitter);
+      launches += 3;
+      dgemm_bm(false, false, dKab, mp, L.Linv, mp, L.on_Va, mp, ma, m, m, 1.0);         // V_a = K_ab L^-T
+      rect_matvec_t_kernel<<<(m + 127) / 128, 128, 0, st()>>>(L.on_Va, mp, ma, m, de1, L.on_c1v);   // c1_v = V_a^T prev_eta1
+      ++launches;
+      dgemm_bm(false, true, dD, lda_, L.on_Va, mp, dTmp, mp, ma, m, ma, 1.0);           // invD_a V_a
+      dgemm_bm(true, true, L.on_Va, mp, dTmp, mp, L.on_C2v, mp, m, m, ma, 0.5);         // C2_v = V_a^T (invD_a V_a) / 2
+      GemmParams<double> kt{};   // Ktilde_a = K_a - kappa_a K_ab^T = K_a - V_a V_a^T
+      kt.A = L.on_Va; kt.lda = mp; kt.B = L.on_Va; kt.ldb = mp; kt.C = dKa; kt.ldc = lda_; kt.M = ma; kt.N = ma; kt.K = m; kt.alpha = -1.0; kt.beta = 1.0;
+      gemm_simt_launch<double, false, false, EPI_PLAIN>(kt, 1, st());
+      ++launches;
+      std::vector<double> hKt((size_t)rows * lda_);
+      CK(cudaMemcpyAsync(hKt.data(), dKa, hKt.size() * 8, cudaMemcpyDeviceToHost, st()));
+      CK(cudaStreamSynchronize(st()));
+      double tr = 0.0;   // trace_ABt(invD_a, Ktilde_a) (KLdivergences.jl:46-48)
+      for (int i = 0; i < ma; ++i) for (int j = 0; j < ma; ++j) tr += invDa[(size_t)i * ma + j] * hKt[(size_t)i * lda_ + j];
+      L.on_trDK = tr;
+      cudaFree(dZa); cudaFree(dzn); cudaFree(dKab); cudaFree(dKa); cudaFree(dD); cudaFree(dTmp); cudaFree(de1);
+    }
+    L.online = true;
+    CK(cudaGetLastError());
+    return sync_status();
+  }
+  // extraKL(model::OnlineSVGP, state) (functions/KLdivergences.jl:37-54), summed over the owned latents; kappa_a mu = V_a mu_v and
+  // kappa_a Sigma kappa_a^T = (V_a X^T)(V_a X^T)^T with Sigma_v = X^T X
+  int online_extra_kl(double* out) override {
+    if (!out) BAD("null output");
+    double tot = 0.0;
+    for (auto& L : lat) {
+      if (!L.online) continue;
+      CKS(ensure_factor(L));
+      ensure_muv(L);
+      const int ma = L.on_ma > 0 ? L.on_ma : m;
+      const int rows = L.on_ma > 0 ? (int)rup(ma, 4) : mp;
+      const int64_t lds = rows;
+      double *dM1 = nullptr, *dS = nullptr, *dk = nullptr;
+      CKS(dalloc(&dM1, (size_t)rows * mp)); CKS(dalloc(&dS, (size_t)rows * lds)); CKS(dalloc(&dk, (size_t)rows));
+      rect_matvec_kernel<<<(ma + 127) / 128, 128, 0, st()>>>(L.on_Va, mp, ma, m, L.muv, dk);
+      ++launches;
+      dgemm_bm(false, false, L.on_Va, mp, L.Xv, mp, dM1, mp, ma, m, m, 1.0);     // V_a X^T
+      dgemm_bm(false, false, dM1, mp, dM1, mp, dS, lds, ma, ma, m, 1.0);          // (V_a X^T)(V_a X^T)^T
+      std::vector<double> hS((size_t)rows * lds), hk(rows);
+      CK(cudaMemcpyAsync(hS.data(), dS, hS.size() * 8, cudaMemcpyDeviceToHost, st()));
+      CK(cudaMemcpyAsync(hk.data(), dk, hk.size() * 8, cudaMemcpyDeviceToHost, st()));
+      CK(cudaStreamSynchronize(st()));
+      cudaFree(dM1); cudaFree(dS); cudaFree(dk);
+      double tr = 0.0, lin = 0.0, quad = 0.0;
+      for (int i = 0; i < ma; ++i) {
+        double row = 0.0;
+        for (int j = 0; j < ma; ++j) {
+          const double d = L.on_ma > 0 ? L.on_invD[(size_t)i * ma + j] : (i == j ? 1.0 : 0.0);
+          tr += d * hS[(size_t)i * lds + j];
+          row += d * hk[j];
+        }
+        quad += hk[i] * row;
+        if (L.on_ma > 0) lin += L.on_preveta1[i] * hk[i];
+      }
+      tot += L.on_prevL - (L.on_trDK + tr) / 2.0 + lin - quad / 2.0;
+    }
+    *out = tot;
+    return AGP_OK;
+  }
+  // first iteration on a new batch (onlinetraining.jl:75-104): the expectation gradients come from the PREVIOUS model's local
+  // updates on this batch; kernel matrices, natural gradient and global update with the current inducing set
+  int step_with_gradients(const int64_t* idx, int B, int base, const double* gmu_h, const double* gS_h) override {
+    if (!gmu_h || !gS_h) BAD("null gradients");
+    if (peer || Ql != Qg) BAD("step_with_gradients: latent-sharded models are not supported");
+    CKS(step_moments(idx, B, base, false));
+    for (int q = 0; q < Ql; ++q) {
+      CK(cudaMemcpyAsync(gmu + (size_t)q * ldB, gmu_h + (size_t)q * B, (size_t)B * 8, cudaMemcpyHostToDevice, st()));
+      CK(cudaMemcpyAsync(gS + (size_t)q * ldB, gS_h + (size_t)q * B, (size_t)B * 8, cudaMemcpyHostToDevice, st()));
+    }
+    CK(cudaStreamSynchronize(st()));
+    skip_lik = true;
+    return step_update(1.0);
+  }
+
   bool can_fuse_lik() const {
     return !noise_any && !is_vgp && prec == AGP_PREC_TF32X3 && model_kind == AGP_MODEL_SVGP && Qg == 1 && Ql == 1 && !need_lam && !peer && !a_opt && !prof &&
            !getenv("AGP_NO_FUSE_LIK");
@@ -1245,8 +1379,19 @@ struct Engine : EngineBase {
     return step_update_b(rho);
   }
   // local updates + everything that still reads V (V^T g, Gram product)
+  bool skip_lik = false;   // step_with_gradients: the expectation gradients were supplied by the caller
   int step_update_a(double rho) {
     if (curB < 1) { ctx->err = "no minibatch in flight"; return AGP_ERR_STATE; }
+    if (!skip_lik) CKS(local_updates_part());
+    skip_lik = false; lik_fused = false;
+    return natgrad_products(rho);
+  }
+  // local_updates! + the expectation gradients of the minibatch in flight (likelihood/*.jl); `update_A!` first when it is optimised
+  int local_updates_only() override {
+    if (curB < 1) { ctx->err = "no minibatch in flight"; return AGP_ERR_STATE; }
+    return local_updates_part();
+  }
+  int local_updates_part() {
     const int B = curB;
     ph_begin(PH_LIK);
     if (a_opt) {   // update_A! precedes variational_updates (training/training.jl:153-158)
@@ -1271,6 +1416,10 @@ struct Engine : EngineBase {
       }
     }
     ph_end();
+    return AGP_OK;
+  }
+  int natgrad_products(double rho) {
+    const int B = curB;
     const bool grp = use_groups && prec == AGP_PREC_TF32X3;
     for (int q = 0; q < Ql; ++q) {
       Latent& L = lat[q];
@@ -1333,6 +1482,7 @@ struct Engine : EngineBase {
       tp.counters = counters; tp.stochastic = stochastic; tp.rm_kappa = rm_kappa; tp.rm_tau = rm_tau; tp.rho = rho;
       tp.logdet = L.logdetP; tp.status = status;
       tp.lr = d_lr; tp.v1_zero = (prec == AGP_PREC_TF32X3) ? L.v1 : nullptr;
+      tp.eta1_off = L.online ? L.on_c1v : nullptr; tp.eta2_off = L.online ? L.on_C2v : nullptr;
       launch_chain(combine_kernel<T>, grid_mp(), dim3(128), 0, tp, (const T*)L.Gpart);
       ++launches;
       ph_end();
@@ -1730,11 +1880,11 @@ struct Engine : EngineBase {
   void* pre_x[2] = {nullptr, nullptr}; double* pre_y[2] = {nullptr, nullptr}; int* pre_ycls[2] = {nullptr, nullptr};
   double* h_res[2] = {nullptr, nullptr}; int* h_stat = nullptr;
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
-  cudaEvent_t ev_xfree[2] = {nullptr, nullptr}, ev_step[2] = {nullptr, nullptr}, ev_vfree = nullptr, ev_p1 = nullptr;
+  cudaEvent_t ev_xfree[2] = {nullptr, nullptr}, ev_step[2] = {nullptr, nullptr}, ev_vfree = nullptr, ev_p1 = nullptr, ev_res = nullptr;
   cudaStream_t copy_stream = nullptr, res_stream = nullptr;
   int64_t n_tickets = 0;
   int res_pending = -1;    // slot whose result kernels (result stream) the main stream has not been ordered behind yet
-  // pipelined variant: three graphs -- [0] stage 1 on the side stream, [1] statistics + local updates + Gram, [2] natural-parameter update + tail
+  // pipelined variant: two graphs -- [0] stage 1 on the side stream, [1] the rest of the step on the main stream
   cudaGraphExec_t gexec_p[3] = {nullptr, nullptr, nullptr}; int64_t g_launches_p[3] = {0, 0, 0};
   int gB_p = -1, gkey_p = -1; double grho_p = -1;
   bool chain_break = false;   // the next launch_chain call has no kernel predecessor in its graph: no programmatic edge
@@ -1750,6 +1900,7 @@ struct Engine : EngineBase {
     h_stat[0] = h_stat[1] = 0;
     CK(cudaEventCreateWithFlags(&ev_vfree, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ev_p1, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ev_res, cudaEventDisableTiming));
     for (int s = 0; s < 2; ++s) {
       CK(cudaMalloc(&pre_x[s], (size_t)Bcap * D * 8));
       CK(cudaMalloc((void**)&pre_y[s], (size_t)nT * ldB * sizeof(double)));
@@ -1780,7 +1931,7 @@ struct Engine : EngineBase {
         const int64_t l0 = launches;
         cudaError_t ce = cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed);
         if (ce != cudaSuccess) { cur_stream = saved; ctx->err = std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(ce); return AGP_ERR_CUDA; }
-        capturing = true; chain_break = (which == 2);   // combine_kernel is the first node of graph 2
+        capturing = true;
         rc = body();
         capturing = false; chain_break = false;
         ce = cudaStreamEndCapture(s, &graph);
@@ -1808,9 +1959,10 @@ struct Engine : EngineBase {
   // counterpart of step_pool's prefetch -- and the result read-back (mu_v = X^T t, mu = L mu_v, device -> pinned host) runs on a
   // third stream beside the next step's statistics product.  Ordering:
   //   copy stream : wait(x, y slot free) -> H2D x, y -> ev_h2d
-  //   side stream : wait(ev_h2d, ev_vfree = step i-1 is done reading V) -> x slot -> staging -> [graph 0] -> ev_p1
-  //   main stream : y slot -> yb; wait(ev_p1) -> [graph 1] -> ev_vfree -> wait(result kernels of step i-1) -> [graph 2] -> ev_step
-  //   result strm : wait(ev_step) -> mu -> h_res[slot], status -> h_stat[slot] -> ev_done
+  //   side stream : wait(ev_h2d, ev_vfree = step i-1 is done reading V, y) -> x slot -> staging, y slot -> yb -> [graph 0] -> ev_p1
+  //   main stream : wait(ev_p1) -> [graph 1: statistics, local updates, Gram | record ev_vfree | wait ev_res = result kernels of step
+  //                 i-1 | natural-parameter update, m x m tail] -> ev_step          (the two events are external-event graph nodes)
+  //   result strm : wait(ev_step) -> mu -> h_res[slot], status -> h_stat[slot] -> ev_done[slot], ev_res
   int step_batch_async_pipelined(const void* xbh, int x_dtype, int x_layout, const void* const* ybh, int y_kind, int B, double rho, int64_t* ticket) {
     const int slot = (int)(n_tickets & 1);
     const size_t es = x_dtype == AGP_DTYPE_F64 ? 8 : 4;
@@ -1831,6 +1983,8 @@ struct Engine : EngineBase {
     CK(cudaStreamWaitEvent(side, ev_h2d[slot], 0));
     CK(cudaStreamWaitEvent(side, ev_vfree, 0));
     CK(cudaMemcpyAsync(stage, pre_x[slot], (size_t)B * D * es, cudaMemcpyDeviceToDevice, side));
+    if (y_kind == AGP_Y_CLASS) CK(cudaMemcpyAsync(ycls, pre_ycls[slot], B * sizeof(int), cudaMemcpyDeviceToDevice, side));
+    else for (int t = 0; t < nT; ++t) CK(cudaMemcpyAsync(yb + (size_t)t * ldB, pre_y[slot] + (size_t)t * ldB, B * sizeof(double), cudaMemcpyDeviceToDevice, side));
     CK(cudaEventRecord(ev_xfree[slot], side));
     CKS(run_piece(0, side, [&]() -> int {
       const int64_t sld = x_layout == AGP_LAYOUT_ROWMAJOR ? D : B;
@@ -1843,10 +1997,7 @@ struct Engine : EngineBase {
       return AGP_OK;
     }));
     CK(cudaEventRecord(ev_p1, side));
-    // main stream
-    if (y_kind == AGP_Y_CLASS) CK(cudaMemcpyAsync(ycls, pre_ycls[slot], B * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
-    else for (int t = 0; t < nT; ++t) CK(cudaMemcpyAsync(yb + (size_t)t * ldB, pre_y[slot] + (size_t)t * ldB, B * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-    CK(cudaEventRecord(ev_free[slot], ctx->stream));
+    // main stream: ONE graph -- statistics, local updates, Gram | ev_vfree | wait(result kernels of step i-1) | update + tail
     CK(cudaStreamWaitEvent(ctx->stream, ev_p1, 0));
     curB = B; cur_from_batch = true; kernel_matrices_stale = false; prefetched = false;
     CKS(run_piece(1, ctx->stream, [&]() -> int {
@@ -1855,11 +2006,14 @@ struct Engine : EngineBase {
       int s2 = moments_impl(true, B, true, 2);
       fuse_lik_next = false;
       CKS(s2);
-      return step_update_a(rho);
+      CKS(step_update_a(rho));
+      // inside a capture these become event-record / event-wait NODES (external events); eagerly they are ordinary stream operations
+      CK(cudaEventRecordWithFlags(ev_vfree, st(), capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
+      CK(cudaStreamWaitEvent(st(), ev_res, capturing ? cudaEventWaitExternal : cudaEventWaitDefault));   // they still read X / t
+      chain_break = true;                              // combine_kernel's in-graph predecessor is not a kernel
+      return step_update_b(rho);
     }));
-    CK(cudaEventRecord(ev_vfree, ctx->stream));
-    join_async();                                   // the result kernels of the previous step still read X / t
-    CKS(run_piece(2, ctx->stream, [&]() -> int { return step_update_b(rho); }));
+    res_pending = -1;
     CK(cudaEventRecord(ev_step[slot], ctx->stream));
     for (auto& L : lat) L.muv_valid = false;
     have_step = true;
@@ -1877,6 +2031,7 @@ struct Engine : EngineBase {
       CK(cudaMemcpyAsync(h_stat + slot, status, sizeof(int), cudaMemcpyDeviceToHost, res_stream));
     }
     CK(cudaEventRecord(ev_done[slot], res_stream));
+    CK(cudaEventRecord(ev_res, res_stream));
     res_pending = slot;
     CK(cudaGetLastError());
     *ticket = n_tickets++;
@@ -2446,6 +2601,14 @@ int agp_profile_read(agp_model* model, int32_t maxp, const char** names, double*
 int agp_time_kernel(agp_model* model, int32_t which, int32_t reps, double* ms) { ENG(model); return e->time_kernel(which, reps, ms); }
 int64_t agp_launch_count(agp_model* model) { return (model && model->eng) ? model->eng->launch_count() : 0; }
 int agp_use_graph(agp_model* model, int on) { ENG(model); return e->use_graph(on); }
+int agp_online_carry(agp_model* model, int32_t latent_local, const double* Za, int32_t ma, const double* invDa, const double* prev_eta1, double prev_L) {
+  ENG(model); return e->online_carry(latent_local, Za, ma, invDa, prev_eta1, prev_L);
+}
+int agp_online_extra_kl(agp_model* model, double* out) { ENG(model); return e->online_extra_kl(out); }
+int agp_local_updates_async(agp_model* model) { ENG(model); return e->local_updates_only(); }
+int agp_step_with_gradients(agp_model* model, const int64_t* idx, int32_t B, int32_t base, const double* grad_mu, const double* grad_Sigma) {
+  ENG(model); return e->step_with_gradients(idx, B, base, grad_mu, grad_Sigma);
+}
 
 // EXPERIMENTAL (see include/agp_b200.h): self-contained, does not touch any model
 int agp_experimental_ns_refine(agp_ctx* ctx, int32_t m, const double* P, double* Y, int32_t iters, int32_t mode, double* resid, double* ms) {

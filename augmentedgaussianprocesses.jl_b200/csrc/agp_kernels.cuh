@@ -735,6 +735,9 @@ struct TailParams {
   double* v1_zero;          // non-null: clear V^T grad_mu after use (the next step accumulates into it without a memset)
   int stochastic; double rm_kappa, rm_tau, rho;
   double* logdet; int* status;
+  // OnlineSVGP (analyticVI.jl:183-203): constant terms of the natural gradient carried over from the previous inducing set,
+  // whitened: eta1_off = (kappa_a L)^T prev_eta1, eta2_off = (kappa_a L)^T invD_a (kappa_a L) / 2.  Null for every other model.
+  const double* eta1_off; const double* eta2_off;
 };
 
 // natural gradient + global update of the natural parameters (inference/analyticVI.jl:160-180, 229-246;
@@ -764,13 +767,14 @@ __global__ void combine_kernel(const TailParams p, const TG* __restrict__ Gpart)
   }
   int64_t o = (int64_t)i * p.ld + j;
   double e2 = p.eta2[o];
+  if (p.eta2_off) g += p.eta2_off[o];
   double d2 = -(g + (i == j ? 0.5 : 0.0)) - e2;
   e2 += lr * d2;
   p.eta2[o] = e2;
   p.P[o] = -2.0 * e2;
   if (i == 0) {
     double e1 = p.eta1[j];
-    double d1 = p.rho * p.v1[j] + p.mu0v[j] - e1;
+    double d1 = p.rho * p.v1[j] + p.mu0v[j] + (p.eta1_off ? p.eta1_off[j] : 0.0) - e1;
     p.eta1[j] = e1 + lr * d1;
     if (p.v1_zero) p.v1_zero[j] = 0.0;
     if (j == 0) *p.logdet = 0.0;
@@ -903,6 +907,21 @@ __global__ void bump_counters_kernel(int64_t* counters, int bump_t, int bump_cur
   if (threadIdx.x == 0 && blockIdx.x == 0) { counters[0] += bump_t; counters[1] += bump_cursor; }
 }
 
+// small rectangular fp64 mat-vec products of the OnlineSVGP carry-over (off the hot path): S is [rows][ld]
+__global__ void rect_matvec_t_kernel(const double* __restrict__ S, int64_t ld, int rows, int cols, const double* __restrict__ x, double* __restrict__ y) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;     // y = S^T x
+  if (j >= cols) return;
+  double a = 0.0;
+  for (int i = 0; i < rows; ++i) a = fma(S[(int64_t)i * ld + j], x[i], a);
+  y[j] = a;
+}
+__global__ void rect_matvec_kernel(const double* __restrict__ S, int64_t ld, int rows, int cols, const double* __restrict__ x, double* __restrict__ y) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;     // y = S x
+  if (i >= rows) return;
+  double a = 0.0;
+  for (int j = 0; j < cols; ++j) a = fma(S[(int64_t)i * ld + j], x[j], a);
+  y[i] = a;
+}
 // K_mm finishing touch in fp64 (gpblocks/latentgp.jl:206): exact diagonal variance + jitter, identity padding
 __global__ void kmm_fix_kernel(double* __restrict__ K, int64_t ld, int m, int mp, double diag) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;

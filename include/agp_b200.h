@@ -280,6 +280,31 @@ int agp_time_kernel(agp_model* model, int32_t which, int32_t reps, double* ms_pe
 /* capture the step into a CUDA graph and replay it on later agp_step*(idx == NULL) calls. */
 int agp_use_graph(agp_model* model, int on);
 
+/* ---- OnlineSVGP (models/OnlineSVGP.jl, training/onlinetraining.jl; AnalyticVI only: OnlineSVGP.jl:46) ----------------------
+ * The streaming model is an SVGP-kind model whose natural gradient carries two constant terms from the previous inducing set
+ * Z_a (natural_gradient!(::OnlineVarLatent), inference/analyticVI.jl:183-203):
+ *   eta1 = K^-1 mu0 + kappa^T grad_mu + kappa_a^T prev_eta1
+ *   eta2 = -(kappa^T diag(grad_Sigma) kappa + kappa_a^T invD_a kappa_a / 2 + K^-1 / 2),   kappa_a = K_ab K^-1.
+ * The inducing set itself is chosen by the caller (the reference draws it with the un-vendored InducingPoints.jl from Julia's
+ * global RNG, onlinetraining.jl:157,175,193): a new set = a new model of that m, then agp_online_carry.
+ *
+ * agp_online_carry: replaces save_old_gp! (onlinetraining.jl:171-183; its outputs invD_a [ma][ma], prev_eta1 [ma], prev_L are
+ * passed in, canonical form) and the K_ab / kappa_a / Ktilde_a part of compute_kappa(::OnlineVarLatent)
+ * (gpblocks/latentgp.jl:217-230).  Za: previous inducing points, row-major [ma][D].  ma = 0: first batch (kappa_a = I, invD_a = I,
+ * prev_eta1 = 0, Ktilde_a = 0: training/states.jl:86-98, latentgp.jl:220-223).  Call after agp_refresh_K; every later step of
+ * this model adds the two terms (stochastic models are refused, like the reference's constructor). */
+int agp_online_carry(agp_model* model, int32_t latent_local, const double* Za, int32_t ma, const double* invDa, const double* prev_eta1,
+                     double prev_L);
+/* extraKL(model::OnlineSVGP, state) (functions/KLdivergences.jl:37-54) of the owned latents: ELBO = agp_elbo parts - this. */
+int agp_online_extra_kl(agp_model* model, double* out);
+/* local_updates! and the expectation gradients of the minibatch whose moments agp_step_moments_async just computed, WITHOUT the
+ * natural gradient (first iteration on a new batch, onlinetraining.jl:81-92: the local updates run under the previous model);
+ * read the results with agp_get_local("grad_mu" / "grad_Sigma"). */
+int agp_local_updates_async(agp_model* model);
+/* kernel matrices of the batch, natural_gradient! and global_update! with SUPPLIED expectation gradients grad_mu / grad_Sigma
+ * (host, [n_latent][B]) instead of this model's own local updates (onlinetraining.jl:93-104), rho = 1. */
+int agp_step_with_gradients(agp_model* model, const int64_t* idx, int32_t B, int32_t base, const double* grad_mu, const double* grad_Sigma);
+
 /* EXPERIMENTAL -- NOT on the product path and not yet run on a GPU (written after the round's GPU budget was spent).
  * Building block of the planned replacement of the fp64 Cholesky tail of global_update! (inference/inference.jl:25-28,
  * Sigma = -1/2 eta2^-1): Newton-Schulz refinement  Y <- Y + Y (I - P Y)  of an approximate inverse Y of the SPD m x m
