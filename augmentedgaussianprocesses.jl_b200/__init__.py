@@ -25,6 +25,7 @@ from .api import (
     Matern52Kernel,
     MOSVGP,
     MOVGP,
+    OnlineSVGP,
     RobbinsMonro,
     ScaleTransform,
     SqExponentialKernel,
@@ -40,6 +41,7 @@ from .api import (
     predict_y,
     proba_y,
     train,
+    train_online,
     transform,
     treat_labels,
     with_lengthscale,

@@ -734,6 +734,125 @@ class MOVGP(AbstractGPModel):
         return f"Multioutput Variational Gaussian Process with the likelihoods {self.likelihoods} infered by {self.inference} "
 
 
+class OnlineSVGP(SVGP):
+    """models/OnlineSVGP.jl:1-78: streaming sparse variational GP, AnalyticVI only, `optimiser = nothing` semantics.
+
+    `OnlineSVGP(kernel, likelihood, inference)`: the model starts without inducing points; every `train_online` call brings one
+    batch (X, y) and the inducing set to use for it.  The reference chooses that set with the un-vendored InducingPoints.jl
+    (`inducingpoints(Zalg, x)`, `updateZ`, `remove_point(Random.GLOBAL_RNG, ...)`, training/onlinetraining.jl:157,175,193) from
+    Julia's global RNG, so -- like the minibatch indices of `train` -- it is an argument here instead of a `Zalg`.
+    A new inducing set is a new device model of that size; the previous one contributes through agp_online_carry."""
+
+    def __init__(self, kernel: Kernel, likelihood: AbstractLikelihood, inference: AnalyticVI, *, verbose: int = 0, mean=None,
+                 T=np.float64, precision: str = "auto", device: int = 0, stream=None):
+        if not isinstance(inference, AnalyticVI) or inference.stoch:
+            raise ValueError("The inference object should be of type `AnalyticVI`")      # OnlineSVGP.jl:46
+        if not isinstance(likelihood, AbstractLikelihood):
+            raise TypeError(f"The {likelihood} is not compatible or implemented with the {inference}")
+        if likelihood.kind in (L.LIK_LOGISTICSOFTMAX, L.LIK_POISSON, L.LIK_HETEROSCEDASTIC) or getattr(likelihood, "opt_noise", None) is not None:
+            raise NotImplementedError("OnlineSVGP is accelerated for likelihoods whose local updates carry no state between batches")
+        self._common_init(inference, verbose, 1, False, False, T, precision, device, stream, None)
+        self.likelihood = likelihood
+        self.likelihoods = [likelihood]
+        self.kernel = kernel
+        self.n_latent = likelihood.n_latent
+        self.kernels = [kernel] * self.n_latent
+        if mean is not None and not np.isscalar(mean):
+            raise NotImplementedError("only ZeroMean / ConstantMean priors cross the boundary")
+        self._mean = None if mean is None else float(mean)
+        self.mu0 = None
+        self.A = None
+        self.Z = None
+        self.Zs = None
+        self.m, self.D = 0, 0
+
+    def __repr__(self):
+        return f"Online Variational Gaussian Process with a {self.likelihood} infered by {self.inference}"
+
+
+def train_online(model: OnlineSVGP, X, y, Z, state: Optional["State"] = None, iterations: int = 20):
+    """`train!(m::OnlineSVGP, X, y, state; iterations)` (training/onlinetraining.jl:36-144) for one batch, with the inducing set `Z`
+    to use for it (see OnlineSVGP).  First iteration: the local updates run under the PREVIOUS inducing set and posterior, the
+    natural gradient under the new one (onlinetraining.jl:75-104); later iterations are ordinary AnalyticVI steps whose natural
+    gradient carries the two previous-set terms (analyticVI.jl:183-203)."""
+    if iterations <= 0:
+        raise ValueError("Number of iterations should be positive")
+    X = np.asarray(X)
+    if X.ndim == 1:
+        X = X[:, None]
+    Z = np.ascontiguousarray(np.asarray(Z, dtype=np.float64))
+    if Z.ndim == 1:
+        Z = Z[:, None]
+    n = X.shape[0]
+    inf = model.inference
+    inf.batchsize = n
+    inf.rho = 1.0
+    ys = _wrap_y(model, y)
+    full = np.arange(n, dtype=np.int64)
+    ip = full.ctypes.data_as(L.c_int64_p)
+    Q = model.n_latent
+    old = model._eng
+    carry, grads = None, None
+    if inf.n_iter > 0:
+        if old is None or state is None:
+            raise ValueError("a trained OnlineSVGP needs the state returned by the previous train_online call")
+        if n > old.capacity:
+            raise ValueError("the batch is larger than the previous one (the reference's in-place local updates need equal sizes)")
+        # save_old_parameters! (onlinetraining.jl:164-183): invD_a = -2 eta2 - K^-1, prev_eta1, prev_L per latent
+        ma = model.m
+        carry = []
+        for q in range(Q):
+            mu, S, e1, e2 = model._get_posterior_raw(q)
+            Kinv, ldK = np.empty((ma, ma)), C.c_double()
+            old.ck(old.lib.agp_get_Kinv(old.model, q, L.dptr(Kinv), C.byref(ldK)))
+            invD = np.triu(-2.0 * e2 - Kinv)
+            invD = invD + np.triu(invD, 1).T                                  # Symmetric(...) reads the upper triangle
+            prevL = float((-np.linalg.slogdet(S)[1] + ldK.value - mu @ e1) / 2.0)
+            carry.append((np.ascontiguousarray(model.Zs[q]), np.ascontiguousarray(invD), np.ascontiguousarray(e1), prevL))
+        # local updates of the previous model on the new batch (onlinetraining.jl:79-92)
+        model._data_key = None
+        _upload(model, old, X, ys, ("online-prev", inf.n_iter))
+        old.ck(old.lib.agp_step_moments_async(old.model, ip, n, 0))
+        old.ck(old.lib.agp_local_updates_async(old.model))
+        gmu, gS = np.empty((Q, n)), np.empty((Q, n))
+        for q in range(Q):
+            old.ck(old.lib.agp_get_local(old.model, b"grad_mu", q, L.dptr(gmu[q]), n))
+            old.ck(old.lib.agp_get_local(old.model, b"grad_Sigma", q, L.dptr(gS[q]), n))
+        grads = (np.ascontiguousarray(gmu), np.ascontiguousarray(gS))
+        old.close()
+        model._eng = None
+    # updateZs! / init_online_model: the device model of the new inducing set (fresh posterior: posterior.jl:47-55)
+    model.Z = Z
+    model.m, model.D = Z.shape
+    model.Zs = [Z] * Q
+    model.mu0 = None if model._mean is None else np.full(model.m, model._mean)
+    model.precision = model.precision_requested
+    model._data_key = None
+    eng = model._engine(n)
+    lib = eng.lib
+    _upload(model, eng, X, ys, ("online", inf.n_iter))
+    model._data_refs = (X, ys)
+    eng.ck(lib.agp_state_reset(eng.model))
+    eng.ck(lib.agp_refresh_K(eng.model))
+    for q in range(Q):
+        if carry is None:
+            eng.ck(lib.agp_online_carry(eng.model, q, None, 0, None, None, 0.0))
+        else:
+            Za, invD, e1, prevL = carry[q]
+            eng.ck(lib.agp_online_carry(eng.model, q, L.dptr(Za), Za.shape[0], L.dptr(invD), L.dptr(e1), prevL))
+    state = State(model)
+    state.B = n
+    for local_iter in range(1, iterations + 1):
+        if local_iter == 1 and grads is not None:
+            eng.ck(lib.agp_step_with_gradients(eng.model, ip, n, 0, L.dptr(grads[0]), L.dptr(grads[1])))
+            eng.ck(lib.agp_sync(eng.model))
+        else:
+            eng.ck(lib.agp_step(eng.model, ip, n, 0, 1.0))
+        model.trained = True
+        inf.n_iter += 1
+    return model, state
+
+
 def _make_desc(model, capacity: int) -> dict:
     q0, ql = model._latent_range()
     inf = model.inference
@@ -1073,7 +1192,12 @@ def ELBO(model: AbstractGPModel, state: Optional[State] = None, y=None) -> float
         out[1] = float(kl.item())
     else:
         eng.ck(eng.lib.agp_elbo(eng.model, rho, L.dptr(out)))
-    return float(out[0] - out[1] - out[2])
+    extra = 0.0
+    if isinstance(model, OnlineSVGP):   # extraKL (functions/KLdivergences.jl:37-54)
+        ek = C.c_double()
+        eng.ck(eng.lib.agp_online_extra_kl(eng.model, C.byref(ek)))
+        extra = ek.value
+    return float(out[0] - out[1] - out[2] - extra)
 
 
 objective = ELBO

@@ -84,6 +84,24 @@ __device__ __forceinline__ WorkUnit get_unit(const GemmWork& w, int u) {
 // long units with short ones when the list is sorted by length
 __device__ __forceinline__ int unit_index(int round, int cta, int G) { return round * G + ((round & 1) ? (G - 1 - cta) : cta); }
 
+// per-role timeline instrumentation for profiles/microbench/gemm_trace.cu (compiled in only with -DAGP_UMMA_TRACE):
+// role 0 = TMA thread, 1 = MMA thread, 2 / 3 = first thread of worker group 0 / 1; records (tag, clock64)
+#ifdef AGP_UMMA_TRACE
+constexpr int UT_SLOTS = 400;
+__device__ unsigned long long agp_ut_trace[160 * 4 * UT_SLOTS * 2];
+__device__ int agp_ut_n[160 * 4];
+__device__ __forceinline__ void ut_trace(int role, int tag) {
+  const int n = agp_ut_n[blockIdx.x * 4 + role]++;
+  if (n < UT_SLOTS) {
+    unsigned long long* r = agp_ut_trace + (((size_t)blockIdx.x * 4 + role) * UT_SLOTS + n) * 2;
+    r[0] = (unsigned long long)tag; r[1] = (unsigned long long)clock64();
+  }
+}
+#define UTT(role, tag) ut_trace(role, tag)
+#else
+#define UTT(role, tag) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 umma_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C,
                     int64_t ldc, int64_t c_split_stride, const GemmWork work, const UmmaEpilogue ep) {
@@ -122,6 +140,7 @@ umma_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   // programmatic dependent launch: barrier init / TMEM allocation above overlap the previous kernel of the chain
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (threadIdx.x == 0) UTT(0, 1);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -134,6 +153,7 @@ umma_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int i = 0; i < wu.nkb; ++i, ++g) {
           const int s = g % RS;
           mbar_wait(raw_empty(s), ((g / RS) & 1) ^ 1);
+          UTT(0, 1000 + g);
           const uint32_t dst = smem_base + s * RAW_BYTES;
           mbar_expect_tx(raw_full(s), 2 * TILE_BYTES);
           const int k = (wu.kb0 + i) * BK;
@@ -152,11 +172,13 @@ umma_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int ab = lt & 1;
       mbar_wait(tmem_empty(ab), ((lt >> 1) & 1) ^ 1);      // the epilogue two units ago has drained this accumulator
       tc_fence_after();
+      if (lane == 0) UTT(1, 100000 + lt);
       const uint32_t acc = tmem_base + ab * BN;
       for (int i = 0; i < wu.nkb; ++i, ++g) {
         const int s = g % CS;
         mbar_wait(conv_full(s), (g / CS) & 1);
         tc_fence_after();
+        if (lane == 0) UTT(1, 2000 + g);
         if (elect_one()) {
           const uint32_t b_hi = conv_base + s * CONV_BYTES, b_lo = b_hi + TILE_BYTES;
           const uint32_t a_hi = tmem_base + TMEM_A0 + s * 64, a_lo = a_hi + 32;
@@ -172,6 +194,7 @@ umma_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (i == wu.nkb - 1) tc_commit(tmem_full(ab));   // accumulator complete
         }
         __syncwarp();
+        if (lane == 0) UTT(1, 3000 + g);
       }
     }
   } else {
@@ -190,11 +213,14 @@ umma_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // do not start before the other group has issued every conversion of the previous unit (the TMA ring and the MMA
       // warp are then at most one phase behind on every barrier this group is about to wait on).
       if (lt > 0) mbar_wait(unit_conv_done(grp ^ 1), ((lt - 1) >> 1) & 1);
+      if (ct == 0) UTT(2 + grp, 200000 + lt);
       for (int i = 0; i < wu.nkb; ++i, ++g) {
         const int rs = g % RS, s = g % CS;
         mbar_wait(raw_full(rs), (g / RS) & 1);               // TMA landed the raw tiles
+        if (ct == 0) UTT(2 + grp, 4000 + g);
         mbar_wait(mma_done(s), ((g / CS) & 1) ^ 1);          // previous MMAs on this slot's converted operands retired
         tc_fence_after();
+        if (ct == 0) UTT(2 + grp, 5000 + g);
         uint8_t* base = smem_gen + rs * RAW_BYTES;
         uint8_t* cbase_s = smem_gen + RS * RAW_BYTES + s * CONV_BYTES;
         {
@@ -236,6 +262,7 @@ umma_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
         mbar_arrive(raw_empty(rs));   // the raw tiles may be overwritten by the next TMA
         mbar_arrive(conv_full(s));    // operands ready for the MMA warp
+        if (ct == 0) UTT(2 + grp, 6000 + g);
       }
       mbar_arrive(unit_conv_done(grp));
       // ----- epilogue of this unit (the other group is already converting the next one) -----
@@ -247,6 +274,7 @@ umma_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (wu.nkb > 0) {
         mbar_wait(tmem_full(ab), (lt >> 1) & 1);
         tc_fence_after();
+        if (ct == 0) UTT(2 + grp, 300000 + lt);
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           uint32_t rr[32];
@@ -281,11 +309,13 @@ umma_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         if (ep.mode == UMMA_EPI_STORE_SUMSQ) atomicAdd(ep.acc0 + row, acc_sq);
         if (ep.mode == UMMA_EPI_STATS_ONLY) { atomicAdd(ep.acc0 + row, acc_sq); atomicAdd(ep.acc1 + row, acc_dot); }
+        if (ct == 0) UTT(2 + grp, 400000 + lt);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) UTT(0, 2);
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }

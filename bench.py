@@ -476,6 +476,105 @@ def run_ours(args, rank, world, local_rank, cfg_name):
         dist.destroy_process_group()
 
 
+def run_predict(args, local_rank):
+    """Extra evidence leg (`--predict`, not the driver's bench line): _predict_f (training/predictions.jl:25-50) of the C2 model on
+    `--predict-rows` test points.  The engine predicts in chunks of its batch capacity: with the default chunk = all rows the
+    test-point kernel matrix K_* (rows x m fp32, 2.1 GB at 2^20 x 512) is written to and read back from HBM -- the one
+    configuration in which the K_nm construction kernel is HBM-bound -- while `--predict-chunk 8192` keeps every
+    chunk's K_* in the 126 MB L2 like a training step.  Prints one JSON line: end-to-end rows/s through agp_predict_f (host f32 rows
+    in, host f64 mean / variance out) and the per-kernel rooflines at that chunk size (agp_time_kernel)."""
+    import ctypes as C
+
+    import torch
+
+    import agp_b200 as agp
+
+    torch.cuda.set_device(local_rank)
+    L = agp._lib
+    c = CONFIGS["C2"]
+    D, m, B0 = c["D"], c["m"], c["B"]
+    n = int(args.predict_rows)
+    chunk = int(args.predict_chunk or n)
+    if n % 128 or chunk % 128:
+        raise SystemExit("--predict-rows / --predict-chunk must be multiples of 128")
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((max(n, 1 << 20), D), dtype=np.float32)            # training inputs (also the pool the kernel timings gather from)
+    w = rng.standard_normal(D).astype(np.float32)
+    y = np.where(X @ w + 0.1 * rng.standard_normal(X.shape[0], dtype=np.float32) >= 0, 1.0, -1.0)
+    Z = X[rng.permutation(X.shape[0])[:m]].astype(np.float64)
+    mbs = np.stack([rng.choice(X.shape[0], B0, replace=False) for _ in range(3)]).astype(np.int64)
+    sc = 1.0 / np.sqrt(D)
+    model = agp.SVGP(agp.SqExponentialKernel() @ agp.ScaleTransform(sc), agp.LogisticLikelihood(), agp.AnalyticSVI(B0), Z, precision="tf32x3", device=local_rank)
+    model._engine(chunk)                      # batch capacity = prediction chunk
+    agp.train(model, X, y, 3, minibatches=list(mbs))
+    eng = model._eng
+    lib = eng.lib
+    Xt = rng.standard_normal((n, D), dtype=np.float32)
+    # parity of the prediction against the oracle on the first rows (outside every timed region)
+    par = None
+    if not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import agp_oracle as O
+
+        mo = O.SVGP(O.Kernel("sqexp", scale=sc), O.LogisticLikelihood(), O.AnalyticSVI(B0), Z)
+        mo, so = O.train(mo, X.astype(np.float64), y, 3, minibatches=list(mbs))
+        mu_o, var_o = O.predict_f(mo, Xt[:2048].astype(np.float64), cov=True)
+        mu_e, var_e = agp.predict_f(model, Xt[:2048], cov=True)
+        par = dict(rows=2048, mu_rel=float(np.linalg.norm(mu_e - mu_o[0]) / np.linalg.norm(mu_o[0])),
+                   var_rel=float(np.linalg.norm(var_e - var_o[0]) / np.linalg.norm(var_o[0])))
+        par["ok"] = bool(par["mu_rel"] < 5e-4 and par["var_rel"] < 5e-4)
+    # end to end: agp_predict_f on host rows
+    mu = np.empty(n); var = np.empty(n)
+    Xk, xp, dt, layout, nt, _ = agp.api._x_args(Xt)
+    reps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        eng.ck(lib.agp_predict_f(eng.model, xp, dt, layout, nt, 1, L.dptr(mu), L.dptr(var)))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        eng.ck(lib.agp_predict_f(eng.model, xp, dt, layout, nt, 1, L.dptr(mu), L.dptr(var)))
+    torch.cuda.synchronize()
+    dt_s = (time.perf_counter() - t0) / reps
+    # kernel level at this chunk size: one resident-list step with B = chunk, then agp_time_kernel
+    kern = {}
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    peak_tf32 = (peaks.get("bf16_tflops", 1590.0)) / 2.0
+    Bk = chunk
+    lists = np.stack([rng.permutation(X.shape[0])[:Bk] for _ in range(3)]).astype(np.int64)
+    eng.ck(lib.agp_minibatches_upload(eng.model, lists.ctypes.data_as(L.c_int64_p), 3, Bk, 0))
+    eng.ck(lib.agp_step(eng.model, None, Bk, 0, X.shape[0] / Bk))
+    tk = {}
+    for which, name in ((0, "knm"), (1, "gemm_v"), (2, "gemm_v_sigma")):
+        v = C.c_double(0.0)
+        eng.ck(lib.agp_time_kernel(eng.model, which, 5, C.byref(v)))
+        tk[name] = v.value * 1e-3
+    byts = 4.0 * (Bk * D + m * D + Bk * m) + 8.0 * Bk
+    traffic = {}
+    tf = os.path.join(ROOT, "profiles", "r2", "ncu_traffic_predict.json")
+    if os.path.exists(tf):
+        traffic = json.load(open(tf))
+    kern["knm"] = dict(bound="hbm", kernel="knm_umma_kernel", rows=Bk, seconds_per_launch=tk["knm"], algorithmic_bytes_per_launch=byts,
+                       achieved=byts / tk["knm"] / 1e9, peak=hbm, unit="GB/s", frac=byts / tk["knm"] / 1e9 / hbm, traffic=traffic.get("knm"),
+                       peak_source="MEASURED_PEAKS.json hbm_gbs, of measured" if "hbm_gbs" in peaks else "fallback 6.65 TB/s, of fallback")
+    for k_ in ("gemm_v", "gemm_v_sigma"):
+        fl = 1.0 * Bk * m * m
+        kern[k_] = dict(bound="tensor", rows=Bk, seconds_per_launch=tk[k_], algorithmic_flops_per_launch=fl, achieved=fl / tk[k_] / 1e12, peak=peak_tf32,
+                        unit="TFLOP/s", frac=fl / tk[k_] / 1e12 / peak_tf32, tensor_pipe_frac_3xtf32=3 * fl / tk[k_] / 1e12 / peak_tf32, traffic=traffic.get(k_))
+    line = dict(leg="predict", metric="predict_f rows/sec, SVGP Logistic SqExp m=512 D=32 (mean + variance)", value=n / dt_s, unit="rows/s", n_gpus=1,
+                ms_per_call=1e3 * dt_s, higher_is_better=True, dtype="tf32x3 (tcgen05), f64 statistics", data="synthetic",
+                config=dict(workload="C2 model, _predict_f on test rows", rows=n, chunk=chunk, D=D, m=m),
+                e2e=dict(value=n / dt_s, unit="rows/s", h2d_bytes_per_call=n * D * 4, d2h_bytes_per_call=n * 16,
+                         call="agp_predict_f(host x[n,D] f32) -> host mean[n], var[n] f64 (pageable host arrays)"),
+                roofline=dict(bound="hbm", kernel="knm", achieved=kern["knm"]["achieved"], peak=hbm, unit="GB/s", frac=kern["knm"]["frac"],
+                              traffic=kern["knm"]["traffic"], kernels=kern,
+                              note="chunk = rows: K_* is materialised in HBM; chunk = 8192: K_* stays in L2 and the DRAM traffic is the x rows in, 16 B/row out"),
+                predict_parity=par)
+    print(json.dumps(line), flush=True)
+    if par is not None and not par["ok"]:
+        sys.exit(3)
+
+
 def cpu_replay(cfg_name, X, y, Z, A, mbs, W, K, elbo_engine, post_engine, max_iters=130):
     """The fp64 oracle replays the trajectory the engine just ran (1 initial + W warm-up + K timed iterations on the same lists) when
     that is at most `max_iters` iterations, otherwise a fresh pair is not available and only the first iterations are timed.
@@ -524,6 +623,9 @@ def main():
     ap.add_argument("--config", default="auto", choices=["auto", "C2", "C3", "C4", "C5"],
                     help="auto = C2 on one GPU (the metric's configuration), C5 (64 latents sharded over the ranks) on N > 1")
     ap.add_argument("--timed-only", action="store_true", help="profiling aid: run only warm-up + the timed loop")
+    ap.add_argument("--predict", action="store_true", help="extra evidence leg: _predict_f of the C2 model on --predict-rows test points")
+    ap.add_argument("--predict-rows", type=int, default=1 << 20)
+    ap.add_argument("--predict-chunk", type=int, default=0, help="prediction chunk = batch capacity of the engine (0 = all rows: K_* goes through HBM)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -531,6 +633,10 @@ def main():
     cfg_name = args.config if args.config != "auto" else ("C2" if args.gpus == 1 else "C5")
     if args.impl == "reference":
         run_reference(args, rank, world, cfg_name)
+        return
+    if args.predict:
+        if rank == 0:
+            run_predict(args, local_rank)
         return
     if world != args.gpus and world == 1 and args.gpus > 1:
         # launched without torchrun: re-exec under torch.distributed.run

@@ -1,9 +1,10 @@
 # AGPB200.jl -- reference-side binding of libagp_b200.so (UNVERIFIED: Julia is not installed in the build image).
 #
-# Overrides the one method of AugmentedGaussianProcesses.jl that the engine replaces,
+# Overrides the methods of AugmentedGaussianProcesses.jl that the engine replaces,
 #     update_parameters!(model::SVGP, state, x, y)            (src/training/training.jl:140-144)
-# plus ELBO(model, state, y) (src/inference/analyticVI.jl:255) and _predict_f (src/training/predictions.jl:25),
-# for models built with AnalyticVI / AnalyticSVI and optimiser = false, Zoptimiser = false.
+#     update_parameters!(model::MOSVGP, state, x, ys)         (src/training/training.jl:153-158, incl. update_A!)
+# plus ELBO(model, state, y) (src/inference/analyticVI.jl:255-297, single- and multi-output) and update_hyperparameters!
+# (src/hyperparameter/autotuning.jl:86-140), for models built with AnalyticVI / AnalyticSVI.
 # Data crosses the ABI exactly as the reference holds it: X as the column-major parent Matrix{Float64} of the
 # RowVecs (src/data/datacontainer.jl:64-66), minibatches as 1-based Vector{Int}, y as Vector{Float64}.
 module AGPB200
@@ -66,50 +67,77 @@ function kernel_params(k)
     return Int32(kind), Float64(s), Float64(var)
 end
 
-function engine(model::SVGP{T}, B::Int) where {T}
+# tcgen05 (tf32x3 = 2) needs m and the batch capacity to be multiples of 128; other shapes (the reference's own tests use 10 inducing
+# points, test/testingtools.jl:66) take the fp32 SIMT path (1).  AGP_B200_PRECISION = f64 | f32 | tf32x3 overrides.
+function precision_code(m::Int, B::Int)
+    p = get(ENV, "AGP_B200_PRECISION", "auto")
+    p == "f64" && return Int32(0); p == "f32" && return Int32(1); p == "tf32x3" && return Int32(2)
+    return (m % 128 == 0 && B % 128 == 0) ? Int32(2) : Int32(1)
+end
+
+likelihoods(model::SVGP) = (AGP.likelihood(model),)
+likelihoods(model::MOSVGP) = Tuple(AGP.likelihood(model))
+model_kind(::SVGP) = Int32(0)
+model_kind(::MOSVGP) = Int32(1)
+# MOSVGP mixing matrix: A[task][1] = weights over the Q latents (single-latent task likelihoods) -> row-major [T][Q]
+mixing(::SVGP) = Float64[]
+mixing(model::MOSVGP) = Float64[model.A[t][1][q] for q in 1:length(model.f), t in 1:length(model.A)][:]   # (Q, T) column-major == [T][Q] row-major
+
+function engine(model::Union{SVGP{T},MOSVGP{T}}, B::Int) where {T}
     haskey(ENGINES, model) && return ENGINES[model]
-    inf = AGP.inference(model); l = AGP.likelihood(model)
-    Q = AGP.n_latent(model); m = AGP.dim(model.f[1]); D = length(first(model.f[1].Z))
+    inf = AGP.inference(model); ls = likelihoods(model)
+    Q = length(model.f); m = AGP.dim(model.f[1]); D = length(first(model.f[1].Z))
+    model isa MOSVGP && any(>(1), model.nf_per_task) && error("AGPB200: MOSVGP tasks must be single-latent likelihoods")
     Z = zeros(Float64, D, m, Q)                       # row-major [Q][m][D] for C == column-major (D, m, Q) here
     for (q, gp) in enumerate(model.f), (i, z) in enumerate(gp.Z); Z[:, i, q] .= z; end
     kp = [kernel_params(AGP.kernel(gp)) for gp in model.f]
     kk = Int32[p[1] for p in kp]; ks = Float64[p[2] for p in kp]; kv = Float64[p[3] for p in kp]
-    lk = Int32[lik_code(l)]
-    p0 = Float64[lik_p0(l)]
-    p1 = Float64[l isa AGP.StudentTLikelihood ? l.σ : 0.0]
+    lk = Int32[lik_code(l) for l in ls]
+    p0 = Float64[lik_p0(l) for l in ls]
+    p1 = Float64[l isa AGP.StudentTLikelihood ? l.σ : 0.0 for l in ls]
+    A = mixing(model)
     o = AGP.opt(inf).optimiser
     κ, τ = o isa RobbinsMonro ? (Float64(o.κ), Float64(o.τ)) : (0.51, 1.0)
     ctx = Ref{Ptr{Cvoid}}(C_NULL); mdl = Ref{Ptr{Cvoid}}(C_NULL)
     rc = ccall((:agp_ctx_create, LIB), Cint, (Cint, Ptr{Cvoid}, Ref{Ptr{Cvoid}}), 0, C_NULL, ctx)
     rc == 0 || error("agp_ctx_create failed (no CUDA device; there is no CPU fallback)")
     e = Engine(ctx[], C_NULL, 0)
-    GC.@preserve Z kk ks kv lk p0 p1 begin
-        d = Ref(ModelDesc(0, Q, 0, Q, m, D, B, 2 #= tf32x3 =#, AGP.is_stochastic(inf) ? 1 : 0, κ, τ, Float64(T(AGP.jitt)), 1,
-                          pointer(lk), pointer(p0), pointer(p1), C_NULL, pointer(kk), pointer(ks), pointer(kv), pointer(Z), C_NULL))
+    GC.@preserve Z kk ks kv lk p0 p1 A begin
+        d = Ref(ModelDesc(model_kind(model), Q, 0, Q, m, D, B, precision_code(m, B), AGP.is_stochastic(inf) ? 1 : 0, κ, τ, Float64(T(AGP.jitt)),
+                          length(ls), pointer(lk), pointer(p0), pointer(p1), isempty(A) ? C_NULL : pointer(A),
+                          pointer(kk), pointer(ks), pointer(kv), pointer(Z), C_NULL))
         check(e, ccall((:agp_model_create, LIB), Cint, (Ptr{Cvoid}, Ref{ModelDesc}, Ref{Ptr{Cvoid}}), e.ctx, d, mdl))
     end
     e.model = mdl[]
-    if l isa AGP.PoissonLikelihood      # `expectation` rule of functions/utils.jl:16-19 (pred_nodes, pred_weights of predictions.jl:4)
+    # quirk Q3: the reference never re-raises HPupdated after update_hyperparameters! (autotuning.jl:45 is commented out), so K_mm
+    # stays the one factorised at the start of train! while K_nm follows the new kernel / Z
+    check(e, ccall((:agp_keep_stale_K, LIB), Cint, (Ptr{Cvoid}, Int32), e.model, 1))
+    if any(l -> l isa AGP.PoissonLikelihood, ls)      # `expectation` rule of functions/utils.jl:16-19 (pred_nodes, pred_weights of predictions.jl:4)
         nodes = collect(Float64, AGP.pred_nodes); w = collect(Float64, AGP.pred_weights)
         GC.@preserve nodes w check(e, ccall((:agp_set_quadrature, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int32),
                                             e.model, nodes, w, length(nodes)))
+    end
+    if model isa MOSVGP && !isnothing(model.A_opt)    # update_A! with ADAM (single_and_multi_output_utils.jl:87-118, states.jl:100-105)
+        ao = model.A_opt
+        check(e, ccall((:agp_set_A_optimiser, LIB), Cint, (Ptr{Cvoid}, Int32, Float64, Float64, Float64, Float64),
+                       e.model, 1, Float64(ao.eta), Float64(ao.beta[1]), Float64(ao.beta[2]), Float64(ao.epsilon)))
     end
     ENGINES[model] = e
     return e
 end
 
 # ---- the override -------------------------------------------------------------------------------------
-function AGP.update_parameters!(model::SVGP{T,L,<:AnalyticVI}, state, x::SubArray, y) where {T,L}
+function device_step!(model, state, x::SubArray, ys::Tuple)
     rows = x.parent                                   # RowVecs over the n×D Matrix
     idx = Int64.(x.indices[1])                        # 1-based minibatch (training.jl:51-55)
     B = length(idx)
     e = engine(model, AGP.batchsize(AGP.inference(model)))
     if e.uploaded != objectid(rows.X)
-        yall = parent(y)
-        ys = Ptr{Cvoid}[pointer(yall)]
-        GC.@preserve yall ys check(e, ccall((:agp_data_upload, LIB), Cint,
+        yall = map(parent, ys)                        # one target vector per task, whole data set
+        yp = Ptr{Cvoid}[pointer(v) for v in yall]
+        GC.@preserve yall yp check(e, ccall((:agp_data_upload, LIB), Cint,
             (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Int64, Ptr{Ptr{Cvoid}}, Cint),
-            e.model, rows.X, 0 #= f64 =#, 0 #= column-major =#, size(rows.X, 1), ys, yall isa AbstractVector{Float64} ? 0 : 1))
+            e.model, rows.X, 0 #= f64 =#, 0 #= column-major =#, size(rows.X, 1), yp, first(yall) isa AbstractVector{Float64} ? 0 : 1))
         e.uploaded = objectid(rows.X)
     end
     if AGP.isHPupdated(AGP.inference(model))
@@ -120,17 +148,35 @@ function AGP.update_parameters!(model::SVGP{T,L,<:AnalyticVI}, state, x::SubArra
     GC.@preserve idx check(e, ccall((:agp_step, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Int32, Int32, Float64),
                                     e.model, idx, B, 1, ρ))
     pull_posterior!(model, e); pull_lik_params!(model, e)                          # keep model.f[k].post in sync for Julia-side consumers
+    return e
+end
+
+function AGP.update_parameters!(model::SVGP{T,L,<:AnalyticVI}, state, x::SubArray, y) where {T,L}
+    device_step!(model, state, x, (y,))
+    return state
+end
+
+# training.jl:153-158: compute_kernel_matrices, update_A!, variational_updates -- all inside agp_step (the A optimiser was
+# registered with agp_set_A_optimiser); the mixing weights are mirrored back into model.A
+function AGP.update_parameters!(model::MOSVGP{T,L,<:AnalyticVI}, state, x::SubArray, ys) where {T,L}
+    e = device_step!(model, state, x, Tuple(ys))
+    if !isnothing(model.A_opt)
+        Q = length(model.f); nt = length(model.A); A = zeros(Q, nt)              # [T][Q] row-major == (Q, T) column-major
+        check(e, ccall((:agp_get_A, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), e.model, A))
+        for t in 1:nt; model.A[t][1] .= A[:, t]; end
+    end
     return state
 end
 
 # λ of PoissonLikelihood / HeteroscedasticLikelihood is re-estimated on the device by every step (poisson.jl:80,
 # heteroscedastic.jl:98): mirror it back into l.invlink.λ
 function pull_lik_params!(model, e::Engine)
-    l = AGP.likelihood(model)
-    if l isa Union{AGP.PoissonLikelihood,AGP.HeteroscedasticGaussianLikelihood}
-        v = Ref{Float64}(0.0)
-        check(e, ccall((:agp_get_lik_param, LIB), Cint, (Ptr{Cvoid}, Int32, Ref{Float64}), e.model, 0, v))
-        l.invlink.λ .= v[]
+    for (t, l) in enumerate(likelihoods(model))
+        if l isa Union{AGP.PoissonLikelihood,AGP.HeteroscedasticGaussianLikelihood}
+            v = Ref{Float64}(0.0)
+            check(e, ccall((:agp_get_lik_param, LIB), Cint, (Ptr{Cvoid}, Int32, Ref{Float64}), e.model, t - 1, v))
+            l.invlink.λ .= v[]
+        end
     end
 end
 
@@ -143,7 +189,8 @@ function pull_posterior!(model, e::Engine)
     end
 end
 
-function AGP.ELBO(model::SVGP{T,L,<:AnalyticVI}, state::NamedTuple, y) where {T,L}
+# analyticVI.jl:255-274 (single output) and :277-297 (multi-output: the sum over the tasks is formed on the device)
+function AGP.ELBO(model::Union{SVGP{T,L,<:AnalyticVI},MOSVGP{T,L,<:AnalyticVI}}, state::NamedTuple, y) where {T,L}
     e = ENGINES[model]; out = zeros(3)
     check(e, ccall((:agp_elbo, LIB), Cint, (Ptr{Cvoid}, Float64, Ptr{Float64}), e.model, Float64(AGP.ρ(AGP.inference(model))), out))
     return out[1] - out[2] - out[3]
@@ -151,7 +198,9 @@ end
 
 # update_hyperparameters! (hyperparameter/autotuning.jl:86-140): the Zygote call is replaced by agp_hyper_grads (closed-form gradient
 # of ELBO(m, x, y, μ₀, ks, Zs, state) on the device); update_kernel! / update_Z! (autotuning_utils.jl:47-82) stay in Julia and their
-# results are pushed back with agp_set_kernel / agp_set_Z; K_mm is refactorised by the next update_parameters! (HPupdated flag).
+# results are pushed back with agp_set_kernel / agp_set_Z.  Like the reference (quirk Q3: setHPupdated! at autotuning.jl:45 is
+# commented out) the flag is NOT raised here: K_mm keeps the factor of this train! call (agp_keep_stale_K(1) at engine creation)
+# while K_nm follows the new kernel / Z.
 function AGP.update_hyperparameters!(m::SVGP{T,L,<:AnalyticVI}, state, x, y) where {T,L}
     any(!isnothing ∘ AGP.opt, m.f) || any(!isnothing ∘ AGP.Zopt, m.f) || return state
     e = ENGINES[m]; Q = length(m.f); M = AGP.dim(m.f[1]); D = length(first(m.f[1].Z))
@@ -174,7 +223,6 @@ function AGP.update_hyperparameters!(m::SVGP{T,L,<:AnalyticVI}, state, x, y) whe
         end
         st
     end
-    AGP.setHPupdated!(AGP.inference(m), true)                         # -> agp_refresh_K at the next update_parameters!
     return merge(state, (; hyperopt_state=hp))
 end
 

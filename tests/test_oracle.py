@@ -271,3 +271,34 @@ def test_elbo_is_monotone_under_full_batch_cavi(lik):
         el.append(mo.ELBO(st, st["y_batch"]))
     el = np.asarray(el)
     assert np.all(np.diff(el) >= -1e-8 * np.abs(el[1:])), el
+
+
+def test_online_svgp_same_inducing_set_accumulates_batches():
+    """Property of natural_gradient!(::OnlineVarLatent) (analyticVI.jl:183-203): with the SAME inducing set on two batches,
+    kappa_a = K_ab / K ~ I and invD_a = -2 eta2 - K^-1, so eta2 after batch 2 = eta2 after batch 1 - kappa_2^T Theta kappa_2 and
+    eta1 accumulates kappa_2^T g_2: for a Gaussian likelihood (gradients independent of the posterior) the streamed posterior
+    equals the one-shot natural parameters of both batches up to the jitter in kappa_a."""
+    rng = np.random.default_rng(5)
+    D, nb, s2 = 2, 60, 0.05
+    Z = rng.uniform(-2, 2, (8, D))
+    k = O.Kernel("sqexp", scale=0.7)
+    mo = O.OnlineSVGP(k, O.GaussianLikelihood(s2), O.AnalyticVI())
+    Xs, ys, st = [], [], None
+    for b in range(2):
+        X = rng.uniform(-2, 2, (nb, D)); y = np.sin(X[:, 0]) + 0.1 * rng.standard_normal(nb)
+        Xs.append(X); ys.append(y)
+        mo, st = O.train_online(mo, X, y, Z, state=st, iterations=3)
+    gp = mo.f[0]
+    Kzz = O.kernelmatrix(k, Z) + O.JITTER_F64 * np.eye(8)
+    Kinv = np.linalg.inv(Kzz)
+    e2 = -(np.eye(8) / 2 + Kinv / 2)          # first batch carries invD_a = I (states.jl:95), kappa_a = I
+    e1 = np.zeros(8)
+    for X, y in zip(Xs, ys):
+        kap = O.kernelmatrix(k, X, Z) @ Kinv
+        e2 = e2 - kap.T @ kap / (2 * s2)
+        e1 = e1 + kap.T @ (y / s2)
+    assert np.linalg.norm(gp.eta2 - e2) / np.linalg.norm(e2) < 5e-3
+    assert np.linalg.norm(gp.eta1 - e1) / np.linalg.norm(e1) < 5e-3
+    # the ELBO (with extraKL) is finite and the posterior is a valid Gaussian
+    assert np.isfinite(mo.ELBO(st, st["y_batch"]))
+    assert np.all(np.linalg.eigvalsh(gp.Sigma) > 0)
