@@ -107,6 +107,7 @@ SIGNATURES = {
     "agp_launch_count": (C.c_int64, [C.c_void_p]),
     "agp_time_kernel": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_double_p]),
     "agp_use_graph": (C.c_int, [C.c_void_p, C.c_int]),
+    "agp_predict_f_cov": (C.c_int, [C.c_void_p, c_double_p, C.c_int64, c_double_p, c_double_p]),
     "agp_online_carry": (C.c_int, [C.c_void_p, C.c_int32, c_double_p, C.c_int32, c_double_p, c_double_p, C.c_double]),
     "agp_online_extra_kl": (C.c_int, [C.c_void_p, c_double_p]),
     "agp_local_updates_async": (C.c_int, [C.c_void_p]),

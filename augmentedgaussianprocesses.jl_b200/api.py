@@ -1243,11 +1243,23 @@ def _predict_f(model, X_test, cov: bool):
 
 def predict_f(model, X_test, state=None, *, cov: bool = False, diag: bool = True, obsdim: int = 1):
     """predictions.jl:136-163"""
-    if not diag:
-        raise NotImplementedError("full predictive covariance (diag=false) is not accelerated")
     X_test = np.asarray(X_test)
     if X_test.ndim == 2 and obsdim == 2:
         X_test = X_test.T
+    if cov and not diag:    # predictions.jl:45-49: full covariance (fp64 on the device, nt x nt per latent)
+        if model.world > 1:
+            raise NotImplementedError("full predictive covariance of a latent-sharded model")
+        Xd = np.ascontiguousarray(X_test if X_test.ndim == 2 else X_test[:, None], dtype=np.float64)
+        nt = Xd.shape[0]
+        eng = model._engine(max(model.inference.batchsize, 1) if model._eng is None else 1)
+        ql = model.n_latent_local
+        mu, S = np.empty((ql, nt)), np.empty((ql, nt, nt))
+        eng.ck(eng.lib.agp_predict_f_cov(eng.model, L.dptr(Xd), nt, L.dptr(mu), L.dptr(S)))
+        if isinstance(model, (MOSVGP, MOVGP)):  # predictions.jl:63-84
+            mu, S = model.A @ mu, np.einsum("tq,qij->tij", model.A**2, S)
+        if mu.shape[0] == 1:
+            return mu[0], S[0]
+        return tuple(mu), tuple(S)
     mu, var = _predict_f(model, X_test, cov)
     if mu.shape[0] == 1:
         return (mu[0], var[0]) if cov else mu[0]

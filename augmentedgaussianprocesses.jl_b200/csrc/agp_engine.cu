@@ -106,6 +106,7 @@ struct EngineBase {
   virtual int use_graph(int on) = 0;
   virtual int online_carry(int ql, const double* Za, int ma, const double* invDa, const double* prev_eta1, double prev_L) = 0;
   virtual int online_extra_kl(double* out) = 0;
+  virtual int predict_f_cov(const double* Xt, int64_t nt, double* mu, double* cov) = 0;
   virtual int local_updates_only() = 0;
   virtual int step_with_gradients(const int64_t* idx, int B, int base, const double* gmu_h, const double* gS_h) = 0;
   virtual void join_async() {}   // order the main stream behind the result stream of the pipelined asynchronous host-batch steps
@@ -1326,6 +1327,58 @@ struct Engine : EngineBase {
     }
     *out = tot;
     return AGP_OK;
+  }
+  // _predict_f(...; cov = true, diag = false) (training/predictions.jl:45-49): full predictive covariance of every owned latent,
+  //   Sigma_f = K** + jitter I - k* A k*^T,  A = K^-1 (I - Sigma K^-1)   ==   K** + jitter I - V* V*^T + (V* X^T)(V* X^T)^T
+  // in the whitened basis (V* = k* L^-T, Sigma_v = X^T X).  O(nt^2 m): fp64 SIMT throughout, off the hot path; Xt row-major [nt][D].
+  int predict_f_cov(const double* Xt, int64_t nt64, double* mu_out, double* cov_out) override {
+    if (!Xt || !mu_out || !cov_out || nt64 < 1) BAD("bad predict arguments");
+    if (nt64 > 16384) BAD("full predictive covariance: at most 16384 test points per call (the result is nt x nt)");
+    const int nt = (int)nt64;
+    if (!have_K) CKS(refresh_K());
+    CKS(ensure_factors());
+    const int64_t ldn = rup(nt, 4);
+    std::vector<double> xp((size_t)nt * Dp, 0.0), xn(nt, 0.0);
+    for (int i = 0; i < nt; ++i) {
+      double s_ = 0;
+      for (int k = 0; k < D; ++k) { double v = Xt[(size_t)i * D + k]; xp[(size_t)i * Dp + k] = v; s_ += v * v; }
+      xn[i] = s_;
+    }
+    double *dX = nullptr, *dxn = nullptr, *dKs = nullptr, *dV = nullptr, *dVS = nullptr, *dC = nullptr, *dmu = nullptr;
+    CKS(dalloc(&dX, xp.size())); CKS(dalloc(&dxn, (size_t)nt)); CKS(dalloc(&dKs, (size_t)nt * mp)); CKS(dalloc(&dV, (size_t)nt * mp));
+    CKS(dalloc(&dVS, (size_t)nt * mp)); CKS(dalloc(&dC, (size_t)nt * ldn)); CKS(dalloc(&dmu, (size_t)nt));
+    CK(cudaMemcpyAsync(dX, xp.data(), xp.size() * 8, cudaMemcpyHostToDevice, st()));
+    CK(cudaMemcpyAsync(dxn, xn.data(), xn.size() * 8, cudaMemcpyHostToDevice, st()));
+    int rc = AGP_OK;
+    for (int q = 0; q < Ql && rc == AGP_OK; ++q) {
+      Latent& L = lat[q];
+      GemmParams<double> g{};   // k* = k(X*, Z)
+      g.A = dX; g.lda = Dp; g.B = L.Zd; g.ldb = Dp; g.C = dKs; g.ldc = mp; g.M = nt; g.N = m; g.K = D;
+      g.alpha = 1.0; g.xx = dxn; g.xx_direct = 1; g.zz = L.zzd; g.scale2 = L.scale * L.scale; g.variance = L.variance; g.kernel_kind = L.kind;
+      gemm_simt_launch<double, false, false, EPI_KERNELFN>(g, 1, st());
+      GemmParams<double> gs = g;   // K** + jitter I (exact diagonal)
+      gs.B = dX; gs.C = dC; gs.ldc = ldn; gs.N = nt; gs.zz = dxn;
+      gemm_simt_launch<double, false, false, EPI_KERNELFN>(gs, 1, st());
+      kmm_fix_kernel<<<dim3((int)((ldn + 127) / 128), nt), 128, 0, st()>>>(dC, ldn, nt, nt, L.variance + jitter);
+      launches += 3;
+      dgemm_bm(false, false, dKs, mp, L.Linv, mp, dV, mp, nt, m, m, 1.0);      // V* = k* L^-T
+      dgemm_bm(false, false, dV, mp, L.Xv, mp, dVS, mp, nt, m, m, 1.0);        // V* X^T
+      rect_matvec_kernel<<<(nt + 127) / 128, 128, 0, st()>>>(dVS, mp, nt, m, L.tvec, dmu);   // mu* = (V* X^T) t
+      ++launches;
+      GemmParams<double> c1{};
+      c1.A = dV; c1.lda = mp; c1.B = dV; c1.ldb = mp; c1.C = dC; c1.ldc = ldn; c1.M = nt; c1.N = nt; c1.K = m; c1.alpha = -1.0; c1.beta = 1.0;
+      gemm_simt_launch<double, false, false, EPI_PLAIN>(c1, 1, st());
+      GemmParams<double> c2 = c1;
+      c2.A = dVS; c2.B = dVS; c2.alpha = 1.0;
+      gemm_simt_launch<double, false, false, EPI_PLAIN>(c2, 1, st());
+      launches += 2;
+      if (cudaMemcpy2DAsync(cov_out + (size_t)q * nt * nt, (size_t)nt * 8, dC, (size_t)ldn * 8, (size_t)nt * 8, nt, cudaMemcpyDeviceToHost, st()) != cudaSuccess) rc = AGP_ERR_CUDA;
+      if (cudaMemcpyAsync(mu_out + (size_t)q * nt, dmu, (size_t)nt * 8, cudaMemcpyDeviceToHost, st()) != cudaSuccess) rc = AGP_ERR_CUDA;
+      if (cudaStreamSynchronize(st()) != cudaSuccess) rc = AGP_ERR_CUDA;
+    }
+    cudaFree(dX); cudaFree(dxn); cudaFree(dKs); cudaFree(dV); cudaFree(dVS); cudaFree(dC); cudaFree(dmu);
+    if (rc == AGP_ERR_CUDA && ctx->err.empty()) ctx->err = "CUDA failure in predict_f_cov";
+    return rc;
   }
   // first iteration on a new batch (onlinetraining.jl:75-104): the expectation gradients come from the PREVIOUS model's local
   // updates on this batch; kernel matrices, natural gradient and global update with the current inducing set
@@ -2605,6 +2658,7 @@ int agp_online_carry(agp_model* model, int32_t latent_local, const double* Za, i
   ENG(model); return e->online_carry(latent_local, Za, ma, invDa, prev_eta1, prev_L);
 }
 int agp_online_extra_kl(agp_model* model, double* out) { ENG(model); return e->online_extra_kl(out); }
+int agp_predict_f_cov(agp_model* model, const double* Xt, int64_t nt, double* mu, double* cov) { ENG(model); return e->predict_f_cov(Xt, nt, mu, cov); }
 int agp_local_updates_async(agp_model* model) { ENG(model); return e->local_updates_only(); }
 int agp_step_with_gradients(agp_model* model, const int64_t* idx, int32_t B, int32_t base, const double* grad_mu, const double* grad_Sigma) {
   ENG(model); return e->step_with_gradients(idx, B, base, grad_mu, grad_Sigma);

@@ -561,6 +561,281 @@ umma_gemm_grouped_kernel(const GemmGroup* __restrict__ groups, const int ngroups
 }
 
 // =====================================================================================================
+// Third-generation main loop (opt-in: AGP_UMMA_V3=1).  MEASURED on a B200 (profiles/r2/gemm_bench_v1_v3.txt, gemm_trace_v3.txt):
+// bit-identical results, but 4 % SLOWER than the kernel above (25.0 / 22.7 / 22.7 us against 24.1 / 20.8 / 20.6 us at C2; 110 / 97 /
+// 100 us against 106 / 90 / 90 us at C3).  With two groups writing their A operands into tensor memory (tcgen05.st) while the MMA
+// warp's tcgen05.mma read theirs from it, single 12-MMA issue bursts stall for ~3000 cycles and the conversions stall with them:
+// tensor-memory traffic of the TS operand form, not converter throughput, is what paces the 3xTF32 main loop.  Kept as the
+// record of that experiment.  Motivation was: the per-role timeline of the
+// kernel above (profiles/microbench/gemm_trace.cu, profiles/r2/gemm_trace_v1.txt) shows a rigid 1500-cycle cadence per 32-deep
+// k-block at every size -- ONE worker group converts at a time (985 cycles of split arithmetic + ~520 cycles of mbarrier / fence /
+// tcgen05.wait::st round trips, nothing overlapped), while the MMA warp issues the block's 12 tcgen05.mma in ~900 cycles and then
+// idles.  Here BOTH worker groups convert concurrently: a group that becomes free takes the next k-block of the CTA from a
+// shared counter (so two conversions are always in flight, whichever unit they belong to), and the group that converts the LAST
+// k-block of a unit drains that unit's accumulator while the other group keeps the MMA warp fed.  Same operand layouts, same MMA
+// order (lo.hi, hi.lo, hi.hi), same epilogues as the kernel above; every mbarrier wait is bounded (trap instead of a hung GPU).
+// GROUPED: tensor maps / epilogue targets per latent from a device array (umma_gemm_grouped_kernel's launch form).
+namespace v3 {
+constexpr int RS3 = 3, CS3 = 3;
+constexpr int RING_BYTES = RS3 * RAW_BYTES + CS3 * CONV_BYTES;           // 192 KB
+constexpr int SMEM_BYTES = RING_BYTES + 1024 + 256;
+constexpr int NBAR = 2 * RS3 + 2 * CS3 + 4;                              // raw_full/empty, conv_full, mma_done, tmem_full/empty
+}
+
+__device__ __forceinline__ void mbar_wait_bounded(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) { printf("umma v3: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+  }
+}
+__device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+
+template <bool GROUPED>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+umma_gemm3_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1, float* __restrict__ C1, const UmmaEpilogue ep1,
+                  const GemmGroup* __restrict__ groups, const int ngroups, int64_t ldc, int64_t c_split_stride, const GemmWork work, const int epi_mode) {
+  using namespace v3;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bars = smem_base + v3::RING_BYTES;
+  auto raw_full = [&](int s) { return bars + 8u * s; };
+  auto raw_empty = [&](int s) { return bars + 8u * (RS3 + s); };
+  auto conv_full = [&](int s) { return bars + 8u * (2 * RS3 + s); };
+  auto mma_done = [&](int s) { return bars + 8u * (2 * RS3 + CS3 + s); };
+  auto tmem_full = [&](int b) { return bars + 8u * (2 * RS3 + 2 * CS3 + b); };
+  auto tmem_empty = [&](int b) { return bars + 8u * (2 * RS3 + 2 * CS3 + 2 + b); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + v3::RING_BYTES + 8 * NBAR);
+  int* grab = reinterpret_cast<int*>(smem_gen + v3::RING_BYTES + 8 * NBAR + 8);           // next k-block of this CTA to convert
+  volatile int* gsel = reinterpret_cast<volatile int*>(smem_gen + v3::RING_BYTES + 8 * NBAR + 16);   // [2 groups][2 parities]
+  const uint32_t conv_base = smem_base + RS3 * RAW_BYTES;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = gridDim.x, cta = blockIdx.x;
+  const int total_units = GROUPED ? work.total * ngroups : work.total;
+  auto unit_of = [&](int u, int& gq) -> WorkUnit {
+    if (GROUPED) return get_unit_grouped(work, ngroups, u, gq);
+    gq = 0;
+    return get_unit(work, u);
+  };
+
+  if (warp == 0 && lane == 0) {
+    if (GROUPED) { tma_prefetch_desc(&groups[0].tmA); tma_prefetch_desc(&groups[0].tmB); }
+    else { tma_prefetch_desc(&tmA1); tma_prefetch_desc(&tmB1); }
+    for (int s = 0; s < RS3; ++s) { mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), NUM_CONV_THREADS); }
+    for (int s = 0; s < CS3; ++s) { mbar_init(conv_full(s), NUM_CONV_THREADS); mbar_init(mma_done(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tmem_full(b), 1); mbar_init(tmem_empty(b), 4); }
+    *grab = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_ptr_smem)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (threadIdx.x == 0) UTT(0, 1);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int g = 0;
+      for (int r = 0;; ++r) {
+        const int u = unit_index(r, cta, G);
+        if (u >= total_units) break;
+        int gq; const WorkUnit wu = unit_of(u, gq);
+        const CUtensorMap* ma = GROUPED ? &groups[gq].tmA : &tmA1;
+        const CUtensorMap* mb = GROUPED ? &groups[gq].tmB : &tmB1;
+        for (int i = 0; i < wu.nkb; ++i, ++g) {
+          const int s = g % RS3;
+          mbar_wait_bounded(raw_empty(s), ((g / RS3) & 1) ^ 1);
+          UTT(0, 1000 + g);
+          const uint32_t dst = smem_base + s * RAW_BYTES;
+          mbar_expect_tx(raw_full(s), 2 * TILE_BYTES);
+          const int k = (wu.kb0 + i) * BK;
+          tma_load_2d(dst + 0 * TILE_BYTES, ma, raw_full(s), k, wu.tile_m * BM);
+          tma_load_2d(dst + 1 * TILE_BYTES, mb, raw_full(s), k, wu.tile_n * BN);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (k-blocks in order; accumulator lt & 1) =====
+    int g = 0, lt = 0;
+    for (int r = 0;; ++r) {
+      const int u = unit_index(r, cta, G);
+      if (u >= total_units) break;
+      int gq; const WorkUnit wu = unit_of(u, gq);
+      if (wu.nkb <= 0) continue;
+      const int ab = lt & 1;
+      mbar_wait_bounded(tmem_empty(ab), ((lt >> 1) & 1) ^ 1);
+      tc_fence_after();
+      if (lane == 0) UTT(1, 100000 + lt);
+      const uint32_t acc = tmem_base + ab * BN;
+      for (int i = 0; i < wu.nkb; ++i, ++g) {
+        const int s = g % CS3;
+        mbar_wait_bounded(conv_full(s), (g / CS3) & 1);
+        tc_fence_after();
+        if (lane == 0) UTT(1, 2000 + g);
+        if (elect_one()) {
+          const uint32_t b_hi = conv_base + s * CONV_BYTES, b_lo = b_hi + TILE_BYTES;
+          const uint32_t a_hi = tmem_base + TMEM_A0 + s * 64, a_lo = a_hi + 32;
+#pragma unroll
+          for (int kk = 0; kk < BK / 8; ++kk) {
+            const uint32_t off = kk * 32;
+            const uint64_t dbh = make_desc(b_hi + off), dbl = make_desc(b_lo + off);
+            tc_mma_tf32_ts(acc, a_lo + kk * 8, dbh, kIdesc, (i > 0 || kk > 0) ? 1u : 0u);  // small terms first
+            tc_mma_tf32_ts(acc, a_hi + kk * 8, dbl, kIdesc, 1u);
+            tc_mma_tf32_ts(acc, a_hi + kk * 8, dbh, kIdesc, 1u);
+          }
+          tc_commit(mma_done(s));
+          if (i == wu.nkb - 1) tc_commit(tmem_full(ab));
+        }
+        __syncwarp();
+        if (lane == 0) UTT(1, 3000 + g);
+      }
+      ++lt;
+    }
+  } else {
+    // ===== worker groups: whichever group is free converts the CTA's next k-block; the converter of a unit's last k-block
+    // drains that unit =====
+    const int grp = (warp - 2) >> 2;
+    const int ct = (threadIdx.x - 64) & 127;
+    const int q = warp & 3;
+    const int arow = q * 32 + lane;
+    int cur_r = 0, cur_g0 = 0, cur_lt = 0;      // cursor: round of the current unit, its first k-block index, its accumulator count
+    int it = 0;
+    for (;; ++it) {
+      if (ct == 0) gsel[grp * 2 + (it & 1)] = atomicAdd(grab, 1);
+      group_bar(2 + grp);
+      const int g = gsel[grp * 2 + (it & 1)];
+      // locate the unit that contains k-block g (units without k-blocks own no accumulator)
+      WorkUnit wu; int gq = 0; bool done = false;
+      for (;;) {
+        const int u = unit_index(cur_r, cta, G);
+        if (u >= total_units) { done = true; break; }
+        wu = unit_of(u, gq);
+        if (wu.nkb > 0 && g < cur_g0 + wu.nkb) break;
+        if (wu.nkb > 0) { cur_g0 += wu.nkb; ++cur_lt; }
+        ++cur_r;
+      }
+      if (done) break;
+      const int i = g - cur_g0, lt = cur_lt;
+      {
+        const int rs = g % RS3, s = g % CS3;
+        if (ct == 0) UTT(2 + grp, 7000 + g);
+        mbar_wait_bounded(raw_full(rs), (g / RS3) & 1);
+        if (ct == 0) UTT(2 + grp, 4000 + g);
+        mbar_wait_bounded(mma_done(s), ((g / CS3) & 1) ^ 1);
+        tc_fence_after();
+        if (ct == 0) UTT(2 + grp, 5000 + g);
+        uint8_t* base = smem_gen + rs * RAW_BYTES;
+        uint8_t* cbase_s = smem_gen + RS3 * RAW_BYTES + s * CONV_BYTES;
+        {
+          const float4* rowp = reinterpret_cast<const float4*>(base + arow * 128);
+          uint32_t h[32], l[32];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 v = rowp[c ^ (arow & 7)];
+            float t;
+            t = tf32_rna(v.x); h[4 * c + 0] = __float_as_uint(t); l[4 * c + 0] = __float_as_uint(tf32_rna(v.x - t));
+            t = tf32_rna(v.y); h[4 * c + 1] = __float_as_uint(t); l[4 * c + 1] = __float_as_uint(tf32_rna(v.y - t));
+            t = tf32_rna(v.z); h[4 * c + 2] = __float_as_uint(t); l[4 * c + 2] = __float_as_uint(tf32_rna(v.z - t));
+            t = tf32_rna(v.w); h[4 * c + 3] = __float_as_uint(t); l[4 * c + 3] = __float_as_uint(tf32_rna(v.w - t));
+          }
+          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + TMEM_A0 + s * 64;
+          TMEM_ST32(ta, h);
+          TMEM_ST32(ta + 32, l);
+        }
+        {
+          const float4* raw = reinterpret_cast<const float4*>(base + 1 * TILE_BYTES);
+          float4* hi = reinterpret_cast<float4*>(cbase_s);
+          float4* lo = reinterpret_cast<float4*>(cbase_s + TILE_BYTES);
+#pragma unroll
+          for (int uu = 0; uu < TILE_BYTES / 16 / NUM_CONV_THREADS; ++uu) {
+            const int e = ct + uu * NUM_CONV_THREADS;
+            const float4 v = raw[e];
+            float4 h, l;
+            h.x = tf32_rna(v.x); l.x = tf32_rna(v.x - h.x);
+            h.y = tf32_rna(v.y); l.y = tf32_rna(v.y - h.y);
+            h.z = tf32_rna(v.z); l.z = tf32_rna(v.z - h.z);
+            h.w = tf32_rna(v.w); l.w = tf32_rna(v.w - h.w);
+            hi[e] = h; lo[e] = l;
+          }
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        fence_proxy_async();
+        mbar_arrive(raw_empty(rs));
+        mbar_arrive(conv_full(s));
+        if (ct == 0) UTT(2 + grp, 6000 + g);
+      }
+      if (i != wu.nkb - 1) continue;
+      // ----- epilogue of unit lt (the other group goes on converting) -----
+      const int ab = lt & 1;
+      const int row = wu.tile_m * BM + q * 32 + lane;
+      UmmaEpilogue ep;
+      if (GROUPED) { ep.mode = epi_mode; ep.acc0 = groups[gq].acc0; ep.acc1 = groups[gq].acc1; ep.tvec = groups[gq].tvec; ep.cin = nullptr; }
+      else ep = ep1;
+      float* cbase = (GROUPED ? groups[gq].C : C1) + (int64_t)wu.split * c_split_stride;
+      float* crow = cbase + (int64_t)row * ldc + (int64_t)wu.tile_n * BN;
+      double acc_sq[4] = {0.0, 0.0, 0.0, 0.0}, acc_dot[4] = {0.0, 0.0, 0.0, 0.0};   // four interleaved fp64 chains per statistic
+      mbar_wait_bounded(tmem_full(ab), (lt >> 1) & 1);
+      tc_fence_after();
+      if (ct == 0) UTT(2 + grp, 300000 + lt);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t rr[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + c * 32);
+        TMEM_LD32(taddr, rr);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (c == BN / 32 - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty(ab));
+        }
+        if (ep.mode != UMMA_EPI_STATS_ONLY) {
+          float4* dst = reinterpret_cast<float4*>(crow + c * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            dst[j] = make_float4(__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1]), __uint_as_float(rr[4 * j + 2]), __uint_as_float(rr[4 * j + 3]));
+        }
+        if (ep.mode == UMMA_EPI_STORE_SUMSQ || ep.mode == UMMA_EPI_STATS_ONLY) {
+          const double* tv = ep.tvec + wu.tile_n * BN + c * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const double v = (double)__uint_as_float(rr[j]);
+            acc_sq[j & 3] = fma(v, v, acc_sq[j & 3]);
+            if (ep.mode == UMMA_EPI_STATS_ONLY) acc_dot[j & 3] = fma(v, tv[j], acc_dot[j & 3]);
+          }
+        }
+        if (ep.mode == UMMA_EPI_STORE_MIRROR && wu.tile_n != wu.tile_m) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            cbase[(int64_t)(wu.tile_n * BN + c * 32 + j) * ldc + row] = __uint_as_float(rr[j]);
+        }
+      }
+      if (ep.mode == UMMA_EPI_STORE_SUMSQ) atomicAdd(ep.acc0 + row, (acc_sq[0] + acc_sq[1]) + (acc_sq[2] + acc_sq[3]));
+      if (ep.mode == UMMA_EPI_STATS_ONLY) {
+        atomicAdd(ep.acc0 + row, (acc_sq[0] + acc_sq[1]) + (acc_sq[2] + acc_sq[3]));
+        atomicAdd(ep.acc1 + row, (acc_dot[0] + acc_dot[1]) + (acc_dot[2] + acc_dot[3]));
+      }
+      if (ct == 0) UTT(2 + grp, 400000 + lt);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) UTT(0, 2);
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// =====================================================================================================
 // Second-generation kernel (opt-in: AGP_UMMA_V2=1; NOT yet measured or parity-checked on a B200 -- written
 // after the round's GPU budget was spent, from the line-level stall profile profiles/r1/umma_stalls_by_line.txt).
 // What the profile showed for the kernel above: the two worker groups alternate by UNIT, so one group converts
@@ -1037,6 +1312,19 @@ static int sm_count() {
 // V = Knm L^-T runs on a side stream while the persistent m x m tail occupies one SM per CTA): 0 = all SMs
 static int g_grid_cap = 0;
 void umma_set_grid_cap(int n) { g_grid_cap = n; }
+// third-generation main loop (two conversions in flight): opt-in with AGP_UMMA_V3=1 (measured slower than the first generation)
+static bool v3_on() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("AGP_UMMA_V3");
+    on = (e && e[0] == '1') ? 1 : 0;
+    if (on) {
+      cudaFuncSetAttribute(umma_gemm3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, v3::SMEM_BYTES);
+      cudaFuncSetAttribute(umma_gemm3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, v3::SMEM_BYTES);
+    }
+  }
+  return on == 1;
+}
 static int grid_cap() { const int n = sm_count(); return (g_grid_cap > 0 && g_grid_cap < n) ? g_grid_cap : n; }
 
 int umma_gemm_nt(std::string* err, UmmaLatent& u, int a_which, int b_which, float* C, int M, int N, const UmmaEpilogue& ep,
@@ -1059,6 +1347,10 @@ int umma_gemm_nt(std::string* err, UmmaLatent& u, int a_which, int b_which, floa
     if (e2 != cudaSuccess) return fail(err, "umma_gemm_nt_v2_kernel", e2);
     return 0;
   }
+  if (v3_on())
+    launch_chain(umma_gemm3_kernel<false>, dim3(grid), dim3(NUM_THREADS), v3::SMEM_BYTES, st, mp->raw[a_which], mp->raw[b_which], C, ep,
+                 (const GemmGroup*)nullptr, 1, (int64_t)u.ldm, (int64_t)0, w, 0);
+  else
   launch_chain(umma_gemm_nt_kernel, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, mp->raw[a_which], mp->raw[b_which], C, (int64_t)u.ldm, (int64_t)0, w, ep);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(err, "umma_gemm_nt_kernel", e);
@@ -1094,6 +1386,9 @@ int umma_gram(std::string* err, UmmaLatent& u, float* Gpart, int B, int m, int* 
   if (u.v2)
     launch_chain(umma_gemm_nt_v2_kernel, dim3(grid), dim3(v2::NUM_THREADS), v2::SMEM_BYTES, st, mp->ut, mp->ut, mp->ut, Gpart, (int64_t)u.ldm,
                  (int64_t)m * u.ldm, w, ep, 0);
+  else if (v3_on())
+    launch_chain(umma_gemm3_kernel<false>, dim3(grid), dim3(NUM_THREADS), v3::SMEM_BYTES, st, mp->ut, mp->ut, Gpart, ep, (const GemmGroup*)nullptr, 1,
+                 (int64_t)u.ldm, (int64_t)m * u.ldm, w, 0);
   else
     launch_chain(umma_gemm_nt_kernel, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, mp->ut, mp->ut, Gpart, (int64_t)u.ldm, (int64_t)m * u.ldm, w, ep);
   *n_split = S;
@@ -1138,6 +1433,11 @@ int umma_gemm_nt_grouped(std::string* err, const UmmaGroups& gs, const UmmaLaten
   w.tri_mode = b_tri ? 1 : 0;
   const int all = w.total * gs.n;
   const int grid = all < grid_cap() ? all : grid_cap();
+  if (v3_on()) {
+    static const CUtensorMap none{};
+    launch_chain(umma_gemm3_kernel<true>, dim3(grid), dim3(NUM_THREADS), v3::SMEM_BYTES, st, none, none, (float*)nullptr, UmmaEpilogue{}, (const GemmGroup*)gs.dev, gs.n,
+                 (int64_t)u.ldm, (int64_t)0, w, epi_mode);
+  } else
   launch_chain(umma_gemm_grouped_kernel, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, (const GemmGroup*)gs.dev, gs.n, (int64_t)u.ldm, (int64_t)0, w, epi_mode);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(err, "umma_gemm_grouped_kernel", e);
@@ -1166,6 +1466,11 @@ int umma_gram_grouped(std::string* err, const UmmaGroups& gs, const UmmaLatent& 
   w.total_kb = total_kb; w.kb_per_split = per; w.tri_mode = 2;
   const int all = w.total * gs.n;
   const int grid = all < sms ? all : sms;
+  if (v3_on()) {
+    static const CUtensorMap none{};
+    launch_chain(umma_gemm3_kernel<true>, dim3(grid), dim3(NUM_THREADS), v3::SMEM_BYTES, st, none, none, (float*)nullptr, UmmaEpilogue{}, (const GemmGroup*)gs.dev, gs.n,
+                 (int64_t)u.ldm, (int64_t)m * u.ldm, w, (int)UMMA_EPI_STORE_MIRROR);
+  } else
   launch_chain(umma_gemm_grouped_kernel, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, (const GemmGroup*)gs.dev, gs.n, (int64_t)u.ldm, (int64_t)m * u.ldm, w,
                (int)UMMA_EPI_STORE_MIRROR);
   *n_split = S;

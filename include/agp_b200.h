@@ -264,6 +264,10 @@ int agp_set_lik_param(agp_model* model, int32_t task, double value);
 int agp_proba_link(agp_model* model, int32_t link, double p0, const double* mu, const double* var, int64_t n, double* pred,
                    double* pred_var);
 
+/* _predict_f(...; cov = true, diag = false) (training/predictions.jl:45-49): posterior mean [n_latent_local][nt] and FULL predictive
+ * covariance [n_latent_local][nt][nt] of the owned latents at nt <= 16384 test points (Xt: row-major fp64 [nt][D]); fp64 throughout. */
+int agp_predict_f_cov(agp_model* model, const double* Xt, int64_t nt, double* mu, double* cov);
+
 /* ---- measurement hooks ------------------------------------------------------------------------ */
 /* per-phase CUDA-event timers around the kernels of a step (off by default; adds event records). */
 int agp_profile_enable(agp_model* model, int on);

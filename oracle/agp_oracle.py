@@ -1416,8 +1416,8 @@ PRED_NODES = _GH_X * math.sqrt(2.0)  # predictions.jl:4
 PRED_WEIGHTS = _GH_W / math.sqrt(math.pi)
 
 
-def predict_f(model, X_test, cov=True):
-    """predictions.jl:25-50 (diag=true).  Returns (K, N*) arrays of latent moments."""
+def predict_f(model, X_test, cov=True, diag=True):
+    """predictions.jl:25-50.  Returns (K, N*) arrays of latent moments; diag=False: (K, N*, N*) full covariances (:45-49)."""
     X_test = np.asarray(X_test, dtype=np.float64)
     mus, vars_ = [], []
     for gp in model.f:
@@ -1428,12 +1428,19 @@ def predict_f(model, X_test, cov=True):
             m = gp.dim
             SK = sla.cho_solve((L, True), gp.Sigma.T).T  # Σ / K
             A = sla.cho_solve((L, True), np.eye(m) - SK)
-            vars_.append(kernelmatrix_diag(gp.kernel, X_test) + model.jitter - diag_ABt(ks @ A, ks))
+            if diag:
+                vars_.append(kernelmatrix_diag(gp.kernel, X_test) + model.jitter - diag_ABt(ks @ A, ks))
+            else:
+                kss = kernelmatrix(gp.kernel, X_test) + model.jitter * np.eye(X_test.shape[0])
+                S = kss - ks @ A @ ks.T
+                vars_.append(_symmetric_upper(S))
     mu = np.stack(mus)
     if isinstance(model, (MOSVGP, MOVGP)):
         mu_t = model.A @ mu
         if not cov:
             return mu_t
+        if not diag:
+            return mu_t, np.einsum("tq,qij->tij", model.A**2, np.stack(vars_))
         return mu_t, (model.A**2) @ np.stack(vars_)
     return (mu, np.stack(vars_)) if cov else mu
 

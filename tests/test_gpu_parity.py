@@ -746,3 +746,20 @@ def test_online_svgp_parity(agp, lik):
         assert abs(ee - eo) <= 1e-7 * max(1.0, abs(eo)), (b, ee, eo)
     with pytest.raises(ValueError):
         agp.OnlineSVGP(engine_kernel(agp, "sqexp", sc, 1.0), engine_lik(agp, lik, 3), agp.AnalyticSVI(16))
+
+
+@pytest.mark.parametrize("prec", ["f64", "tf32x3"])
+def test_predict_f_full_covariance(agp, prec):
+    """_predict_f(...; cov=true, diag=false) (training/predictions.jl:45-49): full predictive covariance against the oracle.  The
+    covariance itself is formed in fp64 on the device; in tf32x3 mode the posterior it is formed from carries that mode's error."""
+    n, D, m, B = (600, 3, 24, 128) if prec == "f64" else (4096, 8, 128, 256)
+    (mo, so), (me, se), (X, y, F) = run_pair(agp, "logistic", prec, n=n, D=D, m=m, B=B, iters=5)
+    Xt = np.random.default_rng(9).standard_normal((37, D))
+    mu_o, S_o = O.predict_f(mo, Xt, cov=True, diag=False)
+    mu_e, S_e = agp.predict_f(me, Xt, cov=True, diag=False)
+    tol = 1e-8 if prec == "f64" else TOL[prec]
+    assert S_e.shape == (37, 37)
+    assert rel_fro(mu_e, mu_o[0]) < tol and rel_fro(S_e, S_o[0]) < tol, (rel_fro(mu_e, mu_o[0]), rel_fro(S_e, S_o[0]))
+    assert np.allclose(S_e, S_e.T, rtol=0, atol=1e-10 * np.abs(S_e).max())
+    _, var_e = agp.predict_f(me, Xt, cov=True)                  # the diagonal agrees with the diag = true path
+    assert rel_fro(np.diag(S_e), var_e) < (1e-8 if prec == "f64" else 5e-4)
