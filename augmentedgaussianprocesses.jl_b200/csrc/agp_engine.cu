@@ -210,6 +210,7 @@ struct Engine : EngineBase {
   double *d_gradA = nullptr, *d_Amt = nullptr, *d_Avt = nullptr, *d_Abt = nullptr;
   double* d_lr = nullptr;          // Robbins-Monro step size of the current iteration (lik_update_kernel -> combine_kernel)
   bool fuse_lik_next = false, fuse_from_batch = false, lik_fused = false;   // rowfinish + local-update fusion (set by the step paths)
+  bool stats_use_early = false;    // moments stage 2 of this step only adds the last N tile (set by step_pool)
   bool racc2_precleared = false;   // the V X^T row-statistic accumulators were cleared off the critical chain (side stream)
   int tail_variant = 3;  // AGP_TAIL_VARIANT: 0 = agp_tail.cuh (generation 1, SIMT tile products), 2 = agp_tail2.cuh (DMMA, panel potf2, one
                          // launch per block step and latent), 3 (default) = agp_tail3.cuh (one persistent launch for all owned latents)
@@ -242,6 +243,13 @@ struct Engine : EngineBase {
   cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool pipeline = true;      // AGP_PIPELINE=0 disables
   bool prefetched = false;   // Knm / V / sum V^2 / idx_cur / xx_cur hold the minibatch at the device cursor
+  // early statistics (single latent, tf32x3, multi-launch tail): row block j of X = chol(P_v)^-1 is final after block step 2j+1 of the
+  // tail, so the side stream runs N tile j of the NEXT step's V X^T statistics (and that block's share of x_finalize) while the tail is
+  // still factorising the later blocks; only the last N tile (and the last row block's finalize) stay on the next step's chain
+  bool stats_early = false;     // racc[1..2] already hold the N tiles 0 .. ntn-2 of the prefetched minibatch's statistics
+  bool early_on = true;         // AGP_EARLY_STATS=0 disables
+  bool early_now = false;       // this step issues the early tiles (set by step_pool around step_update_b)
+  cudaEvent_t ev_blk[16] = {nullptr};
   int64_t* idx_prev = nullptr;  // indices of the minibatch the last step consumed (ELBO / getters after a prefetch)
 
   template <typename U>
@@ -393,6 +401,8 @@ struct Engine : EngineBase {
     CK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
     { const char* e = getenv("AGP_PIPELINE"); if (e && e[0] == '0') pipeline = false; }
+    { const char* e = getenv("AGP_EARLY_STATS"); if (e && e[0] == '0') early_on = false; }
+    for (int j = 0; j < 16; ++j) CK(cudaEventCreateWithFlags(&ev_blk[j], cudaEventDisableTiming));
     CKS(dalloc(&counters, 2)); CKS(dalloc(&status, 1));
     int64_t c0[2] = {1, 0};
     CK(cudaMemcpyAsync(counters, c0, sizeof(c0), cudaMemcpyHostToDevice, st()));
@@ -501,6 +511,7 @@ struct Engine : EngineBase {
         if (ev_step[s]) cudaEventDestroy(ev_step[s]);
       }
     }
+    for (int j = 0; j < 16; ++j) if (ev_blk[j]) cudaEventDestroy(ev_blk[j]);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
     void* ps[] = {idx_prev, xx_cur, pKS, pXb, pxxb, X, xx, y_all, ycls_all, Xb, xxb, stage, idx_pool, idx_cur, counters, status, d_lik_kind, d_p0, d_p1, d_A,
@@ -594,7 +605,7 @@ struct Engine : EngineBase {
     int64_t zero = 0;
     CK(cudaMemcpyAsync(counters + 1, &zero, 8, cudaMemcpyHostToDevice, st()));
     CK(cudaStreamSynchronize(st()));
-    n_lists = nl; pool_B = B; prefetched = false;
+    n_lists = nl; pool_B = B; prefetched = false; stats_early = false;
     drop_graph();
     return AGP_OK;
   }
@@ -712,7 +723,7 @@ struct Engine : EngineBase {
     int s = sync_status();
     have_K = (s == AGP_OK);
     K_dirty = false;
-    prefetched = false;
+    prefetched = false; stats_early = false;
     drop_graph();
     return s;
   }
@@ -751,7 +762,7 @@ struct Engine : EngineBase {
     if (ql < 0 || ql >= Ql || kind < 0 || kind > 2 || !(scale > 0) || !(variance > 0)) BAD("bad kernel parameters");
     lat[ql].kind = kind; lat[ql].scale = scale; lat[ql].variance = variance;
     if (stale_K_ok && have_K) K_dirty = true; else have_K = false;
-    prefetched = false;
+    prefetched = false; stats_early = false;
     drop_graph();
     return AGP_OK;
   }
@@ -905,8 +916,13 @@ struct Engine : EngineBase {
             // var_f - Ktilde = rowsum((V Sigma_v) o V),  mean_f = (V Sigma_v) eta1_v
             ep.mode = UMMA_EPI_STATS_SIGMA; ep.cin = (const float*)(const void*)L.V; ep.tvec = L.eta1v;
             CKS(umma_gemm_sigma(ctx_err(), L.um, L.ns, UM_V, B, ep, st()));
-          } else
-          CKS(umma_gemm_nt(ctx_err(), L.um, UM_V, UM_X, (float*)(void*)L.VS, B, m, ep, st()));
+          } else {
+            // with early statistics the N tiles 0 .. ntn-2 were accumulated behind the previous step's tail: only the last one is left
+            if (stats_use_early) umma_set_tile_range(m / 128 - 1, m / 128 - 1);
+            int sg = umma_gemm_nt(ctx_err(), L.um, UM_V, UM_X, (float*)(void*)L.VS, B, m, ep, st());
+            umma_set_tile_range(-1, -1);
+            CKS(sg);
+          }
         } else {
           GemmParams<T> s{};  // V X^T with Sigma_v = X^T X  (kappa * Sigma of latentgp.jl:189); X is lower triangular
           s.A = L.V; s.lda = ldm; s.B = L.Xv_T; s.ldb = ldm; s.C = L.VS; s.ldc = ldm; s.M = B; s.N = m; s.K = m; s.alpha = 1.0;
@@ -1073,7 +1089,7 @@ struct Engine : EngineBase {
     CK(cudaMemcpy(L.zz, znt.data(), znt.size() * sizeof(T), cudaMemcpyHostToDevice));
     if (L.knm_tc) CKS(umma_knm_setup(ctx_err(), L.uk, (const float*)(const void*)L.Z, Dp, m, D, (float*)(void*)L.Knm, ldm, Bcap, st()));
     if (stale_K_ok && have_K) K_dirty = true; else have_K = false;
-    prefetched = false;
+    prefetched = false; stats_early = false;
     drop_graph();
     return AGP_OK;
   }
@@ -1119,7 +1135,7 @@ struct Engine : EngineBase {
       L.logdetK = L.bklogdetK;
       CKS(whiten(L));
     }
-    kernel_matrices_stale = true; prefetched = false;
+    kernel_matrices_stale = true; prefetched = false; stats_early = false;
     drop_graph();
     int s_ = sync_status();
     have_K = (s_ == AGP_OK);
@@ -1419,7 +1435,7 @@ struct Engine : EngineBase {
     if (B < 1 || B > Bcap) BAD("The size of mini-batch is incorrect (negative or bigger than the batch capacity)");
     if (prec == AGP_PREC_TF32X3 && (B % 128)) BAD("TF32X3 precision needs B % 128 == 0");
     if (!from_batch) CKS(prep_idx(idx, B, base));
-    curB = B; cur_from_batch = from_batch; kernel_matrices_stale = false; prefetched = false;
+    curB = B; cur_from_batch = from_batch; kernel_matrices_stale = false; prefetched = false; stats_early = false;
     fuse_lik_next = fuse_in_step_moments && can_fuse_lik(); fuse_from_batch = from_batch; lik_fused = false;
     int sm = moments_impl(from_batch, B, true);
     fuse_lik_next = false;
@@ -1631,6 +1647,8 @@ struct Engine : EngineBase {
       if (tail_variant == 0) tail_step_kernel<0><<<tiles, TAIL_THREADS, TAIL_SMEM, st()>>>(tp);
       else launch_tail2(tail2_step_kernel, tiles, tp);
       ++launches;
+      // rows [64 k, 64 k + 64) of X are final now; every second block completes a 128-row N tile of the next step's statistics
+      if (early_now && (k & 1) && (k >> 1) + 1 < m / 128) cudaEventRecord(ev_blk[k >> 1], st());
     }
     ph_end();
   }
@@ -1646,8 +1664,9 @@ struct Engine : EngineBase {
     ph_begin(PH_FINAL);
     float* hi = umma_split_ptr(L.um, UM_X, 0);   // non-null only with the opt-in v2 GEMM: X leaves this kernel pre-split
     float* lo = umma_split_ptr(L.um, UM_X, 1);
-    launch_chain(x_finalize_kernel<T>, dim3(m), dim3(128), 0, (const double*)L.Xv, (int64_t)mp, m, (const double*)L.eta1v, L.Xv_T, (int64_t)ldm, hi, lo,
-                 L.tvec, (in_step && stochastic && !(fixed_lr > 0.0)) ? d_lr : (double*)nullptr, counters, rm_kappa, rm_tau, in_step ? 1 : 0);
+    const int row0 = early_now ? (m / 128 - 1) * 128 : 0;    // the earlier row blocks are finalised on the side stream (step_pool)
+    launch_chain(x_finalize_kernel<T>, dim3(m - row0), dim3(128), 0, (const double*)L.Xv, (int64_t)mp, m, (const double*)L.eta1v, L.Xv_T, (int64_t)ldm, hi, lo,
+                 L.tvec, (in_step && stochastic && !(fixed_lr > 0.0)) ? d_lr : (double*)nullptr, counters, rm_kappa, rm_tau, in_step ? 1 : 0, row0);
     ++launches;
     ph_end();
     L.muv_valid = false;
@@ -1753,12 +1772,16 @@ struct Engine : EngineBase {
       CKS(prep_idx(nullptr, B, 0, 0));
       CKS(moments_impl(false, B, true, 1));
     }
-    curB = B; cur_from_batch = false; kernel_matrices_stale = false; prefetched = false;
+    const bool use_early = stats_early && curB == B;        // (stats_early implies prefetched)
+    curB = B; cur_from_batch = false; kernel_matrices_stale = false; prefetched = false; stats_early = false;
     fuse_lik_next = can_fuse_lik(); fuse_from_batch = false; lik_fused = false;
+    stats_use_early = use_early;
     int sm2 = moments_impl(false, B, true, 2);    // V X^T, row statistics (needs the posterior of the previous step)
+    stats_use_early = false;
     fuse_lik_next = false;
     CKS(sm2);
     CKS(step_update_a(rho));                 // local updates, V^T g, Gram product: last readers of V / idx_cur
+    const bool early = pipe && early_ok();
     if (pipe) {
       CK(cudaEventRecord(ev_fork, ctx->stream));
       CK(cudaStreamWaitEvent(side, ev_fork, 0));
@@ -1775,18 +1798,53 @@ struct Engine : EngineBase {
         if (cudaMemsetAsync(lat[0].racc + ldB, 0, 2 * ldB * sizeof(double), st()) != cudaSuccess) s = AGP_ERR_CUDA;
         else racc2_precleared = true;
       }
-      if (s == AGP_OK && cudaEventRecord(ev_join, side) != cudaSuccess) s = AGP_ERR_CUDA;
+      if (s == AGP_OK && !early && cudaEventRecord(ev_join, side) != cudaSuccess) s = AGP_ERR_CUDA;
       cur_stream = nullptr;
       if (s != AGP_OK) { if (ctx->err.empty()) ctx->err = "CUDA failure while prefetching"; return s; }
     }
-    CKS(step_update_b(rho));
+    early_now = early;
+    int sb = step_update_b(rho);
+    early_now = false;
+    CKS(sb);
+    if (early) {
+      // side stream, behind the prefetch: N tile j of the next step's statistics as soon as block step 2j+1 has finished rows
+      // [128 j, 128 j + 128) of X (events recorded by chol_inv), preceded by that row block's fp32 shadow and t = X eta1_v entries
+      Latent& L = lat[0];
+      const int ntn = m / 128;
+      cur_stream = side;
+      int s = AGP_OK;
+      for (int j = 0; j + 1 < ntn && s == AGP_OK; ++j) {
+        if (cudaStreamWaitEvent(side, ev_blk[j], 0) != cudaSuccess) { s = AGP_ERR_CUDA; break; }
+        float* hi = umma_split_ptr(L.um, UM_X, 0);
+        float* lo = umma_split_ptr(L.um, UM_X, 1);
+        x_finalize_kernel<T><<<128, 128, 0, st()>>>((const double*)L.Xv, (int64_t)mp, m, (const double*)L.eta1v, L.Xv_T, (int64_t)ldm, hi, lo, L.tvec,
+                                                    (double*)nullptr, counters, rm_kappa, rm_tau, 0, 128 * j);
+        ++launches;
+        UmmaEpilogue ep{};
+        ep.mode = UMMA_EPI_STATS_ONLY; ep.acc0 = L.racc + ldB; ep.acc1 = L.racc + 2 * ldB; ep.tvec = L.tvec;
+        umma_set_tile_range(j, j);
+        s = umma_gemm_nt(ctx_err(), L.um, UM_V, UM_X, (float*)(void*)L.VS, B, m, ep, st());
+        umma_set_tile_range(-1, -1);
+        ++launches;
+      }
+      if (s == AGP_OK && cudaEventRecord(ev_join, side) != cudaSuccess) s = AGP_ERR_CUDA;
+      cur_stream = nullptr;
+      if (s != AGP_OK) { if (ctx->err.empty()) ctx->err = "CUDA failure in the early statistics"; return s; }
+    }
     if (pipe) {
       CK(cudaStreamWaitEvent(ctx->stream, ev_join, 0));
       prefetched = true;
+      stats_early = early;
       kernel_matrices_stale = true;          // Knm / V now belong to the NEXT minibatch
     }
     have_step = true;
     return AGP_OK;
+  }
+  // the early statistics need: one tf32x3 latent whose tail is the multi-launch chain (row blocks finish launch by launch), at
+  // least two N tiles, 64-row tail blocks that pair up into 128-row tiles, no padding of m, and the first-generation GEMM kernel
+  bool early_ok() const {
+    return early_on && prec == AGP_PREC_TF32X3 && Ql == 1 && Qg == 1 && tail_variant == 2 && !ns_tail_now && !is_vgp && !peer && mp == m && m >= 256 &&
+           m / 128 <= 16 && TNB == 64 && lat[0].factor_valid && !lat[0].um.v2;
   }
 
   // rebuild Knm / V of the minibatch the last step consumed (after a prefetch or a predict_f overwrote them)
@@ -1797,7 +1855,7 @@ struct Engine : EngineBase {
       xx_gather_kernel<T><<<(curB + 255) / 256, 256, 0, st()>>>(idx_cur, curB, xx, xx_cur);
       ++launches;
     }
-    prefetched = false;
+    prefetched = false; stats_early = false;
     kernel_matrices_stale = false;
     return moments_impl(cur_from_batch, curB, true, 1);
   }
@@ -1818,7 +1876,7 @@ struct Engine : EngineBase {
       return step_update(rho);
     }
     if (want_graph && !prof && !capturing) {
-      const bool need_prime = pipeline && (!prefetched || curB != B || (prec == AGP_PREC_TF32X3 && Ql == 1 && !racc2_precleared));
+      const bool need_prime = pipeline && (!prefetched || curB != B || (prec == AGP_PREC_TF32X3 && Ql == 1 && !racc2_precleared) || (early_ok() && !stats_early));
       if (!gexec || gB != B || grho != rho || g_nskey != ns_key || need_prime) {
         drop_graph();
         if (need_prime) return step_pool(B, rho);  // priming step (brings the pipeline to its steady state); later calls replay the graph
@@ -1918,7 +1976,7 @@ struct Engine : EngineBase {
       launches += g_launches_b;
       for (auto& L : lat) L.muv_valid = false;
       lat[0].muv_valid = true;     // the graph recomputed mu_v of latent 0
-      curB = B; cur_from_batch = true; kernel_matrices_stale = false; prefetched = false; have_step = true;
+      curB = B; cur_from_batch = true; kernel_matrices_stale = false; prefetched = false; stats_early = false; have_step = true;
       h_mu_valid = true;
       return AGP_OK;
     }
@@ -2052,7 +2110,7 @@ struct Engine : EngineBase {
     CK(cudaEventRecord(ev_p1, side));
     // main stream: ONE graph -- statistics, local updates, Gram | ev_vfree | wait(result kernels of step i-1) | update + tail
     CK(cudaStreamWaitEvent(ctx->stream, ev_p1, 0));
-    curB = B; cur_from_batch = true; kernel_matrices_stale = false; prefetched = false;
+    curB = B; cur_from_batch = true; kernel_matrices_stale = false; prefetched = false; stats_early = false;
     CKS(run_piece(1, ctx->stream, [&]() -> int {
       fuse_lik_next = can_fuse_lik(); fuse_from_batch = true; lik_fused = false;
       racc2_precleared = (prec == AGP_PREC_TF32X3 && Ql == 1);
@@ -2269,7 +2327,7 @@ struct Engine : EngineBase {
   int set_counters(int64_t t, int64_t cur) override {
     if (t < 1 || cur < 0) BAD("bad counters");
     int64_t c[2] = {t, cur};
-    prefetched = false; drop_graph();
+    prefetched = false; stats_early = false; drop_graph();
     h_steps = t - 1;
     CK(cudaStreamSynchronize(st()));
     CK(cudaMemcpy(counters, c, 16, cudaMemcpyHostToDevice));
@@ -2451,7 +2509,7 @@ struct Engine : EngineBase {
     racc2_precleared = false;
     kernel_matrices_stale = true;
     if (prefetched) {  // fall back to the last consumed minibatch (same as predict_f)
-      prefetched = false;
+      prefetched = false; stats_early = false;
       cudaMemcpyAsync(idx_cur, idx_prev, (size_t)curB * 8, cudaMemcpyDeviceToDevice, st());
       xx_gather_kernel<T><<<(curB + 255) / 256, 256, 0, st()>>>(idx_cur, curB, xx, xx_cur);
       ++launches;
@@ -2497,7 +2555,7 @@ int Engine<T>::predict_f(const void* Xt, int x_dtype, int x_layout, int64_t nt, 
   cudaMemsetAsync(status, 0, sizeof(int), st());
   kernel_matrices_stale = true;
   if (prefetched) {  // the prefetched kernel matrices were overwritten: fall back to the last consumed minibatch
-    prefetched = false; drop_graph();
+    prefetched = false; stats_early = false; drop_graph();
     cudaMemcpyAsync(idx_cur, idx_prev, (size_t)curB * 8, cudaMemcpyDeviceToDevice, st());
     xx_gather_kernel<T><<<(curB + 255) / 256, 256, 0, st()>>>(idx_cur, curB, xx, xx_cur);
     ++launches;

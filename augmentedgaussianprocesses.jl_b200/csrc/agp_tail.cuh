@@ -296,12 +296,12 @@ template <typename T>
 __global__ void x_finalize_kernel(const double* __restrict__ X, int64_t ld, int m, const double* __restrict__ eta1v,
                                   T* __restrict__ shadow, int64_t lds, float* __restrict__ hi, float* __restrict__ lo,
                                   double* __restrict__ tvec, double* __restrict__ lr_next, int64_t* __restrict__ counters,
-                                  double rm_kappa, double rm_tau, int bump) {
+                                  double rm_kappa, double rm_tau, int bump, int row0 = 0) {
   pdl_prologue();
-  const int i = blockIdx.x;
+  const int i = blockIdx.x + row0;    // launches may cover a block of rows (rows leave the tail block by block)
   // Robbins-Monro step size of the NEXT iteration (inference/optimisers.jl:14-19; the counter is bumped after this kernel):
   // one thread of one block, hidden behind the rest of the grid instead of sitting on the next step's chain
-  if (i == 0 && threadIdx.x == 0) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
     if (lr_next) *lr_next = pow(rm_tau + (double)(counters[0] + 1), -rm_kappa);
     if (bump) { counters[0] += 1; counters[1] += 1; }   // end of the step: Robbins-Monro counter and minibatch-list cursor
   }

@@ -55,11 +55,13 @@ constexpr uint32_t kIdesc = make_idesc_tf32(BM, BN);
 struct GemmWork {
   int ntm, ntn, nsplit, total;     // tiles along M, N, split-K slices, number of units
   int total_kb, kb_per_split, tri_mode;
+  int u0;                          // first unit of this launch in the unit enumeration (launches restricted to a range of N tiles)
 };
 struct WorkUnit { int tile_m, tile_n, split, kb0, nkb; };
 
 __device__ __forceinline__ WorkUnit get_unit(const GemmWork& w, int u) {
   WorkUnit r;
+  u += w.u0;
   if (w.tri_mode == 2) {
     r.split = u % w.nsplit;
     int p = u / w.nsplit;                      // p-th upper tile, row-major over (tile_m <= tile_n)
@@ -1312,6 +1314,9 @@ static int sm_count() {
 // V = Knm L^-T runs on a side stream while the persistent m x m tail occupies one SM per CTA): 0 = all SMs
 static int g_grid_cap = 0;
 void umma_set_grid_cap(int n) { g_grid_cap = n; }
+// N-tile range [lo, hi] of the NEXT triangular-B umma_gemm_nt launches (lo < 0: all tiles)
+static int g_tn_lo = -1, g_tn_hi = -1;
+void umma_set_tile_range(int lo, int hi) { g_tn_lo = lo; g_tn_hi = hi; }
 // third-generation main loop (two conversions in flight): opt-in with AGP_UMMA_V3=1 (measured slower than the first generation)
 static bool v3_on() {
   static int on = -1;
@@ -1335,6 +1340,12 @@ int umma_gemm_nt(std::string* err, UmmaLatent& u, int a_which, int b_which, floa
   w.ntm = M / BM; w.ntn = N / BN; w.nsplit = 1; w.total = w.ntm * w.ntn;
   w.total_kb = u.m / BK; w.kb_per_split = w.total_kb;
   w.tri_mode = (b_which == UM_LINV || b_which == UM_X) ? 1 : 0;
+  if (g_tn_lo >= 0) {
+    // tri_mode 1 enumerates the units N tile by N tile, last tile first: tile_n = ntn - 1 - u / ntm
+    if (w.tri_mode != 1 || g_tn_hi >= w.ntn || g_tn_lo > g_tn_hi) return fail(err, "bad N-tile range");
+    w.u0 = (w.ntn - 1 - g_tn_hi) * w.ntm;
+    w.total = (g_tn_hi - g_tn_lo + 1) * w.ntm;
+  }
   const int grid = w.total < grid_cap() ? w.total : grid_cap();
   if (u.v2) {
     // v2 & 2: keep the in-kernel split of the right operand (A/B experiment); otherwise L^-1 / X arrive pre-split

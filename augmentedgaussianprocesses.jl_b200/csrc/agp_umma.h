@@ -58,6 +58,9 @@ int umma_scale_transpose(std::string* err, UmmaLatent& u, const float* V, const 
 void umma_set_pdl(bool on);
 // cap of the persistent grid of umma_gemm_nt (0 = every SM): set around launches that run beside the persistent m x m tail
 void umma_set_grid_cap(int n);
+// restrict the NEXT umma_gemm_nt launches with a lower-triangular right operand to the N tiles [lo, hi] (lo < 0: all tiles): the step's
+// V X^T statistics are issued N tile by N tile as the rows of X leave the m x m tail
+void umma_set_tile_range(int lo, int hi);
 int umma_gram(std::string* err, UmmaLatent& u, float* Gpart, int B, int m, int* n_split, cudaStream_t st);
 
 // ---- grouped launches: the same-shaped product of several latent GPs in ONE persistent launch (multi-latent models: the per-launch

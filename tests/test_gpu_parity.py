@@ -330,12 +330,14 @@ def test_baseline_configs_full_step_size_vs_oracle(agp, cfg):
     check_pair(agp, (mo, so), (me, se), tol)
 
 
-@pytest.mark.parametrize("precision", ["f64", "tf32x3"])
-def test_pipelined_pool_steps_match_host_list_steps(agp, precision):
+@pytest.mark.parametrize("precision,m,B", [("f64", 128, 256), ("tf32x3", 128, 256), ("tf32x3", 256, 512), ("tf32x3", 512, 1024)])
+def test_pipelined_pool_steps_match_host_list_steps(agp, precision, m, B):
     """resident-list steps are software-pipelined (next minibatch's Knm / V built on a side stream during the tail) and
     CUDA-graph replayed; they must give the same posterior / ELBO / state as plain host-list steps, including an ELBO
-    and a prediction in the middle of the run (which invalidate the prefetch)."""
-    n, D, m, B, iters = 4096, 8, 128, 256, 7
+    and a prediction in the middle of the run (which invalidate the prefetch).  m >= 256 (tf32x3) also runs the early
+    statistics: N tile j of the next step's V X^T product is issued on the side stream as soon as the tail has finished rows
+    [128 j, 128 j + 128) of X, and only the last tile stays on the next step's chain."""
+    n, D, iters = 8192, 8, 7
     X, y, Z, mbs, F, rng = make_data("logistic", n, D, m, B, iters, seed=11)
     kern = agp.SqExponentialKernel() @ agp.ScaleTransform(1 / np.sqrt(D))
     ref = agp.SVGP(kern, agp.LogisticLikelihood(), agp.AnalyticSVI(B), Z, precision=precision)
