@@ -246,8 +246,15 @@ struct Engine : EngineBase {
   // early statistics (single latent, tf32x3, multi-launch tail): row block j of X = chol(P_v)^-1 is final after block step 2j+1 of the
   // tail, so the side stream runs N tile j of the NEXT step's V X^T statistics (and that block's share of x_finalize) while the tail is
   // still factorising the later blocks; only the last N tile (and the last row block's finalize) stay on the next step's chain
+  // split Gram (single latent, tf32x3, multi-launch tail; opt-in AGP_SPLIT_GRAM=1 -- measured SLOWER, 196 vs 189 us per C2 step: the
+  // cross-stream join costs the programmatic edges of the chain): the tail's first kernel only needs tile (0, 0) of
+  // P_v, so that tile's Gram slices + its share of combine_kernel + the first 64 x 64 factorisation run on the main stream while the
+  // other nine upper tiles and their combine run beside them on the side stream; the block steps wait for both
+  bool split_gram_on = false, split_gram_now = false, allow_split_gram = false;
+  int split_SA = 0, split_SB = 0;
+  cudaEvent_t ev_g0 = nullptr, ev_gb = nullptr;
   bool stats_early = false;     // racc[1..2] already hold the N tiles 0 .. ntn-2 of the prefetched minibatch's statistics
-  bool early_on = true;         // AGP_EARLY_STATS=0 disables
+  bool early_on = false;        // AGP_EARLY_STATS=1 enables (measured: no gain)
   bool early_now = false;       // this step issues the early tiles (set by step_pool around step_update_b)
   cudaEvent_t ev_blk[16] = {nullptr};
   int64_t* idx_prev = nullptr;  // indices of the minibatch the last step consumed (ELBO / getters after a prefetch)
@@ -343,6 +350,7 @@ struct Engine : EngineBase {
     int want = std::max(1, (2 * 148 + tiles - 1) / tiles);
     k_chunk = (int)rup((Bcap + want - 1) / want, 64);
     n_split = (Bcap + k_chunk - 1) / k_chunk;
+    if (prec == AGP_PREC_TF32X3 && Ql == 1) n_split = std::max(n_split, 32);   // split Gram: tile (0, 0) alone over up to 32 slices
 
     lat.resize(Ql);
     for (int q = 0; q < Ql; ++q) {
@@ -401,7 +409,9 @@ struct Engine : EngineBase {
     CK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
     { const char* e = getenv("AGP_PIPELINE"); if (e && e[0] == '0') pipeline = false; }
-    { const char* e = getenv("AGP_EARLY_STATS"); if (e && e[0] == '0') early_on = false; }
+    { const char* e = getenv("AGP_EARLY_STATS"); if (e && e[0] == '1') early_on = true; }
+    { const char* e = getenv("AGP_SPLIT_GRAM"); if (e && e[0] == '1') split_gram_on = true; }
+    CK(cudaEventCreateWithFlags(&ev_g0, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ev_gb, cudaEventDisableTiming));
     for (int j = 0; j < 16; ++j) CK(cudaEventCreateWithFlags(&ev_blk[j], cudaEventDisableTiming));
     CKS(dalloc(&counters, 2)); CKS(dalloc(&status, 1));
     int64_t c0[2] = {1, 0};
@@ -512,6 +522,8 @@ struct Engine : EngineBase {
       }
     }
     for (int j = 0; j < 16; ++j) if (ev_blk[j]) cudaEventDestroy(ev_blk[j]);
+    if (ev_g0) cudaEventDestroy(ev_g0);
+    if (ev_gb) cudaEventDestroy(ev_gb);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
     void* ps[] = {idx_prev, xx_cur, pKS, pXb, pxxb, X, xx, y_all, ycls_all, Xb, xxb, stage, idx_pool, idx_cur, counters, status, d_lik_kind, d_p0, d_p1, d_A,
@@ -907,7 +919,7 @@ struct Engine : EngineBase {
       {
         ph_begin(PH_KSIGMA);
         if (prec == AGP_PREC_TF32X3) {
-          if (!(racc2_precleared && Ql == 1)) CK(cudaMemsetAsync(L.racc + ldB, 0, 2 * ldB * sizeof(double), st()));
+          if (!((racc2_precleared || stats_use_early) && Ql == 1)) CK(cudaMemsetAsync(L.racc + ldB, 0, 2 * ldB * sizeof(double), st()));
           racc2_precleared = false;
           UmmaEpilogue ep{};
           ep.mode = UMMA_EPI_STATS_ONLY; ep.acc0 = L.racc + ldB; ep.acc1 = L.racc + 2 * ldB; ep.tvec = L.tvec;
@@ -1508,6 +1520,34 @@ struct Engine : EngineBase {
         ph_end();
       }
       if (grp) { umma_set_pdl(false); continue; }     // the Gram products of all owned latents follow in one grouped launch
+      if (split_gram_ok()) {
+        // side stream: tiles 1.. of the Gram product + their natural-parameter update; main stream: tile (0, 0) (step_update_b goes on
+        // with its share of the update and the tail's first kernel, and joins before the block steps)
+        ph_begin(PH_GRAM);
+        const int sms = 148, ut = (m / 128) * (m / 128 + 1) / 2;
+        split_SA = umma_gram_splits(B, std::min(32, n_split));
+        split_SB = umma_gram_splits(B, std::max(1, std::min(n_split, (sms - split_SA) / (ut - 1))));
+        umma_set_pdl(false);
+        CK(cudaEventRecord(ev_g0, ctx->stream));
+        CK(cudaStreamWaitEvent(side, ev_g0, 0));
+        cudaStream_t saved = cur_stream;
+        cur_stream = side;
+        int sg = umma_gram_part(ctx_err(), L.um, (float*)(void*)L.Gpart, B, m, 1, split_SB, sms - split_SA, st());
+        ++launches;
+        if (sg == AGP_OK) { launch_combine(L, rho, split_SB, 2); }
+        if (sg == AGP_OK && cudaEventRecord(ev_gb, side) != cudaSuccess) sg = AGP_ERR_CUDA;
+        cur_stream = saved;
+        CKS(sg);
+        umma_set_pdl(tail_pdl && !prof);      // scale_transpose -> tile (0, 0): programmatic edge on the main stream
+        int sa_ = umma_gram_part(ctx_err(), L.um, (float*)(void*)L.Gpart, B, m, 0, split_SA, split_SA, st());
+        umma_set_pdl(false);
+        CKS(sa_);
+        ++launches;
+        L.gram_splits = split_SA;
+        split_gram_now = true;
+        ph_end();
+        continue;
+      }
       ph_begin(PH_GRAM);
       int ns = n_split;
       if (prec == AGP_PREC_TF32X3) {
@@ -1538,22 +1578,31 @@ struct Engine : EngineBase {
     CK(cudaGetLastError());
     return AGP_OK;
   }
+  // combine_kernel: split-K reduction of the Gram partials + natural-parameter update; blk: 0 = whole matrix, 1 / 2 = split Gram parts
+  void launch_combine(Latent& L, double rho, int ns, int blk) {
+    TailParams tp{};
+    tp.m = m; tp.mp = mp; tp.ld = mp; tp.n_split = ns; tp.gpart_stride = (int64_t)m * ldm; tp.gpart_ld = ldm;
+    tp.g_mirrored = (prec == AGP_PREC_TF32X3) ? 1 : 0;
+    tp.v1 = L.v1; tp.mu0v = L.mu0v; tp.eta1 = L.eta1v; tp.eta2 = L.eta2v; tp.P = L.P;
+    tp.counters = counters; tp.stochastic = stochastic; tp.rm_kappa = rm_kappa; tp.rm_tau = rm_tau; tp.rho = rho;
+    tp.logdet = L.logdetP; tp.status = status;
+    tp.lr = d_lr; tp.v1_zero = (prec == AGP_PREC_TF32X3) ? L.v1 : nullptr;
+    tp.eta1_off = L.online ? L.on_c1v : nullptr; tp.eta2_off = L.online ? L.on_C2v : nullptr;
+    tp.blk_mode = blk;
+    launch_chain(combine_kernel<T>, blk == 1 ? dim3(1, 128) : grid_mp(), dim3(128), 0, tp, (const T*)L.Gpart);
+    ++launches;
+  }
+  bool split_gram_ok() const {
+    return split_gram_on && allow_split_gram && pipeline && !prof && prec == AGP_PREC_TF32X3 && Ql == 1 && Qg == 1 && tail_variant == 2 && !ns_tail_now &&
+           !is_vgp && !peer && mp == m && m >= 256 && !lat[0].um.v2 && !lat[0].online && n_split >= 16;
+  }
   // natural-parameter update + the m x m tail of every owned latent
   int step_update_b(double rho) {
     for (int q = 0; q < Ql; ++q) {
       Latent& L = lat[q];
       const int ns = L.gram_splits;
       ph_begin(PH_COMBINE);
-      TailParams tp{};
-      tp.m = m; tp.mp = mp; tp.ld = mp; tp.n_split = ns; tp.gpart_stride = (int64_t)m * ldm; tp.gpart_ld = ldm;
-      tp.g_mirrored = (prec == AGP_PREC_TF32X3) ? 1 : 0;
-      tp.v1 = L.v1; tp.mu0v = L.mu0v; tp.eta1 = L.eta1v; tp.eta2 = L.eta2v; tp.P = L.P;
-      tp.counters = counters; tp.stochastic = stochastic; tp.rm_kappa = rm_kappa; tp.rm_tau = rm_tau; tp.rho = rho;
-      tp.logdet = L.logdetP; tp.status = status;
-      tp.lr = d_lr; tp.v1_zero = (prec == AGP_PREC_TF32X3) ? L.v1 : nullptr;
-      tp.eta1_off = L.online ? L.on_c1v : nullptr; tp.eta2_off = L.online ? L.on_C2v : nullptr;
-      launch_chain(combine_kernel<T>, grid_mp(), dim3(128), 0, tp, (const T*)L.Gpart);
-      ++launches;
+      launch_combine(L, rho, ns, split_gram_now ? 1 : 0);
       ph_end();
       if (ns_tail_now) CKS(eta_to_moments_ns(L));
       else if (tail_variant != 3) {
@@ -1639,6 +1688,7 @@ struct Engine : EngineBase {
     if (tail_variant == 0) tail_potf2_first_kernel<0><<<1, TAIL_THREADS, TAIL_SMEM, st()>>>(tp);
     else launch_tail2(tail2_potf2_first_kernel<0>, 1, tp);
     ++launches;
+    if (split_gram_now) { cudaStreamWaitEvent(st(), ev_gb, 0); split_gram_now = false; }   // the rest of P_v (side stream) is needed from the first block step on
     for (int k = 0; k < tp.nblk; ++k) {
       int r = tp.nblk - 1 - k;
       int tiles = r * (r + 1) / 2 + r * (k + 1) + k;
@@ -1780,7 +1830,10 @@ struct Engine : EngineBase {
     stats_use_early = false;
     fuse_lik_next = false;
     CKS(sm2);
-    CKS(step_update_a(rho));                 // local updates, V^T g, Gram product: last readers of V / idx_cur
+    allow_split_gram = pipe;
+    int sa = step_update_a(rho);             // local updates, V^T g, Gram product: last readers of V / idx_cur
+    allow_split_gram = false;
+    CKS(sa);
     const bool early = pipe && early_ok();
     if (pipe) {
       CK(cudaEventRecord(ev_fork, ctx->stream));
@@ -1835,6 +1888,7 @@ struct Engine : EngineBase {
       CK(cudaStreamWaitEvent(ctx->stream, ev_join, 0));
       prefetched = true;
       stats_early = early;
+      if (early) racc2_precleared = false;   // the accumulators hold the early tiles, not zeros
       kernel_matrices_stale = true;          // Knm / V now belong to the NEXT minibatch
     }
     have_step = true;
@@ -1876,7 +1930,7 @@ struct Engine : EngineBase {
       return step_update(rho);
     }
     if (want_graph && !prof && !capturing) {
-      const bool need_prime = pipeline && (!prefetched || curB != B || (prec == AGP_PREC_TF32X3 && Ql == 1 && !racc2_precleared) || (early_ok() && !stats_early));
+      const bool need_prime = pipeline && (!prefetched || curB != B || (prec == AGP_PREC_TF32X3 && Ql == 1 && !(racc2_precleared || stats_early)) || (early_ok() && !stats_early));
       if (!gexec || gB != B || grho != rho || g_nskey != ns_key || need_prime) {
         drop_graph();
         if (need_prime) return step_pool(B, rho);  // priming step (brings the pipeline to its steady state); later calls replay the graph
@@ -2117,7 +2171,10 @@ struct Engine : EngineBase {
       int s2 = moments_impl(true, B, true, 2);
       fuse_lik_next = false;
       CKS(s2);
-      CKS(step_update_a(rho));
+      allow_split_gram = true;
+      int sa = step_update_a(rho);
+      allow_split_gram = false;
+      CKS(sa);
       // inside a capture these become event-record / event-wait NODES (external events); eagerly they are ordinary stream operations
       CK(cudaEventRecordWithFlags(ev_vfree, st(), capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
       CK(cudaStreamWaitEvent(st(), ev_res, capturing ? cudaEventWaitExternal : cudaEventWaitDefault));   // they still read X / t

@@ -659,7 +659,10 @@ __global__ void elbo_lik_kernel(const LikParams p_in, double* __restrict__ out) 
           double a = 1.0 / (p0 * p0), bb = c;   // c holds b
           e += -0.5 * log(6.283185307179586) + 0.5 * log(th) - 0.5 * (th * var + th * mu * mu - 2.0 * th * mu * y + th * y * y);
           double sq = sqrt(a) * bb;
-          double ent = 0.5 * (log(a) - 2.0 * log(bb)) + 0.6931471805599453 + 0.5 * log(3.141592653589793 / (2.0 * sq)) - sq + (sq + 0.5);
+          // as written in the reference (scalar a and p in sum / mapreduce, quirk Q13): log(a) / 2 and log(2 K_p(sqrt(ab))) enter once,
+          // for the first sample of the batch; -log(b^2) / 2 and the Bessel-ratio term are summed over every sample
+          double ent = -log(bb) + (sq + 0.5);
+          if (b == 0) ent += 0.5 * log(a) + 0.6931471805599453 + 0.5 * log(3.141592653589793 / (2.0 * sq)) - sq;
           double ex = -log(2.0 * p0 * p0) - (a * bb + bb * bb * sqrt(a)) / (a * bb * bb * p0 * p0) / 2.0;
           kl += ent - ex;
         } else if (kind == 5) {  // bayesiansvm.jl:68-89 (signs as written in the reference)
@@ -738,6 +741,8 @@ struct TailParams {
   // OnlineSVGP (analyticVI.jl:183-203): constant terms of the natural gradient carried over from the previous inducing set,
   // whitened: eta1_off = (kappa_a L)^T prev_eta1, eta2_off = (kappa_a L)^T invD_a (kappa_a L) / 2.  Null for every other model.
   const double* eta1_off; const double* eta2_off;
+  // split Gram (agp_engine.cu): 0 = every element, 1 = only the first 128 x 128 block (grid (1, 128)), 2 = everything else
+  int blk_mode;
 };
 
 // natural gradient + global update of the natural parameters (inference/analyticVI.jl:160-180, 229-246;
@@ -750,6 +755,7 @@ __global__ void combine_kernel(const TailParams p, const TG* __restrict__ Gpart)
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   int i = blockIdx.y;
   if (j >= p.mp) return;
+  if (p.blk_mode == 2 && i < 128 && j < 128) return;
   const double lr = *p.lr;
   if (i >= p.m || j >= p.m) {
     p.P[(int64_t)i * p.ld + j] = (i == j) ? 1.0 : 0.0;

@@ -1408,6 +1408,41 @@ int umma_gram(std::string* err, UmmaLatent& u, float* Gpart, int B, int m, int* 
   return 0;
 }
 
+// One part of the Gram product as its own launch: part 0 = the first diagonal tile (0, 0) over S split-K slices, part 1 = every
+// other upper tile over S slices; at most grid_max persistent CTAs.  The engine runs part 0 on the critical chain (the tail's first
+// kernel only needs that tile) and part 1 beside it (agp_engine.cu, split Gram).
+int umma_gram_part(std::string* err, UmmaLatent& u, float* Gpart, int B, int m, int part, int S, int grid_max, cudaStream_t st) {
+  Maps* mp = (Maps*)u.tmaps;
+  if (B % BM || m % BN) return fail(err, "shape not a multiple of the tile");
+  if (u.v2 || v3_on()) return fail(err, "split Gram launches use the first-generation kernel");
+  const int total_kb = B / BK;
+  const int nt = m / BN, upper_tiles = nt * (nt + 1) / 2;
+  if (S < 1 || S > total_kb || upper_tiles < 2) return fail(err, "bad split count");
+  const int per = (total_kb + S - 1) / S;
+  if ((total_kb + per - 1) / per != S) return fail(err, "split count does not divide the k range evenly enough");
+  GemmWork w{};
+  w.ntm = nt; w.ntn = nt; w.nsplit = S; w.total_kb = total_kb; w.kb_per_split = per; w.tri_mode = 2;
+  w.u0 = part == 0 ? 0 : S;
+  w.total = part == 0 ? S : (upper_tiles - 1) * S;
+  int grid = w.total < sm_count() ? w.total : sm_count();
+  if (grid_max > 0 && grid > grid_max) grid = grid_max;
+  UmmaEpilogue ep{};
+  ep.mode = UMMA_EPI_STORE_MIRROR;
+  launch_chain(umma_gemm_nt_kernel, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, st, mp->ut, mp->ut, Gpart, (int64_t)u.ldm, (int64_t)m * u.ldm, w, ep);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(err, "umma gram part", e);
+  return 0;
+}
+// largest S <= cap whose slices cover the k range without an empty one
+int umma_gram_splits(int B, int cap) {
+  const int total_kb = B / BK;
+  for (int S = cap < total_kb ? cap : total_kb; S >= 1; --S) {
+    const int per = (total_kb + S - 1) / S;
+    if ((total_kb + per - 1) / per == S) return S;
+  }
+  return 1;
+}
+
 // ---- grouped launches (several latent GPs per launch) ----
 int umma_groups_build(std::string* err, UmmaGroups& gs, UmmaLatent* const* lats, int n, int a_which, int b_which, float* const* C,
                       double* const* acc0, double* const* acc1, const double* const* tvec, cudaStream_t st) {

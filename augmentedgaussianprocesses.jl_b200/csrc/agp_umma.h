@@ -62,6 +62,9 @@ void umma_set_grid_cap(int n);
 // V X^T statistics are issued N tile by N tile as the rows of X leave the m x m tail
 void umma_set_tile_range(int lo, int hi);
 int umma_gram(std::string* err, UmmaLatent& u, float* Gpart, int B, int m, int* n_split, cudaStream_t st);
+// the Gram product in two launches: part 0 = tile (0, 0) over S slices, part 1 = the other upper tiles over S slices (<= grid_max CTAs)
+int umma_gram_part(std::string* err, UmmaLatent& u, float* Gpart, int B, int m, int part, int S, int grid_max, cudaStream_t st);
+int umma_gram_splits(int B, int cap);   // largest usable split count <= cap
 
 // ---- grouped launches: the same-shaped product of several latent GPs in ONE persistent launch (multi-latent models: the per-launch
 // fixed cost of a C2 / C4 sized product, ~8 us, is paid once; the persistent CTAs stay balanced over n x tiles work units) ----

@@ -18,7 +18,8 @@ Reference quirks reproduced on purpose: Q1 logistic ELBO uses
 dot(theta, mu); Q2 GammaEntropy uses log(beta[0]) only; Q3 K_mm factorised once per
 train call -- also after update_hyperparameters! (stale K_mm next to a fresh K_nm; the
 fix is the opt-in `model.refresh_K_after_hyper`); Q6 LogisticSoftMax local variables persist across minibatches; Q9
-Robbins-Monro counter starts at 1; Q10 length(y) of a one-hot y is B*K.
+Robbins-Monro counter starts at 1; Q10 length(y) of a one-hot y is B*K; Q13 the Laplace GIGEntropy adds log(a) once and the
+Bessel term of the first sample only (scalar arguments of sum / mapreduce, KLdivergences.jl:105-114).
 """
 from __future__ import annotations
 
@@ -455,12 +456,20 @@ def grad_E_Sigma(lik, y, lv):
 
 
 def GIGEntropy(a, b, p):
-    """functions/KLdivergences.jl:105-114 (the d/dp K_p term is omitted there too)"""
-    a = np.broadcast_to(np.asarray(a, dtype=np.float64), np.shape(b))
-    s = np.sqrt(a * b)
+    """functions/KLdivergences.jl:105-114 (the d/dp K_p term is omitted there too), AS WRITTEN for the only call site
+    (likelihood/laplace.jl:115: scalar a, vector b, scalar p) -- quirk Q13: `sum(log, a)` over a scalar adds log(a) ONCE, and
+    `mapreduce((p, s) -> log(2 besselk(p, s)), +, p, sqrt_ab)` zips the scalar p with the vector, i.e. stops after the FIRST
+    sample; only the third term is broadcast over all samples.  Vector a / p (not used by the reference) broadcast normally."""
+    b = np.asarray(b, dtype=np.float64)
+    s = np.sqrt(np.asarray(a, dtype=np.float64) * b)
+    log_a = np.sum(np.log(np.atleast_1d(np.asarray(a, dtype=np.float64))))          # one term for a scalar a
+    if np.ndim(p) == 0:
+        bessel = math.log(2.0 * ssp.kv(p, np.atleast_1d(s)[0]))                      # zip(p, sqrt_ab) has one element
+    else:
+        bessel = float(np.sum(np.log(2.0 * ssp.kv(p, s))))
     return float(
-        (np.sum(np.log(a)) - np.sum(np.log(b))) / 2.0
-        + np.sum(np.log(2.0 * ssp.kv(p, s)))
+        (log_a - np.sum(np.log(b))) / 2.0
+        + bessel
         + np.sum(s / ssp.kv(p, s) * (ssp.kv(p + 1.0, s) + ssp.kv(p - 1.0, s))) / 2.0
     )
 

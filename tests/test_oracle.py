@@ -126,8 +126,12 @@ def test_f2_likelihood_closed_forms():
     a, b = 2.5, rng.uniform(0.3, 3.0, 7)
     s = np.sqrt(a * b)
     # K_{1/2}(s) = sqrt(pi/2s) e^-s, K_{3/2} = K_{1/2}(1 + 1/s), K_{-1/2} = K_{1/2}
-    closed = 0.5 * np.sum(np.log(a) - np.log(b)) + np.sum(np.log(2.0) + 0.5 * np.log(np.pi / (2 * s)) - s) + np.sum(s + 0.5)
+    # as written for scalar a, p (KLdivergences.jl:105-114, quirk Q13): log(a) once, the log-Bessel term of the FIRST sample only
+    closed = 0.5 * (np.log(a) - np.sum(np.log(b))) + (np.log(2.0) + 0.5 * np.log(np.pi / (2 * s[0])) - s[0]) + np.sum(s + 0.5)
     assert O.GIGEntropy(a, b, 0.5) == pytest.approx(closed, rel=1e-12)
+    # vector arguments broadcast (the textbook entropy without the d/dp term)
+    full = 0.5 * np.sum(np.log(a) - np.log(b)) + np.sum(np.log(2.0) + 0.5 * np.log(np.pi / (2 * s)) - s) + np.sum(s + 0.5)
+    assert O.GIGEntropy(np.full(7, a), b, np.full(7, 0.5)) == pytest.approx(full, rel=1e-12)
     mu, var = rng.standard_normal(5), rng.uniform(0.1, 2.0, 5)
     assert np.allclose(O.expectation(lambda x: x, mu, var), mu, atol=1e-12)
     assert np.allclose(O.expectation(lambda x: x**2, mu, var), mu**2 + var, atol=1e-10)
