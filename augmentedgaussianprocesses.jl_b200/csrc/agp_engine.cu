@@ -404,6 +404,7 @@ struct Engine : EngineBase {
       }
     }
     CKS(groups_init());
+    CKS(fan_init());
     CKS(dalloc(&Xb, (size_t)Bcap * Dp)); CKS(dalloc(&xxb, Bcap));
     CKS(dalloc(&idx_cur, Bcap)); CKS(dalloc(&xx_cur, Bcap)); CKS(dalloc(&idx_prev, Bcap));
     CK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
@@ -501,6 +502,8 @@ struct Engine : EngineBase {
       umma_knm_free(L.uk);
     }
     umma_groups_free(grpV); umma_groups_free(grpS); umma_groups_free(grpG);
+    for (int i = 0; i < NAUX; ++i) { if (aux[i]) cudaStreamDestroy(aux[i]); if (ev_aux_join[i]) cudaEventDestroy(ev_aux_join[i]); }
+    if (ev_aux_fork) cudaEventDestroy(ev_aux_fork);
     for (void* q : peer_opened) cudaIpcCloseMemHandle(q);
     if (side) cudaStreamDestroy(side);
     drop_graph_p();
@@ -802,6 +805,42 @@ struct Engine : EngineBase {
   // Also the whole of _predict_f (training/predictions.jl:25-50): mu* = k* (K \ mu) = V* mu_v and
   // sigma2* = kdiag + jitter - diag(k* A k*^T) = Ktilde* + rowsum((V* Sigma_v) .* V*).
   // stages: 1 = kernel matrices (Knm, V [+ sum V^2]), 2 = V X^T + row statistics, 3 = both
+  // ---- fan-out of the per-latent small kernels (K_nm, row statistics, scale-transpose, combine, finalize) of multi-latent steps over
+  // NAUX auxiliary streams: they are independent across latents and each is too short (4-10 us, partly launch latency) to fill the
+  // GPU alone.  Inside a graph capture the streams become parallel branches.  AGP_FAN=0 disables. ----
+  static constexpr int NAUX = 4;
+  cudaStream_t aux[NAUX] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_aux_fork = nullptr, ev_aux_join[NAUX] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t fan_base = nullptr; bool fan_active = false, fan_on = true;
+  int fan_init() {
+    if (const char* e = getenv("AGP_FAN")) if (e[0] == '0') fan_on = false;
+    if (Ql < 2) fan_on = false;
+    if (!fan_on) return AGP_OK;
+    CK(cudaEventCreateWithFlags(&ev_aux_fork, cudaEventDisableTiming));
+    for (int i = 0; i < NAUX; ++i) {
+      CK(cudaStreamCreateWithFlags(&aux[i], cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&ev_aux_join[i], cudaEventDisableTiming));
+    }
+    return AGP_OK;
+  }
+  void fan_begin() {
+    if (!fan_on || prof || fan_active) return;
+    fan_base = st();
+    cudaEventRecord(ev_aux_fork, fan_base);
+    for (int i = 0; i < NAUX; ++i) cudaStreamWaitEvent(aux[i], ev_aux_fork, 0);
+    fan_active = true;
+  }
+  void fan_select(int q) { if (fan_active) cur_stream = aux[q % NAUX]; }
+  void fan_end() {
+    if (!fan_active) return;
+    for (int i = 0; i < NAUX; ++i) {
+      cudaEventRecord(ev_aux_join[i], aux[i]);
+      cudaStreamWaitEvent(fan_base, ev_aux_join[i], 0);
+    }
+    cur_stream = (fan_base == ctx->stream) ? nullptr : fan_base;
+    fan_active = false;
+  }
+
   // ---- grouped tcgen05 launches: with >= 2 owned latents (tf32x3) each of the three B x m x m products of a step is ONE persistent
   // launch over all owned latents (umma_gemm_grouped_kernel) instead of one launch per latent ----
   UmmaGroups grpV, grpS, grpG;
@@ -824,8 +863,10 @@ struct Engine : EngineBase {
                            double* var_out, int64_t out_ld, int stages) {
     if (stages & 1) {
       ph_begin(PH_KMAT);
+      fan_begin();
       for (int q = 0; q < Ql; ++q) {
         Latent& L = lat[q];
+        fan_select(q);
         if (L.knm_tc) {
           CKS(umma_knm(ctx_err(), L.uk, (const float*)(const void*)Xsrc, Dp, Dp, gather, (const float*)(const void*)(gather ? xx_cur : xsrc),
                        (const float*)(const void*)L.zz, B, L.kind, L.scale * L.scale, L.variance, st()));
@@ -839,6 +880,7 @@ struct Engine : EngineBase {
         ++launches;
         CK(cudaMemsetAsync(L.racc, 0, ldB * sizeof(double), st()));
       }
+      fan_end();
       ph_end();
       ph_begin(PH_KAPPA);
       CKS(umma_gemm_nt_grouped(ctx_err(), grpV, lat[0].um, 1, B, m, UMMA_EPI_STORE_SUMSQ, st()));
@@ -853,14 +895,17 @@ struct Engine : EngineBase {
     ++launches;
     ph_end();
     ph_begin(PH_ROWSTATS);
+    fan_begin();
     for (int q = 0; q < Ql; ++q) {
       Latent& L = lat[q];
+      fan_select(q);
       launch_chain(rowfinish_kernel, dim3((B + 255) / 256), dim3(256), 0, (const double*)L.racc, (const double*)(L.racc + ldB),
                    (const double*)(L.racc + 2 * ldB), B, L.variance + jitter, L.Ktilde, mean_out + (size_t)q * out_ld,
                    var_out + (size_t)q * out_ld, status, fresh_kernel_matrices ? 1 : 0,
                    (const int64_t*)((peer && mean_out == mean_f + (size_t)qbeg * ldB) ? d_xepoch : nullptr), par_stride);
       ++launches;
     }
+    fan_end();
     ph_end();
     CK(cudaGetLastError());
     return AGP_OK;
@@ -1502,8 +1547,10 @@ struct Engine : EngineBase {
   int natgrad_products(double rho) {
     const int B = curB;
     const bool grp = use_groups && prec == AGP_PREC_TF32X3;
+    if (grp) fan_begin();
     for (int q = 0; q < Ql; ++q) {
       Latent& L = lat[q];
+      if (grp) fan_select(q);
       ph_begin(PH_GRADMU);
       // tf32x3: V^T grad_mu is accumulated by the scale-transpose kernel into v1, which combine_kernel clears after use
       if (prec != AGP_PREC_TF32X3) CK(cudaMemsetAsync(L.v1, 0, m * sizeof(double), st()));
@@ -1514,7 +1561,7 @@ struct Engine : EngineBase {
       ph_end();
       if (prec == AGP_PREC_TF32X3) {
         ph_begin(PH_SPLIT);
-        umma_set_pdl(tail_pdl && !prof);
+        umma_set_pdl(tail_pdl && !prof && !fan_active);
         CKS(umma_scale_transpose(ctx_err(), L.um, (const float*)(const void*)L.V, gS + (size_t)q * ldB, rho, gmu + (size_t)q * ldB, L.v1, B, m, st()));
         ++launches;
         ph_end();
@@ -1566,6 +1613,7 @@ struct Engine : EngineBase {
       ph_end();
     }
     if (grp) {
+      fan_end();
       ph_begin(PH_GRAM);
       int ns = n_split;
       umma_set_pdl(tail_pdl && !prof);
@@ -1598,9 +1646,12 @@ struct Engine : EngineBase {
   }
   // natural-parameter update + the m x m tail of every owned latent
   int step_update_b(double rho) {
+    const bool fan3 = !ns_tail_now && tail_variant == 3 && Ql >= 2;
+    if (fan3) fan_begin();
     for (int q = 0; q < Ql; ++q) {
       Latent& L = lat[q];
       const int ns = L.gram_splits;
+      if (fan3) fan_select(q);
       ph_begin(PH_COMBINE);
       launch_combine(L, rho, ns, split_gram_now ? 1 : 0);
       ph_end();
@@ -1610,12 +1661,17 @@ struct Engine : EngineBase {
         L.factor_valid = true; L.ns_seeded = false;
       }
     }
+    if (fan3) fan_end();
     if (!ns_tail_now && tail_variant == 3) {   // every owned latent's Cholesky + inverse factor in one persistent launch
       chol_inv_many(0, Ql);
+      if (fan3) fan_begin();
       for (int q = 0; q < Ql; ++q) {
-        CKS(finalize_factor(lat[q], q == Ql - 1));
+        if (fan3) fan_select(q);
+        int sf = finalize_factor(lat[q], q == Ql - 1);
+        if (sf != AGP_OK) { fan_end(); return sf; }
         lat[q].factor_valid = true; lat[q].ns_seeded = false;
       }
+      if (fan3) fan_end();
     }
     // (the counters are bumped by the last latent's finalize kernel)
     CK(cudaGetLastError());
@@ -1633,7 +1689,7 @@ struct Engine : EngineBase {
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st();
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = (tail_pdl && !prof && !chain_break) ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = (tail_pdl && !prof && !chain_break && !fan_active) ? 1 : 0;
     chain_break = false;
     cudaLaunchKernelEx(&cfg, kern, args...);
   }
