@@ -1059,7 +1059,7 @@ struct Engine : EngineBase {
     // moments under the updated posterior (like ELBO(model, state, y)); sharded models exchange them here (collective call)
     CKS(elbo_moments());
     LikParams lp = lik_params(B, true, 0);
-    if (model_kind == AGP_MODEL_MOSVGP) { lik_update_kernel<<<(B + 127) / 128, 128, 0, st()>>>(lp); ++launches; }
+    if (model_kind == AGP_MODEL_MOSVGP) launch_lik(lp, false);
     if (!hgA) {
       for (int i = 0; i < 4; ++i) CKS(dalloc(&hgH[i], (size_t)Bcap * ldh));
       CKS(dalloc(&hgX, (size_t)Bcap * Dp)); CKS(dalloc(&hgA, (size_t)Ql * ldB)); CKS(dalloc(&hgB, (size_t)Ql * ldB));
@@ -1468,6 +1468,25 @@ struct Engine : EngineBase {
     return step_update(1.0);
   }
 
+  // local_updates! launch: multi-output models take the two-dimensional pair of kernels (AGP_LIK_1D=1: the one-thread-per-sample kernel)
+  void launch_lik(const LikParams& lp, bool chain) {
+    const int B = lp.B;
+    static const bool one_d = getenv("AGP_LIK_1D") != nullptr;
+    if (lp.model_kind == AGP_MODEL_MOSVGP && !one_d) {
+      if (chain) launch_chain(lik_mo_task_kernel, dim3((B + 127) / 128, (lp.n_task + LIK_MO_TPT - 1) / LIK_MO_TPT), dim3(128), 0, lp);
+      else lik_mo_task_kernel<<<dim3((B + 127) / 128, (lp.n_task + LIK_MO_TPT - 1) / LIK_MO_TPT), 128, 0, st()>>>(lp);
+      ++launches;
+      if (lp.update) {
+        if (chain) launch_chain(lik_mo_grad_kernel, dim3((B + 127) / 128, (lp.n_latent_local + LIK_MO_TPT - 1) / LIK_MO_TPT), dim3(128), 0, lp);
+        else lik_mo_grad_kernel<<<dim3((B + 127) / 128, (lp.n_latent_local + LIK_MO_TPT - 1) / LIK_MO_TPT), 128, 0, st()>>>(lp);
+        ++launches;
+      }
+      return;
+    }
+    if (chain) launch_chain(lik_update_kernel, dim3((B + 127) / 128), dim3(128), 0, lp);
+    else lik_update_kernel<<<(B + 127) / 128, 128, 0, st()>>>(lp);
+    ++launches;
+  }
   bool can_fuse_lik() const {
     return !noise_any && !is_vgp && prec == AGP_PREC_TF32X3 && model_kind == AGP_MODEL_SVGP && Qg == 1 && Ql == 1 && !need_lam && !peer && !a_opt && !prof &&
            !getenv("AGP_NO_FUSE_LIK");
@@ -1522,13 +1541,13 @@ struct Engine : EngineBase {
     ph_begin(PH_LIK);
     if (a_opt) {   // update_A! precedes variational_updates (training/training.jl:153-158)
       LikParams lp0 = lik_params(B, cur_from_batch, 0);
-      lik_update_kernel<<<(B + 127) / 128, 128, 0, st()>>>(lp0);                        // labels of this batch + task means with the current A
+      launch_lik(lp0, false);                                                           // labels of this batch + task means with the current A
       update_A_grad_kernel<<<nT * Qg, 256, 0, st()>>>(lik_params(B, true, 0), d_gradA);
       update_A_adam_kernel<<<nT, 32 * ((Qg + 31) / 32), 0, st()>>>(d_A, d_gradA, d_Amt, d_Avt, d_Abt, Qg, a_eta, a_b1, a_b2, a_eps);
-      launches += 3;
+      launches += 2;
     }
     if (need_quad && nq < 1) { ph_end(); ctx->err = "agp_set_quadrature must be called before a Poisson step"; return AGP_ERR_STATE; }
-    if (!lik_fused) { launch_chain(lik_update_kernel, dim3((B + 127) / 128), dim3(128), 0, lik_params(B, cur_from_batch, 1)); ++launches; }
+    if (!lik_fused) launch_lik(lik_params(B, cur_from_batch, 1), true);
     lik_fused = false;
     if (need_lam || noise_any) {  // lambda / noise re-estimation closes local_updates! (poisson.jl:80, heteroscedastic.jl:98, gaussian.jl:62-70)
       LikParams lp = lik_params(B, true, 1);
@@ -1537,8 +1556,7 @@ struct Engine : EngineBase {
       if (is_het) { launch_chain(hetero_grad_kernel, dim3((B + 127) / 128), dim3(128), 0, lp); ++launches; }
       if (noise_any) {   // theta = 1 / sigma^2 and the Gaussian gradients with the NEW noise (gaussian.jl:70-80)
         LikParams lp2 = lik_params(B, true, 2);
-        launch_chain(lik_update_kernel, dim3((B + 127) / 128), dim3(128), 0, lp2);
-        ++launches;
+        launch_lik(lp2, true);
       }
     }
     ph_end();
@@ -2360,7 +2378,7 @@ struct Engine : EngineBase {
     const int B = curB;
     CK(cudaMemsetAsync(d_out, 0, 8 * sizeof(double), st()));
     LikParams lp = lik_params(B, true /* labels already gathered into yb */, 0);
-    if (model_kind == AGP_MODEL_MOSVGP) { lik_update_kernel<<<(B + 127) / 128, 128, 0, st()>>>(lp); ++launches; }
+    if (model_kind == AGP_MODEL_MOSVGP) launch_lik(lp, false);
     elbo_lik_kernel<<<(B + 255) / 256, 256, 0, st()>>>(lp, d_out);
     ++launches;
     std::vector<double> ld(Ql), h(8);

@@ -423,6 +423,84 @@ __global__ void lik_update_kernel(const LikParams p_in) {
   }
 }
 
+// MOSVGP local updates in two dimensions (the loops of lik_update_sample's multi-output branch, same summation order, so the
+// results are bit-identical): one thread per (sample, task) for the task moments + local variables + per-task gradients, then one
+// thread per (sample, owned latent) for the latent gradients.  One thread per sample looping over T x Q (64 x 64 at BASELINE C5) left
+// 64 CTAs latency-bound for ~580 us per step, replicated on every rank of a sharded run.
+constexpr int LIK_MO_TPT = 8;   // tasks (latents) per thread: every latent moment (per-task term) is loaded once for 8 accumulators
+__global__ void lik_mo_task_kernel(const LikParams p_in) {
+  pdl_prologue();
+  const LikParams p = lik_resolve(p_in);
+  const int b = blockIdx.x * blockDim.x + threadIdx.x, t0 = blockIdx.y * LIK_MO_TPT;
+  if (b >= p.B) return;
+  const int64_t ld = p.ldB;
+  const int Q = p.Q, T = p.n_task;
+  const int64_t src = p.idx ? p.idx[b] : (int64_t)b;
+  double mt[LIK_MO_TPT], vt[LIK_MO_TPT];
+#pragma unroll
+  for (int u = 0; u < LIK_MO_TPT; ++u) { mt[u] = 0.0; vt[u] = 0.0; }
+  for (int q = 0; q < Q; ++q) {
+    const double mq = p.mean_f[q * ld + b], vq = p.var_f[q * ld + b];
+#pragma unroll
+    for (int u = 0; u < LIK_MO_TPT; ++u) {
+      const double a = (t0 + u < T) ? p.A[(t0 + u) * Q + q] : 0.0;
+      mt[u] += a * mq;
+      vt[u] += a * a * vq;
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < LIK_MO_TPT; ++u) {
+    const int t = t0 + u;
+    if (t >= T) break;
+    double y = p.idx ? p.y_all[(int64_t)t * p.n + src] : p.yb[t * ld + b];
+    if (p.idx) p.yb[t * ld + b] = y;
+    p.tmu[t * ld + b] = mt[u]; p.tvar[t * ld + b] = vt[u];
+    const int kind = p.lik_kind[t];
+    if (p.update == 1 || (p.update == 2 && kind == 0)) {
+      double c, th, gam, gm, gs;
+      lik_single(kind, p.p0[t], p.p1[t], p.lam[t], y, mt[u], vt[u], c, th, gam, gm, gs);
+      p.c[t * ld + b] = c; p.theta[t * ld + b] = th;
+      p.gm[t * ld + b] = gm; p.gs[t * ld + b] = gs;
+      if (kind == 0 && p.noise_opt && p.noise_opt[t] && p.update == 1) atomicAdd(p.lamacc + 2 * t, (y - mt[u]) * (y - mt[u]) + vt[u]);
+      if (kind == 7 && p.update == 1) {
+        p.gamma[t * ld + b] = gam;
+        atomicAdd(p.lamacc + 2 * t, y);
+        atomicAdd(p.lamacc + 2 * t + 1, expect_logistic(p.qnodes, p.qweights, p.nq, mt[u], vt[u]));
+      }
+    }
+  }
+}
+__global__ void lik_mo_grad_kernel(const LikParams p_in) {
+  pdl_prologue();
+  const LikParams p = lik_resolve(p_in);
+  const int b = blockIdx.x * blockDim.x + threadIdx.x, l0 = blockIdx.y * LIK_MO_TPT;
+  if (b >= p.B) return;
+  const int64_t ld = p.ldB;
+  const int T = p.n_task, Q = p.Q, nl = p.n_latent_local;
+  double muq[LIK_MO_TPT], a1[LIK_MO_TPT], a2[LIK_MO_TPT];
+#pragma unroll
+  for (int u = 0; u < LIK_MO_TPT; ++u) {
+    muq[u] = (l0 + u < nl) ? p.mean_f[(p.latent_begin + l0 + u) * ld + b] : 0.0;
+    a1[u] = 0.0; a2[u] = 0.0;
+  }
+  for (int t = 0; t < T; ++t) {
+    const double tm = p.tmu[t * ld + b], gmt = p.gm[t * ld + b], gst = p.gs[t * ld + b];
+#pragma unroll
+    for (int u = 0; u < LIK_MO_TPT; ++u) {
+      const double a = (l0 + u < nl) ? p.A[t * Q + p.latent_begin + l0 + u] : 0.0;
+      const double others = tm - a * muq[u];
+      a1[u] += a * (gmt - 2.0 * gst * others);
+      a2[u] += a * a * gst;
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < LIK_MO_TPT; ++u) {
+    if (l0 + u >= nl) break;
+    p.gmu[(l0 + u) * ld + b] = a1[u];
+    p.gS[(l0 + u) * ld + b] = a2[u];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // update_A! (models/single_and_multi_output_utils.jl:87-118) for MOSVGP with an A optimiser: runs between the latent
 // moments and local_updates!, i.e. with the local variables of the PREVIOUS iteration and the labels of the current batch.
