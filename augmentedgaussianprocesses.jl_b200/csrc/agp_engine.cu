@@ -726,7 +726,7 @@ struct Engine : EngineBase {
       copy_lower_kernel<<<grid_mp(), 128, 0, st()>>>(L.X, L.Linv, mp, mp);
       symmetrize_shadow_kernel<T><<<dim3((m + 127) / 128, m), 128, 0, st()>>>(L.Kinv, mp, m, (T*)nullptr, ldm);
       shadow_kernel<T><<<dim3((m + 127) / 128, m), 128, 0, st()>>>(L.Linv, mp, m, L.Linv_T, ldm);
-      if (L.um.v2) { CKS(umma_presplit(ctx_err(), L.um, UM_LINV, (const float*)(const void*)L.Linv_T, st())); ++launches; }
+      if (L.um.v2 || L.um.ps) { CKS(umma_presplit(ctx_err(), L.um, UM_LINV, (const float*)(const void*)L.Linv_T, st())); ++launches; }
       symv_kernel<<<(m * 32 + 255) / 256, 256, 0, st()>>>(L.Linv, mp, m, L.mu0, L.mu0v);  // L^-1 mu0
       launches += 5;
       CK(cudaMemcpyAsync(&L.logdetK, L.logdetP + 1, sizeof(double), cudaMemcpyDeviceToHost, st()));
@@ -1188,7 +1188,7 @@ struct Engine : EngineBase {
       CK(cudaMemcpyAsync(L.Kinv, L.bkKinv, mm * 8, cudaMemcpyDeviceToDevice, st()));
       CK(cudaMemcpyAsync(L.mu0v, L.bkmu0v, (size_t)mp * 8, cudaMemcpyDeviceToDevice, st()));
       CK(cudaMemcpyAsync(L.Linv_T, L.bkLinvT, (size_t)m * ldm * sizeof(T), cudaMemcpyDeviceToDevice, st()));
-      if (L.um.v2) { CKS(umma_presplit(ctx_err(), L.um, UM_LINV, (const float*)(const void*)L.Linv_T, st())); ++launches; }
+      if (L.um.v2 || L.um.ps) { CKS(umma_presplit(ctx_err(), L.um, UM_LINV, (const float*)(const void*)L.Linv_T, st())); ++launches; }
       L.logdetK = L.bklogdetK;
       CKS(whiten(L));
     }

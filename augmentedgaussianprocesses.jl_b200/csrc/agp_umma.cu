@@ -272,7 +272,7 @@ umma_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int row = wu.tile_m * BM + q * 32 + lane;
       float* cbase = C + (int64_t)wu.split * c_split_stride;
       float* crow = cbase + (int64_t)row * ldc + (int64_t)wu.tile_n * BN;
-      double acc_sq = 0.0, acc_dot = 0.0;   // fused row statistics (fp64 sums, like rowstats_kernel)
+      double acc_sq4[4] = {0.0, 0.0, 0.0, 0.0}, acc_dot4[4] = {0.0, 0.0, 0.0, 0.0};   // fused row statistics: fp64 sums, four interleaved chains each
       if (wu.nkb > 0) {
         mbar_wait(tmem_full(ab), (lt >> 1) & 1);
         tc_fence_after();
@@ -298,8 +298,8 @@ umma_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const double v = (double)__uint_as_float(rr[j]);
-              acc_sq = fma(v, v, acc_sq);
-              if (ep.mode == UMMA_EPI_STATS_ONLY) acc_dot = fma(v, ep.tvec[wu.tile_n * BN + c * 32 + j], acc_dot);
+              acc_sq4[j & 3] = fma(v, v, acc_sq4[j & 3]);
+              if (ep.mode == UMMA_EPI_STATS_ONLY) acc_dot4[j & 3] = fma(v, ep.tvec[wu.tile_n * BN + c * 32 + j], acc_dot4[j & 3]);
             }
           }
           if (ep.mode == UMMA_EPI_STORE_MIRROR && wu.tile_n != wu.tile_m) {
@@ -309,6 +309,7 @@ umma_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               cbase[(int64_t)(wu.tile_n * BN + c * 32 + j) * ldc + row] = __uint_as_float(rr[j]);
           }
         }
+        const double acc_sq = (acc_sq4[0] + acc_sq4[1]) + (acc_sq4[2] + acc_sq4[3]), acc_dot = (acc_dot4[0] + acc_dot4[1]) + (acc_dot4[2] + acc_dot4[3]);
         if (ep.mode == UMMA_EPI_STORE_SUMSQ) atomicAdd(ep.acc0 + row, acc_sq);
         if (ep.mode == UMMA_EPI_STATS_ONLY) { atomicAdd(ep.acc0 + row, acc_sq); atomicAdd(ep.acc1 + row, acc_dot); }
         if (ct == 0) UTT(2 + grp, 400000 + lt);
@@ -324,10 +325,226 @@ umma_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 
+// Pre-split right operand (default for the two products whose B operand is an m x m matrix that changes at most once per step:
+// V = K_nm L^-T and V X^T; AGP_UMMA_PS=0 selects the kernel above).  L^-1 is split into TF32 hi / lo planes once per agp_refresh_K, X by
+// x_finalize_kernel; the planes arrive by TMA next to the raw A tile (48 KB per stage, 4 stages), so the worker groups only split A
+// (32 instead of 64 values per thread and k-block, no shared-memory stores) and the MMA warp's commit releases the ring stage.
+// Everything else (unit order, group alternation by unit, epilogues) is the kernel above.
+namespace ps {
+constexpr int RSP = 4;
+constexpr int STAGE_BYTES = 3 * TILE_BYTES;                      // A raw | B hi | B lo
+constexpr int RING_BYTES = RSP * STAGE_BYTES;                    // 192 KB
+constexpr int SMEM_BYTES = RING_BYTES + 1024 + 256;
+}
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+umma_gemm_ps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo, float* __restrict__ C,
+                    int64_t ldc, int64_t c_split_stride, const GemmWork work, const UmmaEpilogue ep) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  using namespace ps;
+  const uint32_t bars = smem_base + ps::RING_BYTES;
+  auto raw_full = [&](int s) { return bars + 8u * s; };                 // TMA landed stage s (A raw, B hi, B lo)
+  auto raw_empty = [&](int s) { return bars + 8u * (RSP + s); };        // the MMAs that read stage s have retired (tcgen05.commit)
+  auto conv_full = [&](int s) { return bars + 8u * (2 * RSP + s); };
+  auto mma_done = [&](int s) { return bars + 8u * (2 * RSP + CS + s); };
+  auto tmem_full = [&](int b) { return bars + 8u * (2 * RSP + 2 * CS + b); };
+  auto tmem_empty = [&](int b) { return bars + 8u * (2 * RSP + 2 * CS + 2 + b); };
+  auto unit_conv_done = [&](int b) { return bars + 8u * (2 * RSP + 2 * CS + 4 + b); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + ps::RING_BYTES + 8 * (2 * RSP + 2 * CS + 6));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = gridDim.x, cta = blockIdx.x;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmBhi); tma_prefetch_desc(&tmBlo);
+    for (int s = 0; s < RSP; ++s) { mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), 1); }
+    for (int s = 0; s < CS; ++s) { mbar_init(conv_full(s), NUM_CONV_THREADS); mbar_init(mma_done(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tmem_full(b), 1); mbar_init(tmem_empty(b), 4); mbar_init(unit_conv_done(b), NUM_CONV_THREADS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_ptr_smem)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  // programmatic dependent launch: barrier init / TMEM allocation above overlap the previous kernel of the chain
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (threadIdx.x == 0) UTT(0, 1);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer: raw fp32 tiles, one ring across all units of this CTA =====
+      int g = 0;
+      for (int r = 0;; ++r) {
+        const int u = unit_index(r, cta, G);
+        if (u >= work.total) break;
+        const WorkUnit wu = get_unit(work, u);
+        for (int i = 0; i < wu.nkb; ++i, ++g) {
+          const int s = g % RSP;
+          mbar_wait(raw_empty(s), ((g / RSP) & 1) ^ 1);
+          UTT(0, 1000 + g);
+          const uint32_t dst = smem_base + s * STAGE_BYTES;
+          mbar_expect_tx(raw_full(s), 3 * TILE_BYTES);
+          const int k = (wu.kb0 + i) * BK;
+          tma_load_2d(dst + 0 * TILE_BYTES, &tmA, raw_full(s), k, wu.tile_m * BM);
+          tma_load_2d(dst + 1 * TILE_BYTES, &tmBhi, raw_full(s), k, wu.tile_n * BN);
+          tma_load_2d(dst + 2 * TILE_BYTES, &tmBlo, raw_full(s), k, wu.tile_n * BN);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: accumulator buffer lt & 1, so the epilogue of unit lt overlaps the main loop of unit lt + 1 =====
+    int g = 0, lt = 0;
+    for (int r = 0;; ++r, ++lt) {
+      const int u = unit_index(r, cta, G);
+      if (u >= work.total) break;
+      const WorkUnit wu = get_unit(work, u);
+      const int ab = lt & 1;
+      mbar_wait(tmem_empty(ab), ((lt >> 1) & 1) ^ 1);      // the epilogue two units ago has drained this accumulator
+      tc_fence_after();
+      if (lane == 0) UTT(1, 100000 + lt);
+      const uint32_t acc = tmem_base + ab * BN;
+      for (int i = 0; i < wu.nkb; ++i, ++g) {
+        const int s = g % CS;
+        mbar_wait(conv_full(s), (g / CS) & 1);
+        tc_fence_after();
+        if (lane == 0) UTT(1, 2000 + g);
+        if (elect_one()) {
+          const uint32_t b_hi = smem_base + (g % RSP) * STAGE_BYTES + TILE_BYTES, b_lo = b_hi + TILE_BYTES;   // pre-split B, straight from TMA
+          const uint32_t a_hi = tmem_base + TMEM_A0 + s * 64, a_lo = a_hi + 32;
+#pragma unroll
+          for (int kk = 0; kk < BK / 8; ++kk) {
+            const uint32_t off = kk * 32;  // 8 tf32 = 32 bytes along K inside the 128B swizzle atom (B); 8 TMEM columns (A)
+            const uint64_t dbh = make_desc(b_hi + off), dbl = make_desc(b_lo + off);
+            tc_mma_tf32_ts(acc, a_lo + kk * 8, dbh, kIdesc, (i > 0 || kk > 0) ? 1u : 0u);  // small terms first
+            tc_mma_tf32_ts(acc, a_hi + kk * 8, dbl, kIdesc, 1u);
+            tc_mma_tf32_ts(acc, a_hi + kk * 8, dbh, kIdesc, 1u);
+          }
+          tc_commit(mma_done(s));                          // frees the TMEM A columns of this slot
+          tc_commit(raw_empty(g % RSP));                   // ... and the ring stage (A raw was consumed earlier, B hi / lo just now)
+          if (i == wu.nkb - 1) tc_commit(tmem_full(ab));   // accumulator complete
+        }
+        __syncwarp();
+        if (lane == 0) UTT(1, 3000 + g);
+      }
+    }
+  } else {
+    // ===== worker groups: raw -> hi / lo conversion of the group's units, then their epilogue =====
+    const int grp = (warp - 2) >> 2;
+    const int ct = (threadIdx.x - 64) & 127;         // 0..127 within the group
+    const int q = warp & 3;                          // TMEM lane quarter this warp may access
+    const int arow = q * 32 + lane;                  // A-tile row = TMEM lane handled by this thread
+    int g = 0, lt = 0;
+    for (int r = 0;; ++r, ++lt) {
+      const int u = unit_index(r, cta, G);
+      if (u >= work.total) break;
+      const WorkUnit wu = get_unit(work, u);
+      if ((lt & 1) != grp) { g += wu.nkb; continue; }
+      // A group only sees the mbarrier phases of its own units.  Parity waits are unambiguous only within one phase, so
+      // do not start before the other group has issued every conversion of the previous unit (the TMA ring and the MMA
+      // warp are then at most one phase behind on every barrier this group is about to wait on).
+      if (lt > 0) mbar_wait(unit_conv_done(grp ^ 1), ((lt - 1) >> 1) & 1);
+      if (ct == 0) UTT(2 + grp, 200000 + lt);
+      for (int i = 0; i < wu.nkb; ++i, ++g) {
+        const int rs = g % RSP, s = g % CS;
+        mbar_wait(raw_full(rs), (g / RSP) & 1);              // TMA landed the stage
+        if (ct == 0) UTT(2 + grp, 4000 + g);
+        mbar_wait(mma_done(s), ((g / CS) & 1) ^ 1);          // previous MMAs on this slot's converted operands retired
+        tc_fence_after();
+        if (ct == 0) UTT(2 + grp, 5000 + g);
+        uint8_t* base = smem_gen + rs * STAGE_BYTES;
+        {
+          // A: row `arow` of the raw tile (128 B, 16-byte chunks XOR-swizzled with row & 7) -> hi / lo -> TMEM
+          const float4* rowp = reinterpret_cast<const float4*>(base + arow * 128);
+          uint32_t h[32], l[32];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 v = rowp[c ^ (arow & 7)];
+            float t;
+            t = tf32_rna(v.x); h[4 * c + 0] = __float_as_uint(t); l[4 * c + 0] = __float_as_uint(tf32_rna(v.x - t));
+            t = tf32_rna(v.y); h[4 * c + 1] = __float_as_uint(t); l[4 * c + 1] = __float_as_uint(tf32_rna(v.y - t));
+            t = tf32_rna(v.z); h[4 * c + 2] = __float_as_uint(t); l[4 * c + 2] = __float_as_uint(tf32_rna(v.z - t));
+            t = tf32_rna(v.w); h[4 * c + 3] = __float_as_uint(t); l[4 * c + 3] = __float_as_uint(tf32_rna(v.w - t));
+          }
+          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + TMEM_A0 + s * 64;
+          TMEM_ST32(ta, h);
+          TMEM_ST32(ta + 32, l);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        mbar_arrive(conv_full(s));    // A operand ready for the MMA warp (the ring stage is released by the MMA warp's commit)
+        if (ct == 0) UTT(2 + grp, 6000 + g);
+      }
+      mbar_arrive(unit_conv_done(grp));
+      // ----- epilogue of this unit (the other group is already converting the next one) -----
+      const int ab = lt & 1;
+      const int row = wu.tile_m * BM + q * 32 + lane;
+      float* cbase = C + (int64_t)wu.split * c_split_stride;
+      float* crow = cbase + (int64_t)row * ldc + (int64_t)wu.tile_n * BN;
+      double acc_sq4[4] = {0.0, 0.0, 0.0, 0.0}, acc_dot4[4] = {0.0, 0.0, 0.0, 0.0};   // fused row statistics: fp64 sums, four interleaved chains each
+      if (wu.nkb > 0) {
+        mbar_wait(tmem_full(ab), (lt >> 1) & 1);
+        tc_fence_after();
+        if (ct == 0) UTT(2 + grp, 300000 + lt);
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t rr[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + c * 32);
+          TMEM_LD32(taddr, rr);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (c == BN / 32 - 1) {                            // accumulator drained: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty(ab));
+          }
+          if (ep.mode != UMMA_EPI_STATS_ONLY) {
+            float4* dst = reinterpret_cast<float4*>(crow + c * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              dst[j] = make_float4(__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1]), __uint_as_float(rr[4 * j + 2]), __uint_as_float(rr[4 * j + 3]));
+          }
+          if (ep.mode == UMMA_EPI_STORE_SUMSQ || ep.mode == UMMA_EPI_STATS_ONLY) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const double v = (double)__uint_as_float(rr[j]);
+              acc_sq4[j & 3] = fma(v, v, acc_sq4[j & 3]);
+              if (ep.mode == UMMA_EPI_STATS_ONLY) acc_dot4[j & 3] = fma(v, ep.tvec[wu.tile_n * BN + c * 32 + j], acc_dot4[j & 3]);
+            }
+          }
+          if (ep.mode == UMMA_EPI_STORE_MIRROR && wu.tile_n != wu.tile_m) {
+            // symmetric product: also write the transposed tile (lanes = consecutive addresses)
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              cbase[(int64_t)(wu.tile_n * BN + c * 32 + j) * ldc + row] = __uint_as_float(rr[j]);
+          }
+        }
+        const double acc_sq = (acc_sq4[0] + acc_sq4[1]) + (acc_sq4[2] + acc_sq4[3]), acc_dot = (acc_dot4[0] + acc_dot4[1]) + (acc_dot4[2] + acc_dot4[3]);
+        if (ep.mode == UMMA_EPI_STORE_SUMSQ) atomicAdd(ep.acc0 + row, acc_sq);
+        if (ep.mode == UMMA_EPI_STATS_ONLY) { atomicAdd(ep.acc0 + row, acc_sq); atomicAdd(ep.acc1 + row, acc_dot); }
+        if (ct == 0) UTT(2 + grp, 400000 + lt);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) UTT(0, 2);
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+
+
 // One entry per latent GP of a grouped launch (device array): the operands' tensor maps and the epilogue targets.
 struct alignas(64) GemmGroup {
   CUtensorMap tmA, tmB;
   float* C; double* acc0; double* acc1; const double* tvec;
+  CUtensorMap tmBhi, tmBlo;    // pre-split planes of the right operand (umma_gemm_grouped_ps_kernel)
 };
 // work unit u of a grouped launch: `work` describes ONE group; units are ordered so that the longest k-extents of every group
 // come first (tri_mode 1) and the groups interleave, which keeps the persistent CTAs balanced under the snake order
@@ -514,7 +731,7 @@ umma_gemm_grouped_kernel(const GemmGroup* __restrict__ groups, const int ngroups
       ep.mode = epi_mode; ep.acc0 = groups[gq].acc0; ep.acc1 = groups[gq].acc1; ep.tvec = groups[gq].tvec; ep.cin = nullptr;
       float* cbase = groups[gq].C + (int64_t)wu.split * c_split_stride;
       float* crow = cbase + (int64_t)row * ldc + (int64_t)wu.tile_n * BN;
-      double acc_sq = 0.0, acc_dot = 0.0;   // fused row statistics (fp64 sums, like rowstats_kernel)
+      double acc_sq4[4] = {0.0, 0.0, 0.0, 0.0}, acc_dot4[4] = {0.0, 0.0, 0.0, 0.0};   // fused row statistics: fp64 sums, four interleaved chains each
       if (wu.nkb > 0) {
         mbar_wait(tmem_full(ab), (lt >> 1) & 1);
         tc_fence_after();
@@ -539,8 +756,8 @@ umma_gemm_grouped_kernel(const GemmGroup* __restrict__ groups, const int ngroups
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const double v = (double)__uint_as_float(rr[j]);
-              acc_sq = fma(v, v, acc_sq);
-              if (ep.mode == UMMA_EPI_STATS_ONLY) acc_dot = fma(v, ep.tvec[wu.tile_n * BN + c * 32 + j], acc_dot);
+              acc_sq4[j & 3] = fma(v, v, acc_sq4[j & 3]);
+              if (ep.mode == UMMA_EPI_STATS_ONLY) acc_dot4[j & 3] = fma(v, ep.tvec[wu.tile_n * BN + c * 32 + j], acc_dot4[j & 3]);
             }
           }
           if (ep.mode == UMMA_EPI_STORE_MIRROR && wu.tile_n != wu.tile_m) {
@@ -550,6 +767,7 @@ umma_gemm_grouped_kernel(const GemmGroup* __restrict__ groups, const int ngroups
               cbase[(int64_t)(wu.tile_n * BN + c * 32 + j) * ldc + row] = __uint_as_float(rr[j]);
           }
         }
+        const double acc_sq = (acc_sq4[0] + acc_sq4[1]) + (acc_sq4[2] + acc_sq4[3]), acc_dot = (acc_dot4[0] + acc_dot4[1]) + (acc_dot4[2] + acc_dot4[3]);
         if (ep.mode == UMMA_EPI_STORE_SUMSQ) atomicAdd(ep.acc0 + row, acc_sq);
         if (ep.mode == UMMA_EPI_STATS_ONLY) { atomicAdd(ep.acc0 + row, acc_sq); atomicAdd(ep.acc1 + row, acc_dot); }
       }
@@ -561,6 +779,200 @@ umma_gemm_grouped_kernel(const GemmGroup* __restrict__ groups, const int ngroups
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
+
+// grouped launch form of umma_gemm_ps_kernel (pre-split right operand)
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+umma_gemm_grouped_ps_kernel(const GemmGroup* __restrict__ groups, const int ngroups, int64_t ldc, int64_t c_split_stride, const GemmWork work,
+                         const int epi_mode) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  using namespace ps;
+  const uint32_t bars = smem_base + ps::RING_BYTES;
+  auto raw_full = [&](int s) { return bars + 8u * s; };
+  auto raw_empty = [&](int s) { return bars + 8u * (RSP + s); };
+  auto conv_full = [&](int s) { return bars + 8u * (2 * RSP + s); };
+  auto mma_done = [&](int s) { return bars + 8u * (2 * RSP + CS + s); };
+  auto tmem_full = [&](int b) { return bars + 8u * (2 * RSP + 2 * CS + b); };
+  auto tmem_empty = [&](int b) { return bars + 8u * (2 * RSP + 2 * CS + 2 + b); };
+  auto unit_conv_done = [&](int b) { return bars + 8u * (2 * RSP + 2 * CS + 4 + b); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + ps::RING_BYTES + 8 * (2 * RSP + 2 * CS + 6));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = gridDim.x, cta = blockIdx.x;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&groups[0].tmA); tma_prefetch_desc(&groups[0].tmBhi); tma_prefetch_desc(&groups[0].tmBlo);
+    for (int s = 0; s < RSP; ++s) { mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), 1); }
+    for (int s = 0; s < CS; ++s) { mbar_init(conv_full(s), NUM_CONV_THREADS); mbar_init(mma_done(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tmem_full(b), 1); mbar_init(tmem_empty(b), 4); mbar_init(unit_conv_done(b), NUM_CONV_THREADS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_ptr_smem)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  // programmatic dependent launch: barrier init / TMEM allocation above overlap the previous kernel of the chain
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer: raw fp32 tiles, one ring across all units of this CTA =====
+      int g = 0;
+      for (int r = 0;; ++r) {
+        const int u = unit_index(r, cta, G);
+        if (u >= work.total * ngroups) break;
+        int gq; const WorkUnit wu = get_unit_grouped(work, ngroups, u, gq);
+        for (int i = 0; i < wu.nkb; ++i, ++g) {
+          const int s = g % RSP;
+          mbar_wait(raw_empty(s), ((g / RSP) & 1) ^ 1);
+          const uint32_t dst = smem_base + s * STAGE_BYTES;
+          mbar_expect_tx(raw_full(s), 3 * TILE_BYTES);
+          const int k = (wu.kb0 + i) * BK;
+          tma_load_2d(dst + 0 * TILE_BYTES, &groups[gq].tmA, raw_full(s), k, wu.tile_m * BM);
+          tma_load_2d(dst + 1 * TILE_BYTES, &groups[gq].tmBhi, raw_full(s), k, wu.tile_n * BN);
+          tma_load_2d(dst + 2 * TILE_BYTES, &groups[gq].tmBlo, raw_full(s), k, wu.tile_n * BN);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: accumulator buffer lt & 1, so the epilogue of unit lt overlaps the main loop of unit lt + 1 =====
+    int g = 0, lt = 0;
+    for (int r = 0;; ++r, ++lt) {
+      const int u = unit_index(r, cta, G);
+      if (u >= work.total * ngroups) break;
+      int gq; const WorkUnit wu = get_unit_grouped(work, ngroups, u, gq);
+      const int ab = lt & 1;
+      mbar_wait(tmem_empty(ab), ((lt >> 1) & 1) ^ 1);      // the epilogue two units ago has drained this accumulator
+      tc_fence_after();
+      const uint32_t acc = tmem_base + ab * BN;
+      for (int i = 0; i < wu.nkb; ++i, ++g) {
+        const int s = g % CS;
+        mbar_wait(conv_full(s), (g / CS) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t b_hi = smem_base + (g % RSP) * STAGE_BYTES + TILE_BYTES, b_lo = b_hi + TILE_BYTES;
+          const uint32_t a_hi = tmem_base + TMEM_A0 + s * 64, a_lo = a_hi + 32;
+#pragma unroll
+          for (int kk = 0; kk < BK / 8; ++kk) {
+            const uint32_t off = kk * 32;  // 8 tf32 = 32 bytes along K inside the 128B swizzle atom (B); 8 TMEM columns (A)
+            const uint64_t dbh = make_desc(b_hi + off), dbl = make_desc(b_lo + off);
+            tc_mma_tf32_ts(acc, a_lo + kk * 8, dbh, kIdesc, (i > 0 || kk > 0) ? 1u : 0u);  // small terms first
+            tc_mma_tf32_ts(acc, a_hi + kk * 8, dbl, kIdesc, 1u);
+            tc_mma_tf32_ts(acc, a_hi + kk * 8, dbh, kIdesc, 1u);
+          }
+          tc_commit(mma_done(s));                          // frees the TMEM A columns of this slot
+          tc_commit(raw_empty(g % RSP));                   // ... and the ring stage
+          if (i == wu.nkb - 1) tc_commit(tmem_full(ab));   // accumulator complete
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===== worker groups: raw -> hi / lo conversion of the group's units, then their epilogue =====
+    const int grp = (warp - 2) >> 2;
+    const int ct = (threadIdx.x - 64) & 127;         // 0..127 within the group
+    const int q = warp & 3;                          // TMEM lane quarter this warp may access
+    const int arow = q * 32 + lane;                  // A-tile row = TMEM lane handled by this thread
+    int g = 0, lt = 0;
+    for (int r = 0;; ++r, ++lt) {
+      const int u = unit_index(r, cta, G);
+      if (u >= work.total * ngroups) break;
+      int gq; const WorkUnit wu = get_unit_grouped(work, ngroups, u, gq);
+      if ((lt & 1) != grp) { g += wu.nkb; continue; }
+      // A group only sees the mbarrier phases of its own units.  Parity waits are unambiguous only within one phase, so
+      // do not start before the other group has issued every conversion of the previous unit (the TMA ring and the MMA
+      // warp are then at most one phase behind on every barrier this group is about to wait on).
+      if (lt > 0) mbar_wait(unit_conv_done(grp ^ 1), ((lt - 1) >> 1) & 1);
+      for (int i = 0; i < wu.nkb; ++i, ++g) {
+        const int rs = g % RSP, s = g % CS;
+        mbar_wait(raw_full(rs), (g / RSP) & 1);              // TMA landed the stage
+        mbar_wait(mma_done(s), ((g / CS) & 1) ^ 1);          // previous MMAs on this slot's converted operands retired
+        tc_fence_after();
+        uint8_t* base = smem_gen + rs * STAGE_BYTES;
+        {
+          // A: row `arow` of the raw tile (128 B, 16-byte chunks XOR-swizzled with row & 7) -> hi / lo -> TMEM
+          const float4* rowp = reinterpret_cast<const float4*>(base + arow * 128);
+          uint32_t h[32], l[32];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 v = rowp[c ^ (arow & 7)];
+            float t;
+            t = tf32_rna(v.x); h[4 * c + 0] = __float_as_uint(t); l[4 * c + 0] = __float_as_uint(tf32_rna(v.x - t));
+            t = tf32_rna(v.y); h[4 * c + 1] = __float_as_uint(t); l[4 * c + 1] = __float_as_uint(tf32_rna(v.y - t));
+            t = tf32_rna(v.z); h[4 * c + 2] = __float_as_uint(t); l[4 * c + 2] = __float_as_uint(tf32_rna(v.z - t));
+            t = tf32_rna(v.w); h[4 * c + 3] = __float_as_uint(t); l[4 * c + 3] = __float_as_uint(tf32_rna(v.w - t));
+          }
+          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + TMEM_A0 + s * 64;
+          TMEM_ST32(ta, h);
+          TMEM_ST32(ta + 32, l);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        mbar_arrive(conv_full(s));    // A operand ready for the MMA warp
+      }
+      mbar_arrive(unit_conv_done(grp));
+      // ----- epilogue of this unit (the other group is already converting the next one) -----
+      const int ab = lt & 1;
+      const int row = wu.tile_m * BM + q * 32 + lane;
+      UmmaEpilogue ep;
+      ep.mode = epi_mode; ep.acc0 = groups[gq].acc0; ep.acc1 = groups[gq].acc1; ep.tvec = groups[gq].tvec; ep.cin = nullptr;
+      float* cbase = groups[gq].C + (int64_t)wu.split * c_split_stride;
+      float* crow = cbase + (int64_t)row * ldc + (int64_t)wu.tile_n * BN;
+      double acc_sq4[4] = {0.0, 0.0, 0.0, 0.0}, acc_dot4[4] = {0.0, 0.0, 0.0, 0.0};   // fused row statistics: fp64 sums, four interleaved chains each
+      if (wu.nkb > 0) {
+        mbar_wait(tmem_full(ab), (lt >> 1) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t rr[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + c * 32);
+          TMEM_LD32(taddr, rr);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (c == BN / 32 - 1) {                            // accumulator drained: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty(ab));
+          }
+          if (ep.mode != UMMA_EPI_STATS_ONLY) {
+            float4* dst = reinterpret_cast<float4*>(crow + c * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              dst[j] = make_float4(__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1]), __uint_as_float(rr[4 * j + 2]), __uint_as_float(rr[4 * j + 3]));
+          }
+          if (ep.mode == UMMA_EPI_STORE_SUMSQ || ep.mode == UMMA_EPI_STATS_ONLY) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const double v = (double)__uint_as_float(rr[j]);
+              acc_sq4[j & 3] = fma(v, v, acc_sq4[j & 3]);
+              if (ep.mode == UMMA_EPI_STATS_ONLY) acc_dot4[j & 3] = fma(v, ep.tvec[wu.tile_n * BN + c * 32 + j], acc_dot4[j & 3]);
+            }
+          }
+          if (ep.mode == UMMA_EPI_STORE_MIRROR && wu.tile_n != wu.tile_m) {
+            // symmetric product: also write the transposed tile (lanes = consecutive addresses)
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              cbase[(int64_t)(wu.tile_n * BN + c * 32 + j) * ldc + row] = __uint_as_float(rr[j]);
+          }
+        }
+        const double acc_sq = (acc_sq4[0] + acc_sq4[1]) + (acc_sq4[2] + acc_sq4[3]), acc_dot = (acc_dot4[0] + acc_dot4[1]) + (acc_dot4[2] + acc_dot4[3]);
+        if (ep.mode == UMMA_EPI_STORE_SUMSQ) atomicAdd(ep.acc0 + row, acc_sq);
+        if (ep.mode == UMMA_EPI_STATS_ONLY) { atomicAdd(ep.acc0 + row, acc_sq); atomicAdd(ep.acc1 + row, acc_dot); }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 
 // =====================================================================================================
 // Third-generation main loop (opt-in: AGP_UMMA_V3=1).  MEASURED on a B200 (profiles/r2/gemm_bench_v1_v3.txt, gemm_trace_v3.txt):
@@ -1245,7 +1657,14 @@ int umma_latent_alloc(std::string* err, UmmaLatent& u, int m, int ldm, int Bcap,
   if ((e = cudaFuncSetAttribute(umma_gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)) != cudaSuccess)
     return fail(err, "cudaFuncSetAttribute", e);
   if (const char* env = getenv("AGP_UMMA_V2")) u.v2 = atoi(env);
-  if (u.v2) {
+  u.ps = 1;
+  if (const char* env = getenv("AGP_UMMA_PS")) u.ps = atoi(env) != 0;
+  if (u.v2 || getenv("AGP_UMMA_V3")) u.ps = 0;
+  if (u.ps) {
+    if ((e = cudaFuncSetAttribute(umma_gemm_ps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ps::SMEM_BYTES)) != cudaSuccess)
+      return fail(err, "cudaFuncSetAttribute (ps)", e);
+  }
+  if (u.v2 || u.ps) {
     // pre-split copies of the two m x m right operands: [L^-1 hi | L^-1 lo | X hi | X lo], each [m][ldm]
     const size_t each = (size_t)m * ldm;
     if (each % 4) return fail(err, "v2: m * ldm must be a multiple of 4");
@@ -1254,7 +1673,7 @@ int umma_latent_alloc(std::string* err, UmmaLatent& u, int m, int ldm, int Bcap,
     for (int w = 0; w < 2; ++w)
       for (int h = 0; h < 2; ++h) ok = ok && make_map(&mp->split[w][h], u.Bsplit + (size_t)(2 * w + h) * each, m, m, ldm);
     if (!ok) return fail(err, "cuTensorMapEncodeTiled failed (v2)");
-    if ((e = cudaFuncSetAttribute(umma_gemm_nt_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SMEM_BYTES)) != cudaSuccess)
+    if (u.v2 && (e = cudaFuncSetAttribute(umma_gemm_nt_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SMEM_BYTES)) != cudaSuccess)
       return fail(err, "cudaFuncSetAttribute (v2)", e);
   }
   return 0;
@@ -1266,7 +1685,7 @@ float* umma_split_ptr(const UmmaLatent& u, int which, int lo) {
 }
 
 int umma_presplit(std::string* err, UmmaLatent& u, int which, const float* src, cudaStream_t st) {
-  if (!u.v2) return 0;
+  if (!u.v2 && !u.ps) return 0;
   float* hi = umma_split_ptr(u, which, 0);
   float* lo = umma_split_ptr(u, which, 1);
   if (!hi) return fail(err, "v2: no pre-split buffer for this operand");
@@ -1356,6 +1775,14 @@ int umma_gemm_nt(std::string* err, UmmaLatent& u, int a_which, int b_which, floa
                  (int64_t)0, w, ep, presplit);
     cudaError_t e2 = cudaGetLastError();
     if (e2 != cudaSuccess) return fail(err, "umma_gemm_nt_v2_kernel", e2);
+    return 0;
+  }
+  if (u.ps && (b_which == UM_LINV || b_which == UM_X)) {
+    const int sp = b_which == UM_LINV ? 0 : 1;
+    launch_chain(umma_gemm_ps_kernel, dim3(grid), dim3(NUM_THREADS), ps::SMEM_BYTES, st, mp->raw[a_which], mp->split[sp][0], mp->split[sp][1], C,
+                 (int64_t)u.ldm, (int64_t)0, w, ep);
+    cudaError_t e3 = cudaGetLastError();
+    if (e3 != cudaSuccess) return fail(err, "umma_gemm_ps_kernel", e3);
     return 0;
   }
   if (v3_on())
@@ -1452,6 +1879,10 @@ int umma_groups_build(std::string* err, UmmaGroups& gs, UmmaLatent* const* lats,
     if (!mp) return fail(err, "grouped launch: latent without tensor maps");
     h[q].tmA = a_which < 0 ? mp->ut : mp->raw[a_which];
     h[q].tmB = b_which < 0 ? mp->ut : mp->raw[b_which];
+    const bool psq = lats[q]->ps && (b_which == UM_LINV || b_which == UM_X);
+    if (q == 0) gs.ps = psq ? 1 : 0;
+    else if ((gs.ps != 0) != psq) return fail(err, "grouped launch: latents disagree on the pre-split operand");
+    if (psq) { h[q].tmBhi = mp->split[b_which == UM_LINV ? 0 : 1][0]; h[q].tmBlo = mp->split[b_which == UM_LINV ? 0 : 1][1]; }
     h[q].C = C ? C[q] : nullptr;
     h[q].acc0 = acc0 ? acc0[q] : nullptr; h[q].acc1 = acc1 ? acc1[q] : nullptr; h[q].tvec = tvec ? tvec[q] : nullptr;
   }
@@ -1466,6 +1897,8 @@ int umma_groups_build(std::string* err, UmmaGroups& gs, UmmaLatent* const* lats,
   if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail(err, "cudaStreamSynchronize", e);
   if ((e = cudaFuncSetAttribute(umma_gemm_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)) != cudaSuccess)
     return fail(err, "cudaFuncSetAttribute", e);
+  if ((e = cudaFuncSetAttribute(umma_gemm_grouped_ps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ps::SMEM_BYTES)) != cudaSuccess)
+    return fail(err, "cudaFuncSetAttribute (grouped ps)", e);
   return 0;
 }
 void umma_groups_free(UmmaGroups& gs) { if (gs.dev) cudaFree(gs.dev); gs.dev = nullptr; gs.n = 0; }
@@ -1479,7 +1912,9 @@ int umma_gemm_nt_grouped(std::string* err, const UmmaGroups& gs, const UmmaLaten
   w.tri_mode = b_tri ? 1 : 0;
   const int all = w.total * gs.n;
   const int grid = all < grid_cap() ? all : grid_cap();
-  if (v3_on()) {
+  if (gs.ps) {
+    launch_chain(umma_gemm_grouped_ps_kernel, dim3(grid), dim3(NUM_THREADS), ps::SMEM_BYTES, st, (const GemmGroup*)gs.dev, gs.n, (int64_t)u.ldm, (int64_t)0, w, epi_mode);
+  } else if (v3_on()) {
     static const CUtensorMap none{};
     launch_chain(umma_gemm3_kernel<true>, dim3(grid), dim3(NUM_THREADS), v3::SMEM_BYTES, st, none, none, (float*)nullptr, UmmaEpilogue{}, (const GemmGroup*)gs.dev, gs.n,
                  (int64_t)u.ldm, (int64_t)0, w, epi_mode);

@@ -36,6 +36,9 @@ struct UmmaLatent {
   // bit 1 = keep splitting the m x m operand inside the kernel.  Bsplit = TF32 hi / lo copies of L^-1 and X.
   int v2 = 0;
   float* Bsplit = nullptr;
+  // pre-split right operand with the first-generation main loop (umma_gemm_ps_kernel; default ON, AGP_UMMA_PS=0 disables): Bsplit holds
+  // the planes, the worker groups only split the A operand
+  int ps = 0;
 };
 
 bool umma_shape_ok(int m, int Bcap);
@@ -68,7 +71,7 @@ int umma_gram_splits(int B, int cap);   // largest usable split count <= cap
 
 // ---- grouped launches: the same-shaped product of several latent GPs in ONE persistent launch (multi-latent models: the per-launch
 // fixed cost of a C2 / C4 sized product, ~8 us, is paid once; the persistent CTAs stay balanced over n x tiles work units) ----
-struct UmmaGroups { void* dev = nullptr; int n = 0; };   // device array, one entry (tensor maps + epilogue targets) per latent
+struct UmmaGroups { void* dev = nullptr; int n = 0; int ps = 0; };   // device array, one entry (tensor maps + epilogue targets) per latent
 // a_which / b_which: UmmaMat of the operands (-1 = the latent's U^T buffer: Gram product); C / acc0 / acc1 / tvec: per-latent epilogue
 // targets (null arrays allowed).  Call again after a latent's buffers or tensor maps change.
 int umma_groups_build(std::string* err, UmmaGroups& gs, UmmaLatent* const* lats, int n, int a_which, int b_which, float* const* C,

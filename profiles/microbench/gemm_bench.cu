@@ -22,6 +22,8 @@ int main(int argc, char** argv) {
   cudaMemcpy(dX, X.data(), X.size() * 4, cudaMemcpyHostToDevice); cudaMemset(acc, 0, 3 * B * 8); cudaMemset(tvec, 0, m * 8);
   std::string err; UmmaLatent u;
   if (umma_latent_alloc(&err, u, m, m, B, dA, dV, dL, dX, 0)) { printf("alloc: %s\n", err.c_str()); return 1; }
+  umma_presplit(&err, u, UM_LINV, dL, 0); umma_presplit(&err, u, UM_X, dX, 0);   // pre-split right operands (no-op unless AGP_UMMA_PS / V2)
+  printf("pre-split right operand: %d\n", u.ps);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   auto timeit = [&](const char* name, auto fn, double flops) {
     for (int w = 0; w < 3; ++w) fn();

@@ -48,6 +48,8 @@ int main(int argc, char** argv) {
   cudaMemcpy(dX, X.data(), X.size() * 4, cudaMemcpyHostToDevice); cudaMemset(acc, 0, 3 * B * 8); cudaMemset(tvec, 0, m * 8);
   std::string err; UmmaLatent u;
   if (umma_latent_alloc(&err, u, m, m, B, dA, dV, dL, dX, 0)) { printf("alloc: %s\n", err.c_str()); return 1; }
+  umma_presplit(&err, u, UM_LINV, dL, 0); umma_presplit(&err, u, UM_X, dX, 0);   // pre-split right operands (no-op unless AGP_UMMA_PS / V2)
+  printf("pre-split right operand: %d\n", u.ps);
   std::vector<int> z(160 * 4, 0);
   UmmaEpilogue ep1{}; ep1.mode = UMMA_EPI_STORE_SUMSQ; ep1.acc0 = acc;
   UmmaEpilogue ep2{}; ep2.mode = UMMA_EPI_STATS_ONLY; ep2.acc0 = acc + B; ep2.acc1 = acc + 2 * B; ep2.tvec = tvec;
