@@ -212,6 +212,7 @@ struct Engine : EngineBase {
   bool fuse_lik_next = false, fuse_from_batch = false, lik_fused = false;   // rowfinish + local-update fusion (set by the step paths)
   bool stats_use_early = false;    // moments stage 2 of this step only adds the last N tile (set by step_pool)
   bool racc2_precleared = false;   // the V X^T row-statistic accumulators were cleared off the critical chain (side stream)
+  int chain_variant = 0; // AGP_CHAIN: pivot-chain implementation of the multi-launch tail (agp_tail2.cuh chain16_*): 0 = scalar (default), 1 = look-ahead (opt-in: 132 vs 126.7 us at C2)
   int tail_variant = 3;  // AGP_TAIL_VARIANT: 0 = agp_tail.cuh (generation 1, SIMT tile products), 2 = agp_tail2.cuh (DMMA, panel potf2, one
                          // launch per block step and latent), 3 (default) = agp_tail3.cuh (one persistent launch for all owned latents)
   Tail3Lat* d_t3lat = nullptr; u64* d_t3flags = nullptr;
@@ -442,8 +443,10 @@ struct Engine : EngineBase {
     CK(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, potf2_smem()));
     CK(cudaFuncSetAttribute(tail_potf2_first_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM));
     CK(cudaFuncSetAttribute(tail_step_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM));
-    CK(cudaFuncSetAttribute(tail2_potf2_first_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL2_SMEM));
-    CK(cudaFuncSetAttribute(tail2_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL2_SMEM));
+    CK(cudaFuncSetAttribute(tail2_potf2_first_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL2_SMEM));
+    CK(cudaFuncSetAttribute(tail2_potf2_first_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL2_SMEM));
+    CK(cudaFuncSetAttribute(tail2_step_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL2_SMEM));
+    CK(cudaFuncSetAttribute(tail2_step_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL2_SMEM));
     { const char* e = getenv("AGP_TAIL_PDL"); if (e && e[0] == '0') tail_pdl = false; }
     { const char* e = getenv("AGP_TAIL_NS"); if (e) ns_iters = std::max(0, std::min(8, atoi(e))); }
     { const char* e = getenv("AGP_TAIL_NS_AFTER"); if (e) ns_after = std::max(1, atoi(e)); }
@@ -455,6 +458,7 @@ struct Engine : EngineBase {
     // default: the persistent tail for two or more owned latents (one launch, the chains run side by side), the multi-launch tail2
     // chain for a single latent (126 vs 138 us at m = 512: see agp_tail3.cuh)
     tail_variant = Ql >= 2 ? 3 : 2;
+    { const char* e = getenv("AGP_CHAIN"); if (e) chain_variant = atoi(e) ? 1 : 0; }
     { const char* e = getenv("AGP_TAIL_VARIANT"); if (e) { tail_variant = atoi(e); if (tail_variant != 0 && tail_variant != 2) tail_variant = 3; } }
     { const char* e = getenv("AGP_TAIL3_SMS"); if (e && atoi(e) >= 2) t3_sm_budget = std::min(148, atoi(e)); }
     {   // per-latent descriptors + dependency words of the persistent tail (zero-initialised: epoch 0)
@@ -1760,7 +1764,8 @@ struct Engine : EngineBase {
     TailStepParams tp{};
     tp.P = L.P; tp.W = L.W; tp.Xout = L.Xv; tp.Dinv = L.Dinv; tp.ld = mp; tp.nblk = mp / TNB; tp.logdet = L.logdetP; tp.status = status;
     if (tail_variant == 0) tail_potf2_first_kernel<0><<<1, TAIL_THREADS, TAIL_SMEM, st()>>>(tp);
-    else launch_tail2(tail2_potf2_first_kernel<0>, 1, tp);
+    else if (chain_variant == 0) launch_tail2(tail2_potf2_first_kernel<0, 0>, 1, tp);
+    else launch_tail2(tail2_potf2_first_kernel<0, 1>, 1, tp);
     ++launches;
     if (split_gram_now) { cudaStreamWaitEvent(st(), ev_gb, 0); split_gram_now = false; }   // the rest of P_v (side stream) is needed from the first block step on
     for (int k = 0; k < tp.nblk; ++k) {
@@ -1769,7 +1774,8 @@ struct Engine : EngineBase {
       if (tiles == 0) continue;
       tp.k = k;
       if (tail_variant == 0) tail_step_kernel<0><<<tiles, TAIL_THREADS, TAIL_SMEM, st()>>>(tp);
-      else launch_tail2(tail2_step_kernel, tiles, tp);
+      else if (chain_variant == 0) launch_tail2(tail2_step_kernel<0>, tiles, tp);
+      else launch_tail2(tail2_step_kernel<1>, tiles, tp);
       ++launches;
       // rows [64 k, 64 k + 64) of X are final now; every second block completes a 128-row N tile of the next step's statistics
       if (early_now && (k & 1) && (k >> 1) + 1 < m / 128) cudaEventRecord(ev_blk[k >> 1], st());

@@ -162,20 +162,11 @@ __device__ __forceinline__ void x_rows_store(const double* sx, int r0, int tt, i
   }
 }
 
-template <int ABL = 0>
-__device__ __forceinline__ void tile2_potf2_inv(double* sa, double* sx, double* sl, double* vec, double* __restrict__ Xg, int64_t ldx,
-                                                double* __restrict__ Dg, double* __restrict__ logdet, int* __restrict__ status) {
-  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-  const int r = lane >> 2, kk = lane & 3;
+// ---- the 16-pivot chain of one panel: two implementations (CHAIN 0: scalar chain with the reciprocal started one pivot ahead, the
+// round-1 version; CHAIN 1: next column kept locally + seeded reciprocals) ----
+__device__ __forceinline__ void chain16_scalar(double* sa, double* sx, double* vec, const int c0, const int lane, int* __restrict__ status) {
   double* col = vec;            // [2][20]  (16 column entries + the next diagonal element)
-  double* dvals = vec + 40;     // [64]
-#pragma unroll 1
-  for (int J = 0; J < 4; ++J) {
-    const int c0 = 16 * J, nbelow = TNB - c0 - 16;
-    if (w == 0) {
-      // ---- (a) pivot chain on the 16 x 16 diagonal block ---------------------------------------------------------
-      if (J > 0) bar_sync1();                    // the diagonal block has received the trailing update of panel J-1
-      if (!(ABL & 1)) {
+  double* dvals = vec + 48;     // [64]
       const int rr = lane & 15;
       const bool arow = lane < 16;
       bool bad = false;
@@ -226,6 +217,125 @@ __device__ __forceinline__ void tile2_potf2_inv(double* sa, double* sx, double* 
 #pragma unroll
         for (int q = 0; q < 16; ++q) sx[(c0 + q) * T2LD + c0 + rr] = (q >= rr) ? x[q] * rsv[q] : 0.0;
       }
+}
+
+__device__ __forceinline__ void chain16_lookahead(double* sa, double* sx, double* vec, const int c0, const int lane, int* __restrict__ status) {
+  double* col = vec;            // [2][24]
+  double* dvals = vec + 48;     // [64]
+      const int rr = lane & 15;
+      const bool arow = lane < 16;
+      bool bad = false;
+      double x[16], rsv[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const int hi_ = rr > q ? rr : q, lo_ = rr > q ? q : rr;
+        x[q] = arow ? sa[(c0 + hi_) * T2LD + c0 + lo_] : (q == rr ? 1.0 : 0.0);  // row rr of the block (symmetric) | column rr of W
+      }
+      // The pivot recurrence, as short as the arithmetic allows.  Two latencies used to sit on it -- the shared-memory round trip that
+      // broadcasts column j+1 after pivot j has updated it (~100 cycles) and the reciprocal of the pivot (MUFU.RCP64H ~80) -- 126
+      // cycles per pivot in total.  Now:
+      //  * every lane keeps its own copy of the NEXT column and applies pivot j's rank-1 update to it itself (cA: column j, cN: column
+      //    j+1, both in registers; 15 - j extra DFMAs per lane), so column j+1 is known without waiting for anybody; what travels
+      //    through shared memory is column j+2 (published after pivot j, needed during pivot j+1): one whole pivot of slack;
+      //  * 1 / d_{j+2} is SEEDED at pivot j from the leading 3 x 3 minor of the block as it stands then (det2 / det3; the raw
+      //    MUFU.RCP64H result is refined by the next pivot, so its latency never stalls this in-order warp), and pivot j+2 spends one
+      //    Newton step y <- y (2 - d y) on the true pivot: the seed's error (cancellation in det3) is squared, 1 / d is good to ~1e-15.
+      // Recurrence per pivot: d = cA[j] -> Newton (2 DFMA) -> f = cA[j+1] / d (DMUL) -> cN[q] -= cA[q] f (DFMA).
+      double cA[16], cN[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        cA[q] = sa[(c0 + q) * T2LD + c0];                                                   // column 0 (lower triangle of the tile)
+        cN[q] = (q >= 1) ? sa[(c0 + q) * T2LD + c0 + 1] : sa[(c0 + 1) * T2LD + c0];          // column 1 (symmetric)
+      }
+      double a22n = sa[(c0 + 2) * T2LD + c0 + 2];    // diagonal entry j+2 of the current state (for the seed)
+      double seed_cur = 0.0, seed_first = 0.0;       // seed of 1 / d_j; 1 / d_1 from the first pair
+      double p_det2 = 1.0, p_det3 = 1.0, p_raw = 1.0;   // determinants / raw reciprocal issued by the previous pivot
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        double* pub = col + (j & 1) * 24;          // column j+2 (+ the diagonal entry j+3) of the state AFTER this pivot
+        double d = cA[j];
+        if (!(d > 0.0)) { bad = true; d = 1.0; }                  // PosDefException is raised after the chain (no branch on the chain)
+        double inv;
+        if (j == 0) inv = rcp_chain<2>(d);
+        else inv = fma(seed_cur, fma(-d, seed_cur, 1.0), seed_cur);
+        // seed of the pivot after next, from the 3 x 3 minor (rows / columns j, j+1, j+2) of the state before this pivot
+        double seed2 = 0.0;
+        if (j >= 1 && j < 15) seed2 = p_det2 * fma(p_raw, fma(-p_det3, p_raw, 1.0), p_raw);      // 1 / d_{j+1}, issued by pivot j-1
+        if (j < 15) {
+          const double a01 = cA[j + 1], a11 = cN[j + 1];
+          const double det2 = fma(a11, d, -a01 * a01);            // d_j d_{j+1}
+          if (j == 0) seed_first = d * rcp_chain<1>(det2);
+          if (j < 14) {
+            const double a02 = cA[j + 2], a12 = cN[j + 2];
+            const double t = fma(d * a12, a12, fma(-2.0 * a01 * a02, a12, a11 * a02 * a02));
+            p_det2 = det2; p_det3 = fma(det2, a22n, -t);
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(p_raw) : "d"(p_det3));   // consumed by the NEXT pivot
+          }
+        }
+        // column j+1 after this pivot, locally
+        if (j < 15) {
+          const double f = cA[j + 1] * inv;
+#pragma unroll
+          for (int q = j + 1; q < 16; ++q) cN[q] = fma(-cA[q], f, cN[q]);
+        }
+        // own row (A lanes) / own column of W (W lanes)
+        double g = -x[j] * inv;                  // rows: -a_rj / d_j ; W columns: -w_jr / d_j
+        if (arow && rr <= j) g = 0.0;            // rows at or above the pivot are not touched
+#pragma unroll
+        for (int q = j + 1; q < 16; ++q) x[q] = fma(cA[q], g, x[q]);   // a_rq -= a_rj a_qj / d | w_qr -= a_qj w_jr / d
+        // publish column j+2 of the new state (and the diagonal entry j+3) for the pivot after next
+        if (j < 14) {
+          if (arow) pub[rr] = x[j + 2];
+          if (j < 13 && arow && rr == j + 3) pub[16] = x[j + 3];
+        }
+        rsv[j] = d;
+        if (lane == j) dvals[c0 + j] = d;
+        __syncwarp();
+        // rotate: column j+1 becomes the pivot column; fetch column j+2 (published just now; its consumers are the NEXT pivot's updates)
+        seed_cur = (j == 0) ? seed_first : seed2;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) cA[q] = cN[q];
+        if (j < 14) {
+#pragma unroll
+          for (int q = j + 2; q < 16; ++q) cN[q] = pub[q];
+          a22n = (j < 13) ? pub[16] : 0.0;
+        }
+      }
+      if (bad && lane == 0) atomicOr(status, ST_NOT_POSDEF);
+      // d^-1/2 for the row scaling, branch-free (library rsqrt() carries a slow-path branch per call, and basic-block
+      // boundaries inside the pivot loop stop the scheduler from interleaving the chains): MUFU.RSQ64H + two Newton steps
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        double y;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(rsv[q]));
+        double e = fma(-rsv[q] * y, y, 1.0);
+        y = fma(0.5 * y, e, y);
+        e = fma(-rsv[q] * y, y, 1.0);
+        rsv[q] = fma(0.5 * y, e, y);
+      }
+      // X_JJ = diag(d)^-1/2 W  (rows of W scaled)
+      if (!arow) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) sx[(c0 + q) * T2LD + c0 + rr] = (q >= rr) ? x[q] * rsv[q] : 0.0;
+      }
+}
+
+template <int ABL = 0, int CHAIN = 1>
+__device__ __forceinline__ void tile2_potf2_inv(double* sa, double* sx, double* sl, double* vec, double* __restrict__ Xg, int64_t ldx,
+                                                double* __restrict__ Dg, double* __restrict__ logdet, int* __restrict__ status) {
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const int r = lane >> 2, kk = lane & 3;
+  double* col = vec;            // [2][24]  (16 column entries + three entries of the next two rows, see the seeds below)
+  double* dvals = vec + 48;     // [64]
+#pragma unroll 1
+  for (int J = 0; J < 4; ++J) {
+    const int c0 = 16 * J, nbelow = TNB - c0 - 16;
+    if (w == 0) {
+      // ---- (a) pivot chain on the 16 x 16 diagonal block ---------------------------------------------------------
+      if (J > 0) bar_sync1();                    // the diagonal block has received the trailing update of panel J-1
+      if (!(ABL & 1)) {
+      if (CHAIN == 0) chain16_scalar(sa, sx, vec, c0, lane, status);
+      else chain16_lookahead(sa, sx, vec, c0, lane, status);
       }
     } else {
       const int tt = t - 32;
@@ -317,16 +427,17 @@ __device__ __forceinline__ void tile2_potf2_inv(double* sa, double* sx, double* 
   }
 }
 
-template <int ABL = 0>
+template <int ABL = 0, int CHAIN = 1>
 __global__ void __launch_bounds__(TAIL_THREADS, 1) tail2_potf2_first_kernel(const TailStepParams p) {
   extern __shared__ double sm[];
   pdl_launch_dependents();   // let the next block step get resident while this one runs; it waits in pdl_wait()
   pdl_wait();
   tile2_load(sm, p.P, p.ld);
   __syncthreads();
-  tile2_potf2_inv<ABL>(sm, sm + T2_TILE, sm + 5 * T2_TILE, sm + 5 * T2_TILE + TNB * T2SL, p.Xout, p.ld, p.Dinv, p.logdet, p.status);
+  tile2_potf2_inv<ABL, CHAIN>(sm, sm + T2_TILE, sm + 5 * T2_TILE, sm + 5 * T2_TILE + TNB * T2SL, p.Xout, p.ld, p.Dinv, p.logdet, p.status);
 }
 
+template <int CHAIN = 1>
 __global__ void __launch_bounds__(TAIL_THREADS, 1) tail2_step_kernel(const TailStepParams p) {
   extern __shared__ double sm[];
   double* sX = sm;                  // X_kk
@@ -390,7 +501,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) tail2_step_kernel(const TailS
         for (int s_ = 0; s_ < 5; ++s_)
           if (tl.live[s_]) *reinterpret_cast<double2*>(s1 + tl.row[s_] * T2LD + tl.col[s_] + c2) = make_double2(old5[s_].x - acc5[s_][0], old5[s_].y - acc5[s_][1]);
         __syncthreads();
-        tile2_potf2_inv(s1, s2, sl, vec, p.Xout + (int64_t)(k + 1) * TNB * (ld + 1), ld, p.Dinv + (int64_t)(k + 1) * TNB * TNB, p.logdet, p.status);
+        tile2_potf2_inv<0, CHAIN>(s1, s2, sl, vec, p.Xout + (int64_t)(k + 1) * TNB * (ld + 1), ld, p.Dinv + (int64_t)(k + 1) * TNB * TNB, p.logdet, p.status);
       }
     }
   } else if (b < nA + nW) {

@@ -26,13 +26,21 @@ def main(raw, out_csv, out_json):
     ir, iw, ik = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
     per = {}
     gemm_seen = 0
+    ps_seen = 0
     for r in data:
         b = float(r[ir]) * UNIT.get(units[ir], 1.0) + float(r[iw]) * UNIT.get(units[iw], 1.0)
         name = r[ik]
         if "knm_umma_kernel" in name:
             key = "kmat_knm"
+        elif "umma_gemm_ps_kernel" in name:
+            # round 2: the two products with a pre-split right operand; inside one pipelined step V X^T (main stream) precedes V = K_nm L^-T
+            key = ["gemm_v_sigma", "gemm_v"][ps_seen % 2]
+            ps_seen += 1
         elif "umma_gemm_nt_kernel" in name:
-            key = ["gemm_v_sigma", "gemm_gram", "gemm_v"][gemm_seen % 3]   # order of the three GEMMs inside one pipelined step
+            if ps_seen:
+                key = "gemm_gram"      # with the pre-split kernel in use, the first-generation kernel only runs the Gram product
+            else:
+                key = ["gemm_v_sigma", "gemm_gram", "gemm_v"][gemm_seen % 3]   # order of the three GEMMs inside one pipelined step
             gemm_seen += 1
         elif "tail2_step_kernel" in name or "tail_step_kernel" in name:
             key = "tail_step"

@@ -7,6 +7,7 @@
 #include <cmath>
 using namespace agp;
 static bool g_pdl = false;
+static int g_chain = 1;   // argv[2]: pivot-chain implementation (0 = scalar, 1 = look-ahead)
 template <typename K>
 static void launch2(K kern, int grid, TailStepParams tp, cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};
@@ -18,17 +19,21 @@ static void launch2(K kern, int grid, TailStepParams tp, cudaStream_t st) {
 }
 static void launch_seq(int gen, TailStepParams tp, cudaStream_t st) {
   if (gen == 0) tail_potf2_first_kernel<0><<<1, TAIL_THREADS, TAIL_SMEM, st>>>(tp);
-  else launch2(tail2_potf2_first_kernel<0>, 1, tp, st);
+  else if (g_chain == 0) launch2(tail2_potf2_first_kernel<0, 0>, 1, tp, st);
+  else launch2(tail2_potf2_first_kernel<0, 1>, 1, tp, st);
   for (int k = 0; k < tp.nblk; ++k) {
     int r = tp.nblk - 1 - k, tiles = r * (r + 1) / 2 + r * (k + 1) + k;
     if (!tiles) continue;
     tp.k = k;
     if (gen == 0) tail_step_kernel<0><<<tiles, TAIL_THREADS, TAIL_SMEM, st>>>(tp);
-    else launch2(tail2_step_kernel, tiles, tp, st);
+    else if (g_chain == 0) launch2(tail2_step_kernel<0>, tiles, tp, st);
+    else launch2(tail2_step_kernel<1>, tiles, tp, st);
   }
 }
 int main(int argc, char** argv) {
   const int m = argc > 1 ? atoi(argv[1]) : 512, nblk = m / 64;
+  g_chain = argc > 2 ? atoi(argv[2]) : 1;
+  printf("pivot chain variant %d\n", g_chain);
   std::vector<double> A((size_t)m * m), G((size_t)m * 96);
   srand(1);
   for (auto& g : G) g = rand() / (double)RAND_MAX - 0.5;
@@ -54,8 +59,10 @@ int main(int argc, char** argv) {
   cudaMemcpy(dA, A.data(), bytes, cudaMemcpyHostToDevice);
   cudaFuncSetAttribute(tail_potf2_first_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM);
   cudaFuncSetAttribute(tail_step_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL_SMEM);
-  cudaFuncSetAttribute(tail2_potf2_first_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL2_SMEM);
-  cudaFuncSetAttribute(tail2_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL2_SMEM);
+  cudaFuncSetAttribute(tail2_potf2_first_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL2_SMEM);
+  cudaFuncSetAttribute(tail2_potf2_first_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL2_SMEM);
+  cudaFuncSetAttribute(tail2_step_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL2_SMEM);
+  cudaFuncSetAttribute(tail2_step_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TAIL2_SMEM);
   cudaStream_t st; cudaStreamCreate(&st);
   TailStepParams tp{}; tp.P = dP; tp.W = dW; tp.Xout = dX; tp.Dinv = dD; tp.ld = m; tp.nblk = nblk; tp.logdet = dl; tp.status = ds;
   for (int gen = 0; gen < 3; ++gen) {
