@@ -212,6 +212,7 @@ struct Engine : EngineBase {
   bool fuse_lik_next = false, fuse_from_batch = false, lik_fused = false;   // rowfinish + local-update fusion (set by the step paths)
   bool stats_use_early = false;    // moments stage 2 of this step only adds the last N tile (set by step_pool)
   bool racc2_precleared = false;   // the V X^T row-statistic accumulators were cleared off the critical chain (side stream)
+  bool combine4_on = false;  // AGP_COMBINE4=1: four columns per thread in the natural-parameter update (measured SLOWER: 5.40 k vs 5.51 k it/s at C2 - fewer loads in flight)
   int chain_variant = 0; // AGP_CHAIN: pivot-chain implementation of the multi-launch tail (agp_tail2.cuh chain16_*): 0 = scalar (default), 1 = look-ahead (opt-in: 132 vs 126.7 us at C2)
   int tail_variant = 3;  // AGP_TAIL_VARIANT: 0 = agp_tail.cuh (generation 1, SIMT tile products), 2 = agp_tail2.cuh (DMMA, panel potf2, one
                          // launch per block step and latent), 3 (default) = agp_tail3.cuh (one persistent launch for all owned latents)
@@ -459,6 +460,7 @@ struct Engine : EngineBase {
     // chain for a single latent (126 vs 138 us at m = 512: see agp_tail3.cuh)
     tail_variant = Ql >= 2 ? 3 : 2;
     { const char* e = getenv("AGP_CHAIN"); if (e) chain_variant = atoi(e) ? 1 : 0; }
+    { const char* e = getenv("AGP_COMBINE4"); if (e) combine4_on = e[0] != '0'; }
     { const char* e = getenv("AGP_TAIL_VARIANT"); if (e) { tail_variant = atoi(e); if (tail_variant != 0 && tail_variant != 2) tail_variant = 3; } }
     { const char* e = getenv("AGP_TAIL3_SMS"); if (e && atoi(e) >= 2) t3_sm_budget = std::min(148, atoi(e)); }
     {   // per-latent descriptors + dependency words of the persistent tail (zero-initialised: epoch 0)
@@ -1581,7 +1583,10 @@ struct Engine : EngineBase {
         gemv_t_kernel<T><<<dim3((m + 31) / 32, (B + rpb - 1) / rpb), dim3(32, 8), 0, st()>>>(L.V, ldm, gmu + (size_t)q * ldB, B, m, rpb, L.v1); }
       ++launches;
       ph_end();
-      if (prec == AGP_PREC_TF32X3) {
+      // single launches: the Gram kernel reads V itself (scaling, transposition and V^T grad_mu inside its worker threads); grouped and
+      // split launches keep the scale-transpose pass
+      const bool gram_tn = prec == AGP_PREC_TF32X3 && !grp && L.um.gram_tn && !split_gram_ok();
+      if (prec == AGP_PREC_TF32X3 && !gram_tn) {
         ph_begin(PH_SPLIT);
         umma_set_pdl(tail_pdl && !prof && !fan_active);
         CKS(umma_scale_transpose(ctx_err(), L.um, (const float*)(const void*)L.V, gS + (size_t)q * ldB, rho, gmu + (size_t)q * ldB, L.v1, B, m, st()));
@@ -1619,7 +1624,13 @@ struct Engine : EngineBase {
       }
       ph_begin(PH_GRAM);
       int ns = n_split;
-      if (prec == AGP_PREC_TF32X3) {
+      if (gram_tn) {
+        umma_set_pdl(tail_pdl && !prof && !fan_active);
+        int sg = umma_gram_tn(ctx_err(), L.um, (float*)(void*)L.Gpart, gS + (size_t)q * ldB, rho, gmu + (size_t)q * ldB, L.v1, B, m, &ns, st());
+        umma_set_pdl(false);
+        CKS(sg);
+        ++launches;
+      } else if (prec == AGP_PREC_TF32X3) {
         CKS(umma_gram(ctx_err(), L.um, (float*)(void*)L.Gpart, B, m, &ns, st()));
         umma_set_pdl(false);
         ++launches;
@@ -1659,6 +1670,10 @@ struct Engine : EngineBase {
     tp.lr = d_lr; tp.v1_zero = (prec == AGP_PREC_TF32X3) ? L.v1 : nullptr;
     tp.eta1_off = L.online ? L.on_c1v : nullptr; tp.eta2_off = L.online ? L.on_C2v : nullptr;
     tp.blk_mode = blk;
+    // whole matrix on the tf32x3 path: four columns per thread (combine4_kernel); the summation order of the slices is the scalar kernel's
+    if (blk == 0 && combine4_on && prec == AGP_PREC_TF32X3 && mp == m && m % 4 == 0 && ldm % 4 == 0 && tp.gpart_stride % 4 == 0)
+      launch_chain(combine4_kernel, dim3((m / 4 + 127) / 128, m), dim3(128), 0, tp, (const float*)(const void*)L.Gpart);
+    else
     launch_chain(combine_kernel<T>, blk == 1 ? dim3(1, 128) : grid_mp(), dim3(128), 0, tp, (const T*)L.Gpart);
     ++launches;
   }
@@ -2611,7 +2626,7 @@ struct Engine : EngineBase {
       for (int r = 0; r < reps; ++r)
         xx_gather_kernel<T><<<(B + 255) / 256, 256, 0, st()>>>(idx_pool + ((c[1] + r) % n_lists) * B, B, xx, xxr + (size_t)r * B);
     }
-    if (which == 3) CKS(umma_scale_transpose(ctx_err(), L.um, (const float*)(const void*)L.V, gS, 1.0, gmu, L.v1, B, m, st()));
+    if (which == 3 && !L.um.gram_tn) CKS(umma_scale_transpose(ctx_err(), L.um, (const float*)(const void*)L.V, gS, 1.0, gmu, L.v1, B, m, st()));
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     CK(cudaStreamSynchronize(st()));
@@ -2630,7 +2645,8 @@ struct Engine : EngineBase {
         rc = umma_gemm_nt(ctx_err(), L.um, which == 1 ? UM_KNM : UM_V, which == 1 ? UM_LINV : UM_X, (float*)(void*)(which == 1 ? L.V : L.VS), B, m, ep, st());
       } else {
         int ns = n_split;
-        rc = umma_gram(ctx_err(), L.um, (float*)(void*)L.Gpart, B, m, &ns, st());
+        if (L.um.gram_tn) rc = umma_gram_tn(ctx_err(), L.um, (float*)(void*)L.Gpart, gS, 1.0, gmu, L.v1, B, m, &ns, st());
+        else rc = umma_gram(ctx_err(), L.um, (float*)(void*)L.Gpart, B, m, &ns, st());
       }
       ++launches;
     }

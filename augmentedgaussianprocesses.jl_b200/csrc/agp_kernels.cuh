@@ -865,6 +865,50 @@ __global__ void combine_kernel(const TailParams p, const TG* __restrict__ Gpart)
   }
 }
 
+// The same update, four consecutive columns per thread (16-byte loads of the fp32 split-K partials, all slices in flight at once): the
+// tf32x3 path of a whole matrix with m = mp a multiple of 4 (the partials are mirrored there, so rows are read as stored).  One block
+// per row.  Opt-in (AGP_COMBINE4=1): measured slower than the scalar kernel at C2 (step 185.2 vs 181.3 us) - a quarter of the threads, so fewer loads in flight.
+__global__ void __launch_bounds__(128) combine4_kernel(const TailParams p, const float* __restrict__ Gpart) {
+  pdl_prologue();
+  const int i = blockIdx.y;
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (j >= p.m) return;
+  const double lr = *p.lr;
+  const float4* gp = reinterpret_cast<const float4*>(Gpart + (int64_t)i * p.gpart_ld + j);
+  const int64_t st4 = p.gpart_stride / 4;
+  double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
+  for (int s0 = 0; s0 < p.n_split; s0 += 16) {
+    float4 v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) v[u] = (s0 + u < p.n_split) ? gp[(int64_t)(s0 + u) * st4] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < 16; ++u) { g0 += (double)v[u].x; g1 += (double)v[u].y; g2 += (double)v[u].z; g3 += (double)v[u].w; }
+  }
+  const int64_t o = (int64_t)i * p.ld + j;
+  double2 ea = *reinterpret_cast<const double2*>(p.eta2 + o), eb = *reinterpret_cast<const double2*>(p.eta2 + o + 2);
+  if (p.eta2_off) {
+    const double2 fa = *reinterpret_cast<const double2*>(p.eta2_off + o), fb = *reinterpret_cast<const double2*>(p.eta2_off + o + 2);
+    g0 += fa.x; g1 += fa.y; g2 += fb.x; g3 += fb.y;
+  }
+  ea.x += lr * (-(g0 + (i == j ? 0.5 : 0.0)) - ea.x);
+  ea.y += lr * (-(g1 + (i == j + 1 ? 0.5 : 0.0)) - ea.y);
+  eb.x += lr * (-(g2 + (i == j + 2 ? 0.5 : 0.0)) - eb.x);
+  eb.y += lr * (-(g3 + (i == j + 3 ? 0.5 : 0.0)) - eb.y);
+  *reinterpret_cast<double2*>(p.eta2 + o) = ea; *reinterpret_cast<double2*>(p.eta2 + o + 2) = eb;
+  *reinterpret_cast<double2*>(p.P + o) = make_double2(-2.0 * ea.x, -2.0 * ea.y);
+  *reinterpret_cast<double2*>(p.P + o + 2) = make_double2(-2.0 * eb.x, -2.0 * eb.y);
+  if (i == 0) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const double e1 = p.eta1[j + u];
+      const double d1 = p.rho * p.v1[j + u] + p.mu0v[j + u] + (p.eta1_off ? p.eta1_off[j + u] : 0.0) - e1;
+      p.eta1[j + u] = e1 + lr * d1;
+      if (p.v1_zero) p.v1_zero[j + u] = 0.0;
+    }
+    if (j == 0) *p.logdet = 0.0;
+  }
+}
+
 // Unblocked Cholesky of one 64 x 64 diagonal block held in shared memory, fused with the inverse of
 // its factor (the rank-1 update that eliminates column j is applied to [A | W], W starting as I, so
 // W ends as L^-1).  In: lower triangle of Ablk.  Out: L in the lower triangle of Ablk, L^-1 (lower,

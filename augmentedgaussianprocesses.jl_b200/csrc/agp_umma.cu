@@ -33,8 +33,14 @@ namespace agp {
 namespace {
 
 constexpr int BM = 128, BN = 128, BK = 32;
-constexpr int RS = 4;                          // raw (TMA) ring depth: prefetch distance of 4 k-blocks
-constexpr int CS = 2;                          // converted-operand ring depth (one slot per converter group)
+#ifndef AGP_UMMA_RS
+#define AGP_UMMA_RS 4
+#endif
+#ifndef AGP_UMMA_CS
+#define AGP_UMMA_CS 2
+#endif
+constexpr int RS = AGP_UMMA_RS;                // raw (TMA) ring depth: prefetch distance of 4 k-blocks
+constexpr int CS = AGP_UMMA_CS;                // converted-operand ring depth
 constexpr int TILE_BYTES = BM * BK * 4;        // 16 KB : 128 rows x 128 B (one 128B-swizzle atom wide)
 constexpr int RAW_BYTES = 2 * TILE_BYTES;      // raw A, raw B
 constexpr int CONV_BYTES = 2 * TILE_BYTES;     // B_hi, B_lo   (A_hi / A_lo live in TMEM)
@@ -1538,6 +1544,234 @@ umma_gemm_nt_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   }
 }
 
+// Gram product straight from V (default for single-latent steps; AGP_GRAM_TN=0 goes back to scale_transpose_kernel + the kernel at the
+// top): split-K partials of U^T U, U = diag(sqrt(rho w)) V, with V read as stored ([B][ldm], samples = the K dimension along the ROWS).
+// The transposition and the scaling happen in the worker threads, where the operands are rewritten anyway for the hi / lo split:
+//   * TMA lands un-swizzled [32 samples][128 columns] boxes of V (one per operand; one box for a diagonal tile);
+//   * the TMA warp's 32 lanes put sf[k] = (float)sqrt(max(rho w_k, 0)) and gf[k] = (float)g_k of the k-block next to the stage;
+//   * worker thread r reads COLUMN r of the box (lanes = consecutive words: conflict-free), multiplies by sf[k], splits, and writes
+//     row r of the A operand to tensor memory and row r of the K-major 128B-swizzled B_hi / B_lo tiles (a quarter warp writes eight
+//     different 16-byte chunk positions: conflict-free);
+//   * on diagonal tiles the same thread accumulates (V^T g)_r (transpose(kappa) * grad_mu, analyticVI.jl:168, whitened): fp32 over the
+//     32 samples of a k-block, fp64 across k-blocks, one atomicAdd per unit.
+// This removes scale_transpose_kernel (9.3 us: 16.8 MB read + 16.8 MB written) from the critical chain of the step.  MMA warp,
+// accumulators, unit enumeration (tri_mode 2) and the mirror epilogue are those of umma_gemm_nt_kernel.
+namespace tn {
+constexpr int SC_BYTES = 256;                                    // sf[32] | gf[32]
+constexpr int SC_OFF = RS * RAW_BYTES + CS * CONV_BYTES;         // after the operand rings (which need 1024-byte alignment)
+constexpr int RING_BYTES = SC_OFF + RS * SC_BYTES;
+constexpr int SMEM_BYTES = RING_BYTES + 1024 + 256;
+}
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+umma_gram_tn_kernel(const __grid_constant__ CUtensorMap tmV, float* __restrict__ C, int64_t ldc, int64_t c_split_stride, const GemmWork work,
+                    const double* __restrict__ wvec, const double rho, const double* __restrict__ gvec, double* __restrict__ v1) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bars = smem_base + tn::RING_BYTES;
+  auto raw_full = [&](int s) { return bars + 8u * s; };
+  auto raw_empty = [&](int s) { return bars + 8u * (RS + s); };
+  auto conv_full = [&](int s) { return bars + 8u * (2 * RS + s); };
+  auto mma_done = [&](int s) { return bars + 8u * (2 * RS + CS + s); };
+  auto tmem_full = [&](int b) { return bars + 8u * (2 * RS + 2 * CS + b); };
+  auto tmem_empty = [&](int b) { return bars + 8u * (2 * RS + 2 * CS + 2 + b); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + tn::RING_BYTES + 8 * (2 * RS + 2 * CS + 6));
+  const uint32_t conv_base = smem_base + RS * RAW_BYTES;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = gridDim.x, cta = blockIdx.x;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmV);
+    for (int s = 0; s < RS; ++s) { mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), 2 * NUM_CONV_THREADS); }
+    for (int s = 0; s < CS; ++s) { mbar_init(conv_full(s), 2 * NUM_CONV_THREADS); mbar_init(mma_done(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tmem_full(b), 1); mbar_init(tmem_empty(b), 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_ptr_smem)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  if (warp == 0) {
+    // ===== producer warp: all lanes stage the sample scales of the k-block, lane 0 issues the TMA boxes =====
+    int g = 0;
+    for (int r = 0;; ++r) {
+      const int u = unit_index(r, cta, G);
+      if (u >= work.total) break;
+      const WorkUnit wu = get_unit(work, u);
+      const bool diag = wu.tile_m == wu.tile_n;
+      double wk = wu.nkb > 0 ? wvec[wu.kb0 * BK + lane] : 0.0, gk = wu.nkb > 0 ? gvec[wu.kb0 * BK + lane] : 0.0;
+      for (int i = 0; i < wu.nkb; ++i, ++g) {
+        const int s = g % RS;
+        const float sfv = (float)sqrt(fmax(rho * wk, 0.0)), gfv = (float)gk;
+        if (i + 1 < wu.nkb) { wk = wvec[(wu.kb0 + i + 1) * BK + lane]; gk = gvec[(wu.kb0 + i + 1) * BK + lane]; }   // next k-block, in flight during the wait
+        mbar_wait(raw_empty(s), ((g / RS) & 1) ^ 1);
+        if (lane == 0) UTT(0, 1000 + g);
+        float* sc = reinterpret_cast<float*>(smem_gen + tn::SC_OFF + s * tn::SC_BYTES);
+        sc[lane] = sfv; sc[32 + lane] = gfv;
+        __syncwarp();
+        if (lane == 0) {
+          const uint32_t dst = smem_base + s * RAW_BYTES;
+          mbar_expect_tx(raw_full(s), diag ? TILE_BYTES : 2 * TILE_BYTES);     // release: the scale words above are visible to the waiters
+          const int k = (wu.kb0 + i) * BK;
+          tma_load_2d(dst + 0 * TILE_BYTES, &tmV, raw_full(s), wu.tile_m * BM, k);
+          if (!diag) tma_load_2d(dst + 1 * TILE_BYTES, &tmV, raw_full(s), wu.tile_n * BN, k);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (as umma_gemm_nt_kernel) =====
+    int g = 0, lt = 0;
+    for (int r = 0;; ++r, ++lt) {
+      const int u = unit_index(r, cta, G);
+      if (u >= work.total) break;
+      const WorkUnit wu = get_unit(work, u);
+      const int ab = lt & 1;
+      mbar_wait(tmem_empty(ab), ((lt >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + ab * BN;
+      for (int i = 0; i < wu.nkb; ++i, ++g) {
+        const int s = g % CS;
+        mbar_wait(conv_full(s), (g / CS) & 1);
+        tc_fence_after();
+        if (lane == 0) UTT(1, 2000 + g);
+        if (elect_one()) {
+          const uint32_t b_hi = conv_base + s * CONV_BYTES, b_lo = b_hi + TILE_BYTES;
+          const uint32_t a_hi = tmem_base + TMEM_A0 + s * 64, a_lo = a_hi + 32;
+#pragma unroll
+          for (int kk = 0; kk < BK / 8; ++kk) {
+            const uint32_t off = kk * 32;
+            const uint64_t dbh = make_desc(b_hi + off), dbl = make_desc(b_lo + off);
+            tc_mma_tf32_ts(acc, a_lo + kk * 8, dbh, kIdesc, (i > 0 || kk > 0) ? 1u : 0u);
+            tc_mma_tf32_ts(acc, a_hi + kk * 8, dbl, kIdesc, 1u);
+            tc_mma_tf32_ts(acc, a_hi + kk * 8, dbh, kIdesc, 1u);
+          }
+          tc_commit(mma_done(s));
+          if (i == wu.nkb - 1) tc_commit(tmem_full(ab));
+        }
+        __syncwarp();
+        if (lane == 0) UTT(1, 3000 + g);
+      }
+    }
+  } else {
+    // ===== worker groups: group 0 builds the A operand (tensor memory) and V^T g, group 1 the B operand (shared memory) of EVERY
+    // k-block -- a Gram launch has one unit per CTA, so alternating the groups by unit would leave one of them idle, and one group
+    // alone converts at 2400 cycles per k-block against 1490 for the MMAs; then both drain half of the accumulator columns each =====
+    const int grp = (warp - 2) >> 2;
+    const int q = warp & 3;
+    const int arow = q * 32 + lane;                  // operand row = TMEM lane = column of the V box
+    int g = 0, lt = 0;
+    for (int r = 0;; ++r, ++lt) {
+      const int u = unit_index(r, cta, G);
+      if (u >= work.total) break;
+      const WorkUnit wu = get_unit(work, u);
+      const bool diag = wu.tile_m == wu.tile_n;
+      double vdot = 0.0;
+      for (int i = 0; i < wu.nkb; ++i, ++g) {
+        const int rs = g % RS, s = g % CS;
+        mbar_wait(raw_full(rs), (g / RS) & 1);
+        if ((threadIdx.x & 127) == 64) UTT(2 + grp, 4000 + g);
+        mbar_wait(mma_done(s), ((g / CS) & 1) ^ 1);
+        tc_fence_after();
+        if ((threadIdx.x & 127) == 64) UTT(2 + grp, 5000 + g);
+        const float4* sc4 = reinterpret_cast<const float4*>(smem_gen + tn::SC_OFF + rs * tn::SC_BYTES);
+        if (grp == 0) {
+          const float* rawA = reinterpret_cast<const float*>(smem_gen + rs * RAW_BYTES) + arow;
+          uint32_t h[32], l[32];
+          float dot32 = 0.f;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 sf = sc4[c];
+            const float a0 = rawA[(4 * c + 0) * BM], a1 = rawA[(4 * c + 1) * BM], a2 = rawA[(4 * c + 2) * BM], a3 = rawA[(4 * c + 3) * BM];
+            if (diag) {
+              const float4 gf = sc4[8 + c];
+              dot32 = fmaf(a0, gf.x, dot32); dot32 = fmaf(a1, gf.y, dot32); dot32 = fmaf(a2, gf.z, dot32); dot32 = fmaf(a3, gf.w, dot32);
+            }
+            float v, t;
+            v = a0 * sf.x; t = tf32_rna(v); h[4 * c + 0] = __float_as_uint(t); l[4 * c + 0] = __float_as_uint(tf32_rna(v - t));
+            v = a1 * sf.y; t = tf32_rna(v); h[4 * c + 1] = __float_as_uint(t); l[4 * c + 1] = __float_as_uint(tf32_rna(v - t));
+            v = a2 * sf.z; t = tf32_rna(v); h[4 * c + 2] = __float_as_uint(t); l[4 * c + 2] = __float_as_uint(tf32_rna(v - t));
+            v = a3 * sf.w; t = tf32_rna(v); h[4 * c + 3] = __float_as_uint(t); l[4 * c + 3] = __float_as_uint(tf32_rna(v - t));
+          }
+          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + TMEM_A0 + s * 64;
+          TMEM_ST32(ta, h);
+          TMEM_ST32(ta + 32, l);
+          if (diag) vdot += (double)dot32;
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          tc_fence_before();
+        } else {
+          const float* rawB = reinterpret_cast<const float*>(smem_gen + rs * RAW_BYTES + (diag ? 0 : TILE_BYTES)) + arow;
+          uint8_t* cbase_s = smem_gen + RS * RAW_BYTES + s * CONV_BYTES;
+          float4* bhi = reinterpret_cast<float4*>(cbase_s + arow * 128);
+          float4* blo = reinterpret_cast<float4*>(cbase_s + TILE_BYTES + arow * 128);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 sf = sc4[c];
+            float4 hv, lv;
+            float v;
+            v = rawB[(4 * c + 0) * BM] * sf.x; hv.x = tf32_rna(v); lv.x = tf32_rna(v - hv.x);
+            v = rawB[(4 * c + 1) * BM] * sf.y; hv.y = tf32_rna(v); lv.y = tf32_rna(v - hv.y);
+            v = rawB[(4 * c + 2) * BM] * sf.z; hv.z = tf32_rna(v); lv.z = tf32_rna(v - hv.z);
+            v = rawB[(4 * c + 3) * BM] * sf.w; hv.w = tf32_rna(v); lv.w = tf32_rna(v - hv.w);
+            bhi[c ^ (arow & 7)] = hv;     // row arow of the K-major tile, 16-byte chunk c at its 128B-swizzle position
+            blo[c ^ (arow & 7)] = lv;
+          }
+          fence_proxy_async();            // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        }
+        mbar_arrive(raw_empty(rs));
+        mbar_arrive(conv_full(s));
+        if ((threadIdx.x & 127) == 64) UTT(2 + grp, 6000 + g);
+      }
+      if (grp == 0 && diag && wu.nkb > 0) atomicAdd(v1 + wu.tile_m * BM + arow, vdot);
+      // ----- epilogue: C tile and, off the diagonal, its transpose (UMMA_EPI_STORE_MIRROR of umma_gemm_nt_kernel); group g drains the
+      // column chunks 2g and 2g + 1 -----
+      const int ab = lt & 1;
+      const int row = wu.tile_m * BM + q * 32 + lane;
+      float* cbase = C + (int64_t)wu.split * c_split_stride;
+      float* crow = cbase + (int64_t)row * ldc + (int64_t)wu.tile_n * BN;
+      if (wu.nkb > 0) {
+        mbar_wait(tmem_full(ab), (lt >> 1) & 1);
+        tc_fence_after();
+        if ((threadIdx.x & 127) == 64) UTT(2 + grp, 300000 + lt);
+#pragma unroll 1
+        for (int c = 2 * grp; c < 2 * grp + 2; ++c) {
+          uint32_t rr[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + c * 32);
+          TMEM_LD32(taddr, rr);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (c == 2 * grp + 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty(ab));
+          }
+          float4* dst = reinterpret_cast<float4*>(crow + c * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            dst[j] = make_float4(__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1]), __uint_as_float(rr[4 * j + 2]), __uint_as_float(rr[4 * j + 3]));
+          if (!diag) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              cbase[(int64_t)(wu.tile_n * BN + c * 32 + j) * ldc + row] = __uint_as_float(rr[j]);
+          }
+        }
+        if ((threadIdx.x & 127) == 64) UTT(2 + grp, 400000 + lt);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 // hi = rna_tf32(src), lo = rna_tf32(src - hi) for an m x m operand that every CTA of the v2 GEMM would otherwise split again
 __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ src, float* __restrict__ hi, float* __restrict__ lo,
                                                          int64_t n4) {
@@ -1626,7 +1860,22 @@ bool make_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols,
   return r == CUDA_SUCCESS;
 }
 
+// MN-major view of the same kind of matrix for umma_gram_tn_kernel: (128 columns x 32 rows) boxes, no swizzle (the worker threads read
+// the box column by column and write the swizzled K-major operands themselves)
+bool make_map_tn(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, uint64_t ld) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)BM, (cuuint32_t)BK};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 struct Maps {
+  CUtensorMap vtn;           // V as the operand of umma_gram_tn_kernel
   CUtensorMap raw[UM_COUNT], ut;
   CUtensorMap split[2][2];   // v2: [0] = L^-1, [1] = X ; [.][0] = hi, [.][1] = lo
 };
@@ -1652,10 +1901,16 @@ int umma_latent_alloc(std::string* err, UmmaLatent& u, int m, int ldm, int Bcap,
   bool ok = true;
   for (int i = 0; i < UM_COUNT; ++i) ok = ok && make_map(&mp->raw[i], ptr[i], rows[i], m, ldm);
   ok = ok && make_map(&mp->ut, u.UT, m, Bcap, Bcap);
+  ok = ok && make_map_tn(&mp->vtn, V, Bcap, m, ldm);
   u.tmaps = mp;
   if (!ok) return fail(err, "cuTensorMapEncodeTiled failed");
   if ((e = cudaFuncSetAttribute(umma_gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)) != cudaSuccess)
     return fail(err, "cudaFuncSetAttribute", e);
+  if ((e = cudaFuncSetAttribute(umma_gram_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tn::SMEM_BYTES)) != cudaSuccess)
+    return fail(err, "cudaFuncSetAttribute (gram tn)", e);
+  u.gram_tn = 1;
+  if (const char* env = getenv("AGP_GRAM_TN")) u.gram_tn = atoi(env) != 0;
+  if (getenv("AGP_UMMA_V2") || getenv("AGP_UMMA_V3")) u.gram_tn = 0;     // the experimental main loops keep their own Gram path
   if (const char* env = getenv("AGP_UMMA_V2")) u.v2 = atoi(env);
   u.ps = 1;
   if (const char* env = getenv("AGP_UMMA_PS")) u.ps = atoi(env) != 0;
@@ -1832,6 +2087,31 @@ int umma_gram(std::string* err, UmmaLatent& u, float* Gpart, int B, int m, int* 
   *n_split = S;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(err, "umma gram", e);
+  return 0;
+}
+
+// The Gram product straight from V (umma_gram_tn_kernel): Gpart[s] = split-K partials of V^T diag(rho w) V, and v1 += V^T g
+int umma_gram_tn(std::string* err, UmmaLatent& u, float* Gpart, const double* w, double rho, const double* g, double* v1, int B, int m,
+                 int* n_split, cudaStream_t st) {
+  Maps* mp = (Maps*)u.tmaps;
+  if (!mp || !u.gram_tn) return fail(err, "umma_gram_tn: not available for this latent");
+  if (B % BM || m % BN) return fail(err, "shape not a multiple of the tile");
+  const int total_kb = B / BK;
+  const int nt = m / BN, upper_tiles = nt * (nt + 1) / 2;
+  int S = 148 / upper_tiles;     // one wave (see umma_gram)
+  S = S < 1 ? 1 : S;
+  if (S > *n_split) S = *n_split;
+  if (S > total_kb) S = total_kb;
+  int per = (total_kb + S - 1) / S;
+  S = (total_kb + per - 1) / per;
+  GemmWork wk{};
+  wk.ntm = nt; wk.ntn = nt; wk.nsplit = S; wk.total = upper_tiles * S;
+  wk.total_kb = total_kb; wk.kb_per_split = per; wk.tri_mode = 2;
+  const int grid = wk.total < sm_count() ? wk.total : sm_count();
+  launch_chain(umma_gram_tn_kernel, dim3(grid), dim3(NUM_THREADS), tn::SMEM_BYTES, st, mp->vtn, Gpart, (int64_t)u.ldm, (int64_t)m * u.ldm, wk, w, rho, g, v1);
+  *n_split = S;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(err, "umma gram tn", e);
   return 0;
 }
 

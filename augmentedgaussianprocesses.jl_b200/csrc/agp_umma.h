@@ -39,6 +39,8 @@ struct UmmaLatent {
   // pre-split right operand with the first-generation main loop (umma_gemm_ps_kernel; default ON, AGP_UMMA_PS=0 disables): Bsplit holds
   // the planes, the worker groups only split the A operand
   int ps = 0;
+  // Gram product straight from V (umma_gram_tn_kernel; default ON, AGP_GRAM_TN=0 disables): no scale-transpose pass, U^T is not used
+  int gram_tn = 0;
 };
 
 bool umma_shape_ok(int m, int Bcap);
@@ -65,6 +67,9 @@ void umma_set_grid_cap(int n);
 // V X^T statistics are issued N tile by N tile as the rows of X leave the m x m tail
 void umma_set_tile_range(int lo, int hi);
 int umma_gram(std::string* err, UmmaLatent& u, float* Gpart, int B, int m, int* n_split, cudaStream_t st);
+// the same partials straight from V = u's UM_V matrix, scaled by sqrt(rho w) along the samples inside the kernel; v1 += V^T g
+int umma_gram_tn(std::string* err, UmmaLatent& u, float* Gpart, const double* w, double rho, const double* g, double* v1, int B, int m,
+                 int* n_split, cudaStream_t st);
 // the Gram product in two launches: part 0 = tile (0, 0) over S slices, part 1 = the other upper tiles over S slices (<= grid_max CTAs)
 int umma_gram_part(std::string* err, UmmaLatent& u, float* Gpart, int B, int m, int part, int S, int grid_max, cudaStream_t st);
 int umma_gram_splits(int B, int cap);   // largest usable split count <= cap

@@ -62,5 +62,37 @@ int main(int argc, char** argv) {
     gerr = std::max(gerr, fabs(s - gsum)); gref = std::max(gref, fabs(s));
   }
   printf("gram (%d splits): max abs err %.3e (max |ref| %.1f)\n", ns, gerr, gref);
+  // ---- Gram product straight from V (umma_gram_tn_kernel): random weights / gradient vector, against fp64 ----
+  if (u.gram_tn) {
+    std::uniform_real_distribution<double> ud(0.0, 0.5);
+    const double rho = 3.7;
+    for (int b = 0; b < B; ++b) { w[b] = ud(rng); gz[b] = ud(rng) - 0.25; }
+    w[5] = 0.0; w[B - 1] = -1e-3;   // clamped at zero
+    cudaMemcpy(dw, w.data(), B * 8, cudaMemcpyHostToDevice); cudaMemcpy(dg, gz.data(), B * 8, cudaMemcpyHostToDevice);
+    cudaMemset(dv1, 0, m * 8);
+    int ns2 = 32;
+    umma_gram_tn(&err, u, dG, dw, rho, dg, dv1, B, m, &ns2, 0);
+    cudaDeviceSynchronize();
+    printf("gram_tn launch: %s %s\n", cudaGetErrorString(cudaGetLastError()), err.c_str());
+    std::vector<float> Gq((size_t)ns2 * m * m); cudaMemcpy(Gq.data(), dG, Gq.size() * 4, cudaMemcpyDeviceToHost);
+    std::vector<double> v1(m); cudaMemcpy(v1.data(), dv1, m * 8, cudaMemcpyDeviceToHost);
+    double e2 = 0, r2 = 0, asym = 0;
+    for (int t = 0; t < 400; ++t) {
+      int i = rng() % m, j = rng() % m; double s = 0, gsum = 0, gsumT = 0;
+      if (t < 8) { i = (t * 64 + 3) % m; j = i; }
+      for (int b = 0; b < B; ++b) s += (double)V[(size_t)b * m + i] * V[(size_t)b * m + j] * std::max(rho * w[b], 0.0);
+      for (int sp = 0; sp < ns2; ++sp) { gsum += Gq[(size_t)sp * m * m + (size_t)i * m + j]; gsumT += Gq[(size_t)sp * m * m + (size_t)j * m + i]; }
+      e2 = std::max(e2, fabs(s - gsum)); r2 = std::max(r2, fabs(s)); asym = std::max(asym, fabs(gsum - gsumT));
+    }
+    double ev = 0, rv = 0;
+    for (int j = 0; j < m; ++j) {
+      double s = 0;
+      for (int b = 0; b < B; ++b) s += (double)V[(size_t)b * m + j] * gz[b];
+      ev = std::max(ev, fabs(s - v1[j])); rv = std::max(rv, fabs(s));
+    }
+    printf("gram_tn (%d splits): max abs err %.3e (max |ref| %.1f), asymmetry %.3e; V^T g: max abs err %.3e (max |ref| %.2f)\n", ns2, e2, r2, asym, ev, rv);
+    timeit("gram_tn", [&] { ns2 = 32; umma_gram_tn(&err, u, dG, dw, rho, dg, dv1, B, m, &ns2, 0); }, 2.0 * B * m * m);
+    timeit("scale_T", [&] { umma_scale_transpose(&err, u, dV, dw, rho, dg, dv1, B, m, 0); }, 0.0);
+  }
   return 0;
 }

@@ -73,6 +73,14 @@ int main(int argc, char** argv) {
   ns = 32; umma_gram(&err, u, dG, B, m, &ns, 0);
   cudaDeviceSynchronize();
   dump("Gram U^T U (split-K, mirror)", 148);
+  if (u.gram_tn) {
+    ns = 32; umma_gram_tn(&err, u, dG, dw, 1.0, dg, dv1, B, m, &ns, 0);
+    cudaDeviceSynchronize();
+    cudaMemcpyToSymbol(agp_ut_n, z.data(), z.size() * 4);
+    ns = 32; umma_gram_tn(&err, u, dG, dw, 1.0, dg, dv1, B, m, &ns, 0);
+    cudaDeviceSynchronize();
+    dump("Gram straight from V (umma_gram_tn_kernel)", 148);
+  }
   printf("last error: %s\n", cudaGetErrorString(cudaGetLastError()));
   return 0;
 }
