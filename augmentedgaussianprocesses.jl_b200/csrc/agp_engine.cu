@@ -212,6 +212,9 @@ struct Engine : EngineBase {
   bool fuse_lik_next = false, fuse_from_batch = false, lik_fused = false;   // rowfinish + local-update fusion (set by the step paths)
   bool stats_use_early = false;    // moments stage 2 of this step only adds the last N tile (set by step_pool)
   bool racc2_precleared = false;   // the V X^T row-statistic accumulators were cleared off the critical chain (side stream)
+  bool rowfin_on = false, rowfin_now = false;  // AGP_ROWFIN=1: row finish + local update inside the statistics product's epilogue (UmmaRowFinish) instead of
+                                               // rowfinish_lik_kernel: device-resident C2 +0.8 % (5.44 k vs 5.39 k it/s) but end to end -2.5 % -> opt-in
+  unsigned* d_rowcnt = nullptr;               // per-sample arrival counters of the fused row finish (self-resetting)
   bool combine4_on = false;  // AGP_COMBINE4=1: four columns per thread in the natural-parameter update (measured SLOWER: 5.40 k vs 5.51 k it/s at C2 - fewer loads in flight)
   int chain_variant = 0; // AGP_CHAIN: pivot-chain implementation of the multi-launch tail (agp_tail2.cuh chain16_*): 0 = scalar (default), 1 = look-ahead (opt-in: 132 vs 126.7 us at C2)
   int tail_variant = 3;  // AGP_TAIL_VARIANT: 0 = agp_tail.cuh (generation 1, SIMT tile products), 2 = agp_tail2.cuh (DMMA, panel potf2, one
@@ -461,6 +464,8 @@ struct Engine : EngineBase {
     tail_variant = Ql >= 2 ? 3 : 2;
     { const char* e = getenv("AGP_CHAIN"); if (e) chain_variant = atoi(e) ? 1 : 0; }
     { const char* e = getenv("AGP_COMBINE4"); if (e) combine4_on = e[0] != '0'; }
+    { const char* e = getenv("AGP_ROWFIN"); if (e) rowfin_on = e[0] != '0'; }
+    if (prec == AGP_PREC_TF32X3) CKS(dalloc(&d_rowcnt, (size_t)ldB + 128));
     { const char* e = getenv("AGP_TAIL_VARIANT"); if (e) { tail_variant = atoi(e); if (tail_variant != 0 && tail_variant != 2) tail_variant = 3; } }
     { const char* e = getenv("AGP_TAIL3_SMS"); if (e && atoi(e) >= 2) t3_sm_budget = std::min(148, atoi(e)); }
     {   // per-latent descriptors + dependency words of the persistent tail (zero-initialised: epoch 0)
@@ -537,7 +542,7 @@ struct Engine : EngineBase {
     if (ev_join) cudaEventDestroy(ev_join);
     void* ps[] = {idx_prev, xx_cur, pKS, pXb, pxxb, X, xx, y_all, ycls_all, Xb, xxb, stage, idx_pool, idx_cur, counters, status, d_lik_kind, d_p0, d_p1, d_A,
                   xchg, d_xepoch, d_peers, gmu, gS, lc, ltheta, lgamma_, lalpha, tmu, tvar, gm, gs, yb, ycls, d_out, d_lam, d_lamacc, d_qnodes, d_qw, d_lr, d_gradA, d_Amt, d_Avt, d_Abt, d_noise_opt, d_noise_state,
-                  hgH[0], hgH[1], hgH[2], hgH[3], hgX, hgA, hgB, hgM1, hgM2, hgV, hgP, d_t3lat, d_t3flags};
+                  hgH[0], hgH[1], hgH[2], hgH[3], hgX, hgA, hgB, hgM1, hgM2, hgV, hgP, d_t3lat, d_t3flags, d_rowcnt};
     for (void* p : ps) cudaFree(p);
   }
 
@@ -974,6 +979,14 @@ struct Engine : EngineBase {
           racc2_precleared = false;
           UmmaEpilogue ep{};
           ep.mode = UMMA_EPI_STATS_ONLY; ep.acc0 = L.racc + ldB; ep.acc1 = L.racc + 2 * ldB; ep.tvec = L.tvec;
+          // single-latent SVGP step on the pre-split kernel: the row finish + local update of a sample runs in the epilogue thread that
+          // adds its last N-tile contribution (UmmaRowFinish), no rowfinish_lik_kernel launch
+          UmmaRowFinish fin{};
+          if (fuse_lik_next && rowfin_on && L.um.ps && L.factor_valid && !stats_use_early && d_rowcnt) {
+            fin.cnt = d_rowcnt; fin.B = B; fin.sumsq_v = L.racc; fin.kdiag_jit = L.variance + jitter; fin.Ktilde = L.Ktilde; fin.status = status;
+            fin.lp = lik_params(B, fuse_from_batch, 1);
+            ep.fin = &fin;
+          }
           if (!L.factor_valid) {
             // the previous tail was a Newton-Schulz refinement: no factor, statistics against the full Sigma_v = ns.Y():
             // var_f - Ktilde = rowsum((V Sigma_v) o V),  mean_f = (V Sigma_v) eta1_v
@@ -985,6 +998,7 @@ struct Engine : EngineBase {
             int sg = umma_gemm_nt(ctx_err(), L.um, UM_V, UM_X, (float*)(void*)L.VS, B, m, ep, st());
             umma_set_tile_range(-1, -1);
             CKS(sg);
+            rowfin_now = ep.fin != nullptr;
           }
         } else {
           GemmParams<T> s{};  // V X^T with Sigma_v = X^T X  (kappa * Sigma of latentgp.jl:189); X is lower triangular
@@ -996,7 +1010,10 @@ struct Engine : EngineBase {
         ph_end();
       }
       ph_begin(PH_ROWSTATS);
-      if (prec == AGP_PREC_TF32X3 && fuse_lik_next) {
+      if (prec == AGP_PREC_TF32X3 && fuse_lik_next && rowfin_now) {
+        lik_fused = true;      // done inside the statistics product
+        rowfin_now = false;
+      } else if (prec == AGP_PREC_TF32X3 && fuse_lik_next) {
         // single-latent SVGP step: local updates fused into the row-statistics kernel (step_update_a skips its lik launch)
         launch_chain(rowfinish_lik_kernel, dim3((B + 255) / 256), dim3(256), 0, (const double*)L.racc, (const double*)(L.racc + ldB),
                      (const double*)(L.racc + 2 * ldB), B, L.variance + jitter, L.Ktilde, status, lik_params(B, fuse_from_batch, 1));

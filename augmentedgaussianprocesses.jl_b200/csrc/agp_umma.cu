@@ -344,7 +344,7 @@ constexpr int SMEM_BYTES = RING_BYTES + 1024 + 256;
 }
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 umma_gemm_ps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo, float* __restrict__ C,
-                    int64_t ldc, int64_t c_split_stride, const GemmWork work, const UmmaEpilogue ep) {
+                    int64_t ldc, int64_t c_split_stride, const GemmWork work, const UmmaEpilogue ep, const UmmaRowFinish fin) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -532,6 +532,25 @@ umma_gemm_ps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const double acc_sq = (acc_sq4[0] + acc_sq4[1]) + (acc_sq4[2] + acc_sq4[3]), acc_dot = (acc_dot4[0] + acc_dot4[1]) + (acc_dot4[2] + acc_dot4[3]);
         if (ep.mode == UMMA_EPI_STORE_SUMSQ) atomicAdd(ep.acc0 + row, acc_sq);
         if (ep.mode == UMMA_EPI_STATS_ONLY) { atomicAdd(ep.acc0 + row, acc_sq); atomicAdd(ep.acc1 + row, acc_dot); }
+        if (ep.mode == UMMA_EPI_STATS_ONLY && fin.cnt) {
+          // fused row finish: the last of this row's N-tile units (all have nkb > 0 with a triangular right operand) completes the sample
+          __threadfence();
+          const unsigned prev = atomicAdd(fin.cnt + row, 1u);
+          if (prev == (unsigned)work.ntn - 1u) {
+            __threadfence();
+            fin.cnt[row] = 0u;
+            if (row < fin.B) {
+              const double ssq = __ldcg(ep.acc0 + row), dvs = __ldcg(ep.acc1 + row);
+              const double kt = fin.kdiag_jit - fin.sumsq_v[row];
+              fin.Ktilde[row] = kt;
+              if (!(kt > 0.0)) atomicOr(fin.status, ST_KTILDE);  // latentgp.jl:213
+              const_cast<double*>(fin.lp.mean_f)[row] = dvs;
+              const_cast<double*>(fin.lp.var_f)[row] = ssq + kt;
+              double r0 = 0.0, r1 = 0.0;
+              lik_update_sample(fin.lp, row, r0, r1);
+            }
+          }
+        }
         if (ct == 0) UTT(2 + grp, 400000 + lt);
       }
     }
@@ -2021,6 +2040,7 @@ int umma_gemm_nt(std::string* err, UmmaLatent& u, int a_which, int b_which, floa
     w.total = (g_tn_hi - g_tn_lo + 1) * w.ntm;
   }
   const int grid = w.total < grid_cap() ? w.total : grid_cap();
+  if (ep.fin && !(u.ps && b_which == UM_X)) return fail(err, "fused row finish needs the pre-split kernel (V X^T product)");
   if (u.v2) {
     // v2 & 2: keep the in-kernel split of the right operand (A/B experiment); otherwise L^-1 / X arrive pre-split
     const int sp = (b_which == UM_LINV) ? 0 : (b_which == UM_X) ? 1 : -1;
@@ -2034,8 +2054,15 @@ int umma_gemm_nt(std::string* err, UmmaLatent& u, int a_which, int b_which, floa
   }
   if (u.ps && (b_which == UM_LINV || b_which == UM_X)) {
     const int sp = b_which == UM_LINV ? 0 : 1;
+    UmmaRowFinish fin{};
+    UmmaEpilogue epk = ep;
+    if (ep.fin) {
+      if (ep.mode != UMMA_EPI_STATS_ONLY || g_tn_lo >= 0 || w.tri_mode != 1) return fail(err, "fused row finish: statistics product over all N tiles only");
+      fin = *ep.fin;
+    }
+    epk.fin = nullptr;
     launch_chain(umma_gemm_ps_kernel, dim3(grid), dim3(NUM_THREADS), ps::SMEM_BYTES, st, mp->raw[a_which], mp->split[sp][0], mp->split[sp][1], C,
-                 (int64_t)u.ldm, (int64_t)0, w, ep);
+                 (int64_t)u.ldm, (int64_t)0, w, epk, fin);
     cudaError_t e3 = cudaGetLastError();
     if (e3 != cudaSuccess) return fail(err, "umma_gemm_ps_kernel", e3);
     return 0;

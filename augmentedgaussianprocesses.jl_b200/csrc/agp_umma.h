@@ -6,6 +6,8 @@
 
 #include <string>
 
+#include "agp_lik.cuh"
+
 namespace agp {
 
 enum UmmaMat : int { UM_KNM = 0, UM_V = 1, UM_LINV = 2, UM_X = 3, UM_COUNT = 4 };
@@ -22,10 +24,22 @@ enum UmmaEpiMode : int {
   UMMA_EPI_STATS_SIGMA = 6   // no store ; acc0[row] += sum acc*cin[row][col] ; acc1[row] += sum acc*tvec[col]
                              //   (V Sigma_v -> var_f = rowsum((V Sigma_v) o V), mean_f = (V Sigma_v) eta1_v: statistics against the full covariance)
 };
+// Row finish fused into the UMMA_EPI_STATS_ONLY epilogue of umma_gemm_ps_kernel (single-latent SVGP steps): the thread that adds the LAST
+// N-tile contribution of a sample (per-row arrival counter) forms Ktilde, mean_f and var_f and runs the sample's local update right there
+// -- what rowfinish_lik_kernel does in a launch of its own (5.7 us on the critical chain of the C2 step).  cnt: [rows] zero-initialised,
+// reset by the finishing thread.
+struct UmmaRowFinish {
+  unsigned* cnt = nullptr;
+  int B = 0;                         // samples (rows >= B are padding)
+  const double* sumsq_v = nullptr;   // row sums of squares of V (K_nm L^-T product)
+  double kdiag_jit = 0.0; double* Ktilde = nullptr; int* status = nullptr;
+  LikParams lp;
+};
 struct UmmaEpilogue {
   int mode = 0;
   double* acc0 = nullptr; double* acc1 = nullptr; const double* tvec = nullptr;
   const float* cin = nullptr;
+  const UmmaRowFinish* fin = nullptr;   // host pointer, copied into the launch (pre-split kernel + UMMA_EPI_STATS_ONLY only)
 };
 
 struct UmmaLatent {
