@@ -464,6 +464,9 @@ class AbstractGPModel:
 
     # ---- lazily (re)create the engine with enough batch capacity, carrying the posterior over
     def _engine(self, capacity: int) -> _Engine:
+        # capacity 0: whatever engine exists (prediction: the rows are chunked by the engine, no batch shape to honour)
+        if self._eng is not None and capacity == 0:
+            return self._eng
         if self._eng is not None and capacity <= self._eng.capacity and not (
                 self.precision_requested == "auto" and self.precision == "tf32x3" and capacity % 128):
             return self._eng
@@ -1220,7 +1223,7 @@ def _pred_nodes():
 
 def _predict_f(model, X_test, cov: bool):
     """(Q_local, N*) latent moments of the owned latents, then multi-output mixing on the host."""
-    eng = model._engine(max(model.inference.batchsize, 1) if model._eng is None else 1)
+    eng = model._engine(max(model.inference.batchsize, 1) if model._eng is None else 0)
     Xk, xp, dt, layout, nt, D = _x_args(X_test)
     if D != model.D:
         raise ValueError("input dimension of X_test does not match the inducing points")
@@ -1251,7 +1254,7 @@ def predict_f(model, X_test, state=None, *, cov: bool = False, diag: bool = True
             raise NotImplementedError("full predictive covariance of a latent-sharded model")
         Xd = np.ascontiguousarray(X_test if X_test.ndim == 2 else X_test[:, None], dtype=np.float64)
         nt = Xd.shape[0]
-        eng = model._engine(max(model.inference.batchsize, 1) if model._eng is None else 1)
+        eng = model._engine(max(model.inference.batchsize, 1) if model._eng is None else 0)
         ql = model.n_latent_local
         mu, S = np.empty((ql, nt)), np.empty((ql, nt, nt))
         eng.ck(eng.lib.agp_predict_f_cov(eng.model, L.dptr(Xd), nt, L.dptr(mu), L.dptr(S)))

@@ -765,3 +765,31 @@ def test_predict_f_full_covariance(agp, prec):
     assert np.allclose(S_e, S_e.T, rtol=0, atol=1e-10 * np.abs(S_e).max())
     _, var_e = agp.predict_f(me, Xt, cov=True)                  # the diagonal agrees with the diag = true path
     assert rel_fro(np.diag(S_e), var_e) < (1e-8 if prec == "f64" else 5e-4)
+
+
+@pytest.mark.parametrize("lik,problem", [("gaussian", "Regression"), ("studentt", "Regression"), ("logistic", "Classification"),
+                                         ("logisticsoftmax", "MultiClass"), ("laplace", "Regression"), ("heteroscedastic", "Regression"),
+                                         ("bayesiansvm", "Classification"), ("poisson", "Event"), ("negbinomial", "Event")])
+@pytest.mark.parametrize("shape", [(100, 10, 10), (512, 128, 128)])
+def test_testconv_thresholds_engine(agp, lik, problem, shape):
+    """The reference's own behavioural test (test/testingtools.jl:223-253, driven by test_inference_SVGP :272-302: 10 inducing
+    points, AnalyticVI and AnalyticSVI(10)) through the engine with the default precision ("auto": fp32 SIMT for the reference's
+    test shapes, tcgen05 3xTF32 when m and the minibatch are multiples of 128), beside the same thresholds on the oracle
+    (tests/test_oracle.py::test_testconv_thresholds)."""
+    n, m, B = shape
+    X, y, Z, mbs, F, rng = make_data(lik, n, 2, m, B, 6, seed=3)
+    for inf in (agp.AnalyticVI(), agp.AnalyticSVI(B)):
+        model = agp.SVGP(engine_kernel(agp, "sqexp", 1.0, 1.0), engine_lik(agp, lik), inf, Z)
+        model, st = agp.train(model, X, y, 6, minibatches=mbs)
+        yp = agp.predict_y(model, X)
+        if problem == "Regression":
+            assert np.mean(np.abs(np.asarray(yp) - F[:, 0])) < 15
+            assert np.all(np.asarray(agp.proba_y(model, X)[1]) > 0)
+        elif problem == "Classification":
+            assert np.mean(np.asarray(yp) != (y > 0)) < 0.5
+            assert np.all(np.asarray(agp.proba_y(model, X)[1]) >= 0)
+        elif problem == "Event":
+            assert np.mean(np.abs(np.asarray(yp) - y)) < 20.0
+        else:
+            assert np.mean(np.asarray(yp) != y) < 0.9
+        assert np.isfinite(agp.ELBO(model, st))
