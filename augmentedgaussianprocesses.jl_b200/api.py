@@ -467,8 +467,7 @@ class AbstractGPModel:
         # capacity 0: whatever engine exists (prediction: the rows are chunked by the engine, no batch shape to honour)
         if self._eng is not None and capacity == 0:
             return self._eng
-        if self._eng is not None and capacity <= self._eng.capacity and not (
-                self.precision_requested == "auto" and self.precision == "tf32x3" and capacity % 128):
+        if self._eng is not None and capacity <= self._eng.capacity:
             return self._eng
         old = self._eng
         saved = None
@@ -478,8 +477,9 @@ class AbstractGPModel:
             old.close()
         cap = int(capacity)
         if self.precision_requested == "auto":
-            # the tcgen05 kernels tile m and B by 128; other shapes (e.g. the reference's 10-inducing-point tests) take the fp32 SIMT path
-            self.precision = "tf32x3" if (self.m % 128 == 0 and cap % 128 == 0) else "f32"
+            # the tcgen05 kernels tile m by 128 (a ragged minibatch is padded inside the engine: Engine::rowsK); other numbers of inducing
+            # points (e.g. the reference's 10-inducing-point tests) take the fp32 SIMT path
+            self.precision = "tf32x3" if self.m % 128 == 0 else "f32"
         if self.precision == "tf32x3":
             cap = (cap + 127) // 128 * 128
         self._eng = _Engine(self._desc(cap), self.device, self.stream)
@@ -546,7 +546,7 @@ class AbstractGPModel:
 class SVGP(AbstractGPModel):
     """models/SVGP.jl:22-80.  `SVGP(kernel, likelihood, inference, Z; optimiser=false, Zoptimiser=false)`.
 
-    precision: "auto" (default: "tf32x3" when m and the batch size are multiples of 128, else "f32"), "f64" (fp64 SIMT, exact
+    precision: "auto" (default: "tf32x3" when m is a multiple of 128, else "f32"), "f64" (fp64 SIMT, exact
     mode), "f32" (fp32 SIMT) or "tf32x3" (tcgen05 tensor cores).
     shard=(rank, world): own n_latent/world latents (LogisticSoftMax classes) on this process.
     """

@@ -697,6 +697,9 @@ struct Engine : EngineBase {
     ++launches;
   }
   dim3 grid_mp() const { return dim3((mp + 127) / 128, mp); }
+  // rows of the B x m tensor-core products: the tcgen05 kernels tile the samples by 128, so a ragged minibatch (host index list path)
+  // runs with its row count rounded up -- the extra rows repeat sample 0 (prep_idx) and carry zero weights (natgrad_products)
+  int rowsK(int B) const { return prec == AGP_PREC_TF32X3 ? (int)rup(B, 128) : B; }
 
   // whitened -> canonical natural parameters: eta1 = L^-T eta1_v, eta2 = L^-T eta2_v L^-1   (X = L^-1)
   void canonicalize(Latent& L) {
@@ -801,7 +804,9 @@ struct Engine : EngineBase {
       CKS(ensure_stage((size_t)B * 8));
       CK(cudaMemcpyAsync(stage, idx, (size_t)B * 8, cudaMemcpyHostToDevice, st()));
       idx_rebase_kernel<<<(B + 255) / 256, 256, 0, st()>>>((const int64_t*)stage, idx_cur, B, base);
-      xx_gather_kernel<T><<<(B + 255) / 256, 256, 0, st()>>>(idx_cur, B, xx, xx_cur);
+      const int Bk = rowsK(B);
+      if (Bk != B) { idx_pad_kernel<<<1, 128, 0, st()>>>(idx_cur, B, Bk); ++launches; }
+      xx_gather_kernel<T><<<(Bk + 255) / 256, 256, 0, st()>>>(idx_cur, Bk, xx, xx_cur);
       ++launches;
     } else {
       if (!idx_pool || pool_B != B) { ph_end(); ctx->err = "no resident minibatch lists for this batch size"; return AGP_ERR_STATE; }
@@ -872,6 +877,7 @@ struct Engine : EngineBase {
   }
   int moments_rows_grouped(const T* Xsrc, const T* xsrc, const int64_t* gather, int B, bool fresh_kernel_matrices, double* mean_out,
                            double* var_out, int64_t out_ld, int stages) {
+    const int Bk = rowsK(B);
     if (stages & 1) {
       ph_begin(PH_KMAT);
       fan_begin();
@@ -880,11 +886,11 @@ struct Engine : EngineBase {
         fan_select(q);
         if (L.knm_tc) {
           CKS(umma_knm(ctx_err(), L.uk, (const float*)(const void*)Xsrc, Dp, Dp, gather, (const float*)(const void*)(gather ? xx_cur : xsrc),
-                       (const float*)(const void*)L.zz, B, L.kind, L.scale * L.scale, L.variance, st()));
+                       (const float*)(const void*)L.zz, Bk, L.kind, L.scale * L.scale, L.variance, st()));
         } else {
           GemmParams<T> g{};
           g.A = Xsrc; g.lda = Dp; g.a_gather = gather; g.B = L.Z; g.ldb = Dp; g.C = L.Knm; g.ldc = ldm;
-          g.M = B; g.N = m; g.K = D; g.alpha = 1.0;
+          g.M = Bk; g.N = m; g.K = D; g.alpha = 1.0;
           g.xx = gather ? xx_cur : xsrc; g.xx_direct = 1; g.zz = L.zz; g.scale2 = L.scale * L.scale; g.variance = L.variance; g.kernel_kind = L.kind;
           gemm_simt_launch<T, false, false, EPI_KERNELFN>(g, 1, st());
         }
@@ -894,7 +900,7 @@ struct Engine : EngineBase {
       fan_end();
       ph_end();
       ph_begin(PH_KAPPA);
-      CKS(umma_gemm_nt_grouped(ctx_err(), grpV, lat[0].um, 1, B, m, UMMA_EPI_STORE_SUMSQ, st()));
+      CKS(umma_gemm_nt_grouped(ctx_err(), grpV, lat[0].um, 1, Bk, m, UMMA_EPI_STORE_SUMSQ, st()));
       ++launches;
       ph_end();
     }
@@ -902,7 +908,7 @@ struct Engine : EngineBase {
     ph_begin(PH_KSIGMA);
     for (int q = 0; q < Ql; ++q) CK(cudaMemsetAsync(lat[q].racc + ldB, 0, 2 * ldB * sizeof(double), st()));
     racc2_precleared = false;
-    CKS(umma_gemm_nt_grouped(ctx_err(), grpS, lat[0].um, 1, B, m, UMMA_EPI_STATS_ONLY, st()));
+    CKS(umma_gemm_nt_grouped(ctx_err(), grpS, lat[0].um, 1, Bk, m, UMMA_EPI_STATS_ONLY, st()));
     ++launches;
     ph_end();
     ph_begin(PH_ROWSTATS);
@@ -929,6 +935,7 @@ struct Engine : EngineBase {
   int moments_rows(const T* Xsrc, const T* xsrc, const int64_t* gather, int B, bool fresh_kernel_matrices, double* mean_out,
                    double* var_out, int64_t out_ld, bool need_var, int stages = 3) {
     if (groups_now()) return moments_rows_grouped(Xsrc, xsrc, gather, B, fresh_kernel_matrices, mean_out, var_out, out_ld, stages);
+    const int Bk = rowsK(B);
     for (int q = 0; q < Ql; ++q) {
       Latent& L = lat[q];
       if ((stages & 1) && vgp_identity) {
@@ -943,11 +950,11 @@ struct Engine : EngineBase {
         ph_begin(PH_KMAT);
         if (L.knm_tc) {
           CKS(umma_knm(ctx_err(), L.uk, (const float*)(const void*)Xsrc, Dp, Dp, gather, (const float*)(const void*)(gather ? xx_cur : xsrc),
-                       (const float*)(const void*)L.zz, B, L.kind, L.scale * L.scale, L.variance, st()));
+                       (const float*)(const void*)L.zz, Bk, L.kind, L.scale * L.scale, L.variance, st()));
         } else {
         GemmParams<T> g{};
         g.A = Xsrc; g.lda = Dp; g.a_gather = gather; g.B = L.Z; g.ldb = Dp; g.C = L.Knm; g.ldc = ldm;
-        g.M = B; g.N = m; g.K = D; g.alpha = 1.0;
+        g.M = Bk; g.N = m; g.K = D; g.alpha = 1.0;
         g.xx = gather ? xx_cur : xsrc; g.xx_direct = 1; g.zz = L.zz; g.scale2 = L.scale * L.scale; g.variance = L.variance; g.kernel_kind = L.kind;
         gemm_simt_launch<T, false, false, EPI_KERNELFN>(g, 1, st());
         }
@@ -958,7 +965,7 @@ struct Engine : EngineBase {
           CK(cudaMemsetAsync(L.racc, 0, ldB * sizeof(double), st()));
           UmmaEpilogue ep{};
           ep.mode = UMMA_EPI_STORE_SUMSQ; ep.acc0 = L.racc;
-          CKS(umma_gemm_nt(ctx_err(), L.um, UM_KNM, UM_LINV, (float*)(void*)L.V, B, m, ep, st()));
+          CKS(umma_gemm_nt(ctx_err(), L.um, UM_KNM, UM_LINV, (float*)(void*)L.V, Bk, m, ep, st()));
           ++launches;
           ph_end();
         } else {
@@ -991,11 +998,11 @@ struct Engine : EngineBase {
             // the previous tail was a Newton-Schulz refinement: no factor, statistics against the full Sigma_v = ns.Y():
             // var_f - Ktilde = rowsum((V Sigma_v) o V),  mean_f = (V Sigma_v) eta1_v
             ep.mode = UMMA_EPI_STATS_SIGMA; ep.cin = (const float*)(const void*)L.V; ep.tvec = L.eta1v;
-            CKS(umma_gemm_sigma(ctx_err(), L.um, L.ns, UM_V, B, ep, st()));
+            CKS(umma_gemm_sigma(ctx_err(), L.um, L.ns, UM_V, Bk, ep, st()));
           } else {
             // with early statistics the N tiles 0 .. ntn-2 were accumulated behind the previous step's tail: only the last one is left
             if (stats_use_early) umma_set_tile_range(m / 128 - 1, m / 128 - 1);
-            int sg = umma_gemm_nt(ctx_err(), L.um, UM_V, UM_X, (float*)(void*)L.VS, B, m, ep, st());
+            int sg = umma_gemm_nt(ctx_err(), L.um, UM_V, UM_X, (float*)(void*)L.VS, Bk, m, ep, st());
             umma_set_tile_range(-1, -1);
             CKS(sg);
             rowfin_now = ep.fin != nullptr;
@@ -1532,7 +1539,9 @@ struct Engine : EngineBase {
     if (!have_K) { ctx->err = "agp_refresh_K must be called before a step"; return AGP_ERR_STATE; }
     if (!from_batch && !have_data) { ctx->err = "upload data first"; return AGP_ERR_STATE; }
     if (B < 1 || B > Bcap) BAD("The size of mini-batch is incorrect (negative or bigger than the batch capacity)");
-    if (prec == AGP_PREC_TF32X3 && (B % 128)) BAD("TF32X3 precision needs B % 128 == 0");
+    // tf32x3: a ragged B is padded to the next multiple of 128 on the host index list path (rowsK); host-row batches and the resident
+    // list pool keep the multiple-of-128 rule
+    if (prec == AGP_PREC_TF32X3 && (B % 128) && (from_batch || !idx)) BAD("TF32X3 precision needs B % 128 == 0 on this path (host index lists are padded internally)");
     if (!from_batch) CKS(prep_idx(idx, B, base));
     curB = B; cur_from_batch = from_batch; kernel_matrices_stale = false; prefetched = false; stats_early = false;
     fuse_lik_next = fuse_in_step_moments && can_fuse_lik(); fuse_from_batch = from_batch; lik_fused = false;
@@ -1586,8 +1595,13 @@ struct Engine : EngineBase {
     return AGP_OK;
   }
   int natgrad_products(double rho) {
-    const int B = curB;
+    const int B = curB, Bk = rowsK(curB);
     const bool grp = use_groups && prec == AGP_PREC_TF32X3;
+    if (Bk != B)    // padding rows of a ragged minibatch: zero weights, so they drop out of V^T grad_mu and of the Gram product
+      for (int q = 0; q < Ql; ++q) {
+        CK(cudaMemsetAsync(gS + (size_t)q * ldB + B, 0, (size_t)(Bk - B) * sizeof(double), st()));
+        CK(cudaMemsetAsync(gmu + (size_t)q * ldB + B, 0, (size_t)(Bk - B) * sizeof(double), st()));
+      }
     if (grp) fan_begin();
     for (int q = 0; q < Ql; ++q) {
       Latent& L = lat[q];
@@ -1606,7 +1620,7 @@ struct Engine : EngineBase {
       if (prec == AGP_PREC_TF32X3 && !gram_tn) {
         ph_begin(PH_SPLIT);
         umma_set_pdl(tail_pdl && !prof && !fan_active);
-        CKS(umma_scale_transpose(ctx_err(), L.um, (const float*)(const void*)L.V, gS + (size_t)q * ldB, rho, gmu + (size_t)q * ldB, L.v1, B, m, st()));
+        CKS(umma_scale_transpose(ctx_err(), L.um, (const float*)(const void*)L.V, gS + (size_t)q * ldB, rho, gmu + (size_t)q * ldB, L.v1, Bk, m, st()));
         ++launches;
         ph_end();
       }
@@ -1616,21 +1630,21 @@ struct Engine : EngineBase {
         // with its share of the update and the tail's first kernel, and joins before the block steps)
         ph_begin(PH_GRAM);
         const int sms = 148, ut = (m / 128) * (m / 128 + 1) / 2;
-        split_SA = umma_gram_splits(B, std::min(32, n_split));
-        split_SB = umma_gram_splits(B, std::max(1, std::min(n_split, (sms - split_SA) / (ut - 1))));
+        split_SA = umma_gram_splits(Bk, std::min(32, n_split));
+        split_SB = umma_gram_splits(Bk, std::max(1, std::min(n_split, (sms - split_SA) / (ut - 1))));
         umma_set_pdl(false);
         CK(cudaEventRecord(ev_g0, ctx->stream));
         CK(cudaStreamWaitEvent(side, ev_g0, 0));
         cudaStream_t saved = cur_stream;
         cur_stream = side;
-        int sg = umma_gram_part(ctx_err(), L.um, (float*)(void*)L.Gpart, B, m, 1, split_SB, sms - split_SA, st());
+        int sg = umma_gram_part(ctx_err(), L.um, (float*)(void*)L.Gpart, Bk, m, 1, split_SB, sms - split_SA, st());
         ++launches;
         if (sg == AGP_OK) { launch_combine(L, rho, split_SB, 2); }
         if (sg == AGP_OK && cudaEventRecord(ev_gb, side) != cudaSuccess) sg = AGP_ERR_CUDA;
         cur_stream = saved;
         CKS(sg);
         umma_set_pdl(tail_pdl && !prof);      // scale_transpose -> tile (0, 0): programmatic edge on the main stream
-        int sa_ = umma_gram_part(ctx_err(), L.um, (float*)(void*)L.Gpart, B, m, 0, split_SA, split_SA, st());
+        int sa_ = umma_gram_part(ctx_err(), L.um, (float*)(void*)L.Gpart, Bk, m, 0, split_SA, split_SA, st());
         umma_set_pdl(false);
         CKS(sa_);
         ++launches;
@@ -1643,12 +1657,12 @@ struct Engine : EngineBase {
       int ns = n_split;
       if (gram_tn) {
         umma_set_pdl(tail_pdl && !prof && !fan_active);
-        int sg = umma_gram_tn(ctx_err(), L.um, (float*)(void*)L.Gpart, gS + (size_t)q * ldB, rho, gmu + (size_t)q * ldB, L.v1, B, m, &ns, st());
+        int sg = umma_gram_tn(ctx_err(), L.um, (float*)(void*)L.Gpart, gS + (size_t)q * ldB, rho, gmu + (size_t)q * ldB, L.v1, Bk, m, &ns, st());
         umma_set_pdl(false);
         CKS(sg);
         ++launches;
       } else if (prec == AGP_PREC_TF32X3) {
-        CKS(umma_gram(ctx_err(), L.um, (float*)(void*)L.Gpart, B, m, &ns, st()));
+        CKS(umma_gram(ctx_err(), L.um, (float*)(void*)L.Gpart, Bk, m, &ns, st()));
         umma_set_pdl(false);
         ++launches;
       } else {
@@ -1667,7 +1681,7 @@ struct Engine : EngineBase {
       ph_begin(PH_GRAM);
       int ns = n_split;
       umma_set_pdl(tail_pdl && !prof);
-      CKS(umma_gram_grouped(ctx_err(), grpG, lat[0].um, B, m, &ns, st()));
+      CKS(umma_gram_grouped(ctx_err(), grpG, lat[0].um, Bk, m, &ns, st()));
       umma_set_pdl(false);
       ++launches;
       for (auto& L : lat) L.gram_splits = ns;

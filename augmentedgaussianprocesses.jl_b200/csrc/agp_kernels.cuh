@@ -43,6 +43,11 @@ __global__ void idx_rebase_kernel(const int64_t* __restrict__ src, int64_t* __re
 
 // copy the index list of the current cursor position into the fixed per-step buffer (so that every
 // later kernel of the step - and a captured CUDA graph - reads one fixed address)
+// padding rows [B, Bk) of a ragged minibatch repeat its first sample (their weights are zero: see Engine::rowsK)
+__global__ void idx_pad_kernel(int64_t* __restrict__ idx, int B, int Bk) {
+  for (int b = B + threadIdx.x; b < Bk; b += blockDim.x) idx[b] = idx[0];
+}
+
 template <typename T>
 __global__ void idx_select_kernel(const int64_t* __restrict__ pool, int64_t n_lists, int B,
                                   const int64_t* __restrict__ counters /*[0]=t,[1]=cursor*/, int cursor_offset,

@@ -67,13 +67,15 @@ function kernel_params(k)
     return Int32(kind), Float64(s), Float64(var)
 end
 
-# tcgen05 (tf32x3 = 2) needs m and the batch capacity to be multiples of 128; other shapes (the reference's own tests use 10 inducing
-# points, test/testingtools.jl:66) take the fp32 SIMT path (1).  AGP_B200_PRECISION = f64 | f32 | tf32x3 overrides.
+# tcgen05 (tf32x3 = 2) needs m to be a multiple of 128 and a batch CAPACITY that is one (the engine pads a ragged minibatch of the
+# host index list path itself); other numbers of inducing points (the reference's own tests use 10, test/testingtools.jl:66) take the
+# fp32 SIMT path (1).  AGP_B200_PRECISION = f64 | f32 | tf32x3 overrides.
 function precision_code(m::Int, B::Int)
     p = get(ENV, "AGP_B200_PRECISION", "auto")
     p == "f64" && return Int32(0); p == "f32" && return Int32(1); p == "tf32x3" && return Int32(2)
-    return (m % 128 == 0 && B % 128 == 0) ? Int32(2) : Int32(1)
+    return m % 128 == 0 ? Int32(2) : Int32(1)
 end
+batch_capacity(m::Int, B::Int) = precision_code(m, B) == 2 ? cld(B, 128) * 128 : B
 
 likelihoods(model::SVGP) = (AGP.likelihood(model),)
 likelihoods(model::MOSVGP) = Tuple(AGP.likelihood(model))
@@ -103,7 +105,7 @@ function engine(model::Union{SVGP{T},MOSVGP{T}}, B::Int) where {T}
     rc == 0 || error("agp_ctx_create failed (no CUDA device; there is no CPU fallback)")
     e = Engine(ctx[], C_NULL, 0)
     GC.@preserve Z kk ks kv lk p0 p1 A begin
-        d = Ref(ModelDesc(model_kind(model), Q, 0, Q, m, D, B, precision_code(m, B), AGP.is_stochastic(inf) ? 1 : 0, κ, τ, Float64(T(AGP.jitt)),
+        d = Ref(ModelDesc(model_kind(model), Q, 0, Q, m, D, batch_capacity(m, B), precision_code(m, B), AGP.is_stochastic(inf) ? 1 : 0, κ, τ, Float64(T(AGP.jitt)),
                           length(ls), pointer(lk), pointer(p0), pointer(p1), isempty(A) ? C_NULL : pointer(A),
                           pointer(kk), pointer(ks), pointer(kv), pointer(Z), C_NULL))
         check(e, ccall((:agp_model_create, LIB), Cint, (Ptr{Cvoid}, Ref{ModelDesc}, Ref{Ptr{Cvoid}}), e.ctx, d, mdl))

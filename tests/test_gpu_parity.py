@@ -793,3 +793,32 @@ def test_testconv_thresholds_engine(agp, lik, problem, shape):
         else:
             assert np.mean(np.asarray(yp) != y) < 0.9
         assert np.isfinite(agp.ELBO(model, st))
+
+
+@pytest.mark.parametrize("lik,stoch", [("logistic", True), ("studentt", False), ("logisticsoftmax", True)])
+def test_tf32x3_ragged_minibatch(agp, lik, stoch):
+    """Minibatch sizes that are not multiples of the 128-row tensor-core tile (B = 200, full batch n = 700) on the tcgen05 path: the
+    engine pads the rows of the B x m products itself (the extra rows repeat sample 0 and carry zero weights), so precision "auto"
+    keeps the fast path for any B as long as m is a multiple of 128.  Single-latent (Gram straight from V) and multi-latent (grouped
+    launches) steps, stochastic and full-batch, against the oracle at the tf32x3 tolerance; prediction and ELBO afterwards."""
+    n, D, m, B, iters = 700, 5, 128, 200, 6
+    X, y, Z, mbs, F, rng = make_data(lik, n, D, m, B, iters, seed=21)
+    sc = 1.0 / np.sqrt(D)
+    mo = O.SVGP(oracle_kernel(O, "sqexp", sc, 1.0), oracle_lik(O, lik), O.AnalyticSVI(B) if stoch else O.AnalyticVI(), Z)
+    mo, so = O.train(mo, X, y, iters, minibatches=mbs)
+    me = agp.SVGP(engine_kernel(agp, "sqexp", sc, 1.0), engine_lik(agp, lik), agp.AnalyticSVI(B) if stoch else agp.AnalyticVI(), Z)
+    me, se = agp.train(me, X, y, iters, minibatches=mbs)
+    assert me.precision == "tf32x3"
+    check_pair(agp, (mo, so), (me, se), TOL["tf32x3"])
+    mu_o, var_o = O.predict_f(mo, X[:77], cov=True)
+    mu_e, var_e = agp.predict_f(me, X[:77], cov=True)
+    assert rel_fro(mu_e, mu_o) < TOL["tf32x3"] and rel_fro(var_e, var_o) < 10 * TOL["tf32x3"]
+    # a second train! call with a DIFFERENT ragged size re-uses the engine (capacity 256 >= 150); only for a likelihood whose local
+    # variables carry nothing from batch to batch (LogisticSoftMax keeps alpha / gamma of the previous batch in the state)
+    if stoch and lik == "logistic":
+        B2 = 150
+        mbs2 = [rng.choice(n, B2, replace=False).astype(np.int64) for _ in range(3)]
+        mo.inference.batchsize = B2; me.inference.batchsize = B2
+        mo, so = O.train(mo, X, y, 3, minibatches=mbs2, state=so)
+        me, se = agp.train(me, X, y, 3, minibatches=mbs2, state=se)
+        check_pair(agp, (mo, so), (me, se), TOL["tf32x3"])
