@@ -477,9 +477,10 @@ class AbstractGPModel:
             old.close()
         cap = int(capacity)
         if self.precision_requested == "auto":
-            # the tcgen05 kernels tile m by 128 (a ragged minibatch is padded inside the engine: Engine::rowsK); other numbers of inducing
-            # points (e.g. the reference's 10-inducing-point tests) take the fp32 SIMT path
-            self.precision = "tf32x3" if self.m % 128 == 0 else "f32"
+            # the tcgen05 kernels tile m and B by 128; the engine pads both itself (Engine::mk, Engine::rowsK), so every model with at
+            # least 128 inducing points takes the tensor-core path; smaller ones (e.g. the reference's 10-inducing-point tests) would
+            # mostly multiply padding and take the fp32 SIMT path
+            self.precision = "tf32x3" if self.m >= 128 else "f32"
         if self.precision == "tf32x3":
             cap = (cap + 127) // 128 * 128
         self._eng = _Engine(self._desc(cap), self.device, self.stream)
@@ -546,7 +547,7 @@ class AbstractGPModel:
 class SVGP(AbstractGPModel):
     """models/SVGP.jl:22-80.  `SVGP(kernel, likelihood, inference, Z; optimiser=false, Zoptimiser=false)`.
 
-    precision: "auto" (default: "tf32x3" when m is a multiple of 128, else "f32"), "f64" (fp64 SIMT, exact
+    precision: "auto" (default: "tf32x3" when m >= 128, else "f32"), "f64" (fp64 SIMT, exact
     mode), "f32" (fp32 SIMT) or "tf32x3" (tcgen05 tensor cores).
     shard=(rank, world): own n_latent/world latents (LogisticSoftMax classes) on this process.
     """

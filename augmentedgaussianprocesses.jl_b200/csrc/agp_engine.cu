@@ -121,6 +121,8 @@ template <typename T>
 struct Engine : EngineBase {
   // ---- configuration ----
   int model_kind, Qg, qbeg, Ql, m, D, Dp, mp, Bcap, prec, stochastic, nT;
+  int mk = 0;   // columns of the fp32 B x m operands: m, or m rounded up to the 128-wide tensor-core tile (tf32x3; the padding columns of
+                // L^-1 and X are zero, so whatever the padding inducing points (all-zero rows of Z) put into K_nm never reaches V)
   int64_t ldm, ldB;
   double rm_kappa, rm_tau, jitter;
   std::vector<int> h_lik_kind;
@@ -311,7 +313,8 @@ struct Engine : EngineBase {
     if (!d->lik_kind || !d->kernel_kind || !d->kernel_scale || !d->kernel_variance || !d->Z) BAD("null descriptor array");
     if (is_vgp && stochastic) BAD("VGP is a full-batch model: use AnalyticVI (models/VGP.jl)");
     if (stochastic && !(rm_kappa > 0.5 && rm_kappa <= 1.0 && rm_tau > 0)) BAD("kappa should be in the interval (0.5,1], tau positive");
-    Dp = (int)rup(D, 4); ldm = rup(m, 4); ldB = rup(Bcap, 4);
+    mk = prec == AGP_PREC_TF32X3 ? (int)rup(m, 128) : m;
+    Dp = (int)rup(D, 4); ldm = rup(mk, 4); ldB = rup(Bcap, 4);
     int nblk = (m + POTF2_NB - 1) / POTF2_NB, pw = 1;
     while (pw < nblk) pw *= 2;
     mp = pw * POTF2_NB;
@@ -346,7 +349,7 @@ struct Engine : EngineBase {
     } else BAD("unknown model kind");
     if (is_vgp && Ql != Qg) BAD("VGP latents are not sharded");
     if (prec < 0 || prec > 2) BAD("unknown precision");
-    if (prec == AGP_PREC_TF32X3 && !umma_shape_ok(m, Bcap)) BAD("TF32X3 precision needs m % 128 == 0 and batch_capacity % 128 == 0");
+    if (prec == AGP_PREC_TF32X3 && (m <= 64 || !umma_shape_ok(mk, Bcap))) BAD("TF32X3 precision needs m > 64 and batch_capacity % 128 == 0 (m itself is padded to a multiple of 128 internally)");
 
     CK(cudaSetDevice(ctx->device));
     // split-K of the Gram product kappa^T diag(w) kappa: enough CTAs to fill the chip
@@ -364,18 +367,18 @@ struct Engine : EngineBase {
       if (L.kind < 0 || L.kind > 2 || !(L.scale > 0) || !(L.variance > 0)) BAD("bad kernel parameters");
       L.hZ.assign(d->Z + (size_t)q * m * D, d->Z + (size_t)(q + 1) * m * D);
       if (d->mu0) { L.hmu0.assign(d->mu0 + (size_t)q * m, d->mu0 + (size_t)(q + 1) * m); L.has_mu0 = true; }
-      CKS(dalloc(&L.Z, (size_t)m * Dp)); CKS(dalloc(&L.zz, m));
+      CKS(dalloc(&L.Z, (size_t)mk * Dp)); CKS(dalloc(&L.zz, mk));
       CKS(dalloc(&L.Zd, (size_t)m * Dp)); CKS(dalloc(&L.zzd, m));
       CKS(dalloc(&L.Lc, (size_t)mp * mp)); CKS(dalloc(&L.Linv, (size_t)mp * mp)); CKS(dalloc(&L.Kinv, (size_t)mp * mp));
       CKS(dalloc(&L.mu0, 2 * (size_t)mp)); CKS(dalloc(&L.mu0v, mp));   // mu0: [0, mp) prior mean, [mp, 2mp) scratch for the canonical mean
-      CKS(dalloc(&L.Linv_T, (size_t)m * ldm));
+      CKS(dalloc(&L.Linv_T, (size_t)mk * ldm));
       CKS(dalloc(&L.eta1c, mp)); CKS(dalloc(&L.eta2c, (size_t)mp * mp));
       CKS(dalloc(&L.eta1v, mp)); CKS(dalloc(&L.eta2v, (size_t)mp * mp)); CKS(dalloc(&L.muv, mp)); CKS(dalloc(&L.tvec, mp));
       CKS(dalloc(&L.Xv, (size_t)mp * mp)); CKS(dalloc(&L.Dinv, (size_t)mp * POTF2_NB));
-      CKS(dalloc(&L.Xv_T, (size_t)m * ldm));
+      CKS(dalloc(&L.Xv_T, (size_t)mk * ldm));
       CKS(dalloc(&L.Knm, (size_t)Bcap * ldm)); CKS(dalloc(&L.V, (size_t)Bcap * ldm)); CKS(dalloc(&L.VS, (size_t)Bcap * ldm));
       CKS(dalloc(&L.Ktilde, ldB)); CKS(dalloc(&L.racc, 3 * ldB));
-      CKS(dalloc(&L.Gpart, (size_t)n_split * m * ldm));
+      CKS(dalloc(&L.Gpart, (size_t)n_split * mk * ldm));
       CKS(dalloc(&L.v1, mp));
       CKS(dalloc(&L.P, (size_t)mp * mp)); CKS(dalloc(&L.X, (size_t)mp * mp)); CKS(dalloc(&L.W, (size_t)mp * mp));
       CKS(dalloc(&L.logdetP, 2));
@@ -401,10 +404,10 @@ struct Engine : EngineBase {
       if (L.has_mu0) CK(cudaMemcpyAsync(L.mu0, L.hmu0.data(), m * sizeof(double), cudaMemcpyHostToDevice, st()));
       CK(cudaStreamSynchronize(st()));
       if (prec == AGP_PREC_TF32X3)
-        CKS(umma_latent_alloc(ctx_err(), L.um, m, (int)ldm, Bcap, (const float*)(const void*)L.Knm, (const float*)(const void*)L.V,
+        CKS(umma_latent_alloc(ctx_err(), L.um, mk, (int)ldm, Bcap, (const float*)(const void*)L.Knm, (const float*)(const void*)L.V,
                               (const float*)(const void*)L.Linv_T, (const float*)(const void*)L.Xv_T, st()));
-      if (prec == AGP_PREC_TF32X3 && umma_knm_shape_ok(m, Bcap, D) && !getenv("AGP_KNM_SIMT")) {
-        CKS(umma_knm_setup(ctx_err(), L.uk, (const float*)(const void*)L.Z, Dp, m, D, (float*)(void*)L.Knm, ldm, Bcap, st()));
+      if (prec == AGP_PREC_TF32X3 && umma_knm_shape_ok(mk, Bcap, D) && !getenv("AGP_KNM_SIMT")) {
+        CKS(umma_knm_setup(ctx_err(), L.uk, (const float*)(const void*)L.Z, Dp, mk, D, (float*)(void*)L.Knm, ldm, Bcap, st()));
         L.knm_tc = true;
       }
     }
@@ -900,7 +903,7 @@ struct Engine : EngineBase {
       fan_end();
       ph_end();
       ph_begin(PH_KAPPA);
-      CKS(umma_gemm_nt_grouped(ctx_err(), grpV, lat[0].um, 1, Bk, m, UMMA_EPI_STORE_SUMSQ, st()));
+      CKS(umma_gemm_nt_grouped(ctx_err(), grpV, lat[0].um, 1, Bk, mk, UMMA_EPI_STORE_SUMSQ, st()));
       ++launches;
       ph_end();
     }
@@ -908,7 +911,7 @@ struct Engine : EngineBase {
     ph_begin(PH_KSIGMA);
     for (int q = 0; q < Ql; ++q) CK(cudaMemsetAsync(lat[q].racc + ldB, 0, 2 * ldB * sizeof(double), st()));
     racc2_precleared = false;
-    CKS(umma_gemm_nt_grouped(ctx_err(), grpS, lat[0].um, 1, Bk, m, UMMA_EPI_STATS_ONLY, st()));
+    CKS(umma_gemm_nt_grouped(ctx_err(), grpS, lat[0].um, 1, Bk, mk, UMMA_EPI_STATS_ONLY, st()));
     ++launches;
     ph_end();
     ph_begin(PH_ROWSTATS);
@@ -965,7 +968,7 @@ struct Engine : EngineBase {
           CK(cudaMemsetAsync(L.racc, 0, ldB * sizeof(double), st()));
           UmmaEpilogue ep{};
           ep.mode = UMMA_EPI_STORE_SUMSQ; ep.acc0 = L.racc;
-          CKS(umma_gemm_nt(ctx_err(), L.um, UM_KNM, UM_LINV, (float*)(void*)L.V, Bk, m, ep, st()));
+          CKS(umma_gemm_nt(ctx_err(), L.um, UM_KNM, UM_LINV, (float*)(void*)L.V, Bk, mk, ep, st()));
           ++launches;
           ph_end();
         } else {
@@ -1002,7 +1005,7 @@ struct Engine : EngineBase {
           } else {
             // with early statistics the N tiles 0 .. ntn-2 were accumulated behind the previous step's tail: only the last one is left
             if (stats_use_early) umma_set_tile_range(m / 128 - 1, m / 128 - 1);
-            int sg = umma_gemm_nt(ctx_err(), L.um, UM_V, UM_X, (float*)(void*)L.VS, Bk, m, ep, st());
+            int sg = umma_gemm_nt(ctx_err(), L.um, UM_V, UM_X, (float*)(void*)L.VS, Bk, mk, ep, st());
             umma_set_tile_range(-1, -1);
             CKS(sg);
             rowfin_now = ep.fin != nullptr;
@@ -1174,7 +1177,7 @@ struct Engine : EngineBase {
     CK(cudaMemcpy(L.zzd, zn.data(), zn.size() * sizeof(double), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(L.Z, zt.data(), zt.size() * sizeof(T), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(L.zz, znt.data(), znt.size() * sizeof(T), cudaMemcpyHostToDevice));
-    if (L.knm_tc) CKS(umma_knm_setup(ctx_err(), L.uk, (const float*)(const void*)L.Z, Dp, m, D, (float*)(void*)L.Knm, ldm, Bcap, st()));
+    if (L.knm_tc) CKS(umma_knm_setup(ctx_err(), L.uk, (const float*)(const void*)L.Z, Dp, mk, D, (float*)(void*)L.Knm, ldm, Bcap, st()));
     if (stale_K_ok && have_K) K_dirty = true; else have_K = false;
     prefetched = false; stats_early = false;
     drop_graph();
@@ -1195,13 +1198,13 @@ struct Engine : EngineBase {
     for (auto& L : lat) {
       if (!L.bkLc) {
         CKS(dalloc(&L.bkLc, mm)); CKS(dalloc(&L.bkLinv, mm)); CKS(dalloc(&L.bkKinv, mm)); CKS(dalloc(&L.bkmu0v, mp));
-        CKS(dalloc(&L.bkLinvT, (size_t)m * ldm));
+        CKS(dalloc(&L.bkLinvT, (size_t)mk * ldm));
       }
       CK(cudaMemcpyAsync(L.bkLc, L.Lc, mm * 8, cudaMemcpyDeviceToDevice, st()));
       CK(cudaMemcpyAsync(L.bkLinv, L.Linv, mm * 8, cudaMemcpyDeviceToDevice, st()));
       CK(cudaMemcpyAsync(L.bkKinv, L.Kinv, mm * 8, cudaMemcpyDeviceToDevice, st()));
       CK(cudaMemcpyAsync(L.bkmu0v, L.mu0v, (size_t)mp * 8, cudaMemcpyDeviceToDevice, st()));
-      CK(cudaMemcpyAsync(L.bkLinvT, L.Linv_T, (size_t)m * ldm * sizeof(T), cudaMemcpyDeviceToDevice, st()));
+      CK(cudaMemcpyAsync(L.bkLinvT, L.Linv_T, (size_t)mk * ldm * sizeof(T), cudaMemcpyDeviceToDevice, st()));
       L.bklogdetK = L.logdetK;
     }
     CKS(ensure_factors());
@@ -1217,7 +1220,7 @@ struct Engine : EngineBase {
       CK(cudaMemcpyAsync(L.Linv, L.bkLinv, mm * 8, cudaMemcpyDeviceToDevice, st()));
       CK(cudaMemcpyAsync(L.Kinv, L.bkKinv, mm * 8, cudaMemcpyDeviceToDevice, st()));
       CK(cudaMemcpyAsync(L.mu0v, L.bkmu0v, (size_t)mp * 8, cudaMemcpyDeviceToDevice, st()));
-      CK(cudaMemcpyAsync(L.Linv_T, L.bkLinvT, (size_t)m * ldm * sizeof(T), cudaMemcpyDeviceToDevice, st()));
+      CK(cudaMemcpyAsync(L.Linv_T, L.bkLinvT, (size_t)mk * ldm * sizeof(T), cudaMemcpyDeviceToDevice, st()));
       if (L.um.v2 || L.um.ps) { CKS(umma_presplit(ctx_err(), L.um, UM_LINV, (const float*)(const void*)L.Linv_T, st())); ++launches; }
       L.logdetK = L.bklogdetK;
       CKS(whiten(L));
@@ -1620,7 +1623,7 @@ struct Engine : EngineBase {
       if (prec == AGP_PREC_TF32X3 && !gram_tn) {
         ph_begin(PH_SPLIT);
         umma_set_pdl(tail_pdl && !prof && !fan_active);
-        CKS(umma_scale_transpose(ctx_err(), L.um, (const float*)(const void*)L.V, gS + (size_t)q * ldB, rho, gmu + (size_t)q * ldB, L.v1, Bk, m, st()));
+        CKS(umma_scale_transpose(ctx_err(), L.um, (const float*)(const void*)L.V, gS + (size_t)q * ldB, rho, gmu + (size_t)q * ldB, L.v1, Bk, mk, st()));
         ++launches;
         ph_end();
       }
@@ -1637,14 +1640,14 @@ struct Engine : EngineBase {
         CK(cudaStreamWaitEvent(side, ev_g0, 0));
         cudaStream_t saved = cur_stream;
         cur_stream = side;
-        int sg = umma_gram_part(ctx_err(), L.um, (float*)(void*)L.Gpart, Bk, m, 1, split_SB, sms - split_SA, st());
+        int sg = umma_gram_part(ctx_err(), L.um, (float*)(void*)L.Gpart, Bk, mk, 1, split_SB, sms - split_SA, st());
         ++launches;
         if (sg == AGP_OK) { launch_combine(L, rho, split_SB, 2); }
         if (sg == AGP_OK && cudaEventRecord(ev_gb, side) != cudaSuccess) sg = AGP_ERR_CUDA;
         cur_stream = saved;
         CKS(sg);
         umma_set_pdl(tail_pdl && !prof);      // scale_transpose -> tile (0, 0): programmatic edge on the main stream
-        int sa_ = umma_gram_part(ctx_err(), L.um, (float*)(void*)L.Gpart, Bk, m, 0, split_SA, split_SA, st());
+        int sa_ = umma_gram_part(ctx_err(), L.um, (float*)(void*)L.Gpart, Bk, mk, 0, split_SA, split_SA, st());
         umma_set_pdl(false);
         CKS(sa_);
         ++launches;
@@ -1657,18 +1660,18 @@ struct Engine : EngineBase {
       int ns = n_split;
       if (gram_tn) {
         umma_set_pdl(tail_pdl && !prof && !fan_active);
-        int sg = umma_gram_tn(ctx_err(), L.um, (float*)(void*)L.Gpart, gS + (size_t)q * ldB, rho, gmu + (size_t)q * ldB, L.v1, Bk, m, &ns, st());
+        int sg = umma_gram_tn(ctx_err(), L.um, (float*)(void*)L.Gpart, gS + (size_t)q * ldB, rho, gmu + (size_t)q * ldB, L.v1, Bk, mk, &ns, st());
         umma_set_pdl(false);
         CKS(sg);
         ++launches;
       } else if (prec == AGP_PREC_TF32X3) {
-        CKS(umma_gram(ctx_err(), L.um, (float*)(void*)L.Gpart, Bk, m, &ns, st()));
+        CKS(umma_gram(ctx_err(), L.um, (float*)(void*)L.Gpart, Bk, mk, &ns, st()));
         umma_set_pdl(false);
         ++launches;
       } else {
         GemmParams<T> g{};  // rho * V^T diag(grad_Sigma) V  (functions/utils.jl:70-72, whitened), split over the minibatch
         g.A = L.V; g.lda = ldm; g.B = L.V; g.ldb = ldm; g.C = L.Gpart; g.ldc = ldm; g.M = m; g.N = m; g.K = B;
-        g.k_scale = gS + (size_t)q * ldB; g.k_scale_mul = rho; g.k_chunk = k_chunk; g.zs_c = (int64_t)m * ldm; g.alpha = 1.0;
+        g.k_scale = gS + (size_t)q * ldB; g.k_scale_mul = rho; g.k_chunk = k_chunk; g.zs_c = (int64_t)mk * ldm; g.alpha = 1.0;
         ns = (B + k_chunk - 1) / k_chunk;
         gemm_simt_launch<T, true, true, EPI_PLAIN>(g, ns, st());
         ++launches;
@@ -1681,7 +1684,7 @@ struct Engine : EngineBase {
       ph_begin(PH_GRAM);
       int ns = n_split;
       umma_set_pdl(tail_pdl && !prof);
-      CKS(umma_gram_grouped(ctx_err(), grpG, lat[0].um, Bk, m, &ns, st()));
+      CKS(umma_gram_grouped(ctx_err(), grpG, lat[0].um, Bk, mk, &ns, st()));
       umma_set_pdl(false);
       ++launches;
       for (auto& L : lat) L.gram_splits = ns;
@@ -1693,7 +1696,7 @@ struct Engine : EngineBase {
   // combine_kernel: split-K reduction of the Gram partials + natural-parameter update; blk: 0 = whole matrix, 1 / 2 = split Gram parts
   void launch_combine(Latent& L, double rho, int ns, int blk) {
     TailParams tp{};
-    tp.m = m; tp.mp = mp; tp.ld = mp; tp.n_split = ns; tp.gpart_stride = (int64_t)m * ldm; tp.gpart_ld = ldm;
+    tp.m = m; tp.mp = mp; tp.ld = mp; tp.n_split = ns; tp.gpart_stride = (int64_t)mk * ldm; tp.gpart_ld = ldm;
     tp.g_mirrored = (prec == AGP_PREC_TF32X3) ? 1 : 0;
     tp.v1 = L.v1; tp.mu0v = L.mu0v; tp.eta1 = L.eta1v; tp.eta2 = L.eta2v; tp.P = L.P;
     tp.counters = counters; tp.stochastic = stochastic; tp.rm_kappa = rm_kappa; tp.rm_tau = rm_tau; tp.rho = rho;
@@ -2657,7 +2660,7 @@ struct Engine : EngineBase {
       for (int r = 0; r < reps; ++r)
         xx_gather_kernel<T><<<(B + 255) / 256, 256, 0, st()>>>(idx_pool + ((c[1] + r) % n_lists) * B, B, xx, xxr + (size_t)r * B);
     }
-    if (which == 3 && !L.um.gram_tn) CKS(umma_scale_transpose(ctx_err(), L.um, (const float*)(const void*)L.V, gS, 1.0, gmu, L.v1, B, m, st()));
+    if (which == 3 && !L.um.gram_tn) CKS(umma_scale_transpose(ctx_err(), L.um, (const float*)(const void*)L.V, gS, 1.0, gmu, L.v1, B, mk, st()));
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     CK(cudaStreamSynchronize(st()));
@@ -2673,11 +2676,11 @@ struct Engine : EngineBase {
         UmmaEpilogue ep{};
         ep.mode = which == 1 ? UMMA_EPI_STORE_SUMSQ : UMMA_EPI_STATS_ONLY;
         ep.acc0 = L.racc + (which == 1 ? 0 : ldB); ep.acc1 = L.racc + 2 * ldB; ep.tvec = L.tvec;
-        rc = umma_gemm_nt(ctx_err(), L.um, which == 1 ? UM_KNM : UM_V, which == 1 ? UM_LINV : UM_X, (float*)(void*)(which == 1 ? L.V : L.VS), B, m, ep, st());
+        rc = umma_gemm_nt(ctx_err(), L.um, which == 1 ? UM_KNM : UM_V, which == 1 ? UM_LINV : UM_X, (float*)(void*)(which == 1 ? L.V : L.VS), B, mk, ep, st());
       } else {
         int ns = n_split;
-        if (L.um.gram_tn) rc = umma_gram_tn(ctx_err(), L.um, (float*)(void*)L.Gpart, gS, 1.0, gmu, L.v1, B, m, &ns, st());
-        else rc = umma_gram(ctx_err(), L.um, (float*)(void*)L.Gpart, B, m, &ns, st());
+        if (L.um.gram_tn) rc = umma_gram_tn(ctx_err(), L.um, (float*)(void*)L.Gpart, gS, 1.0, gmu, L.v1, B, mk, &ns, st());
+        else rc = umma_gram(ctx_err(), L.um, (float*)(void*)L.Gpart, B, mk, &ns, st());
       }
       ++launches;
     }

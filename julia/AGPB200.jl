@@ -67,13 +67,13 @@ function kernel_params(k)
     return Int32(kind), Float64(s), Float64(var)
 end
 
-# tcgen05 (tf32x3 = 2) needs m to be a multiple of 128 and a batch CAPACITY that is one (the engine pads a ragged minibatch of the
-# host index list path itself); other numbers of inducing points (the reference's own tests use 10, test/testingtools.jl:66) take the
-# fp32 SIMT path (1).  AGP_B200_PRECISION = f64 | f32 | tf32x3 overrides.
+# tcgen05 (tf32x3 = 2) needs a batch CAPACITY that is a multiple of 128 and more than 64 inducing points (the engine pads m and a ragged
+# minibatch of the host index list path itself); small models (the reference's own tests use 10 inducing points,
+# test/testingtools.jl:66) take the fp32 SIMT path (1).  AGP_B200_PRECISION = f64 | f32 | tf32x3 overrides.
 function precision_code(m::Int, B::Int)
     p = get(ENV, "AGP_B200_PRECISION", "auto")
     p == "f64" && return Int32(0); p == "f32" && return Int32(1); p == "tf32x3" && return Int32(2)
-    return m % 128 == 0 ? Int32(2) : Int32(1)
+    return m >= 128 ? Int32(2) : Int32(1)
 end
 batch_capacity(m::Int, B::Int) = precision_code(m, B) == 2 ? cld(B, 128) * 128 : B
 
