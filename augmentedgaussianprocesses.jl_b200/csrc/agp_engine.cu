@@ -645,6 +645,11 @@ struct Engine : EngineBase {
     const int nb = POTF2_NB, nblk = mp / nb;
     const int64_t ld = mp;
     ph_begin(PH_CHOL);
+    // The recursive-doubling inverse below reads whole s x s diagonal blocks of Xw (s = 128, 256, ...) but only ever writes its 64 x 64
+    // diagonal blocks and the blocks below them: the blocks ABOVE the block diagonal must be zero.  They are after allocation, but Xw
+    // (L.X) is also the scratch matrix of the hyper-parameter gradients / the Newton-Schulz seed (dense Sigma), after which the next
+    // factorisation of a matrix with mp >= 256 silently picked the leftovers up (K-tilde < 0 on the step after agp_hyper_grads).
+    if (nblk > 2) cudaMemsetAsync(Xw, 0, (size_t)mp * mp * sizeof(double), st());
     for (int k = 0; k < nblk; ++k) {
       double* dk = P + (int64_t)k * nb * (ld + 1);
       double* xk = Xw + (int64_t)k * nb * (ld + 1);

@@ -548,7 +548,8 @@ def test_ragged_sizes_layouts_and_host_batch_path(agp, precision):
         e.ck(e.lib.agp_step(e.model, idx1.ctypes.data_as(L.c_int64_p), 10 * B, 1, n / B))
 
 
-@pytest.mark.parametrize("lik,precision", [("gaussian", "f64"), ("logistic", "f64"), ("studentt", "f32"), ("logisticsoftmax", "f64"), ("poisson", "f64")])
+@pytest.mark.parametrize("lik,precision", [("gaussian", "f64"), ("logistic", "f64"), ("studentt", "f32"), ("logisticsoftmax", "f64"), ("poisson", "f64"),
+                                           ("logistic", "tf32x3"), ("logisticsoftmax", "tf32x3")])   # n = m = 160: padded to 256 on the tcgen05 path
 def test_vgp_parity(agp, lik, precision):
     """SURVEY 8 f4: the full VGP with AnalyticVI (natural_gradient!(::VarLatent), analyticVI.jl:126-140) against the oracle."""
     n, D, iters = 160, 3, 6
@@ -823,3 +824,26 @@ def test_tf32x3_ragged_minibatch(agp, lik, stoch, m):
         mo, so = O.train(mo, X, y, 3, minibatches=mbs2, state=so)
         me, se = agp.train(me, X, y, 3, minibatches=mbs2, state=se)
         check_pair(agp, (mo, so), (me, se), TOL["tf32x3"])
+
+
+@pytest.mark.parametrize("m", [128, 130])
+def test_tf32x3_padded_hyperparameter_training(agp, m):
+    """update_hyperparameters! (kernel scale / variance and the inducing points by ADAM, autotuning.jl:86-140) on the tcgen05 path with a
+    padded model (m = 130 -> 256 columns, B = 200 -> 256 rows): set_Z / the re-split of Z for the K_nm kernel / refresh_K must keep the
+    padding rows and columns zero.  K_mm is refactorised after every update (refresh_K_after_hyper) so that the run stays away from the
+    reference's own `K̃ has negative values` error with 130 inducing points in 4 dimensions; m = 128 is the same run without padding of m."""
+    n, D, B, iters = 800, 4, 200, 7
+    X, y, Z, mbs, F, rng = make_data("logistic", n, D, m, B, iters, seed=31)
+    s0, v0 = 1.5, 1.2     # short length scale: K_mm well conditioned, K-tilde of the fp32-class contractions stays far from zero
+    mo = O.SVGP(O.Kernel("sqexp", scale=s0, variance=v0), O.LogisticLikelihood(), O.AnalyticSVI(B), Z, optimiser=O.ADAM(0.01), Zoptimiser=O.ADAM(0.01))
+    mo.refresh_K_after_hyper = True
+    mo, so = O.train(mo, X, y, iters, minibatches=mbs)
+    me = agp.SVGP(v0 * agp.SqExponentialKernel() @ agp.ScaleTransform(s0), agp.LogisticLikelihood(), agp.AnalyticSVI(B), Z, optimiser=True, Zoptimiser=True)
+    me, se = agp.train(me, X, y, iters, minibatches=mbs, refresh_K_after_hyper=True)
+    assert me.precision == "tf32x3"
+    ko = mo.f[0].kernel
+    assert abs(ko.scale - s0) > 1e-3                                     # it moved
+    assert abs(me.kernel.scale - ko.scale) < 1e-3 * ko.scale and abs(me.kernel.variance - ko.variance) < 1e-3 * ko.variance
+    assert rel_fro(me.Z, mo.f[0].Z) < 1e-3
+    mu, S, _, _ = me.posterior(0)
+    assert rel_fro(mu, mo.f[0].mu) < 2e-2 and rel_fro(S, mo.f[0].Sigma) < 2e-2, (rel_fro(mu, mo.f[0].mu), rel_fro(S, mo.f[0].Sigma))
