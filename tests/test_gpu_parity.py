@@ -847,3 +847,84 @@ def test_tf32x3_padded_hyperparameter_training(agp, m):
     assert rel_fro(me.Z, mo.f[0].Z) < 1e-3
     mu, S, _, _ = me.posterior(0)
     assert rel_fro(mu, mo.f[0].mu) < 2e-2 and rel_fro(S, mo.f[0].Sigma) < 2e-2, (rel_fro(mu, mo.f[0].mu), rel_fro(S, mo.f[0].Sigma))
+
+
+# ---- the same features at sizes where the fp64 m x m matrices span several 64 x 64 tiles (m = 150 -> 256 padded, three block steps
+# of the tail, two levels of the recursive inverse): every feature above that was only exercised with m <= 64 (one tile) ----
+M_MED = 150
+
+
+def test_medium_checkpoint_hyper_grads_and_full_covariance(agp):
+    """m = 150, f64: re-entry with a state, get / set posterior through the canonical form, ELBO gradients against the oracle, and
+    the full predictive covariance, all after several steps (the step after agp_hyper_grads used to fail for m > 128)."""
+    n, D, B, iters = 900, 3, 300, 4
+    X, y, Z, mbs, F, rng = make_data("logistic", n, D, M_MED, B, iters, seed=41)
+    sc = 1.3
+    mo = O.SVGP(oracle_kernel(O, "matern32", sc, 1.1), O.LogisticLikelihood(), O.AnalyticSVI(B), Z)
+    mo, so = O.train(mo, X, y, 2, minibatches=mbs[:2])
+    me = agp.SVGP(engine_kernel(agp, "matern32", sc, 1.1), agp.LogisticLikelihood(), agp.AnalyticSVI(B), Z, precision="f64")
+    me, se = agp.train(me, X, y, 2, minibatches=mbs[:2])
+    go, ge = O.hyper_grads(mo, so, X[mbs[1]], so["y_batch"]), agp.hyper_grads(me)
+    for name in ("scale", "variance"):
+        assert abs(ge[0][name] - go[0][name]) <= 1e-7 * max(1.0, abs(go[0][name])), (name, ge[0][name], go[0][name])
+    assert rel_fro(ge[0]["Z"], go[0]["Z"]) < 1e-7
+    # continue with the state (train!(...; state)): K_mm is not refactorised, the Robbins-Monro schedule goes on
+    mo, so = O.train(mo, X, y, 2, minibatches=mbs[2:], state=so)
+    me, se = agp.train(me, X, y, 2, minibatches=mbs[2:], state=se)
+    check_pair(agp, (mo, so), (me, se), 1e-8)
+    # a new model seeded with the natural parameters of the first one continues identically (agp_set_posterior)
+    mu, S, e1, e2 = me.posterior(0)
+    m2 = agp.SVGP(engine_kernel(agp, "matern32", sc, 1.1), agp.LogisticLikelihood(), agp.AnalyticSVI(B), Z, precision="f64")
+    m2, s2 = agp.train(m2, X, y, 1, minibatches=mbs[:1])
+    e = m2._eng
+    e.ck(e.lib.agp_set_posterior(e.model, 0, agp._lib.dptr(np.ascontiguousarray(e1)), agp._lib.dptr(np.ascontiguousarray(e2))))
+    mu2, S2, _, _ = m2.posterior(0)
+    assert rel_fro(mu2, mu) < 1e-9 and rel_fro(S2, S) < 1e-9
+    Xt = rng.standard_normal((33, D))
+    mu_o, S_o = O.predict_f(mo, Xt, cov=True, diag=False)
+    mu_e, S_e = agp.predict_f(me, Xt, cov=True, diag=False)
+    assert rel_fro(np.asarray(mu_e), mu_o) < 1e-8 and rel_fro(np.asarray(S_e), S_o) < 1e-7
+
+
+def test_medium_mosvgp_update_A(agp):
+    """m = 150, f64: multi-latent steps (persistent tail over three latents, 256-padded matrices) with update_A!."""
+    n, D, B, iters, Q, T = 900, 3, 300, 5, 3, 4
+    X, _, Z, mbs, F, rng = make_data("mo", n, D, M_MED, B, iters, seed=43, n_task=max(Q, T))
+    ys = [np.sign(F[:, 0] + 1e-3), F[:, 1] + 0.1 * rng.standard_normal(n), F[:, 2] + 0.1 * rng.standard_t(3.0, n),
+          rng.poisson(3.0 / (1.0 + np.exp(-F[:, 3]))).astype(np.int64)]
+    A = rng.standard_normal((T, Q))
+    A /= np.linalg.norm(A, axis=1, keepdims=True)
+    Zs = [X[rng.permutation(n)[:M_MED]].copy() for _ in range(Q)]
+    sc = 1.3
+    liks_o = [O.LogisticLikelihood(), O.GaussianLikelihood(1e-2), O.StudentTLikelihood(3.0), O.PoissonLikelihood(2.0)]
+    liks_e = [agp.LogisticLikelihood(), agp.GaussianLikelihood(1e-2), agp.StudentTLikelihood(3.0), agp.PoissonLikelihood(2.0)]
+    mo = O.MOSVGP(O.Kernel("sqexp", scale=sc), liks_o, O.AnalyticSVI(B), Zs, A, Aoptimiser=O.ADAM(0.01))
+    me = agp.MOSVGP(agp.SqExponentialKernel() @ agp.ScaleTransform(sc), liks_e, agp.AnalyticSVI(B), Zs, A=A, Aoptimiser=True, precision="f64")
+    mo, so = O.train(mo, X, ys, iters, minibatches=mbs)
+    me, se = agp.train(me, X, ys, iters, minibatches=mbs)
+    assert rel_fro(me.A, mo.A) < 1e-8
+    check_pair(agp, (mo, so), (me, se), 1e-8)
+
+
+def test_medium_online_svgp(agp):
+    """OnlineSVGP with inducing sets of 140 / 200 / 170 points (f64): carry-over terms and extraKL at multi-tile sizes."""
+    rng = np.random.default_rng(47)
+    D, nb = 3, 400
+    sc = 1.3
+    Zall = rng.standard_normal((260, D))
+    sets = [Zall[:140], Zall[30:230], Zall[90:260]]
+    mo = O.OnlineSVGP(oracle_kernel(O, "sqexp", sc, 1.0), O.LogisticLikelihood(), O.AnalyticVI())
+    me = agp.OnlineSVGP(engine_kernel(agp, "sqexp", sc, 1.0), agp.LogisticLikelihood(), agp.AnalyticVI(), precision="f64")
+    so = se = None
+    for b, Zb in enumerate(sets):
+        X = rng.standard_normal((nb, D))
+        f = np.sin(X[:, 0]) + 0.5 * X[:, 1]
+        y = np.where(f + 0.3 * rng.standard_normal(nb) >= 0, 1.0, -1.0)
+        mo, so = O.train_online(mo, X, y, Zb, state=so, iterations=3)
+        me, se = agp.train_online(me, X, y, Zb, state=se, iterations=3)
+        mu, S, _, _ = me.posterior(0)
+        gp = mo.f[0]
+        assert rel_fro(mu, gp.mu) < 1e-7, (b, "mu", rel_fro(mu, gp.mu))
+        assert rel_fro(S, gp.Sigma) < 1e-7, (b, "Sigma", rel_fro(S, gp.Sigma))
+        eo, ee = mo.ELBO(so, so["y_batch"]), agp.ELBO(me, se)
+        assert abs(ee - eo) <= 1e-6 * max(1.0, abs(eo)), (b, ee, eo)
