@@ -928,3 +928,30 @@ def test_medium_online_svgp(agp):
         assert rel_fro(S, gp.Sigma) < 1e-7, (b, "Sigma", rel_fro(S, gp.Sigma))
         eo, ee = mo.ELBO(so, so["y_batch"]), agp.ELBO(me, se)
         assert abs(ee - eo) <= 1e-6 * max(1.0, abs(eo)), (b, ee, eo)
+
+
+@pytest.mark.parametrize("precision,tol", [("f64", 1e-6), ("tf32x3", 5e-3)])
+def test_medium_stale_K_hyperparameter_training(agp, precision, tol):
+    """The reference's stale-K_mm behaviour after update_hyperparameters! (quirk Q3, default of train) with 150 inducing points on a
+    jittered grid (K_mm nearly diagonal, so the reference's own K-tilde check survives the moving K_nm): the factor swap of
+    agp_hyper_grads (fresh K for the gradient, stale K back for the steps) at multi-tile sizes, fp64 and on the padded tcgen05 path."""
+    n, D, m, B, iters = 1200, 3, M_MED, 300, 8
+    X, y, _, mbs, F, rng = make_data("logistic", n, D, m, B, iters, seed=51)
+    X = X * 1.5
+    g = [np.array([a, b, c]) for a in np.linspace(-3.5, 3.5, 6) for b in np.linspace(-3, 3, 5) for c in np.linspace(-3, 3, 5)]
+    Z = np.array(g) + 0.05 * np.random.default_rng(2).standard_normal((m, 3))
+    s0, v0 = 1.5, 1.5
+    mo = O.SVGP(O.Kernel("sqexp", scale=s0, variance=v0), O.LogisticLikelihood(), O.AnalyticSVI(B), Z, optimiser=O.ADAM(0.01), Zoptimiser=O.ADAM(0.01))
+    mo.refresh_K_after_hyper = False
+    mo, so = O.train(mo, X, y, iters, minibatches=mbs)
+    mo, so = O.train(mo, X, y, 3, minibatches=mbs[:3], state=so)
+    me = agp.SVGP(v0 * agp.SqExponentialKernel() @ agp.ScaleTransform(s0), agp.LogisticLikelihood(), agp.AnalyticSVI(B), Z, optimiser=True,
+                  Zoptimiser=True, precision=precision)
+    me, se = agp.train(me, X, y, iters, minibatches=mbs)
+    me, se = agp.train(me, X, y, 3, minibatches=mbs[:3], state=se)
+    ko = mo.f[0].kernel
+    ptol = 1e-8 if precision == "f64" else 1e-3
+    assert abs(ko.scale - s0) > 1e-3
+    assert abs(me.kernel.scale - ko.scale) < ptol * ko.scale and abs(me.kernel.variance - ko.variance) < ptol * ko.variance
+    assert rel_fro(me.Z, mo.f[0].Z) < ptol
+    check_pair(agp, (mo, so), (me, se), tol)
