@@ -36,6 +36,8 @@ def main(raw, out_csv, out_json):
             # round 2: the two products with a pre-split right operand; inside one pipelined step V X^T (main stream) precedes V = K_nm L^-T
             key = ["gemm_v_sigma", "gemm_v"][ps_seen % 2]
             ps_seen += 1
+        elif "umma_gram_tn_kernel" in name:
+            key = "gemm_gram"          # Gram product straight from V (single-latent steps)
         elif "umma_gemm_nt_kernel" in name:
             if ps_seen:
                 key = "gemm_gram"      # with the pre-split kernel in use, the first-generation kernel only runs the Gram product

@@ -10,7 +10,7 @@ timeout 300 python bench.py --impl reference --steps 4 --warmup 1 > $OUT/bench_r
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 150 -c 210 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 14 --warmup 3 --graph 0 --timed-only > $OUT/ncu_launch.log 2>&1; echo "ncu launches rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on \
-    -k regex:'tail2_step_kernel|umma_gemm_nt_kernel|umma_gemm_ps_kernel|knm_umma_kernel|tail2_potf2_first_kernel|combine_kernel|scale_transpose_kernel|x_finalize|rowfinish' -s 60 -c 18 \
+    -k regex:'tail2_step_kernel|umma_gemm_nt_kernel|umma_gemm_ps_kernel|umma_gram_tn_kernel|knm_umma_kernel|tail2_potf2_first_kernel|combine_kernel|scale_transpose_kernel|x_finalize|rowfinish' -s 60 -c 18 \
     -o $OUT/prof python bench.py --steps 6 --warmup 3 --graph 0 --timed-only > $OUT/ncu_full.log 2>&1; echo "ncu full rc=$?"
 timeout 600 ncu --set full --clock-control none -k regex:'knm_umma_kernel' -s 4 -c 1 -o $OUT/prof_knm_1m python bench.py --predict --no-cpu-baseline > $OUT/ncu_knm.log 2>&1; echo "ncu knm rc=$?"
 ls -la $OUT
