@@ -26,8 +26,10 @@ def main():
     sc = 1.0 / np.sqrt(D)
     mbs = [rng.choice(n, B, replace=False).astype(np.int64) for _ in range(iters)]
     ok = True
-    for case in ("mosvgp", "logisticsoftmax"):
-        Q = 2 * world
+    # per_rank = 1: one latent per rank (BASELINE C4 at 8 GPUs): single launches (Gram product straight from V) beside the peer exchange;
+    # per_rank = 2: grouped launches + the persistent tail
+    for case, per_rank in (("mosvgp", 2), ("logisticsoftmax", 2), ("logisticsoftmax", 1), ("mosvgp", 1)):
+        Q = per_rank * world
         if case == "mosvgp":
             W = rng.standard_normal((D, Q))
             ys = [np.where(X @ W[:, t] + 0.1 * rng.standard_normal(n) >= 0, 1.0, -1.0) for t in range(Q)]
@@ -54,7 +56,10 @@ def main():
         errs = [max(rel_fro(mine[q][0], m1.posterior(q0 + q)[0]), rel_fro(mine[q][1], m1.posterior(q0 + q)[1])) for q in range(ql)]
         yp_1 = agp.predict_y(m1, X[:500])
         same_pred = all(np.array_equal(a, b) for a, b in zip(yp_s, yp_1)) if isinstance(yp_1, list) else np.array_equal(yp_s, yp_1)
-        good = max(errs) < 1e-9 and abs(e_s - e_1) <= 1e-9 * abs(e_1) and same_pred
+        # two or more latents per rank: the sharded and the unsharded model run the same grouped kernels (identical arithmetic); with
+        # one latent per rank the sharded ranks take the single-launch kernels, the unsharded model the grouped ones: 3xTF32 rounding
+        tol_same = 1e-9 if per_rank > 1 else 1e-4
+        good = max(errs) < tol_same and abs(e_s - e_1) <= (1e-9 if per_rank > 1 else 1e-5) * abs(e_1) and (same_pred or per_rank == 1)
         # (b) the fp64 oracle (every rank computes it: the check of rank r's latents must not depend on rank 0)
         X64 = X.astype(np.float64)
         if case == "mosvgp":
@@ -72,7 +77,7 @@ def main():
         good_all = bool(allres[:, 0].min() > 0.5 and allres[:, 1].min() > 0.5)
         ok = ok and good_all
         if rank == 0:
-            print(f"[{case}] world={world} peer={getattr(ms, '_peer', False)}: every rank vs unsharded engine: max rel err (mu, Sigma) {allres[:, 2].max():.2e}; "
+            print(f"[{case} x{per_rank}] world={world} peer={getattr(ms, '_peer', False)}: every rank vs unsharded engine: max rel err (mu, Sigma) {allres[:, 2].max():.2e}; "
                   f"vs fp64 oracle: {allres[:, 3].max():.2e}; ELBO {e_s:.6f} / engine {e_1:.6f} / oracle {e_o:.6f} -> {'OK' if good_all else 'MISMATCH'}", flush=True)
         dist.barrier()
     dist.destroy_process_group()
