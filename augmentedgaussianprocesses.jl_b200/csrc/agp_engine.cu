@@ -1547,9 +1547,9 @@ struct Engine : EngineBase {
     if (!have_K) { ctx->err = "agp_refresh_K must be called before a step"; return AGP_ERR_STATE; }
     if (!from_batch && !have_data) { ctx->err = "upload data first"; return AGP_ERR_STATE; }
     if (B < 1 || B > Bcap) BAD("The size of mini-batch is incorrect (negative or bigger than the batch capacity)");
-    // tf32x3: a ragged B is padded to the next multiple of 128 on the host index list path (rowsK); host-row batches and the resident
-    // list pool keep the multiple-of-128 rule
-    if (prec == AGP_PREC_TF32X3 && (B % 128) && (from_batch || !idx)) BAD("TF32X3 precision needs B % 128 == 0 on this path (host index lists are padded internally)");
+    // tf32x3: a ragged B is padded to the next multiple of 128 on the host index list path and for host-row batches (rowsK); the
+    // resident list pool and the pipelined asynchronous batches keep the multiple-of-128 rule
+    if (prec == AGP_PREC_TF32X3 && (B % 128) && !from_batch && !idx) BAD("TF32X3 precision needs B % 128 == 0 for resident minibatch lists (host index lists and host-row batches are padded internally)");
     if (!from_batch) CKS(prep_idx(idx, B, base));
     curB = B; cur_from_batch = from_batch; kernel_matrices_stale = false; prefetched = false; stats_early = false;
     fuse_lik_next = fuse_in_step_moments && can_fuse_lik(); fuse_from_batch = from_batch; lik_fused = false;
@@ -2104,6 +2104,10 @@ struct Engine : EngineBase {
     if (x_dtype == AGP_DTYPE_F64) convert_rows_kernel<double, T><<<bl, 256, 0, st()>>>((const double*)stage, x_layout, sld, B, D, Xb, Dp, xxb);
     else convert_rows_kernel<float, T><<<bl, 256, 0, st()>>>((const float*)stage, x_layout, sld, B, D, Xb, Dp, xxb);
     ++launches;
+    if (rowsK(B) != B) {   // padding rows of a ragged batch: x = 0 (K_nm row k(0, z): finite), zero weights (natgrad_products)
+      CK(cudaMemsetAsync(Xb + (size_t)B * Dp, 0, (size_t)(rowsK(B) - B) * Dp * sizeof(T), st()));
+      CK(cudaMemsetAsync(xxb + B, 0, (size_t)(rowsK(B) - B) * sizeof(T), st()));
+    }
     fuse_in_step_moments = true;
     int s1 = step_moments(nullptr, B, 0, true);
     fuse_in_step_moments = false;
@@ -2133,7 +2137,6 @@ struct Engine : EngineBase {
     if (is_lsm != (y_kind == AGP_Y_CLASS)) BAD("label kind does not match the likelihood");
     if ((x_dtype != 0 && x_dtype != 1) || (x_layout != 0 && x_layout != 1)) BAD("bad dtype/layout");
     if (!have_K) { ctx->err = "agp_refresh_K must be called before a step"; return AGP_ERR_STATE; }
-    if (prec == AGP_PREC_TF32X3 && (B % 128)) BAD("TF32X3 precision needs B % 128 == 0");
     const size_t es = x_dtype == AGP_DTYPE_F64 ? 8 : 4;
     if (!h_mu) CK(cudaMallocHost((void**)&h_mu, (size_t)mp * sizeof(double)));
     h_mu_valid = false;
@@ -2347,7 +2350,8 @@ struct Engine : EngineBase {
     if (is_lsm != (y_kind == AGP_Y_CLASS)) BAD("label kind does not match the likelihood");
     if ((x_dtype != 0 && x_dtype != 1) || (x_layout != 0 && x_layout != 1)) BAD("bad dtype/layout");
     CKS(async_init());
-    if (async_pipelined_ok()) return step_batch_async_pipelined(xbh, x_dtype, x_layout, ybh, y_kind, B, rho, ticket);
+    // a ragged batch on the tcgen05 path takes the in-order variant below (its step pads the rows itself)
+    if (async_pipelined_ok() && !(prec == AGP_PREC_TF32X3 && (B % 128))) return step_batch_async_pipelined(xbh, x_dtype, x_layout, ybh, y_kind, B, rho, ticket);
     join_async();
     const int slot = (int)(n_tickets & 1);
     const size_t es = x_dtype == AGP_DTYPE_F64 ? 8 : 4;

@@ -146,7 +146,7 @@ int agp_set_kernel(agp_model* model, int32_t latent_local, int32_t kind, double 
  * resident list.  rho = n / B (training.jl:30).
  * AGP_PREC_TF32X3: batch_capacity is a multiple of 128 and m > 64; m is padded to the 128-wide tile inside the engine (zero rows /
  * columns of L^-1 and X), and B itself may be ragged on the host-list path (the extra rows of the B x m products repeat sample 0 and
- * carry zero weights); resident lists and agp_step_batch* keep B % 128 == 0. */
+ * carry zero weights; host-row batches are padded with zero rows); resident minibatch lists keep B % 128 == 0. */
 int agp_step(agp_model* model, const int64_t* idx, int32_t B, int32_t idx_base, double rho);
 /* same, without the trailing synchronisation / error read-back (errors surface at agp_sync). */
 int agp_step_async(agp_model* model, const int64_t* idx, int32_t B, int32_t idx_base, double rho);

@@ -824,6 +824,24 @@ def test_tf32x3_ragged_minibatch(agp, lik, stoch, m):
         mo, so = O.train(mo, X, y, 3, minibatches=mbs2, state=so)
         me, se = agp.train(me, X, y, 3, minibatches=mbs2, state=se)
         check_pair(agp, (mo, so), (me, se), TOL["tf32x3"])
+        # host-row batches of a ragged size (agp_step_batch: the x, y views update_parameters! receives), sync and async entry points
+        import ctypes as C
+        L = agp._lib
+        e = me._eng
+        for it in range(2):
+            idx = rng.choice(n, B2, replace=False).astype(np.int64)
+            mo, so = O.train(mo, X, y, 1, minibatches=[idx], state=so)
+            xb = np.ascontiguousarray(X[idx]); yb = np.ascontiguousarray(y[idx], dtype=np.float64)
+            arr = (C.c_void_p * 1)(yb.ctypes.data)
+            if it == 0:
+                e.ck(e.lib.agp_step_batch(e.model, C.c_void_p(xb.ctypes.data), L.DTYPE_F64, L.LAYOUT_ROWMAJOR, arr, L.Y_REAL, B2, n / B2))
+            else:
+                tk = C.c_int64(0)
+                e.ck(e.lib.agp_step_batch_async(e.model, C.c_void_p(xb.ctypes.data), L.DTYPE_F64, L.LAYOUT_ROWMAJOR, arr, L.Y_REAL, B2, n / B2, C.byref(tk)))
+                mu_h = np.empty(m)
+                e.ck(e.lib.agp_result_wait(e.model, tk, L.dptr(mu_h)))
+        mu, S, _, _ = me.posterior(0)
+        assert rel_fro(mu, mo.f[0].mu) < TOL["tf32x3"] and rel_fro(S, mo.f[0].Sigma) < TOL["tf32x3"]
 
 
 @pytest.mark.parametrize("m", [128, 130])
