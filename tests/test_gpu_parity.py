@@ -973,3 +973,21 @@ def test_medium_stale_K_hyperparameter_training(agp, precision, tol):
     assert abs(me.kernel.scale - ko.scale) < ptol * ko.scale and abs(me.kernel.variance - ko.variance) < ptol * ko.variance
     assert rel_fro(me.Z, mo.f[0].Z) < ptol
     check_pair(agp, (mo, so), (me, se), tol)
+
+
+@pytest.mark.parametrize("D", [129, 300])
+def test_tf32x3_input_dimension_above_the_knm_kernel_limit(agp, D):
+    """D > 128: the tcgen05 K_nm kernel does not apply (its x.z product holds at most four 32-wide k-blocks); the tensor-core step then
+    builds K_nm with the SIMT kernel and keeps tcgen05 for the three B x m x m products - with a padded m = 200 and a ragged B = 200."""
+    n, m, B, iters = 900, 200, 200, 4
+    X, y, Z, mbs, F, rng = make_data("logistic", n, D, m, B, iters, seed=61)
+    sc = 1.0 / np.sqrt(D)
+    mo = O.SVGP(oracle_kernel(O, "matern52", sc, 1.3), O.LogisticLikelihood(), O.AnalyticSVI(B), Z)
+    mo, so = O.train(mo, X, y, iters, minibatches=mbs)
+    me = agp.SVGP(engine_kernel(agp, "matern52", sc, 1.3), agp.LogisticLikelihood(), agp.AnalyticSVI(B), Z)
+    me, se = agp.train(me, X, y, iters, minibatches=mbs)
+    assert me.precision == "tf32x3"
+    check_pair(agp, (mo, so), (me, se), TOL["tf32x3"])
+    mu_o, var_o = O.predict_f(mo, X[:50], cov=True)
+    mu_e, var_e = agp.predict_f(me, X[:50], cov=True)
+    assert rel_fro(mu_e, mu_o) < TOL["tf32x3"] and rel_fro(var_e, var_o) < 10 * TOL["tf32x3"]
