@@ -1780,9 +1780,14 @@ struct Engine : EngineBase {
   }
 
   // fused blocked Cholesky + inverse of the factor: P (lower tiles, destroyed) -> Xv = chol(P)^-1, for latents [q0, q0 + count)
+  // Block steps of the m x m tail: the 64-wide blocks that hold rows of the logical matrix.  mp is padded to a power-of-two number of
+  // blocks for the recursive inverse of refresh_K (spd_inverse); the padding blocks of P_v are identity and stay out of the tail (their
+  // factor is the identity, their pivots add log 1 to the log-determinant, and nothing reads the rows of X beyond m): m = 640 runs 10
+  // block steps instead of 16.
+  int nblk_tail() const { return (m + TNB - 1) / TNB; }
   // tail_variant 3: one persistent launch per group of latents (agp_tail3.cuh); otherwise nblk + 1 launches per latent
   int tail3_ctas(int count) const {      // CTAs the persistent tail of `count` latents occupies (first launch)
-    const int nblk = mp / TNB;
+    const int nblk = nblk_tail();
     if (nblk == 1) return std::min(count, t3_sm_budget);
     const int nl = std::min(count, std::max(1, t3_sm_budget / 4));
     return nl * std::max(2, std::min(tail3_team(nblk), t3_sm_budget / nl));
@@ -1793,7 +1798,7 @@ struct Engine : EngineBase {
   void chol_inv_many(int q0, int count) {
     if (tail_variant != 3) { for (int q = q0; q < q0 + count; ++q) chol_inv(lat[q]); return; }
     ph_begin(PH_CHOL);
-    const int nblk = mp / TNB;
+    const int nblk = nblk_tail();
     const int gcap = tail3_team(nblk);
     int done = 0;
     while (done < count) {
@@ -1816,7 +1821,7 @@ struct Engine : EngineBase {
     if (tail_variant == 3) { chol_inv_many((int)(&L - lat.data()), 1); return; }
     ph_begin(PH_CHOL);
     TailStepParams tp{};
-    tp.P = L.P; tp.W = L.W; tp.Xout = L.Xv; tp.Dinv = L.Dinv; tp.ld = mp; tp.nblk = mp / TNB; tp.logdet = L.logdetP; tp.status = status;
+    tp.P = L.P; tp.W = L.W; tp.Xout = L.Xv; tp.Dinv = L.Dinv; tp.ld = mp; tp.nblk = nblk_tail(); tp.logdet = L.logdetP; tp.status = status;
     if (tail_variant == 0) tail_potf2_first_kernel<0><<<1, TAIL_THREADS, TAIL_SMEM, st()>>>(tp);
     else if (chain_variant == 0) launch_tail2(tail2_potf2_first_kernel<0, 0>, 1, tp);
     else launch_tail2(tail2_potf2_first_kernel<0, 1>, 1, tp);

@@ -991,3 +991,20 @@ def test_tf32x3_input_dimension_above_the_knm_kernel_limit(agp, D):
     mu_o, var_o = O.predict_f(mo, X[:50], cov=True)
     mu_e, var_e = agp.predict_f(me, X[:50], cov=True)
     assert rel_fro(mu_e, mu_o) < TOL["tf32x3"] and rel_fro(var_e, var_o) < 10 * TOL["tf32x3"]
+
+
+@pytest.mark.parametrize("lik,precision", [("logistic", "f64"), ("logisticsoftmax", "f64"), ("logistic", "tf32x3"), ("logisticsoftmax", "tf32x3")])
+def test_block_count_not_a_power_of_two(agp, lik, precision):
+    """m = 320: five 64-wide blocks of logical rows inside matrices padded to eight (the recursive inverse of refresh_K needs a power of
+    two); the tail runs five block steps and leaves the identity padding alone - multi-launch chain (one latent) and persistent tail
+    (three latents), fp64 and the tcgen05 path (m padded to 384 columns there).  Posterior, ELBO (log-determinants), predictions."""
+    n, D, m, B, iters = 1500, 4, 320, 256, 4
+    # scale 1.2 (length scale 0.83 in four dimensions): K_mm of 320 inducing points stays well conditioned, so the canonical natural
+    # parameters check_pair also compares (eta = Sigma^-1 mu amplifies rounding by cond K) are meaningful in the 3xTF32 mode too
+    oracle, engine, (X, y, F) = run_pair(agp, lik, precision, n=n, D=D, m=m, B=B, iters=iters, seed=71, scale=1.2)
+    check_pair(agp, oracle, engine, TOL[precision])
+    (mo, so), (me, se) = oracle, engine
+    mu_o, var_o = O.predict_f(mo, X[:60], cov=True)
+    mu_e, var_e = agp.predict_f(me, X[:60], cov=True)
+    assert rel_fro(np.atleast_2d(np.asarray(mu_e)), np.atleast_2d(mu_o)) < 10 * TOL[precision]
+    assert rel_fro(np.atleast_2d(np.asarray(var_e)), np.atleast_2d(var_o)) < 10 * TOL[precision]
