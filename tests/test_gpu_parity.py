@@ -1008,3 +1008,28 @@ def test_block_count_not_a_power_of_two(agp, lik, precision):
     mu_e, var_e = agp.predict_f(me, X[:60], cov=True)
     assert rel_fro(np.atleast_2d(np.asarray(mu_e)), np.atleast_2d(mu_o)) < 10 * TOL[precision]
     assert rel_fro(np.atleast_2d(np.asarray(var_e)), np.atleast_2d(var_o)) < 10 * TOL[precision]
+
+
+@pytest.mark.parametrize("lik", ["gaussian", "logistic", "studentt", "logisticsoftmax", "laplace", "bayesiansvm", "negbinomial", "poisson", "heteroscedastic"])
+def test_medium_all_likelihoods_default_precision(agp, lik):
+    """Every AnalyticVI likelihood with the DEFAULT precision ("auto" -> tcgen05 for m = 150, padded to 256 columns; B = 300 padded to
+    384 rows): stochastic steps, then the ELBO and predict_y / proba_y, against the oracle at the tf32x3 tolerance."""
+    n, D, m, B, iters = 1200, 3, M_MED, 300, 5
+    X, y, Z, mbs, F, rng = make_data(lik, n, D, m, B, iters, seed=81)
+    mo = O.SVGP(oracle_kernel(O, "sqexp", 1.2, 1.0), oracle_lik(O, lik), O.AnalyticSVI(B), Z)
+    mo, so = O.train(mo, X, y, iters, minibatches=mbs)
+    me = agp.SVGP(engine_kernel(agp, "sqexp", 1.2, 1.0), engine_lik(agp, lik), agp.AnalyticSVI(B), Z)
+    me, se = agp.train(me, X, y, iters, minibatches=mbs)
+    assert me.precision == "tf32x3"
+    check_pair(agp, (mo, so), (me, se), TOL["tf32x3"])
+    yo, ye = O.predict_y(mo, X[:200]), agp.predict_y(me, X[:200])
+    if lik in ("logistic", "bayesiansvm", "logisticsoftmax"):
+        assert np.mean(np.asarray(ye) != np.asarray(yo)) <= 0.01          # labels (a sample on a decision boundary may flip)
+    else:
+        assert rel_fro(np.asarray(ye, dtype=np.float64), np.asarray(yo, dtype=np.float64)) < 20 * TOL["tf32x3"]
+    po, pe = O.proba_y(mo, X[:200]), agp.proba_y(me, X[:200])
+    if isinstance(po, tuple):
+        for a, b in zip(pe, po):
+            assert rel_fro(np.asarray(b, dtype=np.float64), np.asarray(a, dtype=np.float64)) < 50 * TOL["tf32x3"]
+    else:
+        assert rel_fro(np.asarray(pe, dtype=np.float64), np.asarray(po, dtype=np.float64)) < 50 * TOL["tf32x3"]
