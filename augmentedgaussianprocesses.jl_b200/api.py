@@ -11,6 +11,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import math
+import warnings
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
@@ -481,6 +482,9 @@ class AbstractGPModel:
             # least 128 inducing points takes the tensor-core path; smaller ones (e.g. the reference's 10-inducing-point tests) would
             # mostly multiply padding and take the fp32 SIMT path
             self.precision = "tf32x3" if self.m >= 128 else "f32"
+            by_cond = getattr(self, "_precision_by_condition", None)
+            if by_cond is not None:         # train() found K_mm too ill conditioned for the faster path (amplification())
+                self.precision = by_cond
         if self.precision == "tf32x3":
             cap = (cap + 127) // 128 * 128
         self._eng = _Engine(self._desc(cap), self.device, self.stream)
@@ -539,6 +543,19 @@ class AbstractGPModel:
         t, c = C.c_int64(), C.c_int64()
         e.ck(e.lib.agp_get_counters(e.model, C.byref(t), C.byref(c)))
         return t.value, c.value
+
+    def amplification(self) -> float:
+        """sqrt(max_q variance_q * ||K_q^-1||_inf) over the owned latents, read from the engine's fp64 K_mm^-1 (agp_get_Kinv; needs
+        agp_refresh_K).  V = K_nm L^-T multiplies the rounding error of the fp32-class K_nm entries (relative to the kernel variance) by
+        ||L^-1||_2 = sqrt(||K^-1||_2) <= sqrt(||K^-1||_inf): the whitened iteration loses about log10 of this figure in digits on the
+        fp32 / 3xTF32 paths, nothing in fp64."""
+        e, m, amp = self._eng, self.m, 0.0
+        Kinv, ld = np.empty((m, m)), C.c_double()
+        for q in range(self.n_latent_local):
+            e.ck(e.lib.agp_get_Kinv(e.model, q, L.dptr(Kinv), C.byref(ld)))
+            k = self.kernels[self._latent_range()[0] + q]
+            amp = max(amp, math.sqrt(float(k.variance) * float(np.abs(Kinv).sum(axis=1).max())))
+        return amp
 
     def launch_count(self) -> int:
         return int(self._eng.lib.agp_launch_count(self._eng.model)) if self._eng else 0
@@ -925,6 +942,14 @@ class State:
 # --------------------------------------------------------------------------------------------------
 # train!  (training/training.jl:13-111)
 # --------------------------------------------------------------------------------------------------
+# precision="auto": the largest error amplification sqrt(variance ||K_mm^-1||_inf) (AbstractGPModel.amplification) each path keeps; a fresh
+# train() call moves a model above it to the next path.  Calibrated with tools/shape_sweep.py on a B200 (profiles/r2/shape_sweep/): relative
+# error of mu / Sigma / ELBO / predictions against the fp64 oracle <= 2e-5 x amplification on the 3xTF32 tensor-core path (the tensor
+# cores' truncating fp32 accumulation over long sums of cancelling terms), <= 2e-6 x on the fp32 CUDA-core path; targets 5e-4 / 2e-4 as
+# in the parity tests.
+AMPLIFICATION_LIMIT = (("tf32x3", 30.0), ("f32", 100.0), ("f64", float("inf")))
+
+
 def _wrap_y(model, y):
     if isinstance(model, (MOSVGP, MOVGP)):
         if len(y) != model.n_task:
@@ -997,6 +1022,7 @@ def train(model: AbstractGPModel, X=None, y=None, iterations: int = 100, *, call
     model._data_refs = (X, ys)   # keep the keyed arrays alive: a freed array's id() can be reused by a new one
     lib = eng.lib
     eng.ck(lib.agp_keep_stale_K(eng.model, 0 if refresh_K_after_hyper else 1))
+    fresh = state is None
     if state is None:
         inf.HyperParametersUpdated = True
         eng.ck(lib.agp_state_reset(eng.model))
@@ -1004,6 +1030,26 @@ def train(model: AbstractGPModel, X=None, y=None, iterations: int = 100, *, call
     if inf.HyperParametersUpdated:
         eng.ck(lib.agp_refresh_K(eng.model))  # compute_K, once per train! call (training.jl:41-43, Q3)
         inf.HyperParametersUpdated = False
+        if fresh and model.world == 1 and model.precision_requested == "auto" and model.precision != "f64" \
+                and os.environ.get("AGP_COND_SWITCH", "1") != "0":
+            amp = model.amplification()
+            want = next(p for p, lim in AMPLIFICATION_LIMIT if amp <= lim and not (p == "tf32x3" and model.precision == "f32"))
+            if want != model.precision:
+                # precision="auto" promises the reference's (fp64) results to the tolerances of the parity tests: the fp32-class paths lose
+                # ~log10(amp) digits in V = K_nm L^-T, the tensor-core accumulation more than the CUDA-core one
+                warnings.warn(f"K_mm is ill conditioned (error amplification {amp:.1e}): precision='auto' moves this model from the "
+                              f"{model.precision} to the {want} path; pass precision='{model.precision}' to keep the faster one",
+                              RuntimeWarning, stacklevel=2)
+                model._precision_by_condition = want
+                model._eng.close()
+                model._eng = None
+                eng = model._engine(B)
+                lib = eng.lib
+                _upload(model, eng, X, ys, (id(X), tuple(id(v) for v in ys), X.shape))
+                eng.ck(lib.agp_keep_stale_K(eng.model, 0 if refresh_K_after_hyper else 1))
+                eng.ck(lib.agp_state_reset(eng.model))
+                state = State(model)
+                eng.ck(lib.agp_refresh_K(eng.model))
     state.B = B
     rng = rng or np.random.default_rng()
     full = np.arange(n, dtype=np.int64) if not inf.stoch else None

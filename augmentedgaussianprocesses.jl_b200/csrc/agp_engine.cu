@@ -165,7 +165,7 @@ struct Engine : EngineBase {
     double *P = nullptr, *X = nullptr, *W = nullptr;  // tail workspaces [mp][mp]
     double* logdetP = nullptr;                        // device scalars: [0] logdet P_v, [1] scratch for K
     UmmaLatent um;                                    // tcgen05 path
-    UmmaKnm uk; bool knm_tc = false;                  // tcgen05 K_nm construction (D <= 128)
+    UmmaKnm uk; bool knm_tc = false;                  // tcgen05 K_nm construction (16 < D <= 128)
     int gram_splits = 1;                              // split-K partials of the last Gram product
     // OnlineSVGP carry-over (agp_online_carry): whitened offsets of the natural gradient + what extraKL needs
     bool online = false; int on_ma = 0;
@@ -406,7 +406,10 @@ struct Engine : EngineBase {
       if (prec == AGP_PREC_TF32X3)
         CKS(umma_latent_alloc(ctx_err(), L.um, mk, (int)ldm, Bcap, (const float*)(const void*)L.Knm, (const float*)(const void*)L.V,
                               (const float*)(const void*)L.Linv_T, (const float*)(const void*)L.Xv_T, st()));
-      if (prec == AGP_PREC_TF32X3 && umma_knm_shape_ok(mk, Bcap, D) && !getenv("AGP_KNM_SIMT")) {
+      // D <= 16: K_nm from the coordinate differences on the CUDA cores (one 16-deep k-block of gemm_simt_kernel, a few us) instead of
+      // |x|^2 + |z|^2 - 2 x.z on the tensor cores: low-dimensional inputs are where K_mm is ill conditioned, and V = K_nm L^-T amplifies
+      // the absolute error of the product form by sqrt(cond K_mm) (tools/shape_sweep.py: D = 1..3, m ~ 500, cond 1e6).
+      if (prec == AGP_PREC_TF32X3 && umma_knm_shape_ok(mk, Bcap, D) && (D > 16 || getenv("AGP_KNM_TC_SMALL_D")) && !getenv("AGP_KNM_SIMT")) {
         CKS(umma_knm_setup(ctx_err(), L.uk, (const float*)(const void*)L.Z, Dp, mk, D, (float*)(void*)L.Knm, ldm, Bcap, st()));
         L.knm_tc = true;
       }
@@ -2685,7 +2688,7 @@ struct Engine : EngineBase {
         if (L.knm_tc)
           rc = umma_knm(ctx_err(), L.uk, (const float*)(const void*)X, Dp, Dp, idx_pool + ((c[1] + r) % n_lists) * B,
                         (const float*)(const void*)(xxr + (size_t)r * B), (const float*)(const void*)L.zz, B, L.kind, L.scale * L.scale, L.variance, st());
-        else { ctx->err = "K_nm tensor-core kernel not active (D > 128)"; rc = AGP_ERR_STATE; }
+        else { ctx->err = "K_nm tensor-core kernel not active (D > 128 or D <= 16)"; rc = AGP_ERR_STATE; }
       } else if (which == 1 || which == 2) {
         UmmaEpilogue ep{};
         ep.mode = which == 1 ? UMMA_EPI_STORE_SUMSQ : UMMA_EPI_STATS_ONLY;

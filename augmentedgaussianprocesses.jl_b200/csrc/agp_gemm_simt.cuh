@@ -33,9 +33,12 @@ struct GemmParams {
   int lower_only;            // skip tiles that lie strictly above the diagonal
   int k_from_diag;           // TN product of lower-triangular factors: start k at max(row0, col0)
   int k_to_diag;             // NT with a lower-triangular B ([N][K], zero for k > n): stop k at the tile's last column
-  // EPI_KERNELFN: C = variance * base(scale2 * (xx[row] + zz[col] - 2 acc))
-  const T* xx; const T* zz; double scale2, variance; int kernel_kind;
-  int xx_direct;             // 1: xx is already gathered (indexed by the logical row), 0: indexed through a_gather
+  // EPI_KERNELFN: the k-loop accumulates sum_k (a_k - b_k)^2 instead of the product, C = variance * base(scale2 * acc).
+  // (The differences keep a relative rounding error on the squared distance; |x|^2 + |z|^2 - 2 x.z has an absolute one of
+  // eps (|x|^2 + |z|^2), which V = K_nm L^-T amplifies by sqrt(cond K_mm) - the tcgen05 K_nm kernel accepts that for D > 16.)
+  const T* xx; const T* zz;  // unused by this kernel since the difference form (kept: callers fill them for the tcgen05 path)
+  double scale2, variance; int kernel_kind;
+  int xx_direct;
 };
 
 __device__ __forceinline__ float kfn_eval(int kind, float d2, float var) {
@@ -189,7 +192,14 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmParams<T> p) {
 #pragma unroll
         for (int i = 0; i < TM; ++i)
 #pragma unroll
-          for (int j = 0; j < TN; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+          for (int j = 0; j < TN; ++j) {
+            if constexpr (EPI == EPI_KERNELFN) {   // squared distance from the differences: relative, not absolute, rounding error
+              T d = a[i] - b[j];
+              acc[i][j] = fma(d, d, acc[i][j]);
+            } else {
+              acc[i][j] = fma(a[i], b[j], acc[i][j]);
+            }
+          }
       }
       __syncthreads();
       if (more) { store_a(); store_b(); }
@@ -203,11 +213,6 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmParams<T> p) {
   for (int i = 0; i < TM; ++i) {
     int row = bm + (i / W) * (BM / 2) + ty * W + (i % W);
     if (row >= p.M) continue;
-    T xr = T(0);
-    if constexpr (EPI == EPI_KERNELFN) {
-      int64_t prow = (p.a_gather && !p.xx_direct) ? p.a_gather[row] : (int64_t)row;
-      xr = p.xx[prow];
-    }
 #pragma unroll
     for (int jc = 0; jc < 2; ++jc) {
       int col0 = bn + jc * (BN / 2) + tx * W;
@@ -217,8 +222,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmParams<T> p) {
         T v = acc[i][jc * W + j];
         int col = col0 + j;
         if constexpr (EPI == EPI_KERNELFN) {
-          T zc = (col < p.N) ? p.zz[col] : T(0);
-          T d2 = (T)p.scale2 * (xr + zc - T(2) * v);
+          T d2 = (T)p.scale2 * v;
           v = kfn_eval(p.kernel_kind, d2, (T)p.variance);
         } else {
           v = alpha * v;

@@ -365,11 +365,15 @@ def test_pipelined_pool_steps_match_host_list_steps(agp, precision, m, B):
         assert mdl.counters() == (iters + 1, iters - 1)
 
 
-@pytest.mark.parametrize("D,kind", [(8, "sqexp"), (32, "sqexp"), (64, "matern32"), (100, "matern52"), (128, "sqexp")])
-def test_knm_tensor_core_kernel(agp, D, kind):
+@pytest.mark.parametrize("D,kind,force_tc", [(8, "sqexp", True), (8, "sqexp", False), (3, "matern52", False), (24, "sqexp", False), (32, "sqexp", False),
+                                             (64, "matern32", False), (100, "matern52", False), (128, "sqexp", False)])
+def test_knm_tensor_core_kernel(agp, D, kind, force_tc, monkeypatch):
     """K_nm construction on tcgen05 (agp_knm.cu: gathered rows -> TMEM, pre-split Z by TMA, 3xTF32, TMA store) against
     the oracle's kernelmatrix (latentgp.jl:210) on the same gathered minibatch.  Tolerance: fp32 rounding of the
-    GEMM-form squared distance, |x|^2 + |z|^2 - 2 x.z ~ 2 D, scaled by 1/D in the exponent -> 2e-6 absolute on k in [0, var]."""
+    GEMM-form squared distance, |x|^2 + |z|^2 - 2 x.z ~ 2 D, scaled by 1/D in the exponent -> 2e-6 absolute on k in [0, var].
+    D <= 16 takes the difference-form CUDA-core kernel inside a tcgen05 model unless AGP_KNM_TC_SMALL_D is set (force_tc)."""
+    if force_tc:
+        monkeypatch.setenv("AGP_KNM_TC_SMALL_D", "1")
     n, m, B = 2048, 256, 512
     variance = 1.7
     (mo, so), (me, se), _ = run_pair(agp, "gaussian", "tf32x3", n=n, D=D, m=m, B=B, iters=1, kind=kind, variance=variance, seed=5)
@@ -798,11 +802,12 @@ def test_testconv_thresholds_engine(agp, lik, problem, shape):
 
 @pytest.mark.parametrize("m", [128, 200])
 @pytest.mark.parametrize("lik,stoch", [("logistic", True), ("studentt", False), ("logisticsoftmax", True)])
-def test_tf32x3_ragged_minibatch(agp, lik, stoch, m):
+def test_tf32x3_ragged_minibatch(agp, lik, stoch, m, monkeypatch):
     """Minibatch sizes that are not multiples of the 128-row tensor-core tile (B = 200, full batch n = 700) on the tcgen05 path: the
     engine pads the rows of the B x m products itself (the extra rows repeat sample 0 and carry zero weights), so precision "auto"
     keeps the fast path for any B and any m >= 128 (m = 200 runs as 256 columns with zero rows / columns of L^-1 and X).  Single-latent (Gram straight from V) and multi-latent (grouped
     launches) steps, stochastic and full-batch, against the oracle at the tf32x3 tolerance; prediction and ELBO afterwards."""
+    monkeypatch.setenv("AGP_COND_SWITCH", "0")   # this test pins the tensor-core path; the conditioning policy of precision="auto" has its own test
     n, D, B, iters = 700, 5, 200, 6    # m = 200: padded to 256 columns inside the engine (zero rows / columns of L^-1 and X)
     X, y, Z, mbs, F, rng = make_data(lik, n, D, m, B, iters, seed=21)
     sc = 1.0 / np.sqrt(D)
@@ -845,11 +850,12 @@ def test_tf32x3_ragged_minibatch(agp, lik, stoch, m):
 
 
 @pytest.mark.parametrize("m", [128, 130])
-def test_tf32x3_padded_hyperparameter_training(agp, m):
+def test_tf32x3_padded_hyperparameter_training(agp, m, monkeypatch):
     """update_hyperparameters! (kernel scale / variance and the inducing points by ADAM, autotuning.jl:86-140) on the tcgen05 path with a
     padded model (m = 130 -> 256 columns, B = 200 -> 256 rows): set_Z / the re-split of Z for the K_nm kernel / refresh_K must keep the
     padding rows and columns zero.  K_mm is refactorised after every update (refresh_K_after_hyper) so that the run stays away from the
     reference's own `K̃ has negative values` error with 130 inducing points in 4 dimensions; m = 128 is the same run without padding of m."""
+    monkeypatch.setenv("AGP_COND_SWITCH", "0")   # this test pins the tensor-core path; the conditioning policy of precision="auto" has its own test
     n, D, B, iters = 800, 4, 200, 7
     X, y, Z, mbs, F, rng = make_data("logistic", n, D, m, B, iters, seed=31)
     s0, v0 = 1.5, 1.2     # short length scale: K_mm well conditioned, K-tilde of the fp32-class contractions stays far from zero
@@ -976,9 +982,10 @@ def test_medium_stale_K_hyperparameter_training(agp, precision, tol):
 
 
 @pytest.mark.parametrize("D", [129, 300])
-def test_tf32x3_input_dimension_above_the_knm_kernel_limit(agp, D):
+def test_tf32x3_input_dimension_above_the_knm_kernel_limit(agp, D, monkeypatch):
     """D > 128: the tcgen05 K_nm kernel does not apply (its x.z product holds at most four 32-wide k-blocks); the tensor-core step then
     builds K_nm with the SIMT kernel and keeps tcgen05 for the three B x m x m products - with a padded m = 200 and a ragged B = 200."""
+    monkeypatch.setenv("AGP_COND_SWITCH", "0")   # this test pins the tensor-core path; the conditioning policy of precision="auto" has its own test
     n, m, B, iters = 900, 200, 200, 4
     X, y, Z, mbs, F, rng = make_data("logistic", n, D, m, B, iters, seed=61)
     sc = 1.0 / np.sqrt(D)
@@ -1011,9 +1018,10 @@ def test_block_count_not_a_power_of_two(agp, lik, precision):
 
 
 @pytest.mark.parametrize("lik", ["gaussian", "logistic", "studentt", "logisticsoftmax", "laplace", "bayesiansvm", "negbinomial", "poisson", "heteroscedastic"])
-def test_medium_all_likelihoods_default_precision(agp, lik):
+def test_medium_all_likelihoods_default_precision(agp, lik, monkeypatch):
     """Every AnalyticVI likelihood with the DEFAULT precision ("auto" -> tcgen05 for m = 150, padded to 256 columns; B = 300 padded to
     384 rows): stochastic steps, then the ELBO and predict_y / proba_y, against the oracle at the tf32x3 tolerance."""
+    monkeypatch.setenv("AGP_COND_SWITCH", "0")   # this test pins the tensor-core path; the conditioning policy of precision="auto" has its own test
     n, D, m, B, iters = 1200, 3, M_MED, 300, 5
     X, y, Z, mbs, F, rng = make_data(lik, n, D, m, B, iters, seed=81)
     mo = O.SVGP(oracle_kernel(O, "sqexp", 1.2, 1.0), oracle_lik(O, lik), O.AnalyticSVI(B), Z)
@@ -1033,3 +1041,46 @@ def test_medium_all_likelihoods_default_precision(agp, lik):
             assert rel_fro(np.asarray(b, dtype=np.float64), np.asarray(a, dtype=np.float64)) < 50 * TOL["tf32x3"]
     else:
         assert rel_fro(np.asarray(pe, dtype=np.float64), np.asarray(po, dtype=np.float64)) < 50 * TOL["tf32x3"]
+
+
+def test_auto_precision_follows_conditioning(agp):
+    """precision="auto" on an ill-conditioned K_mm (486 inducing points on a line, SqExponential: cond ~ 1e6; a failing draw of
+    tools/shape_sweep.py): V = K_nm L^-T amplifies the rounding of the fp32-class paths by sqrt(variance ||K_mm^-1||), so train() warns and
+    moves the model down the list of api.AMPLIFICATION_LIMIT until the oracle tolerance holds; an explicit precision is never overridden
+    (and then misses that tolerance - the reason for the policy); a well-conditioned model of the same size stays on the tensor cores."""
+    import warnings as W
+    from agp_b200.api import AMPLIFICATION_LIMIT
+    n, D, m, iters = 1149, 1, 486, 3
+    X, y, Z, mbs, F, rng = make_data("poisson", n, D, m, n, iters, seed=1234)
+    mo = O.SVGP(oracle_kernel(O, "sqexp", 3.0, 1.2), oracle_lik(O, "poisson"), O.AnalyticVI(), Z)
+    mo, so = O.train(mo, X, y, iters)
+    with pytest.warns(RuntimeWarning, match="ill conditioned"):
+        me = agp.SVGP(engine_kernel(agp, "sqexp", 3.0, 1.2), engine_lik(agp, "poisson"), agp.AnalyticVI(), Z)
+        me, se = agp.train(me, X, y, iters)
+    amp = me.amplification()
+    want = next(p for p, lim in AMPLIFICATION_LIMIT if amp <= lim)
+    assert amp > AMPLIFICATION_LIMIT[0][1] and me.precision == want and want in ("f32", "f64"), (amp, me.precision)
+    tol = {"f32": 2e-4, "f64": 1e-7}[want]
+    mu, S, _, _ = me.posterior(0)
+    assert rel_fro(mu, mo.f[0].mu) < tol and rel_fro(S, mo.f[0].Sigma) < tol, (rel_fro(mu, mo.f[0].mu), rel_fro(S, mo.f[0].Sigma))
+    eo, ee = mo.ELBO(so, so["y_batch"]), agp.ELBO(me, se)
+    assert abs(ee - eo) < 5 * tol * max(1.0, abs(eo))
+    # a second fresh train() call keeps the path found (no second warning, no second engine)
+    eng0 = me._eng
+    with W.catch_warnings():
+        W.simplefilter("error")
+        me, se = agp.train(me, X, y, 1)
+    assert me._eng is eng0 and me.precision == want
+    # explicit precision: no override
+    with W.catch_warnings():
+        W.simplefilter("error")
+        mt = agp.SVGP(engine_kernel(agp, "sqexp", 3.0, 1.2), engine_lik(agp, "poisson"), agp.AnalyticVI(), Z, precision="tf32x3")
+        mt, st = agp.train(mt, X, y, iters)
+    assert mt.precision == "tf32x3"
+    # well conditioned (length scale far below the spacing in eight dimensions): stays on the tensor-core path, silently
+    X8, y8, Z8, _, _, _ = make_data("poisson", 1200, 8, 256, 1200, 2, seed=5)
+    with W.catch_warnings():
+        W.simplefilter("error")
+        m8 = agp.SVGP(engine_kernel(agp, "sqexp", 1.0, 1.0), engine_lik(agp, "poisson"), agp.AnalyticVI(), Z8)
+        m8, s8 = agp.train(m8, X8, y8, 2)
+    assert m8.precision == "tf32x3" and m8.amplification() <= AMPLIFICATION_LIMIT[0][1]
