@@ -29,6 +29,7 @@ mutable struct Engine
     ctx::Ptr{Cvoid}
     model::Ptr{Cvoid}
     uploaded::UInt   # objectid of the data parent currently resident
+    fresh::Bool      # no step taken yet (the conditioning policy may still rebuild the engine at another precision)
 end
 
 function check(e::Engine, rc::Cint)
@@ -40,6 +41,12 @@ function check(e::Engine, rc::Cint)
 end
 
 const ENGINES = IdDict{Any,Engine}()
+function release!(model)
+    e = pop!(ENGINES, model)
+    ccall((:agp_model_destroy, LIB), Cvoid, (Ptr{Cvoid},), e.model)
+    ccall((:agp_ctx_destroy, LIB), Cvoid, (Ptr{Cvoid},), e.ctx)
+    return nothing
+end
 
 lik_code(::AGP.GaussianLikelihood) = (Int32(0))
 lik_code(::AGP.BernoulliLikelihood{<:AGP.LogisticLink}) = Int32(1)
@@ -70,12 +77,37 @@ end
 # tcgen05 (tf32x3 = 2) needs a batch CAPACITY that is a multiple of 128 and more than 64 inducing points (the engine pads m and a ragged
 # minibatch of the host index list path itself); small models (the reference's own tests use 10 inducing points,
 # test/testingtools.jl:66) take the fp32 SIMT path (1).  AGP_B200_PRECISION = f64 | f32 | tf32x3 overrides.
-function precision_code(m::Int, B::Int)
+function precision_code(m::Int, B::Int, model = nothing)
     p = get(ENV, "AGP_B200_PRECISION", "auto")
     p == "f64" && return Int32(0); p == "f32" && return Int32(1); p == "tf32x3" && return Int32(2)
+    haskey(PRECISION_BY_CONDITION, model) && return PRECISION_BY_CONDITION[model]
     return m >= 128 ? Int32(2) : Int32(1)
 end
-batch_capacity(m::Int, B::Int) = precision_code(m, B) == 2 ? cld(B, 128) * 128 : B
+batch_capacity(m::Int, B::Int, model = nothing) = precision_code(m, B, model) == 2 ? cld(B, 128) * 128 : B
+
+# The same conditioning policy as the Python host layer (api.AMPLIFICATION_LIMIT, DESIGN section 3): after the first agp_refresh_K the
+# error amplification sqrt(variance ||K_mm^-1||_inf) decides whether the model keeps the tcgen05 path (<= 30), moves to the fp32
+# CUDA-core path (<= 100) or to the fp64 path.  Returns true when the engine has to be rebuilt.
+const PRECISION_BY_CONDITION = IdDict{Any,Int32}()
+function amplification(model, e)
+    m = AGP.dim(model.f[1]); Kinv = zeros(m, m); ld = Ref(0.0); amp = 0.0
+    for (q, gp) in enumerate(model.f)
+        check(e, ccall((:agp_get_Kinv, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Ref{Float64}), e.model, q - 1, Kinv, ld))
+        amp = max(amp, sqrt(kernel_params(AGP.kernel(gp))[3] * maximum(sum(abs, Kinv; dims = 1))))
+    end
+    return amp
+end
+function conditioning_switch!(model, e, m::Int, B::Int)
+    get(ENV, "AGP_B200_PRECISION", "auto") == "auto" || return false
+    cur = precision_code(m, B, model)
+    cur == 0 && return false
+    amp = amplification(model, e)
+    want = amp <= 30 && cur == 2 ? Int32(2) : amp <= 100 ? Int32(1) : Int32(0)
+    want == cur && return false
+    @warn "AGPB200: K_mm is ill conditioned (error amplification $amp): moving the model to precision code $want (0 = f64, 1 = f32)"
+    PRECISION_BY_CONDITION[model] = want
+    return true
+end
 
 likelihoods(model::SVGP) = (AGP.likelihood(model),)
 likelihoods(model::MOSVGP) = Tuple(AGP.likelihood(model))
@@ -103,9 +135,9 @@ function engine(model::Union{SVGP{T},MOSVGP{T}}, B::Int) where {T}
     ctx = Ref{Ptr{Cvoid}}(C_NULL); mdl = Ref{Ptr{Cvoid}}(C_NULL)
     rc = ccall((:agp_ctx_create, LIB), Cint, (Cint, Ptr{Cvoid}, Ref{Ptr{Cvoid}}), 0, C_NULL, ctx)
     rc == 0 || error("agp_ctx_create failed (no CUDA device; there is no CPU fallback)")
-    e = Engine(ctx[], C_NULL, 0)
+    e = Engine(ctx[], C_NULL, 0, true)
     GC.@preserve Z kk ks kv lk p0 p1 A begin
-        d = Ref(ModelDesc(model_kind(model), Q, 0, Q, m, D, batch_capacity(m, B), precision_code(m, B), AGP.is_stochastic(inf) ? 1 : 0, κ, τ, Float64(T(AGP.jitt)),
+        d = Ref(ModelDesc(model_kind(model), Q, 0, Q, m, D, batch_capacity(m, B, model), precision_code(m, B, model), AGP.is_stochastic(inf) ? 1 : 0, κ, τ, Float64(T(AGP.jitt)),
                           length(ls), pointer(lk), pointer(p0), pointer(p1), isempty(A) ? C_NULL : pointer(A),
                           pointer(kk), pointer(ks), pointer(kv), pointer(Z), C_NULL))
         check(e, ccall((:agp_model_create, LIB), Cint, (Ptr{Cvoid}, Ref{ModelDesc}, Ref{Ptr{Cvoid}}), e.ctx, d, mdl))
@@ -144,8 +176,13 @@ function device_step!(model, state, x::SubArray, ys::Tuple)
     end
     if AGP.isHPupdated(AGP.inference(model))
         check(e, ccall((:agp_refresh_K, LIB), Cint, (Ptr{Cvoid},), e.model))      # compute_K
+        if e.fresh && conditioning_switch!(model, e, AGP.dim(model.f[1]), AGP.batchsize(AGP.inference(model)))
+            release!(model)                           # rebuild on the slower, more accurate path and start this step again
+            return device_step!(model, state, x, ys)
+        end
         AGP.setHPupdated!(AGP.inference(model), false)
     end
+    e.fresh = false
     ρ = Float64(AGP.ρ(AGP.inference(model)))
     GC.@preserve idx check(e, ccall((:agp_step, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Int32, Int32, Float64),
                                     e.model, idx, B, 1, ρ))
