@@ -1030,8 +1030,9 @@ def train(model: AbstractGPModel, X=None, y=None, iterations: int = 100, *, call
     if inf.HyperParametersUpdated:
         eng.ck(lib.agp_refresh_K(eng.model))  # compute_K, once per train! call (training.jl:41-43, Q3)
         inf.HyperParametersUpdated = False
+        # (full models form V = chol(K) directly - no K_nm L^-T product, nothing to amplify)
         if fresh and model.world == 1 and model.precision_requested == "auto" and model.precision != "f64" \
-                and os.environ.get("AGP_COND_SWITCH", "1") != "0":
+                and not isinstance(model, (VGP, MOVGP)) and os.environ.get("AGP_COND_SWITCH", "1") != "0":
             amp = model.amplification()
             want = next(p for p, lim in AMPLIFICATION_LIMIT if amp <= lim and not (p == "tf32x3" and model.precision == "f32"))
             if want != model.precision:
