@@ -438,6 +438,7 @@ struct Engine : EngineBase {
     mean_f = xchg; var_f = xchg + 2 * par_stride;   // parity 0 halves; parity 1 (peer mode only) follows each at + par_stride
     CKS(dalloc(&d_xepoch, 1));
     CKS(dalloc(&gmu, (size_t)Ql * ldB)); CKS(dalloc(&gS, (size_t)Ql * ldB));
+    CKS(gram_tn_group_init());
     CKS(dalloc(&lc, (size_t)R * ldB)); CKS(dalloc(&ltheta, (size_t)R * ldB)); CKS(dalloc(&lgamma_, (size_t)R * ldB));
     CKS(dalloc(&lalpha, ldB));
     CKS(dalloc(&tmu, (size_t)nT * ldB)); CKS(dalloc(&tvar, (size_t)nT * ldB));
@@ -518,7 +519,7 @@ struct Engine : EngineBase {
       if (L.ns_alloc) umma_ns_free(L.ns);
       umma_knm_free(L.uk);
     }
-    umma_groups_free(grpV); umma_groups_free(grpS); umma_groups_free(grpG);
+    umma_groups_free(grpV); umma_groups_free(grpS); umma_groups_free(grpG); umma_groups_free(grpGT);
     for (int i = 0; i < NAUX; ++i) { if (aux[i]) cudaStreamDestroy(aux[i]); if (ev_aux_join[i]) cudaEventDestroy(ev_aux_join[i]); }
     if (ev_aux_fork) cudaEventDestroy(ev_aux_fork);
     for (void* q : peer_opened) cudaIpcCloseMemHandle(q);
@@ -870,10 +871,11 @@ struct Engine : EngineBase {
 
   // ---- grouped tcgen05 launches: with >= 2 owned latents (tf32x3) each of the three B x m x m products of a step is ONE persistent
   // launch over all owned latents (umma_gemm_grouped_kernel) instead of one launch per latent ----
-  UmmaGroups grpV, grpS, grpG;
+  UmmaGroups grpV, grpS, grpG, grpGT;
   bool use_groups = false;
+  bool grp_gram_tn = false;      // grouped Gram product straight from V (no scale-transpose launches); AGP_GRAM_TN_GROUPED=0 disables
   int groups_init() {
-    use_groups = false;
+    use_groups = false; grp_gram_tn = false;
     if (prec != AGP_PREC_TF32X3 || Ql < 2 || is_vgp || getenv("AGP_NO_GROUPED")) return AGP_OK;
     std::vector<UmmaLatent*> lp; std::vector<float*> cV, cG; std::vector<double*> a0V, a0S, a1S; std::vector<const double*> tv;
     for (auto& L : lat) {
@@ -884,6 +886,23 @@ struct Engine : EngineBase {
     CKS(umma_groups_build(ctx_err(), grpS, lp.data(), Ql, UM_V, UM_X, nullptr, a0S.data(), a1S.data(), tv.data(), st()));
     CKS(umma_groups_build(ctx_err(), grpG, lp.data(), Ql, -1, -1, cG.data(), nullptr, nullptr, nullptr, st()));
     use_groups = true;
+    return AGP_OK;
+  }
+  // needs the gradient buffers (gmu, gS), which the constructor allocates after groups_init
+  int gram_tn_group_init() {
+    grp_gram_tn = false;
+    if (!use_groups) return AGP_OK;
+    bool tn_ok = true;
+    for (auto& L : lat) tn_ok = tn_ok && L.um.gram_tn;
+    if (const char* env = getenv("AGP_GRAM_TN_GROUPED")) tn_ok = tn_ok && atoi(env) != 0;
+    if (!tn_ok) return AGP_OK;
+    std::vector<UmmaLatent*> lp; std::vector<float*> cG; std::vector<const double*> wq, gq; std::vector<double*> v1q;
+    for (int q = 0; q < Ql; ++q) {
+      lp.push_back(&lat[q].um); cG.push_back((float*)(void*)lat[q].Gpart);
+      wq.push_back(gS + (size_t)q * ldB); gq.push_back(gmu + (size_t)q * ldB); v1q.push_back(lat[q].v1);
+    }
+    CKS(umma_gram_tn_groups_build(ctx_err(), grpGT, lp.data(), Ql, cG.data(), wq.data(), gq.data(), v1q.data(), st()));
+    grp_gram_tn = true;
     return AGP_OK;
   }
   int moments_rows_grouped(const T* Xsrc, const T* xsrc, const int64_t* gather, int B, bool fresh_kernel_matrices, double* mean_out,
@@ -1613,6 +1632,18 @@ struct Engine : EngineBase {
         CK(cudaMemsetAsync(gS + (size_t)q * ldB + B, 0, (size_t)(Bk - B) * sizeof(double), st()));
         CK(cudaMemsetAsync(gmu + (size_t)q * ldB + B, 0, (size_t)(Bk - B) * sizeof(double), st()));
       }
+    if (grp && grp_gram_tn) {
+      // one launch: every owned latent's Gram partials and V^T grad_mu straight from V (scaling / transposition in the worker threads)
+      ph_begin(PH_GRAM);
+      int ns = n_split;
+      umma_set_pdl(tail_pdl && !prof);
+      CKS(umma_gram_tn_grouped(ctx_err(), grpGT, lat[0].um, rho, Bk, mk, &ns, st()));
+      umma_set_pdl(false);
+      ++launches;
+      for (auto& L : lat) L.gram_splits = ns;
+      ph_end();
+      return AGP_OK;
+    }
     if (grp) fan_begin();
     for (int q = 0; q < Ql; ++q) {
       Latent& L = lat[q];

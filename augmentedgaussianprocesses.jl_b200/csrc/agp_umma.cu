@@ -1581,9 +1581,23 @@ constexpr int SC_OFF = RS * RAW_BYTES + CS * CONV_BYTES;         // after the op
 constexpr int RING_BYTES = SC_OFF + RS * SC_BYTES;
 constexpr int SMEM_BYTES = RING_BYTES + 1024 + 256;
 }
+// GROUPED: one launch for the Gram products of several latent GPs (multi-latent steps): the tensor map of V, the weights, the gradient
+// vector and the outputs of unit u's latent come from a device array, the units of all latents interleave (get_unit_grouped).
+struct alignas(64) GramTnGroup {
+  CUtensorMap tmV;
+  float* C; const double* w; const double* g; double* v1;
+};
+template <bool GROUPED>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-umma_gram_tn_kernel(const __grid_constant__ CUtensorMap tmV, float* __restrict__ C, int64_t ldc, int64_t c_split_stride, const GemmWork work,
-                    const double* __restrict__ wvec, const double rho, const double* __restrict__ gvec, double* __restrict__ v1) {
+umma_gram_tn_kernel(const __grid_constant__ CUtensorMap tmV1, float* __restrict__ C1, int64_t ldc, int64_t c_split_stride, const GemmWork work,
+                    const double* __restrict__ wvec1, const double rho, const double* __restrict__ gvec1, double* __restrict__ v1_1,
+                    const GramTnGroup* __restrict__ groups, const int ngroups) {
+  const int total_units = GROUPED ? work.total * ngroups : work.total;
+  auto unit_of = [&](int u, int& gq) -> WorkUnit {
+    if (GROUPED) return get_unit_grouped(work, ngroups, u, gq);
+    gq = 0;
+    return get_unit(work, u);
+  };
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -1601,7 +1615,7 @@ umma_gram_tn_kernel(const __grid_constant__ CUtensorMap tmV, float* __restrict__
   const int G = gridDim.x, cta = blockIdx.x;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(GROUPED ? &groups[0].tmV : &tmV1);
     for (int s = 0; s < RS; ++s) { mbar_init(raw_full(s), 1); mbar_init(raw_empty(s), 2 * NUM_CONV_THREADS); }
     for (int s = 0; s < CS; ++s) { mbar_init(conv_full(s), 2 * NUM_CONV_THREADS); mbar_init(mma_done(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(tmem_full(b), 1); mbar_init(tmem_empty(b), 8); }
@@ -1623,9 +1637,12 @@ umma_gram_tn_kernel(const __grid_constant__ CUtensorMap tmV, float* __restrict__
     int g = 0;
     for (int r = 0;; ++r) {
       const int u = unit_index(r, cta, G);
-      if (u >= work.total) break;
-      const WorkUnit wu = get_unit(work, u);
+      if (u >= total_units) break;
+      int gq; const WorkUnit wu = unit_of(u, gq);
       const bool diag = wu.tile_m == wu.tile_n;
+      const CUtensorMap* tmV = GROUPED ? &groups[gq].tmV : &tmV1;
+      const double* __restrict__ wvec = GROUPED ? groups[gq].w : wvec1;
+      const double* __restrict__ gvec = GROUPED ? groups[gq].g : gvec1;
       double wk = wu.nkb > 0 ? wvec[wu.kb0 * BK + lane] : 0.0, gk = wu.nkb > 0 ? gvec[wu.kb0 * BK + lane] : 0.0;
       for (int i = 0; i < wu.nkb; ++i, ++g) {
         const int s = g % RS;
@@ -1640,8 +1657,8 @@ umma_gram_tn_kernel(const __grid_constant__ CUtensorMap tmV, float* __restrict__
           const uint32_t dst = smem_base + s * RAW_BYTES;
           mbar_expect_tx(raw_full(s), diag ? TILE_BYTES : 2 * TILE_BYTES);     // release: the scale words above are visible to the waiters
           const int k = (wu.kb0 + i) * BK;
-          tma_load_2d(dst + 0 * TILE_BYTES, &tmV, raw_full(s), wu.tile_m * BM, k);
-          if (!diag) tma_load_2d(dst + 1 * TILE_BYTES, &tmV, raw_full(s), wu.tile_n * BN, k);
+          tma_load_2d(dst + 0 * TILE_BYTES, tmV, raw_full(s), wu.tile_m * BM, k);
+          if (!diag) tma_load_2d(dst + 1 * TILE_BYTES, tmV, raw_full(s), wu.tile_n * BN, k);
         }
       }
     }
@@ -1650,8 +1667,8 @@ umma_gram_tn_kernel(const __grid_constant__ CUtensorMap tmV, float* __restrict__
     int g = 0, lt = 0;
     for (int r = 0;; ++r, ++lt) {
       const int u = unit_index(r, cta, G);
-      if (u >= work.total) break;
-      const WorkUnit wu = get_unit(work, u);
+      if (u >= total_units) break;
+      int gq; const WorkUnit wu = unit_of(u, gq);
       const int ab = lt & 1;
       mbar_wait(tmem_empty(ab), ((lt >> 1) & 1) ^ 1);
       tc_fence_after();
@@ -1689,9 +1706,11 @@ umma_gram_tn_kernel(const __grid_constant__ CUtensorMap tmV, float* __restrict__
     int g = 0, lt = 0;
     for (int r = 0;; ++r, ++lt) {
       const int u = unit_index(r, cta, G);
-      if (u >= work.total) break;
-      const WorkUnit wu = get_unit(work, u);
+      if (u >= total_units) break;
+      int gq; const WorkUnit wu = unit_of(u, gq);
       const bool diag = wu.tile_m == wu.tile_n;
+      float* __restrict__ C = GROUPED ? groups[gq].C : C1;
+      double* __restrict__ v1 = GROUPED ? groups[gq].v1 : v1_1;
       double vdot = 0.0;
       for (int i = 0; i < wu.nkb; ++i, ++g) {
         const int rs = g % RS, s = g % CS;
@@ -1925,7 +1944,7 @@ int umma_latent_alloc(std::string* err, UmmaLatent& u, int m, int ldm, int Bcap,
   if (!ok) return fail(err, "cuTensorMapEncodeTiled failed");
   if ((e = cudaFuncSetAttribute(umma_gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)) != cudaSuccess)
     return fail(err, "cudaFuncSetAttribute", e);
-  if ((e = cudaFuncSetAttribute(umma_gram_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tn::SMEM_BYTES)) != cudaSuccess)
+  if ((e = cudaFuncSetAttribute(umma_gram_tn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tn::SMEM_BYTES)) != cudaSuccess)
     return fail(err, "cudaFuncSetAttribute (gram tn)", e);
   u.gram_tn = 1;
   if (const char* env = getenv("AGP_GRAM_TN")) u.gram_tn = atoi(env) != 0;
@@ -2135,7 +2154,8 @@ int umma_gram_tn(std::string* err, UmmaLatent& u, float* Gpart, const double* w,
   wk.ntm = nt; wk.ntn = nt; wk.nsplit = S; wk.total = upper_tiles * S;
   wk.total_kb = total_kb; wk.kb_per_split = per; wk.tri_mode = 2;
   const int grid = wk.total < sm_count() ? wk.total : sm_count();
-  launch_chain(umma_gram_tn_kernel, dim3(grid), dim3(NUM_THREADS), tn::SMEM_BYTES, st, mp->vtn, Gpart, (int64_t)u.ldm, (int64_t)m * u.ldm, wk, w, rho, g, v1);
+  launch_chain(umma_gram_tn_kernel<false>, dim3(grid), dim3(NUM_THREADS), tn::SMEM_BYTES, st, mp->vtn, Gpart, (int64_t)u.ldm, (int64_t)m * u.ldm, wk, w, rho, g, v1,
+               (const GramTnGroup*)nullptr, 1);
   *n_split = S;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(err, "umma gram tn", e);
@@ -2264,6 +2284,61 @@ int umma_gram_grouped(std::string* err, const UmmaGroups& gs, const UmmaLatent& 
   *n_split = S;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(err, "umma gram (grouped)", e);
+  return 0;
+}
+
+// Grouped Gram product straight from V (umma_gram_tn_kernel<true>): no scale-transpose pass per latent
+int umma_gram_tn_groups_build(std::string* err, UmmaGroups& gs, UmmaLatent* const* lats, int n, float* const* Gpart, const double* const* w,
+                              const double* const* g, double* const* v1, cudaStream_t st) {
+  std::vector<GramTnGroup> h((size_t)n);
+  for (int q = 0; q < n; ++q) {
+    Maps* mp = (Maps*)lats[q]->tmaps;
+    if (!mp || !lats[q]->gram_tn) return fail(err, "grouped Gram from V: not available for this latent");
+    h[q].tmV = mp->vtn; h[q].C = Gpart[q]; h[q].w = w[q]; h[q].g = g[q]; h[q].v1 = v1[q];
+  }
+  cudaError_t e;
+  if (!gs.dev || gs.n != n) {
+    if (gs.dev) cudaFree(gs.dev);
+    gs.dev = nullptr;
+    if ((e = cudaMalloc(&gs.dev, (size_t)n * sizeof(GramTnGroup))) != cudaSuccess) return fail(err, "cudaMalloc", e);
+  }
+  gs.n = n;
+  if ((e = cudaMemcpyAsync(gs.dev, h.data(), (size_t)n * sizeof(GramTnGroup), cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail(err, "cudaMemcpy", e);
+  if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail(err, "cudaStreamSynchronize", e);
+  if ((e = cudaFuncSetAttribute(umma_gram_tn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tn::SMEM_BYTES)) != cudaSuccess)
+    return fail(err, "cudaFuncSetAttribute (grouped gram tn)", e);
+  return 0;
+}
+
+int umma_gram_tn_grouped(std::string* err, const UmmaGroups& gs, const UmmaLatent& u, double rho, int B, int m, int* n_split, cudaStream_t st) {
+  if (!gs.dev || gs.n < 1) return fail(err, "grouped launch without groups");
+  if (B % BM || m % BN) return fail(err, "shape not a multiple of the tile");
+  const int total_kb = B / BK;
+  const int nt = m / BN, upper_tiles = nt * (nt + 1) / 2;
+  // split-K as in umma_gram_grouped: wave-quantised k-blocks per CTA, plus the unit's drain (the worker groups of this kernel convert AND
+  // drain, so an epilogue is not hidden behind the next unit: ~4 k-blocks' worth) and the partial that combine_kernel re-reads
+  const int sms = sm_count();
+  int bestS = 1; long best = -1;
+  for (int S = 1; S <= *n_split && S <= total_kb; ++S) {
+    const int per = (total_kb + S - 1) / S;
+    const int Su = (total_kb + per - 1) / per;
+    const long units = (long)upper_tiles * gs.n * Su;
+    const long cost = ((units + sms - 1) / sms) * (long)(per + 4) + 2L * Su;
+    if (best < 0 || cost < best) { best = cost; bestS = Su; }
+  }
+  const int per = (total_kb + bestS - 1) / bestS;
+  const int S = (total_kb + per - 1) / per;
+  GemmWork w{};
+  w.ntm = nt; w.ntn = nt; w.nsplit = S; w.total = upper_tiles * S;
+  w.total_kb = total_kb; w.kb_per_split = per; w.tri_mode = 2;
+  const int all = w.total * gs.n;
+  const int grid = all < sms ? all : sms;
+  static const CUtensorMap none{};
+  launch_chain(umma_gram_tn_kernel<true>, dim3(grid), dim3(NUM_THREADS), tn::SMEM_BYTES, st, none, (float*)nullptr, (int64_t)u.ldm, (int64_t)m * u.ldm, w,
+               (const double*)nullptr, rho, (const double*)nullptr, (double*)nullptr, (const GramTnGroup*)gs.dev, gs.n);
+  *n_split = S;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(err, "umma gram tn (grouped)", e);
   return 0;
 }
 

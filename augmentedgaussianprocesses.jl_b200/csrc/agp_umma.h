@@ -101,6 +101,12 @@ int umma_gemm_nt_grouped(std::string* err, const UmmaGroups& gs, const UmmaLaten
 // Gpart_q[s] = split-K partials of U_q^T U_q for every group; *n_split in: capacity of the partial buffers, out: slices used
 int umma_gram_grouped(std::string* err, const UmmaGroups& gs, const UmmaLatent& shape, int B, int m, int* n_split, cudaStream_t st);
 
+// the same partials straight from every group's V (umma_gram_tn_kernel<true>; no scale-transpose pass, v1_q += V_q^T g_q inside): a
+// separate device array (entries: V's tensor map, Gpart, the sample weights w_q, g_q, v1_q); rho multiplies every weight
+int umma_gram_tn_groups_build(std::string* err, UmmaGroups& gs, UmmaLatent* const* lats, int n, float* const* Gpart, const double* const* w,
+                              const double* const* g, double* const* v1, cudaStream_t st);
+int umma_gram_tn_grouped(std::string* err, const UmmaGroups& gs, const UmmaLatent& shape, double rho, int B, int m, int* n_split, cudaStream_t st);
+
 // ---- EXPERIMENTAL, not on the product path (never run on a GPU yet): Newton-Schulz refinement of an m x m inverse ----
 // Y <- Y + Y (I - P Y) as two 3xTF32 tensor-core products per iteration (T = I - Y P, then Y' = Y + Y T^T), the candidate
 // replacement of the fp64 Cholesky tail once the Robbins-Monro step is small (profiles/r1/studies/newton_schulz_*.txt:
