@@ -458,6 +458,15 @@ def run_ours(args, rank, world, local_rank, cfg_name):
         parity = None
         if not args.no_cpu_baseline and cfg_name == "C2" and world == 1:
             cpu, parity = cpu_replay(cfg_name, X, y, Z, A, mbs, W, K, elbo, post_timed)
+        # the driver's N = 1 point is C2 (the metric's single-latent configuration, which does not shard); a multi-latent line carries the
+        # one-GPU figure of ITS workload (measured with `--gpus 1 --config C5|C4`, committed) so that strong-scaling efficiency can be read
+        # as value / (N x same_workload_one_gpu.value)
+        one_gpu = None
+        if Q > 1:
+            try:
+                one_gpu = json.load(open(os.path.join(ROOT, "profiles", "r2", "one_gpu_points.json"))).get(cfg_name)
+            except Exception:
+                one_gpu = None
         line = dict(metric=METRIC, value=value, unit="iters/s", n_gpus=world, steps=K, warmup=W, ms_per_step=ms / K,
                     higher_is_better=True, scaling="weak" if Q == 1 else "strong", vs_baseline=None,
                     dtype={"f32": "f32 (fp32 SIMT contractions, f64 m x m tail)", "tf32x3": "tf32x3 (tcgen05, f64 m x m tail)", "f64": "f64"}[args.precision],
@@ -467,6 +476,8 @@ def run_ours(args, rank, world, local_rank, cfg_name):
                              exchange=("none (single rank)" if world == 1 else "per-sample moments over NVLink peer memory inside the step" if peer else "NCCL all-gather of the per-sample moments"),
                              env={k: os.environ[k] for k in sorted(os.environ) if k.startswith("AGP_")}),
                     gpu_launches=int(launches), elbo_last=elbo, elbo_parity=parity, roofline=roof, cpu_baseline=cpu, e2e=e2e, clocks=clocks, phases=phases)
+        if one_gpu is not None:
+            line["same_workload_one_gpu"] = one_gpu
         print(json.dumps(line), flush=True)
         if parity is not None and not parity["ok"]:
             sys.stderr.write("ELBO / posterior parity against the CPU oracle FAILED: %r\n" % (parity,))
