@@ -145,6 +145,36 @@ __global__ void rowfinish_kernel(const double* __restrict__ sumsq_v, const doubl
   var_f[b] = sumsq_vs[b] + kt;
 }
 
+// ---- batched forms of the small per-latent kernels of multi-latent steps: up to SMALL_NB latents per launch, the latent of a block
+// from blockIdx.y / .z, its pointers from arrays passed BY VALUE in the launch (no device-side table to keep in sync).  At C5 (64 latents
+// on one GPU) 64 launches of 4-11 us each, fanned over four streams, become four. ----
+constexpr int SMALL_NB = 16;
+struct RowFinishBatch { const double* racc[SMALL_NB]; double* Ktilde[SMALL_NB]; double kdiag[SMALL_NB]; };
+// rowfinish_kernel for the latents of a batch: racc[z] = {sum V^2 | sum (VX^T)^2 | sum (VX^T) t}, each ldB long; mean_f / var_f point at
+// the first latent of the batch, rows out_ld apart
+__global__ void rowfinish_batched_kernel(const RowFinishBatch bt, int64_t ldB, int B, double* __restrict__ mean_f, double* __restrict__ var_f,
+                                         int64_t out_ld, int* __restrict__ status, int compute_ktilde, const int64_t* __restrict__ xepoch,
+                                         int64_t par_stride) {
+  pdl_prologue();
+  const int z = blockIdx.y;
+  if (xepoch) { const int64_t off = ((*xepoch + 1) & 1) * par_stride; mean_f += off; var_f += off; }   // next exchange's buffer
+  mean_f += (int64_t)z * out_ld; var_f += (int64_t)z * out_ld;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double* __restrict__ racc = bt.racc[z];
+  double* __restrict__ Kt = bt.Ktilde[z];
+  double kt;
+  if (compute_ktilde) {
+    kt = bt.kdiag[z] - racc[b];
+    Kt[b] = kt;
+    if (!(kt > 0.0)) atomicOr(status, ST_KTILDE);  // latentgp.jl:213
+  } else {
+    kt = Kt[b];
+  }
+  mean_f[b] = racc[2 * ldB + b];
+  var_f[b] = racc[ldB + b] + kt;
+}
+
 // out[j] += sum_b V[b][j] * g[b]   (transpose(kappa) * grad_mu of analyticVI.jl:168, whitened; rho applied later)
 // block = 32 columns x 8 row lanes; grid = (ceil(m/32), row_chunks); one atomicAdd per column per block
 template <typename T>
@@ -594,8 +624,7 @@ struct TailParams {
 // precision K^-1 becomes I and K \ mu0 becomes L^-1 mu0), and P_v = -2 eta2_v whose inverse is Sigma_v
 // (inference.jl:26).  G is symmetrised from its upper triangle like Julia's Symmetric() (analyticVI.jl:238, Q5).
 template <typename TG>
-__global__ void combine_kernel(const TailParams p, const TG* __restrict__ Gpart) {
-  pdl_prologue();
+__device__ __forceinline__ void combine_body(const TailParams& p, const TG* __restrict__ Gpart) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   int i = blockIdx.y;
   if (j >= p.mp) return;
@@ -629,6 +658,23 @@ __global__ void combine_kernel(const TailParams p, const TG* __restrict__ Gpart)
     if (p.v1_zero) p.v1_zero[j] = 0.0;
     if (j == 0) *p.logdet = 0.0;
   }
+}
+template <typename TG>
+__global__ void combine_kernel(const TailParams p, const TG* __restrict__ Gpart) {
+  pdl_prologue();
+  combine_body<TG>(p, Gpart);
+}
+// the same update for the latents of a batch (blockIdx.z): `common` holds everything the latents share, the per-latent pointers follow
+struct CombineBatch {
+  const double* v1[SMALL_NB]; const double* mu0v[SMALL_NB]; double* eta1[SMALL_NB]; double* eta2[SMALL_NB]; double* P[SMALL_NB];
+  double* v1_zero[SMALL_NB]; double* logdet[SMALL_NB]; const float* G[SMALL_NB];
+};
+__global__ void combine_batched_kernel(const TailParams common, const CombineBatch bt) {
+  pdl_prologue();
+  const int z = blockIdx.z;
+  TailParams p = common;
+  p.v1 = bt.v1[z]; p.mu0v = bt.mu0v[z]; p.eta1 = bt.eta1[z]; p.eta2 = bt.eta2[z]; p.P = bt.P[z]; p.v1_zero = bt.v1_zero[z]; p.logdet = bt.logdet[z];
+  combine_body<float>(p, bt.G[z]);
 }
 
 // The same update, four consecutive columns per thread (16-byte loads of the fp32 split-K partials, all slices in flight at once): the

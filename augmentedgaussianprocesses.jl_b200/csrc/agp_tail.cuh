@@ -293,18 +293,9 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) tail_step_kernel(const TailSt
 // contraction, optional TF32 hi/lo split of that shadow, and t_i = (X eta1_v)_i  (mu_v = X^T t is never needed in
 // the hot loop: mean_f = V mu_v = (V X^T) t).
 template <typename T>
-__global__ void x_finalize_kernel(const double* __restrict__ X, int64_t ld, int m, const double* __restrict__ eta1v,
-                                  T* __restrict__ shadow, int64_t lds, float* __restrict__ hi, float* __restrict__ lo,
-                                  double* __restrict__ tvec, double* __restrict__ lr_next, int64_t* __restrict__ counters,
-                                  double rm_kappa, double rm_tau, int bump, int row0 = 0) {
-  pdl_prologue();
-  const int i = blockIdx.x + row0;    // launches may cover a block of rows (rows leave the tail block by block)
-  // Robbins-Monro step size of the NEXT iteration (inference/optimisers.jl:14-19; the counter is bumped after this kernel):
-  // one thread of one block, hidden behind the rest of the grid instead of sitting on the next step's chain
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    if (lr_next) *lr_next = pow(rm_tau + (double)(counters[0] + 1), -rm_kappa);
-    if (bump) { counters[0] += 1; counters[1] += 1; }   // end of the step: Robbins-Monro counter and minibatch-list cursor
-  }
+__device__ __forceinline__ void x_finalize_row(const int i, const double* __restrict__ X, int64_t ld, int m, const double* __restrict__ eta1v,
+                                               T* __restrict__ shadow, int64_t lds, float* __restrict__ hi, float* __restrict__ lo,
+                                               double* __restrict__ tvec) {
   double s = 0.0;
   for (int j = threadIdx.x; j < m; j += blockDim.x) {
     double v = (j <= i) ? X[(int64_t)i * ld + j] : 0.0;
@@ -331,6 +322,37 @@ __global__ void x_finalize_kernel(const double* __restrict__ X, int64_t ld, int 
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) a += sh[w];
     tvec[i] = a;
   }
+}
+template <typename T>
+__global__ void x_finalize_kernel(const double* __restrict__ X, int64_t ld, int m, const double* __restrict__ eta1v,
+                                  T* __restrict__ shadow, int64_t lds, float* __restrict__ hi, float* __restrict__ lo,
+                                  double* __restrict__ tvec, double* __restrict__ lr_next, int64_t* __restrict__ counters,
+                                  double rm_kappa, double rm_tau, int bump, int row0 = 0) {
+  pdl_prologue();
+  const int i = blockIdx.x + row0;    // launches may cover a block of rows (rows leave the tail block by block)
+  // Robbins-Monro step size of the NEXT iteration (inference/optimisers.jl:14-19; the counter is bumped after this kernel):
+  // one thread of one block, hidden behind the rest of the grid instead of sitting on the next step's chain
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (lr_next) *lr_next = pow(rm_tau + (double)(counters[0] + 1), -rm_kappa);
+    if (bump) { counters[0] += 1; counters[1] += 1; }   // end of the step: Robbins-Monro counter and minibatch-list cursor
+  }
+  x_finalize_row<T>(i, X, ld, m, eta1v, shadow, lds, hi, lo, tvec);
+}
+// the latents of a batch in one launch (blockIdx.y = latent; pointers by value, see SMALL_NB in agp_kernels.cuh); lr_next / bump are
+// passed by the launch that holds the step's LAST latent only
+constexpr int FINALIZE_NB = 16;
+template <typename T>
+struct FinalizeBatch { const double* X[FINALIZE_NB]; const double* eta1v[FINALIZE_NB]; T* shadow[FINALIZE_NB]; float* hi[FINALIZE_NB]; float* lo[FINALIZE_NB]; double* tvec[FINALIZE_NB]; };
+template <typename T>
+__global__ void x_finalize_batched_kernel(const FinalizeBatch<T> bt, int64_t ld, int m, int64_t lds, double* __restrict__ lr_next,
+                                          int64_t* __restrict__ counters, double rm_kappa, double rm_tau, int bump) {
+  pdl_prologue();
+  const int z = blockIdx.y;
+  if (blockIdx.x == 0 && z == 0 && threadIdx.x == 0) {
+    if (lr_next) *lr_next = pow(rm_tau + (double)(counters[0] + 1), -rm_kappa);
+    if (bump) { counters[0] += 1; counters[1] += 1; }
+  }
+  x_finalize_row<T>(blockIdx.x, bt.X[z], ld, m, bt.eta1v[z], bt.shadow[z], lds, bt.hi[z], bt.lo[z], bt.tvec[z]);
 }
 
 // End of a step whose tail was the experimental Newton-Schulz refinement (no factor X, so no x_finalize_kernel): the step-size /
