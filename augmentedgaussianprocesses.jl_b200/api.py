@@ -950,6 +950,16 @@ class State:
 AMPLIFICATION_LIMIT = (("tf32x3", 30.0), ("f32", 100.0), ("f64", float("inf")))
 
 
+def precision_for_amplification(amp: float, current: str) -> str:
+    """The path precision="auto" keeps for an error amplification `amp`: the first entry of AMPLIFICATION_LIMIT that admits it, never a
+    faster path than the one the shapes selected (`current`: a model below 128 inducing points stays off the tensor cores)."""
+    order = [p for p, _ in AMPLIFICATION_LIMIT]
+    for p, lim in AMPLIFICATION_LIMIT:
+        if amp <= lim and order.index(p) >= order.index(current):
+            return p
+    return order[-1]
+
+
 def _wrap_y(model, y):
     if isinstance(model, (MOSVGP, MOVGP)):
         if len(y) != model.n_task:
@@ -1034,7 +1044,7 @@ def train(model: AbstractGPModel, X=None, y=None, iterations: int = 100, *, call
         if fresh and model.world == 1 and model.precision_requested == "auto" and model.precision != "f64" \
                 and not isinstance(model, (VGP, MOVGP)) and os.environ.get("AGP_COND_SWITCH", "1") != "0":
             amp = model.amplification()
-            want = next(p for p, lim in AMPLIFICATION_LIMIT if amp <= lim and not (p == "tf32x3" and model.precision == "f32"))
+            want = precision_for_amplification(amp, model.precision)
             if want != model.precision:
                 # precision="auto" promises the reference's (fp64) results to the tolerances of the parity tests: the fp32-class paths lose
                 # ~log10(amp) digits in V = K_nm L^-T, the tensor-core accumulation more than the CUDA-core one

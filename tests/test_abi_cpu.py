@@ -91,3 +91,17 @@ def test_constructor_and_argument_errors(agp):
         agp.VGP(np.random.randn(6, 2), np.ones(6), k, agp.GaussianLikelihood(), agp.AnalyticSVI(3))
     with pytest.raises(ValueError):   # sample-count check (data/utils.jl)
         agp.VGP(np.random.randn(6, 2), np.ones(5), k, agp.GaussianLikelihood(), agp.AnalyticVI())
+
+
+def test_precision_policy_tiers(agp):
+    """precision="auto": the path kept for an error amplification sqrt(variance ||K_mm^-1||_inf) (api.AMPLIFICATION_LIMIT):
+    tensor cores up to 30, fp32 CUDA cores up to 100, fp64 above; never a faster path than the shapes selected."""
+    from agp_b200.api import AMPLIFICATION_LIMIT, precision_for_amplification as pick
+    assert [p for p, _ in AMPLIFICATION_LIMIT] == ["tf32x3", "f32", "f64"]
+    lims = dict(AMPLIFICATION_LIMIT)
+    assert lims["tf32x3"] < lims["f32"] < lims["f64"] == float("inf")
+    assert pick(1.0, "tf32x3") == "tf32x3" and pick(lims["tf32x3"], "tf32x3") == "tf32x3"
+    assert pick(lims["tf32x3"] * 1.01, "tf32x3") == "f32" and pick(lims["f32"], "tf32x3") == "f32"
+    assert pick(lims["f32"] * 1.01, "tf32x3") == "f64" and pick(1e9, "f32") == "f64"
+    assert pick(1.0, "f32") == "f32"          # a small model (m < 128) is not moved onto the tensor cores
+    assert pick(1.0, "f64") == "f64" and pick(50.0, "f64") == "f64"
