@@ -446,6 +446,9 @@ struct Engine : EngineBase {
     CKS(dalloc(&ycls, ldB));
     CKS(dalloc(&d_out, 8));
     CKS(dalloc(&d_lr, 1));
+    CKS(dalloc(&d_tile0_flag, 1));
+    CK(cudaMemsetAsync(d_tile0_flag, 0, sizeof(int), st()));
+    { const char* e = getenv("AGP_EARLY_POTF2"); if (e && e[0] == '0') early_potf2 = false; }
     CK(cudaStreamSynchronize(st()));
     CKS(upload_lr(1));
     CKS(dalloc(&d_lam, nT)); CKS(dalloc(&d_lamacc, 2 * (size_t)nT)); CKS(dalloc(&d_qnodes, 128)); CKS(dalloc(&d_qw, 128));
@@ -549,7 +552,7 @@ struct Engine : EngineBase {
     if (ev_join) cudaEventDestroy(ev_join);
     void* ps[] = {idx_prev, xx_cur, pKS, pXb, pxxb, X, xx, y_all, ycls_all, Xb, xxb, stage, idx_pool, idx_cur, counters, status, d_lik_kind, d_p0, d_p1, d_A,
                   xchg, d_xepoch, d_peers, gmu, gS, lc, ltheta, lgamma_, lalpha, tmu, tvar, gm, gs, yb, ycls, d_out, d_lam, d_lamacc, d_qnodes, d_qw, d_lr, d_gradA, d_Amt, d_Avt, d_Abt, d_noise_opt, d_noise_state,
-                  hgH[0], hgH[1], hgH[2], hgH[3], hgX, hgA, hgB, hgM1, hgM2, hgV, hgP, d_t3lat, d_t3flags, d_rowcnt};
+                  hgH[0], hgH[1], hgH[2], hgH[3], hgX, hgA, hgB, hgM1, hgM2, hgV, hgP, d_t3lat, d_t3flags, d_rowcnt, d_tile0_flag};
     for (void* p : ps) cudaFree(p);
   }
 
@@ -1751,6 +1754,9 @@ struct Engine : EngineBase {
     return AGP_OK;
   }
   // combine_kernel: split-K reduction of the Gram partials + natural-parameter update; blk: 0 = whole matrix, 1 / 2 = split Gram parts
+  // the tail's first kernel starts on tile (0, 0) while combine_kernel is still running (AGP_EARLY_POTF2=0 disables)
+  int* d_tile0_flag = nullptr;
+  bool early_potf2 = true, tile0_signal_now = false;
   TailParams combine_params(Latent& L, double rho, int ns, int blk) {
     TailParams tp{};
     tp.m = m; tp.mp = mp; tp.ld = mp; tp.n_split = ns; tp.gpart_stride = (int64_t)mk * ldm; tp.gpart_ld = ldm;
@@ -1764,7 +1770,10 @@ struct Engine : EngineBase {
     return tp;
   }
   void launch_combine(Latent& L, double rho, int ns, int blk) {
-    const TailParams tp = combine_params(L, rho, ns, blk);
+    TailParams tp = combine_params(L, rho, ns, blk);
+    const bool c4 = blk == 0 && combine4_on && prec == AGP_PREC_TF32X3 && mp == m && m % 4 == 0 && ldm % 4 == 0 && tp.gpart_stride % 4 == 0;
+    tile0_signal_now = tile0_signal_now && blk == 0 && !c4 && d_tile0_flag != nullptr;
+    if (tile0_signal_now) tp.tile0_flag = d_tile0_flag;
     // whole matrix on the tf32x3 path: four columns per thread (combine4_kernel); the summation order of the slices is the scalar kernel's
     if (blk == 0 && combine4_on && prec == AGP_PREC_TF32X3 && mp == m && m % 4 == 0 && ldm % 4 == 0 && tp.gpart_stride % 4 == 0)
       launch_chain(combine4_kernel, dim3((m / 4 + 127) / 128, m), dim3(128), 0, tp, (const float*)(const void*)L.Gpart);
@@ -1832,8 +1841,10 @@ struct Engine : EngineBase {
       const int ns = L.gram_splits;
       if (fan3) fan_select(q);
       ph_begin(PH_COMBINE);
+      tile0_signal_now = early_potf2 && tail_variant == 2 && !ns_tail_now && !split_gram_now && !prof;
       launch_combine(L, rho, ns, split_gram_now ? 1 : 0);
       ph_end();
+      if (ns_tail_now || tail_variant == 3) tile0_signal_now = false;
       if (ns_tail_now) CKS(eta_to_moments_ns(L));
       else if (tail_variant != 3) {
         CKS(eta_to_moments(L, q == Ql - 1));   // the last latent's finalize kernel also prepares the next step size
@@ -1925,6 +1936,8 @@ struct Engine : EngineBase {
     ph_begin(PH_CHOL);
     TailStepParams tp{};
     tp.P = L.P; tp.W = L.W; tp.Xout = L.Xv; tp.Dinv = L.Dinv; tp.ld = mp; tp.nblk = nblk_tail(); tp.logdet = L.logdetP; tp.status = status;
+    tp.early_flag = (tile0_signal_now && tail_variant == 2) ? d_tile0_flag : nullptr;   // the combine launch just before this one signals
+    tile0_signal_now = false;
     if (tail_variant == 0) tail_potf2_first_kernel<0><<<1, TAIL_THREADS, TAIL_SMEM, st()>>>(tp);
     else if (chain_variant == 0) launch_tail2(tail2_potf2_first_kernel<0, 0>, 1, tp);
     else launch_tail2(tail2_potf2_first_kernel<0, 1>, 1, tp);

@@ -617,6 +617,10 @@ struct TailParams {
   const double* eta1_off; const double* eta2_off;
   // split Gram (agp_engine.cu): 0 = every element, 1 = only the first 128 x 128 block (grid (1, 128)), 2 = everything else
   int blk_mode;
+  // non-null (whole-matrix launches in front of the multi-launch tail): the 64 blocks that hold rows 0..63 of column block 0 count
+  // themselves here once their part of P_v is written, so that the tail's first kernel can start on tile (0, 0) while the rest of
+  // this grid is still running (tail2_potf2_first_kernel, TailStepParams::early_flag)
+  int* tile0_flag;
 };
 
 // natural gradient + global update of the natural parameters (inference/analyticVI.jl:160-180, 229-246;
@@ -663,6 +667,11 @@ template <typename TG>
 __global__ void combine_kernel(const TailParams p, const TG* __restrict__ Gpart) {
   pdl_prologue();
   combine_body<TG>(p, Gpart);
+  if (p.tile0_flag && blockIdx.x == 0 && blockIdx.y < 64) {     // block-uniform
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(p.tile0_flag, 1);
+  }
 }
 // the same update for the latents of a batch (blockIdx.z): `common` holds everything the latents share, the per-latent pointers follow
 struct CombineBatch {

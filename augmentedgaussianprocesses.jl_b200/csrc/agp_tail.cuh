@@ -37,6 +37,9 @@ struct TailStepParams {
   int64_t ld;
   int nblk, k;
   double* logdet; int* status;
+  // tail2_potf2_first_kernel only: non-null = the in-stream predecessor is combine_kernel with TailParams::tile0_flag set; the kernel
+  // starts as soon as that counter says tile (0, 0) of P_v is written instead of waiting for the whole grid
+  int* early_flag;
 };
 
 // ---- shared-memory tile helpers (256 threads) -------------------------------------------------------

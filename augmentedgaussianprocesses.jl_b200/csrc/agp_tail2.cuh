@@ -431,10 +431,29 @@ template <int ABL = 0, int CHAIN = 1>
 __global__ void __launch_bounds__(TAIL_THREADS, 1) tail2_potf2_first_kernel(const TailStepParams p) {
   extern __shared__ double sm[];
   pdl_launch_dependents();   // let the next block step get resident while this one runs; it waits in pdl_wait()
-  pdl_wait();
+  if (p.early_flag) {
+    // Start on tile (0, 0) while the natural-parameter update is still writing the other tiles of P_v: its 64 blocks of rows 0..63 /
+    // column block 0 release-count themselves in early_flag (combine_kernel).  The spin is bounded (~0.5 ms): on a timeout the full
+    // programmatic dependency below makes the tile valid anyway, so the counter only ever shortens the wait.
+    if (threadIdx.x == 0) {
+      const long long t0 = clock64();
+      int v;
+      do {
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p.early_flag) : "memory");
+      } while (v < 64 && clock64() - t0 < 1000000LL);
+      if (v < 64) pdl_wait();
+      *p.early_flag = 0;     // every producer of this step has arrived (or finished): ready for the next step
+    }
+    __syncthreads();
+  } else {
+    pdl_wait();
+  }
   tile2_load(sm, p.P, p.ld);
   __syncthreads();
   tile2_potf2_inv<ABL, CHAIN>(sm, sm + T2_TILE, sm + 5 * T2_TILE, sm + 5 * T2_TILE + TNB * T2SL, p.Xout, p.ld, p.Dinv, p.logdet, p.status);
+  // the block steps that follow read every tile of P_v: this grid must not complete before the producer grid has (their programmatic
+  // dependency is on THIS kernel only)
+  if (p.early_flag) pdl_wait();
 }
 
 template <int CHAIN = 1>
